@@ -1,0 +1,245 @@
+"""TEST INFRASTRUCTURE ONLY -- generates the committed fixtures under ``tests/golden/``.
+
+Run in the build container (needs ``/root/reference``):  ``python -m oracle.make_golden``
+
+Fixtures produced
+-----------------
+``tests/golden/v3_jit_linear.npz``
+    The reference's strongest pin on this path (reference ``tests/test_interpolation.py:297-378``,
+    ``test_interp_regression_v3``): inputs decoded from
+    ``tests/test_data/test_interpolation_data_random_linear.nc`` and the Parcels-v3 JIT golden
+    trajectories decoded from ``tests/test_data/test_interpolation_jit_linear.zarr``.
+    (``.nc`` = NetCDF-4/HDF5 with contiguous little-endian f64 datasets; ``.zarr`` = zarr-v2 with
+    blosc-1/lz4/byte-shuffle chunks -- both decoded here without h5py/zarr)
+``tests/golden/v3_jit_cgrid.npz``
+    Same for ``..._cgrid_velocity`` (CGrid_Velocity on a rectilinear C-grid).
+``tests/golden/ref_cases.npz``
+    Outputs of the reference's OWN code (run through ``oracle/ref_harness.py``) on seeded
+    synthetic inputs covering dtype / mesh / 2-D-3-D / static-time-varying / out-of-bounds /
+    delayed-release / backward-in-time / partial-last-step cases.  Inputs are regenerated from
+    the seeds by ``tests/cases.py``; only the reference's outputs are stored.
+"""
+
+from __future__ import annotations
+
+import json
+import os
+import struct
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+REF_TESTDATA = "/root/reference/tests/test_data"
+
+
+# ----------------------------------------------------------------------------------------------
+# minimal HDF5 (superblock v2/3, v2 object headers, contiguous layout) dataset locator
+# ----------------------------------------------------------------------------------------------
+def _h5_datasets(buf: bytes) -> dict[str, tuple[int, tuple[int, ...]]]:
+    """Return {name: (byte offset, shape)} for contiguous datasets linked from the root group."""
+    assert buf[:8] == b"\x89HDF\r\n\x1a\n"
+    ver = buf[8]
+    assert ver in (2, 3), ver
+    off_sz, len_sz = buf[9], buf[10]
+    assert off_sz == 8 and len_sz == 8
+    root = struct.unpack_from("<Q", buf, 12 + 8 * 3)[0]
+
+    def messages(addr):
+        assert buf[addr : addr + 4] == b"OHDR", buf[addr : addr + 4]
+        flags = buf[addr + 5]
+        p = addr + 6
+        if flags & 0x20:
+            p += 16
+        if flags & 0x10:
+            p += 4
+        szf = 1 << (flags & 3)
+        chunk0 = int.from_bytes(buf[p : p + szf], "little")
+        p += szf
+        track = bool(flags & 0x04)
+        blocks = [(p, p + chunk0)]
+        out = []
+        while blocks:
+            s, e = blocks.pop(0)
+            q = s
+            while q + 4 <= e - 0:  # (gap/checksum at the end is shorter than a message header)
+                mtype = buf[q]
+                msize = struct.unpack_from("<H", buf, q + 1)[0]
+                q += 4 + (2 if track else 0)
+                if q + msize > e:
+                    break
+                body = buf[q : q + msize]
+                if mtype == 0x10:  # continuation
+                    caddr, clen = struct.unpack_from("<QQ", body, 0)
+                    assert buf[caddr : caddr + 4] == b"OCHK"
+                    blocks.append((caddr + 4, caddr + clen - 4))
+                else:
+                    out.append((mtype, body))
+                q += msize
+        return out
+
+    found = {}
+    for mtype, body in messages(root):
+        if mtype != 6:  # link message
+            continue
+        ver_l, fl = body[0], body[1]
+        p = 2
+        ltype = 0
+        if fl & 0x08:
+            ltype = body[p]
+            p += 1
+        if fl & 0x04:
+            p += 8
+        if fl & 0x10:
+            p += 1
+        lsz = 1 << (fl & 3)
+        nlen = int.from_bytes(body[p : p + lsz], "little")
+        p += lsz
+        name = body[p : p + nlen].decode()
+        p += nlen
+        if ltype != 0:
+            continue
+        oaddr = struct.unpack_from("<Q", body, p)[0]
+        shape, daddr = None, None
+        for mt, b in messages(oaddr):
+            if mt == 1:  # dataspace
+                v, rank, f = b[0], b[1], b[2]
+                q = 4 if v == 2 else 8
+                shape = tuple(struct.unpack_from("<Q", b, q + 8 * i)[0] for i in range(rank))
+            elif mt == 8 and b[0] == 3 and b[1] == 1:  # layout v3, contiguous
+                daddr = struct.unpack_from("<Q", b, 2)[0]
+        if shape is not None and daddr is not None:
+            found[name] = (daddr, shape)
+    return found
+
+
+def read_nc_f64(path: str, names: list[str]) -> dict[str, np.ndarray]:
+    buf = open(path, "rb").read()
+    ds = _h5_datasets(buf)
+    out = {}
+    for n in names:
+        off, shape = ds[n]
+        cnt = int(np.prod(shape))
+        out[n] = np.frombuffer(buf, dtype="<f8", count=cnt, offset=off).reshape(shape).copy()
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+# blosc-1 (lz4, byte shuffle) chunk decoder for zarr-v2
+# ----------------------------------------------------------------------------------------------
+def _lz4_raw(src: bytes, n_out: int) -> bytes:
+    import pyarrow as pa
+
+    return pa.Codec("lz4_raw").decompress(src, decompressed_size=n_out).to_pybytes()
+
+
+def blosc_decode(raw: bytes) -> bytes:
+    _ver, _verlz, flags, typesize, nbytes, blocksize, _cbytes = struct.unpack_from("<BBBBIII", raw, 0)
+    if flags & 0x02:  # memcpyed
+        return raw[16 : 16 + nbytes]
+    shuffled = bool(flags & 0x01)
+    dont_split = bool(flags & 0x10)
+    nblocks = (nbytes + blocksize - 1) // blocksize
+    bstarts = struct.unpack_from(f"<{nblocks}I", raw, 16)
+    out = bytearray()
+    for b in range(nblocks):
+        bsize = min(blocksize, nbytes - b * blocksize)
+        leftover = bsize != blocksize
+        nsplit = typesize if (not dont_split and typesize <= 16 and bsize // typesize >= 128 and not leftover) else 1
+        # blosc-1 splits a full block into `typesize` streams when it is large enough
+        if not dont_split and typesize <= 16 and bsize >= typesize * 128 and not leftover:
+            nsplit = typesize
+        p = bstarts[b]
+        seg = bsize // nsplit
+        blk = bytearray()
+        for _ in range(nsplit):
+            csize = struct.unpack_from("<i", raw, p)[0]
+            p += 4
+            blk += raw[p : p + csize] if csize == seg else _lz4_raw(raw[p : p + csize], seg)
+            p += csize
+        if shuffled and typesize > 1:
+            n = bsize // typesize
+            a = np.frombuffer(bytes(blk[: n * typesize]), dtype=np.uint8).reshape(typesize, n).T.copy()
+            blk = bytearray(a.tobytes()) + blk[n * typesize :]
+        out += blk
+    return bytes(out)
+
+
+def read_zarr_v2(path: str, var: str) -> np.ndarray:
+    meta = json.load(open(os.path.join(path, var, ".zarray")))
+    shape, chunks, dtype = meta["shape"], meta["chunks"], np.dtype(meta["dtype"])
+    fill = meta["fill_value"]
+    out = np.full(shape, np.nan if fill == "NaN" else (0 if fill is None else fill), dtype=dtype)
+    grid = [(s + c - 1) // c for s, c in zip(shape, chunks, strict=True)]
+    for idx in np.ndindex(*grid):
+        f = os.path.join(path, var, ".".join(str(i) for i in idx))
+        if not os.path.exists(f):
+            continue
+        arr = np.frombuffer(blosc_decode(open(f, "rb").read()), dtype=dtype).reshape(chunks)
+        sl = tuple(slice(i * c, min((i + 1) * c, s)) for i, c, s in zip(idx, chunks, shape, strict=True))
+        out[sl] = arr[tuple(slice(0, s.stop - s.start) for s in sl)]
+    return out
+
+
+def make_v3(interp_name: str, out_name: str):
+    nc = read_nc_f64(
+        os.path.join(REF_TESTDATA, f"test_interpolation_data_random_{interp_name}.nc"),
+        ["U", "V", "W", "time", "depth", "lat", "lon"],
+    )
+    z = os.path.join(REF_TESTDATA, f"test_interpolation_jit_{interp_name}.zarr")
+    traj = read_zarr_v2(z, "trajectory")
+    order = np.argsort(traj, kind="stable")  # reference test sorts v3 rows by trajectory (:372)
+    gold = {k: read_zarr_v2(z, k)[order] for k in ("lon", "lat", "z")}
+    np.savez_compressed(
+        os.path.join(GOLDEN, out_name),
+        U=nc["U"], V=nc["V"], W=nc["W"], time=nc["time"], depth=nc["depth"], lat=nc["lat"], lon=nc["lon"],
+        gold_lon=gold["lon"], gold_lat=gold["lat"], gold_z=gold["z"], trajectory=traj[order],
+    )  # fmt: skip
+    print(out_name, {k: v.shape for k, v in nc.items()}, gold["lon"].shape, "NaN frac", np.isnan(gold["lon"]).mean())
+
+
+def make_ref_cases():
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import cases  # tests/cases.py: seeded input generators shared by tests and this script
+
+    from . import ref_harness as rh
+
+    out = {}
+    for name, spec in cases.CASES.items():
+        c = cases.build(spec)
+        fs = rh.build_fieldset(
+            lon=c["lon"], lat=c["lat"], depth=c["depth"], times=c["times"], U=c["U"], V=c["V"], W=c["W"],
+            mesh=c["mesh"], constants=c["constants"], interp=c.get("interp", "linear"),
+            padding=c.get("padding", ("low", "low", "high")),
+        )  # fmt: skip
+        ps = rh.make_pset(fs, x=c["x"], y=c["y"], z=c["z"], t=c["t"])
+        k = rh.kernels()
+
+        def DeleteParticle(particles, fieldset):
+            particles[particles.state >= 50].state = 30
+
+        kern = [getattr(k, kn) for kn in c["kernels"]]
+        if c["delete_on_error"]:
+            kern.append(DeleteParticle)
+        err = ""
+        if c["rng_seed"] is not None:
+            np.random.seed(c["rng_seed"])
+        try:
+            for seg in c["segments"]:
+                ps.execute(kern, dt=c["dt"], verbose_progress=False, **seg)
+        except Exception as e:  # the reference raised: store which error
+            err = type(e).__name__
+        for key in ("x", "y", "z", "t", "state", "ei", "particle_id", "dt"):
+            out[f"{name}/{key}"] = ps._data[key]
+        out[f"{name}/error"] = np.array(err)
+        print(f"{name}: n_out={len(ps._data['x'])} err={err!r} states={np.unique(ps._data['state'])}")
+    np.savez_compressed(os.path.join(GOLDEN, "ref_cases.npz"), **out)
+
+
+if __name__ == "__main__":
+    os.makedirs(GOLDEN, exist_ok=True)
+    make_v3("linear", "v3_jit_linear.npz")
+    make_v3("cgrid_velocity", "v3_jit_cgrid.npz")
+    make_ref_cases()

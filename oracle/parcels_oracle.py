@@ -1,0 +1,582 @@
+"""TEST INFRASTRUCTURE ONLY -- CPU oracle for the hot path ``ParticleSet.execute(AdvectionRK4 | ...)``.
+
+A NumPy restatement of the reference's (Parcels v4-alpha, ``/root/reference``) algorithm for the
+path named in BASELINE.json's ``north_star``.  It deliberately uses the same NumPy operations in
+the same order and with the same dtype promotion as the reference, so that it is bit-identical to
+the reference's own code (pinned by ``tests/test_oracle_vs_reference.py`` through
+``oracle/ref_harness.py`` and by the committed fixtures under ``tests/golden/``, which hold
+outputs of the reference itself plus the reference's own known-answer tests).
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` / ``--impl
+reference`` legs may import this module, and only as the checker / CPU baseline.  The product
+(``parcels_b200``) never imports it and has no CPU fallback.
+
+Every function cites the reference file:line it follows (paths relative to
+``/root/reference/src/parcels``).
+"""
+
+from __future__ import annotations
+
+import numpy as np
+
+# --- status codes: _core/statuscodes.py:19-34 -------------------------------------------------
+SUCCESS, END_OF_LOOP, EVALUATE, REPEAT, DELETE = 0, 1, 10, 20, 30
+STOP_EXECUTION, STOP_ALL_EXECUTION = 40, 41
+ERROR, ERROR_INTERPOLATION, ERROR_GRID_SEARCHING = 50, 51, 52
+ERROR_OUT_OF_BOUNDS, ERROR_THROUGH_SURFACE, ERROR_OUTSIDE_TIME_INTERVAL = 60, 61, 70
+
+# --- search sentinels: _core/index_search.py:15-17 --------------------------------------------
+GRID_SEARCH_ERROR, LEFT_OUT_OF_BOUNDS, RIGHT_OUT_OF_BOUNDS = -3, -2, -1
+
+EARTH_RADIUS = 6366707.019493707  # _core/mesh.py:6
+DEG2M_EARTH = EARTH_RADIUS * np.pi / 180.0  # _core/mesh.py:37-40
+
+
+class OutsideTimeInterval(RuntimeError):
+    pass
+
+
+class OracleParticleError(RuntimeError):
+    """Raised where the reference raises a mapped exception (_core/kernel.py:239-245)."""
+
+    def __init__(self, code, msg=""):
+        super().__init__(f"particle error state {code} {msg}")
+        self.code = code
+
+
+# ----------------------------------------------------------------------------------------------
+# Grid / fields (host-side description; equivalent of XGrid + ModelData for this path)
+# ----------------------------------------------------------------------------------------------
+class OGrid:
+    """Structured grid: 1-D (rectilinear) or 2-D (curvilinear) lon/lat, 1-D depth.
+
+    An axis that the grid does not have is ``None`` (``XGrid.axes``, _core/xgrid.py:145-147).
+    ``xdim/ydim/zdim`` are *cell counts* (_core/xgrid.py:21-24,208-231): for LOW/HIGH padding
+    with no face dimension in the dataset this is ``n_nodes - 1``; pass explicitly otherwise.
+    """
+
+    def __init__(self, lon=None, lat=None, depth=None, mesh="flat", radius=None, xdim=None, ydim=None, zdim=None,
+                 offsets=(1, 1, 0)):
+        self.lon = None if lon is None else np.asarray(lon)
+        self.lat = None if lat is None else np.asarray(lat)
+        self.depth = None if depth is None else np.asarray(depth)
+        self.spherical = mesh == "spherical" or radius is not None
+        # XGrid.deg2m (_core/xgrid.py:201-206): 1.0 on flat meshes
+        self.deg2m = ((EARTH_RADIUS if radius is None else radius) * np.pi / 180.0) if self.spherical else 1.0
+        self.curvilinear = self.lon is not None and self.lon.ndim == 2
+        if self.lon is not None:
+            nxn = self.lon.shape[-1]
+            self.xdim = (nxn - 1) if xdim is None else xdim
+        else:
+            self.xdim = None
+        if self.lat is not None:
+            nyn = self.lat.shape[0]
+            self.ydim = (nyn - 1) if ydim is None else ydim
+        else:
+            self.ydim = None
+        if self.depth is not None:
+            self.zdim = (len(self.depth) - 1) if zdim is None else zdim
+        else:
+            self.zdim = None
+        # C-grid staggering offsets X, Y, Z (_xinterpolators.py:99-109): 1 for LOW padding else 0
+        self.offsets = {"X": offsets[0], "Y": offsets[1], "Z": offsets[2]}
+        self.hash = None
+
+    @property
+    def axes(self):
+        out = []
+        if self.depth is not None:
+            out.append("Z")
+        if self.lat is not None:
+            out.append("Y")
+        if self.lon is not None:
+            out.append("X")
+        return out
+
+
+class OFieldSet:
+    """U, V (, W) arrays laid out (T, Z, Y, X) on one grid, plus constant fields.
+
+    ``time``: float64 seconds since the start of the time interval, or None for a field
+    without a time dimension (``Field.time_interval`` is None, _core/field.py:112-117).
+    ``interp``: "linear" (XLinear_Velocity) or "cgrid_velocity" (CGrid_Velocity).
+    ``constants``: name -> value (``FieldSet.add_constant_field``, _core/fieldset.py:175-205);
+    constant fields live on their own 1-node grid (_core/model.py:292-318), so ``ngrids`` is 2.
+    """
+
+    def __init__(self, grid: OGrid, U, V, W=None, time=None, interp="linear", constants=None, const_mesh=None):
+        self.grid = grid
+        self.U = np.asarray(U)
+        self.V = np.asarray(V)
+        self.W = None if W is None else np.asarray(W)
+        self.time = None if time is None else np.asarray(time, dtype=np.float64)
+        if self.time is not None and len(self.time) < 2:
+            self.time = None  # model.py:511-515: a single time level => no time interval
+        self.interp = interp
+        self.constants = dict(constants or {})
+        self.const_spherical = grid.spherical if const_mesh is None else (const_mesh == "spherical")
+        self.const_deg2m = DEG2M_EARTH if self.const_spherical else 1.0
+
+    @property
+    def ngrids(self):
+        return 2 if self.constants else 1
+
+
+def create_particle_data(x, y, z, t, ngrids=1, dt=1.0, particle_ids=None):
+    """SoA dict of the default Particle (_core/particle.py:123-222)."""
+    x = np.asarray(x).flatten()
+    n = x.size
+    t = np.asarray(t, dtype=np.float64).flatten()
+    if t.size == 1:
+        t = np.repeat(t, n)
+    return {
+        "ei": np.zeros((n, ngrids), dtype=np.int32),
+        "t": t.astype(np.float64),
+        "z": np.asarray(z).flatten().astype(np.float32),
+        "y": np.asarray(y).flatten().astype(np.float32),
+        "x": x.astype(np.float32),
+        "particle_id": (np.arange(n) if particle_ids is None else np.asarray(particle_ids)).astype(np.int64),
+        "dz": np.zeros(n, dtype=np.float32),
+        "dy": np.zeros(n, dtype=np.float32),
+        "dx": np.zeros(n, dtype=np.float32),
+        "dt": np.full(n, dt, dtype=np.float64),
+        "state": np.full(n, EVALUATE, dtype=np.int32),
+    }
+
+
+class View:
+    """Boolean-mask window on the SoA (_core/particlesetview.py): reads copy, writes go through."""
+
+    def __init__(self, data, mask):
+        object.__setattr__(self, "_d", data)
+        object.__setattr__(self, "_m", mask)
+
+    def __getattr__(self, name):
+        return self._d[name][self._m]
+
+    def __setattr__(self, name, value):
+        self._d[name][self._m] = value
+
+    def n(self):
+        return int(np.count_nonzero(self._m))
+
+
+# ----------------------------------------------------------------------------------------------
+# Index search
+# ----------------------------------------------------------------------------------------------
+def search_1d(arr, x):
+    """_core/index_search.py:20-62 (``_search_1d_array``)."""
+    if len(arr) < 2:
+        return np.zeros(shape=x.shape, dtype=np.int32), np.zeros_like(x)
+    n = len(arr)
+    idx = np.clip(np.searchsorted(arr, x, side="left") - 1, 0, n - 2)
+    lo = arr[idx]
+    hi = arr[np.clip(idx + 1, 1, n - 1)]
+    b = (x - lo) / (hi - lo)
+    idx = np.where(x < arr[0], LEFT_OUT_OF_BOUNDS, idx)
+    idx = np.where(x > arr[-1], RIGHT_OUT_OF_BOUNDS, idx)
+    return np.atleast_1d(idx), np.atleast_1d(b)
+
+
+def search_time(time_flt, t):
+    """_core/index_search.py:65-91 (``_search_time_index``) + TimeInterval check (utils/time.py:62-64)."""
+    t = np.atleast_1d(t)
+    if time_flt is None:
+        return np.zeros(t.shape, dtype=np.int32), np.zeros(t.shape, dtype=np.float32)
+    length = time_flt[-1] - time_flt[0]
+    if not ((0 <= t).all() and (t <= length).all()):
+        raise OutsideTimeInterval(str(t))
+    return search_1d(time_flt - time_flt[0], t)
+
+
+def ravel_index(grid: OGrid, zi, yi, xi):
+    """_core/basegrid.py:83-118,259-278: ei = zi*ydim*xdim + yi*xdim + xi over the axes present."""
+    dims, idx = [], []
+    for ax, d, i in (("Z", grid.zdim, zi), ("Y", grid.ydim, yi), ("X", grid.xdim, xi)):
+        if ax in grid.axes:
+            dims.append(d)
+            idx.append(np.asarray(i).astype(int))
+    dims = np.array(dims, dtype=int)
+    strides = np.cumprod(dims[::-1])[::-1]
+    ei = 0
+    for k in range(len(dims) - 1):
+        ei = ei + idx[k] * strides[k + 1]
+    return ei + idx[-1]
+
+
+def unravel_index(grid: OGrid, ei):
+    """_core/basegrid.py:120-152,219-256."""
+    axes = grid.axes
+    dims = np.array([{"Z": grid.zdim, "Y": grid.ydim, "X": grid.xdim}[a] for a in axes], dtype=int)
+    strides = np.cumprod(dims[::-1])[::-1]
+    out = {}
+    ei = np.asarray(ei)
+    for k in range(len(dims) - 1):
+        out[axes[k]] = ei // strides[k + 1]
+        ei = ei % strides[k + 1]
+    out[axes[-1]] = ei
+    return out
+
+
+def grid_search(grid: OGrid, z, y, x, ei=None):
+    """_core/xgrid.py:316-356 (``XGrid.search``)."""
+    if grid.depth is not None:
+        zi, zeta = search_1d(grid.depth, z)
+    else:
+        zi, zeta = np.zeros(z.shape, dtype=int), np.zeros(z.shape, dtype=float)
+    if grid.curvilinear:
+        from . import curvilinear_oracle as co
+
+        yi0 = xi0 = None
+        if ei is not None:
+            hint = unravel_index(grid, ei)
+            xi0, yi0 = hint.get("X"), hint.get("Y")
+        yi, eta, xi, xsi = co.search_indices_curvilinear_2d(grid, y, x, yi0, xi0)
+        return (zi, zeta), (yi, eta), (xi, xsi)
+    if grid.lat is not None:
+        yi, eta = search_1d(grid.lat, y)
+    else:
+        yi, eta = np.zeros(y.shape, dtype=int), np.zeros(y.shape, dtype=float)
+    if grid.lon is not None:
+        xi, xsi = search_1d(grid.lon, x)
+    else:
+        xi, xsi = np.zeros(x.shape, dtype=int), np.zeros(x.shape, dtype=float)
+    return (zi, zeta), (yi, eta), (xi, xsi)
+
+
+# ----------------------------------------------------------------------------------------------
+# Interpolation
+# ----------------------------------------------------------------------------------------------
+def _take(data, ti, zi, yi, xi):
+    """Pointwise gather ``data[ti, zi, yi, xi]``; size-1 (mock) dims are not indexed
+    (_xinterpolators.py:61-75: an axis the field has no dimension for repeats its corner)."""
+    T, Z, Y, X = data.shape
+    ti = ti if T > 1 else np.zeros_like(ti)
+    zi = zi if Z > 1 else np.zeros_like(zi)
+    yi = yi if Y > 1 else np.zeros_like(yi)
+    xi = xi if X > 1 else np.zeros_like(xi)
+    return data[ti, zi, yi, xi]
+
+
+def xlinear(data, ti, tau, zi, zeta, yi, eta, xi, xsi):
+    """_xinterpolators.py:78-96,112-153 (``XLinear.interp`` on A-grid corner data).
+
+    Negative sentinel indices wrap like NumPy fancy indexing does in the reference; the caller
+    zeroes those values afterwards (_core/field.py:359-370).
+    """
+    T, Z, Y, X = data.shape
+    two_t = bool(np.any(tau > 0))
+    two_z = bool(np.any(zeta > 0))
+    t_lv = (ti, np.clip(ti + 1, 0, T - 1)) if two_t else (ti,)
+    z_lv = (zi, np.clip(zi + 1, 0, Z - 1)) if two_z else (zi,)
+    y_lv = (yi, np.clip(yi + 1, 0, Y - 1))
+    x_lv = (xi, np.clip(xi + 1, 0, X - 1))
+    c = np.array([[[[_take(data, a, b, cc, d) for d in x_lv] for cc in y_lv] for b in z_lv] for a in t_lv])
+    if two_t:
+        w = tau[np.newaxis, :]
+        c = c[0, :] * (1 - w) + c[1, :] * w
+    else:
+        c = c[0, :]
+    if two_z:
+        w = zeta[np.newaxis, :]
+        c = c[0, :] * (1 - w) + c[1, :] * w
+    else:
+        c = c[0, :]
+    return (
+        (1 - xsi) * (1 - eta) * c[0, 0, :]
+        + xsi * (1 - eta) * c[0, 1, :]
+        + (1 - xsi) * eta * c[1, 0, :]
+        + xsi * eta * c[1, 1, :]
+    )
+
+
+def xlinear_velocity(fs: OFieldSet, pos, gp):
+    """_xinterpolators.py:169-190 (``XLinear_Velocity.interp``)."""
+    (ti, tau), (zi, zeta), (yi, eta), (xi, xsi) = gp
+    u = xlinear(fs.U, ti, tau, zi, zeta, yi, eta, xi, xsi)
+    v = xlinear(fs.V, ti, tau, zi, zeta, yi, eta, xi, xsi)
+    if fs.grid.spherical:
+        u /= fs.grid.deg2m * np.cos(np.deg2rad(pos["y"]))
+        v /= fs.grid.deg2m
+    if fs.W is not None:
+        w = xlinear(fs.W, ti, tau, zi, zeta, yi, eta, xi, xsi)
+    else:
+        w = np.zeros_like(u)
+    return u, v, w
+
+
+# ----------------------------------------------------------------------------------------------
+# VectorField.eval
+# ----------------------------------------------------------------------------------------------
+def _flag_positions(view: View | None, zi, yi, xi):
+    """_core/field.py:327-356 (``_update_particle_states_position``).  NB: X/Y index -2 (left
+    out of bounds) is NOT flagged by the reference; only -1 and -3 are."""
+    if view is None or view.n() == 0:  # `if particles:` is False for an empty view
+        return
+    for idx in (xi, yi):
+        view.state = np.maximum(np.where(idx == -1, ERROR_OUT_OF_BOUNDS, view.state), view.state)
+        view.state = np.maximum(np.where(idx == GRID_SEARCH_ERROR, ERROR_GRID_SEARCHING, view.state), view.state)
+    view.state = np.maximum(np.where(zi == RIGHT_OUT_OF_BOUNDS, ERROR_OUT_OF_BOUNDS, view.state), view.state)
+    view.state = np.maximum(np.where(zi == LEFT_OUT_OF_BOUNDS, ERROR_THROUGH_SURFACE, view.state), view.state)
+
+
+def eval_uvw(fs: OFieldSet, t, z, y, x, view: View | None, want3d: bool):
+    """_core/field.py:250-304 (``VectorField.eval`` + ``__getitem__`` error mapping :31-44)."""
+    try:
+        ei = None if view is None else view.ei[:, -1]
+        z, y, x = np.atleast_1d(z), np.atleast_1d(y), np.atleast_1d(x)
+        if np.any(np.isnan(t)):
+            raise ValueError("Time values cannot be NaN")
+        ti, tau = search_time(fs.time, t)
+        (zi, zeta), (yi, eta), (xi, xsi) = grid_search(fs.grid, z, y, x, ei)
+        if view is not None:
+            e = view.ei
+            e[:, -1] = ravel_index(fs.grid, zi, yi, xi)  # field.py:307-317 (int64 -> int32 store)
+            view.ei = e
+        _flag_positions(view, zi, yi, xi)
+        pos = {"t": t, "z": z, "y": y, "x": x}
+        gp = ((ti, tau), (zi, zeta), (yi, eta), (xi, xsi))
+        if fs.interp == "linear":
+            u, v, w = xlinear_velocity(fs, pos, gp)
+        else:
+            from . import curvilinear_oracle as co
+
+            u, v, w = co.cgrid_velocity(fs, pos, gp)
+        oob = (xi < 0) | (yi < 0) | (zi < 0)
+        for vel in (u, v, w):
+            if view is not None and view.n() > 0:
+                view.state = np.maximum(np.where(np.isnan(vel), ERROR_INTERPOLATION, view.state), view.state)
+            if np.any(oob):
+                vel[oob] = 0.0
+        return (u, v, w) if want3d else (u, v)
+    except OutsideTimeInterval:
+        view.state = ERROR_OUTSIDE_TIME_INTERVAL  # plain assignment to the whole view (field.py:31-36)
+        return (0, 0, 0) if want3d else (0, 0)
+
+
+def eval_constant(fs: OFieldSet, name, view: View):
+    """``fieldset.Kh_zonal[particles]`` on the constant-field grid (lon=[0], lat=[0], no depth;
+    _core/model.py:292-318): the grid search returns index 0 everywhere (index_search.py:45-46),
+    ``ei[:, -1]`` is overwritten with 0 (cell counts are 0) and XConstantField returns
+    ``data[0,0,0,0] * ones_like(x)`` (_xinterpolators.py:156-166)."""
+    e = view.ei
+    e[:, -1] = 0
+    view.ei = e
+    val = np.asarray(fs.constants[name]) * np.ones_like(view.x)
+    if view.n() > 0:
+        view.state = np.maximum(np.where(np.isnan(val), ERROR_INTERPOLATION, view.state), view.state)
+    return val
+
+
+# ----------------------------------------------------------------------------------------------
+# Kernels
+# ----------------------------------------------------------------------------------------------
+def AdvectionRK4(p: View, fs: OFieldSet):
+    """kernels/_advection.py:42-55."""
+    (u1, v1) = eval_uvw(fs, p.t, p.z, p.y, p.x, p, False)
+    x1 = p.x + u1 * 0.5 * p.dt
+    y1 = p.y + v1 * 0.5 * p.dt
+    (u2, v2) = eval_uvw(fs, p.t + 0.5 * p.dt, p.z, y1, x1, p, False)
+    x2 = p.x + u2 * 0.5 * p.dt
+    y2 = p.y + v2 * 0.5 * p.dt
+    (u3, v3) = eval_uvw(fs, p.t + 0.5 * p.dt, p.z, y2, x2, p, False)
+    x3 = p.x + u3 * p.dt
+    y3 = p.y + v3 * p.dt
+    (u4, v4) = eval_uvw(fs, p.t + p.dt, p.z, y3, x3, p, False)
+    p.dx = p.dx + (u1 + 2 * u2 + 2 * u3 + u4) / 6.0 * p.dt
+    p.dy = p.dy + (v1 + 2 * v2 + 2 * v3 + v4) / 6.0 * p.dt
+
+
+def AdvectionRK4_3D(p: View, fs: OFieldSet):
+    """kernels/_advection.py:58-75."""
+    (u1, v1, w1) = eval_uvw(fs, p.t, p.z, p.y, p.x, p, True)
+    x1 = p.x + u1 * 0.5 * p.dt
+    y1 = p.y + v1 * 0.5 * p.dt
+    z1 = p.z + w1 * 0.5 * p.dt
+    (u2, v2, w2) = eval_uvw(fs, p.t + 0.5 * p.dt, z1, y1, x1, p, True)
+    x2 = p.x + u2 * 0.5 * p.dt
+    y2 = p.y + v2 * 0.5 * p.dt
+    z2 = p.z + w2 * 0.5 * p.dt
+    (u3, v3, w3) = eval_uvw(fs, p.t + 0.5 * p.dt, z2, y2, x2, p, True)
+    x3 = p.x + u3 * p.dt
+    y3 = p.y + v3 * p.dt
+    z3 = p.z + w3 * p.dt
+    (u4, v4, w4) = eval_uvw(fs, p.t + p.dt, z3, y3, x3, p, True)
+    p.dx = p.dx + (u1 + 2 * u2 + 2 * u3 + u4) / 6 * p.dt
+    p.dy = p.dy + (v1 + 2 * v2 + 2 * v3 + v4) / 6 * p.dt
+    p.dz = p.dz + (w1 + 2 * w2 + 2 * w3 + w4) / 6 * p.dt
+
+
+def AdvectionEE(p: View, fs: OFieldSet):
+    """kernels/_advection.py:78-82."""
+    (u1, v1) = eval_uvw(fs, p.t, p.z, p.y, p.x, p, False)
+    p.dx = p.dx + u1 * p.dt
+    p.dy = p.dy + v1 * p.dt
+
+
+def AdvectionRK2(p: View, fs: OFieldSet):
+    """kernels/_advection.py:20-27."""
+    (u1, v1) = eval_uvw(fs, p.t, p.z, p.y, p.x, p, False)
+    x1 = p.x + u1 * 0.5 * p.dt
+    y1 = p.y + v1 * 0.5 * p.dt
+    (u2, v2) = eval_uvw(fs, p.t + 0.5 * p.dt, p.z, y1, x1, p, False)
+    p.dx = p.dx + u2 * p.dt
+    p.dy = p.dy + v2 * p.dt
+
+
+def AdvectionRK2_3D(p: View, fs: OFieldSet):
+    """kernels/_advection.py:30-39."""
+    (u1, v1, w1) = eval_uvw(fs, p.t, p.z, p.y, p.x, p, True)
+    x1 = p.x + u1 * 0.5 * p.dt
+    y1 = p.y + v1 * 0.5 * p.dt
+    z1 = p.z + w1 * 0.5 * p.dt
+    (u2, v2, w2) = eval_uvw(fs, p.t + 0.5 * p.dt, z1, y1, x1, p, True)
+    p.dx = p.dx + u2 * p.dt
+    p.dy = p.dy + v2 * p.dt
+    p.dz = p.dz + w2 * p.dt
+
+
+class DiffusionUniformKh:
+    """kernels/_advectiondiffusion.py:11-18,120-153.  ``normal(view)`` supplies the two N(0,1)
+    draws per particle; the default mirrors the reference's legacy global RandomState
+    (``np.random.normal``).  Tests inject the engine's Philox stream to compare the
+    deterministic part bit-for-bit."""
+
+    __name__ = "DiffusionUniformKh"
+
+    def __init__(self, normal=None):
+        self.normal = normal
+
+    def __call__(self, p: View, fs: OFieldSet):
+        if self.normal is None:
+            dWx = np.random.normal(0, np.sqrt(np.fabs(p.dt)))
+            dWy = np.random.normal(0, np.sqrt(np.fabs(p.dt)))
+        else:
+            zx, zy = self.normal(p)
+            dWx = zx * np.sqrt(np.fabs(p.dt))
+            dWy = zy * np.sqrt(np.fabs(p.dt))
+        kh_zonal = eval_constant(fs, "Kh_zonal", p)
+        kh_meridional = eval_constant(fs, "Kh_meridional", p)
+        if fs.const_spherical:
+            kh_zonal = kh_zonal / pow(fs.const_deg2m * np.cos(p.y * np.pi / 180), 2)
+            kh_meridional = kh_meridional / pow(fs.const_deg2m, 2)
+        bx = np.sqrt(2 * kh_zonal)
+        by = np.sqrt(2 * kh_meridional)
+        p.dx = p.dx + bx * dWx
+        p.dy = p.dy + by * dWy
+
+
+def DeleteOnError(p: View, fs: OFieldSet):
+    """The idiom of the reference's tests (tests/common_kernels.py:12-13,
+    tests/test_interpolation.py:357-359): every error state becomes Delete."""
+    s = p.state
+    p.state = np.where(s >= 50, DELETE, s)
+
+
+# ----------------------------------------------------------------------------------------------
+# Kernel.execute / ParticleSet.execute
+# ----------------------------------------------------------------------------------------------
+_ERRORS_TO_THROW = (  # order of _core/kernel.py:31-38
+    ERROR_OUTSIDE_TIME_INTERVAL,
+    ERROR_OUT_OF_BOUNDS,
+    ERROR_THROUGH_SURFACE,
+    ERROR_INTERPOLATION,
+    ERROR_GRID_SEARCHING,
+    ERROR,
+)
+
+
+def _remove(pdata, idx):
+    """_core/particleset.py:247-250 (np.delete on every array)."""
+    for k in pdata:
+        pdata[k] = np.delete(pdata[k], idx, axis=0)
+
+
+def kernel_execute(pdata, fs: OFieldSet, kernels, endtime, dt, max_iters=None):
+    """_core/kernel.py:174-247 (``Kernel.execute``) + ``_position_update`` (:108-120).
+
+    ``max_iters`` (testing aid, not in the reference) stops after that many loop iterations.
+    Returns the number of particle-steps evaluated.
+    """
+    sign = 1 if dt > 0 else -1
+    pdata["state"][:] = EVALUATE
+    nsteps = 0
+    it = 0
+    while len(pdata["state"]) > 0 and np.any(np.isin(pdata["state"], [EVALUATE, REPEAT])):
+        if max_iters is not None and it >= max_iters:
+            break
+        it += 1
+        tte = sign * (endtime - pdata["t"])
+        ev = np.isin(pdata["state"], [SUCCESS, EVALUATE]) & (tte >= 0)
+        if not np.any(ev):
+            return nsteps
+        if sign == 1:
+            pdata["dt"][:] = np.maximum(np.minimum(pdata["dt"], tte), 0)
+        else:
+            pdata["dt"][:] = np.minimum(np.maximum(pdata["dt"], -tte), 0)
+        nsteps += int(np.count_nonzero(ev))
+        for f in kernels:
+            f(View(pdata, ev), fs)
+        upd = ev & np.isin(pdata["state"], [EVALUATE, SUCCESS])
+        if np.any(upd):
+            p = View(pdata, upd)
+            p.x = p.x + p.dx
+            p.y = p.y + p.dy
+            p.z = p.z + p.dz
+            p.t = p.t + p.dt
+            p.dx = 0
+            p.dy = 0
+            p.dz = 0
+        pdata["dt"][:] = dt
+        eol = (pdata["state"] == EVALUATE) & (pdata["t"] == endtime)
+        pdata["state"][eol] = END_OF_LOOP
+        dele = np.where(pdata["state"] == DELETE)[0]
+        if len(dele) > 0:
+            _remove(pdata, dele)
+        if np.any(pdata["state"] == STOP_ALL_EXECUTION):
+            return nsteps
+        for code in _ERRORS_TO_THROW:
+            if np.any(pdata["state"] == code):
+                raise OracleParticleError(code)
+    return nsteps
+
+
+def pset_execute(pdata, fs: OFieldSet, kernels, dt, runtime=None, endtime=None, outputdt=None, on_output=None):
+    """_core/particleset.py:355-470 (outer loop) with float-second arguments
+    (:497-585: start = first release time, or 0 / interval end when t is NaN)."""
+    if len(pdata["state"]) == 0:
+        return 0
+    if not isinstance(kernels, (list, tuple)):
+        kernels = [kernels]
+    dt = float(dt)
+    sign = 1 if dt > 0 else -1
+    pdata["dt"][:] = dt
+    first = np.nanmin(pdata["t"]) if sign == 1 else np.nanmax(pdata["t"])
+    if np.all(np.isnan(pdata["t"])):
+        first = np.nan
+    if np.isnan(first):
+        start = 0.0 if sign == 1 else float(fs.time[-1] - fs.time[0])
+    else:
+        start = float(first)
+    end = float(endtime) if endtime is not None else start + sign * float(runtime)
+    if np.isnan(pdata["t"]).any():
+        pdata["t"][:] = start
+    next_output = None
+    if outputdt is not None:
+        if on_output is not None:
+            on_output(pdata, start)
+        next_output = start + outputdt * sign
+    time = start
+    total = 0
+    while sign * (time - end) < 0:
+        if next_output is not None:
+            next_time = min(next_output, end) if sign > 0 else max(next_output, end)
+        else:
+            next_time = end
+        total += kernel_execute(pdata, fs, kernels, next_time, dt)
+        if next_output is not None and abs(next_time - next_output) < 0.001:
+            if on_output is not None:
+                on_output(pdata, next_output)
+            next_output += outputdt * sign
+        time = next_time
+    return total
