@@ -1,0 +1,164 @@
+/* parcels_b200.h -- C-ABI of libparcels_b200.so: the B200-native replacement for the hot path
+ * ParticleSet.execute(AdvectionRK4 | AdvectionRK4_3D | AdvectionEE | AdvectionRK2[_3D]
+ *                     [+ DiffusionUniformKh] [+ delete-on-error handler]).
+ *
+ * The reference (Parcels v4-alpha, pure Python/NumPy) has no FFI; this header DEFINES the
+ * drop-in boundary.  Each entry point cites the reference interface it
+ * replaces (paths relative to /root/reference/src/parcels).  All functions return 0 on
+ * success and a negative pb_status on failure; pb_last_error_string() describes the failure.
+ * One engine per GPU; an engine is driven by one host thread; all device work is ordered on
+ * an engine-owned CUDA stream.  Plain pointers and sizes only -- no torch / numpy types.
+ */
+#ifndef PARCELS_B200_H
+#define PARCELS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PB_ABI_VERSION 1
+
+typedef struct pb_engine pb_engine;
+
+enum pb_status {
+    PB_OK = 0,
+    PB_ERR_INVALID = -1,     /* bad argument / unsupported configuration                      */
+    PB_ERR_CUDA = -2,        /* CUDA runtime error (message in pb_last_error_string)           */
+    PB_ERR_STATE = -3,       /* call order violated (e.g. advect before grid/field upload)     */
+    PB_ERR_NO_DEVICE = -4    /* no CUDA device: there is NO CPU fallback                       */
+};
+
+/* Velocity-field slots (VectorField components, _core/field.py:198-240). */
+enum pb_field_slot { PB_FIELD_U = 0, PB_FIELD_V = 1, PB_FIELD_W = 2 };
+
+/* Advection scheme (kernels/_advection.py). */
+enum pb_scheme {
+    PB_ADVECTION_EE = 1,      /* :78-82   */
+    PB_ADVECTION_RK2 = 2,     /* :20-27   */
+    PB_ADVECTION_RK2_3D = 3,  /* :30-39   */
+    PB_ADVECTION_RK4 = 4,     /* :42-55   */
+    PB_ADVECTION_RK4_3D = 5   /* :58-75   */
+};
+
+/* Particle status codes written by the device: identical to _core/statuscodes.py:19-34. */
+enum pb_state {
+    PB_SUCCESS = 0, PB_END_OF_LOOP = 1, PB_EVALUATE = 10, PB_REPEAT = 20, PB_DELETE = 30,
+    PB_STOP_EXECUTION = 40, PB_STOP_ALL_EXECUTION = 41, PB_ERROR = 50, PB_ERROR_INTERPOLATION = 51,
+    PB_ERROR_GRID_SEARCHING = 52, PB_ERROR_OUT_OF_BOUNDS = 60, PB_ERROR_THROUGH_SURFACE = 61,
+    PB_ERROR_OUTSIDE_TIME_INTERVAL = 70
+};
+
+/* ---- engine life cycle ------------------------------------------------------------------ */
+int32_t pb_abi_version(void);
+const char* pb_last_error_string(void);
+int32_t pb_device_count(void);
+/* Creates an engine on CUDA device `device` (fails with PB_ERR_NO_DEVICE when there is none). */
+int32_t pb_engine_create(int32_t device, pb_engine** out);
+void pb_engine_destroy(pb_engine* e);
+/* Blocks until all work queued on the engine's stream has finished. */
+int32_t pb_engine_synchronize(pb_engine* e);
+
+/* Device timing on the engine's own stream (torch.cuda.Event only sees torch's streams):
+ * begin records a CUDA event, end records a second one, waits for it and returns the elapsed ms. */
+int32_t pb_timer_begin(pb_engine* e);
+int32_t pb_timer_end_ms(pb_engine* e, float* ms);
+
+/* ---- grid: replaces XGrid.search inputs (_core/xgrid.py:316-356) --------------------------
+ * Rectilinear grid: 1-D node coordinates lon[nx], lat[ny], depth[nz] (depth may be NULL/nz=0:
+ * the grid has no Z axis) of dtype float32 (coord_is_f64=0) or float64 (=1) -- the dtype is
+ * part of the contract because the reference's arithmetic promotes on it
+ * (_core/index_search.py:47-51).  time_s[nt]: seconds since the start of the field's time
+ * interval (float64), nt<2 or NULL => the field has no time dimension
+ * (_core/index_search.py:77-83).  xdim/ydim/zdim_cells: cell counts used by ravel_index
+ * (_core/basegrid.py:83-118, _core/xgrid.py:21-24,208-231; depend on SGRID padding).
+ * The engine copies everything to HBM; the host keeps ownership of its buffers. */
+int32_t pb_grid_upload_rectilinear(pb_engine* e, const void* lon, int64_t nx, const void* lat, int64_t ny,
+                                   const void* depth, int64_t nz, int32_t coord_is_f64,
+                                   const double* time_s, int64_t nt, int32_t spherical, double deg2m,
+                                   int64_t xdim_cells, int64_t ydim_cells, int64_t zdim_cells);
+
+/* ---- field data: replaces ModelData.field_data -> xarray .isel gathers -------------------
+ * (_core/model.py:67-77, interpolators/_xinterpolators.py:25-96).  C-contiguous (T,Z,Y,X),
+ * float32 or float64, NaNs already filled (model.py:135-143).  Size-1 dims are never indexed
+ * (mock dims, _core/xgrid.py:71-105).  Staged through pinned memory, async H2D. */
+int32_t pb_field_upload(pb_engine* e, int32_t slot, const void* data, int32_t data_is_f64, int64_t T,
+                        int64_t Z, int64_t Y, int64_t X);
+/* Same, but `data` is already a DEVICE pointer owned by the caller (e.g. a torch tensor) that
+ * must outlive the engine's use of it; nothing is copied. */
+int32_t pb_field_attach_device(pb_engine* e, int32_t slot, const void* dev_data, int32_t data_is_f64,
+                               int64_t T, int64_t Z, int64_t Y, int64_t X);
+int32_t pb_field_clear(pb_engine* e, int32_t slot);
+
+/* ---- particles: replaces the SoA dict of create_particle_data (_core/particle.py:182-222)
+ * Host arrays are the pset._data ndarrays themselves (x,y,z,dx,dy,dz float32; t float64;
+ * state int32; ei = LAST column of the (N, ngrids) int32 `ei` array, _core/field.py:279;
+ * particle_id int64).  upload copies host -> HBM; download copies back in the ORIGINAL order
+ * (the device may keep particles permuted). */
+int32_t pb_particles_upload(pb_engine* e, int64_t n, const float* x, const float* y, const float* z,
+                            const float* dx, const float* dy, const float* dz, const double* t,
+                            const int32_t* state, const int32_t* ei, const int64_t* particle_id);
+int32_t pb_particles_download(pb_engine* e, int64_t n, float* x, float* y, float* z, float* dx, float* dy,
+                              float* dz, double* t, int32_t* state, int32_t* ei);
+/* Device-resident bench support: snapshot / restore the particle SoA inside HBM. */
+int32_t pb_particles_snapshot(pb_engine* e);
+int32_t pb_particles_restore(pb_engine* e);
+int64_t pb_particles_count(pb_engine* e);
+
+/* ---- the hot path: replaces Kernel.execute(pset, endtime, dt) (_core/kernel.py:174-247) -- */
+typedef struct pb_advect_args {
+    int32_t scheme;            /* enum pb_scheme                                                */
+    int32_t diffusion;         /* 1: DiffusionUniformKh fused after the advection kernel
+                                  (kernels/_advectiondiffusion.py:120-153)                      */
+    int32_t delete_on_error;   /* 1: a trailing error handler turns every state >= 50 into
+                                  Delete (reference idiom tests/common_kernels.py:12-13)        */
+    int32_t kh_spherical;      /* mesh of the constant Kh fields                                */
+    double dt;                 /* signed time step, seconds                                     */
+    double endtime;            /* seconds since the start of the time interval                  */
+    double kh_zonal;           /* constant-field values (m^2/s)                                 */
+    double kh_meridional;
+    double kh_deg2m;
+    uint64_t seed;             /* Philox4x32-10 key for the Wiener increments                   */
+    uint64_t rng_call;         /* counter word: index of this Kernel.execute call               */
+    int64_t max_iters;         /* <0: run to endtime; >=0: at most this many loop iterations
+                                  (used to replay up to the first error)    */
+} pb_advect_args;
+
+typedef struct pb_report {
+    int64_t particle_steps;    /* particle-steps evaluated (one step = all RK stages)           */
+    int64_t n_error;           /* particles that ended in a state >= 50                          */
+    int64_t n_deleted;         /* particles that ended in state Delete (30)                     */
+    int64_t first_error_iter;  /* smallest loop iteration at which an error state arose, or -1  */
+    int64_t n_out_of_time;     /* particles that sampled outside the time interval (state 70)    */
+    int64_t max_iters_done;    /* largest per-particle iteration count                          */
+    int64_t cache_refills;     /* corner-cache refills (diagnostic: HBM gathers actually made)   */
+    int32_t max_state;
+    int32_t reserved;
+    float kernel_ms;           /* CUDA-event time of the advection kernel on the engine stream   */
+    float reserved2;
+} pb_report;
+
+/* Runs the inner loop of Kernel.execute for every particle until `endtime` (or an error /
+ * deletion / max_iters).  Synchronous: returns after the kernel has finished and `rep` is
+ * filled.  Particle arrays stay in HBM; call pb_particles_download to read them back. */
+int32_t pb_advect(pb_engine* e, const pb_advect_args* args, pb_report* rep);
+/* Asynchronous variant: enqueues on the engine stream and returns; the report is available
+ * after pb_engine_synchronize() through pb_last_report(). */
+int32_t pb_advect_async(pb_engine* e, const pb_advect_args* args);
+int32_t pb_last_report(pb_engine* e, pb_report* rep);
+
+/* Marks every particle currently in state Evaluate/Success whose time-to-endtime >= 0 with
+ * ErrorOutsideTimeInterval (70): the reference flags the WHOLE evaluated view when any particle
+ * samples outside the time interval (_core/index_search.py:85-86, _core/field.py:31-44). */
+int32_t pb_flag_view_outside_time(pb_engine* e, double dt, double endtime);
+
+/* Pure helper used by tests: the engine's Philox4x32-10 + Box-Muller normals for
+ * (seed, rng_call, iteration, particle_id), computed ON THE DEVICE. out = 2 doubles per id. */
+int32_t pb_debug_normals(pb_engine* e, uint64_t seed, uint64_t rng_call, int64_t iter, int64_t n,
+                         const int64_t* particle_id, double* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PARCELS_B200_H */

@@ -1,0 +1,36 @@
+"""parcels_b200 -- B200-native Lagrangian particle advection behind the Parcels v4 API.
+
+``ParticleSet.execute([AdvectionRK4 | AdvectionRK4_3D | ...], dt=, runtime=|endtime=)`` runs the
+whole per-particle time loop in hand-written sm_100a CUDA (``csrc/engine.cu``) through the C-ABI
+``include/parcels_b200.h`` (ctypes).  There is no CPU implementation in this package.
+"""
+
+from . import kernels
+from .fieldset import Field, FieldSet, VectorField, XGrid
+from .kernels import (
+    AdvectionEE,
+    AdvectionRK2,
+    AdvectionRK2_3D,
+    AdvectionRK4,
+    AdvectionRK4_3D,
+    DeleteParticle,
+    DiffusionUniformKh,
+)
+from .particle import Particle
+from .particleset import ParticleSet
+from .statuscodes import (
+    FieldInterpolationError,
+    FieldOutOfBoundError,
+    FieldOutOfBoundSurfaceError,
+    GeneralError,
+    GridSearchingError,
+    OutsideTimeInterval,
+    StatusCode,
+)
+
+__all__ = [
+    "AdvectionEE", "AdvectionRK2", "AdvectionRK2_3D", "AdvectionRK4", "AdvectionRK4_3D", "DeleteParticle",
+    "DiffusionUniformKh", "Field", "FieldInterpolationError", "FieldOutOfBoundError", "FieldOutOfBoundSurfaceError",
+    "FieldSet", "GeneralError", "GridSearchingError", "OutsideTimeInterval", "Particle", "ParticleSet", "StatusCode",
+    "VectorField", "XGrid", "kernels",
+]  # fmt: skip

@@ -1,0 +1,141 @@
+"""Thin Python wrapper of one ``pb_engine`` (one per GPU).  Plumbing only: every call below is
+a ctypes call into ``libparcels_b200.so``; all compute happens in the CUDA kernels."""
+
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import AdvectArgs, Report, check, ptr
+
+
+def _report_dict(r: Report) -> dict:
+    return {name: getattr(r, name) for name, _ in Report._fields_ if not name.startswith("reserved")}
+
+
+class Engine:
+    def __init__(self, device: int = 0):
+        self._lib = _lib.load()
+        h = C.c_void_p()
+        check(self._lib.pb_engine_create(int(device), C.byref(h)))
+        self._h = h
+        self.device = int(device)
+        self._keep = []  # device tensors attached by pointer must outlive the engine's use
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.pb_engine_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- grid / fields -------------------------------------------------------------------------
+    def upload_rectilinear_grid(self, lon, lat, depth, time_s, spherical, deg2m, xdim, ydim, zdim):
+        lon = np.ascontiguousarray(lon)
+        cdt = lon.dtype
+        if cdt not in (np.float32, np.float64):
+            raise TypeError(f"grid coordinates must be float32 or float64, got {cdt}")
+        lat = np.ascontiguousarray(lat)
+        if lat.dtype != cdt or (depth is not None and np.asarray(depth).dtype != cdt):
+            raise TypeError("lon, lat and depth must share one dtype (the reference's arithmetic promotes on it)")
+        depth = None if depth is None else np.ascontiguousarray(depth)
+        time_s = None if time_s is None else np.ascontiguousarray(time_s, dtype=np.float64)
+        check(
+            self._lib.pb_grid_upload_rectilinear(
+                self._h, ptr(lon), lon.size, ptr(lat), lat.size, ptr(depth), 0 if depth is None else depth.size,
+                int(cdt == np.float64), ptr(time_s), 0 if time_s is None else time_s.size, int(bool(spherical)),
+                float(deg2m), int(xdim), int(ydim), int(zdim or 0),
+            )
+        )  # fmt: skip
+
+    def upload_field(self, slot: int, data):
+        data = np.asarray(data)
+        if data.ndim != 4:
+            raise ValueError("field data must be laid out (T, Z, Y, X)")
+        if data.dtype not in (np.float32, np.float64):
+            raise TypeError(f"field data must be float32 or float64, got {data.dtype}")
+        data = np.ascontiguousarray(data)
+        T, Z, Y, X = data.shape
+        check(self._lib.pb_field_upload(self._h, slot, ptr(data), int(data.dtype == np.float64), T, Z, Y, X))
+
+    def attach_field_device(self, slot: int, dev_ptr: int, is_f64: bool, shape, keepalive=None):
+        T, Z, Y, X = shape
+        check(self._lib.pb_field_attach_device(self._h, slot, C.c_void_p(dev_ptr), int(is_f64), T, Z, Y, X))
+        self._keep.append(keepalive)
+
+    def clear_field(self, slot: int):
+        check(self._lib.pb_field_clear(self._h, slot))
+
+    # -- particles -----------------------------------------------------------------------------
+    def upload_particles(self, d: dict, ei_last: np.ndarray):
+        n = d["x"].shape[0]
+        for k, dt in (("x", np.float32), ("y", np.float32), ("z", np.float32), ("t", np.float64), ("state", np.int32)):
+            if d[k].dtype != dt:
+                raise TypeError(f"particle variable {k!r} must be {np.dtype(dt).name} (default Particle), got {d[k].dtype}")
+        check(
+            self._lib.pb_particles_upload(
+                self._h, n, ptr(d["x"]), ptr(d["y"]), ptr(d["z"]), ptr(d["dx"]), ptr(d["dy"]), ptr(d["dz"]), ptr(d["t"]),
+                ptr(d["state"]), ptr(ei_last), ptr(d["particle_id"]),
+            )
+        )  # fmt: skip
+
+    def download_particles(self, d: dict, ei_last: np.ndarray):
+        n = d["x"].shape[0]
+        check(
+            self._lib.pb_particles_download(
+                self._h, n, ptr(d["x"]), ptr(d["y"]), ptr(d["z"]), ptr(d["dx"]), ptr(d["dy"]), ptr(d["dz"]), ptr(d["t"]),
+                ptr(d["state"]), ptr(ei_last),
+            )
+        )  # fmt: skip
+
+    def snapshot(self):
+        check(self._lib.pb_particles_snapshot(self._h))
+
+    def restore(self):
+        check(self._lib.pb_particles_restore(self._h))
+
+    def synchronize(self):
+        check(self._lib.pb_engine_synchronize(self._h))
+
+    def timer_begin(self):
+        check(self._lib.pb_timer_begin(self._h))
+
+    def timer_end_ms(self) -> float:
+        ms = C.c_float()
+        check(self._lib.pb_timer_end_ms(self._h, C.byref(ms)))
+        return float(ms.value)
+
+    # -- hot path --------------------------------------------------------------------------------
+    @staticmethod
+    def make_args(scheme, dt, endtime, *, diffusion=False, delete_on_error=False, kh=(0.0, 0.0), kh_spherical=False,
+                  kh_deg2m=1.0, seed=0, rng_call=0, max_iters=-1) -> AdvectArgs:  # fmt: skip
+        return AdvectArgs(int(scheme), int(diffusion), int(delete_on_error), int(kh_spherical), float(dt), float(endtime),
+                          float(kh[0]), float(kh[1]), float(kh_deg2m), int(seed), int(rng_call), int(max_iters))  # fmt: skip
+
+    def advect(self, args: AdvectArgs) -> dict:
+        rep = Report()
+        check(self._lib.pb_advect(self._h, C.byref(args), C.byref(rep)))
+        return _report_dict(rep)
+
+    def advect_async(self, args: AdvectArgs):
+        check(self._lib.pb_advect_async(self._h, C.byref(args)))
+
+    def last_report(self) -> dict:
+        rep = Report()
+        check(self._lib.pb_last_report(self._h, C.byref(rep)))
+        return _report_dict(rep)
+
+    def flag_view_outside_time(self, dt, endtime):
+        check(self._lib.pb_flag_view_outside_time(self._h, float(dt), float(endtime)))
+
+    def debug_normals(self, seed, rng_call, it, particle_id):
+        pid = np.ascontiguousarray(particle_id, dtype=np.int64)
+        out = np.empty((pid.size, 2), dtype=np.float64)
+        check(self._lib.pb_debug_normals(self._h, int(seed), int(rng_call), int(it), pid.size, ptr(pid), ptr(out)))
+        return out

@@ -1,0 +1,178 @@
+"""Host-side mirror of the reference's ``FieldSet`` / ``Field`` / ``VectorField`` / ``XGrid``
+for the hot path: it only *describes* the arrays; the velocity data itself is pinned in HBM by
+the engine the first time a ParticleSet executes on it (reference: ``_core/fieldset.py``,
+``_core/field.py``, ``_core/xgrid.py``, ``_core/model.py``).
+"""
+
+from __future__ import annotations
+
+import numpy as np
+
+from .engine import Engine
+
+EARTH_RADIUS = 6366707.019493707  # reference _core/mesh.py:6
+
+__all__ = ["Field", "FieldSet", "VectorField", "XGrid"]
+
+
+def _to_seconds(time):
+    """time axis -> (float64 seconds since the first level, origin) (reference index_search.py:88)."""
+    if time is None:
+        return None, None
+    time = np.asarray(time)
+    if time.size < 2:  # a single level is "no time dimension" (model.py:511-515)
+        return None, None
+    if np.issubdtype(time.dtype, np.datetime64) or np.issubdtype(time.dtype, np.timedelta64):
+        sec = ((time - time[0]) / np.timedelta64(1, "s")).astype(np.float64)
+        return sec, time[0]
+    sec = time.astype(np.float64)
+    return sec - sec[0], sec[0]
+
+
+class XGrid:
+    """Structured grid (rectilinear: 1-D lon/lat; depth optional).  ``xdim/ydim/zdim`` are cell
+    counts as in the reference (``_core/xgrid.py:21-24,208-231``); they default to nodes - 1,
+    which is what LOW/HIGH SGRID padding gives."""
+
+    def __init__(self, lon, lat, depth=None, mesh="spherical", radius=None, xdim=None, ydim=None, zdim=None):
+        self.lon = np.asarray(lon)
+        self.lat = np.asarray(lat)
+        self.depth = None if depth is None else np.asarray(depth)
+        if self.lon.ndim != 1 or self.lat.ndim != 1:
+            raise NotImplementedError("curvilinear (2-D lon/lat) grids are not on this engine yet")
+        if mesh not in ("flat", "spherical"):
+            raise ValueError(f"mesh must be 'flat' or 'spherical'. Got {mesh!r}")
+        self.mesh = mesh
+        self.radius = (EARTH_RADIUS if radius is None else radius) if mesh == "spherical" else None
+        self.xdim = self.lon.size - 1 if xdim is None else xdim
+        self.ydim = self.lat.size - 1 if ydim is None else ydim
+        self.zdim = None if self.depth is None else (self.depth.size - 1 if zdim is None else zdim)
+
+    def is_spherical(self):
+        return self.mesh == "spherical"
+
+    @property
+    def deg2m(self):  # reference _core/xgrid.py:201-206, _core/mesh.py:37-40
+        return self.radius * np.pi / 180.0 if self.mesh == "spherical" else 1.0
+
+    @property
+    def axes(self):
+        return (["Z"] if self.depth is not None else []) + ["Y", "X"]
+
+
+class Field:
+    def __init__(self, name, data, grid, fieldset):
+        self.name = name
+        self.data = data
+        self.grid = grid
+        self._fieldset = fieldset
+
+
+class VectorField:
+    def __init__(self, name, U, V, W=None):
+        self.name, self.U, self.V, self.W = name, U, V, W
+        self.grid = U.grid
+        self.vector_type = "3D" if W is not None else "2D"
+
+
+class _ConstantGrid:
+    """Grid of the constant fields (reference _core/model.py:292-318): one node, own mesh."""
+
+    def __init__(self, mesh):
+        self.mesh = mesh
+
+    def is_spherical(self):
+        return self.mesh == "spherical"
+
+    @property
+    def deg2m(self):
+        return EARTH_RADIUS * np.pi / 180.0 if self.mesh == "spherical" else 1.0
+
+
+class FieldSet:
+    """Velocity fields U, V (, W) laid out (T, Z, Y, X) on one A-grid, plus constant fields.
+
+    Build with :meth:`from_arrays` (NumPy arrays) or ``parcels_b200.adapter.from_parcels`` (a
+    FieldSet of the reference package).  Time is float seconds or datetime64/timedelta64.
+    """
+
+    def __init__(self, grid: XGrid, U, V, W=None, time=None, interp_method="linear"):
+        if interp_method != "linear":
+            raise NotImplementedError(f"interp_method {interp_method!r}: only XLinear_Velocity ('linear') is on this engine")
+        self.grid = grid
+        self.fields = {}
+        self.constants = {}
+        self.context = {}
+        self._const_grid = None
+        self._time_s, self._time_origin = _to_seconds(time)
+        for name, arr in (("U", U), ("V", V), ("W", W)):
+            if arr is None:
+                continue
+            arr = np.asarray(arr)
+            if arr.ndim != 4:
+                raise ValueError(f"{name} must be laid out (T, Z, Y, X); got shape {arr.shape}")
+            self.fields[name] = Field(name, arr, grid, self)
+        self.U, self.V, self.W = self.fields["U"], self.fields["V"], self.fields.get("W")
+        self.UV = VectorField("UV", self.U, self.V)
+        self.fields["UV"] = self.UV
+        if self.W is not None:
+            self.UVW = VectorField("UVW", self.U, self.V, self.W)
+            self.fields["UVW"] = self.UVW
+        T = self.U.data.shape[0]
+        if self._time_s is not None and T != self._time_s.size:
+            raise ValueError(f"time axis has {self._time_s.size} levels but U has {T}")
+        if self._time_s is None and T != 1:
+            raise ValueError("fields with more than one time level need a time axis")
+        self._engines: dict[int, Engine] = {}
+
+    @classmethod
+    def from_arrays(cls, *, lon, lat, U, V, W=None, depth=None, time=None, mesh="spherical", radius=None, **kw):
+        return cls(XGrid(lon, lat, depth, mesh=mesh, radius=radius, **kw), U, V, W, time=time)
+
+    # -- reference API surface used on this path -----------------------------------------------
+    @property
+    def time_interval(self):
+        """(left, right) in float seconds since the interval start, or None (reference TimeInterval)."""
+        if self._time_s is None:
+            return None
+        return (0.0, float(self._time_s[-1]))
+
+    @property
+    def gridset(self):
+        return [self.grid] + ([self._const_grid] if self._const_grid is not None else [])
+
+    def add_constant_field(self, name, value, mesh="spherical"):
+        """reference _core/fieldset.py:175-205."""
+        if mesh not in ("flat", "spherical"):
+            raise ValueError(f"mesh must be one of ['flat', 'spherical']. Got {mesh!r}.")
+        if self._const_grid is None:
+            self._const_grid = _ConstantGrid(mesh)
+        elif self._const_grid.mesh != mesh:
+            raise NotImplementedError("constant fields on two different meshes")
+        self.constants[name] = float(np.full((1, 1, 1, 1), value)[0, 0, 0, 0])
+        f = Field(name, np.full((1, 1, 1, 1), value), self._const_grid, self)
+        self.fields[name] = f
+        setattr(self, name, f)
+
+    def add_context(self, name, value):
+        if name in self.context:
+            raise ValueError(f"FieldSet already has a context with name '{name}'")
+        self.context[name] = value
+
+    # -- engine management: fields are uploaded once and stay resident in HBM --------------------
+    def engine(self, device: int = 0) -> Engine:
+        eng = self._engines.get(device)
+        if eng is None:
+            eng = Engine(device)
+            g = self.grid
+            eng.upload_rectilinear_grid(g.lon, g.lat, g.depth, self._time_s, g.is_spherical(), g.deg2m, g.xdim, g.ydim, g.zdim)
+            for slot, name in enumerate(("U", "V", "W")):
+                if name in self.fields:
+                    eng.upload_field(slot, self.fields[name].data)
+            self._engines[device] = eng
+        return eng
+
+    def release(self):
+        for e in self._engines.values():
+            e.close()
+        self._engines.clear()

@@ -1,0 +1,66 @@
+"""Built-in kernels, by the reference's names (``parcels.kernels``).
+
+On this engine a built-in kernel is a *token*: ``ParticleSet.execute`` recognises the function
+(by identity or, for the reference's own function objects, by ``__name__``), and the whole
+kernel list is lowered to ONE fused CUDA kernel that runs the per-particle time loop on the GPU
+(``csrc/engine.cu``).  The bodies below never run -- there is no CPU path in this package.
+"""
+
+from __future__ import annotations
+
+__all__ = [
+    "AdvectionEE",
+    "AdvectionRK2",
+    "AdvectionRK2_3D",
+    "AdvectionRK4",
+    "AdvectionRK4_3D",
+    "DeleteParticle",
+    "DiffusionUniformKh",
+]
+
+
+def _device_only(name):
+    raise RuntimeError(
+        f"{name} is a device kernel token: pass it to ParticleSet.execute(); parcels_b200 has no CPU implementation."
+    )
+
+
+def AdvectionEE(particles, fieldset):  # reference kernels/_advection.py:78-82
+    """Explicit Euler advection of (x, y) with fieldset.UV."""
+    _device_only("AdvectionEE")
+
+
+def AdvectionRK2(particles, fieldset):  # reference kernels/_advection.py:20-27
+    """Second-order Runge-Kutta advection of (x, y) with fieldset.UV."""
+    _device_only("AdvectionRK2")
+
+
+def AdvectionRK2_3D(particles, fieldset):  # reference kernels/_advection.py:30-39
+    """Second-order Runge-Kutta advection of (x, y, z) with fieldset.UVW."""
+    _device_only("AdvectionRK2_3D")
+
+
+def AdvectionRK4(particles, fieldset):  # reference kernels/_advection.py:42-55
+    """Fourth-order Runge-Kutta advection of (x, y) with fieldset.UV."""
+    _device_only("AdvectionRK4")
+
+
+def AdvectionRK4_3D(particles, fieldset):  # reference kernels/_advection.py:58-75
+    """Fourth-order Runge-Kutta advection of (x, y, z) with fieldset.UVW."""
+    _device_only("AdvectionRK4_3D")
+
+
+def DiffusionUniformKh(particles, fieldset):  # reference kernels/_advectiondiffusion.py:120-153
+    """Uniform-Kh Brownian displacement; needs constant fields Kh_zonal and Kh_meridional."""
+    _device_only("DiffusionUniformKh")
+
+
+def DeleteParticle(particles, fieldset):
+    """Error handler of the reference's tests (tests/common_kernels.py:12-13): every particle whose
+    state is an error (>= 50) is marked Delete.  Must be the LAST kernel of the list."""
+    _device_only("DeleteParticle")
+
+
+# scheme ids of include/parcels_b200.h (enum pb_scheme)
+SCHEMES = {"AdvectionEE": 1, "AdvectionRK2": 2, "AdvectionRK2_3D": 3, "AdvectionRK4": 4, "AdvectionRK4_3D": 5}
+SCHEMES_3D = {"AdvectionRK2_3D", "AdvectionRK4_3D"}

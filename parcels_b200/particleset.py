@@ -1,0 +1,246 @@
+"""``ParticleSet`` with the reference's constructor / ``execute`` API (``_core/particleset.py``)
+whose inner loop -- ``Kernel.execute`` (``_core/kernel.py:174-247``) -- runs on the GPU.
+
+Host code here is control only: argument normalisation, the outer loop over output
+intervals, error mapping and compaction of deleted particles.  It never computes a
+trajectory; if the CUDA library or a GPU is missing, ``execute`` raises.
+"""
+
+from __future__ import annotations
+
+import datetime
+import types
+
+import numpy as np
+
+from . import kernels as K
+from .particle import Particle, create_particle_data
+from .statuscodes import ERRORS_TO_THROW, StatusCode, raise_for_state
+
+__all__ = ["ParticleSet"]
+
+
+def _to_float_seconds(v):
+    """reference _core/utils/time.py:192-207."""
+    if isinstance(v, datetime.timedelta):
+        return v.total_seconds()
+    if isinstance(v, np.timedelta64):
+        return float(v / np.timedelta64(1, "s"))
+    return float(v)
+
+
+class KernelPlan:
+    """The kernel list lowered to the fused device kernel's switches (include/parcels_b200.h)."""
+
+    def __init__(self, kernel_list, fieldset):
+        if isinstance(kernel_list, types.FunctionType):
+            kernel_list = [kernel_list]
+        if not isinstance(kernel_list, list):
+            raise ValueError(f"kernels must be a list. Got {kernel_list=!r}")
+        if len(kernel_list) == 0:
+            raise ValueError("List of `kernels` should have at least one function.")
+        names = []
+        for f in kernel_list:
+            if not isinstance(f, types.FunctionType):
+                raise TypeError(f"Argument `kernels` should be a function or list of functions. Got {type(f)}")
+            names.append(f.__name__)
+        self.funcname = "".join(names)
+        self.delete_on_error = False
+        if names[-1] == "DeleteParticle":
+            self.delete_on_error = True
+            names = names[:-1]
+        self.diffusion = False
+        if names and names[-1] == "DiffusionUniformKh":
+            self.diffusion = True
+            names = names[:-1]
+        if len(names) != 1 or names[0] not in K.SCHEMES:
+            raise NotImplementedError(
+                f"kernel list {[f.__name__ for f in kernel_list]} is not lowered to the GPU engine: supported lists are "
+                "[Advection{EE,RK2,RK2_3D,RK4,RK4_3D}] (+ DiffusionUniformKh) (+ DeleteParticle). "
+                "parcels_b200 has no CPU fallback for user kernels."
+            )
+        self.scheme_name = names[0]
+        self.scheme = K.SCHEMES[names[0]]
+        if names[0] in K.SCHEMES_3D and fieldset.W is None:
+            raise AttributeError("FieldSet has no UVW VectorField (no W field) for a 3-D advection kernel")
+        self.kh = (0.0, 0.0)
+        self.kh_spherical = False
+        self.kh_deg2m = 1.0
+        if self.diffusion:
+            try:
+                self.kh = (fieldset.constants["Kh_zonal"], fieldset.constants["Kh_meridional"])
+            except KeyError as e:
+                raise AttributeError("DiffusionUniformKh needs constant fields Kh_zonal and Kh_meridional") from e
+            g = fieldset.Kh_zonal.grid
+            self.kh_spherical = g.is_spherical()
+            self.kh_deg2m = g.deg2m
+
+
+class ParticleSet:
+    """Same construction arguments as the reference (``_core/particleset.py:59-137``):
+    ``ParticleSet(fieldset, pclass=Particle, t=, z=, y=, x=, particle_ids=)``; ``t`` may be
+    float seconds, timedelta64 or (with a datetime time axis) datetime64."""
+
+    def __init__(self, fieldset, pclass=Particle, *, t=None, z=None, y=None, x=None, particle_ids=None, device=0,
+                 seed=0):  # fmt: skip
+        if pclass is not Particle:
+            raise NotImplementedError("only the default Particle (float32 positions) is supported on the engine")
+        self.fieldset = fieldset
+        self._pclass = pclass
+        self.device = device
+        self.seed = int(seed)  # Philox key of the Wiener increments (DiffusionUniformKh)
+        self._rng_call = 0
+        self.last_report = None
+        y = np.empty(0) if y is None else np.array(y).flatten()
+        x = np.empty(0) if x is None else np.array(x).flatten()
+        if particle_ids is None:
+            particle_ids = np.arange(x.size)
+        if z is None:
+            depth = fieldset.grid.depth
+            if depth is not None and depth.size:
+                z = np.ones(x.size) * depth[np.argmin(np.abs(depth))]
+            else:
+                z = np.zeros(x.size)
+        else:
+            z = np.array(z).flatten()
+        assert x.size == y.size and x.size == z.size, "x, y, z don't all have the same lengths"
+        if t is None or np.size(t) == 0:
+            t = np.array(np.nan)
+        else:
+            t = np.array(t).flatten()
+            if np.issubdtype(t.dtype, np.datetime64):
+                t = ((t - fieldset._time_origin) / np.timedelta64(1, "s")).astype(np.float64)
+            elif np.issubdtype(t.dtype, np.timedelta64):
+                t = (t / np.timedelta64(1, "s")).astype(np.float64)
+            else:
+                t = t.astype(np.float64)
+        t = np.repeat(t, x.size) if t.size == 1 else t
+        assert x.size == t.size, "t and positions (x, y, z) do not have the same lengths."
+        self._data = create_particle_data(
+            nparticles=x.size,
+            ngrids=len(fieldset.gridset),
+            initial=dict(t=t, z=z, y=y, x=x, particle_id=np.asarray(particle_ids)),
+        )
+
+    # -- container protocol ----------------------------------------------------------------------
+    def __len__(self):
+        return len(self._data["x"])
+
+    def __getattr__(self, name):
+        data = self.__dict__.get("_data")
+        if data is not None and name in data:
+            return data[name]
+        raise AttributeError(name)
+
+    @property
+    def size(self):
+        return len(self)
+
+    def remove_indices(self, indices):
+        """reference _core/particleset.py:247-250."""
+        for k in self._data:
+            self._data[k] = np.delete(self._data[k], indices, axis=0)
+
+    # -- the hot path ------------------------------------------------------------------------------
+    def _kernel_execute(self, plan: KernelPlan, endtime: float, dt: float):
+        """Replaces ``Kernel.execute(pset, endtime, dt)`` (reference _core/kernel.py:174-247)."""
+        d = self._data
+        n = len(self)
+        d["state"][:] = StatusCode.Evaluate
+        if n == 0:
+            return
+        if np.isnan(d["t"]).any():
+            bad = np.where(np.isnan(d["t"]))[0]
+            raise ValueError(f"Time values for particles with indices {bad} cannot be NaN.")  # field.py:396-398
+        eng = self.fieldset.engine(self.device)
+        ei_last = np.ascontiguousarray(d["ei"][:, -1])
+        self._rng_call += 1
+
+        def args(max_iters=-1):
+            return eng.make_args(plan.scheme, dt, endtime, diffusion=plan.diffusion, delete_on_error=plan.delete_on_error,
+                                 kh=plan.kh, kh_spherical=plan.kh_spherical, kh_deg2m=plan.kh_deg2m, seed=self.seed,
+                                 rng_call=self._rng_call, max_iters=max_iters)  # fmt: skip
+
+        eng.upload_particles(d, ei_last)
+        rep = eng.advect(args())
+        if rep["n_error"] > 0:
+            # The reference stops the whole set at the END of the first loop iteration in which any
+            # particle is in an error state (kernel.py:239-245).  Replay from the host copy up to and
+            # including that iteration so every particle is left exactly where the reference leaves it.
+            k = rep["first_error_iter"]
+            eng.upload_particles(d, ei_last)
+            rep = eng.advect(args(max_iters=k + 1))
+            if rep["n_out_of_time"] > 0:
+                # an out-of-interval sample flags the WHOLE evaluated view (index_search.py:85-86, field.py:31-44)
+                eng.upload_particles(d, ei_last)
+                eng.advect(args(max_iters=k))
+                eng.flag_view_outside_time(dt, endtime)
+        self.last_report = rep
+        eng.download_particles(d, ei_last)
+        d["ei"][:, -1] = ei_last
+        d["dt"][:] = dt  # kernel.py:225-226
+        dele = np.where(d["state"] == StatusCode.Delete)[0]
+        if len(dele) > 0:
+            self.remove_indices(dele)
+            d = self._data
+        for code in ERRORS_TO_THROW:
+            hit = d["state"] == code
+            if np.any(hit):
+                raise_for_state(code, d["z"][hit], d["y"][hit], d["x"][hit], d["t"][hit])
+
+    def execute(self, kernels, dt, endtime=None, runtime=None, output_file=None, verbose_progress=False):
+        """reference _core/particleset.py:355-470 (outer loop) and :497-585 (argument handling)."""
+        if len(self) == 0:
+            return
+        plan = KernelPlan(kernels, self.fieldset)
+        try:
+            dt = _to_float_seconds(dt)
+            sign_dt = int(np.sign(dt))
+            assert sign_dt in (-1, 1)
+        except (ValueError, TypeError, AssertionError) as e:
+            raise ValueError(f"dt must be a non-zero datetime.timedelta or np.timedelta64 object, got {dt=!r}") from e
+        self._data["dt"][:] = dt
+        if runtime is not None:
+            runtime = _to_float_seconds(runtime)
+            if runtime < 0:
+                raise ValueError(f"The runtime must be a non-negative timedelta or float. Got {runtime=!r}")
+        ti = self.fieldset.time_interval
+        if runtime is not None and endtime is not None:
+            raise ValueError(f"runtime and endtime are mutually exclusive - provide one or the other. Got {runtime=!r}, {endtime=!r}")
+        if runtime is None and ti is None:
+            raise ValueError("The runtime must be provided when the time_interval is not defined for a fieldset.")
+        if runtime is None and endtime is None:
+            raise ValueError("Either runtime or endtime must be provided.")
+        t = self._data["t"]
+        first = (np.nanmin(t) if sign_dt == 1 else np.nanmax(t)) if not np.isnan(t).all() else np.nan
+        if endtime is not None:
+            if isinstance(endtime, np.datetime64):
+                endtime = float((endtime - self.fieldset._time_origin) / np.timedelta64(1, "s"))
+            else:
+                endtime = _to_float_seconds(endtime)
+            if ti is not None and not (ti[0] <= endtime <= ti[1]):
+                raise ValueError(f"Calculated/provided end time of {endtime!r} is not in fieldset time interval {ti!r}.")
+        if np.isnan(first):
+            start_time = 0.0 if sign_dt == 1 else float(ti[1] if ti is not None else runtime)
+        else:
+            start_time = float(first)
+        end_time = endtime if endtime is not None else start_time + sign_dt * runtime
+        if np.isnan(t).any():
+            t[:] = start_time
+        outputdt = _to_float_seconds(output_file.outputdt) if output_file is not None else None
+        next_output = None
+        if output_file is not None:
+            output_file.write(self, start_time)
+            next_output = start_time + outputdt * sign_dt
+        time = start_time
+        while sign_dt * (time - end_time) < 0:
+            if next_output is not None:
+                next_time = min(next_output, end_time) if sign_dt > 0 else max(next_output, end_time)
+            else:
+                next_time = end_time
+            self._kernel_execute(plan, next_time, dt)
+            if next_output is not None and np.abs(next_time - next_output) < 0.001:
+                output_file.write(self, next_output)
+                if np.isfinite(outputdt):
+                    next_output += outputdt * sign_dt
+            time = next_time

@@ -1,0 +1,126 @@
+"""CPU tests of the boundary and the host logic (no GPU, no compute calls):
+the C-ABI library loads and exports every symbol include/parcels_b200.h declares, the host
+mirror validates arguments like the reference, and the product fails loudly without a GPU."""
+
+import os
+import re
+
+import numpy as np
+import pytest
+
+import parcels_b200 as pb
+from parcels_b200 import _lib
+from parcels_b200.particleset import KernelPlan
+from philox_ref import philox4x32_10, wiener_normals
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module", autouse=True)
+def built():
+    from parcels_b200 import build
+
+    build.build()
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "parcels_b200.h")).read()
+    declared = set(re.findall(r"\b(pb_[a-z_0-9]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    lib = _lib.load()
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    assert lib.pb_abi_version() == 1
+
+
+def test_struct_layouts_match_header():
+    import ctypes
+
+    assert ctypes.sizeof(_lib.AdvectArgs) == 4 * 4 + 5 * 8 + 2 * 8 + 8
+    assert ctypes.sizeof(_lib.Report) == 7 * 8 + 2 * 4 + 2 * 4
+
+
+def _fs(with_w=True):
+    z = np.zeros((2, 3, 4, 5), np.float32)
+    return pb.FieldSet.from_arrays(lon=np.linspace(0, 1, 5), lat=np.linspace(0, 1, 4), depth=np.linspace(0, 1, 3),
+                                   time=np.array([0.0, 10.0]), U=z, V=z, W=z if with_w else None, mesh="flat")  # fmt: skip
+
+
+def test_kernel_plan_lowering():
+    fs = _fs()
+    p = KernelPlan([pb.AdvectionRK4_3D, pb.DeleteParticle], fs)
+    assert (p.scheme, p.diffusion, p.delete_on_error) == (5, False, True)
+    fs.add_constant_field("Kh_zonal", 100, mesh="flat")
+    fs.add_constant_field("Kh_meridional", 50, mesh="flat")
+    p = KernelPlan([pb.AdvectionRK4, pb.DiffusionUniformKh], fs)
+    assert (p.scheme, p.diffusion, p.delete_on_error, p.kh) == (4, True, False, (100.0, 50.0))
+    assert len(fs.gridset) == 2  # constant fields live on their own grid => ei has 2 columns
+
+
+def test_kernel_plan_rejects_user_kernels_loudly():
+    def MyKernel(particles, fieldset):
+        pass
+
+    with pytest.raises(NotImplementedError, match="no CPU fallback"):
+        KernelPlan([pb.AdvectionRK4, MyKernel], _fs())
+    with pytest.raises(TypeError):
+        KernelPlan([1], _fs())
+    with pytest.raises(ValueError):
+        KernelPlan([], _fs())
+    with pytest.raises(AttributeError):
+        KernelPlan([pb.AdvectionRK4_3D], _fs(with_w=False))
+
+
+def test_builtin_kernels_have_no_cpu_body():
+    with pytest.raises(RuntimeError, match="no CPU implementation"):
+        pb.AdvectionRK4(None, None)
+
+
+def test_particleset_layout_matches_reference_default_particle():
+    ps = pb.ParticleSet(_fs(), x=[0.1, 0.2], y=[0.1, 0.2], z=[0.5, 0.5], t=np.array([0.0, 1.0]))
+    d = ps._data
+    assert {k: v.dtype for k, v in d.items()} == {
+        "ei": np.int32, "t": np.float64, "z": np.float32, "y": np.float32, "x": np.float32, "particle_id": np.int64,
+        "dz": np.float32, "dy": np.float32, "dx": np.float32, "dt": np.float64, "state": np.int32,
+    }  # fmt: skip
+    assert d["ei"].shape == (2, 1) and (d["state"] == pb.StatusCode.Evaluate).all()
+
+
+def test_execute_argument_validation():
+    ps = pb.ParticleSet(_fs(), x=[0.1], y=[0.1], z=[0.5], t=[0.0])
+    with pytest.raises(ValueError, match="mutually exclusive"):
+        ps.execute(pb.AdvectionRK4, dt=1.0, runtime=1.0, endtime=2.0)
+    with pytest.raises(ValueError, match="non-zero"):
+        ps.execute(pb.AdvectionRK4, dt=0.0, runtime=1.0)
+    with pytest.raises(ValueError, match="Either runtime or endtime"):
+        ps.execute(pb.AdvectionRK4, dt=1.0)
+    with pytest.raises(ValueError, match="not in fieldset time interval"):
+        ps.execute(pb.AdvectionRK4, dt=1.0, endtime=100.0)
+
+
+def test_no_gpu_means_loud_failure_not_fallback():
+    if _lib.load().pb_device_count() > 0:
+        pytest.skip("a GPU is present")
+    ps = pb.ParticleSet(_fs(), x=[0.1], y=[0.1], z=[0.5], t=[0.0])
+    with pytest.raises(_lib.EngineError, match="no CPU fallback"):
+        ps.execute(pb.AdvectionRK4, dt=1.0, runtime=2.0)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "parcels_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src and "parcels_oracle" not in src, f
+
+
+def test_philox_known_answer():
+    """Random123 known-answer vectors for philox4x32-10."""
+    out = philox4x32_10([0], [0], [0], [0], 0, 0)
+    assert [int(o[0]) for o in out] == [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]
+    out = philox4x32_10([0xFFFFFFFF], [0xFFFFFFFF], [0xFFFFFFFF], [0xFFFFFFFF], 0xFFFFFFFF, 0xFFFFFFFF)
+    assert [int(o[0]) for o in out] == [0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD]
+    zx, zy = wiener_normals(7, 1, 0, np.arange(200000))
+    assert abs(zx.mean()) < 0.01 and abs(zy.std() - 1) < 0.01
