@@ -95,7 +95,7 @@ class ClockSampler:
                     self.samples.append([s.strip() for s in out.split(",")])
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            self._stop.wait(0.05)
 
     def __enter__(self):
         self._t.start()
@@ -197,7 +197,7 @@ def run_reference_arm(a, field, dt, nsteps, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=list(WORKLOADS))

@@ -1,0 +1,55 @@
+"""Build the engine's host mirror from a live FieldSet / ParticleSet of the reference package.
+
+Reads only public attributes of the reference objects (``fieldset.U.data``, ``field.grid.lon``,
+``grid._mesh``, ``grid.xdim`` ...; reference ``_core/field.py``, ``_core/xgrid.py``), so it works with
+the real xarray-backed objects and with any duck type exposing the same attributes.  Nothing here
+computes: it hands NumPy buffers to ``parcels_b200.FieldSet``.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+
+from .fieldset import FieldSet, XGrid
+from .particleset import ParticleSet
+
+SUPPORTED_VECTOR_INTERP = ("XLinear_Velocity",)
+
+
+def _values(da):
+    return np.asarray(getattr(da, "values", da))
+
+
+def from_parcels(ref_fieldset) -> FieldSet:
+    """reference FieldSet -> parcels_b200.FieldSet (rectilinear A-grid, XLinear_Velocity)."""
+    U = ref_fieldset.U
+    g = U.grid
+    vf = getattr(ref_fieldset, "UVW", None) or ref_fieldset.UV
+    interp = type(vf.interp_method).__name__
+    if interp not in SUPPORTED_VECTOR_INTERP:
+        raise NotImplementedError(f"vector interpolator {interp} is not on the engine (supported: {SUPPORTED_VECTOR_INTERP})")
+    lon, lat = np.asarray(g.lon), np.asarray(g.lat)
+    if lon.ndim != 1:
+        raise NotImplementedError("curvilinear grids are not on the engine yet")
+    axes = list(g.axes)
+    depth = np.asarray(g.depth) if "Z" in axes else None
+    spherical = g._mesh.is_spherical()
+    grid = XGrid(lon, lat, depth, mesh="spherical" if spherical else "flat", radius=getattr(g._mesh, "radius", None),
+                 xdim=g.xdim, ydim=g.ydim, zdim=g.zdim if "Z" in axes else None)  # fmt: skip
+    time = None
+    if U.time_interval is not None:
+        time = _values(U.data.time)
+    W = getattr(ref_fieldset, "W", None)
+    fs = FieldSet(grid, _values(U.data), _values(ref_fieldset.V.data), None if W is None else _values(W.data), time=time)
+    for name, f in ref_fieldset.fields.items():
+        if type(getattr(f, "interp_method", None)).__name__ == "XConstantField":
+            fs.add_constant_field(name, float(_values(f.data)[0, 0, 0, 0]), mesh="spherical" if f.grid._mesh.is_spherical() else "flat")
+    return fs
+
+
+def pset_from_parcels(ref_pset, fieldset: FieldSet, **kw) -> ParticleSet:
+    """reference ParticleSet -> parcels_b200.ParticleSet sharing the SAME SoA arrays."""
+    d = ref_pset._data
+    ps = ParticleSet(fieldset, x=d["x"], y=d["y"], z=d["z"], t=d["t"], particle_ids=d["particle_id"], **kw)
+    ps._data = d  # share the reference's dict of ndarrays: results are written back in place
+    return ps
