@@ -314,6 +314,9 @@ def main():
     h2d = n * (6 * 4 + 8 + 4 + 4 + 8)
     d2h = n * (6 * 4 + 8 + 4 + 4)
 
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return
     peak, peak_src = measured_peak()

@@ -1,6 +1,7 @@
 /* parcels_b200.h -- C-ABI of libparcels_b200.so: the B200-native replacement for the hot path
  * ParticleSet.execute(AdvectionRK4 | AdvectionRK4_3D | AdvectionEE | AdvectionRK2[_3D]
- *                     [+ DiffusionUniformKh] [+ delete-on-error handler]).
+ *                     [+ DiffusionUniformKh] [+ delete-on-error handler])
+ * on rectilinear A-grids (XLinear_Velocity) and rectilinear / curvilinear C-grids (CGrid_Velocity).
  *
  * The reference (Parcels v4-alpha, pure Python/NumPy) has no FFI; this header DEFINES the
  * drop-in boundary.  Each entry point cites the reference interface it
@@ -79,6 +80,27 @@ int32_t pb_grid_upload_rectilinear(pb_engine* e, const void* lon, int64_t nx, co
                                    const double* time_s, int64_t nt, int32_t spherical, double deg2m,
                                    int64_t xdim_cells, int64_t ydim_cells, int64_t zdim_cells);
 
+/* Curvilinear grid: 2-D node coordinates lon2d/lat2d of shape (ny, nx), C-contiguous.  Cell search =
+ * hint test + spatial-hash fallback (_core/index_search.py:94-295).  The hash table is the CSR table
+ * of _core/spatialhash.py:269-387 (unique Morton keys ascending, per-key start/count, flat face ids
+ * j*(nx-1)+i ascending within a key), built ONCE on the host (parcels_b200/spatialhash.py) so that the
+ * candidate order -- "first containing face wins", :511-535 -- is the reference's; hash_box6 =
+ * (xmin, xmax, ymin, ymax, zmin, zmax) of the hash grid, hash_bitwidth the quantisation (:212-228).
+ * The query itself runs on the device. */
+int32_t pb_grid_upload_curvilinear(pb_engine* e, const void* lon2d, const void* lat2d, int64_t ny, int64_t nx,
+                                   const void* depth, int64_t nz, int32_t coord_is_f64, const double* time_s,
+                                   int64_t nt, int32_t spherical, double deg2m, int64_t xdim_cells,
+                                   int64_t ydim_cells, int64_t zdim_cells, const uint32_t* hash_keys,
+                                   const int64_t* hash_starts, const int64_t* hash_counts, int64_t n_keys,
+                                   const uint32_t* hash_faces, int64_t n_entries, const double* hash_box6,
+                                   int32_t hash_bitwidth);
+
+/* Vector interpolator of fieldset.UV / UVW (VectorField.interp_method, _core/field.py:236-246):
+ * XLinear_Velocity (A-grid, interpolators/_xinterpolators.py:169-190) or CGrid_Velocity (:193-332)
+ * with the SGRID staggering offsets of _get_offsets_dictionary (:99-109: 1 for LOW padding). */
+enum pb_interp { PB_INTERP_XLINEAR_VELOCITY = 0, PB_INTERP_CGRID_VELOCITY = 1 };
+int32_t pb_set_interpolation(pb_engine* e, int32_t method, int32_t off_x, int32_t off_y, int32_t off_z);
+
 /* ---- field data: replaces ModelData.field_data -> xarray .isel gathers -------------------
  * (_core/model.py:67-77, interpolators/_xinterpolators.py:25-96).  C-contiguous (T,Z,Y,X),
  * float32 or float64, NaNs already filled (model.py:135-143).  Size-1 dims are never indexed
@@ -123,6 +145,10 @@ typedef struct pb_advect_args {
     uint64_t rng_call;         /* counter word: index of this Kernel.execute call               */
     int64_t max_iters;         /* <0: run to endtime; >=0: at most this many loop iterations
                                   (used to replay up to the first error)    */
+    int32_t hint_all_zero;     /* curvilinear grids: 1 when the hinted xi (unravel of ei) of every
+                                  evaluated particle is 0 -- the reference then skips the hint test for
+                                  the whole batch at the first eval (_core/index_search.py:269-282)   */
+    int32_t reserved;
 } pb_advect_args;
 
 typedef struct pb_report {

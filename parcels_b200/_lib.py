@@ -32,6 +32,8 @@ class AdvectArgs(C.Structure):
         ("seed", C.c_uint64),
         ("rng_call", C.c_uint64),
         ("max_iters", C.c_int64),
+        ("hint_all_zero", C.c_int32),
+        ("reserved", C.c_int32),
     ]
 
 
@@ -67,6 +69,12 @@ SYMBOLS = {
         [_P, _P, C.c_int64, _P, C.c_int64, _P, C.c_int64, C.c_int32, _P, C.c_int64, C.c_int32, C.c_double,
          C.c_int64, C.c_int64, C.c_int64],
     ),  # fmt: skip
+    "pb_grid_upload_curvilinear": (
+        C.c_int32,
+        [_P, _P, _P, C.c_int64, C.c_int64, _P, C.c_int64, C.c_int32, _P, C.c_int64, C.c_int32, C.c_double, C.c_int64,
+         C.c_int64, C.c_int64, _P, _P, _P, C.c_int64, _P, C.c_int64, _P, C.c_int32],
+    ),  # fmt: skip
+    "pb_set_interpolation": (C.c_int32, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "pb_field_upload": (C.c_int32, [_P, C.c_int32, _P, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_int64]),
     "pb_field_attach_device": (C.c_int32, [_P, C.c_int32, _P, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_int64]),
     "pb_field_clear": (C.c_int32, [_P, C.c_int32]),

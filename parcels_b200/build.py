@@ -6,7 +6,9 @@ import os
 import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SRC = os.path.join(HERE, "csrc", "engine.cu")
+CSRC = os.path.join(HERE, "csrc")
+SOURCES = ["engine.cu", "agrid.cu", "cgrid.cu"]  # one translation unit per kernel family: compiled in parallel
+DEPS = [os.path.join(CSRC, f) for f in (*SOURCES, "common.cuh")]
 OUT = os.path.join(HERE, "lib", "libparcels_b200.so")
 HEADER = os.path.join(os.path.dirname(HERE), "include", "parcels_b200.h")
 
@@ -15,7 +17,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo",
     "-fmad=false",  # no FMA contraction: arithmetic must round exactly like the reference's NumPy ops
-    "-Xcompiler", "-fPIC", "-shared",
+    "-Xcompiler", "-fPIC",
 ]  # fmt: skip
 
 
@@ -23,7 +25,7 @@ def needs_build() -> bool:
     if not os.path.exists(OUT):
         return True
     t = os.path.getmtime(OUT)
-    return any(os.path.getmtime(f) > t for f in (SRC, HEADER, __file__))
+    return any(os.path.getmtime(f) > t for f in (*DEPS, HEADER, __file__))
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -31,12 +33,25 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return OUT
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc, *NVCC_FLAGS, *(["-Xptxas", "-v"] if verbose else []), "-o", OUT, SRC]
+    objdir = os.path.join(HERE, "lib", "obj")
+    os.makedirs(objdir, exist_ok=True)
+    procs = []
+    for src in SOURCES:
+        obj = os.path.join(objdir, src.replace(".cu", ".o"))
+        cmd = [nvcc, *NVCC_FLAGS, *(["-Xptxas", "-v"] if verbose else []), "-c", "-o", obj, os.path.join(CSRC, src)]
+        procs.append((cmd, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)))
+    objs = []
+    for cmd, obj, p in procs:
+        out, err = p.communicate()
+        if p.returncode != 0:
+            raise RuntimeError(f"nvcc failed:\n{' '.join(cmd)}\n{out}\n{err}")
+        if verbose:
+            print(err)
+        objs.append(obj)
+    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", OUT, *objs]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
-        raise RuntimeError(f"nvcc failed:\n{' '.join(cmd)}\n{res.stdout}\n{res.stderr}")
-    if verbose:
-        print(res.stderr)
+        raise RuntimeError(f"link failed:\n{' '.join(cmd)}\n{res.stdout}\n{res.stderr}")
     return OUT
 
 

@@ -1,0 +1,449 @@
+// cgrid.cu -- C-grid policy of advect_kernel: CGrid_Velocity on rectilinear and curvilinear grids
+// (reference interpolators/_xinterpolators.py:193-332), the curvilinear cell search with hint
+// (_core/index_search.py:94-295) and the device-side spatial-hash query (_core/spatialhash.py:389-535;
+// the table is built once on the host and uploaded).
+//
+// Per particle, in registers: the current cell (yi, xi), its 4 corner lon/lat, on spherical
+// curvilinear meshes the cell's tangent-plane basis and projected corners, and the 2 faces x 2
+// time levels of U, V, W that CGrid_Velocity reads.  Everything is re-gathered from HBM only when the
+// particle changes cell / time level.
+#include "common.cuh"
+
+// np.remainder for a positive divisor (floored modulo), in the array dtype
+__device__ __forceinline__ float mod_np(float a, float b) {
+    float r = fmodf(a, b);
+    if (r != 0.f) { if (r < 0.f) r += b; } else r = copysignf(0.f, b);
+    return r;
+}
+__device__ __forceinline__ double mod_np(double a, double b) {
+    double r = fmod(a, b);
+    if (r != 0.0) { if (r < 0.0) r += b; } else r = copysign(0.0, b);
+    return r;
+}
+__device__ __forceinline__ float sqrt_np(float x) { return sqrtf(x); }
+__device__ __forceinline__ double sqrt_np(double x) { return sqrt(x); }
+__device__ __forceinline__ float sin_np(float x) { return sinf(x); }
+__device__ __forceinline__ double sin_np(double x) { return sin(x); }
+
+template <class A, class D>
+struct CGridCtx {
+    AxisCell<A> cz, cy, cx;  // cy, cx: rectilinear grids only
+    AxisCell<double> ct;
+    int yi, xi;              // horizontal cell of the last search (curvilinear: -3 after a failed search)
+    int kyi, kxi;            // cell whose corners are cached below (INT_MIN: none)
+    A clon[4], clat[4];      // raw corner lon/lat, CCW from (yi, xi)
+    double pu[4], pv[4];     // spherical curvilinear: corners projected on the cell's tangent plane
+    double eu[3], ev[3];     //                        orthonormal basis of that plane
+    int fti, fzi, fyi, fxi;  // key of the cached face values
+    D fu[4], fv[4], fw[4];   // [time level * 2 + face]
+    int state, ei;
+    unsigned int refills;
+    bool out_of_time;
+};
+
+// ------------------------------------------------------------------------------------------------
+// curvilinear point-in-cell (index_search.py:94-239)
+// ------------------------------------------------------------------------------------------------
+template <class A, class D>
+__device__ __forceinline__ void load_corners(const GridDev& g, CGridCtx<A, D>& e, int j, int i) {
+    if (e.kyi == j && e.kxi == i) return;
+    e.kyi = j; e.kxi = i;
+    const A* __restrict__ lon = (const A*)g.lon;
+    const A* __restrict__ lat = (const A*)g.lat;
+    const long long nx = g.nx;
+    const long long o00 = (long long)j * nx + i;
+    e.clon[0] = ldg(lon + o00);          e.clat[0] = ldg(lat + o00);
+    e.clon[1] = ldg(lon + o00 + 1);      e.clat[1] = ldg(lat + o00 + 1);
+    e.clon[2] = ldg(lon + o00 + nx + 1); e.clat[2] = ldg(lat + o00 + nx + 1);
+    e.clon[3] = ldg(lon + o00 + nx);     e.clat[3] = ldg(lat + o00 + nx);
+    if (g.spherical) {  // _spherical_project_cell_and_query, cell part (index_search.py:203-236)
+        double cX[4], cY[4], cZ[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const double la = deg2rad_np((double)e.clat[k]), lo = deg2rad_np((double)e.clon[k]);
+            const double cl = cos(la);
+            cX[k] = cos(lo) * cl; cY[k] = sin(lo) * cl; cZ[k] = sin(la);
+        }
+        double ux = (cX[1] + cX[2]) - (cX[0] + cX[3]);
+        double uy = (cY[1] + cY[2]) - (cY[0] + cY[3]);
+        double uz = (cZ[1] + cZ[2]) - (cZ[0] + cZ[3]);
+        double un = sqrt(ux * ux + uy * uy + uz * uz);
+        if (un == 0.0) un = 1.0;
+        e.eu[0] = ux / un; e.eu[1] = uy / un; e.eu[2] = uz / un;
+        double vx = (cX[2] + cX[3]) - (cX[0] + cX[1]);
+        double vy = (cY[2] + cY[3]) - (cY[0] + cY[1]);
+        double vz = (cZ[2] + cZ[3]) - (cZ[0] + cZ[1]);
+        const double d = vx * e.eu[0] + vy * e.eu[1] + vz * e.eu[2];
+        vx = vx - d * e.eu[0]; vy = vy - d * e.eu[1]; vz = vz - d * e.eu[2];
+        double vn = sqrt(vx * vx + vy * vy + vz * vz);
+        if (vn == 0.0) vn = 1.0;
+        e.ev[0] = vx / vn; e.ev[1] = vy / vn; e.ev[2] = vz / vn;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            e.pu[k] = cX[k] * e.eu[0] + cY[k] * e.eu[1] + cZ[k] * e.eu[2];
+            e.pv[k] = cX[k] * e.ev[0] + cY[k] * e.ev[1] + cZ[k] * e.ev[2];
+        }
+    }
+}
+
+// _bilinear_inverse (index_search.py:132-149); np.dot(_invA, p) sums left to right
+__device__ __forceinline__ bool bilinear_inverse(const double (&px)[4], const double (&py)[4], double xq, double yq,
+                                                 double& xsi, double& eta) {
+    const double a0 = px[0], a1 = px[1] - px[0], a2 = px[3] - px[0], a3 = ((px[0] - px[1]) + px[2]) - px[3];
+    const double b0 = py[0], b1 = py[1] - py[0], b2 = py[3] - py[0], b3 = ((py[0] - py[1]) + py[2]) - py[3];
+    const double aa = a3 * b2 - a2 * b3;
+    const double bb = a3 * b0 - a0 * b3 + a1 * b2 - a2 * b1 + xq * b3 - yq * a3;
+    const double cc = a1 * b0 - a0 * b1 + xq * b1 - yq * a1;
+    const double det2 = bb * bb - 4 * aa * cc;
+    const double det = det2 > 0 ? sqrt(det2) : -1.0;
+    eta = fabs(aa) < 1e-12 ? -cc / bb : (det2 > 0 ? (-bb + det) / (2 * aa) : -1.0);
+    const double den = a1 + a3 * eta;
+    xsi = fabs(den) < 1e-12 ? ((yq - py[0]) / (py[1] - py[0]) + (yq - py[3]) / (py[2] - py[3])) * 0.5
+                            : (xq - a0 - a2 * eta) / den;
+    return xsi >= 0 && xsi <= 1 && eta >= 0 && eta <= 1;
+}
+
+struct Query {  // the sampled point, prepared once per eval
+    double x, y;     // degrees (float64, as point_in_cell casts them)
+    double qu_x, qu_y, qu_z;  // unit-sphere xyz in float64 (spherical)
+};
+
+template <class A, class D>
+__device__ __forceinline__ bool point_in_cell(const GridDev& g, CGridCtx<A, D>& e, int j, int i, const Query& q,
+                                              double& xsi, double& eta) {
+    load_corners(g, e, j, i);
+    if (g.spherical) {
+        const double qu = q.qu_x * e.eu[0] + q.qu_y * e.eu[1] + q.qu_z * e.eu[2];
+        const double qv = q.qu_x * e.ev[0] + q.qu_y * e.ev[1] + q.qu_z * e.ev[2];
+        return bilinear_inverse(e.pu, e.pv, qu, qv, xsi, eta);
+    }
+    double px[4], py[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { px[k] = (double)e.clon[k]; py[k] = (double)e.clat[k]; }
+    return bilinear_inverse(px, py, q.x, q.y, xsi, eta);
+}
+
+// ------------------------------------------------------------------------------------------------
+// spatial-hash query (spatialhash.py:389-535, quantize :647-695, Morton :554-597,698-716)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned int dilate10(unsigned int n) {
+    n &= 0x000003FFu;
+    n = (n | (n << 16)) & 0xFF0000FFu;
+    n = (n | (n << 8)) & 0x0300F00Fu;
+    n = (n | (n << 4)) & 0x030C30C3u;
+    n = (n | (n << 2)) & 0x09249249u;
+    return n;
+}
+// The hash-grid bounds are scalars of the grid's coordinate dtype A (np.nanmin of A-typed arrays), so
+// the normalisation runs in Q = promote(dtype of the sampled position, A).
+template <class Q, class A, class P>
+__device__ __forceinline__ unsigned int quant(P v, double lo_, double hi_, int bw) {
+    const A lo = (A)lo_, hi = (A)hi_;
+    const A d = hi - lo;
+    const Q vn = d != 0 ? ((Q)v - (Q)lo) / (Q)d : (Q)0;
+    Q s = vn * (Q)bw;
+    s = s < (Q)0 ? (Q)0 : (s > (Q)bw ? (Q)bw : s);  // np.clip (NaN coordinates are rejected by the finite test)
+    return (unsigned int)s;
+}
+
+template <class A, class D, class PY, class PX>
+__device__ __forceinline__ void hash_query(const GridDev& g, CGridCtx<A, D>& e, PY y, PX x, const Query& q, int& yi, int& xi,
+                                           double& xsi, double& eta) {
+    yi = -3; xi = -3; xsi = -1.0; eta = -1.0;  // GRID_SEARCH_ERROR, coords -1 (spatialhash.py:454-455,511)
+    using P = prom_t<PY, PX>;
+    using Q = prom_t<P, A>;
+    P hx, hy, hz;
+    if (g.spherical) {  // trig in the dtype of the sampled position (spatialhash.py:417-421)
+        const PY lat = deg2rad_np(y);
+        const PX lon = deg2rad_np(x);
+        hx = cos_np(lon) * cos_np(lat);
+        hy = sin_np(lon) * cos_np(lat);
+        hz = sin_np(lat);
+    } else {
+        hx = x; hy = y; hz = 0;
+    }
+    const unsigned int code = (dilate10(quant<Q, A>(hz, g.hbox[4], g.hbox[5], g.hash_bitwidth)) << 2) |
+                              (dilate10(quant<Q, A>(hy, g.hbox[2], g.hbox[3], g.hash_bitwidth)) << 1) |
+                              dilate10(quant<Q, A>(hx, g.hbox[0], g.hbox[1], g.hash_bitwidth));
+    long long l = 0, h = g.hnkeys;  // np.searchsorted(keys, code) (side="left")
+    while (l < h) {
+        const long long m = (l + h) >> 1;
+        if (ldg(g.hkeys + m) < code) l = m + 1; else h = m;
+    }
+    const bool finite = isfinite((double)x) && isfinite((double)y);
+    if (!(l < g.hnkeys && finite && ldg(g.hkeys + l) == code)) return;
+    const long long start = ldg(g.hstarts + l), cnt = ldg(g.hcounts + l);
+    const int ncol = g.nx - 1;
+    for (long long k = 0; k < cnt; ++k) {  // first candidate (ascending face id) that contains the point wins
+        const unsigned int face = ldg(g.hfaces + start + k);
+        const int j = (int)(face / (unsigned)ncol), i = (int)(face % (unsigned)ncol);
+        double cs, ce;
+        if (point_in_cell(g, e, j, i, q, cs, ce)) {
+            yi = j; xi = i;
+            xsi = (double)(float)cs;  // coords_best is float32 (spatialhash.py:511,529)
+            eta = (double)(float)ce;
+            return;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// CGrid_Velocity arithmetic (typed like NumPy: A corner coords, C face values, TY/TX bcoords)
+// ------------------------------------------------------------------------------------------------
+// _geodetic_distance (utils/interpolation.py:178-185): result dtype promote(A, L) on spherical meshes,
+// A on flat meshes
+template <bool SPH, class A, class L>
+__device__ __forceinline__ auto edge_length(A lat1, A lat2, A lon1, A lon2, L lat, double deg2m)
+    -> typename std::conditional<SPH, decltype(A() * L()), A>::type {
+    if constexpr (SPH) {
+        using R = decltype(A() * L());
+        const L rad_lat = (L)(3.14159265358979323846 / 180.0) * lat;
+        const R t1 = ((lon2 - lon1) * (A)deg2m) * cos_np(rad_lat);
+        const A t2 = (lat2 - lat1) * (A)deg2m;
+        return sqrt_np((R)(t1 * t1 + t2 * t2));
+    } else {
+        const A d1 = lon2 - lon1, d2 = lat2 - lat1;
+        return sqrt_np((A)(d1 * d1 + d2 * d2));
+    }
+}
+
+template <bool SPH, class C, class A, class TZ, class TY, class TX, class PY, int NC>
+__device__ __forceinline__ void cgrid_finish(const GridDev& g, const A (&px)[4], const A (&py)[4], C cu0, C cu1, C cv0, C cv1,
+                                             C cw0, C cw1, TZ zeta, TY eta, TX xsi, PY y, Val& u, Val& v, Val& w) {
+    constexpr bool sph = SPH;
+    const auto omx = 1 - xsi;
+    const auto ome = 1 - eta;
+    // latitude at the middle of each edge: einsum("ij,ji->i", phi2D_lin(., .), py), summed left to right
+    const auto l1 = (omx * (TX)1.0) * py[0] + (xsi * (TX)1.0) * py[1] + (xsi * (TX)0.0) * py[2] + (omx * (TX)0.0) * py[3];
+    const auto l2 = ((TY)0.0 * ome) * py[0] + ((TY)1.0 * ome) * py[1] + ((TY)1.0 * eta) * py[2] + ((TY)0.0 * eta) * py[3];
+    const auto l3 = (omx * (TX)0.0) * py[0] + (xsi * (TX)0.0) * py[1] + (xsi * (TX)1.0) * py[2] + (omx * (TX)1.0) * py[3];
+    const auto l4 = ((TY)1.0 * ome) * py[0] + ((TY)0.0 * ome) * py[1] + ((TY)0.0 * eta) * py[2] + ((TY)1.0 * eta) * py[3];
+    const auto c1 = edge_length<SPH>(py[0], py[1], px[0], px[1], l1, g.deg2m);
+    const auto c2 = edge_length<SPH>(py[1], py[2], px[1], px[2], l2, g.deg2m);
+    const auto c3 = edge_length<SPH>(py[2], py[3], px[2], px[3], l3, g.deg2m);
+    const auto c4 = edge_length<SPH>(py[3], py[0], px[3], px[0], l4, g.deg2m);
+    const auto U0 = cu0 * c4;
+    const auto U1 = cu1 * c2;
+    const auto Uvel = omx * U0 + xsi * U1;
+    const auto V0 = cv0 * c1;
+    const auto V1 = cv1 * c3;
+    const auto Vvel = ome * V0 + eta * V1;
+    // _compute_jacobian_determinant (utils/interpolation.py:188-198)
+    const auto dxdxsi = (eta - 1) * px[0] + ome * px[1] + eta * px[2] + (-eta) * px[3];
+    const auto dxdeta = (xsi - 1) * px[0] + (-xsi) * px[1] + xsi * px[2] + omx * px[3];
+    const auto dydxsi = (eta - 1) * py[0] + ome * py[1] + eta * py[2] + (-eta) * py[3];
+    const auto dydeta = (xsi - 1) * py[0] + (-xsi) * py[1] + xsi * py[2] + omx * py[3];
+    auto jac = dxdxsi * dydeta - dxdeta * dydxsi;
+    if (sph) jac = jac * (decltype(jac))g.deg2m;
+    auto uu = ((-ome) * Uvel - omx * Vvel) * px[0] + (ome * Uvel - xsi * Vvel) * px[1] + (eta * Uvel + xsi * Vvel) * px[2] +
+              ((-eta) * Uvel + omx * Vvel) * px[3];
+    auto vv = ((-ome) * Uvel - omx * Vvel) * py[0] + (ome * Uvel - xsi * Vvel) * py[1] + (eta * Uvel + xsi * Vvel) * py[2] +
+              ((-eta) * Uvel + omx * Vvel) * py[3];
+    auto ur = uu / jac;
+    auto vr = vv / jac;
+    if (sph) {  // u /= conversion; v /= conversion (in place: keeps u's dtype)
+        const PY conv = (PY)g.deg2m * cos_np(deg2rad_np(y));
+        ur = (decltype(ur))(ur / conv);
+        vr = (decltype(vr))(vr / conv);
+    }
+    u = Val{(double)ur, std::is_same<decltype(ur), float>::value};
+    v = Val{(double)vr, std::is_same<decltype(vr), float>::value};
+    if (NC == 3) {
+        const auto wr = cw0 * (1 - zeta) + cw1 * zeta;
+        w = Val{(double)wr, std::is_same<decltype(wr), float>::value};
+    } else {
+        w = Val{0.0, u.f32};
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// the policy
+// ------------------------------------------------------------------------------------------------
+template <class A, class D, int NC_, bool CURV>
+struct CGridPolicy {
+    static constexpr int NC = NC_;
+    using Ctx = CGridCtx<A, D>;
+
+    __device__ static __forceinline__ void init(Ctx& e, const AdvectParams& p, int ei) {
+        e.cx.idx = e.cy.idx = e.cz.idx = e.ct.idx = -100;
+        e.cx.lo = e.cx.hi = e.cy.lo = e.cy.hi = e.cz.lo = e.cz.hi = (A)0;
+        e.ct.lo = e.ct.hi = 0.0;
+        e.kyi = e.kxi = INT_MIN;
+        e.fti = e.fzi = e.fyi = e.fxi = INT_MIN;
+        e.ei = ei;
+        // hint of the first search: unravel_index(ei) (basegrid.py:120-152,219-256), floor semantics
+        const long long xd = p.g.xdim, yd = p.g.ydim;
+        long long r = ei;
+        if (p.g.nz > 0 && xd * yd > 0) { const long long pl = xd * yd; r = ((r % pl) + pl) % pl; }
+        if (xd > 0) {
+            long long yy = r / xd, xx = r % xd;
+            if (xx < 0) { xx += xd; yy -= 1; }
+            e.yi = (int)yy; e.xi = (int)xx;
+        } else {
+            e.yi = e.xi = -3;
+        }
+    }
+
+    template <class PZ, class PY, class PX>
+    __device__ static __forceinline__ void eval(const AdvectParams& p, Ctx& e, bool no_hint, double t, PZ z, PY y, PX x, Val& u,
+                                                Val& v, Val& w) {
+        const GridDev& g = p.g;
+        const FieldDev& f = p.f;
+        using TZ = prom_t<PZ, A>;
+        // -- time (index_search.py:65-91)
+        double tau = 0.0;
+        int ti = 0;
+        if (g.nt > 0) {
+            if (!(0 <= t && t <= g.time_len)) {
+                e.state = PB_ERROR_OUTSIDE_TIME_INTERVAL;
+                e.out_of_time = true;
+                u = Val{0.0, false}; v = u; w = u;
+                return;
+            }
+            tau = axis_search<double, double>(g.time, g.nt, t, e.ct);
+            ti = e.ct.idx;
+        }
+        // -- depth
+        TZ zeta = 0;
+        int zi = 0;
+        if (g.nz > 0) {
+            zeta = axis_search<PZ, A>((const A*)g.depth, g.nz, z, e.cz);
+            zi = e.cz.idx;
+        }
+        int yi, xi;
+        A px[4], py[4];
+        if (CURV) {
+            // -- _search_indices_curvilinear_2d (index_search.py:242-295): hint, then spatial hash
+            Query q;
+            q.x = (double)x; q.y = (double)y;
+            if (g.spherical) {
+                const double la = deg2rad_np(q.y), lo = deg2rad_np(q.x);
+                const double cl = cos(la);
+                q.qu_x = cos(lo) * cl; q.qu_y = sin(lo) * cl; q.qu_z = sin(la);
+            }
+            double xsi = -1.0, eta = -1.0;
+            bool found = false;
+            if (!no_hint && e.yi >= 0 && e.xi >= 0 && e.yi < g.ny - 1 && e.xi < g.nx - 1)
+                found = point_in_cell(g, e, e.yi, e.xi, q, xsi, eta);
+            if (found) { yi = e.yi; xi = e.xi; }
+            else hash_query(g, e, y, x, q, yi, xi, xsi, eta);
+            e.yi = yi; e.xi = xi;
+            long long r = (long long)yi * g.xdim + (long long)xi;
+            if (g.nz > 0) r += (long long)zi * (g.ydim * g.xdim);
+            e.ei = (int)r;
+            int s = e.state;
+            if (zi == -1) s = max(s, (int)PB_ERROR_OUT_OF_BOUNDS);
+            if (xi == -3 || yi == -3) s = max(s, (int)PB_ERROR_GRID_SEARCHING);
+            if (zi == -2) s = max(s, (int)PB_ERROR_THROUGH_SURFACE);
+            e.state = s;
+            if (xi < 0 || yi < 0 || zi < 0) { u = Val{0.0, false}; v = u; w = u; return; }
+            load_corners(g, e, yi, xi);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { px[k] = e.clon[k]; py[k] = e.clat[k]; }
+            finish<PZ, PY, double, double>(p, e, ti, tau, zi, zeta, yi, eta, xi, xsi, y, px, py, u, v, w);
+        } else {
+            using TY = prom_t<PY, A>;
+            using TX = prom_t<PX, A>;
+            const TY eta = axis_search<PY, A>((const A*)g.lat, g.ny, y, e.cy);
+            const TX xsi = axis_search<PX, A>((const A*)g.lon, g.nx, x, e.cx);
+            yi = e.cy.idx; xi = e.cx.idx;
+            long long r = (long long)yi * g.xdim + (long long)xi;
+            if (g.nz > 0) r += (long long)zi * (g.ydim * g.xdim);
+            e.ei = (int)r;
+            int s = e.state;
+            if (xi == -1 || yi == -1 || zi == -1) s = max(s, (int)PB_ERROR_OUT_OF_BOUNDS);
+            if (zi == -2) s = max(s, (int)PB_ERROR_THROUGH_SURFACE);
+            e.state = s;
+            if (xi < 0 || yi < 0 || zi < 0) { u = Val{0.0, false}; v = u; w = u; return; }
+            px[0] = e.cx.lo; px[1] = e.cx.hi; px[2] = e.cx.hi; px[3] = e.cx.lo;  // _xinterpolators.py:218-220
+            py[0] = e.cy.lo; py[1] = e.cy.lo; py[2] = e.cy.hi; py[3] = e.cy.hi;
+            finish<PZ, PY, TY, TX>(p, e, ti, tau, zi, zeta, yi, eta, xi, xsi, y, px, py, u, v, w);
+        }
+        if (u.v != u.v || v.v != v.v || w.v != w.v) e.state = max(e.state, (int)PB_ERROR_INTERPOLATION);
+    }
+
+    template <class PZ, class PY, class TY, class TX>
+    __device__ static __forceinline__ void finish(const AdvectParams& p, Ctx& e, int ti, double tau, int zi, prom_t<PZ, A> zeta,
+                                                  int yi, TY eta, int xi, TX xsi, PY y, A (&px)[4], A (&py)[4], Val& u, Val& v,
+                                                  Val& w) {
+        const GridDev& g = p.g;
+        const FieldDev& f = p.f;
+        using TZ = prom_t<PZ, A>;
+        if (g.spherical) {  // corner longitudes unwrapped relative to corner 0 (_xinterpolators.py:230-233)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) px[k] = mod_np((A)(px[k] + (A)180.0), (A)360.0) - (A)180.0;
+#pragma unroll
+            for (int k = 1; k < 4; ++k) if (px[k] - px[0] > (A)180) px[k] = px[k] - (A)360;
+#pragma unroll
+            for (int k = 1; k < 4; ++k) if (-px[k] + px[0] > (A)180) px[k] = px[k] + (A)360;
+        }
+        // -- the 2 faces x 2 time levels of U, V (, W) this cell needs (:246-330)
+        if (e.fti != ti || e.fzi != zi || e.fyi != yi || e.fxi != xi) {
+            e.fti = ti; e.fzi = zi; e.fyi = yi; e.fxi = xi;
+            e.refills++;
+            const long long ot[2] = {(long long)min(max(ti, 0), f.T - 1) * f.sT, up_idx(ti, f.T) * f.sT};
+            const long long oz = (long long)min(max(zi, 0), f.Z - 1) * f.sZ;
+            const long long oy0 = (long long)yi * f.sY, oy1 = up_idx(yi, f.Y) * f.sY;
+            const long long oyo = (long long)min(max(yi + g.off_y, 0), f.Y - 1) * f.sY;
+            const long long ox0 = (long long)xi * f.sX, ox1 = up_idx(xi, f.X) * f.sX;
+            const long long oxo = (long long)min(max(xi + g.off_x, 0), f.X - 1) * f.sX;
+            const D* __restrict__ U = (const D*)f.p[0];
+            const D* __restrict__ V = (const D*)f.p[1];
+#pragma unroll
+            for (int tl = 0; tl < 2; ++tl) {
+                e.fu[tl * 2 + 0] = ldg(U + ot[tl] + oz + oyo + ox0);
+                e.fu[tl * 2 + 1] = ldg(U + ot[tl] + oz + oyo + ox1);
+                e.fv[tl * 2 + 0] = ldg(V + ot[tl] + oz + oy0 + oxo);
+                e.fv[tl * 2 + 1] = ldg(V + ot[tl] + oz + oy1 + oxo);
+            }
+            if (NC_ == 3) {
+                const D* __restrict__ W = (const D*)f.p[2];
+                const long long oz0 = (long long)min(max(zi + g.off_z, 0), f.Z - 1) * f.sZ;
+                const long long oz1 = (long long)min(max(zi + g.off_z + 1, 0), f.Z - 1) * f.sZ;
+#pragma unroll
+                for (int tl = 0; tl < 2; ++tl) {
+                    e.fw[tl * 2 + 0] = ldg(W + ot[tl] + oz0 + oyo + oxo);
+                    e.fw[tl * 2 + 1] = ldg(W + ot[tl] + oz1 + oyo + oxo);
+                }
+            } else {
+                e.fw[0] = e.fw[1] = e.fw[2] = e.fw[3] = (D)0;
+            }
+        }
+        if (g.spherical) reduce_and_finish<true, TZ, TY, TX, PY>(g, e, px, py, tau, zeta, eta, xsi, y, u, v, w);
+        else reduce_and_finish<false, TZ, TY, TX, PY>(g, e, px, py, tau, zeta, eta, xsi, y, u, v, w);
+    }
+
+    template <bool SPH, class TZ, class TY, class TX, class PY>
+    __device__ static __forceinline__ void reduce_and_finish(const GridDev& g, Ctx& e, const A (&px)[4], const A (&py)[4], double tau,
+                                                             TZ zeta, TY eta, TX xsi, PY y, Val& u, Val& v, Val& w) {
+        if (tau > 0) {  // lenT == 2: reduce over time in promote(D, float64)
+            const double omt = 1 - tau;
+            cgrid_finish<SPH, double, A, TZ, TY, TX, PY, NC_>(g, px, py, e.fu[0] * omt + e.fu[2] * tau, e.fu[1] * omt + e.fu[3] * tau,
+                                                              e.fv[0] * omt + e.fv[2] * tau, e.fv[1] * omt + e.fv[3] * tau,
+                                                              e.fw[0] * omt + e.fw[2] * tau, e.fw[1] * omt + e.fw[3] * tau, zeta,
+                                                              eta, xsi, y, u, v, w);
+        } else {
+            cgrid_finish<SPH, D, A, TZ, TY, TX, PY, NC_>(g, px, py, e.fu[0], e.fu[1], e.fv[0], e.fv[1], e.fw[0], e.fw[1], zeta, eta,
+                                                         xsi, y, u, v, w);
+        }
+    }
+};
+
+template <class A, class D, int NC, bool CURV>
+static cudaError_t launch1(const AdvectParams& p, cudaStream_t s) {
+    const int block = 128;
+    const long long grid = (p.P.n + block - 1) / block;
+    advect_kernel<CGridPolicy<A, D, NC, CURV>><<<(unsigned)grid, block, 0, s>>>(p);
+    return cudaGetLastError();
+}
+
+template <class A, class D>
+static cudaError_t launch_ad(const AdvectParams& p, int nc, cudaStream_t s) {
+    if (p.g.curvilinear) return nc == 3 ? launch1<A, D, 3, true>(p, s) : launch1<A, D, 2, true>(p, s);
+    return nc == 3 ? launch1<A, D, 3, false>(p, s) : launch1<A, D, 2, false>(p, s);
+}
+
+cudaError_t launch_cgrid(const AdvectParams& p, bool coord_f64, bool data_f64, int nc, cudaStream_t s) {
+    if (coord_f64) return data_f64 ? launch_ad<double, double>(p, nc, s) : launch_ad<double, float>(p, nc, s);
+    return data_f64 ? launch_ad<float, double>(p, nc, s) : launch_ad<float, float>(p, nc, s);
+}

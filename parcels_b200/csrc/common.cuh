@@ -1,0 +1,341 @@
+// common.cuh -- shared by the A-grid (agrid.cu) and C-grid (cgrid.cu) kernels and the host API
+// (engine.cu): device descriptors, NumPy-compatible numeric helpers, the register-cached 1-D axis
+// search, Philox, and the generic advect_kernel<Policy> (Kernel.execute's loop, one lane per particle).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <climits>
+#include <cstdint>
+#include <type_traits>
+
+#include "../../include/parcels_b200.h"
+
+// ------------------------------------------------------------------------------------------------
+// device-side descriptors
+// ------------------------------------------------------------------------------------------------
+struct GridDev {
+    const void* lon;
+    const void* lat;
+    const void* depth;
+    const double* time;  // seconds since interval start (time[0] == 0 after host normalisation)
+    int nx, ny, nz, nt;  // node counts; nz == 0: grid has no Z axis
+    int spherical;
+    int pad_;
+    double deg2m;
+    double time_len;  // time[nt-1] - time[0]
+    long long xdim, ydim, zdim;  // cell counts for ravel_index
+    // curvilinear grids (lon/lat are 2-D (ny, nx) arrays) + the spatial hash of _core/spatialhash.py
+    int curvilinear;
+    int hash_bitwidth;
+    const unsigned int* hkeys;    // unique Morton codes, ascending
+    const long long* hstarts;     // CSR start of each key in hfaces
+    const long long* hcounts;     // number of candidate faces per key
+    const unsigned int* hfaces;   // flat face id j * (nx - 1) + i, ascending within a key
+    long long hnkeys;
+    double hbox[6];               // xmin, xmax, ymin, ymax, zmin, zmax of the hash grid
+    int off_x, off_y, off_z;      // C-grid staggering offsets (_xinterpolators.py:99-109)
+    int pad2_;
+};
+
+struct FieldDev {
+    const void* p[3];
+    int T, Z, Y, X;            // data shape (shared by all components on an A-grid)
+    long long sT, sZ, sY, sX;  // element strides; 0 for size-1 (never indexed) dims
+};
+
+struct ReportDev {
+    unsigned long long particle_steps;
+    unsigned long long n_error;
+    unsigned long long n_deleted;
+    long long first_error_iter;  // LLONG_MAX when none
+    unsigned long long n_out_of_time;
+    long long max_iters_done;
+    unsigned long long cache_refills;
+    int max_state;
+    int pad_;
+};
+
+struct ParticlesDev {
+    float *x, *y, *z, *dx, *dy, *dz;
+    double* t;
+    int* state;
+    int* ei;
+    long long* pid;
+    long long n;
+};
+
+struct AdvectParams {
+    GridDev g;
+    FieldDev f;
+    ParticlesDev P;
+    int scheme, diffusion, delete_on_error, kh_spherical;
+    double dt, endtime, kh_zonal, kh_meridional, kh_deg2m;
+    unsigned long long seed, rng_call;
+    long long max_iters;
+    int hint_all_zero;  // curvilinear: every hinted xi of the evaluated view is 0 => the reference skips
+                        // the hint for the whole batch at the first eval (index_search.py:269-282)
+    int pad_;
+    ReportDev* rep;
+};
+
+// ------------------------------------------------------------------------------------------------
+// small numeric helpers (NumPy-compatible promotion: C++ usual arithmetic conversions on
+// float/double are the same lattice as NumPy's for float32/float64 arrays; Python scalars are
+// "weak", so literals below are always cast to the array type first)
+// ------------------------------------------------------------------------------------------------
+template <class A, class B>
+using prom_t = decltype(A() + B());
+
+template <class T>
+__device__ __forceinline__ T ldg(const T* p) {
+    return __ldg(p);
+}
+
+// np.deg2rad: x * (pi/180) evaluated in the array dtype (npy_deg2rad / npy_deg2radf)
+__device__ __forceinline__ float deg2rad_np(float x) { return x * (float)(3.14159265358979323846 / 180.0); }
+__device__ __forceinline__ double deg2rad_np(double x) { return x * (3.14159265358979323846 / 180.0); }
+__device__ __forceinline__ float cos_np(float x) { return cosf(x); }
+__device__ __forceinline__ double cos_np(double x) { return cos(x); }
+
+// A value with NumPy's dtype tag: interpolated velocities are float32 only when grid coordinates,
+// field data and the sampled position are all float32 (stage 1) -- the tag decides in which
+// precision the in-place spherical division is rounded (_xinterpolators.py:182-184).
+struct Val {
+    double v;
+    bool f32;
+};
+
+// ------------------------------------------------------------------------------------------------
+// Philox4x32-10 + Box-Muller (Wiener increments of DiffusionUniformKh)
+// ------------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                                       uint32_t k1, uint32_t out[4]) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint64_t p0 = (uint64_t)M0 * c0, p1 = (uint64_t)M1 * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        uint32_t n1 = (uint32_t)p1;
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        uint32_t n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += W0; k1 += W1;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+__device__ __forceinline__ void wiener_normals(unsigned long long seed, unsigned long long rng_call, long long iter,
+                                               long long pid, double& zx, double& zy) {
+    uint32_t r[4];
+    // counter = (pid_lo, pid_hi, iteration, call index); key = seed
+    philox4x32_10((uint32_t)pid, (uint32_t)((unsigned long long)pid >> 32), (uint32_t)iter, (uint32_t)rng_call,
+                  (uint32_t)seed, (uint32_t)(seed >> 32), r);
+    const double two_m32 = 2.3283064365386963e-10;  // 2^-32
+    double u1 = ((double)r[0] + 0.5) * two_m32;
+    double u2 = ((double)r[1] + 0.5) * two_m32;
+    double rad = sqrt(-2.0 * log(u1));
+    double ang = 6.283185307179586476925 * u2;
+    zx = rad * cos(ang);
+    zy = rad * sin(ang);
+}
+
+// ------------------------------------------------------------------------------------------------
+// 1-D axis search with a register-resident cell (reference _core/index_search.py:20-62)
+//   idx = clip(searchsorted(arr, x, 'left') - 1, 0, n-2);  b = (x - arr[idx]) / (arr[idx+1] - arr[idx])
+//   idx = -2 if x < arr[0];  idx = -1 if x > arr[-1]
+// The previous cell [lo, hi] is kept in registers: lo < x <= hi is exactly the searchsorted
+// condition for that cell, so a hit costs no memory access.
+// ------------------------------------------------------------------------------------------------
+template <class A>
+struct AxisCell {
+    int idx;  // raw result of the last search (may be a negative sentinel)
+    A lo, hi;
+};
+
+template <class P, class A>
+__device__ __forceinline__ prom_t<P, A> axis_search(const A* __restrict__ arr, int n, P x, AxisCell<A>& c) {
+    using R = prom_t<P, A>;
+    if (n < 2) {  // index_search.py:45-46
+        c.idx = 0;
+        return (R)0;
+    }
+    const R xr = (R)x;
+    if (!(c.idx >= 0 && xr > (R)c.lo && xr <= (R)c.hi)) {
+        int l = 0, h = n;  // first i with arr[i] >= x   (side="left")
+        while (l < h) {
+            int m = (l + h) >> 1;
+            if ((R)ldg(arr + m) < xr) l = m + 1; else h = m;
+        }
+        if (x != x) l = n;  // NaN sorts last
+        int i = min(max(l - 1, 0), n - 2);
+        c.lo = ldg(arr + i);
+        c.hi = ldg(arr + i + 1);
+        c.idx = i;
+        if (xr < (R)ldg(arr)) c.idx = -2;          // LEFT_OUT_OF_BOUNDS
+        if (xr > (R)ldg(arr + n - 1)) c.idx = -1;  // RIGHT_OUT_OF_BOUNDS
+    }
+    return (xr - (R)c.lo) / (R)(c.hi - c.lo);  // denominator rounded in the coordinate dtype
+}
+
+// ------------------------------------------------------------------------------------------------
+// gather index helpers (NumPy fancy-index semantics of the reference's corner gathers)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ long long wrap_idx(int i, int n) {  // NumPy negative-index wrap
+    int w = i < 0 ? i + n : i;
+    return (long long)min(max(w, 0), n - 1);
+}
+__device__ __forceinline__ long long up_idx(int i, int n) {  // np.clip(i + 1, 0, n - 1)
+    return (long long)min(max(i + 1, 0), n - 1);
+}
+
+// u * 0.5 keeps u's dtype (Python float is weak)
+__device__ __forceinline__ double half_of(const Val& a) { return a.f32 ? (double)((float)a.v * 0.5f) : a.v * 0.5; }
+
+// ------------------------------------------------------------------------------------------------
+// the kernel: Kernel.execute's loop, one lane per particle
+// ------------------------------------------------------------------------------------------------
+// Policy supplies: Ctx (with members state, ei, refills, out_of_time), init(Ctx&, params, ei), and
+//   eval<PZ,PY,PX>(params, Ctx&, no_hint, t, z, y, x, u, v, w)  == VectorField.eval for one particle.
+template <class Policy>
+__global__ void __launch_bounds__(128) advect_kernel(const AdvectParams p) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long my_steps = 0, my_refills = 0;
+    int final_state = 0;
+    long long my_iters = 0;
+    bool errored = false, deleted = false, oot = false;
+    long long err_iter = LLONG_MAX;
+
+    if (i < p.P.n) {
+        float x = p.P.x[i], y = p.P.y[i], z = p.P.z[i];
+        float dx = p.P.dx[i], dy = p.P.dy[i], dz = p.P.dz[i];
+        double t = p.P.t[i];
+        const long long pid = p.diffusion ? p.P.pid[i] : 0;
+
+        typename Policy::Ctx e;
+        Policy::init(e, p, p.P.ei[i]);
+        e.state = PB_EVALUATE;  // kernel.py:188
+        e.refills = 0;
+        e.out_of_time = false;
+
+        const int sign = p.dt > 0 ? 1 : -1;
+        const bool three_d = (p.scheme == PB_ADVECTION_RK4_3D || p.scheme == PB_ADVECTION_RK2_3D);
+        const int nstage = (p.scheme == PB_ADVECTION_EE) ? 1 : ((p.scheme == PB_ADVECTION_RK2 || p.scheme == PB_ADVECTION_RK2_3D) ? 2 : 4);
+
+        long long it = 0;
+        for (;; ++it) {
+            if (p.max_iters >= 0 && it >= p.max_iters) break;
+            const double tte = sign * (p.endtime - t);                       // kernel.py:191
+            if (!((e.state == PB_SUCCESS || e.state == PB_EVALUATE) && tte >= 0)) break;  // :193-195
+            // adapt dt to end exactly on endtime (:199-203)
+            const double dtp = (sign == 1) ? fmax(fmin(p.dt, tte), 0.0) : fmin(fmax(p.dt, -tte), 0.0);
+            my_steps++;
+
+            // ---- advection kernel (kernels/_advection.py) ----
+            Val u1, v1, w1, uk, vk, wk;
+            // with DiffusionUniformKh in the list, ei[:, -1] was overwritten with 0 for every particle by the
+            // constant-field evals of the previous step: curvilinear hints are all zero again
+            Policy::template eval<float, float, float>(p, e, (it == 0 && p.hint_all_zero) || (it > 0 && p.diffusion), t, z, y, x, u1, v1, w1);
+            double su = u1.v, sv = v1.v, sw = w1.v;  // running RK4 sums, left to right
+            uk = u1; vk = v1; wk = w1;
+            for (int k = 1; k < nstage; ++k) {
+                // stage position: x + u*0.5*dt (k = 1, 2) or x + u*dt (k = 3)
+                const bool full = (k == 3);
+                const double xs = (double)x + (full ? uk.v : half_of(uk)) * dtp;
+                const double ys = (double)y + (full ? vk.v : half_of(vk)) * dtp;
+                const double ts = t + (full ? dtp : 0.5 * dtp);
+                if (three_d) {
+                    const double zs = (double)z + (full ? wk.v : half_of(wk)) * dtp;
+                    Policy::template eval<double, double, double>(p, e, false, ts, zs, ys, xs, uk, vk, wk);
+                } else {
+                    Policy::template eval<float, double, double>(p, e, false, ts, z, ys, xs, uk, vk, wk);
+                }
+                if (nstage == 4) {
+                    const double m = (k == 3) ? 1.0 : 2.0;  // u1 + 2*u2 + 2*u3 + u4
+                    su = su + m * uk.v; sv = sv + m * vk.v; sw = sw + m * wk.v;
+                }
+            }
+            double ddx, ddy, ddz;
+            if (nstage == 4) {
+                ddx = su / 6.0 * dtp; ddy = sv / 6.0 * dtp; ddz = sw / 6.0 * dtp;
+            } else {  // EE: u1*dt ; RK2: u2*dt
+                ddx = uk.v * dtp; ddy = vk.v * dtp; ddz = wk.v * dtp;
+            }
+            dx = (float)((double)dx + ddx);
+            dy = (float)((double)dy + ddy);
+            if (three_d) dz = (float)((double)dz + ddz);
+
+            // ---- DiffusionUniformKh (kernels/_advectiondiffusion.py:120-153) ----
+            if (p.diffusion) {
+                double zx, zy;
+                wiener_normals(p.seed, p.rng_call, it, pid, zx, zy);
+                const double sq = sqrt(fabs(dtp));
+                const double dWx = zx * sq, dWy = zy * sq;
+                double khz = p.kh_zonal, khm = p.kh_meridional;
+                if (p.kh_spherical) {
+                    const float ang = (y * (float)3.14159265358979323846) / 180.0f;  // lat * np.pi / 180 in f32
+                    const float m = (float)p.kh_deg2m * cosf(ang);
+                    khz = khz / (double)(m * m);
+                    khm = khm / (p.kh_deg2m * p.kh_deg2m);
+                }
+                const double bx = sqrt(2 * khz), by = sqrt(2 * khm);
+                dx = (float)((double)dx + bx * dWx);
+                dy = (float)((double)dy + by * dWy);
+                e.ei = 0;  // the constant-field evals overwrite ei[:, -1] with cell 0 (model.py:292-318)
+            }
+            // ---- trailing error handler: every error state becomes Delete ----
+            if (p.delete_on_error && e.state >= 50) e.state = PB_DELETE;
+
+            // ---- position update only for particles still in a normal state (kernel.py:108-116,220-222)
+            if (e.state == PB_EVALUATE || e.state == PB_SUCCESS) {
+                x = x + dx; y = y + dy; z = z + dz;
+                t = t + dtp;
+                dx = 0.f; dy = 0.f; dz = 0.f;
+            }
+            if (e.state == PB_EVALUATE && t == p.endtime) e.state = PB_END_OF_LOOP;  // :229-230
+            if (e.state == PB_DELETE) { deleted = true; ++it; break; }
+            if (e.state >= 50) { errored = true; err_iter = it; ++it; break; }
+        }
+        my_iters = it;
+        my_refills = e.refills;
+        oot = e.out_of_time;
+        final_state = e.state;
+        p.P.x[i] = x; p.P.y[i] = y; p.P.z[i] = z;
+        p.P.dx[i] = dx; p.P.dy[i] = dy; p.P.dz[i] = dz;
+        p.P.t[i] = t;
+        p.P.state[i] = e.state;
+        p.P.ei[i] = e.ei;
+    }
+
+    // ---- report: warp-reduce then one atomic per warp ----
+    const unsigned full = 0xffffffffu;
+    unsigned long long s_steps = my_steps, s_ref = my_refills;
+    unsigned n_err = errored, n_del = deleted, n_oot = oot;
+    long long mx_it = my_iters, mn_err = err_iter;
+    int mx_state = final_state;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s_steps += __shfl_xor_sync(full, s_steps, o);
+        s_ref += __shfl_xor_sync(full, s_ref, o);
+        n_err += __shfl_xor_sync(full, n_err, o);
+        n_del += __shfl_xor_sync(full, n_del, o);
+        n_oot += __shfl_xor_sync(full, n_oot, o);
+        mx_it = max(mx_it, __shfl_xor_sync(full, mx_it, o));
+        mn_err = min(mn_err, __shfl_xor_sync(full, mn_err, o));
+        mx_state = max(mx_state, __shfl_xor_sync(full, mx_state, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (s_steps) atomicAdd(&p.rep->particle_steps, s_steps);
+        if (s_ref) atomicAdd(&p.rep->cache_refills, s_ref);
+        if (n_err) atomicAdd(&p.rep->n_error, (unsigned long long)n_err);
+        if (n_del) atomicAdd(&p.rep->n_deleted, (unsigned long long)n_del);
+        if (n_oot) atomicAdd(&p.rep->n_out_of_time, (unsigned long long)n_oot);
+        if (mx_it) atomicMax(&p.rep->max_iters_done, mx_it);
+        if (mn_err != LLONG_MAX) atomicMin(&p.rep->first_error_iter, mn_err);
+        if (mx_state) atomicMax(&p.rep->max_state, mx_state);
+    }
+}
+
+// launchers implemented in agrid.cu / cgrid.cu (one translation unit per grid family keeps nvcc parallel)
+cudaError_t launch_agrid(const AdvectParams& p, bool coord_f64, bool data_f64, bool has_time, int nc, cudaStream_t s);
+cudaError_t launch_cgrid(const AdvectParams& p, bool coord_f64, bool data_f64, int nc, cudaStream_t s);

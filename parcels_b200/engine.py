@@ -54,6 +54,34 @@ class Engine:
             )
         )  # fmt: skip
 
+    def upload_curvilinear_grid(self, lon2d, lat2d, depth, time_s, spherical, deg2m, xdim, ydim, zdim, h: dict):
+        lon2d = np.ascontiguousarray(lon2d)
+        cdt = lon2d.dtype
+        if cdt not in (np.float32, np.float64):
+            raise TypeError(f"grid coordinates must be float32 or float64, got {cdt}")
+        lat2d = np.ascontiguousarray(lat2d)
+        if lat2d.dtype != cdt or (depth is not None and np.asarray(depth).dtype != cdt):
+            raise TypeError("lon, lat and depth must share one dtype (the reference's arithmetic promotes on it)")
+        depth = None if depth is None else np.ascontiguousarray(depth)
+        time_s = None if time_s is None else np.ascontiguousarray(time_s, dtype=np.float64)
+        ny, nx = lon2d.shape
+        keys = np.ascontiguousarray(h["keys"], dtype=np.uint32)
+        starts = np.ascontiguousarray(h["starts"], dtype=np.int64)
+        counts = np.ascontiguousarray(h["counts"], dtype=np.int64)
+        faces = np.ascontiguousarray(h["faces"], dtype=np.uint32)
+        box = np.ascontiguousarray(h["box"], dtype=np.float64)
+        check(
+            self._lib.pb_grid_upload_curvilinear(
+                self._h, ptr(lon2d), ptr(lat2d), ny, nx, ptr(depth), 0 if depth is None else depth.size,
+                int(cdt == np.float64), ptr(time_s), 0 if time_s is None else time_s.size, int(bool(spherical)),
+                float(deg2m), int(xdim), int(ydim), int(zdim or 0), ptr(keys), ptr(starts), ptr(counts), keys.size,
+                ptr(faces), faces.size, ptr(box), int(h["bitwidth"]),
+            )
+        )  # fmt: skip
+
+    def set_interpolation(self, method: int, off_x: int, off_y: int, off_z: int):
+        check(self._lib.pb_set_interpolation(self._h, int(method), int(off_x), int(off_y), int(off_z)))
+
     def upload_field(self, slot: int, data):
         data = np.asarray(data)
         if data.ndim != 4:
@@ -114,9 +142,10 @@ class Engine:
     # -- hot path --------------------------------------------------------------------------------
     @staticmethod
     def make_args(scheme, dt, endtime, *, diffusion=False, delete_on_error=False, kh=(0.0, 0.0), kh_spherical=False,
-                  kh_deg2m=1.0, seed=0, rng_call=0, max_iters=-1) -> AdvectArgs:  # fmt: skip
+                  kh_deg2m=1.0, seed=0, rng_call=0, max_iters=-1, hint_all_zero=False) -> AdvectArgs:  # fmt: skip
         return AdvectArgs(int(scheme), int(diffusion), int(delete_on_error), int(kh_spherical), float(dt), float(endtime),
-                          float(kh[0]), float(kh[1]), float(kh_deg2m), int(seed), int(rng_call), int(max_iters))  # fmt: skip
+                          float(kh[0]), float(kh[1]), float(kh_deg2m), int(seed), int(rng_call), int(max_iters),
+                          int(bool(hint_all_zero)), 0)  # fmt: skip
 
     def advect(self, args: AdvectArgs) -> dict:
         rep = Report()

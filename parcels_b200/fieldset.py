@@ -38,15 +38,30 @@ class XGrid:
         self.lon = np.asarray(lon)
         self.lat = np.asarray(lat)
         self.depth = None if depth is None else np.asarray(depth)
-        if self.lon.ndim != 1 or self.lat.ndim != 1:
-            raise NotImplementedError("curvilinear (2-D lon/lat) grids are not on this engine yet")
+        if self.lon.ndim not in (1, 2) or self.lat.ndim != self.lon.ndim:
+            raise ValueError("lon/lat must both be 1-D (rectilinear) or both 2-D (curvilinear, shape (ny, nx))")
+        if self.lon.ndim == 2 and self.lon.shape != self.lat.shape:
+            raise ValueError("curvilinear lon and lat must share one shape (ny, nx)")
         if mesh not in ("flat", "spherical"):
             raise ValueError(f"mesh must be 'flat' or 'spherical'. Got {mesh!r}")
         self.mesh = mesh
         self.radius = (EARTH_RADIUS if radius is None else radius) if mesh == "spherical" else None
-        self.xdim = self.lon.size - 1 if xdim is None else xdim
-        self.ydim = self.lat.size - 1 if ydim is None else ydim
+        self.xdim = self.lon.shape[-1] - 1 if xdim is None else xdim
+        self.ydim = self.lat.shape[0] - 1 if ydim is None else ydim
+        self._hash = None
         self.zdim = None if self.depth is None else (self.depth.size - 1 if zdim is None else zdim)
+
+    @property
+    def curvilinear(self):
+        return self.lon.ndim == 2
+
+    def get_spatial_hash(self):
+        """reference _core/basegrid.py:192-216: built lazily, once."""
+        if self._hash is None:
+            from .spatialhash import build_spatial_hash
+
+            self._hash = build_spatial_hash(self.lon, self.lat, self.is_spherical())
+        return self._hash
 
     def is_spherical(self):
         return self.mesh == "spherical"
@@ -96,9 +111,16 @@ class FieldSet:
     FieldSet of the reference package).  Time is float seconds or datetime64/timedelta64.
     """
 
-    def __init__(self, grid: XGrid, U, V, W=None, time=None, interp_method="linear"):
-        if interp_method != "linear":
-            raise NotImplementedError(f"interp_method {interp_method!r}: only XLinear_Velocity ('linear') is on this engine")
+    def __init__(self, grid: XGrid, U, V, W=None, time=None, interp_method="linear", padding=("low", "low", "high")):
+        if interp_method not in ("linear", "cgrid_velocity"):
+            raise NotImplementedError(
+                f"interp_method {interp_method!r}: XLinear_Velocity ('linear') and CGrid_Velocity ('cgrid_velocity') are on this engine"
+            )
+        if grid.curvilinear and interp_method != "cgrid_velocity":
+            raise NotImplementedError("curvilinear grids are supported with CGrid_Velocity only")
+        self.interp_method = interp_method
+        # C-grid staggering offsets X, Y, Z: 1 for LOW SGRID padding (reference _xinterpolators.py:99-109)
+        self.offsets = tuple(int(p == "low") for p in padding)
         self.grid = grid
         self.fields = {}
         self.constants = {}
@@ -126,8 +148,10 @@ class FieldSet:
         self._engines: dict[int, Engine] = {}
 
     @classmethod
-    def from_arrays(cls, *, lon, lat, U, V, W=None, depth=None, time=None, mesh="spherical", radius=None, **kw):
-        return cls(XGrid(lon, lat, depth, mesh=mesh, radius=radius, **kw), U, V, W, time=time)
+    def from_arrays(cls, *, lon, lat, U, V, W=None, depth=None, time=None, mesh="spherical", radius=None,
+                    interp_method="linear", padding=("low", "low", "high"), **kw):  # fmt: skip
+        return cls(XGrid(lon, lat, depth, mesh=mesh, radius=radius, **kw), U, V, W, time=time, interp_method=interp_method,
+                   padding=padding)  # fmt: skip
 
     # -- reference API surface used on this path -----------------------------------------------
     @property
@@ -165,7 +189,12 @@ class FieldSet:
         if eng is None:
             eng = Engine(device)
             g = self.grid
-            eng.upload_rectilinear_grid(g.lon, g.lat, g.depth, self._time_s, g.is_spherical(), g.deg2m, g.xdim, g.ydim, g.zdim)
+            if g.curvilinear:
+                eng.upload_curvilinear_grid(g.lon, g.lat, g.depth, self._time_s, g.is_spherical(), g.deg2m, g.xdim, g.ydim,
+                                            g.zdim, g.get_spatial_hash())  # fmt: skip
+            else:
+                eng.upload_rectilinear_grid(g.lon, g.lat, g.depth, self._time_s, g.is_spherical(), g.deg2m, g.xdim, g.ydim, g.zdim)
+            eng.set_interpolation(1 if self.interp_method == "cgrid_velocity" else 0, *self.offsets)
             for slot, name in enumerate(("U", "V", "W")):
                 if name in self.fields:
                     eng.upload_field(slot, self.fields[name].data)

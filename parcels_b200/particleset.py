@@ -155,11 +155,19 @@ class ParticleSet:
         eng = self.fieldset.engine(self.device)
         ei_last = np.ascontiguousarray(d["ei"][:, -1])
         self._rng_call += 1
+        hint_all_zero = False
+        g = self.fieldset.grid
+        if g.curvilinear:
+            # the reference skips the hint test for the WHOLE batch when every hinted xi is 0
+            # (`if np.any(xi)`, _core/index_search.py:269), e.g. on the first eval of a fresh set
+            sign = 1 if dt > 0 else -1
+            evaluated = sign * (endtime - d["t"]) >= 0
+            hint_all_zero = not np.any((ei_last[evaluated].astype(np.int64) % g.xdim) != 0)
 
         def args(max_iters=-1):
             return eng.make_args(plan.scheme, dt, endtime, diffusion=plan.diffusion, delete_on_error=plan.delete_on_error,
                                  kh=plan.kh, kh_spherical=plan.kh_spherical, kh_deg2m=plan.kh_deg2m, seed=self.seed,
-                                 rng_call=self._rng_call, max_iters=max_iters)  # fmt: skip
+                                 rng_call=self._rng_call, max_iters=max_iters, hint_all_zero=hint_all_zero)  # fmt: skip
 
         eng.upload_particles(d, ei_last)
         rep = eng.advect(args())

@@ -53,6 +53,37 @@ def smooth_uvw(rng, lon, lat, depth, nt, ddtype, umax=1.0, wmax=1e-3, noise=0.05
     return (umax * U).astype(ddtype), (umax * V).astype(ddtype), (wmax * W).astype(ddtype)
 
 
+def curv_mesh(ny, nx, spherical, cdtype):
+    """Smooth curvilinear node mesh (rotated 25 deg, stretched, warped): 2-D lon/lat (ny, nx)."""
+    I, J = np.meshgrid(np.linspace(0, 1, nx), np.linspace(0, 1, ny))
+    th = np.deg2rad(25.0)
+    a = I + 0.15 * I**2
+    b = J + 0.1 * np.sin(np.pi * I) * J
+    X = np.cos(th) * a - np.sin(th) * b
+    Y = np.sin(th) * a + np.cos(th) * b
+    if spherical:
+        lon, lat = -20 + 30 * X, 35 + 25 * Y
+    else:
+        lon, lat = 1e4 * X, 1e4 * Y
+    return lon.astype(cdtype), lat.astype(cdtype)
+
+
+def points_in_mesh(rng, lon, lat, n, margin=0.5):
+    """Random points inside the mesh: bilinear blend inside random cells (kept `margin` cells off the rim)."""
+    ny, nx = lon.shape
+    jj = rng.uniform(margin, ny - 1 - margin, n)
+    ii = rng.uniform(margin, nx - 1 - margin, n)
+    j0, i0 = jj.astype(int), ii.astype(int)
+    fj, fi = jj - j0, ii - i0
+
+    def bl(a):
+        a = a.astype(np.float64)
+        return ((1 - fj) * (1 - fi) * a[j0, i0] + (1 - fj) * fi * a[j0, i0 + 1] + fj * fi * a[j0 + 1, i0 + 1]
+                + fj * (1 - fi) * a[j0 + 1, i0])  # fmt: skip
+
+    return bl(lon), bl(lat)
+
+
 def _default(spec, k, v):
     return spec[k] if k in spec else v
 
@@ -115,6 +146,21 @@ CASES = {
     "through_surface": dict(seed=15, kind="smooth", cdtype="f8", ddtype="f4", mesh="flat", nx=15, ny=13, nz=6, nt=2,
                             tstep=4000.0, n=300, kernels=["AdvectionRK4_3D"], dt=200.0, segments=[dict(runtime=4000.0)],
                             delete=True, margin=0.02, wmax=0.2),
+    # ---- C-grid (CGrid_Velocity): curvilinear search with hint + spatial-hash fallback ----
+    "curv_flat_2d": dict(seed=21, kind="curv", cdtype="f8", mesh="flat", nx=31, ny=23, nz=1, nt=3, tstep=600.0, n=400,
+                         kernels=["AdvectionRK4"], dt=60.0, segments=[dict(runtime=600.0)], delete=True, umax=1.5),
+    "curv_sph_2d": dict(seed=22, kind="curv", cdtype="f8", mesh="spherical", nx=41, ny=33, nz=1, nt=3, tstep=7200.0, n=500,
+                        kernels=["AdvectionRK4"], dt=900.0, segments=[dict(runtime=14400.0)], delete=True, umax=20.0),
+    "curv_sph_3d": dict(seed=23, kind="curv", cdtype="f8", mesh="spherical", nx=31, ny=23, nz=6, nt=3, tstep=3600.0, n=400,
+                        kernels=["AdvectionRK4_3D"], dt=600.0, segments=[dict(runtime=7200.0)], delete=True, umax=15.0),
+    "curv_sph_f32": dict(seed=24, kind="curv", cdtype="f4", mesh="spherical", nx=31, ny=23, nz=1, nt=2, tstep=7200.0, n=300,
+                         kernels=["AdvectionRK4"], dt=600.0, segments=[dict(runtime=7200.0)], delete=True, umax=15.0),
+    "cgrid_rect_3d": dict(seed=25, kind="smooth", interp="cgrid_velocity", cdtype="f4", ddtype="f8", mesh="flat", nx=16,
+                          ny=13, nz=6, nt=4, tstep=200.0, n=400, kernels=["AdvectionRK4_3D"], dt=50.0,
+                          segments=[dict(runtime=600.0)], delete=True, margin=-0.02, umax=4.0),
+    "cgrid_rect_sph": dict(seed=26, kind="smooth", interp="cgrid_velocity", cdtype="f8", ddtype="f4", mesh="spherical",
+                           nx=21, ny=17, nz=5, nt=3, tstep=3600.0, n=300, kernels=["AdvectionRK4"], dt=600.0,
+                           segments=[dict(runtime=7200.0)], delete=True, margin=0.02, umax=10.0),
 }
 
 
@@ -134,9 +180,27 @@ def build(spec):
         out["z"] = np.zeros(n)
         out["t"] = np.zeros(n)
         return out
+    if spec["kind"] == "curv":
+        cd = np.dtype(spec["cdtype"])
+        nx, ny, nz, nt = spec["nx"], spec["ny"], spec["nz"], spec["nt"]
+        lon, lat = curv_mesh(ny, nx, mesh == "spherical", cd)
+        three_d = spec["kernels"][0].endswith("_3D")
+        depth = (np.linspace(0, 1, nz) ** 1.4 * 200.0).astype(cd) if nz > 1 else None
+        shape = (nt, nz, ny, nx)
+        umax = spec["umax"]
+        U = (umax * rng.uniform(-1, 1, shape)).astype(np.float32)
+        V = (umax * rng.uniform(-1, 1, shape)).astype(np.float32)
+        W = (1e-2 * rng.uniform(-1, 1, shape)).astype(np.float32) if three_d else None
+        x, y = points_in_mesh(rng, lon, lat, n)
+        z = rng.uniform(2.0, 190.0, n) if nz > 1 else np.zeros(n)
+        out.update(lon=lon, lat=lat, depth=depth, times=np.arange(nt) * spec["tstep"], U=U, V=V, W=W, x=x, y=y, z=z,
+                   t=np.zeros(n), interp="cgrid_velocity", padding=("low", "low", "high"))  # fmt: skip
+        return out
     cd = np.dtype(spec["cdtype"])
     dd = np.dtype(spec["ddtype"])
     nx, ny, nz, nt = spec["nx"], spec["ny"], spec["nz"], spec["nt"]
+    if "interp" in spec:
+        out["interp"] = spec["interp"]
     if mesh == "spherical":
         lon = np.linspace(-10.0, 10.0, nx).astype(cd)
         lat = np.linspace(30.0, 50.0, ny).astype(cd)

@@ -9,7 +9,8 @@ import parcels_b200 as pb
 
 def make_fieldset(c):
     fs = pb.FieldSet.from_arrays(lon=c["lon"], lat=c["lat"], depth=c["depth"], time=c["times"], U=c["U"], V=c["V"],
-                                 W=c["W"], mesh=c["mesh"])  # fmt: skip
+                                 W=c["W"], mesh=c["mesh"], interp_method=c.get("interp", "linear"),
+                                 padding=c.get("padding", ("low", "low", "high")))  # fmt: skip
     for k, v in (c["constants"] or {}).items():
         fs.add_constant_field(k, v, mesh=c["mesh"])
     return fs

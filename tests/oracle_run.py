@@ -17,7 +17,8 @@ _KERNELS = {
 
 
 def oracle_fieldset(c):
-    g = po.OGrid(c["lon"], c["lat"], c["depth"], mesh=c["mesh"])
+    pad = c.get("padding", ("low", "low", "high"))
+    g = po.OGrid(c["lon"], c["lat"], c["depth"], mesh=c["mesh"], offsets=tuple(int(p == "low") for p in pad))
     return po.OFieldSet(g, c["U"], c["V"], c["W"], time=c["times"], constants=c["constants"],
                         interp=c.get("interp", "linear"))  # fmt: skip
 

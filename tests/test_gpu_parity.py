@@ -25,7 +25,8 @@ pytestmark = pytest.mark.gpu
 
 ERR_NAME = {60: "FieldOutOfBoundError", 61: "FieldOutOfBoundSurfaceError", 70: "OutsideTimeInterval",
             51: "FieldInterpolationError", 52: "GridSearchingError", 50: "GeneralError"}  # fmt: skip
-FLAT_EXACT = {"flat_f32c_f64d", "c1_peninsula", "delayed_partial", "raise_oob", "raise_time", "rk2_3d", "through_surface"}
+FLAT_EXACT = {"flat_f32c_f64d", "c1_peninsula", "delayed_partial", "raise_oob", "raise_time", "rk2_3d", "through_surface",
+              "cgrid_rect_3d", "curv_flat_2d"}
 NON_DIFFUSION = [n for n in cases.CASES if "DiffusionUniformKh" not in cases.CASES[n]["kernels"]]
 
 
@@ -70,14 +71,16 @@ def test_engine_matches_reference_outputs(name, golden_dir):
     _compare(name, ps._data, ref, name in FLAT_EXACT)
 
 
-def test_engine_reproduces_v3_jit_goldens(golden_dir):
+@pytest.mark.parametrize("interp", ["linear", "cgrid_velocity"])
+def test_engine_reproduces_v3_jit_goldens(golden_dir, interp):
     """The reference's own regression test (tests/test_interpolation.py:297-378), atol 1e-6."""
     import parcels_b200 as pb
 
-    g = np.load(os.path.join(golden_dir, "v3_jit_linear.npz"))
+    g = np.load(os.path.join(golden_dir, "v3_jit_linear.npz" if interp == "linear" else "v3_jit_cgrid.npz"))
     lon, lat, depth = (g[k].astype(np.float32) for k in ("lon", "lat", "depth"))
     x, y, z = np.meshgrid(np.linspace(0, 1, 7), np.linspace(0, 1, 13), np.linspace(0, 1, 5))
-    fs = pb.FieldSet.from_arrays(lon=lon, lat=lat, depth=depth, time=g["time"], U=g["U"], V=g["V"], W=g["W"], mesh="flat")
+    fs = pb.FieldSet.from_arrays(lon=lon, lat=lat, depth=depth, time=g["time"], U=g["U"], V=g["V"], W=g["W"], mesh="flat",
+                                 interp_method=interp, padding=("low", "low", "high"))  # fmt: skip
     ps = pb.ParticleSet(fs, x=x, y=y, z=z, t=np.zeros(x.size))
     n = x.size
     obs = {k: np.full((n, 5), np.nan, dtype=np.float32) for k in "xyz"}

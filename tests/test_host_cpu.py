@@ -37,7 +37,7 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layouts_match_header():
     import ctypes
 
-    assert ctypes.sizeof(_lib.AdvectArgs) == 4 * 4 + 5 * 8 + 2 * 8 + 8
+    assert ctypes.sizeof(_lib.AdvectArgs) == 4 * 4 + 5 * 8 + 2 * 8 + 8 + 2 * 4
     assert ctypes.sizeof(_lib.Report) == 7 * 8 + 2 * 4 + 2 * 4
 
 
@@ -124,3 +124,23 @@ def test_philox_known_answer():
     assert [int(o[0]) for o in out] == [0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD]
     zx, zy = wiener_normals(7, 1, 0, np.arange(200000))
     assert abs(zx.mean()) < 0.01 and abs(zy.std() - 1) < 0.01
+
+
+def test_host_spatial_hash_equals_oracle_table():
+    """The product's host-side table build must give the reference's table (here: via the oracle
+    restatement, itself pinned to the reference's own SpatialHash by tests/test_oracle_vs_reference.py)."""
+    import cases
+    from oracle import curvilinear_oracle as co
+    from oracle import parcels_oracle as po
+    from parcels_b200.spatialhash import build_spatial_hash
+
+    for spherical, cd in ((False, "f8"), (True, "f8"), (True, "f4")):
+        lon, lat = cases.curv_mesh(23, 31, spherical, np.dtype(cd))
+        h = build_spatial_hash(lon, lat, spherical)
+        o = co.OHash(po.OGrid(lon, lat, None, mesh="spherical" if spherical else "flat"))
+        assert h["bitwidth"] == o.bitwidth
+        np.testing.assert_array_equal(h["keys"], o.keys)
+        np.testing.assert_array_equal(h["starts"], o.starts)
+        np.testing.assert_array_equal(h["counts"], o.counts)
+        np.testing.assert_array_equal(h["faces"], o.faces)
+        np.testing.assert_array_equal(h["box"], np.array([float(b) for b in o.box]))

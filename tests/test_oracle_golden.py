@@ -41,15 +41,19 @@ def _v3_case(g):
     return lon, lat, depth, x.flatten(), y.flatten(), z.flatten()
 
 
-def test_oracle_reproduces_v3_jit_goldens(golden_dir):
-    g = np.load(os.path.join(golden_dir, "v3_jit_linear.npz"))
+@pytest.mark.parametrize("interp", ["linear", "cgrid_velocity"])
+def test_oracle_reproduces_v3_jit_goldens(golden_dir, interp):
+    g = np.load(os.path.join(golden_dir, "v3_jit_linear.npz" if interp == "linear" else "v3_jit_cgrid.npz"))
     lon, lat, depth, x, y, z = _v3_case(g)
-    fs = po.OFieldSet(po.OGrid(lon, lat, depth, mesh="flat"), g["U"], g["V"], g["W"], time=g["time"])
+    fs = po.OFieldSet(po.OGrid(lon, lat, depth, mesh="flat", offsets=(1, 1, 0)), g["U"], g["V"], g["W"], time=g["time"],
+                      interp=interp)  # fmt: skip
     pd = po.create_particle_data(x, y, z, 0.0)
     n = len(x)
     obs = {k: np.full((n, 4), np.nan, dtype=np.float32) for k in "xyz"}
 
-    def on_output(pdata, _t, state={"i": 0}):
+    state = {"i": 0}
+
+    def on_output(pdata, _t):
         i = state["i"]
         if i < 4:
             for k in "xyz":
