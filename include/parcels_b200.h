@@ -174,6 +174,16 @@ int32_t pb_advect(pb_engine* e, const pb_advect_args* args, pb_report* rep);
 int32_t pb_advect_async(pb_engine* e, const pb_advect_args* args);
 int32_t pb_last_report(pb_engine* e, pb_report* rep);
 
+/* VectorField.eval at n arbitrary sample points (fieldset.UV[t, z, y, x] / fieldset.UVW[...],
+ * _core/field.py:250-304): time + grid search, interpolation, unit conversion, error states
+ * (state_out starts at Evaluate and is raised like particles.state), ei_out = ravel_index of the cell.
+ * positions_are_f32 = 1 evaluates with float32 positions (a particle's own arrays), 0 with float64
+ * (an RK stage position) -- the reference's arithmetic promotes on that dtype.  ei_hint (may be NULL)
+ * seeds the curvilinear search like particles.ei does; no_hint = 1 skips the hint test. */
+int32_t pb_sample_velocity(pb_engine* e, int64_t n, const double* t, const double* z, const double* y, const double* x,
+                           int32_t positions_are_f32, int32_t three_d, const int32_t* ei_hint, int32_t no_hint,
+                           double* u, double* v, double* w, int32_t* ei_out, int32_t* state_out);
+
 /* Marks every particle currently in state Evaluate/Success whose time-to-endtime >= 0 with
  * ErrorOutsideTimeInterval (70): the reference flags the WHOLE evaluated view when any particle
  * samples outside the time interval (_core/index_search.py:85-86, _core/field.py:31-44). */

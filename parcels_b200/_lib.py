@@ -86,6 +86,7 @@ SYMBOLS = {
     "pb_advect": (C.c_int32, [_P, C.POINTER(AdvectArgs), C.POINTER(Report)]),
     "pb_advect_async": (C.c_int32, [_P, C.POINTER(AdvectArgs)]),
     "pb_last_report": (C.c_int32, [_P, C.POINTER(Report)]),
+    "pb_sample_velocity": (C.c_int32, [_P, C.c_int64, _P, _P, _P, _P, C.c_int32, C.c_int32, _P, C.c_int32, _P, _P, _P, _P, _P]),
     "pb_flag_view_outside_time": (C.c_int32, [_P, C.c_double, C.c_double]),
     "pb_debug_normals": (C.c_int32, [_P, C.c_uint64, C.c_uint64, C.c_int64, C.c_int64, _P, _P]),
 }

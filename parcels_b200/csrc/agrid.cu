@@ -198,3 +198,18 @@ cudaError_t launch_agrid(const AdvectParams& p, bool coord_f64, bool data_f64, b
     if (coord_f64) return data_f64 ? launch_ad<double, double>(p, has_time, nc, s) : launch_ad<double, float>(p, has_time, nc, s);
     return data_f64 ? launch_ad<float, double>(p, has_time, nc, s) : launch_ad<float, float>(p, has_time, nc, s);
 }
+
+template <class A, class D, bool HT, int NC>
+static cudaError_t sample1(const SampleParams& p, cudaStream_t s) {
+    sample_kernel<AGridPolicy<A, D, HT, NC>><<<(unsigned)((p.n + 127) / 128), 128, 0, s>>>(p);
+    return cudaGetLastError();
+}
+template <class A, class D>
+static cudaError_t sample_ad(const SampleParams& p, bool ht, int nc, cudaStream_t s) {
+    if (ht) return nc == 3 ? sample1<A, D, true, 3>(p, s) : sample1<A, D, true, 2>(p, s);
+    return nc == 3 ? sample1<A, D, false, 3>(p, s) : sample1<A, D, false, 2>(p, s);
+}
+cudaError_t launch_sample_agrid(const SampleParams& p, bool coord_f64, bool data_f64, bool has_time, int nc, cudaStream_t s) {
+    if (coord_f64) return data_f64 ? sample_ad<double, double>(p, has_time, nc, s) : sample_ad<double, float>(p, has_time, nc, s);
+    return data_f64 ? sample_ad<float, double>(p, has_time, nc, s) : sample_ad<float, float>(p, has_time, nc, s);
+}

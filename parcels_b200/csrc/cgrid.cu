@@ -447,3 +447,18 @@ cudaError_t launch_cgrid(const AdvectParams& p, bool coord_f64, bool data_f64, i
     if (coord_f64) return data_f64 ? launch_ad<double, double>(p, nc, s) : launch_ad<double, float>(p, nc, s);
     return data_f64 ? launch_ad<float, double>(p, nc, s) : launch_ad<float, float>(p, nc, s);
 }
+
+template <class A, class D, int NC, bool CURV>
+static cudaError_t sample1(const SampleParams& p, cudaStream_t s) {
+    sample_kernel<CGridPolicy<A, D, NC, CURV>><<<(unsigned)((p.n + 127) / 128), 128, 0, s>>>(p);
+    return cudaGetLastError();
+}
+template <class A, class D>
+static cudaError_t sample_ad(const SampleParams& p, int nc, cudaStream_t s) {
+    if (p.g.curvilinear) return nc == 3 ? sample1<A, D, 3, true>(p, s) : sample1<A, D, 2, true>(p, s);
+    return nc == 3 ? sample1<A, D, 3, false>(p, s) : sample1<A, D, 2, false>(p, s);
+}
+cudaError_t launch_sample_cgrid(const SampleParams& p, bool coord_f64, bool data_f64, int nc, cudaStream_t s) {
+    if (coord_f64) return data_f64 ? sample_ad<double, double>(p, nc, s) : sample_ad<double, float>(p, nc, s);
+    return data_f64 ? sample_ad<float, double>(p, nc, s) : sample_ad<float, float>(p, nc, s);
+}

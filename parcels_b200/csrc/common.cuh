@@ -336,6 +336,52 @@ __global__ void __launch_bounds__(128) advect_kernel(const AdvectParams p) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// VectorField.eval on arbitrary sample points (reference _core/field.py:250-304): one lane per sample.
+// Used by the public FieldSet.UV/UVW.eval() of the host mirror and by the parity tests to pin a
+// single evaluation (indices, state, velocities) against the oracle.
+// ------------------------------------------------------------------------------------------------
+struct SampleParams {
+    GridDev g;
+    FieldDev f;
+    long long n;
+    const double* t;
+    const double* z;
+    const double* y;
+    const double* x;
+    const int* ei_hint;  // may be NULL (no hint)
+    int pos_f32;         // 1: positions are float32 values (the particle's own arrays), 0: float64
+    int no_hint;
+    double* u;
+    double* v;
+    double* w;
+    int* ei_out;
+    int* state_out;
+};
+
+template <class Policy>
+__global__ void sample_kernel(const SampleParams s) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= s.n) return;
+    AdvectParams p{};
+    p.g = s.g;
+    p.f = s.f;
+    typename Policy::Ctx e;
+    Policy::init(e, p, s.ei_hint ? s.ei_hint[i] : 0);
+    e.state = PB_EVALUATE;
+    e.refills = 0;
+    e.out_of_time = false;
+    Val u, v, w;
+    const bool nh = s.no_hint || !s.ei_hint;
+    if (s.pos_f32) Policy::template eval<float, float, float>(p, e, nh, s.t[i], (float)s.z[i], (float)s.y[i], (float)s.x[i], u, v, w);
+    else Policy::template eval<double, double, double>(p, e, nh, s.t[i], s.z[i], s.y[i], s.x[i], u, v, w);
+    s.u[i] = u.v; s.v[i] = v.v; s.w[i] = w.v;
+    s.ei_out[i] = e.ei;
+    s.state_out[i] = e.state;
+}
+
 // launchers implemented in agrid.cu / cgrid.cu (one translation unit per grid family keeps nvcc parallel)
 cudaError_t launch_agrid(const AdvectParams& p, bool coord_f64, bool data_f64, bool has_time, int nc, cudaStream_t s);
 cudaError_t launch_cgrid(const AdvectParams& p, bool coord_f64, bool data_f64, int nc, cudaStream_t s);
+cudaError_t launch_sample_agrid(const SampleParams& p, bool coord_f64, bool data_f64, bool has_time, int nc, cudaStream_t s);
+cudaError_t launch_sample_cgrid(const SampleParams& p, bool coord_f64, bool data_f64, int nc, cudaStream_t s);

@@ -421,10 +421,80 @@ int32_t pb_particles_restore(pb_engine* e) {
 
 int64_t pb_particles_count(pb_engine* e) { return e ? e->n : -1; }
 
+static void fill_field_desc(pb_engine* e, FieldDev& f) {
+    const long long T = e->fshape[0][0], Z = e->fshape[0][1], Y = e->fshape[0][2], X = e->fshape[0][3];
+    for (int c = 0; c < 3; ++c) f.p[c] = e->fptr[c];
+    f.T = (int)T; f.Z = (int)Z; f.Y = (int)Y; f.X = (int)X;
+    f.sX = X > 1 ? 1 : 0;
+    f.sY = Y > 1 ? X : 0;
+    f.sZ = Z > 1 ? X * Y : 0;
+    f.sT = T > 1 ? X * Y * Z : 0;
+}
+
+// validation shared by pb_advect and pb_sample_velocity; nc = 2 (UV) or 3 (UVW)
+static int32_t check_fields(pb_engine* e, int nc) {
+    if (!e->have_grid) return fail(PB_ERR_STATE, "grid not uploaded (pb_grid_upload_*)");
+    if (!e->fptr[0] || !e->fptr[1]) return fail(PB_ERR_STATE, "U and V not uploaded");
+    if (nc == 3 && !e->fptr[2]) return fail(PB_ERR_STATE, "3-D evaluation needs a W field (fieldset.UVW)");
+    for (int c = 1; c < nc; ++c) {
+        if (e->f_f64[c] != e->f_f64[0]) return fail(PB_ERR_INVALID, "U, V, W must share one dtype");
+        for (int d = 0; d < 4; ++d)
+            if (e->fshape[c][d] != e->fshape[0][d]) return fail(PB_ERR_INVALID, "U, V, W must share one shape");
+    }
+    const long long T = e->fshape[0][0], Z = e->fshape[0][1], Y = e->fshape[0][2], X = e->fshape[0][3];
+    if ((X > 1 && X != e->g.nx) || (Y > 1 && Y != e->g.ny) || (Z > 1 && e->g.nz > 0 && Z != e->g.nz) ||
+        (T > 1 && e->g.nt > 0 && T != e->g.nt))
+        return fail(PB_ERR_INVALID, "field shape (%lld,%lld,%lld,%lld) does not match grid nodes (nt=%d nz=%d ny=%d nx=%d)", T, Z, Y, X,
+                    e->g.nt, e->g.nz, e->g.ny, e->g.nx);
+    if ((T > 1) != (e->g.nt > 0)) return fail(PB_ERR_INVALID, "field has %lld time levels but the grid time axis has %d", T, e->g.nt);
+    if (Z > 1 && e->g.nz == 0) return fail(PB_ERR_INVALID, "field has a depth dimension but the grid has no Z axis");
+    if (e->g.curvilinear && e->interp != PB_INTERP_CGRID_VELOCITY)
+        return fail(PB_ERR_INVALID, "curvilinear grids are only supported with CGrid_Velocity interpolation");
+    return PB_OK;
+}
+
+int32_t pb_sample_velocity(pb_engine* e, int64_t n, const double* t, const double* z, const double* y, const double* x,
+                           int32_t positions_are_f32, int32_t three_d, const int32_t* ei_hint, int32_t no_hint, double* u,
+                           double* v, double* w, int32_t* ei_out, int32_t* state_out) {
+    if (!e) return fail(PB_ERR_INVALID, "engine is NULL");
+    if (n < 0 || (n && (!t || !z || !y || !x || !u || !v || !w || !ei_out || !state_out))) return fail(PB_ERR_INVALID, "NULL argument");
+    const int nc = three_d ? 3 : 2;
+    int32_t rc = check_fields(e, nc);
+    if (rc) return rc;
+    if (n == 0) return PB_OK;
+    CK(cudaSetDevice(e->device));
+    double* d = nullptr;  // t z y x u v w
+    int* di = nullptr;    // hint ei state
+    CK(cudaMalloc(&d, (size_t)n * 7 * sizeof(double)));
+    CK(cudaMalloc(&di, (size_t)n * 3 * sizeof(int)));
+    const double* src[4] = {t, z, y, x};
+    for (int k = 0; k < 4; ++k) CK(cudaMemcpyAsync(d + k * n, src[k], n * 8, cudaMemcpyHostToDevice, e->stream));
+    if (ei_hint) CK(cudaMemcpyAsync(di, ei_hint, n * 4, cudaMemcpyHostToDevice, e->stream));
+    SampleParams sp{};
+    sp.g = e->g;
+    fill_field_desc(e, sp.f);
+    sp.n = n;
+    sp.t = d; sp.z = d + n; sp.y = d + 2 * n; sp.x = d + 3 * n;
+    sp.u = d + 4 * n; sp.v = d + 5 * n; sp.w = d + 6 * n;
+    sp.ei_hint = ei_hint ? di : nullptr;
+    sp.ei_out = di + n; sp.state_out = di + 2 * n;
+    sp.pos_f32 = positions_are_f32; sp.no_hint = no_hint;
+    cudaError_t ce = e->interp == PB_INTERP_CGRID_VELOCITY
+                         ? launch_sample_cgrid(sp, e->coord_f64 != 0, e->f_f64[0] != 0, nc, e->stream)
+                         : launch_sample_agrid(sp, e->coord_f64 != 0, e->f_f64[0] != 0, e->g.nt > 0, nc, e->stream);
+    if (ce != cudaSuccess) return fail(PB_ERR_CUDA, "sample_kernel launch failed: %s", cudaGetErrorString(ce));
+    double* dst[3] = {u, v, w};
+    for (int k = 0; k < 3; ++k) CK(cudaMemcpyAsync(dst[k], d + (4 + k) * n, n * 8, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemcpyAsync(ei_out, di + n, n * 4, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemcpyAsync(state_out, di + 2 * n, n * 4, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    cudaFree(d);
+    cudaFree(di);
+    return PB_OK;
+}
+
 int32_t pb_advect_async(pb_engine* e, const pb_advect_args* a) {
     if (!e || !a) return fail(PB_ERR_INVALID, "NULL argument");
-    if (!e->have_grid) return fail(PB_ERR_STATE, "pb_advect before pb_grid_upload_*");
-    if (!e->fptr[0] || !e->fptr[1]) return fail(PB_ERR_STATE, "pb_advect before U and V were uploaded");
     if (a->dt == 0.0 || a->dt != a->dt) return fail(PB_ERR_INVALID, "dt must be a non-zero number");
     int nc;
     switch (a->scheme) {
@@ -432,33 +502,16 @@ int32_t pb_advect_async(pb_engine* e, const pb_advect_args* a) {
         case PB_ADVECTION_RK2_3D: case PB_ADVECTION_RK4_3D: nc = 3; break;
         default: return fail(PB_ERR_INVALID, "unknown scheme %d", a->scheme);
     }
-    if (nc == 3 && !e->fptr[2]) return fail(PB_ERR_STATE, "3-D scheme needs a W field (fieldset.UVW)");
-    for (int c = 1; c < nc; ++c) {
-        if (e->f_f64[c] != e->f_f64[0]) return fail(PB_ERR_INVALID, "U, V, W must share one dtype");
-        for (int d = 0; d < 4; ++d)
-            if (e->fshape[c][d] != e->fshape[0][d]) return fail(PB_ERR_INVALID, "U, V, W must share one shape on an A-grid");
+    {
+        int32_t rc = check_fields(e, nc);
+        if (rc) return rc;
     }
-    if (e->g.curvilinear && e->interp != PB_INTERP_CGRID_VELOCITY)
-        return fail(PB_ERR_INVALID, "curvilinear grids are only supported with CGrid_Velocity interpolation");
     if (a->diffusion && !e->have_pid) return fail(PB_ERR_STATE, "diffusion needs particle_id (RNG counter)");
-    const long long T = e->fshape[0][0], Z = e->fshape[0][1], Y = e->fshape[0][2], X = e->fshape[0][3];
-    // A-grid data must match the node counts wherever the dim is indexed
-    if ((X > 1 && X != e->g.nx) || (Y > 1 && Y != e->g.ny) || (Z > 1 && e->g.nz > 0 && Z != e->g.nz) ||
-        (T > 1 && e->g.nt > 0 && T != e->g.nt))
-        return fail(PB_ERR_INVALID, "field shape (%lld,%lld,%lld,%lld) does not match grid nodes (nt=%d nz=%d ny=%d nx=%d)", T, Z, Y, X,
-                    e->g.nt, e->g.nz, e->g.ny, e->g.nx);
-    if ((T > 1) != (e->g.nt > 0)) return fail(PB_ERR_INVALID, "field has %lld time levels but the grid time axis has %d", T, e->g.nt);
-    if (Z > 1 && e->g.nz == 0) return fail(PB_ERR_INVALID, "field has a depth dimension but the grid has no Z axis");
     CK(cudaSetDevice(e->device));
 
     AdvectParams p{};
     p.g = e->g;
-    for (int c = 0; c < 3; ++c) p.f.p[c] = e->fptr[c];
-    p.f.T = (int)T; p.f.Z = (int)Z; p.f.Y = (int)Y; p.f.X = (int)X;
-    p.f.sX = X > 1 ? 1 : 0;
-    p.f.sY = Y > 1 ? X : 0;
-    p.f.sZ = Z > 1 ? X * Y : 0;
-    p.f.sT = T > 1 ? X * Y * Z : 0;
+    fill_field_desc(e, p.f);
     p.P = ParticlesDev{(float*)e->px.p, (float*)e->py.p, (float*)e->pz.p, (float*)e->pdx.p, (float*)e->pdy.p,
                        (float*)e->pdz.p, (double*)e->pt.p, (int*)e->pstate.p, (int*)e->pei.p, (long long*)e->ppid.p, e->n};
     p.scheme = a->scheme; p.diffusion = a->diffusion; p.delete_on_error = a->delete_on_error;

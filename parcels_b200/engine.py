@@ -160,6 +160,17 @@ class Engine:
         check(self._lib.pb_last_report(self._h, C.byref(rep)))
         return _report_dict(rep)
 
+    def sample_velocity(self, t, z, y, x, *, three_d, positions_are_f32=False, ei_hint=None, no_hint=False):
+        t, z, y, x = (np.ascontiguousarray(np.broadcast_to(np.asarray(a, dtype=np.float64), np.shape(x)).ravel()) for a in (t, z, y, x))
+        n = x.size
+        u, v, w = (np.empty(n, dtype=np.float64) for _ in range(3))
+        ei = np.empty(n, dtype=np.int32)
+        st = np.empty(n, dtype=np.int32)
+        hint = None if ei_hint is None else np.ascontiguousarray(ei_hint, dtype=np.int32)
+        check(self._lib.pb_sample_velocity(self._h, n, ptr(t), ptr(z), ptr(y), ptr(x), int(positions_are_f32), int(three_d),
+                                           ptr(hint), int(no_hint), ptr(u), ptr(v), ptr(w), ptr(ei), ptr(st)))  # fmt: skip
+        return u, v, w, ei, st
+
     def flag_view_outside_time(self, dt, endtime):
         check(self._lib.pb_flag_view_outside_time(self._h, float(dt), float(endtime)))
 

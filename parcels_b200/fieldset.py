@@ -89,6 +89,19 @@ class VectorField:
         self.grid = U.grid
         self.vector_type = "3D" if W is not None else "2D"
 
+    def eval(self, t, z, y, x, particles=None, *, device=0, positions_are_f32=False):
+        """``fieldset.UV.eval(t, z, y, x)`` (reference _core/field.py:250-295), evaluated ON THE DEVICE
+        (``pb_sample_velocity``).  Returns (u, v) or (u, v, w) float64 arrays; out-of-bounds samples are 0."""
+        fs = self.U._fieldset
+        u, v, w, _ei, _st = fs.engine(device).sample_velocity(t, z, y, x, three_d=self.W is not None,
+                                                              positions_are_f32=positions_are_f32)  # fmt: skip
+        shape = np.shape(np.atleast_1d(x))
+        out = (u.reshape(shape), v.reshape(shape)) + ((w.reshape(shape),) if self.W is not None else ())
+        return out
+
+    def __getitem__(self, key):
+        return self.eval(*key)
+
 
 class _ConstantGrid:
     """Grid of the constant fields (reference _core/model.py:292-318): one node, own mesh."""
