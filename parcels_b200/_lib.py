@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libparcels_b200.so")
+LIB_PATH = os.environ.get("PB_LIB", os.path.join(HERE, "lib", "libparcels_b200.so"))  # PB_LIB: tuning variants
 
 c_f32p = C.POINTER(C.c_float)
 c_f64p = C.POINTER(C.c_double)

@@ -8,6 +8,9 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SOURCES = ["engine.cu", "agrid.cu", "cgrid.cu"]  # one translation unit per kernel family: compiled in parallel
+# Per-source tuning (measured on B200, profiles/README.md): the A-grid kernel runs best with its corner
+# cache in shared memory and <= 96 registers (5 blocks of 128 threads per SM).
+EXTRA_FLAGS = {"agrid.cu": ["-DPB_MINBLOCKS=5", "-DPB_SMEM_CACHE"], "cgrid.cu": ["-DPB_MINBLOCKS=3"]}
 DEPS = [os.path.join(CSRC, f) for f in (*SOURCES, "common.cuh")]
 OUT = os.path.join(HERE, "lib", "libparcels_b200.so")
 HEADER = os.path.join(os.path.dirname(HERE), "include", "parcels_b200.h")
@@ -38,7 +41,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     procs = []
     for src in SOURCES:
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, *(["-Xptxas", "-v"] if verbose else []), "-c", "-o", obj, os.path.join(CSRC, src)]
+        cmd = [nvcc, *NVCC_FLAGS, *EXTRA_FLAGS.get(src, []), *(["-Xptxas", "-v"] if verbose else []), "-c", "-o", obj,
+               os.path.join(CSRC, src)]  # fmt: skip
         procs.append((cmd, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)))
     objs = []
     for cmd, obj, p in procs:

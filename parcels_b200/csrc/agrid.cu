@@ -7,10 +7,29 @@
 // corner cache + XLinear (reference interpolators/_xinterpolators.py:78-153)
 // ------------------------------------------------------------------------------------------------
 
+// PB_SMEM_CACHE: keep the corner block in shared memory ([value][thread] layout: conflict-free, one
+// column per lane) instead of registers -- frees 16*NC registers per thread for occupancy.
+#ifndef PB_BLOCK
+#define PB_BLOCK 128
+#endif
 template <class D, int NC>
 struct Corners {
     int ti, zi, yi, xi;  // key of the block held in v (INT_MIN: empty)
+#ifdef PB_SMEM_CACHE
+    D* sm;               // this lane's column of the block-shared cache
+    __device__ __forceinline__ void put(int c, int k, D val) { sm[(c * 16 + k) * PB_BLOCK] = val; }
+    __device__ __forceinline__ void load(int c, D (&out)[16]) const {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) out[k] = sm[(c * 16 + k) * PB_BLOCK];
+    }
+#else
     D v[NC][16];         // [component][(t*2+z)*4 + y*2 + x]
+    __device__ __forceinline__ void put(int c, int k, D val) { v[c][k] = val; }
+    __device__ __forceinline__ void load(int c, D (&out)[16]) const {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) out[k] = v[c][k];
+    }
+#endif
 
     __device__ __forceinline__ void fill(const FieldDev& f, int nti, int nzi, int nyi, int nxi) {
         ti = nti; zi = nzi; yi = nyi; xi = nxi;
@@ -23,7 +42,7 @@ struct Corners {
             const D* __restrict__ base = (const D*)f.p[c];
 #pragma unroll
             for (int k = 0; k < 16; ++k)
-                v[c][k] = ldg(base + ot[k >> 3] + oz[(k >> 2) & 1] + oy[(k >> 1) & 1] + ox[k & 1]);
+                put(c, k, ldg(base + ot[k >> 3] + oz[(k >> 2) & 1] + oy[(k >> 1) & 1] + ox[k & 1]));
         }
     }
 };
@@ -57,17 +76,39 @@ __device__ __forceinline__ Val zlerp_bilinear(const C (&c)[8], TZ zeta, TY eta, 
 // same, and so is the dtype whenever the particles of a batch share their clock.
 template <class D, class TT, class TZ, class TY, class TX>
 __device__ __forceinline__ Val xlinear(const D (&v)[16], TT tau, TZ zeta, TY eta, TX xsi) {
-    if (tau > 0) {
-        using R = prom_t<D, TT>;
-        R r[8];
+    if constexpr (std::is_same<TZ, double>::value && std::is_same<TY, double>::value && std::is_same<TX, double>::value) {
+        // Every barycentric coordinate is float64 (float64 grid, or an RK stage position): all arithmetic
+        // after the gather is float64 whatever D is, and a float32 corner value converts exactly.  One code
+        // path; a skipped lerp just copies (x*(1-0) + y*0 == x would differ only for non-finite y).
+        double r[8];
+        if (tau > 0) {
+            const double omt = 1 - (double)tau;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) r[k] = v[k] * (1 - tau) + v[8 + k] * tau;
-        return zlerp_bilinear<R, TZ, TY, TX>(r, zeta, eta, xsi);
+            for (int k = 0; k < 8; ++k) r[k] = (double)v[k] * omt + (double)v[8 + k] * (double)tau;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) r[k] = (double)v[k];
+        }
+        if (zeta > 0) {
+            const double omz = 1 - zeta;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) r[k] = r[k] * omz + r[4 + k] * zeta;
+        }
+        const double q = (1 - xsi) * (1 - eta) * r[0] + xsi * (1 - eta) * r[1] + (1 - xsi) * eta * r[2] + xsi * eta * r[3];
+        return Val{q, false};
     } else {
-        D r[8];
+        if (tau > 0) {
+            using R = prom_t<D, TT>;
+            R r[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) r[k] = v[k];
-        return zlerp_bilinear<D, TZ, TY, TX>(r, zeta, eta, xsi);
+            for (int k = 0; k < 8; ++k) r[k] = v[k] * (1 - tau) + v[8 + k] * tau;
+            return zlerp_bilinear<R, TZ, TY, TX>(r, zeta, eta, xsi);
+        } else {
+            D r[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) r[k] = v[k];
+            return zlerp_bilinear<D, TZ, TY, TX>(r, zeta, eta, xsi);
+        }
     }
 }
 
@@ -79,6 +120,9 @@ struct EvalCtx {
     AxisCell<A> cx, cy, cz;
     AxisCell<double> ct;
     Corners<D, NC> cor;
+    double last_t, last_tau;  // stages 2 and 3 of a step (and stage 4 / next stage 1) sample the same time
+    int szi, syi, sxi;        // indices of the last completed search: ei is raveled once, on exit
+    bool searched;
     int state;
     int ei;
     unsigned int refills;
@@ -107,7 +151,13 @@ __device__ __forceinline__ void eval_uvw(const GridDev& g, const FieldDev& f, Ev
             u = Val{0.0, false}; v = u; w = u;
             return;
         }
-        tau = (TT)axis_search<double, double>(g.time, g.nt, t, e.ct);
+        if (t == e.last_t) {
+            tau = (TT)e.last_tau;
+        } else {
+            tau = (TT)axis_search<double, double>(g.time, g.nt, t, e.ct);
+            e.last_t = t;
+            e.last_tau = (double)tau;
+        }
         ti = e.ct.idx;
     }
     // -- XGrid.search (xgrid.py:316-356)
@@ -121,10 +171,10 @@ __device__ __forceinline__ void eval_uvw(const GridDev& g, const FieldDev& f, Ev
     TX xsi = axis_search<PX, A>((const A*)g.lon, g.nx, x, e.cx);
     const int yi = e.cy.idx, xi = e.cx.idx;
 
-    // -- particles.ei[:, igrid] = ravel_index (field.py:307-317, basegrid.py:259-278); int64 -> int32
-    long long r = (long long)yi * g.xdim + (long long)xi;
-    if (g.nz > 0) r += (long long)zi * (g.ydim * g.xdim);
-    e.ei = (int)r;
+    // -- particles.ei[:, igrid] = ravel_index(zi, yi, xi) (field.py:307-317): only the LAST eval's value
+    //    survives, so the indices are kept and raveled once on exit (AGridPolicy::finish)
+    e.szi = zi; e.syi = yi; e.sxi = xi;
+    e.searched = true;
 
     // -- state from positions (field.py:327-356).  X/Y index -2 is NOT an error in the reference.
     int s = e.state;
@@ -137,8 +187,11 @@ __device__ __forceinline__ void eval_uvw(const GridDev& g, const FieldDev& f, Ev
         e.refills++;
     }
 
-    u = xlinear<D, TT, TZ, TY, TX>(e.cor.v[0], tau, zeta, eta, xsi);
-    v = xlinear<D, TT, TZ, TY, TX>(e.cor.v[1], tau, zeta, eta, xsi);
+    D blk[16];
+    e.cor.load(0, blk);
+    u = xlinear<D, TT, TZ, TY, TX>(blk, tau, zeta, eta, xsi);
+    e.cor.load(1, blk);
+    v = xlinear<D, TT, TZ, TY, TX>(blk, tau, zeta, eta, xsi);
     if (g.spherical) {  // u /= deg2m * cos(deg2rad(y)); v /= deg2m   (in-place: result keeps u's dtype)
         PY conv = (PY)g.deg2m * cos_np(deg2rad_np(y));
         if (u.f32 && std::is_same<PY, float>::value) {
@@ -150,7 +203,8 @@ __device__ __forceinline__ void eval_uvw(const GridDev& g, const FieldDev& f, Ev
         v.v = v.f32 ? (double)((float)v.v / (float)g.deg2m) : v.v / g.deg2m;
     }
     if (NC == 3) {
-        w = xlinear<D, TT, TZ, TY, TX>(e.cor.v[NC - 1], tau, zeta, eta, xsi);
+        e.cor.load(NC - 1, blk);
+        w = xlinear<D, TT, TZ, TY, TX>(blk, tau, zeta, eta, xsi);
     } else {
         w = Val{0.0, u.f32};
     }
@@ -171,7 +225,22 @@ struct AGridPolicy {
         e.cx.lo = e.cx.hi = e.cy.lo = e.cy.hi = e.cz.lo = e.cz.hi = (A)0;
         e.ct.lo = e.ct.hi = 0.0;
         e.cor.ti = e.cor.zi = e.cor.yi = e.cor.xi = INT_MIN;
+#ifdef PB_SMEM_CACHE
+        extern __shared__ __align__(16) unsigned char pb_smem[];
+        e.cor.sm = reinterpret_cast<D*>(pb_smem) + threadIdx.x;
+#endif
         e.ei = ei;
+        e.last_t = -1.0;  // valid sample times are >= 0
+        e.last_tau = 0.0;
+        e.searched = false;
+        e.szi = e.syi = e.sxi = 0;
+    }
+    // ravel_index (basegrid.py:259-278) over the axes present; int64 arithmetic stored to int32
+    __device__ static __forceinline__ void finish(Ctx& e, const AdvectParams& p) {
+        if (!e.searched) return;
+        long long r = (long long)e.syi * p.g.xdim + (long long)e.sxi;
+        if (p.g.nz > 0) r += (long long)e.szi * (p.g.ydim * p.g.xdim);
+        e.ei = (int)r;
     }
     template <class PZ, class PY, class PX>
     __device__ static __forceinline__ void eval(const AdvectParams& p, Ctx& e, bool /*no_hint*/, double t, PZ z, PY y, PX x,
@@ -182,9 +251,18 @@ struct AGridPolicy {
 
 template <class A, class D, bool HT, int NC>
 static cudaError_t launch1(const AdvectParams& p, cudaStream_t s) {
-    const int block = 128;
+    const int block = PB_BLOCK;
     const long long grid = (p.P.n + block - 1) / block;
-    advect_kernel<AGridPolicy<A, D, HT, NC>><<<(unsigned)grid, block, 0, s>>>(p);
+#ifdef PB_SMEM_CACHE
+    const size_t smem = (size_t)NC * 16 * sizeof(D) * PB_BLOCK;
+    if (smem > 48 * 1024) {
+        cudaError_t ce = cudaFuncSetAttribute(advect_kernel<AGridPolicy<A, D, HT, NC>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (ce != cudaSuccess) return ce;
+    }
+#else
+    const size_t smem = 0;
+#endif
+    advect_kernel<AGridPolicy<A, D, HT, NC>><<<(unsigned)grid, block, smem, s>>>(p);
     return cudaGetLastError();
 }
 
@@ -201,7 +279,16 @@ cudaError_t launch_agrid(const AdvectParams& p, bool coord_f64, bool data_f64, b
 
 template <class A, class D, bool HT, int NC>
 static cudaError_t sample1(const SampleParams& p, cudaStream_t s) {
-    sample_kernel<AGridPolicy<A, D, HT, NC>><<<(unsigned)((p.n + 127) / 128), 128, 0, s>>>(p);
+#ifdef PB_SMEM_CACHE
+    const size_t smem = (size_t)NC * 16 * sizeof(D) * PB_BLOCK;
+    if (smem > 48 * 1024) {
+        cudaError_t ce = cudaFuncSetAttribute(sample_kernel<AGridPolicy<A, D, HT, NC>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (ce != cudaSuccess) return ce;
+    }
+#else
+    const size_t smem = 0;
+#endif
+    sample_kernel<AGridPolicy<A, D, HT, NC>><<<(unsigned)((p.n + PB_BLOCK - 1) / PB_BLOCK), PB_BLOCK, smem, s>>>(p);
     return cudaGetLastError();
 }
 template <class A, class D>

@@ -284,6 +284,8 @@ struct CGridPolicy {
         }
     }
 
+    __device__ static __forceinline__ void finish(Ctx&, const AdvectParams&) {}
+
     template <class PZ, class PY, class PX>
     __device__ static __forceinline__ void eval(const AdvectParams& p, Ctx& e, bool no_hint, double t, PZ z, PY y, PX x, Val& u,
                                                 Val& v, Val& w) {

@@ -197,8 +197,16 @@ __device__ __forceinline__ double half_of(const Val& a) { return a.f32 ? (double
 // ------------------------------------------------------------------------------------------------
 // Policy supplies: Ctx (with members state, ei, refills, out_of_time), init(Ctx&, params, ei), and
 //   eval<PZ,PY,PX>(params, Ctx&, no_hint, t, z, y, x, u, v, w)  == VectorField.eval for one particle.
+#ifndef PB_MINBLOCKS
+#define PB_MINBLOCKS 3
+#endif
+#ifdef PB_BLOCK
+#define PB_BLOCK_THREADS PB_BLOCK
+#else
+#define PB_BLOCK_THREADS 128
+#endif
 template <class Policy>
-__global__ void __launch_bounds__(128) advect_kernel(const AdvectParams p) {
+__global__ void __launch_bounds__(PB_BLOCK_THREADS, PB_MINBLOCKS) advect_kernel(const AdvectParams p) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long my_steps = 0, my_refills = 0;
     int final_state = 0;
@@ -219,9 +227,10 @@ __global__ void __launch_bounds__(128) advect_kernel(const AdvectParams p) {
         e.out_of_time = false;
 
         const int sign = p.dt > 0 ? 1 : -1;
-        const bool three_d = (p.scheme == PB_ADVECTION_RK4_3D || p.scheme == PB_ADVECTION_RK2_3D);
+        constexpr bool three_d = (Policy::NC == 3);  // RK4_3D / RK2_3D sample fieldset.UVW, the others fieldset.UV
         const int nstage = (p.scheme == PB_ADVECTION_EE) ? 1 : ((p.scheme == PB_ADVECTION_RK2 || p.scheme == PB_ADVECTION_RK2_3D) ? 2 : 4);
 
+        bool ei_zeroed = false;
         long long it = 0;
         for (;; ++it) {
             if (p.max_iters >= 0 && it >= p.max_iters) break;
@@ -244,7 +253,7 @@ __global__ void __launch_bounds__(128) advect_kernel(const AdvectParams p) {
                 const double xs = (double)x + (full ? uk.v : half_of(uk)) * dtp;
                 const double ys = (double)y + (full ? vk.v : half_of(vk)) * dtp;
                 const double ts = t + (full ? dtp : 0.5 * dtp);
-                if (three_d) {
+                if constexpr (three_d) {
                     const double zs = (double)z + (full ? wk.v : half_of(wk)) * dtp;
                     Policy::template eval<double, double, double>(p, e, false, ts, zs, ys, xs, uk, vk, wk);
                 } else {
@@ -281,7 +290,7 @@ __global__ void __launch_bounds__(128) advect_kernel(const AdvectParams p) {
                 const double bx = sqrt(2 * khz), by = sqrt(2 * khm);
                 dx = (float)((double)dx + bx * dWx);
                 dy = (float)((double)dy + by * dWy);
-                e.ei = 0;  // the constant-field evals overwrite ei[:, -1] with cell 0 (model.py:292-318)
+                ei_zeroed = true;  // the constant-field evals overwrite ei[:, -1] with cell 0 (model.py:292-318)
             }
             // ---- trailing error handler: every error state becomes Delete ----
             if (p.delete_on_error && e.state >= 50) e.state = PB_DELETE;
@@ -296,6 +305,8 @@ __global__ void __launch_bounds__(128) advect_kernel(const AdvectParams p) {
             if (e.state == PB_DELETE) { deleted = true; ++it; break; }
             if (e.state >= 50) { errored = true; err_iter = it; ++it; break; }
         }
+        Policy::finish(e, p);
+        if (ei_zeroed) e.ei = 0;
         my_iters = it;
         my_refills = e.refills;
         oot = e.out_of_time;
@@ -376,6 +387,7 @@ __global__ void sample_kernel(const SampleParams s) {
     if (s.pos_f32) Policy::template eval<float, float, float>(p, e, nh, s.t[i], (float)s.z[i], (float)s.y[i], (float)s.x[i], u, v, w);
     else Policy::template eval<double, double, double>(p, e, nh, s.t[i], s.z[i], s.y[i], s.x[i], u, v, w);
     s.u[i] = u.v; s.v[i] = v.v; s.w[i] = w.v;
+    Policy::finish(e, p);
     s.ei_out[i] = e.ei;
     s.state_out[i] = e.state;
 }
