@@ -148,7 +148,8 @@ typedef struct pb_advect_args {
     int32_t hint_all_zero;     /* curvilinear grids: 1 when the hinted xi (unravel of ei) of every
                                   evaluated particle is 0 -- the reference then skips the hint test for
                                   the whole batch at the first eval (_core/index_search.py:269-282)   */
-    int32_t reserved;
+    int32_t resume;            /* 1: continue the same Kernel.execute call after a migration round
+                                  (mode D): particle states are NOT reset to Evaluate            */
 } pb_advect_args;
 
 typedef struct pb_report {
@@ -159,6 +160,7 @@ typedef struct pb_report {
     int64_t n_out_of_time;     /* particles that sampled outside the time interval (state 70)    */
     int64_t max_iters_done;    /* largest per-particle iteration count                          */
     int64_t cache_refills;     /* corner-cache refills (diagnostic: HBM gathers actually made)   */
+    int64_t n_migrate;         /* mode D: particles that left the owned slab and wait for migration */
     int32_t max_state;
     int32_t reserved;
     float kernel_ms;           /* CUDA-event time of the advection kernel on the engine stream   */
@@ -183,6 +185,25 @@ int32_t pb_last_report(pb_engine* e, pb_report* rep);
 int32_t pb_sample_velocity(pb_engine* e, int64_t n, const double* t, const double* z, const double* y, const double* x,
                            int32_t positions_are_f32, int32_t three_d, const int32_t* ei_hint, int32_t no_hint,
                            double* u, double* v, double* w, int32_t* ei_out, int32_t* state_out);
+
+/* ---- multi-GPU mode D: X-slab domain decomposition with particle migration ------------
+ * The reference has no distributed layer; this is new.  Each rank's engine holds the columns
+ * lon[xi_offset : xi_offset + nx_local] of the global rectilinear grid (its owned columns + a halo) and the
+ * matching field slab; pass the GLOBAL xdim_cells to pb_grid_upload_rectilinear so that `ei` stays global.
+ * bounds[nranks+1]: rank r advances particles with bounds[r] <= x < bounds[r+1] (rank 0 also everything left
+ * of bounds[1], the last rank everything right of bounds[nranks-1]); pb_advect stops a particle as soon as
+ * it leaves the owned interval (pb_report.n_migrate).  A stage position outside owned+halo columns is a
+ * halo violation: state 99, counted in n_error.
+ * Migration round: pb_migrate_count -> (exchange counts) -> pb_migrate_pack -> all-to-all-v of the 48-byte
+ * records over NCCL -> pb_migrate_unpack (compacts the stayers, appends the arrivals) -> pb_advect(resume=1). */
+int32_t pb_decomp_set(pb_engine* e, int32_t nranks, int32_t rank, const double* bounds, int64_t xi_offset,
+                      int32_t left_is_global, int32_t right_is_global);
+int32_t pb_migrate_count(pb_engine* e, int64_t* counts /* [nranks] records to send to each rank */);
+int32_t pb_migrate_pack(pb_engine* e, void* sendbuf_dev, int64_t capacity_records);
+int32_t pb_migrate_unpack(pb_engine* e, const void* recvbuf_dev, int64_t n_in);
+#define PB_MIGRATION_RECORD_BYTES 48
+/* particle ids in device order (after migrations the order on a rank is arbitrary) */
+int32_t pb_particles_download_ids(pb_engine* e, int64_t n, int64_t* particle_id);
 
 /* Marks every particle currently in state Evaluate/Success whose time-to-endtime >= 0 with
  * ErrorOutsideTimeInterval (70): the reference flags the WHOLE evaluated view when any particle

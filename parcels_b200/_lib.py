@@ -33,7 +33,7 @@ class AdvectArgs(C.Structure):
         ("rng_call", C.c_uint64),
         ("max_iters", C.c_int64),
         ("hint_all_zero", C.c_int32),
-        ("reserved", C.c_int32),
+        ("resume", C.c_int32),
     ]
 
 
@@ -46,6 +46,7 @@ class Report(C.Structure):
         ("n_out_of_time", C.c_int64),
         ("max_iters_done", C.c_int64),
         ("cache_refills", C.c_int64),
+        ("n_migrate", C.c_int64),
         ("max_state", C.c_int32),
         ("reserved", C.c_int32),
         ("kernel_ms", C.c_float),
@@ -87,6 +88,11 @@ SYMBOLS = {
     "pb_advect_async": (C.c_int32, [_P, C.POINTER(AdvectArgs)]),
     "pb_last_report": (C.c_int32, [_P, C.POINTER(Report)]),
     "pb_sample_velocity": (C.c_int32, [_P, C.c_int64, _P, _P, _P, _P, C.c_int32, C.c_int32, _P, C.c_int32, _P, _P, _P, _P, _P]),
+    "pb_decomp_set": (C.c_int32, [_P, C.c_int32, C.c_int32, _P, C.c_int64, C.c_int32, C.c_int32]),
+    "pb_migrate_count": (C.c_int32, [_P, _P]),
+    "pb_migrate_pack": (C.c_int32, [_P, _P, C.c_int64]),
+    "pb_migrate_unpack": (C.c_int32, [_P, _P, C.c_int64]),
+    "pb_particles_download_ids": (C.c_int32, [_P, C.c_int64, _P]),
     "pb_flag_view_outside_time": (C.c_int32, [_P, C.c_double, C.c_double]),
     "pb_debug_normals": (C.c_int32, [_P, C.c_uint64, C.c_uint64, C.c_int64, C.c_int64, _P, _P]),
 }

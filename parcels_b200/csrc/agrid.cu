@@ -173,7 +173,14 @@ __device__ __forceinline__ void eval_uvw(const GridDev& g, const FieldDev& f, Ev
 
     // -- particles.ei[:, igrid] = ravel_index(zi, yi, xi) (field.py:307-317): only the LAST eval's value
     //    survives, so the indices are kept and raveled once on exit (AGridPolicy::finish)
-    e.szi = zi; e.syi = yi; e.sxi = xi;
+    int gxi = xi;
+    if (g.decomposed) {
+        // mode D: local column -> global column.  A sentinel at a slab edge that is NOT the edge of the global
+        // domain means a stage position left owned+halo columns: the halo is too small for this dt.
+        if (xi >= 0) gxi = xi + g.xi_offset;
+        else if ((xi == -2 && !g.left_global) || (xi == -1 && !g.right_global)) e.state = max(e.state, 99);
+    }
+    e.szi = zi; e.syi = yi; e.sxi = gxi;
     e.searched = true;
 
     // -- state from positions (field.py:327-356).  X/Y index -2 is NOT an error in the reference.

@@ -35,7 +35,12 @@ struct GridDev {
     long long hnkeys;
     double hbox[6];               // xmin, xmax, ymin, ymax, zmin, zmax of the hash grid
     int off_x, off_y, off_z;      // C-grid staggering offsets (_xinterpolators.py:99-109)
-    int pad2_;
+    // multi-GPU mode D (X-slab domain decomposition): this engine holds lon[xi_offset : xi_offset + nx]
+    // of the global axis (owned columns + halo); cell indices written to `ei` are GLOBAL.
+    int decomposed;
+    int xi_offset;
+    int left_global, right_global;  // whether the local lon edge is the edge of the global domain
+    double own_lo, own_hi;          // particles with own_lo <= x < own_hi are advanced here, others migrate
 };
 
 struct FieldDev {
@@ -52,6 +57,7 @@ struct ReportDev {
     unsigned long long n_out_of_time;
     long long max_iters_done;
     unsigned long long cache_refills;
+    unsigned long long n_migrate;  // mode D: particles that left the owned slab and wait for migration
     int max_state;
     int pad_;
 };
@@ -75,7 +81,7 @@ struct AdvectParams {
     long long max_iters;
     int hint_all_zero;  // curvilinear: every hinted xi of the evaluated view is 0 => the reference skips
                         // the hint for the whole batch at the first eval (index_search.py:269-282)
-    int pad_;
+    int resume;         // 1: continue a Kernel.execute call after a migration (states are NOT reset to Evaluate)
     ReportDev* rep;
 };
 
@@ -211,7 +217,7 @@ __global__ void __launch_bounds__(PB_BLOCK_THREADS, PB_MINBLOCKS) advect_kernel(
     unsigned long long my_steps = 0, my_refills = 0;
     int final_state = 0;
     long long my_iters = 0;
-    bool errored = false, deleted = false, oot = false;
+    bool errored = false, deleted = false, oot = false, migrate = false;
     long long err_iter = LLONG_MAX;
 
     if (i < p.P.n) {
@@ -222,7 +228,7 @@ __global__ void __launch_bounds__(PB_BLOCK_THREADS, PB_MINBLOCKS) advect_kernel(
 
         typename Policy::Ctx e;
         Policy::init(e, p, p.P.ei[i]);
-        e.state = PB_EVALUATE;  // kernel.py:188
+        e.state = p.resume ? p.P.state[i] : (int)PB_EVALUATE;  // kernel.py:188
         e.refills = 0;
         e.out_of_time = false;
 
@@ -236,6 +242,10 @@ __global__ void __launch_bounds__(PB_BLOCK_THREADS, PB_MINBLOCKS) advect_kernel(
             if (p.max_iters >= 0 && it >= p.max_iters) break;
             const double tte = sign * (p.endtime - t);                       // kernel.py:191
             if (!((e.state == PB_SUCCESS || e.state == PB_EVALUATE) && tte >= 0)) break;  // :193-195
+            if (p.g.decomposed && !((double)x >= p.g.own_lo && (double)x < p.g.own_hi)) {  // mode D: not ours (any more)
+                migrate = true;
+                break;
+            }
             // adapt dt to end exactly on endtime (:199-203)
             const double dtp = (sign == 1) ? fmax(fmin(p.dt, tte), 0.0) : fmin(fmax(p.dt, -tte), 0.0);
             my_steps++;
@@ -321,7 +331,7 @@ __global__ void __launch_bounds__(PB_BLOCK_THREADS, PB_MINBLOCKS) advect_kernel(
     // ---- report: warp-reduce then one atomic per warp ----
     const unsigned full = 0xffffffffu;
     unsigned long long s_steps = my_steps, s_ref = my_refills;
-    unsigned n_err = errored, n_del = deleted, n_oot = oot;
+    unsigned n_err = errored, n_del = deleted, n_oot = oot, n_mig = migrate;
     long long mx_it = my_iters, mn_err = err_iter;
     int mx_state = final_state;
 #pragma unroll
@@ -331,6 +341,7 @@ __global__ void __launch_bounds__(PB_BLOCK_THREADS, PB_MINBLOCKS) advect_kernel(
         n_err += __shfl_xor_sync(full, n_err, o);
         n_del += __shfl_xor_sync(full, n_del, o);
         n_oot += __shfl_xor_sync(full, n_oot, o);
+        n_mig += __shfl_xor_sync(full, n_mig, o);
         mx_it = max(mx_it, __shfl_xor_sync(full, mx_it, o));
         mn_err = min(mn_err, __shfl_xor_sync(full, mn_err, o));
         mx_state = max(mx_state, __shfl_xor_sync(full, mx_state, o));
@@ -341,6 +352,7 @@ __global__ void __launch_bounds__(PB_BLOCK_THREADS, PB_MINBLOCKS) advect_kernel(
         if (n_err) atomicAdd(&p.rep->n_error, (unsigned long long)n_err);
         if (n_del) atomicAdd(&p.rep->n_deleted, (unsigned long long)n_del);
         if (n_oot) atomicAdd(&p.rep->n_out_of_time, (unsigned long long)n_oot);
+        if (n_mig) atomicAdd(&p.rep->n_migrate, (unsigned long long)n_mig);
         if (mx_it) atomicMax(&p.rep->max_iters_done, mx_it);
         if (mn_err != LLONG_MAX) atomicMin(&p.rep->first_error_iter, mn_err);
         if (mx_state) atomicMax(&p.rep->max_state, mx_state);

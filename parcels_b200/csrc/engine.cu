@@ -74,6 +74,71 @@ __global__ void normals_kernel(unsigned long long seed, unsigned long long rng_c
     out[2 * i + 1] = zy;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// migration kernels (mode D)
+// ------------------------------------------------------------------------------------------------
+struct MigRecord {  // 48 B per migrating particle
+    double t;
+    long long pid;
+    float x, y, z, dx, dy, dz;
+    int state, ei;
+};
+
+// dest[i] = destination rank of particle i, or -1 if it stays.  A particle moves iff it still has to be
+// advanced (state Evaluate) and its x lies outside this rank's owned interval [bounds[rank], bounds[rank+1]).
+__global__ void mig_classify(ParticlesDev P, const double* __restrict__ bounds, int nranks, int rank, int* dest,
+                             unsigned long long* counts) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.n) return;
+    int d = -1;
+    if (P.state[i] == PB_EVALUATE) {
+        const double x = (double)P.x[i];
+        int r = 0;
+        while (r + 1 < nranks && x >= bounds[r + 1]) ++r;  // rank 0 owns (-inf, b1), the last rank [b_{n-1}, +inf)
+        if (x != x) r = rank;                             // NaN stays (the kernel flags it)
+        if (r != rank) d = r;
+    }
+    dest[i] = d;
+    atomicAdd(&counts[d < 0 ? nranks : d], 1ULL);
+}
+
+__global__ void mig_pack(ParticlesDev P, const int* __restrict__ dest, int nranks, unsigned long long* cursors, MigRecord* send,
+                         long long* keep_idx) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.n) return;
+    const int d = dest[i];
+    if (d < 0) {
+        keep_idx[atomicAdd(&cursors[nranks], 1ULL)] = i;
+    } else {
+        MigRecord r;
+        r.t = P.t[i]; r.pid = P.pid[i];
+        r.x = P.x[i]; r.y = P.y[i]; r.z = P.z[i];
+        r.dx = P.dx[i]; r.dy = P.dy[i]; r.dz = P.dz[i];
+        r.state = P.state[i]; r.ei = P.ei[i];
+        send[atomicAdd(&cursors[d], 1ULL)] = r;
+    }
+}
+
+__global__ void mig_compact(ParticlesDev src, ParticlesDev dst, const long long* __restrict__ keep_idx, long long n_keep) {
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_keep) return;
+    const long long i = keep_idx[k];
+    dst.x[k] = src.x[i]; dst.y[k] = src.y[i]; dst.z[k] = src.z[i];
+    dst.dx[k] = src.dx[i]; dst.dy[k] = src.dy[i]; dst.dz[k] = src.dz[i];
+    dst.t[k] = src.t[i]; dst.state[k] = src.state[i]; dst.ei[k] = src.ei[i]; dst.pid[k] = src.pid[i];
+}
+
+__global__ void mig_unpack(ParticlesDev dst, long long base, const MigRecord* __restrict__ recv, long long n_in) {
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_in) return;
+    const MigRecord r = recv[k];
+    const long long j = base + k;
+    dst.x[j] = r.x; dst.y[j] = r.y; dst.z[j] = r.z;
+    dst.dx[j] = r.dx; dst.dy[j] = r.dy; dst.dz[j] = r.dz;
+    dst.t[j] = r.t; dst.state[j] = r.state; dst.ei[j] = r.ei; dst.pid[j] = r.pid;
+}
+
 // ------------------------------------------------------------------------------------------------
 // host-side engine
 // ------------------------------------------------------------------------------------------------
@@ -114,6 +179,12 @@ struct pb_engine {
     // particles
     DevBuf px, py, pz, pdx, pdy, pdz, pt, pstate, pei, ppid;
     DevBuf snap;  // snapshot of all particle arrays
+    // mode D (domain decomposition): alternate SoA for compaction, migration work buffers
+    DevBuf ax, ay, az, adx, ady, adz, at, astate, aei, apid;
+    DevBuf mdest, mkeep, mcount, mbounds;
+    int nranks = 1, rank = 0;
+    long long n_keep = 0, n_send = 0;
+    std::vector<long long> send_counts;
     long long n = 0;
     bool have_pid = false;
     // report
@@ -169,6 +240,9 @@ void pb_engine_destroy(pb_engine* e) {
     if (!e) return;
     cudaSetDevice(e->device);
     cudaStreamSynchronize(e->stream);
+    for (DevBuf* b : {&e->ax, &e->ay, &e->az, &e->adx, &e->ady, &e->adz, &e->at, &e->astate, &e->aei, &e->apid, &e->mdest, &e->mkeep,
+                      &e->mcount, &e->mbounds})
+        b->release();
     for (DevBuf* b : {&e->hkeys, &e->hstarts, &e->hcounts, &e->hfaces, &e->lon, &e->lat, &e->depth, &e->time, &e->fbuf[0], &e->fbuf[1], &e->fbuf[2], &e->px, &e->py, &e->pz,
                       &e->pdx, &e->pdy, &e->pdz, &e->pt, &e->pstate, &e->pei, &e->ppid, &e->snap})
         b->release();
@@ -383,6 +457,16 @@ int32_t pb_particles_download(pb_engine* e, int64_t n, float* x, float* y, float
     return PB_OK;
 }
 
+int32_t pb_particles_download_ids(pb_engine* e, int64_t n, int64_t* particle_id) {
+    if (!e || (n && !particle_id)) return fail(PB_ERR_INVALID, "NULL argument");
+    if (n != e->n) return fail(PB_ERR_INVALID, "download of %lld ids but %lld particles are resident", (long long)n, (long long)e->n);
+    if (!e->have_pid && n) return fail(PB_ERR_STATE, "no particle ids resident");
+    CK(cudaSetDevice(e->device));
+    if (n) CK(cudaMemcpyAsync(particle_id, e->ppid.p, n * 8, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return PB_OK;
+}
+
 static const size_t kSnapOff[10] = {0, 4, 8, 12, 16, 20, 24, 32, 36, 40};  // per-particle byte offsets x..ei (t at 24)
 
 int32_t pb_particles_snapshot(pb_engine* e) {
@@ -520,6 +604,7 @@ int32_t pb_advect_async(pb_engine* e, const pb_advect_args* a) {
     p.kh_zonal = a->kh_zonal; p.kh_meridional = a->kh_meridional; p.kh_deg2m = a->kh_deg2m;
     p.seed = a->seed; p.rng_call = a->rng_call; p.max_iters = a->max_iters;
     p.hint_all_zero = a->hint_all_zero;
+    p.resume = a->resume;
     p.g.off_x = e->g.off_x; p.g.off_y = e->g.off_y; p.g.off_z = e->g.off_z;
     p.rep = e->d_rep;
 
@@ -552,6 +637,7 @@ int32_t pb_last_report(pb_engine* e, pb_report* rep) {
         o.n_out_of_time = (int64_t)r.n_out_of_time;
         o.max_iters_done = r.max_iters_done;
         o.cache_refills = (int64_t)r.cache_refills;
+        o.n_migrate = (int64_t)r.n_migrate;
         o.max_state = r.max_state;
         float ms = 0.f;
         CK(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
@@ -602,6 +688,113 @@ int32_t pb_debug_normals(pb_engine* e, uint64_t seed, uint64_t rng_call, int64_t
     CK(cudaStreamSynchronize(e->stream));
     cudaFree(d_pid);
     cudaFree(d_out);
+    return PB_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// mode D: X-slab domain decomposition + particle migration.  The exchange itself is an
+// all-to-all-v done by the caller over NCCL (torch.distributed) on the device buffers packed here.
+// ------------------------------------------------------------------------------------------------
+int32_t pb_decomp_set(pb_engine* e, int32_t nranks, int32_t rank, const double* bounds, int64_t xi_offset,
+                      int32_t left_is_global, int32_t right_is_global) {
+    if (!e || !bounds) return fail(PB_ERR_INVALID, "NULL argument");
+    if (nranks < 1 || rank < 0 || rank >= nranks) return fail(PB_ERR_INVALID, "bad rank %d of %d", rank, nranks);
+    if (!e->have_grid || e->g.curvilinear) return fail(PB_ERR_STATE, "domain decomposition needs an uploaded rectilinear grid");
+    for (int r = 0; r < nranks; ++r)
+        if (!(bounds[r] < bounds[r + 1])) return fail(PB_ERR_INVALID, "slab bounds must be strictly increasing");
+    CK(cudaSetDevice(e->device));
+    int32_t rc = upload(e, e->mbounds, bounds, (size_t)(nranks + 1) * sizeof(double));
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(e->stream));
+    e->nranks = nranks; e->rank = rank;
+    e->g.decomposed = nranks > 1 ? 1 : 0;
+    e->g.xi_offset = (int)xi_offset;
+    e->g.left_global = left_is_global ? 1 : 0;
+    e->g.right_global = right_is_global ? 1 : 0;
+    e->g.own_lo = bounds[rank];
+    e->g.own_hi = bounds[rank + 1];
+    e->send_counts.assign(nranks, 0);
+    return PB_OK;
+}
+
+static ParticlesDev cur_particles(pb_engine* e) {
+    return ParticlesDev{(float*)e->px.p, (float*)e->py.p, (float*)e->pz.p, (float*)e->pdx.p, (float*)e->pdy.p,
+                        (float*)e->pdz.p, (double*)e->pt.p, (int*)e->pstate.p, (int*)e->pei.p, (long long*)e->ppid.p, e->n};
+}
+
+int32_t pb_migrate_count(pb_engine* e, int64_t* counts) {
+    if (!e || !counts) return fail(PB_ERR_INVALID, "NULL argument");
+    if (e->nranks < 1 || e->mbounds.bytes == 0) return fail(PB_ERR_STATE, "pb_decomp_set not called");
+    if (!e->have_pid && e->n) return fail(PB_ERR_STATE, "migration needs particle_id");
+    CK(cudaSetDevice(e->device));
+    const int nr = e->nranks;
+    int32_t rc;
+    if ((rc = e->mdest.ensure(e->n ? e->n * 4 : 4))) return rc;
+    if ((rc = e->mcount.ensure((size_t)(nr + 1) * 8))) return rc;
+    CK(cudaMemsetAsync(e->mcount.p, 0, (size_t)(nr + 1) * 8, e->stream));
+    if (e->n > 0) {
+        mig_classify<<<(unsigned)((e->n + 255) / 256), 256, 0, e->stream>>>(cur_particles(e), (const double*)e->mbounds.p, nr, e->rank,
+                                                                            (int*)e->mdest.p, (unsigned long long*)e->mcount.p);
+        CK(cudaGetLastError());
+    }
+    std::vector<unsigned long long> h(nr + 1);
+    CK(cudaMemcpyAsync(h.data(), e->mcount.p, (size_t)(nr + 1) * 8, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    e->n_send = 0;
+    for (int r = 0; r < nr; ++r) { counts[r] = (int64_t)h[r]; e->send_counts[r] = (long long)h[r]; e->n_send += (long long)h[r]; }
+    e->n_keep = (long long)h[nr];
+    return PB_OK;
+}
+
+int32_t pb_migrate_pack(pb_engine* e, void* sendbuf_dev, int64_t capacity_records) {
+    if (!e) return fail(PB_ERR_INVALID, "engine is NULL");
+    if (e->n_send > capacity_records) return fail(PB_ERR_INVALID, "send buffer holds %lld records, %lld needed", (long long)capacity_records, e->n_send);
+    if (e->n_send && !sendbuf_dev) return fail(PB_ERR_INVALID, "NULL send buffer");
+    CK(cudaSetDevice(e->device));
+    const int nr = e->nranks;
+    // cursors: [0..nr-1] = exclusive prefix of the per-destination counts, [nr] = 0 (keep cursor)
+    std::vector<unsigned long long> cur(nr + 1, 0);
+    for (int r = 1; r < nr; ++r) cur[r] = cur[r - 1] + (unsigned long long)e->send_counts[r - 1];
+    CK(cudaMemcpyAsync(e->mcount.p, cur.data(), (size_t)(nr + 1) * 8, cudaMemcpyHostToDevice, e->stream));
+    int32_t rc;
+    if ((rc = e->mkeep.ensure(e->n_keep ? e->n_keep * 8 : 8))) return rc;
+    if (e->n > 0) {
+        mig_pack<<<(unsigned)((e->n + 255) / 256), 256, 0, e->stream>>>(cur_particles(e), (const int*)e->mdest.p, nr,
+                                                                        (unsigned long long*)e->mcount.p, (MigRecord*)sendbuf_dev,
+                                                                        (long long*)e->mkeep.p);
+        CK(cudaGetLastError());
+    }
+    CK(cudaStreamSynchronize(e->stream));  // cur goes out of scope; the caller hands sendbuf to NCCL next
+    return PB_OK;
+}
+
+int32_t pb_migrate_unpack(pb_engine* e, const void* recvbuf_dev, int64_t n_in) {
+    if (!e || n_in < 0 || (n_in && !recvbuf_dev)) return fail(PB_ERR_INVALID, "bad argument");
+    CK(cudaSetDevice(e->device));
+    const long long n_new = e->n_keep + n_in;
+    const size_t cap = n_new ? (size_t)n_new : 1;
+    DevBuf* alt[10] = {&e->ax, &e->ay, &e->az, &e->adx, &e->ady, &e->adz, &e->at, &e->astate, &e->aei, &e->apid};
+    DevBuf* cur[10] = {&e->px, &e->py, &e->pz, &e->pdx, &e->pdy, &e->pdz, &e->pt, &e->pstate, &e->pei, &e->ppid};
+    const size_t es[10] = {4, 4, 4, 4, 4, 4, 8, 4, 4, 8};
+    for (int k = 0; k < 10; ++k) {
+        int32_t rc = alt[k]->ensure(cap * es[k] + (cap * es[k]) / 4);  // 25 % head-room: fewer reallocations
+        if (rc) return rc;
+    }
+    ParticlesDev dst{(float*)e->ax.p, (float*)e->ay.p, (float*)e->az.p, (float*)e->adx.p, (float*)e->ady.p, (float*)e->adz.p,
+                     (double*)e->at.p, (int*)e->astate.p, (int*)e->aei.p, (long long*)e->apid.p, n_new};
+    if (e->n_keep > 0) {
+        mig_compact<<<(unsigned)((e->n_keep + 255) / 256), 256, 0, e->stream>>>(cur_particles(e), dst, (const long long*)e->mkeep.p, e->n_keep);
+        CK(cudaGetLastError());
+    }
+    if (n_in > 0) {
+        mig_unpack<<<(unsigned)((n_in + 255) / 256), 256, 0, e->stream>>>(dst, e->n_keep, (const MigRecord*)recvbuf_dev, n_in);
+        CK(cudaGetLastError());
+    }
+    CK(cudaStreamSynchronize(e->stream));
+    for (int k = 0; k < 10; ++k) std::swap(*cur[k], *alt[k]);
+    e->n = n_new;
+    e->n_send = 0; e->n_keep = n_new;
     return PB_OK;
 }
 

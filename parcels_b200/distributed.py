@@ -1,7 +1,15 @@
-"""Multi-GPU mode R (replicas): one process per GPU, the field replicated in every GPU's HBM,
-particles sharded contiguously by rank.  Particles do not interact on this path, so the step loop
-needs NO collective; ``torch.distributed`` is used only to assemble results / timings
-(NCCL on GPUs, gloo in the CPU tests).  (the reference has no distributed layer.)
+"""Multi-GPU execution (the reference has no distributed layer at all).
+
+Mode R (replicas): one process per GPU, the field replicated in every GPU's HBM, particles sharded
+contiguously by rank.  Particles do not interact on this path, so the step loop needs NO collective;
+``torch.distributed`` only assembles results / timings (NCCL on GPUs, gloo in the CPU tests).
+
+Mode D (domain decomposition, config 5): the rectilinear field is cut into X-slabs (+ halo columns), one per
+GPU; a particle is advanced by the rank that owns its longitude and MIGRATES when it leaves the slab:
+device-side classify/pack kernels (``csrc/engine.cu``) -> counts exchanged with ``all_to_all_single`` ->
+48-byte particle records exchanged with ``all_to_all_single`` (NCCL over NVLink) -> device-side
+compact+append -> the kernel resumes.  Trajectories are bit-identical to a single-GPU run because every
+particle-step sees the same grid values (the slab is a slice of the global axis; ``ei`` stays global).
 """
 
 from __future__ import annotations
@@ -52,3 +60,140 @@ def allreduce_sum(value: float, dist, device="cpu") -> float:
     t = torch.tensor([float(value)], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.SUM)
     return float(t.item())
+
+
+# --------------------------------------------------------------------------------------------------
+# mode D
+# --------------------------------------------------------------------------------------------------
+RECORD_BYTES = 48  # PB_MIGRATION_RECORD_BYTES
+
+
+def slab_plan(lon, world: int, halo_cells: int) -> list[dict]:
+    """Cut the global X axis (node coordinates ``lon``) into ``world`` slabs of whole cells.
+
+    Returns per rank: ``bounds`` (world+1 owned-interval edges, shared by all ranks), the inclusive local
+    node range [lo, hi] = owned cells +- halo, ``xi_offset`` = lo, and whether each local edge is a
+    global edge."""
+    lon = np.asarray(lon)
+    nx = lon.size
+    ncell = nx - 1
+    if world > ncell:
+        raise ValueError(f"cannot cut {ncell} cells into {world} slabs")
+    edges = [round(r * ncell / world) for r in range(world + 1)]
+    bounds = np.asarray(lon[edges], dtype=np.float64)
+    plans = []
+    for r in range(world):
+        lo = max(0, edges[r] - halo_cells)
+        hi = min(nx - 1, edges[r + 1] + halo_cells)
+        plans.append(dict(rank=r, bounds=bounds, lo=lo, hi=hi, xi_offset=lo, left_global=lo == 0, right_global=hi == nx - 1,
+                          own_cells=(edges[r], edges[r + 1])))  # fmt: skip
+    return plans
+
+
+def route_counts(x, bounds) -> np.ndarray:
+    """Host restatement of the device classify kernel: owner rank of each x (used by the CPU tests)."""
+    b = np.asarray(bounds)
+    return np.clip(np.searchsorted(b[1:-1], x, side="right"), 0, len(b) - 2)
+
+
+class DecomposedFieldSet:
+    """This rank's X-slab of a rectilinear A-grid FieldSet, resident on ``device``."""
+
+    def __init__(self, *, lon, lat, U, V, W=None, depth=None, time=None, mesh="spherical", rank, world, halo_cells=4,
+                 device=0):  # fmt: skip
+        from .fieldset import FieldSet
+
+        self.rank, self.world, self.device = rank, world, device
+        self.plan = slab_plan(lon, world, halo_cells)[rank]
+        lo, hi = self.plan["lo"], self.plan["hi"]
+        sl = slice(lo, hi + 1)
+        self.fs = FieldSet.from_arrays(lon=np.ascontiguousarray(np.asarray(lon)[sl]), lat=lat, depth=depth, time=time,
+                                       U=np.ascontiguousarray(np.asarray(U)[..., sl]), V=np.ascontiguousarray(np.asarray(V)[..., sl]),
+                                       W=None if W is None else np.ascontiguousarray(np.asarray(W)[..., sl]), mesh=mesh,
+                                       xdim=np.asarray(lon).size - 1)  # fmt: skip  (GLOBAL cell count: ei stays global)
+        self.engine = self.fs.engine(device)
+        self.engine.decomp_set(world, rank, self.plan["bounds"], self.plan["xi_offset"], self.plan["left_global"],
+                               self.plan["right_global"])  # fmt: skip
+
+
+def _exchange(eng, counts, dist, device):
+    """One migration round: counts -> all_to_all -> records -> all_to_all -> unpack.  Returns #received.
+
+    NCCL: both all-to-alls run on device buffers (records never touch the host).  gloo (CPU tests / two
+    ranks sharing one GPU): the same device-side pack/unpack kernels, records staged through the host."""
+    import torch
+
+    world = dist.get_world_size()
+    rank = dist.get_rank()
+    n_out = int(counts.sum())
+    if dist.get_backend() == "nccl":
+        send_counts = torch.as_tensor(counts, dtype=torch.int64, device=device)
+        recv_counts = torch.empty(world, dtype=torch.int64, device=device)
+        dist.all_to_all_single(recv_counts, send_counts)
+        rc = recv_counts.cpu().numpy()
+        n_in = int(rc.sum())
+        sendbuf = torch.empty(max(n_out, 1) * RECORD_BYTES, dtype=torch.uint8, device=device)
+        recvbuf = torch.empty(max(n_in, 1) * RECORD_BYTES, dtype=torch.uint8, device=device)
+        eng.migrate_pack(sendbuf.data_ptr(), n_out)  # synchronises the engine stream before NCCL touches the buffer
+        dist.all_to_all_single(recvbuf[: n_in * RECORD_BYTES], sendbuf[: n_out * RECORD_BYTES],
+                               output_split_sizes=[int(c) * RECORD_BYTES for c in rc],
+                               input_split_sizes=[int(c) * RECORD_BYTES for c in counts])  # fmt: skip
+        torch.cuda.synchronize(device)
+        eng.migrate_unpack(recvbuf.data_ptr(), n_in)
+        return n_in
+    sendbuf = torch.empty(max(n_out, 1) * RECORD_BYTES, dtype=torch.uint8, device=device)
+    eng.migrate_pack(sendbuf.data_ptr(), n_out)
+    host = sendbuf[: n_out * RECORD_BYTES].cpu().numpy()
+    offs = np.concatenate(([0], np.cumsum(counts))) * RECORD_BYTES
+    chunks = [host[offs[r] : offs[r + 1]].tobytes() for r in range(world)]
+    everyone = [None] * world
+    dist.all_gather_object(everyone, chunks)
+    mine = b"".join(everyone[src][rank] for src in range(world))
+    n_in = len(mine) // RECORD_BYTES
+    recvbuf = torch.frombuffer(bytearray(mine) if mine else bytearray(RECORD_BYTES), dtype=torch.uint8).to(device)
+    torch.cuda.synchronize(device)
+    eng.migrate_unpack(recvbuf.data_ptr(), n_in)
+    return n_in
+
+
+def execute_decomposed(dfs: DecomposedFieldSet, pdata: dict, kernels, dt: float, endtime: float, dist, max_rounds=100000):
+    """``Kernel.execute`` over a domain-decomposed field: ``pdata`` is ANY shard of the particle set (it is
+    routed to the owners first).  Returns (local particle dict after the call, stats)."""
+    import torch
+
+    from .particleset import KernelPlan
+    from .statuscodes import StatusCode
+
+    plan = KernelPlan(kernels, dfs.fs)
+    if plan.diffusion:
+        raise NotImplementedError("DiffusionUniformKh is not supported with domain decomposition yet")
+    if not plan.delete_on_error:
+        raise NotImplementedError("domain-decomposed execution needs the DeleteParticle handler (errors cannot be replayed "
+                                  "step-exactly across ranks)")  # fmt: skip
+    eng = dfs.engine
+    device = torch.device(f"cuda:{dfs.device}")
+    pdata["state"][:] = StatusCode.Evaluate
+    pdata["dt"][:] = dt
+    eng.upload_particles(pdata, np.ascontiguousarray(pdata["ei"][:, -1]))
+    stats = dict(rounds=0, migrated=0, particle_steps=0, kernel_ms=0.0)
+    first = True
+    for _ in range(max_rounds):
+        counts = eng.migrate_count()
+        moving = allreduce_sum(float(counts.sum()), dist, device)
+        if moving > 0:
+            stats["migrated"] += int(counts.sum())
+            _exchange(eng, counts, dist, device)
+        elif not first:
+            break
+        rep = eng.advect(eng.make_args(plan.scheme, dt, endtime, delete_on_error=True, resume=not first))
+        first = False
+        stats["rounds"] += 1
+        stats["particle_steps"] += rep["particle_steps"]
+        stats["kernel_ms"] += rep["kernel_ms"]
+        if allreduce_max(float(rep["max_state"] == 99), dist, device) > 0:
+            raise RuntimeError("halo violation: a stage position left the owned+halo columns; increase halo_cells or reduce dt")
+    out = eng.download_all(ngrids=pdata["ei"].shape[1])
+    out["dt"][:] = dt
+    keep = out["state"] != StatusCode.Delete
+    out = {k: v[keep] for k, v in out.items()}
+    return out, stats

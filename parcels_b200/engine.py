@@ -142,10 +142,10 @@ class Engine:
     # -- hot path --------------------------------------------------------------------------------
     @staticmethod
     def make_args(scheme, dt, endtime, *, diffusion=False, delete_on_error=False, kh=(0.0, 0.0), kh_spherical=False,
-                  kh_deg2m=1.0, seed=0, rng_call=0, max_iters=-1, hint_all_zero=False) -> AdvectArgs:  # fmt: skip
+                  kh_deg2m=1.0, seed=0, rng_call=0, max_iters=-1, hint_all_zero=False, resume=False) -> AdvectArgs:  # fmt: skip
         return AdvectArgs(int(scheme), int(diffusion), int(delete_on_error), int(kh_spherical), float(dt), float(endtime),
                           float(kh[0]), float(kh[1]), float(kh_deg2m), int(seed), int(rng_call), int(max_iters),
-                          int(bool(hint_all_zero)), 0)  # fmt: skip
+                          int(bool(hint_all_zero)), int(bool(resume)))  # fmt: skip
 
     def advect(self, args: AdvectArgs) -> dict:
         rep = Report()
@@ -170,6 +170,40 @@ class Engine:
         check(self._lib.pb_sample_velocity(self._h, n, ptr(t), ptr(z), ptr(y), ptr(x), int(positions_are_f32), int(three_d),
                                            ptr(hint), int(no_hint), ptr(u), ptr(v), ptr(w), ptr(ei), ptr(st)))  # fmt: skip
         return u, v, w, ei, st
+
+    # -- mode D: domain decomposition + migration ------------------------------------------------------
+    def decomp_set(self, nranks, rank, bounds, xi_offset, left_is_global, right_is_global):
+        b = np.ascontiguousarray(bounds, dtype=np.float64)
+        assert b.size == nranks + 1
+        self._nranks = int(nranks)
+        check(self._lib.pb_decomp_set(self._h, int(nranks), int(rank), ptr(b), int(xi_offset), int(left_is_global),
+                                      int(right_is_global)))  # fmt: skip
+
+    def migrate_count(self) -> np.ndarray:
+        counts = np.zeros(self._nranks, dtype=np.int64)
+        check(self._lib.pb_migrate_count(self._h, ptr(counts)))
+        return counts
+
+    def migrate_pack(self, sendbuf_ptr: int, capacity_records: int):
+        check(self._lib.pb_migrate_pack(self._h, C.c_void_p(sendbuf_ptr), int(capacity_records)))
+
+    def migrate_unpack(self, recvbuf_ptr: int, n_in: int):
+        check(self._lib.pb_migrate_unpack(self._h, C.c_void_p(recvbuf_ptr), int(n_in)))
+
+    def particle_count(self) -> int:
+        return int(self._lib.pb_particles_count(self._h))
+
+    def download_all(self, ngrids=1) -> dict:
+        """Download the resident particle set (its size may have changed through migration)."""
+        from .particle import create_particle_data
+
+        n = self.particle_count()
+        d = create_particle_data(nparticles=n, ngrids=ngrids, initial={})
+        ei_last = np.zeros(n, dtype=np.int32)
+        self.download_particles(d, ei_last)
+        d["ei"][:, -1] = ei_last
+        check(self._lib.pb_particles_download_ids(self._h, n, ptr(d["particle_id"])))
+        return d
 
     def flag_view_outside_time(self, dt, endtime):
         check(self._lib.pb_flag_view_outside_time(self._h, float(dt), float(endtime)))

@@ -38,7 +38,7 @@ def test_struct_layouts_match_header():
     import ctypes
 
     assert ctypes.sizeof(_lib.AdvectArgs) == 4 * 4 + 5 * 8 + 2 * 8 + 8 + 2 * 4
-    assert ctypes.sizeof(_lib.Report) == 7 * 8 + 2 * 4 + 2 * 4
+    assert ctypes.sizeof(_lib.Report) == 8 * 8 + 2 * 4 + 2 * 4
 
 
 def _fs(with_w=True):
