@@ -22,6 +22,7 @@
 #include <cuda_runtime.h>
 
 #include <climits>
+#include <cmath>
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
@@ -712,8 +713,10 @@ int32_t pb_decomp_set(pb_engine* e, int32_t nranks, int32_t rank, const double* 
     e->g.xi_offset = (int)xi_offset;
     e->g.left_global = left_is_global ? 1 : 0;
     e->g.right_global = right_is_global ? 1 : 0;
-    e->g.own_lo = bounds[rank];
-    e->g.own_hi = bounds[rank + 1];
+    // rank 0 also owns everything left of the domain, the last rank everything right of it (there the
+    // reference's own out-of-bounds semantics apply: index -2 / -1 at a GLOBAL edge)
+    e->g.own_lo = rank == 0 ? -HUGE_VAL : bounds[rank];
+    e->g.own_hi = rank == nranks - 1 ? HUGE_VAL : bounds[rank + 1];
     e->send_counts.assign(nranks, 0);
     return PB_OK;
 }

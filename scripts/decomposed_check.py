@@ -56,6 +56,10 @@ if rank == 0:
         ok &= same
         if not same:
             print(f"MISMATCH {k}: {merged[k].shape} vs {ref[k].shape}")
+            if merged[k].shape == ref[k].shape:
+                bad = np.where((merged[k] != ref[k]).reshape(len(ref[k]), -1).any(axis=1))[0]
+                print("   count", len(bad), "first:", [(int(merged["particle_id"][b]), merged[k][b].tolist(), ref[k][b].tolist(),
+                                                        float(merged["x"][b]), float(ref["x"][b])) for b in bad[:6]])
     print(f"decomposed({world} ranks, backend={dist.get_backend()}): {len(ref['x'])} survivors, {int(tot)} migrations, "
           f"rounds={stats['rounds']} -> {'PASS bit-exact' if ok else 'FAIL'}")
 dist.barrier()
