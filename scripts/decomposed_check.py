@@ -40,7 +40,7 @@ dfs = D.DecomposedFieldSet(lon=f["lon"], lat=f["lat"], depth=f["depth"], time=f[
                            mesh="spherical", rank=rank, world=world, halo_cells=a.halo, device=dev)
 mine = D.shard_particles(full, rank, world)  # arbitrary shard: routed to the owners by the first migration round
 out, stats = D.execute_decomposed(dfs, mine, [pb.AdvectionRK4_3D, pb.DeleteParticle], dt, runtime, dist)
-tot = D.allreduce_sum(stats["migrated"], dist)
+tot = D.allreduce_sum(stats["migrated"], dist, device="cpu" if a.same_gpu else f"cuda:{dev}")
 merged = D.gather_particles(out, dist, dst=0)
 ok = True
 if rank == 0:
