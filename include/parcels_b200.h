@@ -85,7 +85,9 @@ int32_t pb_grid_upload_rectilinear(pb_engine* e, const void* lon, int64_t nx, co
  * of _core/spatialhash.py:269-387 (unique Morton keys ascending, per-key start/count, flat face ids
  * j*(nx-1)+i ascending within a key), built ONCE on the host (parcels_b200/spatialhash.py) so that the
  * candidate order -- "first containing face wins", :511-535 -- is the reference's; hash_box6 =
- * (xmin, xmax, ymin, ymax, zmin, zmax) of the hash grid, hash_bitwidth the quantisation (:212-228).
+ * (xmin, xmax, ymin, ymax, zmin, zmax) of the hash grid, hash_bitwidth the quantisation (:212-228);
+ * face_qbox[(ny-1)*(nx-1)] = each face's quantised bounding box packed 6 x 10 bits (xlo | xhi<<10 | ylo<<20 |
+ * yhi<<30 | zlo<<40 | zhi<<50), i.e. the set of hash cells the face is listed under (:269-300).
  * The query itself runs on the device. */
 int32_t pb_grid_upload_curvilinear(pb_engine* e, const void* lon2d, const void* lat2d, int64_t ny, int64_t nx,
                                    const void* depth, int64_t nz, int32_t coord_is_f64, const double* time_s,
@@ -93,7 +95,7 @@ int32_t pb_grid_upload_curvilinear(pb_engine* e, const void* lon2d, const void* 
                                    int64_t ydim_cells, int64_t zdim_cells, const uint32_t* hash_keys,
                                    const int64_t* hash_starts, const int64_t* hash_counts, int64_t n_keys,
                                    const uint32_t* hash_faces, int64_t n_entries, const double* hash_box6,
-                                   int32_t hash_bitwidth);
+                                   int32_t hash_bitwidth, const uint64_t* face_qbox);
 
 /* Vector interpolator of fieldset.UV / UVW (VectorField.interp_method, _core/field.py:236-246):
  * XLinear_Velocity (A-grid, interpolators/_xinterpolators.py:169-190) or CGrid_Velocity (:193-332)

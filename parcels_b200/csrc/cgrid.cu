@@ -44,6 +44,68 @@ struct CGridCtx {
 // ------------------------------------------------------------------------------------------------
 // curvilinear point-in-cell (index_search.py:94-239)
 // ------------------------------------------------------------------------------------------------
+// Tangent-plane basis and projected corners of ONE cell (_spherical_project_cell_and_query, cell part,
+// index_search.py:203-236).  out[16] = pu[4], pv[4], eu[3], ev[3], 2 pad.
+template <class A>
+__device__ __forceinline__ void project_cell(const A (&clon)[4], const A (&clat)[4], double (&pu)[4], double (&pv)[4],
+                                             double (&eu)[3], double (&ev)[3]) {
+    double cX[4], cY[4], cZ[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const double la = deg2rad_np((double)clat[k]), lo = deg2rad_np((double)clon[k]);
+        const double cl = cos(la);
+        cX[k] = cos(lo) * cl; cY[k] = sin(lo) * cl; cZ[k] = sin(la);
+    }
+    double ux = (cX[1] + cX[2]) - (cX[0] + cX[3]);
+    double uy = (cY[1] + cY[2]) - (cY[0] + cY[3]);
+    double uz = (cZ[1] + cZ[2]) - (cZ[0] + cZ[3]);
+    double un = sqrt(ux * ux + uy * uy + uz * uz);
+    if (un == 0.0) un = 1.0;
+    eu[0] = ux / un; eu[1] = uy / un; eu[2] = uz / un;
+    double vx = (cX[2] + cX[3]) - (cX[0] + cX[1]);
+    double vy = (cY[2] + cY[3]) - (cY[0] + cY[1]);
+    double vz = (cZ[2] + cZ[3]) - (cZ[0] + cZ[1]);
+    const double d = vx * eu[0] + vy * eu[1] + vz * eu[2];
+    vx = vx - d * eu[0]; vy = vy - d * eu[1]; vz = vz - d * eu[2];
+    double vn = sqrt(vx * vx + vy * vy + vz * vz);
+    if (vn == 0.0) vn = 1.0;
+    ev[0] = vx / vn; ev[1] = vy / vn; ev[2] = vz / vn;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        pu[k] = cX[k] * eu[0] + cY[k] * eu[1] + cZ[k] * eu[2];
+        pv[k] = cX[k] * ev[0] + cY[k] * ev[1] + cZ[k] * ev[2];
+    }
+}
+
+// One thread per cell, once per grid upload: the projections every point-in-cell test needs.  Same device
+// function as the on-the-fly path => bit-identical values; a candidate test then costs 16 loads, no trig.
+template <class A>
+__global__ void precompute_cells_kernel(const A* __restrict__ lon, const A* __restrict__ lat, int ny, int nx, double* __restrict__ out) {
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long ncell = (long long)(ny - 1) * (nx - 1);
+    if (c >= ncell) return;
+    const int j = (int)(c / (nx - 1)), i = (int)(c % (nx - 1));
+    const long long o00 = (long long)j * nx + i;
+    const A clon[4] = {lon[o00], lon[o00 + 1], lon[o00 + nx + 1], lon[o00 + nx]};
+    const A clat[4] = {lat[o00], lat[o00 + 1], lat[o00 + nx + 1], lat[o00 + nx]};
+    double pu[4], pv[4], eu[3], ev[3];
+    project_cell<A>(clon, clat, pu, pv, eu, ev);
+    double* o = out + c * 16;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { o[k] = pu[k]; o[4 + k] = pv[k]; }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { o[8 + k] = eu[k]; o[11 + k] = ev[k]; }
+    o[14] = 0.0; o[15] = 0.0;
+}
+
+cudaError_t launch_precompute_cells(const void* lon, const void* lat, int ny, int nx, bool coord_f64, double* out, cudaStream_t s) {
+    const long long ncell = (long long)(ny - 1) * (nx - 1);
+    const unsigned grid = (unsigned)((ncell + 127) / 128);
+    if (coord_f64) precompute_cells_kernel<double><<<grid, 128, 0, s>>>((const double*)lon, (const double*)lat, ny, nx, out);
+    else precompute_cells_kernel<float><<<grid, 128, 0, s>>>((const float*)lon, (const float*)lat, ny, nx, out);
+    return cudaGetLastError();
+}
+
 template <class A, class D>
 __device__ __forceinline__ void load_corners(const GridDev& g, CGridCtx<A, D>& e, int j, int i) {
     if (e.kyi == j && e.kxi == i) return;
@@ -56,32 +118,17 @@ __device__ __forceinline__ void load_corners(const GridDev& g, CGridCtx<A, D>& e
     e.clon[1] = ldg(lon + o00 + 1);      e.clat[1] = ldg(lat + o00 + 1);
     e.clon[2] = ldg(lon + o00 + nx + 1); e.clat[2] = ldg(lat + o00 + nx + 1);
     e.clon[3] = ldg(lon + o00 + nx);     e.clat[3] = ldg(lat + o00 + nx);
-    if (g.spherical) {  // _spherical_project_cell_and_query, cell part (index_search.py:203-236)
-        double cX[4], cY[4], cZ[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const double la = deg2rad_np((double)e.clat[k]), lo = deg2rad_np((double)e.clon[k]);
-            const double cl = cos(la);
-            cX[k] = cos(lo) * cl; cY[k] = sin(lo) * cl; cZ[k] = sin(la);
-        }
-        double ux = (cX[1] + cX[2]) - (cX[0] + cX[3]);
-        double uy = (cY[1] + cY[2]) - (cY[0] + cY[3]);
-        double uz = (cZ[1] + cZ[2]) - (cZ[0] + cZ[3]);
-        double un = sqrt(ux * ux + uy * uy + uz * uz);
-        if (un == 0.0) un = 1.0;
-        e.eu[0] = ux / un; e.eu[1] = uy / un; e.eu[2] = uz / un;
-        double vx = (cX[2] + cX[3]) - (cX[0] + cX[1]);
-        double vy = (cY[2] + cY[3]) - (cY[0] + cY[1]);
-        double vz = (cZ[2] + cZ[3]) - (cZ[0] + cZ[1]);
-        const double d = vx * e.eu[0] + vy * e.eu[1] + vz * e.eu[2];
-        vx = vx - d * e.eu[0]; vy = vy - d * e.eu[1]; vz = vz - d * e.eu[2];
-        double vn = sqrt(vx * vx + vy * vy + vz * vz);
-        if (vn == 0.0) vn = 1.0;
-        e.ev[0] = vx / vn; e.ev[1] = vy / vn; e.ev[2] = vz / vn;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            e.pu[k] = cX[k] * e.eu[0] + cY[k] * e.eu[1] + cZ[k] * e.eu[2];
-            e.pv[k] = cX[k] * e.ev[0] + cY[k] * e.ev[1] + cZ[k] * e.ev[2];
+    if (g.spherical) {
+        if (g.cellproj) {
+            const double2* __restrict__ c = reinterpret_cast<const double2*>(g.cellproj + ((long long)j * (nx - 1) + i) * 16);
+            const double2 q0 = __ldg(c), q1 = __ldg(c + 1), q2 = __ldg(c + 2), q3 = __ldg(c + 3), q4 = __ldg(c + 4), q5 = __ldg(c + 5),
+                          q6 = __ldg(c + 6);
+            e.pu[0] = q0.x; e.pu[1] = q0.y; e.pu[2] = q1.x; e.pu[3] = q1.y;
+            e.pv[0] = q2.x; e.pv[1] = q2.y; e.pv[2] = q3.x; e.pv[3] = q3.y;
+            e.eu[0] = q4.x; e.eu[1] = q4.y; e.eu[2] = q5.x;
+            e.ev[0] = q5.y; e.ev[1] = q6.x; e.ev[2] = q6.y;
+        } else {
+            project_cell<A>(e.clon, e.clat, e.pu, e.pv, e.eu, e.ev);
         }
     }
 }
@@ -146,10 +193,9 @@ __device__ __forceinline__ unsigned int quant(P v, double lo_, double hi_, int b
     return (unsigned int)s;
 }
 
-template <class A, class D, class PY, class PX>
-__device__ __forceinline__ void hash_query(const GridDev& g, CGridCtx<A, D>& e, PY y, PX x, const Query& q, int& yi, int& xi,
-                                           double& xsi, double& eta) {
-    yi = -3; xi = -3; xsi = -1.0; eta = -1.0;  // GRID_SEARCH_ERROR, coords -1 (spatialhash.py:454-455,511)
+// quantised hash-grid coordinates of the sampled point (spatialhash.py:417-431,647-695)
+template <class A, class PY, class PX>
+__device__ __forceinline__ void hash_coords(const GridDev& g, PY y, PX x, unsigned int& qx, unsigned int& qy, unsigned int& qz) {
     using P = prom_t<PY, PX>;
     using Q = prom_t<P, A>;
     P hx, hy, hz;
@@ -162,10 +208,30 @@ __device__ __forceinline__ void hash_query(const GridDev& g, CGridCtx<A, D>& e, 
     } else {
         hx = x; hy = y; hz = 0;
     }
-    const unsigned int code = (dilate10(quant<Q, A>(hz, g.hbox[4], g.hbox[5], g.hash_bitwidth)) << 2) |
-                              (dilate10(quant<Q, A>(hy, g.hbox[2], g.hbox[3], g.hash_bitwidth)) << 1) |
-                              dilate10(quant<Q, A>(hx, g.hbox[0], g.hbox[1], g.hash_bitwidth));
-    long long l = 0, h = g.hnkeys;  // np.searchsorted(keys, code) (side="left")
+    qx = quant<Q, A>(hx, g.hbox[0], g.hbox[1], g.hash_bitwidth);
+    qy = quant<Q, A>(hy, g.hbox[2], g.hbox[3], g.hash_bitwidth);
+    qz = quant<Q, A>(hz, g.hbox[4], g.hbox[5], g.hash_bitwidth);
+}
+
+// is face (j, i) listed under hash cell (qx, qy, qz)?  (its quantised bounding box contains the cell)
+__device__ __forceinline__ bool face_listed(const GridDev& g, int j, int i, unsigned int qx, unsigned int qy, unsigned int qz) {
+    const unsigned long long b = ldg(g.hqbox + (long long)j * (g.nx - 1) + i);
+    const unsigned int xl = b & 1023u, xh = (b >> 10) & 1023u, yl = (b >> 20) & 1023u, yh = (b >> 30) & 1023u,
+                       zl = (b >> 40) & 1023u, zh = (b >> 50) & 1023u;
+    return qx >= xl && qx <= xh && qy >= yl && qy <= yh && qz >= zl && qz <= zh;
+}
+
+template <class A, class D, class PY, class PX>
+__device__ __forceinline__ void hash_query(const GridDev& g, CGridCtx<A, D>& e, PY y, PX x, const Query& q, unsigned int qx,
+                                           unsigned int qy, unsigned int qz, int& yi, int& xi, double& xsi, double& eta) {
+    yi = -3; xi = -3; xsi = -1.0; eta = -1.0;  // GRID_SEARCH_ERROR, coords -1 (spatialhash.py:454-455,511)
+    const unsigned int code = (dilate10(qz) << 2) | (dilate10(qy) << 1) | dilate10(qx);
+    long long l = 0, h = g.hnkeys;  // np.searchsorted(keys, code) (side="left"), narrowed by the bucket table
+    if (g.hbucket) {
+        const unsigned int b = code >> g.hbucket_shift;
+        l = ldg(g.hbucket + b);
+        h = ldg(g.hbucket + b + 1);
+    }
     while (l < h) {
         const long long m = (l + h) >> 1;
         if (ldg(g.hkeys + m) < code) l = m + 1; else h = m;
@@ -327,8 +393,39 @@ struct CGridPolicy {
             bool found = false;
             if (!no_hint && e.yi >= 0 && e.xi >= 0 && e.yi < g.ny - 1 && e.xi < g.nx - 1)
                 found = point_in_cell(g, e, e.yi, e.xi, q, xsi, eta);
-            if (found) { yi = e.yi; xi = e.xi; }
-            else hash_query(g, e, y, x, q, yi, xi, xsi, eta);
+            if (found) {
+                yi = e.yi; xi = e.xi;
+            } else {
+                // The reference goes straight to the spatial hash.  Most misses are a move into an adjacent
+                // cell: test the 8 neighbours first and accept a hit only when the point is SAFELY interior
+                // (then that cell is the only one containing it, so the hash's "first containing candidate"
+                // is the same cell and yields the same coordinates, float32-rounded like spatialhash.py:511).
+                // Anything else -- edge-grazing points, jumps, no valid hint -- takes the exact hash path.
+                bool nb = false;
+                unsigned int qx, qy, qz;
+                hash_coords<A, PY, PX>(g, y, x, qx, qy, qz);
+                if (!no_hint && e.yi >= 0 && e.xi >= 0 && e.yi < g.ny - 1 && e.xi < g.nx - 1 && isfinite(q.x) && isfinite(q.y)) {
+                    const int hj = e.yi, hi = e.xi;
+#pragma unroll 1
+                    for (int k = 0; k < 8 && !nb; ++k) {
+                        const int dj = (k == 0 || k == 1 || k == 2) ? -1 : ((k == 3 || k == 4) ? 0 : 1);
+                        const int di = (k == 0 || k == 3 || k == 5) ? -1 : ((k == 1 || k == 6) ? 0 : 1);
+                        const int j = hj + dj, i = hi + di;
+                        if (j < 0 || i < 0 || j >= g.ny - 1 || i >= g.nx - 1) continue;
+                        double cs, ce;
+                        // ... and only when the hash table lists that face under the point's hash cell (a face
+                        // whose corner bounding box misses the point is invisible to the reference's query)
+                        if (point_in_cell(g, e, j, i, q, cs, ce) && cs > 1e-6 && cs < 1 - 1e-6 && ce > 1e-6 && ce < 1 - 1e-6 &&
+                            face_listed(g, j, i, qx, qy, qz)) {
+                            nb = true;
+                            yi = j; xi = i;
+                            xsi = (double)(float)cs;
+                            eta = (double)(float)ce;
+                        }
+                    }
+                }
+                if (!nb) hash_query(g, e, y, x, q, qx, qy, qz, yi, xi, xsi, eta);
+            }
             e.yi = yi; e.xi = xi;
             long long r = (long long)yi * g.xdim + (long long)xi;
             if (g.nz > 0) r += (long long)zi * (g.ydim * g.xdim);

@@ -33,6 +33,11 @@ struct GridDev {
     const long long* hcounts;     // number of candidate faces per key
     const unsigned int* hfaces;   // flat face id j * (nx - 1) + i, ascending within a key
     long long hnkeys;
+    const int* hbucket;           // hbucket[b] = first key index with (key >> hbucket_shift) >= b  (2^20 + 1 entries)
+    int hbucket_shift;
+    int pad3_;
+    const unsigned long long* hqbox;  // per face: quantised bbox (the hash cells that list the face), 6 x 10 bits
+    const double* cellproj;       // spherical curvilinear: per cell 16 doubles = pu[4], pv[4], eu[3], ev[3], pad[2]
     double hbox[6];               // xmin, xmax, ymin, ymax, zmin, zmax of the hash grid
     int off_x, off_y, off_z;      // C-grid staggering offsets (_xinterpolators.py:99-109)
     // multi-GPU mode D (X-slab domain decomposition): this engine holds lon[xi_offset : xi_offset + nx]
@@ -407,5 +412,6 @@ __global__ void sample_kernel(const SampleParams s) {
 // launchers implemented in agrid.cu / cgrid.cu (one translation unit per grid family keeps nvcc parallel)
 cudaError_t launch_agrid(const AdvectParams& p, bool coord_f64, bool data_f64, bool has_time, int nc, cudaStream_t s);
 cudaError_t launch_cgrid(const AdvectParams& p, bool coord_f64, bool data_f64, int nc, cudaStream_t s);
+cudaError_t launch_precompute_cells(const void* lon, const void* lat, int ny, int nx, bool coord_f64, double* out, cudaStream_t s);
 cudaError_t launch_sample_agrid(const SampleParams& p, bool coord_f64, bool data_f64, bool has_time, int nc, cudaStream_t s);
 cudaError_t launch_sample_cgrid(const SampleParams& p, bool coord_f64, bool data_f64, int nc, cudaStream_t s);

@@ -167,7 +167,7 @@ struct pb_engine {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, tev0 = nullptr, tev1 = nullptr;
     // grid
-    DevBuf lon, lat, depth, time, hkeys, hstarts, hcounts, hfaces;
+    DevBuf lon, lat, depth, time, hkeys, hstarts, hcounts, hfaces, hbucket, cellproj, hqbox;
     int interp = 0;  // enum pb_interp
     GridDev g{};
     bool have_grid = false;
@@ -244,7 +244,7 @@ void pb_engine_destroy(pb_engine* e) {
     for (DevBuf* b : {&e->ax, &e->ay, &e->az, &e->adx, &e->ady, &e->adz, &e->at, &e->astate, &e->aei, &e->apid, &e->mdest, &e->mkeep,
                       &e->mcount, &e->mbounds})
         b->release();
-    for (DevBuf* b : {&e->hkeys, &e->hstarts, &e->hcounts, &e->hfaces, &e->lon, &e->lat, &e->depth, &e->time, &e->fbuf[0], &e->fbuf[1], &e->fbuf[2], &e->px, &e->py, &e->pz,
+    for (DevBuf* b : {&e->hqbox, &e->hbucket, &e->cellproj, &e->hkeys, &e->hstarts, &e->hcounts, &e->hfaces, &e->lon, &e->lat, &e->depth, &e->time, &e->fbuf[0], &e->fbuf[1], &e->fbuf[2], &e->px, &e->py, &e->pz,
                       &e->pdx, &e->pdy, &e->pdz, &e->pt, &e->pstate, &e->pei, &e->ppid, &e->snap})
         b->release();
     if (e->d_rep) cudaFree(e->d_rep);
@@ -333,6 +333,7 @@ int32_t pb_grid_upload_rectilinear(pb_engine* e, const void* lon, int64_t nx, co
     e->g.nx = (int)nx; e->g.ny = (int)ny;
     e->g.curvilinear = 0;
     e->g.hkeys = nullptr; e->g.hstarts = nullptr; e->g.hcounts = nullptr; e->g.hfaces = nullptr; e->g.hnkeys = 0;
+    e->g.hbucket = nullptr; e->g.cellproj = nullptr; e->g.hqbox = nullptr;
     return upload_zt(e, depth, nz, coord_is_f64, time_s, nt, spherical, deg2m, xdim_cells, ydim_cells, zdim_cells);
 }
 
@@ -341,11 +342,12 @@ int32_t pb_grid_upload_curvilinear(pb_engine* e, const void* lon2d, const void* 
                                    int32_t spherical, double deg2m, int64_t xdim_cells, int64_t ydim_cells,
                                    int64_t zdim_cells, const uint32_t* hash_keys, const int64_t* hash_starts,
                                    const int64_t* hash_counts, int64_t n_keys, const uint32_t* hash_faces,
-                                   int64_t n_entries, const double* hash_box6, int32_t hash_bitwidth) {
+                                   int64_t n_entries, const double* hash_box6, int32_t hash_bitwidth,
+                                   const uint64_t* face_qbox) {
     if (!e) return fail(PB_ERR_INVALID, "engine is NULL");
     if (!lon2d || !lat2d || nx < 2 || ny < 2) return fail(PB_ERR_INVALID, "curvilinear grid needs (ny, nx) lon/lat with ny, nx >= 2");
     if (nx > INT_MAX || ny > INT_MAX || nz > INT_MAX || nt > INT_MAX) return fail(PB_ERR_INVALID, "axis too long");
-    if (!hash_keys || !hash_starts || !hash_counts || !hash_faces || !hash_box6 || n_keys < 1 || n_entries < 1)
+    if (!hash_keys || !hash_starts || !hash_counts || !hash_faces || !hash_box6 || !face_qbox || n_keys < 1 || n_entries < 1)
         return fail(PB_ERR_INVALID, "curvilinear grid needs its spatial-hash table");
     if (hash_bitwidth < 1 || hash_bitwidth > 1023) return fail(PB_ERR_INVALID, "hash bitwidth must be in 1..1023");
     CK(cudaSetDevice(e->device));
@@ -357,6 +359,7 @@ int32_t pb_grid_upload_curvilinear(pb_engine* e, const void* lon2d, const void* 
     if ((rc = upload(e, e->hstarts, hash_starts, n_keys * 8))) return rc;
     if ((rc = upload(e, e->hcounts, hash_counts, n_keys * 8))) return rc;
     if ((rc = upload(e, e->hfaces, hash_faces, n_entries * 4))) return rc;
+    if ((rc = upload(e, e->hqbox, face_qbox, (size_t)(ny - 1) * (nx - 1) * 8))) return rc;
     GridDev& g = e->g;
     g.nx = (int)nx; g.ny = (int)ny;
     g.curvilinear = 1;
@@ -366,7 +369,30 @@ int32_t pb_grid_upload_curvilinear(pb_engine* e, const void* lon2d, const void* 
     g.hcounts = (const long long*)e->hcounts.p;
     g.hfaces = (const unsigned int*)e->hfaces.p;
     g.hnkeys = n_keys;
+    g.hqbox = (const unsigned long long*)e->hqbox.p;
     for (int k = 0; k < 6; ++k) g.hbox[k] = hash_box6[k];
+    {   // bucket table over the top bits of the 30-bit Morton key: narrows the binary search to a few keys
+        const int bits = 20, shift = 30 - bits;
+        const long long nb = 1LL << bits;
+        std::vector<int> bucket(nb + 1);
+        long long k = 0;
+        for (long long b = 0; b <= nb; ++b) {
+            while (k < n_keys && (long long)(hash_keys[k] >> shift) < b) ++k;
+            bucket[b] = (int)k;
+        }
+        if ((rc = upload(e, e->hbucket, bucket.data(), (size_t)(nb + 1) * sizeof(int)))) return rc;
+        CK(cudaStreamSynchronize(e->stream));
+        g.hbucket = (const int*)e->hbucket.p;
+        g.hbucket_shift = shift;
+    }
+    g.cellproj = nullptr;
+    if (spherical) {  // per-cell tangent-plane projections, computed once on the device
+        const size_t ncell = (size_t)(ny - 1) * (nx - 1);
+        if ((rc = e->cellproj.ensure(ncell * 16 * sizeof(double)))) return rc;
+        cudaError_t ce = launch_precompute_cells(e->lon.p, e->lat.p, (int)ny, (int)nx, coord_is_f64 != 0, (double*)e->cellproj.p, e->stream);
+        if (ce != cudaSuccess) return fail(PB_ERR_CUDA, "precompute_cells launch failed: %s", cudaGetErrorString(ce));
+        g.cellproj = (const double*)e->cellproj.p;
+    }
     return upload_zt(e, depth, nz, coord_is_f64, time_s, nt, spherical, deg2m, xdim_cells, ydim_cells, zdim_cells);
 }
 

@@ -70,12 +70,14 @@ class Engine:
         counts = np.ascontiguousarray(h["counts"], dtype=np.int64)
         faces = np.ascontiguousarray(h["faces"], dtype=np.uint32)
         box = np.ascontiguousarray(h["box"], dtype=np.float64)
+        qbox = np.ascontiguousarray(h["qbox"], dtype=np.uint64)
+        assert qbox.size == (ny - 1) * (nx - 1)
         check(
             self._lib.pb_grid_upload_curvilinear(
                 self._h, ptr(lon2d), ptr(lat2d), ny, nx, ptr(depth), 0 if depth is None else depth.size,
                 int(cdt == np.float64), ptr(time_s), 0 if time_s is None else time_s.size, int(bool(spherical)),
                 float(deg2m), int(xdim), int(ydim), int(zdim or 0), ptr(keys), ptr(starts), ptr(counts), keys.size,
-                ptr(faces), faces.size, ptr(box), int(h["bitwidth"]),
+                ptr(faces), faces.size, ptr(box), int(h["bitwidth"]), ptr(qbox),
             )
         )  # fmt: skip
 

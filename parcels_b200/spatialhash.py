@@ -91,5 +91,10 @@ def build_spatial_hash(lon2d: np.ndarray, lat2d: np.ndarray, spherical: bool) ->
     codes = (packed >> np.uint64(32)).astype(np.uint32)
     starts = np.concatenate(([0], np.flatnonzero(codes[1:] != codes[:-1]) + 1)).astype(np.int64)
     counts = np.diff(np.concatenate((starts, [codes.size]))).astype(np.int64)
+    # per-face quantised bounding box, packed 6 x 10 bits: a face is listed under hash cell (qx, qy, qz) iff the
+    # cell lies inside this box -- lets the device decide table membership without walking the table
+    qbox = (lo[0] | (hi[0] << 10) | (lo[1] << 20) | (hi[1] << 30) | (lo[2] << 40) | (hi[2] << 50)).astype(np.uint64)
+    qbox[~valid] = np.uint64(1023)  # lo = 1023 > hi = 0: empty
     return dict(keys=np.ascontiguousarray(codes[starts]), starts=starts, counts=counts, faces=np.ascontiguousarray(faces),
-                box=np.array([float(b) for b in box], dtype=np.float64), bitwidth=int(bitwidth))  # fmt: skip
+                box=np.array([float(b) for b in box], dtype=np.float64), bitwidth=int(bitwidth),
+                qbox=np.ascontiguousarray(qbox))  # fmt: skip
