@@ -226,6 +226,7 @@ __device__ __forceinline__ void eval_uvw(const GridDev& g, const FieldDev& f, Ev
 template <class A, class D, bool HAS_TIME, int NC_>
 struct AGridPolicy {
     static constexpr int NC = NC_;
+    static constexpr bool RUNTIME_DTYPE = false;  // interpolation arithmetic is typed on the position dtype
     using Ctx = EvalCtx<A, D, NC_>;
     __device__ static __forceinline__ void init(Ctx& e, const AdvectParams&, int ei) {
         e.cx.idx = e.cy.idx = e.cz.idx = e.ct.idx = -100;

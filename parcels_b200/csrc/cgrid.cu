@@ -20,10 +20,19 @@ __device__ __forceinline__ double mod_np(double a, double b) {
     if (r != 0.0) { if (r < 0.0) r += b; } else r = copysign(0.0, b);
     return r;
 }
+// Out-of-line transcendentals: the curvilinear path evaluates ~13 double-precision sin/cos per sample;
+// inlining each expansion (~200 SASS instructions) made the kernel overflow the instruction cache
+// (ncu: stall_no_inst dominant).  One shared copy each.
+__device__ __noinline__ double cos_ool(double x) { return cos(x); }
+__device__ __noinline__ double sin_ool(double x) { return sin(x); }
+__device__ __noinline__ float cosf_ool(float x) { return cosf(x); }
+__device__ __noinline__ float sinf_ool(float x) { return sinf(x); }
+__device__ __forceinline__ float cosx(float x) { return cosf_ool(x); }
+__device__ __forceinline__ double cosx(double x) { return cos_ool(x); }
+__device__ __forceinline__ float sinx(float x) { return sinf_ool(x); }
+__device__ __forceinline__ double sinx(double x) { return sin_ool(x); }
 __device__ __forceinline__ float sqrt_np(float x) { return sqrtf(x); }
 __device__ __forceinline__ double sqrt_np(double x) { return sqrt(x); }
-__device__ __forceinline__ float sin_np(float x) { return sinf(x); }
-__device__ __forceinline__ double sin_np(double x) { return sin(x); }
 
 template <class A, class D>
 struct CGridCtx {
@@ -53,8 +62,8 @@ __device__ __forceinline__ void project_cell(const A (&clon)[4], const A (&clat)
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const double la = deg2rad_np((double)clat[k]), lo = deg2rad_np((double)clon[k]);
-        const double cl = cos(la);
-        cX[k] = cos(lo) * cl; cY[k] = sin(lo) * cl; cZ[k] = sin(la);
+        const double cl = cos_ool(la);
+        cX[k] = cos_ool(lo) * cl; cY[k] = sin_ool(lo) * cl; cZ[k] = sin_ool(la);
     }
     double ux = (cX[1] + cX[2]) - (cX[0] + cX[3]);
     double uy = (cY[1] + cY[2]) - (cY[0] + cY[3]);
@@ -133,21 +142,33 @@ __device__ __forceinline__ void load_corners(const GridDev& g, CGridCtx<A, D>& e
     }
 }
 
-// _bilinear_inverse (index_search.py:132-149); np.dot(_invA, p) sums left to right
-__device__ __forceinline__ bool bilinear_inverse(const double (&px)[4], const double (&py)[4], double xq, double yq,
-                                                 double& xsi, double& eta) {
-    const double a0 = px[0], a1 = px[1] - px[0], a2 = px[3] - px[0], a3 = ((px[0] - px[1]) + px[2]) - px[3];
-    const double b0 = py[0], b1 = py[1] - py[0], b2 = py[3] - py[0], b3 = ((py[0] - py[1]) + py[2]) - py[3];
+// _bilinear_inverse (index_search.py:132-149); np.dot(_invA, p) sums left to right.  Out of line (one copy,
+// shared by the hint, neighbour and hash-candidate tests) with everything passed and returned in registers.
+struct BilinearInv {
+    double xsi, eta;
+    bool inside;
+};
+__device__ __noinline__ BilinearInv bilinear_inverse_v(double px0, double px1, double px2, double px3, double py0, double py1,
+                                                       double py2, double py3, double xq, double yq) {
+    const double a0 = px0, a1 = px1 - px0, a2 = px3 - px0, a3 = ((px0 - px1) + px2) - px3;
+    const double b0 = py0, b1 = py1 - py0, b2 = py3 - py0, b3 = ((py0 - py1) + py2) - py3;
     const double aa = a3 * b2 - a2 * b3;
     const double bb = a3 * b0 - a0 * b3 + a1 * b2 - a2 * b1 + xq * b3 - yq * a3;
     const double cc = a1 * b0 - a0 * b1 + xq * b1 - yq * a1;
     const double det2 = bb * bb - 4 * aa * cc;
     const double det = det2 > 0 ? sqrt(det2) : -1.0;
-    eta = fabs(aa) < 1e-12 ? -cc / bb : (det2 > 0 ? (-bb + det) / (2 * aa) : -1.0);
-    const double den = a1 + a3 * eta;
-    xsi = fabs(den) < 1e-12 ? ((yq - py[0]) / (py[1] - py[0]) + (yq - py[3]) / (py[2] - py[3])) * 0.5
-                            : (xq - a0 - a2 * eta) / den;
-    return xsi >= 0 && xsi <= 1 && eta >= 0 && eta <= 1;
+    BilinearInv r;
+    r.eta = fabs(aa) < 1e-12 ? -cc / bb : (det2 > 0 ? (-bb + det) / (2 * aa) : -1.0);
+    const double den = a1 + a3 * r.eta;
+    r.xsi = fabs(den) < 1e-12 ? ((yq - py0) / (py1 - py0) + (yq - py3) / (py2 - py3)) * 0.5 : (xq - a0 - a2 * r.eta) / den;
+    r.inside = r.xsi >= 0 && r.xsi <= 1 && r.eta >= 0 && r.eta <= 1;
+    return r;
+}
+__device__ __forceinline__ bool bilinear_inverse(const double (&px)[4], const double (&py)[4], double xq, double yq,
+                                                 double& xsi, double& eta) {
+    const BilinearInv r = bilinear_inverse_v(px[0], px[1], px[2], px[3], py[0], py[1], py[2], py[3], xq, yq);
+    xsi = r.xsi; eta = r.eta;
+    return r.inside;
 }
 
 struct Query {  // the sampled point, prepared once per eval
@@ -202,9 +223,9 @@ __device__ __forceinline__ void hash_coords(const GridDev& g, PY y, PX x, unsign
     if (g.spherical) {  // trig in the dtype of the sampled position (spatialhash.py:417-421)
         const PY lat = deg2rad_np(y);
         const PX lon = deg2rad_np(x);
-        hx = cos_np(lon) * cos_np(lat);
-        hy = sin_np(lon) * cos_np(lat);
-        hz = sin_np(lat);
+        hx = cosx(lon) * cosx(lat);
+        hy = sinx(lon) * cosx(lat);
+        hz = sinx(lat);
     } else {
         hx = x; hy = y; hz = 0;
     }
@@ -221,8 +242,8 @@ __device__ __forceinline__ bool face_listed(const GridDev& g, int j, int i, unsi
     return qx >= xl && qx <= xh && qy >= yl && qy <= yh && qz >= zl && qz <= zh;
 }
 
-template <class A, class D, class PY, class PX>
-__device__ __forceinline__ void hash_query(const GridDev& g, CGridCtx<A, D>& e, PY y, PX x, const Query& q, unsigned int qx,
+template <class A, class D>
+__device__ __forceinline__ void hash_query(const GridDev& g, CGridCtx<A, D>& e, const Query& q, bool finite, unsigned int qx,
                                            unsigned int qy, unsigned int qz, int& yi, int& xi, double& xsi, double& eta) {
     yi = -3; xi = -3; xsi = -1.0; eta = -1.0;  // GRID_SEARCH_ERROR, coords -1 (spatialhash.py:454-455,511)
     const unsigned int code = (dilate10(qz) << 2) | (dilate10(qy) << 1) | dilate10(qx);
@@ -236,7 +257,6 @@ __device__ __forceinline__ void hash_query(const GridDev& g, CGridCtx<A, D>& e, 
         const long long m = (l + h) >> 1;
         if (ldg(g.hkeys + m) < code) l = m + 1; else h = m;
     }
-    const bool finite = isfinite((double)x) && isfinite((double)y);
     if (!(l < g.hnkeys && finite && ldg(g.hkeys + l) == code)) return;
     const long long start = ldg(g.hstarts + l), cnt = ldg(g.hcounts + l);
     const int ncol = g.nx - 1;
@@ -264,7 +284,7 @@ __device__ __forceinline__ auto edge_length(A lat1, A lat2, A lon1, A lon2, L la
     if constexpr (SPH) {
         using R = decltype(A() * L());
         const L rad_lat = (L)(3.14159265358979323846 / 180.0) * lat;
-        const R t1 = ((lon2 - lon1) * (A)deg2m) * cos_np(rad_lat);
+        const R t1 = ((lon2 - lon1) * (A)deg2m) * cosx(rad_lat);
         const A t2 = (lat2 - lat1) * (A)deg2m;
         return sqrt_np((R)(t1 * t1 + t2 * t2));
     } else {
@@ -273,9 +293,10 @@ __device__ __forceinline__ auto edge_length(A lat1, A lat2, A lon1, A lon2, L la
     }
 }
 
-template <bool SPH, class C, class A, class TZ, class TY, class TX, class PY, int NC>
+// `conv` = deg2m * cos_ool(deg2rad(y)) in the dtype of the sampled y (spherical meshes only)
+template <bool SPH, class C, class A, class TZ, class TY, class TX, class CV, int NC>
 __device__ __forceinline__ void cgrid_finish(const GridDev& g, const A (&px)[4], const A (&py)[4], C cu0, C cu1, C cv0, C cv1,
-                                             C cw0, C cw1, TZ zeta, TY eta, TX xsi, PY y, Val& u, Val& v, Val& w) {
+                                             C cw0, C cw1, TZ zeta, TY eta, TX xsi, CV conv, Val& u, Val& v, Val& w) {
     constexpr bool sph = SPH;
     const auto omx = 1 - xsi;
     const auto ome = 1 - eta;
@@ -308,7 +329,6 @@ __device__ __forceinline__ void cgrid_finish(const GridDev& g, const A (&px)[4],
     auto ur = uu / jac;
     auto vr = vv / jac;
     if (sph) {  // u /= conversion; v /= conversion (in place: keeps u's dtype)
-        const PY conv = (PY)g.deg2m * cos_np(deg2rad_np(y));
         ur = (decltype(ur))(ur / conv);
         vr = (decltype(vr))(vr / conv);
     }
@@ -325,9 +345,11 @@ __device__ __forceinline__ void cgrid_finish(const GridDev& g, const A (&px)[4],
 // ------------------------------------------------------------------------------------------------
 // the policy
 // ------------------------------------------------------------------------------------------------
-template <class A, class D, int NC_, bool CURV>
+// Rectilinear C-grid (1-D lon/lat): bcoords come from the typed 1-D axis search.
+template <class A, class D, int NC_>
 struct CGridPolicy {
     static constexpr int NC = NC_;
+    static constexpr bool RUNTIME_DTYPE = false;
     using Ctx = CGridCtx<A, D>;
 
     __device__ static __forceinline__ void init(Ctx& e, const AdvectParams& p, int ei) {
@@ -380,67 +402,7 @@ struct CGridPolicy {
         }
         int yi, xi;
         A px[4], py[4];
-        if (CURV) {
-            // -- _search_indices_curvilinear_2d (index_search.py:242-295): hint, then spatial hash
-            Query q;
-            q.x = (double)x; q.y = (double)y;
-            if (g.spherical) {
-                const double la = deg2rad_np(q.y), lo = deg2rad_np(q.x);
-                const double cl = cos(la);
-                q.qu_x = cos(lo) * cl; q.qu_y = sin(lo) * cl; q.qu_z = sin(la);
-            }
-            double xsi = -1.0, eta = -1.0;
-            bool found = false;
-            if (!no_hint && e.yi >= 0 && e.xi >= 0 && e.yi < g.ny - 1 && e.xi < g.nx - 1)
-                found = point_in_cell(g, e, e.yi, e.xi, q, xsi, eta);
-            if (found) {
-                yi = e.yi; xi = e.xi;
-            } else {
-                // The reference goes straight to the spatial hash.  Most misses are a move into an adjacent
-                // cell: test the 8 neighbours first and accept a hit only when the point is SAFELY interior
-                // (then that cell is the only one containing it, so the hash's "first containing candidate"
-                // is the same cell and yields the same coordinates, float32-rounded like spatialhash.py:511).
-                // Anything else -- edge-grazing points, jumps, no valid hint -- takes the exact hash path.
-                bool nb = false;
-                unsigned int qx, qy, qz;
-                hash_coords<A, PY, PX>(g, y, x, qx, qy, qz);
-                if (!no_hint && e.yi >= 0 && e.xi >= 0 && e.yi < g.ny - 1 && e.xi < g.nx - 1 && isfinite(q.x) && isfinite(q.y)) {
-                    const int hj = e.yi, hi = e.xi;
-#pragma unroll 1
-                    for (int k = 0; k < 8 && !nb; ++k) {
-                        const int dj = (k == 0 || k == 1 || k == 2) ? -1 : ((k == 3 || k == 4) ? 0 : 1);
-                        const int di = (k == 0 || k == 3 || k == 5) ? -1 : ((k == 1 || k == 6) ? 0 : 1);
-                        const int j = hj + dj, i = hi + di;
-                        if (j < 0 || i < 0 || j >= g.ny - 1 || i >= g.nx - 1) continue;
-                        double cs, ce;
-                        // ... and only when the hash table lists that face under the point's hash cell (a face
-                        // whose corner bounding box misses the point is invisible to the reference's query)
-                        if (point_in_cell(g, e, j, i, q, cs, ce) && cs > 1e-6 && cs < 1 - 1e-6 && ce > 1e-6 && ce < 1 - 1e-6 &&
-                            face_listed(g, j, i, qx, qy, qz)) {
-                            nb = true;
-                            yi = j; xi = i;
-                            xsi = (double)(float)cs;
-                            eta = (double)(float)ce;
-                        }
-                    }
-                }
-                if (!nb) hash_query(g, e, y, x, q, qx, qy, qz, yi, xi, xsi, eta);
-            }
-            e.yi = yi; e.xi = xi;
-            long long r = (long long)yi * g.xdim + (long long)xi;
-            if (g.nz > 0) r += (long long)zi * (g.ydim * g.xdim);
-            e.ei = (int)r;
-            int s = e.state;
-            if (zi == -1) s = max(s, (int)PB_ERROR_OUT_OF_BOUNDS);
-            if (xi == -3 || yi == -3) s = max(s, (int)PB_ERROR_GRID_SEARCHING);
-            if (zi == -2) s = max(s, (int)PB_ERROR_THROUGH_SURFACE);
-            e.state = s;
-            if (xi < 0 || yi < 0 || zi < 0) { u = Val{0.0, false}; v = u; w = u; return; }
-            load_corners(g, e, yi, xi);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) { px[k] = e.clon[k]; py[k] = e.clat[k]; }
-            finish<PZ, PY, double, double>(p, e, ti, tau, zi, zeta, yi, eta, xi, xsi, y, px, py, u, v, w);
-        } else {
+        {
             using TY = prom_t<PY, A>;
             using TX = prom_t<PX, A>;
             const TY eta = axis_search<PY, A>((const A*)g.lat, g.ny, y, e.cy);
@@ -476,7 +438,14 @@ struct CGridPolicy {
 #pragma unroll
             for (int k = 1; k < 4; ++k) if (-px[k] + px[0] > (A)180) px[k] = px[k] + (A)360;
         }
-        // -- the 2 faces x 2 time levels of U, V (, W) this cell needs (:246-330)
+        load_faces(g, f, e, ti, zi, yi, xi);
+        if (g.spherical) reduce_and_finish<true, TZ, TY, TX, PY>(g, e, px, py, tau, zeta, eta, xsi, y, u, v, w);
+        else reduce_and_finish<false, TZ, TY, TX, PY>(g, e, px, py, tau, zeta, eta, xsi, y, u, v, w);
+    }
+
+    // the 2 faces x 2 time levels of U, V (, W) this cell needs (_xinterpolators.py:246-330), re-gathered only
+    // when the cell or the time level changed
+    __device__ static __forceinline__ void load_faces(const GridDev& g, const FieldDev& f, Ctx& e, int ti, int zi, int yi, int xi) {
         if (e.fti != ti || e.fzi != zi || e.fyi != yi || e.fxi != xi) {
             e.fti = ti; e.fzi = zi; e.fyi = yi; e.fxi = xi;
             e.refills++;
@@ -508,38 +477,209 @@ struct CGridPolicy {
                 e.fw[0] = e.fw[1] = e.fw[2] = e.fw[3] = (D)0;
             }
         }
-        if (g.spherical) reduce_and_finish<true, TZ, TY, TX, PY>(g, e, px, py, tau, zeta, eta, xsi, y, u, v, w);
-        else reduce_and_finish<false, TZ, TY, TX, PY>(g, e, px, py, tau, zeta, eta, xsi, y, u, v, w);
     }
 
     template <bool SPH, class TZ, class TY, class TX, class PY>
     __device__ static __forceinline__ void reduce_and_finish(const GridDev& g, Ctx& e, const A (&px)[4], const A (&py)[4], double tau,
                                                              TZ zeta, TY eta, TX xsi, PY y, Val& u, Val& v, Val& w) {
+        const PY conv = SPH ? (PY)g.deg2m * cosx(deg2rad_np(y)) : (PY)1;
         if (tau > 0) {  // lenT == 2: reduce over time in promote(D, float64)
             const double omt = 1 - tau;
             cgrid_finish<SPH, double, A, TZ, TY, TX, PY, NC_>(g, px, py, e.fu[0] * omt + e.fu[2] * tau, e.fu[1] * omt + e.fu[3] * tau,
                                                               e.fv[0] * omt + e.fv[2] * tau, e.fv[1] * omt + e.fv[3] * tau,
                                                               e.fw[0] * omt + e.fw[2] * tau, e.fw[1] * omt + e.fw[3] * tau, zeta,
-                                                              eta, xsi, y, u, v, w);
+                                                              eta, xsi, conv, u, v, w);
         } else {
             cgrid_finish<SPH, D, A, TZ, TY, TX, PY, NC_>(g, px, py, e.fu[0], e.fu[1], e.fv[0], e.fv[1], e.fw[0], e.fw[1], zeta, eta,
-                                                         xsi, y, u, v, w);
+                                                         xsi, conv, u, v, w);
         }
     }
 };
 
-template <class A, class D, int NC, bool CURV>
-static cudaError_t launch1(const AdvectParams& p, cudaStream_t s) {
+
+// ------------------------------------------------------------------------------------------------
+// Curvilinear C-grid policy.  xsi/eta always come out of the closed-form bilinear inverse as float64
+// (float32-rounded on a hash/neighbour hit), so the dtype of the sampled position only matters in three
+// small places (depth bcoord, hash-grid quantisation, the spherical conversion factor): they branch at
+// run time and the whole search + interpolation is instantiated ONCE per kernel.
+// ------------------------------------------------------------------------------------------------
+template <class A, class D, int NC_, bool SPH>
+struct CurvPolicy {
+    static constexpr int NC = NC_;
+    static constexpr bool RUNTIME_DTYPE = true;
+    using Ctx = CGridCtx<A, D>;
+
+    __device__ static __forceinline__ void init(Ctx& e, const AdvectParams& p, int ei) { CGridPolicy<A, D, NC_>::init(e, p, ei); }
+    __device__ static __forceinline__ void finish(Ctx&, const AdvectParams&) {}
+
+    __device__ static __forceinline__ void eval_rt(const AdvectParams& p, Ctx& e, bool no_hint, double t, double z, double y, double x,
+                                                   bool xy_f32, bool z_f32, Val& u, Val& v, Val& w) {
+        const GridDev& g = p.g;
+        const FieldDev& f = p.f;
+        u = Val{0.0, false}; v = u; w = u;
+        // -- time (index_search.py:65-91)
+        double tau = 0.0;
+        int ti = 0;
+        if (g.nt > 0) {
+            if (!(0 <= t && t <= g.time_len)) {
+                e.state = PB_ERROR_OUTSIDE_TIME_INTERVAL;
+                e.out_of_time = true;
+                return;
+            }
+            tau = axis_search<double, double>(g.time, g.nt, t, e.ct);
+            ti = e.ct.idx;
+        }
+        // -- depth: bcoord dtype = promote(position dtype, A)
+        double zeta = 0.0;
+        bool zeta_f32 = false;
+        int zi = 0;
+        if (g.nz > 0) {
+            if (z_f32 && std::is_same<A, float>::value) {
+                zeta = (double)axis_search<float, A>((const A*)g.depth, g.nz, (float)z, e.cz);
+                zeta_f32 = true;
+            } else if (z_f32) {
+                zeta = (double)axis_search<float, A>((const A*)g.depth, g.nz, (float)z, e.cz);  // float z, float64 axis -> float64
+            } else {
+                zeta = (double)axis_search<double, A>((const A*)g.depth, g.nz, z, e.cz);
+            }
+            zi = e.cz.idx;
+        }
+        // -- _search_indices_curvilinear_2d (index_search.py:242-295): hint, (neighbours,) spatial hash
+        Query q;
+        q.x = x; q.y = y;
+        if (SPH) {
+            const double la = deg2rad_np(y), lo = deg2rad_np(x);
+            const double cl = cos_ool(la);
+            q.qu_x = cos_ool(lo) * cl; q.qu_y = sin_ool(lo) * cl; q.qu_z = sin_ool(la);
+        }
+        double xsi = -1.0, eta = -1.0;
+        int yi, xi;
+        const bool hint_ok = !no_hint && e.yi >= 0 && e.xi >= 0 && e.yi < g.ny - 1 && e.xi < g.nx - 1;
+        bool found = false;
+        if (hint_ok) found = point_in_cell(g, e, e.yi, e.xi, q, xsi, eta);
+        if (found) {
+            yi = e.yi; xi = e.xi;
+        } else {
+            // The reference goes straight to the spatial hash.  Most misses are a move into an adjacent cell:
+            // test the 8 neighbours first and accept a hit only when (a) the point is SAFELY interior -- then
+            // that cell is the only one containing it -- and (b) the hash table lists that face under the
+            // point's hash cell (a face whose corner bounding box misses the point is invisible to the
+            // reference's query).  Then the hash's "first containing candidate" is this very cell with these
+            // very coordinates, float32-rounded like spatialhash.py:511.  Anything else -- edge-grazing
+            // points, jumps, no valid hint -- takes the exact hash path.
+            unsigned int qx, qy, qz;
+            if (xy_f32) hash_coords<A, float, float>(g, (float)y, (float)x, qx, qy, qz);
+            else hash_coords<A, double, double>(g, y, x, qx, qy, qz);
+            bool nb = false;
+            if (hint_ok && isfinite(x) && isfinite(y)) {
+                const int hj = e.yi, hi = e.xi;
+#pragma unroll 1
+                for (int k = 0; k < 8 && !nb; ++k) {
+                    const int dj = (k < 3) ? -1 : ((k < 5) ? 0 : 1);
+                    const int di = (k == 0 || k == 3 || k == 5) ? -1 : ((k == 1 || k == 6) ? 0 : 1);
+                    const int j = hj + dj, i = hi + di;
+                    if (j < 0 || i < 0 || j >= g.ny - 1 || i >= g.nx - 1) continue;
+                    double cs, ce;
+                    if (point_in_cell(g, e, j, i, q, cs, ce) && cs > 1e-6 && cs < 1 - 1e-6 && ce > 1e-6 && ce < 1 - 1e-6 &&
+                        face_listed(g, j, i, qx, qy, qz)) {
+                        nb = true;
+                        yi = j; xi = i;
+                        xsi = (double)(float)cs;
+                        eta = (double)(float)ce;
+                    }
+                }
+            }
+            if (!nb) hash_query(g, e, q, xy_f32 ? isfinite((float)x) && isfinite((float)y) : isfinite(x) && isfinite(y), qx, qy, qz, yi, xi, xsi, eta);
+        }
+        e.yi = yi; e.xi = xi;
+        long long r = (long long)yi * g.xdim + (long long)xi;
+        if (g.nz > 0) r += (long long)zi * (g.ydim * g.xdim);
+        e.ei = (int)r;
+        int s = e.state;
+        if (zi == -1) s = max(s, (int)PB_ERROR_OUT_OF_BOUNDS);
+        if (xi == -3 || yi == -3) s = max(s, (int)PB_ERROR_GRID_SEARCHING);
+        if (zi == -2) s = max(s, (int)PB_ERROR_THROUGH_SURFACE);
+        e.state = s;
+        if (xi < 0 || yi < 0 || zi < 0) return;
+
+        // -- CGrid_Velocity (_xinterpolators.py:193-332)
+        load_corners(g, e, yi, xi);
+        A px[4], py[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { px[k] = e.clon[k]; py[k] = e.clat[k]; }
+        if (SPH) {  // corner longitudes unwrapped relative to corner 0 (:230-233)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) px[k] = mod_np((A)(px[k] + (A)180.0), (A)360.0) - (A)180.0;
+#pragma unroll
+            for (int k = 1; k < 4; ++k) if (px[k] - px[0] > (A)180) px[k] = px[k] - (A)360;
+#pragma unroll
+            for (int k = 1; k < 4; ++k) if (-px[k] + px[0] > (A)180) px[k] = px[k] + (A)360;
+        }
+        CGridPolicy<A, D, NC_>::load_faces(g, f, e, ti, zi, yi, xi);
+        // spherical conversion factor in the dtype of the sampled y
+        double conv = 1.0;
+        if (SPH) conv = xy_f32 ? (double)((float)g.deg2m * cosf_ool(deg2rad_np((float)y))) : g.deg2m * cos_ool(deg2rad_np(y));
+        Val wdummy;
+        if constexpr (SPH || std::is_same<A, double>::value) {
+            // every operand the face values meet is float64 (edge lengths are float64: float64 bcoords on a
+            // spherical mesh / float64 corner coordinates), so they convert exactly: ONE float64 code path
+            double c[6];
+            if (tau > 0) {
+                const double omt = 1 - tau;
+                c[0] = e.fu[0] * omt + e.fu[2] * tau; c[1] = e.fu[1] * omt + e.fu[3] * tau;
+                c[2] = e.fv[0] * omt + e.fv[2] * tau; c[3] = e.fv[1] * omt + e.fv[3] * tau;
+            } else {
+                c[0] = (double)e.fu[0]; c[1] = (double)e.fu[1]; c[2] = (double)e.fv[0]; c[3] = (double)e.fv[1];
+            }
+            cgrid_finish<SPH, double, A, double, double, double, double, 2>(g, px, py, c[0], c[1], c[2], c[3], 0.0, 0.0, 0.0, eta, xsi,
+                                                                            conv, u, v, wdummy);
+        } else {  // flat mesh with float32 corner coordinates: edge lengths are float32, the face dtype matters
+            if (tau > 0) {
+                const double omt = 1 - tau;
+                cgrid_finish<SPH, double, A, double, double, double, double, 2>(g, px, py, e.fu[0] * omt + e.fu[2] * tau,
+                                                                                e.fu[1] * omt + e.fu[3] * tau, e.fv[0] * omt + e.fv[2] * tau,
+                                                                                e.fv[1] * omt + e.fv[3] * tau, 0.0, 0.0, 0.0, eta, xsi, conv, u,
+                                                                                v, wdummy);
+            } else {
+                cgrid_finish<SPH, D, A, double, double, double, double, 2>(g, px, py, e.fu[0], e.fu[1], e.fv[0], e.fv[1], (D)0, (D)0, 0.0, eta,
+                                                                           xsi, conv, u, v, wdummy);
+            }
+        }
+        if (NC_ == 3) {  // W: linear in zeta between the two Z faces (:316-330); dtype as NumPy would promote
+            const bool tl = tau > 0;
+            if (!tl && std::is_same<D, float>::value && zeta_f32) {
+                const float zf = (float)zeta;
+                const float wr = (float)e.fw[0] * (1 - zf) + (float)e.fw[1] * zf;
+                w = Val{(double)wr, true};
+            } else {
+                const double omt = 1 - tau;
+                const double w0 = tl ? e.fw[0] * omt + e.fw[2] * tau : (double)e.fw[0];
+                const double w1 = tl ? e.fw[1] * omt + e.fw[3] * tau : (double)e.fw[1];
+                const double omz = zeta_f32 ? (double)(1 - (float)zeta) : 1 - zeta;
+                w = Val{w0 * omz + w1 * zeta, false};
+            }
+        } else {
+            w = Val{0.0, u.f32};
+        }
+        if (u.v != u.v || v.v != v.v || w.v != w.v) e.state = max(e.state, (int)PB_ERROR_INTERPOLATION);
+    }
+};
+
+template <class Policy>
+static cudaError_t launch_policy(const AdvectParams& p, cudaStream_t s) {
     const int block = 128;
     const long long grid = (p.P.n + block - 1) / block;
-    advect_kernel<CGridPolicy<A, D, NC, CURV>><<<(unsigned)grid, block, 0, s>>>(p);
+    advect_kernel<Policy><<<(unsigned)grid, block, 0, s>>>(p);
     return cudaGetLastError();
 }
 
 template <class A, class D>
 static cudaError_t launch_ad(const AdvectParams& p, int nc, cudaStream_t s) {
-    if (p.g.curvilinear) return nc == 3 ? launch1<A, D, 3, true>(p, s) : launch1<A, D, 2, true>(p, s);
-    return nc == 3 ? launch1<A, D, 3, false>(p, s) : launch1<A, D, 2, false>(p, s);
+    if (p.g.curvilinear) {
+        if (p.g.spherical) return nc == 3 ? launch_policy<CurvPolicy<A, D, 3, true>>(p, s) : launch_policy<CurvPolicy<A, D, 2, true>>(p, s);
+        return nc == 3 ? launch_policy<CurvPolicy<A, D, 3, false>>(p, s) : launch_policy<CurvPolicy<A, D, 2, false>>(p, s);
+    }
+    return nc == 3 ? launch_policy<CGridPolicy<A, D, 3>>(p, s) : launch_policy<CGridPolicy<A, D, 2>>(p, s);
 }
 
 cudaError_t launch_cgrid(const AdvectParams& p, bool coord_f64, bool data_f64, int nc, cudaStream_t s) {
@@ -547,15 +687,18 @@ cudaError_t launch_cgrid(const AdvectParams& p, bool coord_f64, bool data_f64, i
     return data_f64 ? launch_ad<float, double>(p, nc, s) : launch_ad<float, float>(p, nc, s);
 }
 
-template <class A, class D, int NC, bool CURV>
-static cudaError_t sample1(const SampleParams& p, cudaStream_t s) {
-    sample_kernel<CGridPolicy<A, D, NC, CURV>><<<(unsigned)((p.n + 127) / 128), 128, 0, s>>>(p);
+template <class Policy>
+static cudaError_t sample_policy(const SampleParams& p, cudaStream_t s) {
+    sample_kernel<Policy><<<(unsigned)((p.n + 127) / 128), 128, 0, s>>>(p);
     return cudaGetLastError();
 }
 template <class A, class D>
 static cudaError_t sample_ad(const SampleParams& p, int nc, cudaStream_t s) {
-    if (p.g.curvilinear) return nc == 3 ? sample1<A, D, 3, true>(p, s) : sample1<A, D, 2, true>(p, s);
-    return nc == 3 ? sample1<A, D, 3, false>(p, s) : sample1<A, D, 2, false>(p, s);
+    if (p.g.curvilinear) {
+        if (p.g.spherical) return nc == 3 ? sample_policy<CurvPolicy<A, D, 3, true>>(p, s) : sample_policy<CurvPolicy<A, D, 2, true>>(p, s);
+        return nc == 3 ? sample_policy<CurvPolicy<A, D, 3, false>>(p, s) : sample_policy<CurvPolicy<A, D, 2, false>>(p, s);
+    }
+    return nc == 3 ? sample_policy<CGridPolicy<A, D, 3>>(p, s) : sample_policy<CGridPolicy<A, D, 2>>(p, s);
 }
 cudaError_t launch_sample_cgrid(const SampleParams& p, bool coord_f64, bool data_f64, int nc, cudaStream_t s) {
     if (coord_f64) return data_f64 ? sample_ad<double, double>(p, nc, s) : sample_ad<double, float>(p, nc, s);

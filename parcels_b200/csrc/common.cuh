@@ -257,10 +257,33 @@ __global__ void __launch_bounds__(PB_BLOCK_THREADS, PB_MINBLOCKS) advect_kernel(
 
             // ---- advection kernel (kernels/_advection.py) ----
             Val u1, v1, w1, uk, vk, wk;
+            double su, sv, sw;  // running RK4 sums, left to right
             // with DiffusionUniformKh in the list, ei[:, -1] was overwritten with 0 for every particle by the
             // constant-field evals of the previous step: curvilinear hints are all zero again
-            Policy::template eval<float, float, float>(p, e, (it == 0 && p.hint_all_zero) || (it > 0 && p.diffusion), t, z, y, x, u1, v1, w1);
-            double su = u1.v, sv = v1.v, sw = w1.v;  // running RK4 sums, left to right
+            const bool nohint1 = (it == 0 && p.hint_all_zero) || (it > 0 && p.diffusion);
+            if constexpr (Policy::RUNTIME_DTYPE) {
+                // One eval call site (the policy branches at run time where the position dtype matters):
+                // keeps the heavy curvilinear search + C-grid code in the instruction cache.
+                su = sv = sw = 0.0;
+                uk = Val{0.0, false}; vk = uk; wk = uk;
+#pragma unroll 1
+                for (int k = 0; k < nstage; ++k) {
+                    const bool full = (k == 3);
+                    const bool first = (k == 0);
+                    const double xs = first ? (double)x : (double)x + (full ? uk.v : half_of(uk)) * dtp;
+                    const double ys = first ? (double)y : (double)y + (full ? vk.v : half_of(vk)) * dtp;
+                    const double zs = (first || !three_d) ? (double)z : (double)z + (full ? wk.v : half_of(wk)) * dtp;
+                    const double ts = first ? t : t + (full ? dtp : 0.5 * dtp);
+                    Policy::eval_rt(p, e, first && nohint1, ts, zs, ys, xs, /*xy_f32=*/first, /*z_f32=*/first || !three_d, uk, vk, wk);
+                    if (first) { su = uk.v; sv = vk.v; sw = wk.v; }
+                    else if (nstage == 4) {
+                        const double m = (k == 3) ? 1.0 : 2.0;  // u1 + 2*u2 + 2*u3 + u4
+                        su = su + m * uk.v; sv = sv + m * vk.v; sw = sw + m * wk.v;
+                    }
+                }
+            } else {
+            Policy::template eval<float, float, float>(p, e, nohint1, t, z, y, x, u1, v1, w1);
+            su = u1.v; sv = v1.v; sw = w1.v;
             uk = u1; vk = v1; wk = w1;
             for (int k = 1; k < nstage; ++k) {
                 // stage position: x + u*0.5*dt (k = 1, 2) or x + u*dt (k = 3)
@@ -278,6 +301,7 @@ __global__ void __launch_bounds__(PB_BLOCK_THREADS, PB_MINBLOCKS) advect_kernel(
                     const double m = (k == 3) ? 1.0 : 2.0;  // u1 + 2*u2 + 2*u3 + u4
                     su = su + m * uk.v; sv = sv + m * vk.v; sw = sw + m * wk.v;
                 }
+            }
             }
             double ddx, ddy, ddz;
             if (nstage == 4) {
@@ -401,8 +425,14 @@ __global__ void sample_kernel(const SampleParams s) {
     e.out_of_time = false;
     Val u, v, w;
     const bool nh = s.no_hint || !s.ei_hint;
-    if (s.pos_f32) Policy::template eval<float, float, float>(p, e, nh, s.t[i], (float)s.z[i], (float)s.y[i], (float)s.x[i], u, v, w);
-    else Policy::template eval<double, double, double>(p, e, nh, s.t[i], s.z[i], s.y[i], s.x[i], u, v, w);
+    if constexpr (Policy::RUNTIME_DTYPE) {
+        const bool f = s.pos_f32 != 0;
+        Policy::eval_rt(p, e, nh, s.t[i], f ? (double)(float)s.z[i] : s.z[i], f ? (double)(float)s.y[i] : s.y[i],
+                        f ? (double)(float)s.x[i] : s.x[i], f, f, u, v, w);
+    } else {
+        if (s.pos_f32) Policy::template eval<float, float, float>(p, e, nh, s.t[i], (float)s.z[i], (float)s.y[i], (float)s.x[i], u, v, w);
+        else Policy::template eval<double, double, double>(p, e, nh, s.t[i], s.z[i], s.y[i], s.x[i], u, v, w);
+    }
     s.u[i] = u.v; s.v[i] = v.v; s.w[i] = w.v;
     Policy::finish(e, p);
     s.ei_out[i] = e.ei;
