@@ -117,6 +117,124 @@ def c3_particles(field, n, seed):
     return dict(x=bl(lon), y=bl(lat), z=np.zeros(n), t=np.zeros(n))
 
 
+def _hash_noise(t, z, y, x, salt):
+    """deterministic noise in [-0.05, 0.05) from GLOBAL indices (so neighbouring slabs agree on halo columns)"""
+    h = np.sin(t * 12.9898 + z * 78.233 + y * 37.719 + x * 4.1414 + salt) * 43758.5453
+    return ((h - np.floor(h)) * 0.1 - 0.05).astype(np.float32)
+
+
+def c5_slab(rank, world, halo, nx=4320, ny=2160, nz=50, nt=2):
+    """config 5: rectilinear 1/12 deg x 50 levels field, THIS RANK'S X-slab only (columns lo..hi of the global
+    axis incl. halo); analytic modes + index-hashed noise, so every rank can build its slab independently."""
+    from parcels_b200.distributed import slab_plan
+
+    lon = np.linspace(-180.0, 180.0, nx)
+    lat = np.linspace(-80.0, 80.0, ny)
+    depth = 5500.0 * (np.linspace(0.0, 1.0, nz) ** 1.8)
+    times = np.arange(nt) * 86400.0
+    plan = slab_plan(lon, world, halo)[rank]
+    lo, hi = plan["lo"], plan["hi"]
+    xi = np.arange(lo, hi + 1, dtype=np.float64)[None, None, None, :]
+    yi = np.arange(ny, dtype=np.float64)[None, None, :, None]
+    zi = np.arange(nz, dtype=np.float64)[None, :, None, None]
+    ti = np.arange(nt, dtype=np.float64)[:, None, None, None]
+    X, Y, Z = 2 * np.pi * xi / (nx - 1), 2 * np.pi * yi / (ny - 1), zi / (nz - 1)
+    U = (np.sin(3 * X + 0.3 * ti) * np.cos(2 * Y) * (1 - 0.5 * Z) * 0.6 + np.cos(5 * Y + ti) * 0.3).astype(np.float32)
+    U = U + _hash_noise(ti, zi, yi, xi, 0.1)
+    V = (np.cos(2 * X + 0.2 * ti) * np.sin(4 * Y) * (1 - 0.3 * Z) * 0.6 + np.sin(3 * X) * 0.25).astype(np.float32)
+    V = V + _hash_noise(ti, zi, yi, xi, 1.7) + np.zeros_like(U)
+    W = ((np.sin(2 * X) * np.sin(3 * Y) * np.sin(np.pi * Z) * np.cos(0.5 * ti) * 0.9).astype(np.float32)
+         + _hash_noise(ti, zi, yi, xi, 2.9)) * np.float32(1e-3)  # fmt: skip
+    return dict(lon=lon, lat=lat, depth=depth, times=times, U=np.ascontiguousarray(U), V=np.ascontiguousarray(V),
+                W=np.ascontiguousarray(W.astype(np.float32)), lo=lo, hi=hi, plan=plan)
+
+
+def run_decomposed_bench(a, rank, local_rank, world):
+    """Mode D bench (config 5): field cut into X-slabs, particles migrate over NCCL.  One bench step = one
+    Kernel.execute over the decomposed field (advect kernels + migration rounds + all-to-all-v)."""
+    import torch
+    import torch.distributed as dist
+
+    import parcels_b200 as pb
+    from parcels_b200 import build
+    from parcels_b200 import distributed as D
+    from parcels_b200.particle import create_particle_data
+
+    build.build()
+    torch.cuda.set_device(local_rank)
+    dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    small = a.workload.endswith("_small")
+    dims = dict(nx=432, ny=216, nz=20, nt=2) if small else dict(nx=4320, ny=2160, nz=50, nt=2)
+    n_per_gpu = a.particles or (200_000 if small else 12_500_000)
+    dt, nsteps, halo = 600.0, 48, 3
+    f = c5_slab(rank, world, halo, **dims)
+    fs = pb.FieldSet.from_arrays(lon=f["lon"][f["lo"] : f["hi"] + 1].copy(), lat=f["lat"], depth=f["depth"], time=f["times"],
+                                 U=f["U"], V=f["V"], W=f["W"], mesh="spherical", xdim=f["lon"].size - 1)  # fmt: skip
+    dfs = D.DecomposedFieldSet.__new__(D.DecomposedFieldSet)
+    dfs.rank, dfs.world, dfs.device, dfs.plan, dfs.fs = rank, world, local_rank, f["plan"], fs
+    dfs.engine = fs.engine(local_rank)
+    dfs.engine.decomp_set(world, rank, f["plan"]["bounds"], f["plan"]["xi_offset"], f["plan"]["left_global"], f["plan"]["right_global"])
+    rng = np.random.default_rng(100 + rank)
+    b = f["plan"]["bounds"]
+    # every rank seeds particles uniformly over the GLOBAL domain: the first migration round routes them
+    n = n_per_gpu
+    x, y, z = rng.uniform(-170, 170, n), rng.uniform(-70, 70, n), rng.uniform(5, 5000, n)
+    pid = np.arange(n, dtype=np.int64) + rank * n
+    runtime = dt * nsteps
+    kernels = [pb.AdvectionRK4_3D, pb.DeleteParticle]
+    dev = f"cuda:{local_rank}"
+
+    def one_pass():
+        pdata = create_particle_data(nparticles=n, ngrids=1, initial=dict(x=x, y=y, z=z, t=np.zeros(n), particle_id=pid))
+        torch.cuda.synchronize()
+        dist.barrier()
+        t0 = time.perf_counter()
+        out, stats = D.execute_decomposed(dfs, pdata, kernels, dt, runtime, dist)
+        torch.cuda.synchronize()
+        dist.barrier()
+        return time.perf_counter() - t0, stats
+
+    for _ in range(a.warmup):
+        one_pass()
+    tot_t, tot_steps, tot_mig, rounds, kms = 0.0, 0, 0, 0, 0.0
+    with ClockSampler(local_rank) as clk:
+        for _ in range(a.steps):
+            t, st = one_pass()
+            tot_t += D.allreduce_max(t, dist, dev)
+            tot_steps += D.allreduce_sum(st["particle_steps"], dist, dev)
+            tot_mig += D.allreduce_sum(st["migrated"], dist, dev)
+            rounds = max(rounds, st["rounds"])
+            kms += D.allreduce_max(st["kernel_ms"], dist, dev)
+    dist.barrier()
+    dist.destroy_process_group()
+    if rank != 0:
+        return
+    peak, peak_src = measured_peak()
+    value = tot_steps / tot_t
+    kernel_rate = tot_steps / world / (kms * 1e-3)
+    achieved = 832 * kernel_rate / 1e9
+    line = {
+        "metric": METRIC, "value": value, "unit": "particle-steps/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": 1e3 * tot_t / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": f"{a.workload}: BASELINE.json configs[4] -- AdvectionRK4_3D, rectilinear {dims['nx']}x{dims['ny']}x{dims['nz']} "
+                               f"T={dims['nt']} f32 field DOMAIN-DECOMPOSED into {world} X-slabs (+{halo} halo columns), {n_per_gpu} "
+                               f"particles/GPU seeded over the whole domain, NCCL all-to-all-v migration; dt={dt:g} s x {nsteps} steps",
+                   "timed_region": "upload of the particle shard + initial routing + advect kernels + migration rounds + download "
+                                   "(wall clock between barriers, max over ranks)",
+                   "migrations_per_pass": tot_mig / a.steps, "advect_rounds_per_pass": rounds,
+                   "kernel_ms_per_pass_max_rank": kms / a.steps},
+        "e2e": {"value": value, "unit": "particle-steps/s", "h2d_bytes_per_step": n * 48 * world, "d2h_bytes_per_step": n * 48 * world,
+                "note": "the mode-D pass IS end-to-end: host particle arrays in, host arrays out"},
+        "gpu_launches": int(a.steps * rounds * 4),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "peak_source": peak_src, "algorithmic_bytes_per_particle_step": 832,
+                     "note": "per-GPU advect-kernel rate (kernel time only)"},
+        "clocks": clk.summary(),
+    }  # fmt: skip
+    print(json.dumps(line))
+
+
 # name -> spec.  bytes: algorithmic bytes per particle-step (SURVEY.md 8d / BASELINE.md 4)
 WORKLOADS = {
     "c2": dict(field=c2_field, fkw=dict(nx=1440, ny=720, nz=50, nt=3), particles=c2_particles, n=1_000_000, dt=600.0,
@@ -279,7 +397,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c2", choices=list(WORKLOADS))
+    ap.add_argument("--workload", default="c2", choices=list(WORKLOADS) + ["c5", "c5_small"])
     ap.add_argument("--particles", type=int, default=None, help="particles per GPU (default: the workload's)")
     ap.add_argument("--cpu-sample", type=int, default=20000, help="particles of the cpu_baseline sample")
     ap.add_argument("--ref-particles-per-core", type=int, default=4000)
@@ -290,6 +408,14 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    if a.workload.startswith("c5"):
+        if a.impl == "reference":
+            if rank == 0:
+                print(json.dumps({"impl": "reference", "unavailable": "config 5 has no single-process CPU equivalent; use --workload c2"}))
+            return
+        if world < 2:
+            raise SystemExit("workload c5 is the domain-decomposed mode: launch with torchrun on >= 2 GPUs")
+        return run_decomposed_bench(a, rank, local_rank, world)
     w = WORKLOADS[a.workload]
     n_per_gpu = a.particles or w["n"]
     dt, nsteps = w["dt"], w["nsteps"]
@@ -380,7 +506,10 @@ def main():
     e2e = None
     if not a.no_e2e:
         k_e2e = min(a.steps, 5) if n_per_gpu > 2_000_000 else a.steps
-        fresh = [{k: v.copy() for k, v in init.items()} for _ in range(k_e2e)]  # host input batches, made before timing
+        def pinned(v):  # page-locked host copy (the contract's "inputs from pinned host memory")
+            return torch.from_numpy(np.ascontiguousarray(v)).pin_memory().numpy()
+
+        fresh = [{k: pinned(v) for k, v in init.items()} for _ in range(k_e2e)]  # host input batches, made before timing
         for _ in range(min(a.warmup, 2)):
             ps._data = {k: v.copy() for k, v in init.items()}
             ps.execute(kernels, dt=dt, runtime=runtime)

@@ -187,14 +187,18 @@ class ParticleSet:
         eng.download_particles(d, ei_last)
         d["ei"][:, -1] = ei_last
         d["dt"][:] = dt  # kernel.py:225-226
-        dele = np.where(d["state"] == StatusCode.Delete)[0]
-        if len(dele) > 0:
-            self.remove_indices(dele)
-            d = self._data
-        for code in ERRORS_TO_THROW:
-            hit = d["state"] == code
-            if np.any(hit):
-                raise_for_state(code, d["z"][hit], d["y"][hit], d["x"][hit], d["t"][hit])
+        # the device report says whether any particle was deleted / errored: the O(N) host scans of
+        # kernel.py:98-106,239-245 only run when there is something to find
+        if rep["n_deleted"] > 0 or rep["max_state"] == StatusCode.Delete:
+            dele = np.where(d["state"] == StatusCode.Delete)[0]
+            if len(dele) > 0:
+                self.remove_indices(dele)
+                d = self._data
+        if rep["max_state"] >= StatusCode.Error:
+            for code in ERRORS_TO_THROW:
+                hit = d["state"] == code
+                if np.any(hit):
+                    raise_for_state(code, d["z"][hit], d["y"][hit], d["x"][hit], d["t"][hit])
 
     def execute(self, kernels, dt, endtime=None, runtime=None, output_file=None, verbose_progress=False):
         """reference _core/particleset.py:355-470 (outer loop) and :497-585 (argument handling)."""
