@@ -36,6 +36,7 @@ enum pb_field_slot { PB_FIELD_U = 0, PB_FIELD_V = 1, PB_FIELD_W = 2 };
 
 /* Advection scheme (kernels/_advection.py). */
 enum pb_scheme {
+    PB_ADVECTION_NONE = 0,    /* no advection kernel in the list (e.g. [DiffusionUniformKh] alone) */
     PB_ADVECTION_EE = 1,      /* :78-82   */
     PB_ADVECTION_RK2 = 2,     /* :20-27   */
     PB_ADVECTION_RK2_3D = 3,  /* :30-39   */

@@ -239,7 +239,7 @@ __global__ void __launch_bounds__(PB_BLOCK_THREADS, PB_MINBLOCKS) advect_kernel(
 
         const int sign = p.dt > 0 ? 1 : -1;
         constexpr bool three_d = (Policy::NC == 3);  // RK4_3D / RK2_3D sample fieldset.UVW, the others fieldset.UV
-        const int nstage = (p.scheme == PB_ADVECTION_EE) ? 1 : ((p.scheme == PB_ADVECTION_RK2 || p.scheme == PB_ADVECTION_RK2_3D) ? 2 : 4);
+        const int nstage = (p.scheme == PB_ADVECTION_NONE) ? 0 : (p.scheme == PB_ADVECTION_EE) ? 1 : ((p.scheme == PB_ADVECTION_RK2 || p.scheme == PB_ADVECTION_RK2_3D) ? 2 : 4);
 
         bool ei_zeroed = false;
         long long it = 0;
@@ -282,7 +282,8 @@ __global__ void __launch_bounds__(PB_BLOCK_THREADS, PB_MINBLOCKS) advect_kernel(
                     }
                 }
             } else {
-            Policy::template eval<float, float, float>(p, e, nohint1, t, z, y, x, u1, v1, w1);
+            u1 = Val{0.0, false}; v1 = u1; w1 = u1;
+            if (nstage > 0) Policy::template eval<float, float, float>(p, e, nohint1, t, z, y, x, u1, v1, w1);
             su = u1.v; sv = v1.v; sw = w1.v;
             uk = u1; vk = v1; wk = w1;
             for (int k = 1; k < nstage; ++k) {

@@ -609,7 +609,7 @@ int32_t pb_advect_async(pb_engine* e, const pb_advect_args* a) {
     if (a->dt == 0.0 || a->dt != a->dt) return fail(PB_ERR_INVALID, "dt must be a non-zero number");
     int nc;
     switch (a->scheme) {
-        case PB_ADVECTION_EE: case PB_ADVECTION_RK2: case PB_ADVECTION_RK4: nc = 2; break;
+        case PB_ADVECTION_NONE: case PB_ADVECTION_EE: case PB_ADVECTION_RK2: case PB_ADVECTION_RK4: nc = 2; break;
         case PB_ADVECTION_RK2_3D: case PB_ADVECTION_RK4_3D: nc = 3; break;
         default: return fail(PB_ERR_INVALID, "unknown scheme %d", a->scheme);
     }

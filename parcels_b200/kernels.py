@@ -62,5 +62,5 @@ def DeleteParticle(particles, fieldset):
 
 
 # scheme ids of include/parcels_b200.h (enum pb_scheme)
-SCHEMES = {"AdvectionEE": 1, "AdvectionRK2": 2, "AdvectionRK2_3D": 3, "AdvectionRK4": 4, "AdvectionRK4_3D": 5}
+SCHEMES = {"_none": 0, "AdvectionEE": 1, "AdvectionRK2": 2, "AdvectionRK2_3D": 3, "AdvectionRK4": 4, "AdvectionRK4_3D": 5}
 SCHEMES_3D = {"AdvectionRK2_3D", "AdvectionRK4_3D"}

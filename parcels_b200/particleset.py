@@ -53,6 +53,8 @@ class KernelPlan:
         if names and names[-1] == "DiffusionUniformKh":
             self.diffusion = True
             names = names[:-1]
+        if len(names) == 0 and self.diffusion:
+            names = ["_none"]
         if len(names) != 1 or names[0] not in K.SCHEMES:
             raise NotImplementedError(
                 f"kernel list {[f.__name__ for f in kernel_list]} is not lowered to the GPU engine: supported lists are "
