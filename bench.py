@@ -170,10 +170,7 @@ def run_decomposed_bench(a, rank, local_rank, world):
     f = c5_slab(rank, world, halo, **dims)
     fs = pb.FieldSet.from_arrays(lon=f["lon"][f["lo"] : f["hi"] + 1].copy(), lat=f["lat"], depth=f["depth"], time=f["times"],
                                  U=f["U"], V=f["V"], W=f["W"], mesh="spherical", xdim=f["lon"].size - 1)  # fmt: skip
-    dfs = D.DecomposedFieldSet.__new__(D.DecomposedFieldSet)
-    dfs.rank, dfs.world, dfs.device, dfs.plan, dfs.fs = rank, world, local_rank, f["plan"], fs
-    dfs.engine = fs.engine(local_rank)
-    dfs.engine.decomp_set(world, rank, f["plan"]["bounds"], f["plan"]["xi_offset"], f["plan"]["left_global"], f["plan"]["right_global"])
+    dfs = D.DecomposedFieldSet.from_slab(fs, f["plan"], rank=rank, world=world, device=local_rank)
     rng = np.random.default_rng(100 + rank)
     b = f["plan"]["bounds"]
     # every rank seeds particles uniformly over the GLOBAL domain: the first migration round routes them

@@ -116,6 +116,20 @@ int32_t pb_field_attach_device(pb_engine* e, int32_t slot, const void* dev_data,
                                int64_t T, int64_t Z, int64_t Y, int64_t X);
 int32_t pb_field_clear(pb_engine* e, int32_t slot);
 
+/* Time-slab streaming -- GPU analogue of the reference's WindowedArray (_core/_windowed_array.py:25-97,
+ * _core/model.py:79-113): keep only `window_levels` consecutive time levels of U, V, W in HBM.
+ * pb_field_window_create allocates window_levels + 1 ring slots per component (level L lives in slot
+ * L % (window_levels + 1)); pb_field_window_load copies ONE level (Z*Y*X values, host memory, ideally pinned)
+ * into its slot asynchronously on a copy stream -- also while pb_advect_async is running, as long as that
+ * level is outside the window in use; pb_field_window_set(first, n) declares levels [first, first+n) resident
+ * for the next advect calls (stream-ordered after the pending loads).  pb_advect stops a particle whose next
+ * step would sample outside the resident levels (pb_report.n_wait_window): slide the window and call
+ * pb_advect again with resume = 1. */
+int32_t pb_field_window_create(pb_engine* e, int32_t slot, int32_t data_is_f64, int64_t T_total, int64_t Z, int64_t Y,
+                               int64_t X, int32_t window_levels);
+int32_t pb_field_window_load(pb_engine* e, int32_t slot, int64_t level, const void* host_level_data);
+int32_t pb_field_window_set(pb_engine* e, int64_t first_level, int64_t n_levels);
+
 /* ---- particles: replaces the SoA dict of create_particle_data (_core/particle.py:182-222)
  * Host arrays are the pset._data ndarrays themselves (x,y,z,dx,dy,dz float32; t float64;
  * state int32; ei = LAST column of the (N, ngrids) int32 `ei` array, _core/field.py:279;
@@ -164,6 +178,9 @@ typedef struct pb_report {
     int64_t max_iters_done;    /* largest per-particle iteration count                          */
     int64_t cache_refills;     /* corner-cache refills (diagnostic: HBM gathers actually made)   */
     int64_t n_migrate;         /* mode D: particles that left the owned slab and wait for migration */
+    int64_t n_wait_window;     /* time-slab streaming: particles whose next step needs a non-resident level */
+    double wait_t_min;         /* smallest / largest time of those particles (valid when n_wait_window > 0) */
+    double wait_t_max;
     int32_t max_state;
     int32_t reserved;
     float kernel_ms;           /* CUDA-event time of the advection kernel on the engine stream   */

@@ -47,6 +47,9 @@ class Report(C.Structure):
         ("max_iters_done", C.c_int64),
         ("cache_refills", C.c_int64),
         ("n_migrate", C.c_int64),
+        ("n_wait_window", C.c_int64),
+        ("wait_t_min", C.c_double),
+        ("wait_t_max", C.c_double),
         ("max_state", C.c_int32),
         ("reserved", C.c_int32),
         ("kernel_ms", C.c_float),
@@ -79,6 +82,9 @@ SYMBOLS = {
     "pb_field_upload": (C.c_int32, [_P, C.c_int32, _P, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_int64]),
     "pb_field_attach_device": (C.c_int32, [_P, C.c_int32, _P, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_int64]),
     "pb_field_clear": (C.c_int32, [_P, C.c_int32]),
+    "pb_field_window_create": (C.c_int32, [_P, C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int32]),
+    "pb_field_window_load": (C.c_int32, [_P, C.c_int32, C.c_int64, _P]),
+    "pb_field_window_set": (C.c_int32, [_P, C.c_int64, C.c_int64]),
     "pb_particles_upload": (C.c_int32, [_P, C.c_int64] + [_P] * 10),
     "pb_particles_download": (C.c_int32, [_P, C.c_int64] + [_P] * 9),
     "pb_particles_snapshot": (C.c_int32, [_P]),

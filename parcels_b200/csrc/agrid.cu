@@ -33,7 +33,7 @@ struct Corners {
 
     __device__ __forceinline__ void fill(const FieldDev& f, int nti, int nzi, int nyi, int nxi) {
         ti = nti; zi = nzi; yi = nyi; xi = nxi;
-        long long ot[2] = {wrap_idx(nti, f.T) * f.sT, up_idx(nti, f.T) * f.sT};
+        long long ot[2] = {tslot(f, wrap_idx(nti, f.T)) * f.sT, tslot(f, up_idx(nti, f.T)) * f.sT};
         long long oz[2] = {wrap_idx(nzi, f.Z) * f.sZ, up_idx(nzi, f.Z) * f.sZ};
         long long oy[2] = {wrap_idx(nyi, f.Y) * f.sY, up_idx(nyi, f.Y) * f.sY};
         long long ox[2] = {wrap_idx(nxi, f.X) * f.sX, up_idx(nxi, f.X) * f.sX};

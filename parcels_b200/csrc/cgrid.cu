@@ -449,7 +449,7 @@ struct CGridPolicy {
         if (e.fti != ti || e.fzi != zi || e.fyi != yi || e.fxi != xi) {
             e.fti = ti; e.fzi = zi; e.fyi = yi; e.fxi = xi;
             e.refills++;
-            const long long ot[2] = {(long long)min(max(ti, 0), f.T - 1) * f.sT, up_idx(ti, f.T) * f.sT};
+            const long long ot[2] = {tslot(f, (long long)min(max(ti, 0), f.T - 1)) * f.sT, tslot(f, up_idx(ti, f.T)) * f.sT};
             const long long oz = (long long)min(max(zi, 0), f.Z - 1) * f.sZ;
             const long long oy0 = (long long)yi * f.sY, oy1 = up_idx(yi, f.Y) * f.sY;
             const long long oyo = (long long)min(max(yi + g.off_y, 0), f.Y - 1) * f.sY;

@@ -50,9 +50,15 @@ struct GridDev {
 
 struct FieldDev {
     const void* p[3];
-    int T, Z, Y, X;            // data shape (shared by all components on an A-grid)
+    int T, Z, Y, X;            // data shape (shared by all components on an A-grid); T = levels of the time axis
     long long sT, sZ, sY, sX;  // element strides; 0 for size-1 (never indexed) dims
+    // time-slab streaming (the GPU analogue of the reference's WindowedArray, _core/_windowed_array.py): the
+    // buffers hold `ring` time levels, level L lives in slot L % ring; ring == T when every level is resident
+    int ring;
+    int windowed;
+    double win_t0, win_t1;     // the resident levels cover sample times win_t0 <= t <= win_t1
 };
+__device__ __forceinline__ long long tslot(const FieldDev& f, long long level) { return f.windowed ? level % f.ring : level; }
 
 struct ReportDev {
     unsigned long long particle_steps;
@@ -63,6 +69,8 @@ struct ReportDev {
     long long max_iters_done;
     unsigned long long cache_refills;
     unsigned long long n_migrate;  // mode D: particles that left the owned slab and wait for migration
+    unsigned long long n_wait_window;  // time-slab streaming: particles whose next step needs a level not resident
+    unsigned long long wait_t_min_bits, wait_t_max_bits;  // IEEE bits of min / max t of those particles (t >= 0)
     int max_state;
     int pad_;
 };
@@ -222,7 +230,7 @@ __global__ void __launch_bounds__(PB_BLOCK_THREADS, PB_MINBLOCKS) advect_kernel(
     unsigned long long my_steps = 0, my_refills = 0;
     int final_state = 0;
     long long my_iters = 0;
-    bool errored = false, deleted = false, oot = false, migrate = false;
+    bool errored = false, deleted = false, oot = false, migrate = false, wait_window = false;
     long long err_iter = LLONG_MAX;
 
     if (i < p.P.n) {
@@ -253,6 +261,18 @@ __global__ void __launch_bounds__(PB_BLOCK_THREADS, PB_MINBLOCKS) advect_kernel(
             }
             // adapt dt to end exactly on endtime (:199-203)
             const double dtp = (sign == 1) ? fmax(fmin(p.dt, tte), 0.0) : fmin(fmax(p.dt, -tte), 0.0);
+            if (p.f.windowed) {  // every sample time of this step (t .. t+dt) must lie inside the resident time levels
+                const double ta = t, tb = t + dtp;
+                if (!(fmin(ta, tb) >= p.f.win_t0 && fmax(ta, tb) <= p.f.win_t1)) {
+                    // outside the field's whole time interval is the reference's OutsideTimeInterval, not a wait
+                    if (fmin(ta, tb) >= 0 && fmax(ta, tb) <= p.g.time_len) {
+                        wait_window = true;
+                        atomicMin(&p.rep->wait_t_min_bits, (unsigned long long)__double_as_longlong(t));  // rare: once per window slide
+                        atomicMax(&p.rep->wait_t_max_bits, (unsigned long long)__double_as_longlong(t));
+                        break;
+                    }
+                }
+            }
             my_steps++;
 
             // ---- advection kernel (kernels/_advection.py) ----
@@ -361,7 +381,7 @@ __global__ void __launch_bounds__(PB_BLOCK_THREADS, PB_MINBLOCKS) advect_kernel(
     // ---- report: warp-reduce then one atomic per warp ----
     const unsigned full = 0xffffffffu;
     unsigned long long s_steps = my_steps, s_ref = my_refills;
-    unsigned n_err = errored, n_del = deleted, n_oot = oot, n_mig = migrate;
+    unsigned n_err = errored, n_del = deleted, n_oot = oot, n_mig = migrate, n_ww = wait_window;
     long long mx_it = my_iters, mn_err = err_iter;
     int mx_state = final_state;
 #pragma unroll
@@ -372,6 +392,7 @@ __global__ void __launch_bounds__(PB_BLOCK_THREADS, PB_MINBLOCKS) advect_kernel(
         n_del += __shfl_xor_sync(full, n_del, o);
         n_oot += __shfl_xor_sync(full, n_oot, o);
         n_mig += __shfl_xor_sync(full, n_mig, o);
+        n_ww += __shfl_xor_sync(full, n_ww, o);
         mx_it = max(mx_it, __shfl_xor_sync(full, mx_it, o));
         mn_err = min(mn_err, __shfl_xor_sync(full, mn_err, o));
         mx_state = max(mx_state, __shfl_xor_sync(full, mx_state, o));
@@ -383,6 +404,7 @@ __global__ void __launch_bounds__(PB_BLOCK_THREADS, PB_MINBLOCKS) advect_kernel(
         if (n_del) atomicAdd(&p.rep->n_deleted, (unsigned long long)n_del);
         if (n_oot) atomicAdd(&p.rep->n_out_of_time, (unsigned long long)n_oot);
         if (n_mig) atomicAdd(&p.rep->n_migrate, (unsigned long long)n_mig);
+        if (n_ww) atomicAdd(&p.rep->n_wait_window, (unsigned long long)n_ww);
         if (mx_it) atomicMax(&p.rep->max_iters_done, mx_it);
         if (mn_err != LLONG_MAX) atomicMin(&p.rep->first_error_iter, mn_err);
         if (mx_state) atomicMax(&p.rep->max_state, mx_state);

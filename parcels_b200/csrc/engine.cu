@@ -177,6 +177,12 @@ struct pb_engine {
     const void* fptr[3] = {nullptr, nullptr, nullptr};
     int f_f64[3] = {0, 0, 0};
     long long fshape[3][4] = {};
+    // time-slab streaming: ring of (window + 1) levels per component, loads on a dedicated copy stream
+    int ring = 0;                    // 0: every level resident
+    long long win_first = 0, win_n = 0;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t copy_done = nullptr;
+    std::vector<double> time_host;   // seconds since the interval start
     // particles
     DevBuf px, py, pz, pdx, pdy, pdz, pt, pstate, pei, ppid;
     DevBuf snap;  // snapshot of all particle arrays
@@ -198,6 +204,7 @@ struct pb_engine {
 static void zero_report(ReportDev& r) {
     memset(&r, 0, sizeof(r));
     r.first_error_iter = LLONG_MAX;
+    r.wait_t_min_bits = ~0ULL;
 }
 
 extern "C" {
@@ -229,6 +236,8 @@ int32_t pb_engine_create(int32_t device, pb_engine** out) {
     CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&e->ev0));
     CK(cudaEventCreate(&e->ev1));
+    CK(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&e->copy_done, cudaEventDisableTiming));
     CK(cudaEventCreate(&e->tev0));
     CK(cudaEventCreate(&e->tev1));
     CK(cudaMalloc(&e->d_rep, sizeof(ReportDev)));
@@ -251,6 +260,8 @@ void pb_engine_destroy(pb_engine* e) {
     if (e->h_rep) cudaFreeHost(e->h_rep);
     cudaEventDestroy(e->ev0);
     cudaEventDestroy(e->ev1);
+    cudaStreamDestroy(e->copy_stream);
+    cudaEventDestroy(e->copy_done);
     cudaEventDestroy(e->tev0);
     cudaEventDestroy(e->tev1);
     cudaStreamDestroy(e->stream);
@@ -311,6 +322,7 @@ static int32_t upload_zt(pb_engine* e, const void* depth, int64_t nz, int32_t co
     g.spherical = spherical ? 1 : 0;
     g.deg2m = spherical ? deg2m : 1.0;
     g.time_len = nt ? tnorm[nt - 1] : 0.0;
+    e->time_host = tnorm;
     g.xdim = xdim_cells; g.ydim = ydim_cells; g.zdim = zdim_cells;
     e->coord_f64 = coord_is_f64 ? 1 : 0;
     e->have_grid = true;
@@ -494,8 +506,6 @@ int32_t pb_particles_download_ids(pb_engine* e, int64_t n, int64_t* particle_id)
     return PB_OK;
 }
 
-static const size_t kSnapOff[10] = {0, 4, 8, 12, 16, 20, 24, 32, 36, 40};  // per-particle byte offsets x..ei (t at 24)
-
 int32_t pb_particles_snapshot(pb_engine* e) {
     if (!e) return fail(PB_ERR_INVALID, "engine is NULL");
     CK(cudaSetDevice(e->device));
@@ -510,7 +520,6 @@ int32_t pb_particles_snapshot(pb_engine* e) {
         if (n) CK(cudaMemcpyAsync(s + off, c.src, n * c.es, cudaMemcpyDeviceToDevice, e->stream));
         off += n * c.es;
     }
-    (void)kSnapOff;
     return PB_OK;
 }
 
@@ -540,7 +549,16 @@ static void fill_field_desc(pb_engine* e, FieldDev& f) {
     f.sY = Y > 1 ? X : 0;
     f.sZ = Z > 1 ? X * Y : 0;
     f.sT = T > 1 ? X * Y * Z : 0;
+    f.ring = e->ring ? e->ring : (int)T;
+    f.windowed = e->ring ? 1 : 0;
+    f.win_t0 = 0.0; f.win_t1 = 0.0;
+    if (e->ring && e->win_n > 0 && !e->time_host.empty()) {
+        f.win_t0 = e->time_host[e->win_first];
+        f.win_t1 = e->time_host[e->win_first + e->win_n - 1];
+    }
 }
+
+
 
 // validation shared by pb_advect and pb_sample_velocity; nc = 2 (UV) or 3 (UVW)
 static int32_t check_fields(pb_engine* e, int nc) {
@@ -665,6 +683,12 @@ int32_t pb_last_report(pb_engine* e, pb_report* rep) {
         o.max_iters_done = r.max_iters_done;
         o.cache_refills = (int64_t)r.cache_refills;
         o.n_migrate = (int64_t)r.n_migrate;
+        o.n_wait_window = (int64_t)r.n_wait_window;
+        if (r.n_wait_window) {
+            long long lo = (long long)r.wait_t_min_bits, hi = (long long)r.wait_t_max_bits;
+            memcpy(&o.wait_t_min, &lo, 8);
+            memcpy(&o.wait_t_max, &hi, 8);
+        }
         o.max_state = r.max_state;
         float ms = 0.f;
         CK(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
@@ -824,6 +848,53 @@ int32_t pb_migrate_unpack(pb_engine* e, const void* recvbuf_dev, int64_t n_in) {
     for (int k = 0; k < 10; ++k) std::swap(*cur[k], *alt[k]);
     e->n = n_new;
     e->n_send = 0; e->n_keep = n_new;
+    return PB_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// time-slab streaming: GPU analogue of the reference's WindowedArray
+// (_core/_windowed_array.py:25-97, _core/model.py:79-113): only `window_levels` consecutive time levels of
+// U, V, W are resident; one extra ring slot receives the next level on a copy stream while the advection
+// kernel runs on the levels it needs.
+// ------------------------------------------------------------------------------------------------
+int32_t pb_field_window_create(pb_engine* e, int32_t slot, int32_t data_is_f64, int64_t T_total, int64_t Z, int64_t Y, int64_t X,
+                               int32_t window_levels) {
+    if (!e) return fail(PB_ERR_INVALID, "engine is NULL");
+    if (slot < 0 || slot > 2) return fail(PB_ERR_INVALID, "bad field slot %d", slot);
+    if (T_total < 2 || Z < 1 || Y < 1 || X < 1 || window_levels < 2) return fail(PB_ERR_INVALID, "a time window needs >= 2 levels of a time-varying field");
+    if (window_levels + 1 > T_total) return fail(PB_ERR_INVALID, "window (%d levels) + 1 prefetch slot exceeds the %lld levels of the field: upload it whole", window_levels, (long long)T_total);
+    if (e->ring && e->ring != window_levels + 1) return fail(PB_ERR_INVALID, "all components must use the same window");
+    CK(cudaSetDevice(e->device));
+    const size_t level_bytes = (size_t)Z * Y * X * (data_is_f64 ? 8 : 4);
+    int32_t rc = e->fbuf[slot].ensure(level_bytes * (size_t)(window_levels + 1));
+    if (rc) return rc;
+    e->ring = window_levels + 1;
+    e->win_first = 0; e->win_n = 0;
+    return set_field(e, slot, e->fbuf[slot].p, data_is_f64, T_total, Z, Y, X);
+}
+
+int32_t pb_field_window_load(pb_engine* e, int32_t slot, int64_t level, const void* host_level_data) {
+    if (!e || !host_level_data) return fail(PB_ERR_INVALID, "NULL argument");
+    if (slot < 0 || slot > 2 || !e->ring || !e->fptr[slot]) return fail(PB_ERR_STATE, "pb_field_window_create first");
+    if (level < 0 || level >= e->fshape[slot][0]) return fail(PB_ERR_INVALID, "time level %lld out of range", (long long)level);
+    CK(cudaSetDevice(e->device));
+    const size_t level_bytes = (size_t)e->fshape[slot][1] * e->fshape[slot][2] * e->fshape[slot][3] * (e->f_f64[slot] ? 8 : 4);
+    char* dst = (char*)e->fbuf[slot].p + (size_t)(level % e->ring) * level_bytes;
+    CK(cudaMemcpyAsync(dst, host_level_data, level_bytes, cudaMemcpyHostToDevice, e->copy_stream));
+    return PB_OK;
+}
+
+int32_t pb_field_window_set(pb_engine* e, int64_t first_level, int64_t n_levels) {
+    if (!e) return fail(PB_ERR_INVALID, "engine is NULL");
+    if (!e->ring) return fail(PB_ERR_STATE, "pb_field_window_create first");
+    if (first_level < 0 || n_levels < 2 || n_levels > e->ring || first_level + n_levels > e->fshape[0][0])
+        return fail(PB_ERR_INVALID, "bad window [%lld, +%lld)", (long long)first_level, (long long)n_levels);
+    CK(cudaSetDevice(e->device));
+    // the advection stream must not start before the pending level loads have landed
+    CK(cudaEventRecord(e->copy_done, e->copy_stream));
+    CK(cudaStreamWaitEvent(e->stream, e->copy_done, 0));
+    e->win_first = first_level; e->win_n = n_levels;
     return PB_OK;
 }
 

@@ -111,8 +111,20 @@ class DecomposedFieldSet:
                                        U=np.ascontiguousarray(np.asarray(U)[..., sl]), V=np.ascontiguousarray(np.asarray(V)[..., sl]),
                                        W=None if W is None else np.ascontiguousarray(np.asarray(W)[..., sl]), mesh=mesh,
                                        xdim=np.asarray(lon).size - 1)  # fmt: skip  (GLOBAL cell count: ei stays global)
-        self.engine = self.fs.engine(device)
-        self.engine.decomp_set(world, rank, self.plan["bounds"], self.plan["xi_offset"], self.plan["left_global"],
+        self._attach()
+
+    @classmethod
+    def from_slab(cls, fs, plan, *, rank, world, device):
+        """Wrap a FieldSet that already holds ONLY this rank's slab (built with the GLOBAL ``xdim``), e.g. when
+        every rank generates / reads just its own columns."""
+        self = cls.__new__(cls)
+        self.rank, self.world, self.device, self.plan, self.fs = rank, world, device, plan, fs
+        self._attach()
+        return self
+
+    def _attach(self):
+        self.engine = self.fs.engine(self.device)
+        self.engine.decomp_set(self.world, self.rank, self.plan["bounds"], self.plan["xi_offset"], self.plan["left_global"],
                                self.plan["right_global"])  # fmt: skip
 
 

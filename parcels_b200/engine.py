@@ -94,6 +94,19 @@ class Engine:
         T, Z, Y, X = data.shape
         check(self._lib.pb_field_upload(self._h, slot, ptr(data), int(data.dtype == np.float64), T, Z, Y, X))
 
+    def window_create(self, slot: int, dtype, shape, window_levels: int):
+        T, Z, Y, X = shape
+        check(self._lib.pb_field_window_create(self._h, slot, int(np.dtype(dtype) == np.float64), T, Z, Y, X, int(window_levels)))
+
+    def window_load(self, slot: int, level: int, level_data: np.ndarray):
+        level_data = np.ascontiguousarray(level_data)
+        # the copy is asynchronous for pinned memory: keep the last few host buffers alive until it has run
+        self._level_keepalive = (getattr(self, "_level_keepalive", []) + [level_data])[-16:]
+        check(self._lib.pb_field_window_load(self._h, slot, int(level), ptr(level_data)))
+
+    def window_set(self, first_level: int, n_levels: int):
+        check(self._lib.pb_field_window_set(self._h, int(first_level), int(n_levels)))
+
     def attach_field_device(self, slot: int, dev_ptr: int, is_f64: bool, shape, keepalive=None):
         T, Z, Y, X = shape
         check(self._lib.pb_field_attach_device(self._h, slot, C.c_void_p(dev_ptr), int(is_f64), T, Z, Y, X))

@@ -15,6 +15,19 @@ EARTH_RADIUS = 6366707.019493707  # reference _core/mesh.py:6
 __all__ = ["Field", "FieldSet", "VectorField", "XGrid"]
 
 
+def window_range(time_s, t, sign: int, window: int) -> tuple[int, int]:
+    """Time levels [first, first + n) to keep resident so that a particle at time ``t`` can step in direction
+    ``sign`` (reference analogue: the span a WindowedArray keeps, _core/_windowed_array.py:56-97)."""
+    T = len(time_s)
+    if sign > 0:
+        first = int(np.clip(np.searchsorted(time_s, t, side="right") - 1, 0, max(T - 2, 0)))
+    else:
+        last = int(np.clip(np.searchsorted(time_s, t, side="left"), 1, T - 1))
+        first = max(0, last - window + 1)
+    first = min(first, max(T - window, 0))
+    return first, min(window, T - first)
+
+
 def _to_seconds(time):
     """time axis -> (float64 seconds since the first level, origin) (reference index_search.py:88)."""
     if time is None:
@@ -124,7 +137,8 @@ class FieldSet:
     FieldSet of the reference package).  Time is float seconds or datetime64/timedelta64.
     """
 
-    def __init__(self, grid: XGrid, U, V, W=None, time=None, interp_method="linear", padding=("low", "low", "high")):
+    def __init__(self, grid: XGrid, U, V, W=None, time=None, interp_method="linear", padding=("low", "low", "high"),
+                 time_window=None):  # fmt: skip
         if interp_method not in ("linear", "cgrid_velocity"):
             raise NotImplementedError(
                 f"interp_method {interp_method!r}: XLinear_Velocity ('linear') and CGrid_Velocity ('cgrid_velocity') are on this engine"
@@ -132,6 +146,10 @@ class FieldSet:
         if grid.curvilinear and interp_method != "cgrid_velocity":
             raise NotImplementedError("curvilinear grids are supported with CGrid_Velocity only")
         self.interp_method = interp_method
+        # time-slab streaming: keep only `time_window` consecutive time levels in HBM (U/V/W may then be any
+        # array-like indexable by level: np.memmap, a lazy loader ...); None = every level resident
+        self.time_window = None if time_window is None else int(time_window)
+        self._win = {}
         # C-grid staggering offsets X, Y, Z: 1 for LOW SGRID padding (reference _xinterpolators.py:99-109)
         self.offsets = tuple(int(p == "low") for p in padding)
         self.grid = grid
@@ -143,8 +161,9 @@ class FieldSet:
         for name, arr in (("U", U), ("V", V), ("W", W)):
             if arr is None:
                 continue
-            arr = np.asarray(arr)
-            if arr.ndim != 4:
+            if self.time_window is None:
+                arr = np.asarray(arr)
+            if len(arr.shape) != 4:
                 raise ValueError(f"{name} must be laid out (T, Z, Y, X); got shape {arr.shape}")
             self.fields[name] = Field(name, arr, grid, self)
         self.U, self.V, self.W = self.fields["U"], self.fields["V"], self.fields.get("W")
@@ -162,9 +181,9 @@ class FieldSet:
 
     @classmethod
     def from_arrays(cls, *, lon, lat, U, V, W=None, depth=None, time=None, mesh="spherical", radius=None,
-                    interp_method="linear", padding=("low", "low", "high"), **kw):  # fmt: skip
+                    interp_method="linear", padding=("low", "low", "high"), time_window=None, **kw):  # fmt: skip
         return cls(XGrid(lon, lat, depth, mesh=mesh, radius=radius, **kw), U, V, W, time=time, interp_method=interp_method,
-                   padding=padding)  # fmt: skip
+                   padding=padding, time_window=time_window)  # fmt: skip
 
     # -- reference API surface used on this path -----------------------------------------------
     @property
@@ -210,9 +229,44 @@ class FieldSet:
             eng.set_interpolation(1 if self.interp_method == "cgrid_velocity" else 0, *self.offsets)
             for slot, name in enumerate(("U", "V", "W")):
                 if name in self.fields:
-                    eng.upload_field(slot, self.fields[name].data)
+                    d = self.fields[name].data
+                    if self.time_window is None:
+                        eng.upload_field(slot, d)
+                    else:
+                        eng.window_create(slot, d.dtype, d.shape, self.time_window)
+            self._win[device] = dict(first=0, n=0, resident=set())
             self._engines[device] = eng
         return eng
+
+    # -- time-slab streaming ---------------------------------------------------------------------------
+    def _load_level(self, eng, device, level):
+        w = self._win[device]
+        ring = self.time_window + 1
+        w["resident"] = {lv for lv in w["resident"] if lv % ring != level % ring}
+        for slot, name in enumerate(("U", "V", "W")):
+            if name in self.fields:
+                eng.window_load(slot, level, np.asarray(self.fields[name].data[level]))
+        w["resident"].add(level)
+
+    def slide_window(self, device, t, sign):
+        """Make the levels a particle at time ``t`` needs resident; returns True if the window moved."""
+        eng = self._engines[device]
+        w = self._win[device]
+        first, n = window_range(self._time_s, t, sign, self.time_window)
+        moved = (first, n) != (w["first"], w["n"])
+        for lv in range(first, first + n):
+            if lv not in w["resident"]:
+                self._load_level(eng, device, lv)
+        eng.window_set(first, n)
+        w["first"], w["n"] = first, n
+        return moved
+
+    def prefetch_next(self, device, sign):
+        """Start copying the level the next window will need into the spare ring slot (overlaps the kernel)."""
+        w = self._win[device]
+        nxt = w["first"] + w["n"] if sign > 0 else w["first"] - 1
+        if 0 <= nxt < len(self._time_s) and nxt not in w["resident"]:
+            self._load_level(self._engines[device], device, nxt)
 
     def release(self):
         for e in self._engines.values():

@@ -46,6 +46,9 @@ class KernelPlan:
             names.append(f.__name__)
         self.funcname = "".join(names)
         self.delete_on_error = False
+        if fieldset.time_window is not None and names[-1] != "DeleteParticle":
+            raise NotImplementedError("time-windowed FieldSets need the DeleteParticle handler: an error cannot be replayed "
+                                      "step-exactly once the window has moved on")  # fmt: skip
         if names[-1] == "DeleteParticle":
             self.delete_on_error = True
             names = names[:-1]
@@ -172,8 +175,11 @@ class ParticleSet:
                                  rng_call=self._rng_call, max_iters=max_iters, hint_all_zero=hint_all_zero)  # fmt: skip
 
         eng.upload_particles(d, ei_last)
-        rep = eng.advect(args())
-        if rep["n_error"] > 0:
+        if self.fieldset.time_window is not None:
+            rep = self._advect_windowed(eng, plan, d, dt, endtime, args)
+        else:
+            rep = eng.advect(args())
+        if rep["n_error"] > 0 and self.fieldset.time_window is None:
             # The reference stops the whole set at the END of the first loop iteration in which any
             # particle is in an error state (kernel.py:239-245).  Replay from the host copy up to and
             # including that iteration so every particle is left exactly where the reference leaves it.
@@ -201,6 +207,36 @@ class ParticleSet:
                 hit = d["state"] == code
                 if np.any(hit):
                     raise_for_state(code, d["z"][hit], d["y"][hit], d["x"][hit], d["t"][hit])
+
+    def _advect_windowed(self, eng, plan, d, dt, endtime, args):
+        """Time-slab streaming: advance until every particle reached ``endtime``, sliding the resident time
+        levels as the particles' clock crosses them; the next level is copied while the kernel runs."""
+        fs = self.fieldset
+        sign = 1 if dt > 0 else -1
+        todo = sign * (endtime - d["t"]) >= 0
+        t_ref = (d["t"][todo].min() if sign > 0 else d["t"][todo].max()) if todo.any() else float(d["t"][0])
+        fs.slide_window(self.device, t_ref, sign)
+        total = None
+        first = True
+        while True:
+            a = args()
+            a.resume = 0 if first else 1
+            eng.advect_async(a)
+            fs.prefetch_next(self.device, sign)  # H2D of the next level overlaps the kernel
+            rep = eng.last_report()
+            if total is None:
+                total = dict(rep)
+            else:
+                for k in ("particle_steps", "cache_refills", "kernel_ms"):
+                    total[k] += rep[k]
+                for k in ("n_error", "n_deleted", "max_state", "n_out_of_time", "first_error_iter", "n_wait_window"):
+                    total[k] = rep[k]
+            first = False
+            if rep["n_wait_window"] == 0:
+                return total
+            moved = fs.slide_window(self.device, rep["wait_t_min"] if sign > 0 else rep["wait_t_max"], sign)
+            if not moved:
+                raise RuntimeError(f"time window of {fs.time_window} levels cannot cover one step of dt={dt}: widen time_window")
 
     def execute(self, kernels, dt, endtime=None, runtime=None, output_file=None, verbose_progress=False):
         """reference _core/particleset.py:355-470 (outer loop) and :497-585 (argument handling)."""

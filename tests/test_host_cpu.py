@@ -38,7 +38,7 @@ def test_struct_layouts_match_header():
     import ctypes
 
     assert ctypes.sizeof(_lib.AdvectArgs) == 4 * 4 + 5 * 8 + 2 * 8 + 8 + 2 * 4
-    assert ctypes.sizeof(_lib.Report) == 8 * 8 + 2 * 4 + 2 * 4
+    assert ctypes.sizeof(_lib.Report) == 11 * 8 + 2 * 4 + 2 * 4
 
 
 def _fs(with_w=True):
@@ -144,3 +144,23 @@ def test_host_spatial_hash_equals_oracle_table():
         np.testing.assert_array_equal(h["counts"], o.counts)
         np.testing.assert_array_equal(h["faces"], o.faces)
         np.testing.assert_array_equal(h["box"], np.array([float(b) for b in o.box]))
+
+
+def test_window_range_policy():
+    """time-slab streaming: which levels must be resident for a particle at time t (host logic only)"""
+    from parcels_b200.fieldset import window_range
+
+    t = np.arange(6) * 100.0  # levels at 0, 100, ..., 500
+    assert window_range(t, 0.0, 1, 3) == (0, 3)
+    assert window_range(t, 100.0, 1, 3) == (1, 3)  # on a level: that level starts the window
+    assert window_range(t, 250.0, 1, 3) == (2, 3)
+    assert window_range(t, 450.0, 1, 3) == (3, 3)  # clipped so that 3 levels still fit
+    assert window_range(t, 500.0, 1, 2) == (4, 2)
+    assert window_range(t, 500.0, -1, 3) == (3, 3)
+    assert window_range(t, 250.0, -1, 3) == (1, 3)  # covers [100, 300]
+    assert window_range(t, 200.0, -1, 3) == (0, 3)
+    assert window_range(t, 50.0, -1, 3) == (0, 3)
+    for sign in (1, -1):  # the particle's own time is always inside the window
+        for tt in np.linspace(0, 500, 41):
+            f, n = window_range(t, tt, sign, 3)
+            assert t[f] <= tt <= t[f + n - 1] and n >= 2
