@@ -173,16 +173,18 @@ def run_decomposed_bench(a, rank, local_rank, world):
     dfs = D.DecomposedFieldSet.from_slab(fs, f["plan"], rank=rank, world=world, device=local_rank)
     rng = np.random.default_rng(100 + rank)
     b = f["plan"]["bounds"]
-    # every rank seeds particles uniformly over the GLOBAL domain: the first migration round routes them
+    # every rank seeds its particles inside its own slab (as a domain-decomposed application would); whatever
+    # leaves the slab during the pass migrates over NCCL
     n = n_per_gpu
-    x, y, z = rng.uniform(-170, 170, n), rng.uniform(-70, 70, n), rng.uniform(5, 5000, n)
+    x = rng.uniform(max(b[rank], -175.0), min(b[rank + 1], 175.0), n)
+    y, z = rng.uniform(-70, 70, n), rng.uniform(5, 5000, n)
     pid = np.arange(n, dtype=np.int64) + rank * n
     runtime = dt * nsteps
     kernels = [pb.AdvectionRK4_3D, pb.DeleteParticle]
     dev = f"cuda:{local_rank}"
 
     def one_pass():
-        pdata = create_particle_data(nparticles=n, ngrids=1, initial=dict(x=x, y=y, z=z, t=np.zeros(n), particle_id=pid))
+        pdata = create_particle_data(nparticles=n, ngrids=1, initial=dict(x=x, y=y, z=z, t=np.zeros(n), particle_id=pid))  # input batch
         torch.cuda.synchronize()
         dist.barrier()
         t0 = time.perf_counter()
@@ -216,7 +218,7 @@ def run_decomposed_bench(a, rank, local_rank, world):
         "data": "synthetic",
         "config": {"workload": f"{a.workload}: BASELINE.json configs[4] -- AdvectionRK4_3D, rectilinear {dims['nx']}x{dims['ny']}x{dims['nz']} "
                                f"T={dims['nt']} f32 field DOMAIN-DECOMPOSED into {world} X-slabs (+{halo} halo columns), {n_per_gpu} "
-                               f"particles/GPU seeded over the whole domain, NCCL all-to-all-v migration; dt={dt:g} s x {nsteps} steps",
+                               f"particles/GPU seeded in the rank's own slab, NCCL all-to-all-v migration; dt={dt:g} s x {nsteps} steps",
                    "timed_region": "upload of the particle shard + initial routing + advect kernels + migration rounds + download "
                                    "(wall clock between barriers, max over ranks)",
                    "migrations_per_pass": tot_mig / a.steps, "advect_rounds_per_pass": rounds,

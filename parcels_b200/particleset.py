@@ -95,6 +95,7 @@ class ParticleSet:
         self.device = device
         self.seed = int(seed)  # Philox key of the Wiener increments (DiffusionUniformKh)
         self._rng_call = 0
+        self._device_synced = False
         self.last_report = None
         y = np.empty(0) if y is None else np.array(y).flatten()
         x = np.empty(0) if x is None else np.array(x).flatten()
@@ -147,8 +148,12 @@ class ParticleSet:
             self._data[k] = np.delete(self._data[k], indices, axis=0)
 
     # -- the hot path ------------------------------------------------------------------------------
-    def _kernel_execute(self, plan: KernelPlan, endtime: float, dt: float):
-        """Replaces ``Kernel.execute(pset, endtime, dt)`` (reference _core/kernel.py:174-247)."""
+    def _kernel_execute(self, plan: KernelPlan, endtime: float, dt: float, *, resident: bool = False):
+        """Replaces ``Kernel.execute(pset, endtime, dt)`` (reference _core/kernel.py:174-247).
+
+        ``resident=True`` (set by ``execute`` for the 2nd, 3rd, ... output interval of ONE call): the device
+        copy of the particle SoA left by the previous interval is still exact -- nothing on the host can have
+        changed it in between -- so the host->device upload is skipped."""
         d = self._data
         n = len(self)
         d["state"][:] = StatusCode.Evaluate
@@ -174,7 +179,9 @@ class ParticleSet:
                                  kh=plan.kh, kh_spherical=plan.kh_spherical, kh_deg2m=plan.kh_deg2m, seed=self.seed,
                                  rng_call=self._rng_call, max_iters=max_iters, hint_all_zero=hint_all_zero)  # fmt: skip
 
-        eng.upload_particles(d, ei_last)
+        if not (resident and self._device_synced and eng.particle_count() == n):
+            eng.upload_particles(d, ei_last)
+        self._device_synced = False
         if self.fieldset.time_window is not None:
             rep = self._advect_windowed(eng, plan, d, dt, endtime, args)
         else:
@@ -197,11 +204,13 @@ class ParticleSet:
         d["dt"][:] = dt  # kernel.py:225-226
         # the device report says whether any particle was deleted / errored: the O(N) host scans of
         # kernel.py:98-106,239-245 only run when there is something to find
+        self._device_synced = True  # host arrays == device arrays from here on (until the host compacts them)
         if rep["n_deleted"] > 0 or rep["max_state"] == StatusCode.Delete:
             dele = np.where(d["state"] == StatusCode.Delete)[0]
             if len(dele) > 0:
                 self.remove_indices(dele)
                 d = self._data
+                self._device_synced = False
         if rep["max_state"] >= StatusCode.Error:
             for code in ERRORS_TO_THROW:
                 hit = d["state"] == code
@@ -283,12 +292,15 @@ class ParticleSet:
             output_file.write(self, start_time)
             next_output = start_time + outputdt * sign_dt
         time = start_time
+        interval = 0
+        self._device_synced = False  # between execute() calls the host owns the arrays
         while sign_dt * (time - end_time) < 0:
             if next_output is not None:
                 next_time = min(next_output, end_time) if sign_dt > 0 else max(next_output, end_time)
             else:
                 next_time = end_time
-            self._kernel_execute(plan, next_time, dt)
+            self._kernel_execute(plan, next_time, dt, resident=interval > 0)
+            interval += 1
             if next_output is not None and np.abs(next_time - next_output) < 0.001:
                 output_file.write(self, next_output)
                 if np.isfinite(outputdt):
