@@ -124,7 +124,8 @@ int32_t pb_field_clear(pb_engine* e, int32_t slot);
  * level is outside the window in use; pb_field_window_set(first, n) declares levels [first, first+n) resident
  * for the next advect calls (stream-ordered after the pending loads).  pb_advect stops a particle whose next
  * step would sample outside the resident levels (pb_report.n_wait_window): slide the window and call
- * pb_advect again with resume = 1. */
+ * pb_advect again with resume = 1.  A step that straddles a time level samples 3 levels, so window_levels = 3 is
+ * the general minimum (2 suffices only when no step straddles a level). */
 int32_t pb_field_window_create(pb_engine* e, int32_t slot, int32_t data_is_f64, int64_t T_total, int64_t Z, int64_t Y,
                                int64_t X, int32_t window_levels);
 int32_t pb_field_window_load(pb_engine* e, int32_t slot, int64_t level, const void* host_level_data);

@@ -35,12 +35,17 @@ def _run(f, window, dt, segments, t0, n=4000, seed=3):
 def test_windowed_equals_resident(window, mode):
     f = _field()
     tend = float(f["times"][-1])
-    if mode == "forward":
+    # window == 2 can only serve steps that never straddle a time level (a straddling step samples 3 levels):
+    # those cases keep every step aligned with the hourly levels; window == 3 also gets unaligned segments
+    if mode == "forward" and window == 2:
+        dt, segs, t0 = 600.0, [dict(runtime=2 * 3600.0), dict(runtime=3 * 3600.0 + 300.0)], lambda n, r: np.zeros(n)
+    elif mode == "forward":
         dt, segs, t0 = 600.0, [dict(runtime=0.4 * tend), dict(runtime=0.55 * tend)], lambda n, r: np.zeros(n)
     elif mode == "backward":
         dt, segs, t0 = -600.0, [dict(runtime=0.9 * tend)], lambda n, r: np.full(n, tend)
     else:
-        dt, segs, t0 = 900.0, [dict(endtime=0.8 * tend)], lambda n, r: np.round(r.uniform(0, 0.5 * tend, n) / 300) * 300
+        q = 900 if window == 2 else 300
+        dt, segs, t0 = 900.0, [dict(endtime=0.8 * tend)], lambda n, r: np.round(r.uniform(0, 0.5 * tend, n) / q) * q
     ref = _run(f, None, dt, segs, t0)
     win = _run(f, window, dt, segs, t0)
     assert win.last_report["particle_steps"] > 0
