@@ -346,6 +346,23 @@ def _oracle_pass(w, field, parts):
     return steps, time.perf_counter() - t0
 
 
+def _c_port_pass(w, field, parts):
+    """strong CPU baseline: the C + OpenMP restatement (oracle/advect_rk4_3d.c) on all host cores"""
+    from oracle import c_port
+    from oracle import parcels_oracle as po
+
+    pd = po.create_particle_data(parts["x"], parts["y"], parts["z"], parts["t"])
+    g = po.OGrid(field["lon"], field["lat"], field["depth"], mesh=field["mesh"])
+    c_port.advect_rk4_3d(lon=field["lon"], lat=field["lat"], depth=field["depth"], time=field["times"], U=field["U"], V=field["V"],
+                         W=field["W"], spherical=g.spherical, deg2m=g.deg2m, pdata=dict(pd), dt=w["dt"], endtime=w["dt"])  # warm-up: 1 step
+    pd = po.create_particle_data(parts["x"], parts["y"], parts["z"], parts["t"])
+    t0 = time.perf_counter()
+    steps = c_port.advect_rk4_3d(lon=field["lon"], lat=field["lat"], depth=field["depth"], time=field["times"], U=field["U"],
+                                 V=field["V"], W=field["W"], spherical=g.spherical, deg2m=g.deg2m, pdata=pd, dt=w["dt"],
+                                 endtime=w["dt"] * w["nsteps"])  # fmt: skip
+    return steps, time.perf_counter() - t0
+
+
 def _worker(args):
     seed, n = args
     w, field = _G["w"], _G["field"]
@@ -560,6 +577,13 @@ def main():
         line["cpu_baseline"] = {"value": s / t, "unit": "particle-steps/s", "cores": 1, "kind": "port",
                                 "sample": f"{a.cpu_sample} particles of the same workload, {nsteps} dt-steps, NumPy oracle port of "
                                           f"the reference path ({t:.1f} s)"}  # fmt: skip
+        if w["kernels"] == ["AdvectionRK4_3D"] and field.get("interp", "linear") == "linear":
+            cores = len(os.sched_getaffinity(0))
+            big = w["particles"](field, min(n_per_gpu, 400_000), 1)
+            s2, t2 = _c_port_pass(w, field, big)
+            line["cpu_baseline_strong"] = {"value": s2 / t2, "unit": "particle-steps/s", "cores": cores, "kind": "port",
+                                           "sample": f"{len(big['x'])} particles, {nsteps} dt-steps, C + OpenMP restatement "
+                                                     f"(oracle/advect_rk4_3d.c, same arithmetic, all host cores; {t2:.1f} s)"}  # fmt: skip
     print(json.dumps(line))
 
 
