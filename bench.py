@@ -375,15 +375,21 @@ def run_reference_arm(a, w, field):
     import multiprocessing as mp
 
     cores = len(os.sched_getaffinity(0))
-    per = a.ref_particles_per_core
     _G["w"], _G["field"] = w, field
     _oracle_fieldset(w, field)  # incl. the spatial hash: built once, before forking
     ctx = mp.get_context("fork")
     with ctx.Pool(cores) as pool:
-        def one_pass(k):
+        def one_pass(k, per_=None):
             t0 = time.perf_counter()
-            steps = sum(pool.map(_worker, [(1000 * k + c, per) for c in range(cores)]))
+            steps = sum(pool.map(_worker, [(1000 * k + c, per_ or per) for c in range(cores)]))
             return steps, time.perf_counter() - t0
+
+        # size the per-step sample so that one bench step takes ~a.ref_step_seconds on THIS box (the whole
+        # --steps K --warmup W run must end within a few minutes): calibrate on a small pass first
+        per = a.ref_particles_per_core
+        if per <= 0:
+            s0, t0_ = one_pass(-1, 200)
+            per = int(np.clip(a.ref_step_seconds * (s0 / t0_) / (cores * w["nsteps"]), 50, 20000))
 
         for k in range(a.warmup):
             one_pass(k)
@@ -416,7 +422,8 @@ def main():
     ap.add_argument("--workload", default="c2", choices=list(WORKLOADS) + ["c5", "c5_small"])
     ap.add_argument("--particles", type=int, default=None, help="particles per GPU (default: the workload's)")
     ap.add_argument("--cpu-sample", type=int, default=20000, help="particles of the cpu_baseline sample")
-    ap.add_argument("--ref-particles-per-core", type=int, default=4000)
+    ap.add_argument("--ref-particles-per-core", type=int, default=0, help="0: calibrate to --ref-step-seconds per bench step")
+    ap.add_argument("--ref-step-seconds", type=float, default=5.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     a = ap.parse_args()
