@@ -388,7 +388,7 @@ def run_reference_arm(a, w, field):
         # --steps K --warmup W run must end within a few minutes): calibrate on a small pass first
         per = a.ref_particles_per_core
         if per <= 0:
-            s0, t0_ = one_pass(-1, 200)
+            s0, t0_ = one_pass(999, 200)
             per = int(np.clip(a.ref_step_seconds * (s0 / t0_) / (cores * w["nsteps"]), 50, 20000))
 
         for k in range(a.warmup):
