@@ -168,6 +168,11 @@ typedef struct pb_advect_args {
                                   the whole batch at the first eval (_core/index_search.py:269-282)   */
     int32_t resume;            /* 1: continue the same Kernel.execute call after a migration round
                                   (mode D): particle states are NOT reset to Evaluate            */
+    int32_t kernels_only;      /* 1: run the kernel functions of ONE loop iteration on the evaluated particles
+                                  and return (dx/dy/dz accumulated, state/ei updated) WITHOUT the position
+                                  update, EndofLoop and delete bookkeeping -- the host finishes the iteration
+                                  (used when the kernel list also holds user Python kernels)              */
+    int32_t reserved;
 } pb_advect_args;
 
 typedef struct pb_report {

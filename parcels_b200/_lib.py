@@ -34,6 +34,8 @@ class AdvectArgs(C.Structure):
         ("max_iters", C.c_int64),
         ("hint_all_zero", C.c_int32),
         ("resume", C.c_int32),
+        ("kernels_only", C.c_int32),
+        ("reserved", C.c_int32),
     ]
 
 

@@ -95,6 +95,8 @@ struct AdvectParams {
     int hint_all_zero;  // curvilinear: every hinted xi of the evaluated view is 0 => the reference skips
                         // the hint for the whole batch at the first eval (index_search.py:269-282)
     int resume;         // 1: continue a Kernel.execute call after a migration (states are NOT reset to Evaluate)
+    int kernels_only;   // 1: one iteration's kernel functions only; the host does the position update etc.
+    int pad_;
     ReportDev* rep;
 };
 
@@ -352,6 +354,7 @@ __global__ void __launch_bounds__(PB_BLOCK_THREADS, PB_MINBLOCKS) advect_kernel(
                 dy = (float)((double)dy + by * dWy);
                 ei_zeroed = true;  // the constant-field evals overwrite ei[:, -1] with cell 0 (model.py:292-318)
             }
+            if (p.kernels_only) { ++it; break; }  // dx/dy/dz, state, ei are written back below; the host finishes the iteration
             // ---- trailing error handler: every error state becomes Delete ----
             if (p.delete_on_error && e.state >= 50) e.state = PB_DELETE;
 

@@ -650,6 +650,7 @@ int32_t pb_advect_async(pb_engine* e, const pb_advect_args* a) {
     p.seed = a->seed; p.rng_call = a->rng_call; p.max_iters = a->max_iters;
     p.hint_all_zero = a->hint_all_zero;
     p.resume = a->resume;
+    p.kernels_only = a->kernels_only;
     p.g.off_x = e->g.off_x; p.g.off_y = e->g.off_y; p.g.off_z = e->g.off_z;
     p.rep = e->d_rep;
 

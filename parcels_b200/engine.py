@@ -157,10 +157,10 @@ class Engine:
     # -- hot path --------------------------------------------------------------------------------
     @staticmethod
     def make_args(scheme, dt, endtime, *, diffusion=False, delete_on_error=False, kh=(0.0, 0.0), kh_spherical=False,
-                  kh_deg2m=1.0, seed=0, rng_call=0, max_iters=-1, hint_all_zero=False, resume=False) -> AdvectArgs:  # fmt: skip
+                  kh_deg2m=1.0, seed=0, rng_call=0, max_iters=-1, hint_all_zero=False, resume=False, kernels_only=False) -> AdvectArgs:  # fmt: skip
         return AdvectArgs(int(scheme), int(diffusion), int(delete_on_error), int(kh_spherical), float(dt), float(endtime),
                           float(kh[0]), float(kh[1]), float(kh_deg2m), int(seed), int(rng_call), int(max_iters),
-                          int(bool(hint_all_zero)), int(bool(resume)))  # fmt: skip
+                          int(bool(hint_all_zero)), int(bool(resume)), int(bool(kernels_only)), 0)  # fmt: skip
 
     def advect(self, args: AdvectArgs) -> dict:
         rep = Report()

@@ -102,17 +102,41 @@ class VectorField:
         self.grid = U.grid
         self.vector_type = "3D" if W is not None else "2D"
 
-    def eval(self, t, z, y, x, particles=None, *, device=0, positions_are_f32=False):
-        """``fieldset.UV.eval(t, z, y, x)`` (reference _core/field.py:250-295), evaluated ON THE DEVICE
-        (``pb_sample_velocity``).  Returns (u, v) or (u, v, w) float64 arrays; out-of-bounds samples are 0."""
+    def eval(self, t, z, y, x, particles=None, *, device=None, positions_are_f32=None):
+        """``fieldset.UV.eval(t, z, y, x[, particles])`` (reference _core/field.py:250-295), evaluated ON THE DEVICE
+        (``pb_sample_velocity``).  Returns (u, v) or (u, v, w) float64 arrays; out-of-bounds samples are 0.  With
+        ``particles`` (a ParticleSet or the ParticleSetView a user kernel received) the search is hinted by, and
+        writes back, ``particles.ei[:, -1]`` and raises ``particles.state`` exactly like the reference does."""
         fs = self.U._fieldset
-        u, v, w, _ei, _st = fs.engine(device).sample_velocity(t, z, y, x, three_d=self.W is not None,
-                                                              positions_are_f32=positions_are_f32)  # fmt: skip
-        shape = np.shape(np.atleast_1d(x))
-        out = (u.reshape(shape), v.reshape(shape)) + ((w.reshape(shape),) if self.W is not None else ())
-        return out
+        if device is None:
+            device = next(iter(fs._engines), 0)
+        z, y, x = (np.atleast_1d(a.__array__() if hasattr(a, "__array__") else a) for a in (z, y, x))
+        t = np.atleast_1d(t.__array__() if hasattr(t, "__array__") else t)
+        if positions_are_f32 is None:
+            positions_are_f32 = all(a.dtype == np.float32 for a in (z, y, x))
+        hint = None
+        if particles is not None:
+            hint = np.ascontiguousarray(np.asarray(particles.ei)[:, -1])
+        u, v, w, ei, st = fs.engine(device).sample_velocity(t, z, y, x, three_d=self.W is not None,
+                                                            positions_are_f32=positions_are_f32, ei_hint=hint)  # fmt: skip
+        if particles is not None:
+            from .statuscodes import StatusCode
+
+            particles.ei[:, -1] = ei
+            state = np.asarray(particles.state)
+            if np.any(st == StatusCode.ErrorOutsideTimeInterval):  # whole view flagged, zeros returned (field.py:31-44)
+                particles.state = StatusCode.ErrorOutsideTimeInterval
+                u[:] = 0
+                v[:] = 0
+                w[:] = 0
+            else:
+                particles.state = np.where(st >= StatusCode.Error, np.maximum(state, st), state)
+        shape = np.shape(x)
+        return (u.reshape(shape), v.reshape(shape)) + ((w.reshape(shape),) if self.W is not None else ())
 
     def __getitem__(self, key):
+        if hasattr(key, "_data") and not isinstance(key, tuple):  # a ParticleSet / ParticleSetView
+            return self.eval(key.t, key.z, key.y, key.x, key)
         return self.eval(*key)
 
 

@@ -29,6 +29,17 @@ def _to_float_seconds(v):
     return float(v)
 
 
+def _is_token(f):
+    """one of this package's device-kernel tokens (kernels.py), not a user function that happens to share the name"""
+    return getattr(K, f.__name__, None) is f
+
+
+def _delete_on_error(particles, fieldset):
+    """DeleteParticle token inside a stepwise list (reference idiom tests/common_kernels.py:12-13)."""
+    s = np.asarray(particles.state)
+    particles.state = np.where(s >= 50, StatusCode.Delete, s)
+
+
 class KernelPlan:
     """The kernel list lowered to the fused device kernel's switches (include/parcels_b200.h)."""
 
@@ -58,20 +69,40 @@ class KernelPlan:
             names = names[:-1]
         if len(names) == 0 and self.diffusion:
             names = ["_none"]
-        if len(names) != 1 or names[0] not in K.SCHEMES:
-            raise NotImplementedError(
-                f"kernel list {[f.__name__ for f in kernel_list]} is not lowered to the GPU engine: supported lists are "
-                "[Advection{EE,RK2,RK2_3D,RK4,RK4_3D}] (+ DiffusionUniformKh) (+ DeleteParticle). "
-                "parcels_b200 has no CPU fallback for user kernels."
-            )
-        self.scheme_name = names[0]
-        self.scheme = K.SCHEMES[names[0]]
-        if names[0] in K.SCHEMES_3D and fieldset.W is None:
-            raise AttributeError("FieldSet has no UVW VectorField (no W field) for a 3-D advection kernel")
+        builtin = set(K.SCHEMES) | {"DiffusionUniformKh", "DeleteParticle"}
+        self.stepwise = not (len(names) == 1 and names[0] in K.SCHEMES)
+        if self.stepwise:
+            # the list mixes built-ins with user Python kernels: the loop control runs on the host step by step
+            # (stepwise.py), every built-in kernel still runs on the device
+            if fieldset.time_window is not None:
+                raise NotImplementedError("user Python kernels are not supported on time-windowed FieldSets yet")
+            self.delete_on_error = self.diffusion = False
+            self.items = []
+            for f in kernel_list:
+                n = f.__name__
+                if n in K.SCHEMES and f.__module__ == K.__name__ or (n in K.SCHEMES and n != "_none" and n.startswith("Advection") and _is_token(f)):
+                    if n in K.SCHEMES_3D and fieldset.W is None:
+                        raise AttributeError("FieldSet has no UVW VectorField (no W field) for a 3-D advection kernel")
+                    self.items.append(["device", K.SCHEMES[n], False, self])
+                elif n == "DiffusionUniformKh" and _is_token(f):
+                    if self.items and self.items[-1][0] == "device" and not self.items[-1][2]:
+                        self.items[-1][2] = True  # fused with the advection kernel right before it
+                    else:
+                        self.items.append(["device", K.SCHEMES["_none"], True, self])
+                elif n == "DeleteParticle" and _is_token(f):
+                    self.items.append(["python", _delete_on_error])
+                else:
+                    self.items.append(["python", f])
+            self.scheme_name, self.scheme = "stepwise", -1
+        else:
+            self.scheme_name = names[0]
+            self.scheme = K.SCHEMES[names[0]]
+            if names[0] in K.SCHEMES_3D and fieldset.W is None:
+                raise AttributeError("FieldSet has no UVW VectorField (no W field) for a 3-D advection kernel")
         self.kh = (0.0, 0.0)
         self.kh_spherical = False
         self.kh_deg2m = 1.0
-        if self.diffusion:
+        if self.diffusion or (self.stepwise and any(i[0] == "device" and i[2] for i in self.items)):
             try:
                 self.kh = (fieldset.constants["Kh_zonal"], fieldset.constants["Kh_meridional"])
             except KeyError as e:
@@ -156,6 +187,13 @@ class ParticleSet:
         changed it in between -- so the host->device upload is skipped."""
         d = self._data
         n = len(self)
+        if plan.stepwise:
+            from .stepwise import kernel_execute_stepwise
+
+            if n and np.isnan(d["t"]).any():
+                raise ValueError("Time values cannot be NaN.")
+            self._device_synced = False
+            return kernel_execute_stepwise(self, plan, endtime, dt)
         d["state"][:] = StatusCode.Evaluate
         if n == 0:
             return

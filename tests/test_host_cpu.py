@@ -37,7 +37,7 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layouts_match_header():
     import ctypes
 
-    assert ctypes.sizeof(_lib.AdvectArgs) == 4 * 4 + 5 * 8 + 2 * 8 + 8 + 2 * 4
+    assert ctypes.sizeof(_lib.AdvectArgs) == 4 * 4 + 5 * 8 + 2 * 8 + 8 + 4 * 4
     assert ctypes.sizeof(_lib.Report) == 11 * 8 + 2 * 4 + 2 * 4
 
 
@@ -58,18 +58,47 @@ def test_kernel_plan_lowering():
     assert len(fs.gridset) == 2  # constant fields live on their own grid => ei has 2 columns
 
 
-def test_kernel_plan_rejects_user_kernels_loudly():
+def test_kernel_plan_mixed_lists_keep_builtins_on_the_device():
     def MyKernel(particles, fieldset):
         pass
 
-    with pytest.raises(NotImplementedError, match="no CPU fallback"):
-        KernelPlan([pb.AdvectionRK4, MyKernel], _fs())
+    def DeleteParticle(particles, fieldset):  # a USER function that merely shares the token's name
+        pass
+
+    fs = _fs()
+    fs.add_constant_field("Kh_zonal", 1.0, mesh="flat")
+    fs.add_constant_field("Kh_meridional", 1.0, mesh="flat")
+    p = KernelPlan([pb.AdvectionRK4, pb.DiffusionUniformKh, MyKernel, DeleteParticle], fs)
+    assert p.stepwise and [i[0] for i in p.items] == ["device", "python", "python"]
+    assert p.items[0][1:3] == [4, True]  # AdvectionRK4 fused with DiffusionUniformKh in one device call
+    assert p.items[2][1] is DeleteParticle
+    assert not KernelPlan([pb.AdvectionRK4, pb.DeleteParticle], fs).stepwise  # built-ins only: one fused launch
     with pytest.raises(TypeError):
         KernelPlan([1], _fs())
     with pytest.raises(ValueError):
         KernelPlan([], _fs())
     with pytest.raises(AttributeError):
         KernelPlan([pb.AdvectionRK4_3D], _fs(with_w=False))
+
+
+def test_particlesetview_write_through_semantics():
+    """reference _core/particlesetview.py: reads are masked copies, in-place ops / assignments write through"""
+    from parcels_b200.particlesetview import ParticleSetView
+
+    d = {"x": np.arange(5, dtype=np.float32), "state": np.array([10, 60, 10, 51, 10], np.int32), "ei": np.zeros((5, 1), np.int32),
+         "dt": np.full(5, 2.0)}  # fmt: skip
+    v = ParticleSetView(d, np.array([True, True, False, True, True]))
+    v.x += 10
+    np.testing.assert_array_equal(d["x"], [10, 11, 2, 13, 14])
+    v[v.state >= 50].state = 30
+    np.testing.assert_array_equal(d["state"], [10, 30, 10, 30, 10])
+    assert (v.x + v.x * 0.5 * v.dt).dtype == np.float64 and len(v.x) == 4 and v.x.max() == 14
+    v.ei[:, -1] = 7
+    np.testing.assert_array_equal(d["ei"].ravel(), [7, 7, 0, 7, 7])
+    v.x = v.x - 1
+    np.testing.assert_array_equal(d["x"], [9, 10, 2, 12, 13])
+    v[1:3].x = 0  # integer/slice indices are relative to the view
+    np.testing.assert_array_equal(d["x"], [9, 0, 2, 0, 13])
 
 
 def test_builtin_kernels_have_no_cpu_body():
