@@ -16,7 +16,7 @@ from .kernels import (
     DeleteParticle,
     DiffusionUniformKh,
 )
-from .particle import Particle
+from .particle import Particle, ParticleClass, Variable
 from .particleset import ParticleSet
 from .statuscodes import (
     FieldInterpolationError,
@@ -31,6 +31,6 @@ from .statuscodes import (
 __all__ = [
     "AdvectionEE", "AdvectionRK2", "AdvectionRK2_3D", "AdvectionRK4", "AdvectionRK4_3D", "DeleteParticle",
     "DiffusionUniformKh", "Field", "FieldInterpolationError", "FieldOutOfBoundError", "FieldOutOfBoundSurfaceError",
-    "FieldSet", "GeneralError", "GridSearchingError", "OutsideTimeInterval", "Particle", "ParticleSet", "StatusCode",
+    "FieldSet", "GeneralError", "GridSearchingError", "OutsideTimeInterval", "Particle", "ParticleClass", "ParticleSet", "Variable", "StatusCode",
     "VectorField", "XGrid", "kernels",
 ]  # fmt: skip

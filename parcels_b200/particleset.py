@@ -14,7 +14,7 @@ import types
 import numpy as np
 
 from . import kernels as K
-from .particle import Particle, create_particle_data
+from .particle import Particle, ParticleClass, create_particle_data
 from .statuscodes import ERRORS_TO_THROW, StatusCode, raise_for_state
 
 __all__ = ["ParticleSet"]
@@ -118,9 +118,9 @@ class ParticleSet:
     float seconds, timedelta64 or (with a datetime time axis) datetime64."""
 
     def __init__(self, fieldset, pclass=Particle, *, t=None, z=None, y=None, x=None, particle_ids=None, device=0,
-                 seed=0):  # fmt: skip
-        if pclass is not Particle:
-            raise NotImplementedError("only the default Particle (float32 positions) is supported on the engine")
+                 seed=0, **kwargs):  # fmt: skip
+        if not isinstance(pclass, ParticleClass):
+            raise NotImplementedError("pclass must be parcels_b200.Particle or Particle.add_variable(...) (float32 positions)")
         self.fieldset = fieldset
         self._pclass = pclass
         self.device = device
@@ -157,7 +157,12 @@ class ParticleSet:
             nparticles=x.size,
             ngrids=len(fieldset.gridset),
             initial=dict(t=t, z=z, y=y, x=x, particle_id=np.asarray(particle_ids)),
+            pclass=pclass,
         )
+        for k, v in kwargs.items():  # initial values of extra variables (reference particleset.py:129-134)
+            if k not in self._data:
+                raise RuntimeError(f"Particle class does not have Variable {k}")
+            self._data[k][:] = np.array(v).flatten()
 
     # -- container protocol ----------------------------------------------------------------------
     def __len__(self):

@@ -75,3 +75,38 @@ def test_user_kernel_can_sample_the_velocity_field():
     np.testing.assert_array_equal(seen["ei"], pd["ei"][:, -1])
     np.testing.assert_array_equal(seen["state"], pd["state"])
     np.testing.assert_allclose(seen["u"], ou, rtol=1e-6, atol=1e-12)
+
+
+@pytest.mark.parametrize("interp", ["linear", "cgrid_velocity"])
+def test_v3_regression_written_like_the_reference_test(golden_dir, interp):
+    """reference tests/test_interpolation.py:297-378 transcribed line by line onto this package's API: custom
+    particle class with a `pid` variable, user-defined DeleteParticle, output every second -- atol 1e-6 vs v3 JIT."""
+    import os
+
+    g = np.load(os.path.join(golden_dir, "v3_jit_linear.npz" if interp == "linear" else "v3_jit_cgrid.npz"))
+    lon, lat, depth = (g[k].astype(np.float32) for k in ("lon", "lat", "depth"))
+    fieldset = pb.FieldSet.from_arrays(lon=lon, lat=lat, depth=depth, time=g["time"], U=g["U"], V=g["V"], W=g["W"], mesh="flat",
+                                       interp_method=interp, padding=("low", "low", "high"))  # fmt: skip
+    x, y, z = np.meshgrid(np.linspace(0, 1, 7), np.linspace(0, 1, 13), np.linspace(0, 1, 5))
+    TestP = pb.Particle.add_variable(pb.Variable("pid", dtype=np.int32, initial=0))
+    pset = pb.ParticleSet(fieldset, pclass=TestP, x=x, y=y, z=z, t=np.zeros(x.size), pid=np.arange(x.size))
+
+    def DeleteParticle(particles, fieldset):
+        any_error = particles.state >= 50  # This captures all Errors
+        particles[any_error].state = pb.StatusCode.Delete
+
+    obs = {k: np.full((x.size, 5), np.nan, dtype=np.float32) for k in "xyz"}
+
+    class Out:
+        outputdt = np.timedelta64(1, "s")
+        i = 0
+
+        def write(self, ps, _time):
+            for k in "xyz":
+                obs[k][ps.pid, self.i] = ps._data[k]
+            self.i += 1
+
+    pset.execute([pb.AdvectionRK4_3D, DeleteParticle], runtime=np.timedelta64(4, "s"), dt=np.timedelta64(1, "s"), output_file=Out())
+    assert pset.last_report["mode"] == "stepwise"
+    for k, gk in (("x", "gold_lon"), ("y", "gold_lat"), ("z", "gold_z")):
+        np.testing.assert_allclose(obs[k][:, :4], g[gk], atol=1e-6, equal_nan=True)
