@@ -12,17 +12,21 @@
 #ifndef PB_BLOCK
 #define PB_BLOCK 128
 #endif
-template <class D, int NC>
+// SF64: store the cached corner values converted to float64 (only for float64 grids, whose interpolation is
+// float64 throughout -- a float32 value converts exactly): no F2F per read, twice the shared memory.
+template <class D, int NC, bool SF64 = false>
 struct Corners {
     int ti, zi, yi, xi;  // key of the block held in v (INT_MIN: empty)
 #ifdef PB_SMEM_CACHE
-    D* sm;               // this lane's column of the block-shared cache
-    __device__ __forceinline__ void put(int c, int k, D val) { sm[(c * 16 + k) * PB_BLOCK] = val; }
-    __device__ __forceinline__ void load(int c, D (&out)[16]) const {
+    using S = typename std::conditional<SF64, double, D>::type;
+    S* sm;               // this lane's column of the block-shared cache
+    __device__ __forceinline__ void put(int c, int k, D val) { sm[(c * 16 + k) * PB_BLOCK] = (S)val; }
+    __device__ __forceinline__ void load(int c, S (&out)[16]) const {
 #pragma unroll
         for (int k = 0; k < 16; ++k) out[k] = sm[(c * 16 + k) * PB_BLOCK];
     }
 #else
+    using S = D;
     D v[NC][16];         // [component][(t*2+z)*4 + y*2 + x]
     __device__ __forceinline__ void put(int c, int k, D val) { v[c][k] = val; }
     __device__ __forceinline__ void load(int c, D (&out)[16]) const {
@@ -119,7 +123,11 @@ template <class A, class D, int NC>
 struct EvalCtx {
     AxisCell<A> cx, cy, cz;
     AxisCell<double> ct;
+#ifdef PB_SMEM_CACHE
+    Corners<D, NC, std::is_same<A, double>::value> cor;
+#else
     Corners<D, NC> cor;
+#endif
     double last_t, last_tau;  // stages 2 and 3 of a step (and stage 4 / next stage 1) sample the same time
     int szi, syi, sxi;        // indices of the last completed search: ei is raveled once, on exit
     bool searched;
@@ -194,11 +202,12 @@ __device__ __forceinline__ void eval_uvw(const GridDev& g, const FieldDev& f, Ev
         e.refills++;
     }
 
-    D blk[16];
+    using DV = typename decltype(e.cor)::S;  // float64 copies on float64 grids (exact), else the data dtype
+    DV blk[16];
     e.cor.load(0, blk);
-    u = xlinear<D, TT, TZ, TY, TX>(blk, tau, zeta, eta, xsi);
+    u = xlinear<DV, TT, TZ, TY, TX>(blk, tau, zeta, eta, xsi);
     e.cor.load(1, blk);
-    v = xlinear<D, TT, TZ, TY, TX>(blk, tau, zeta, eta, xsi);
+    v = xlinear<DV, TT, TZ, TY, TX>(blk, tau, zeta, eta, xsi);
     if (g.spherical) {  // u /= deg2m * cos(deg2rad(y)); v /= deg2m   (in-place: result keeps u's dtype)
         PY conv = (PY)g.deg2m * cos_np(deg2rad_np(y));
         if (u.f32 && std::is_same<PY, float>::value) {
@@ -211,7 +220,7 @@ __device__ __forceinline__ void eval_uvw(const GridDev& g, const FieldDev& f, Ev
     }
     if (NC == 3) {
         e.cor.load(NC - 1, blk);
-        w = xlinear<D, TT, TZ, TY, TX>(blk, tau, zeta, eta, xsi);
+        w = xlinear<DV, TT, TZ, TY, TX>(blk, tau, zeta, eta, xsi);
     } else {
         w = Val{0.0, u.f32};
     }
@@ -235,7 +244,7 @@ struct AGridPolicy {
         e.cor.ti = e.cor.zi = e.cor.yi = e.cor.xi = INT_MIN;
 #ifdef PB_SMEM_CACHE
         extern __shared__ __align__(16) unsigned char pb_smem[];
-        e.cor.sm = reinterpret_cast<D*>(pb_smem) + threadIdx.x;
+        e.cor.sm = reinterpret_cast<typename decltype(e.cor)::S*>(pb_smem) + threadIdx.x;
 #endif
         e.ei = ei;
         e.last_t = -1.0;  // valid sample times are >= 0
@@ -262,7 +271,7 @@ static cudaError_t launch1(const AdvectParams& p, cudaStream_t s) {
     const int block = PB_BLOCK;
     const long long grid = (p.P.n + block - 1) / block;
 #ifdef PB_SMEM_CACHE
-    const size_t smem = (size_t)NC * 16 * sizeof(D) * PB_BLOCK;
+    const size_t smem = (size_t)NC * 16 * sizeof(typename decltype(EvalCtx<A, D, NC>::cor)::S) * PB_BLOCK;
     if (smem > 48 * 1024) {
         cudaError_t ce = cudaFuncSetAttribute(advect_kernel<AGridPolicy<A, D, HT, NC>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (ce != cudaSuccess) return ce;
@@ -288,7 +297,7 @@ cudaError_t launch_agrid(const AdvectParams& p, bool coord_f64, bool data_f64, b
 template <class A, class D, bool HT, int NC>
 static cudaError_t sample1(const SampleParams& p, cudaStream_t s) {
 #ifdef PB_SMEM_CACHE
-    const size_t smem = (size_t)NC * 16 * sizeof(D) * PB_BLOCK;
+    const size_t smem = (size_t)NC * 16 * sizeof(typename decltype(EvalCtx<A, D, NC>::cor)::S) * PB_BLOCK;
     if (smem > 48 * 1024) {
         cudaError_t ce = cudaFuncSetAttribute(sample_kernel<AGridPolicy<A, D, HT, NC>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (ce != cudaSuccess) return ce;

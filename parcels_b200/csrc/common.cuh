@@ -308,7 +308,13 @@ __global__ void __launch_bounds__(PB_BLOCK_THREADS, PB_MINBLOCKS) advect_kernel(
             if (nstage > 0) Policy::template eval<float, float, float>(p, e, nohint1, t, z, y, x, u1, v1, w1);
             su = u1.v; sv = v1.v; sw = w1.v;
             uk = u1; vk = v1; wk = w1;
-            for (int k = 1; k < nstage; ++k) {
+#ifdef PB_UNROLL_STAGES
+#pragma unroll
+#else
+#pragma unroll 1
+#endif
+            for (int k = 1; k < 4; ++k) {
+                if (k >= nstage) break;
                 // stage position: x + u*0.5*dt (k = 1, 2) or x + u*dt (k = 3)
                 const bool full = (k == 3);
                 const double xs = (double)x + (full ? uk.v : half_of(uk)) * dtp;
