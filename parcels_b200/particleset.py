@@ -29,9 +29,17 @@ def _to_float_seconds(v):
     return float(v)
 
 
-def _is_token(f):
-    """one of this package's device-kernel tokens (kernels.py), not a user function that happens to share the name"""
-    return getattr(K, f.__name__, None) is f
+def _builtin_name(f):
+    """Name of the built-in kernel ``f`` stands for, or None for a user function.  Built-ins are this package's
+    tokens (kernels.py, by identity) and the reference package's own kernel functions (by module + name); a user
+    function that merely shares a name -- e.g. the ubiquitous user-defined ``DeleteParticle`` -- is NOT one."""
+    n = f.__name__
+    if n != "_none" and getattr(K, n, None) is f:
+        return n
+    mod = getattr(f, "__module__", "") or ""
+    if mod.startswith("parcels.kernels") and (n in K.SCHEMES or n == "DiffusionUniformKh") and n != "_none":
+        return n
+    return None
 
 
 def _delete_on_error(particles, fieldset):
@@ -50,46 +58,41 @@ class KernelPlan:
             raise ValueError(f"kernels must be a list. Got {kernel_list=!r}")
         if len(kernel_list) == 0:
             raise ValueError("List of `kernels` should have at least one function.")
-        names = []
         for f in kernel_list:
             if not isinstance(f, types.FunctionType):
                 raise TypeError(f"Argument `kernels` should be a function or list of functions. Got {type(f)}")
-            names.append(f.__name__)
-        self.funcname = "".join(names)
-        self.delete_on_error = False
-        if fieldset.time_window is not None and names[-1] != "DeleteParticle":
-            raise NotImplementedError("time-windowed FieldSets need the DeleteParticle handler: an error cannot be replayed "
-                                      "step-exactly once the window has moved on")  # fmt: skip
-        if names[-1] == "DeleteParticle":
+        self.funcname = "".join(f.__name__ for f in kernel_list)
+        tokens = [_builtin_name(f) for f in kernel_list]  # None for user functions (recognised by identity, not by name)
+        names = list(tokens)
+        self.delete_on_error = self.diffusion = False
+        if names and names[-1] == "DeleteParticle":
             self.delete_on_error = True
             names = names[:-1]
-        self.diffusion = False
         if names and names[-1] == "DiffusionUniformKh":
             self.diffusion = True
             names = names[:-1]
         if len(names) == 0 and self.diffusion:
             names = ["_none"]
-        builtin = set(K.SCHEMES) | {"DiffusionUniformKh", "DeleteParticle"}
         self.stepwise = not (len(names) == 1 and names[0] in K.SCHEMES)
+        if fieldset.time_window is not None and (self.stepwise or not self.delete_on_error):
+            raise NotImplementedError("time-windowed FieldSets need a list of built-in kernels ending with the DeleteParticle token: "
+                                      "an error cannot be replayed step-exactly once the window has moved on")  # fmt: skip
         if self.stepwise:
             # the list mixes built-ins with user Python kernels: the loop control runs on the host step by step
             # (stepwise.py), every built-in kernel still runs on the device
-            if fieldset.time_window is not None:
-                raise NotImplementedError("user Python kernels are not supported on time-windowed FieldSets yet")
             self.delete_on_error = self.diffusion = False
             self.items = []
-            for f in kernel_list:
-                n = f.__name__
-                if n in K.SCHEMES and f.__module__ == K.__name__ or (n in K.SCHEMES and n != "_none" and n.startswith("Advection") and _is_token(f)):
+            for f, n in zip(kernel_list, tokens, strict=True):
+                if n in K.SCHEMES:
                     if n in K.SCHEMES_3D and fieldset.W is None:
                         raise AttributeError("FieldSet has no UVW VectorField (no W field) for a 3-D advection kernel")
                     self.items.append(["device", K.SCHEMES[n], False, self])
-                elif n == "DiffusionUniformKh" and _is_token(f):
+                elif n == "DiffusionUniformKh":
                     if self.items and self.items[-1][0] == "device" and not self.items[-1][2]:
                         self.items[-1][2] = True  # fused with the advection kernel right before it
                     else:
                         self.items.append(["device", K.SCHEMES["_none"], True, self])
-                elif n == "DeleteParticle" and _is_token(f):
+                elif n == "DeleteParticle":
                     self.items.append(["python", _delete_on_error])
                 else:
                     self.items.append(["python", f])
