@@ -242,4 +242,6 @@ if __name__ == "__main__":
     os.makedirs(GOLDEN, exist_ok=True)
     make_v3("linear", "v3_jit_linear.npz")
     make_v3("cgrid_velocity", "v3_jit_cgrid.npz")
+    make_v3("freeslip", "v3_jit_freeslip.npz")
+    make_v3("nearest", "v3_jit_nearest.npz")
     make_ref_cases()

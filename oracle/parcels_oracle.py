@@ -305,6 +305,97 @@ def xlinear_velocity(fs: OFieldSet, pos, gp):
     return u, v, w
 
 
+def _corner_block(data, ti, tau, zi, zeta, yi, xi):
+    """_xinterpolators.py:78-96 (``_get_corner_data_Agrid``): (lenT, lenZ, 2, 2, N)"""
+    T, Z, Y, X = data.shape
+    two_t = bool(np.any(tau > 0))
+    two_z = bool(np.any(zeta > 0))
+    t_lv = (ti, np.clip(ti + 1, 0, T - 1)) if two_t else (ti,)
+    z_lv = (zi, np.clip(zi + 1, 0, Z - 1)) if two_z else (zi,)
+    y_lv = (yi, np.clip(yi + 1, 0, Y - 1))
+    x_lv = (xi, np.clip(xi + 1, 0, X - 1))
+    return np.array([[[[_take(data, a, b, cc, d) for d in x_lv] for cc in y_lv] for b in z_lv] for a in t_lv]), two_z
+
+
+def spatialslip_velocity(fs: OFieldSet, pos, gp, a, b):
+    """_xinterpolators.py:385-480 (``_Spatialslip``; XFreeslip a=1, b=0; XPartialslip a=b=0.5): XLinear damped near
+    land (cells whose corner velocities are all ~0 at the lower time level)."""
+    (ti, tau), (zi, zeta), (yi, eta), (xi, xsi) = gp
+    u = xlinear(fs.U, ti, tau, zi, zeta, yi, eta, xi, xsi)
+    v = xlinear(fs.V, ti, tau, zi, zeta, yi, eta, xi, xsi)
+    w = xlinear(fs.W, ti, tau, zi, zeta, yi, eta, xi, xsi) if fs.W is not None else None
+    cU, two_z = _corner_block(fs.U, ti, tau, zi, zeta, yi, xi)
+    cV, _ = _corner_block(fs.V, ti, tau, zi, zeta, yi, xi)
+
+    def land(z_, y_, x_):
+        return np.where(np.isclose(cU[0, z_, y_, x_, :], 0.0) & np.isclose(cV[0, z_, y_, x_, :], 0.0), True, False)
+
+    def all_land(pairs):
+        m = np.ones(len(xsi), dtype=bool)
+        for y_, x_ in pairs:
+            m &= land(0, y_, x_)
+        if two_z:
+            for y_, x_ in pairs:
+                m &= land(1, y_, x_)
+        return m
+
+    def all_land_zz(pairs):  # the W factors always look at both Z levels (:460-470)
+        m = np.ones(len(xsi), dtype=bool)
+        for y_, x_ in pairs:
+            m &= land(0, y_, x_) & land(1, y_, x_)
+        return m
+
+    f_u = np.ones_like(xsi)
+    m = all_land([(0, 0), (0, 1)]) & (eta > 0)
+    f_u[m] = f_u[m] * (a + b * eta[m]) / eta[m]
+    m = all_land([(1, 0), (1, 1)]) & (eta < 1)
+    f_u[m] = f_u[m] * (1 - b * eta[m]) / (1 - eta[m])
+    u = u * f_u
+    if fs.grid.spherical:
+        u /= 1852 * 60 * np.cos(np.deg2rad(pos["y"]))
+    f_v = np.ones_like(eta)
+    m = all_land([(0, 0), (1, 0)]) & (xsi > 0)
+    f_v[m] = f_v[m] * (a + b * xsi[m]) / xsi[m]
+    m = all_land([(0, 1), (1, 1)]) & (xsi < 1)
+    f_v[m] = f_v[m] * (1 - b * xsi[m]) / (1 - xsi[m])
+    v = v * f_v
+    if fs.grid.spherical:
+        v /= 1852 * 60
+    if w is not None:
+        f_w = np.ones_like(zeta)
+        m = all_land_zz([(0, 0), (0, 1)]) & (eta > 0)
+        f_w[m] = f_w[m] * (a + b * eta[m]) / eta[m]
+        m = all_land_zz([(1, 0), (1, 1)]) & (eta < 1)
+        f_w[m] = f_w[m] * (1 - b * eta[m]) / (1 - eta[m])
+        m = all_land_zz([(0, 0), (1, 0)]) & (xsi > 0)
+        f_w[m] = f_w[m] * (a + b * xsi[m]) / xsi[m]
+        m = all_land_zz([(0, 1), (1, 1)]) & (xsi < 1)
+        f_w[m] = f_w[m] * (1 - b * xsi[m]) / (1 - xsi[m])
+        w = w * f_w
+    else:
+        w = np.zeros_like(u)
+    return u, v, w
+
+
+def xnearest(data, ti, tau, zi, zeta, yi, eta, xi, xsi):
+    """_xinterpolators.py:515-560 (``XNearest.interp``): nearest node in space, linear in time."""
+    T, Z, Y, X = data.shape
+    two_t = bool(np.any(tau > 0))
+    zf = np.where(zeta <= 0.5, zi, np.clip(zi + 1, 0, Z - 1))
+    yf = np.where(eta <= 0.5, yi, np.clip(yi + 1, 0, Y - 1))
+    xf = np.where(xsi <= 0.5, xi, np.clip(xi + 1, 0, X - 1))
+    c0 = _take(data, ti, zf, yf, xf)
+    if two_t:
+        return c0 * (1 - tau) + _take(data, np.clip(ti + 1, 0, T - 1), zf, yf, xf) * tau
+    return c0
+
+
+def xnearest_velocity(fs: OFieldSet, pos, gp):
+    """``XNearest_Velocity`` of the reference's regression test (tests/test_interpolation.py:279-294): no unit conversion."""
+    (ti, tau), (zi, zeta), (yi, eta), (xi, xsi) = gp
+    return tuple(xnearest(f, ti, tau, zi, zeta, yi, eta, xi, xsi) for f in (fs.U, fs.V, fs.W))
+
+
 # ----------------------------------------------------------------------------------------------
 # VectorField.eval
 # ----------------------------------------------------------------------------------------------
@@ -338,6 +429,12 @@ def eval_uvw(fs: OFieldSet, t, z, y, x, view: View | None, want3d: bool):
         gp = ((ti, tau), (zi, zeta), (yi, eta), (xi, xsi))
         if fs.interp == "linear":
             u, v, w = xlinear_velocity(fs, pos, gp)
+        elif fs.interp == "freeslip":
+            u, v, w = spatialslip_velocity(fs, pos, gp, 1.0, 0.0)
+        elif fs.interp == "partialslip":
+            u, v, w = spatialslip_velocity(fs, pos, gp, 0.5, 0.5)
+        elif fs.interp == "nearest":
+            u, v, w = xnearest_velocity(fs, pos, gp)
         else:
             from . import curvilinear_oracle as co
 

@@ -290,7 +290,16 @@ def build_fieldset(
         f = Field(name, model)
         f.interp_method = XLinear()
         fields[name] = f
-    vi = {"linear": XLinear_Velocity, "cgrid_velocity": CGrid_Velocity}[interp]()
+    from parcels.interpolators._base import VectorInterpolator
+    from parcels.interpolators._xinterpolators import XFreeslip, XNearest, XPartialslip
+
+    class XNearest_Velocity(VectorInterpolator):  # noqa: N801 -- as defined in the reference's tests/test_interpolation.py:279-294
+        def interp(self, particle_positions, grid_positions, vectorfield):
+            n = XNearest()
+            return tuple(n.interp(particle_positions, grid_positions, f) for f in (vectorfield.U, vectorfield.V, vectorfield.W))
+
+    vi = {"linear": XLinear_Velocity, "cgrid_velocity": CGrid_Velocity, "freeslip": XFreeslip, "partialslip": XPartialslip,
+          "nearest": XNearest_Velocity}[interp]()  # fmt: skip
     fields["UV"] = VectorField("UV", fields["U"], fields["V"], interp_method=vi)
     if W is not None:
         fields["UVW"] = VectorField("UVW", fields["U"], fields["V"], fields["W"], interp_method=vi)

@@ -168,6 +168,16 @@ CASES = {
     "cgrid_rect_sph": dict(seed=26, kind="smooth", interp="cgrid_velocity", cdtype="f8", ddtype="f4", mesh="spherical",
                            nx=21, ny=17, nz=5, nt=3, tstep=3600.0, n=300, kernels=["AdvectionRK4"], dt=600.0,
                            segments=[dict(runtime=7200.0)], delete=True, margin=0.02, umax=10.0),
+    # ---- other A-grid vector interpolators (reference _xinterpolators.py:385-560): land = nodes with U = V = 0 ----
+    "freeslip_3d": dict(seed=31, kind="smooth", interp="freeslip", land=True, cdtype="f4", ddtype="f8", mesh="flat", nx=16, ny=13,
+                        nz=6, nt=4, tstep=200.0, n=400, kernels=["AdvectionRK4_3D"], dt=50.0, segments=[dict(runtime=600.0)],
+                        delete=True, margin=-0.02, umax=4.0),
+    "partialslip_sph": dict(seed=32, kind="smooth", interp="partialslip", land=True, cdtype="f8", ddtype="f4", mesh="spherical",
+                            nx=21, ny=17, nz=5, nt=3, tstep=3600.0, n=300, kernels=["AdvectionRK4"], dt=600.0,
+                            segments=[dict(runtime=7200.0)], delete=True, margin=0.02, umax=10.0),
+    "nearest_3d": dict(seed=33, kind="smooth", interp="nearest", cdtype="f8", ddtype="f4", mesh="spherical", nx=21, ny=17, nz=5,
+                       nt=3, tstep=3600.0, n=300, kernels=["AdvectionRK4_3D"], dt=600.0, segments=[dict(runtime=7200.0)],
+                       delete=True, margin=0.02, umax=10.0),
 }
 
 
@@ -221,6 +231,12 @@ def build(spec):
     U, V, W = smooth_uvw(rng, lon.astype(np.float64), lat.astype(np.float64),
                          None if depth is None else depth.astype(np.float64), nt, dd,
                          umax=umax, wmax=_default(spec, "wmax", 1e-3))  # fmt: skip
+    if spec.get("land"):  # blocks of land: U = V = W = 0 on about a quarter of the nodes, all levels and times
+        blk = rng.uniform(0, 1, (ny // 3 + 1, nx // 3 + 1)) < 0.25
+        land = np.kron(blk, np.ones((3, 3), dtype=bool))[:ny, :nx]
+        U[..., land] = 0
+        V[..., land] = 0
+        W[..., land] = 0
     times = np.arange(nt) * spec["tstep"] if nt > 1 else None
     m = spec["margin"]  # negative margin => some particles start outside the domain
     lx, ly = float(lon[-1] - lon[0]), float(lat[-1] - lat[0])

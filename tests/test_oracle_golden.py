@@ -41,9 +41,13 @@ def _v3_case(g):
     return lon, lat, depth, x.flatten(), y.flatten(), z.flatten()
 
 
-@pytest.mark.parametrize("interp", ["linear", "cgrid_velocity"])
+V3_FILES = {"linear": "v3_jit_linear.npz", "cgrid_velocity": "v3_jit_cgrid.npz", "freeslip": "v3_jit_freeslip.npz",
+            "nearest": "v3_jit_nearest.npz"}  # fmt: skip
+
+
+@pytest.mark.parametrize("interp", list(V3_FILES))
 def test_oracle_reproduces_v3_jit_goldens(golden_dir, interp):
-    g = np.load(os.path.join(golden_dir, "v3_jit_linear.npz" if interp == "linear" else "v3_jit_cgrid.npz"))
+    g = np.load(os.path.join(golden_dir, V3_FILES[interp]))
     lon, lat, depth, x, y, z = _v3_case(g)
     fs = po.OFieldSet(po.OGrid(lon, lat, depth, mesh="flat", offsets=(1, 1, 0)), g["U"], g["V"], g["W"], time=g["time"],
                       interp=interp)  # fmt: skip
