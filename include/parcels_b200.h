@@ -100,8 +100,17 @@ int32_t pb_grid_upload_curvilinear(pb_engine* e, const void* lon2d, const void* 
 
 /* Vector interpolator of fieldset.UV / UVW (VectorField.interp_method, _core/field.py:236-246):
  * XLinear_Velocity (A-grid, interpolators/_xinterpolators.py:169-190) or CGrid_Velocity (:193-332)
- * with the SGRID staggering offsets of _get_offsets_dictionary (:99-109: 1 for LOW padding). */
-enum pb_interp { PB_INTERP_XLINEAR_VELOCITY = 0, PB_INTERP_CGRID_VELOCITY = 1 };
+ * with the SGRID staggering offsets of _get_offsets_dictionary (:99-109: 1 for LOW padding).
+ * Rectilinear A-grids also take XFreeslip / XPartialslip (_Spatialslip, :385-495) and the per-component
+ * nearest-node interpolator (XNearest, :515-560, wrapped as XNearest_Velocity by the reference's
+ * tests/test_interpolation.py:279-294). */
+enum pb_interp {
+    PB_INTERP_XLINEAR_VELOCITY = 0,
+    PB_INTERP_CGRID_VELOCITY = 1,
+    PB_INTERP_XFREESLIP = 2,
+    PB_INTERP_XPARTIALSLIP = 3,
+    PB_INTERP_XNEAREST_VELOCITY = 4
+};
 int32_t pb_set_interpolation(pb_engine* e, int32_t method, int32_t off_x, int32_t off_y, int32_t off_z);
 
 /* ---- field data: replaces ModelData.field_data -> xarray .isel gathers -------------------

@@ -13,7 +13,7 @@ import numpy as np
 from .fieldset import FieldSet, XGrid
 from .particleset import ParticleSet
 
-SUPPORTED_VECTOR_INTERP = ("XLinear_Velocity",)
+SUPPORTED_VECTOR_INTERP = {"XLinear_Velocity": "linear", "XFreeslip": "freeslip", "XPartialslip": "partialslip"}
 
 
 def _values(da):
@@ -27,7 +27,7 @@ def from_parcels(ref_fieldset) -> FieldSet:
     vf = getattr(ref_fieldset, "UVW", None) or ref_fieldset.UV
     interp = type(vf.interp_method).__name__
     if interp not in SUPPORTED_VECTOR_INTERP:
-        raise NotImplementedError(f"vector interpolator {interp} is not on the engine (supported: {SUPPORTED_VECTOR_INTERP})")
+        raise NotImplementedError(f"vector interpolator {interp} is not on the engine (supported: {sorted(SUPPORTED_VECTOR_INTERP)})")
     lon, lat = np.asarray(g.lon), np.asarray(g.lat)
     if lon.ndim != 1:
         raise NotImplementedError("curvilinear grids are not on the engine yet")
@@ -40,7 +40,8 @@ def from_parcels(ref_fieldset) -> FieldSet:
     if U.time_interval is not None:
         time = _values(U.data.time)
     W = getattr(ref_fieldset, "W", None)
-    fs = FieldSet(grid, _values(U.data), _values(ref_fieldset.V.data), None if W is None else _values(W.data), time=time)
+    fs = FieldSet(grid, _values(U.data), _values(ref_fieldset.V.data), None if W is None else _values(W.data), time=time,
+                  interp_method=SUPPORTED_VECTOR_INTERP[interp])
     for name, f in ref_fieldset.fields.items():
         if type(getattr(f, "interp_method", None)).__name__ == "XConstantField":
             fs.add_constant_field(name, float(_values(f.data)[0, 0, 0, 0]), mesh="spherical" if f.grid._mesh.is_spherical() else "flat")

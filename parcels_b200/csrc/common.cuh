@@ -40,6 +40,7 @@ struct GridDev {
     const double* cellproj;       // spherical curvilinear: per cell 16 doubles = pu[4], pv[4], eu[3], ev[3], pad[2]
     double hbox[6];               // xmin, xmax, ymin, ymax, zmin, zmax of the hash grid
     int off_x, off_y, off_z;      // C-grid staggering offsets (_xinterpolators.py:99-109)
+    float slip_a, slip_b;         // _Spatialslip coefficients: XFreeslip (1, 0), XPartialslip (0.5, 0.5)
     // multi-GPU mode D (X-slab domain decomposition): this engine holds lon[xi_offset : xi_offset + nx]
     // of the global axis (owned columns + halo); cell indices written to `ei` are GLOBAL.
     int decomposed;
@@ -474,6 +475,9 @@ __global__ void sample_kernel(const SampleParams s) {
 // launchers implemented in agrid.cu / cgrid.cu (one translation unit per grid family keeps nvcc parallel)
 cudaError_t launch_agrid(const AdvectParams& p, bool coord_f64, bool data_f64, bool has_time, int nc, cudaStream_t s);
 cudaError_t launch_cgrid(const AdvectParams& p, bool coord_f64, bool data_f64, int nc, cudaStream_t s);
+// mode: 1 = _Spatialslip (g.slip_a/b), 2 = XNearest per component  (aslip.cu)
+cudaError_t launch_agrid_alt(const AdvectParams& p, int mode, bool coord_f64, bool data_f64, bool has_time, int nc, cudaStream_t s);
+cudaError_t launch_sample_agrid_alt(const SampleParams& p, int mode, bool coord_f64, bool data_f64, bool has_time, int nc, cudaStream_t s);
 cudaError_t launch_precompute_cells(const void* lon, const void* lat, int ny, int nx, bool coord_f64, double* out, cudaStream_t s);
 cudaError_t launch_sample_agrid(const SampleParams& p, bool coord_f64, bool data_f64, bool has_time, int nc, cudaStream_t s);
 cudaError_t launch_sample_cgrid(const SampleParams& p, bool coord_f64, bool data_f64, int nc, cudaStream_t s);

@@ -408,12 +408,21 @@ int32_t pb_grid_upload_curvilinear(pb_engine* e, const void* lon2d, const void* 
     return upload_zt(e, depth, nz, coord_is_f64, time_s, nt, spherical, deg2m, xdim_cells, ydim_cells, zdim_cells);
 }
 
+// kernel family of aslip.cu: 1 = _Spatialslip, 2 = nearest node; 0 = not an alternative A-grid interpolator
+static int agrid_alt_mode(int interp) {
+    if (interp == PB_INTERP_XFREESLIP || interp == PB_INTERP_XPARTIALSLIP) return 1;
+    return interp == PB_INTERP_XNEAREST_VELOCITY ? 2 : 0;
+}
+
 int32_t pb_set_interpolation(pb_engine* e, int32_t method, int32_t off_x, int32_t off_y, int32_t off_z) {
     if (!e) return fail(PB_ERR_INVALID, "engine is NULL");
-    if (method != PB_INTERP_XLINEAR_VELOCITY && method != PB_INTERP_CGRID_VELOCITY) return fail(PB_ERR_INVALID, "unknown interpolation %d", method);
+    if (method < PB_INTERP_XLINEAR_VELOCITY || method > PB_INTERP_XNEAREST_VELOCITY) return fail(PB_ERR_INVALID, "unknown interpolation %d", method);
     if ((off_x | off_y | off_z) & ~1) return fail(PB_ERR_INVALID, "staggering offsets must be 0 or 1");
     e->interp = method;
     e->g.off_x = off_x; e->g.off_y = off_y; e->g.off_z = off_z;
+    // _Spatialslip(a, b): XFreeslip (1, 0), XPartialslip (0.5, 0.5)  (_xinterpolators.py:483-506)
+    e->g.slip_a = method == PB_INTERP_XPARTIALSLIP ? 0.5f : 1.0f;
+    e->g.slip_b = method == PB_INTERP_XPARTIALSLIP ? 0.5f : 0.0f;
     return PB_OK;
 }
 
@@ -608,9 +617,11 @@ int32_t pb_sample_velocity(pb_engine* e, int64_t n, const double* t, const doubl
     sp.ei_hint = ei_hint ? di : nullptr;
     sp.ei_out = di + n; sp.state_out = di + 2 * n;
     sp.pos_f32 = positions_are_f32; sp.no_hint = no_hint;
+    const int alt = agrid_alt_mode(e->interp);
     cudaError_t ce = e->interp == PB_INTERP_CGRID_VELOCITY
                          ? launch_sample_cgrid(sp, e->coord_f64 != 0, e->f_f64[0] != 0, nc, e->stream)
-                         : launch_sample_agrid(sp, e->coord_f64 != 0, e->f_f64[0] != 0, e->g.nt > 0, nc, e->stream);
+                     : alt ? launch_sample_agrid_alt(sp, alt, e->coord_f64 != 0, e->f_f64[0] != 0, e->g.nt > 0, nc, e->stream)
+                           : launch_sample_agrid(sp, e->coord_f64 != 0, e->f_f64[0] != 0, e->g.nt > 0, nc, e->stream);
     if (ce != cudaSuccess) return fail(PB_ERR_CUDA, "sample_kernel launch failed: %s", cudaGetErrorString(ce));
     double* dst[3] = {u, v, w};
     for (int k = 0; k < 3; ++k) CK(cudaMemcpyAsync(dst[k], d + (4 + k) * n, n * 8, cudaMemcpyDeviceToHost, e->stream));
@@ -658,9 +669,11 @@ int32_t pb_advect_async(pb_engine* e, const pb_advect_args* a) {
     CK(cudaMemcpyAsync(e->d_rep, e->h_rep, sizeof(ReportDev), cudaMemcpyHostToDevice, e->stream));
     CK(cudaEventRecord(e->ev0, e->stream));
     if (e->n > 0) {
+        const int alt = agrid_alt_mode(e->interp);
         cudaError_t ce = e->interp == PB_INTERP_CGRID_VELOCITY
                              ? launch_cgrid(p, e->coord_f64 != 0, e->f_f64[0] != 0, nc, e->stream)
-                             : launch_agrid(p, e->coord_f64 != 0, e->f_f64[0] != 0, e->g.nt > 0, nc, e->stream);
+                         : alt ? launch_agrid_alt(p, alt, e->coord_f64 != 0, e->f_f64[0] != 0, e->g.nt > 0, nc, e->stream)
+                               : launch_agrid(p, e->coord_f64 != 0, e->f_f64[0] != 0, e->g.nt > 0, nc, e->stream);
         if (ce != cudaSuccess) return fail(PB_ERR_CUDA, "advect_kernel launch failed: %s", cudaGetErrorString(ce));
     }
     CK(cudaEventRecord(e->ev1, e->stream));

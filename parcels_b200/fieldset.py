@@ -154,6 +154,11 @@ class _ConstantGrid:
         return EARTH_RADIUS * np.pi / 180.0 if self.mesh == "spherical" else 1.0
 
 
+# VectorField.interp_method -> enum pb_interp: XLinear_Velocity, CGrid_Velocity, XFreeslip, XPartialslip
+# (reference interpolators/_xinterpolators.py:169-506) and the per-component XNearest (:515-560)
+INTERP_METHODS = {"linear": 0, "cgrid_velocity": 1, "freeslip": 2, "partialslip": 3, "nearest": 4}
+
+
 class FieldSet:
     """Velocity fields U, V (, W) laid out (T, Z, Y, X) on one A-grid, plus constant fields.
 
@@ -163,10 +168,8 @@ class FieldSet:
 
     def __init__(self, grid: XGrid, U, V, W=None, time=None, interp_method="linear", padding=("low", "low", "high"),
                  time_window=None):  # fmt: skip
-        if interp_method not in ("linear", "cgrid_velocity"):
-            raise NotImplementedError(
-                f"interp_method {interp_method!r}: XLinear_Velocity ('linear') and CGrid_Velocity ('cgrid_velocity') are on this engine"
-            )
+        if interp_method not in INTERP_METHODS:
+            raise NotImplementedError(f"interp_method {interp_method!r}: this engine has {sorted(INTERP_METHODS)}")
         if grid.curvilinear and interp_method != "cgrid_velocity":
             raise NotImplementedError("curvilinear grids are supported with CGrid_Velocity only")
         self.interp_method = interp_method
@@ -250,7 +253,7 @@ class FieldSet:
                                             g.zdim, g.get_spatial_hash())  # fmt: skip
             else:
                 eng.upload_rectilinear_grid(g.lon, g.lat, g.depth, self._time_s, g.is_spherical(), g.deg2m, g.xdim, g.ydim, g.zdim)
-            eng.set_interpolation(1 if self.interp_method == "cgrid_velocity" else 0, *self.offsets)
+            eng.set_interpolation(INTERP_METHODS[self.interp_method], *self.offsets)
             for slot, name in enumerate(("U", "V", "W")):
                 if name in self.fields:
                     d = self.fields[name].data

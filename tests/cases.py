@@ -175,6 +175,11 @@ CASES = {
     "partialslip_sph": dict(seed=32, kind="smooth", interp="partialslip", land=True, cdtype="f8", ddtype="f4", mesh="spherical",
                             nx=21, ny=17, nz=5, nt=3, tstep=3600.0, n=300, kernels=["AdvectionRK4"], dt=600.0,
                             segments=[dict(runtime=7200.0)], delete=True, margin=0.02, umax=10.0),
+    # 2-D advection at the surface of a 3-D field whose land mask grows with depth: the whole batch has zeta == 0, so the
+    # reference's land test looks at the first depth level only (lenZ == 1, _xinterpolators.py:400,426-434)
+    "freeslip_surface": dict(seed=34, kind="smooth", interp="freeslip", land="depth", surface=True, cdtype="f8", ddtype="f4",
+                             mesh="flat", nx=19, ny=16, nz=5, nt=3, tstep=400.0, n=300, kernels=["AdvectionRK4"], dt=60.0,
+                             segments=[dict(runtime=720.0)], delete=True, margin=0.02, umax=4.0),
     "nearest_3d": dict(seed=33, kind="smooth", interp="nearest", cdtype="f8", ddtype="f4", mesh="spherical", nx=21, ny=17, nz=5,
                        nt=3, tstep=3600.0, n=300, kernels=["AdvectionRK4_3D"], dt=600.0, segments=[dict(runtime=7200.0)],
                        delete=True, margin=0.02, umax=10.0),
@@ -232,11 +237,13 @@ def build(spec):
                          None if depth is None else depth.astype(np.float64), nt, dd,
                          umax=umax, wmax=_default(spec, "wmax", 1e-3))  # fmt: skip
     if spec.get("land"):  # blocks of land: U = V = W = 0 on about a quarter of the nodes, all levels and times
-        blk = rng.uniform(0, 1, (ny // 3 + 1, nx // 3 + 1)) < 0.25
-        land = np.kron(blk, np.ones((3, 3), dtype=bool))[:ny, :nx]
-        U[..., land] = 0
-        V[..., land] = 0
-        W[..., land] = 0
+        r = rng.uniform(0, 1, (ny // 3 + 1, nx // 3 + 1))
+        for k in range(U.shape[1]):  # land="depth": the land mask grows with depth (bathymetry)
+            blk = r < (0.25 if spec["land"] is True else 0.1 + 0.08 * k)
+            land = np.kron(blk, np.ones((3, 3), dtype=bool))[:ny, :nx]
+            U[:, k][..., land] = 0
+            V[:, k][..., land] = 0
+            W[:, k][..., land] = 0
     times = np.arange(nt) * spec["tstep"] if nt > 1 else None
     m = spec["margin"]  # negative margin => some particles start outside the domain
     lx, ly = float(lon[-1] - lon[0]), float(lat[-1] - lat[0])
@@ -249,6 +256,8 @@ def build(spec):
         z = rng.uniform(float(depth[0]) + m * lz, float(depth[-1]) - m * lz, n)
     if spec["kernels"][0] in ("AdvectionRK4", "AdvectionEE", "AdvectionRK2") and depth is not None:
         z = np.abs(z)  # 2-D kernels: keep particles below the surface
+    if spec.get("surface"):  # every particle exactly on the first depth level: zeta == 0 for the whole batch
+        z = np.full(n, float(depth[0]))
     rel = spec.get("release", ("const", 0.0))
     t = np.full(n, rel[1]) if rel[0] == "const" else np.round(rng.uniform(rel[1], rel[2], n))
     uses_w = spec["kernels"][0].endswith("_3D")

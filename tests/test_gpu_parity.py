@@ -27,7 +27,7 @@ pytestmark = pytest.mark.gpu
 ERR_NAME = {60: "FieldOutOfBoundError", 61: "FieldOutOfBoundSurfaceError", 70: "OutsideTimeInterval",
             51: "FieldInterpolationError", 52: "GridSearchingError", 50: "GeneralError"}  # fmt: skip
 FLAT_EXACT = {"flat_f32c_f64d", "c1_peninsula", "delayed_partial", "raise_oob", "raise_time", "rk2_3d", "through_surface",
-              "cgrid_rect_3d"}
+              "cgrid_rect_3d", "freeslip_3d", "freeslip_surface"}
 # Curvilinear search: the reference's closed-form bilinear inverse amplifies last-ulp differences (np.dot's
 # BLAS summation order, libm vs libdevice trig) by the cell's condition number, and spatial-hash hits are
 # rounded to float32 (spatialhash.py:511) -- a flipped rounding moves a weight by 6e-8.  Stated tolerance:
@@ -77,12 +77,16 @@ def test_engine_matches_reference_outputs(name, golden_dir):
     _compare(name, ps._data, ref, name in FLAT_EXACT)
 
 
-@pytest.mark.parametrize("interp", ["linear", "cgrid_velocity"])
+V3_FILES = {"linear": "v3_jit_linear.npz", "cgrid_velocity": "v3_jit_cgrid.npz", "freeslip": "v3_jit_freeslip.npz",
+            "nearest": "v3_jit_nearest.npz"}  # fmt: skip
+
+
+@pytest.mark.parametrize("interp", list(V3_FILES))
 def test_engine_reproduces_v3_jit_goldens(golden_dir, interp):
     """The reference's own regression test (tests/test_interpolation.py:297-378), atol 1e-6."""
     import parcels_b200 as pb
 
-    g = np.load(os.path.join(golden_dir, "v3_jit_linear.npz" if interp == "linear" else "v3_jit_cgrid.npz"))
+    g = np.load(os.path.join(golden_dir, V3_FILES[interp]))
     lon, lat, depth = (g[k].astype(np.float32) for k in ("lon", "lat", "depth"))
     x, y, z = np.meshgrid(np.linspace(0, 1, 7), np.linspace(0, 1, 13), np.linspace(0, 1, 5))
     fs = pb.FieldSet.from_arrays(lon=lon, lat=lat, depth=depth, time=g["time"], U=g["U"], V=g["V"], W=g["W"], mesh="flat",
