@@ -536,12 +536,15 @@ def main():
         for _ in range(min(a.warmup, 2)):
             ps._data = {k: v.copy() for k, v in init.items()}
             ps.execute(kernels, dt=dt, runtime=runtime)
+            _ = ps._data
         barrier()
         e2e_steps = 0
         t0 = time.perf_counter()
         for i in range(k_e2e):
             ps._data = fresh[i]
             ps.execute(kernels, dt=dt, runtime=runtime)
+            result = ps._data  # device -> host read of the step's result (the particle SoA after the pass)
+            assert not ps._host_stale and len(result["x"]) > 0
             e2e_steps += ps.last_report["particle_steps"]
         barrier()
         e2e_s = reduce(time.perf_counter() - t0, "MAX")

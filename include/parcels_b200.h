@@ -155,6 +155,20 @@ int32_t pb_particles_snapshot(pb_engine* e);
 int32_t pb_particles_restore(pb_engine* e);
 int64_t pb_particles_count(pb_engine* e);
 
+/* ---- output path: replaces ParticleFile.write's row selection + column copies (_core/particlefile.py:142-221)
+ * and Kernel.remove_deleted (_core/kernel.py:98-106) for a particle set that stays resident in HBM ----------
+ * pb_output_select evaluates `_to_write_particles` (:198-221) on the device for the resident particles:
+ *   finite t  and  t_out - |dt/2| <= t <= t_out + |dt/2|          (dt: the nominal step Kernel.execute leaves
+ * in particles.dt, kernel.py:225-226), in storage order, and returns the number of rows.  pb_output_gather
+ * copies ONLY those rows of the written columns (Variable.to_write, _core/particle.py:123-175: x, y, z, t,
+ * particle_id; NULL = skip the column) and, optionally, their storage indices (np.where(...)[0]) to the host.
+ * pb_particles_remove_deleted drops particles in state Delete keeping the storage order, as
+ * ParticleSet.remove_indices -> np.delete does (_core/particleset.py:247-250). */
+int32_t pb_output_select(pb_engine* e, double t_out, double dt, int64_t* n_selected);
+int32_t pb_output_gather(pb_engine* e, int64_t n_selected, int64_t* index, float* x, float* y, float* z, double* t,
+                         int64_t* particle_id);
+int32_t pb_particles_remove_deleted(pb_engine* e, int64_t* n_left);
+
 /* ---- the hot path: replaces Kernel.execute(pset, endtime, dt) (_core/kernel.py:174-247) -- */
 typedef struct pb_advect_args {
     int32_t scheme;            /* enum pb_scheme                                                */

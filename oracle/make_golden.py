@@ -238,6 +238,77 @@ def make_ref_cases():
     np.savez_compressed(os.path.join(GOLDEN, "ref_cases.npz"), **out)
 
 
+OUTPUT_CASES = {"delayed_partial": 300.0, "flat_f32c_f64d": 30.0, "backward": None}
+
+
+def make_output_golden():
+    """ParticleFile.write's row selection (reference _core/particlefile.py:198-221), run by the reference itself:
+    (1) the rule on seeded vectors, (2) the rows an execute() with an output file writes, per output time."""
+    import cases as tc
+    from oracle import ref_harness as rh
+
+    rh.install()
+    from parcels._core.particlefile import _to_write_particles
+
+    out = {}
+    rng = np.random.default_rng(77)
+    n = 4000
+    t = np.round(rng.uniform(-50, 250, n), 1)
+    t[rng.uniform(size=n) < 0.05] = np.nan
+    t[rng.uniform(size=n) < 0.02] = np.inf
+    dt = np.where(rng.uniform(size=n) < 0.5, 10.0, -10.0)
+    pid = np.arange(n, dtype=np.int64)
+    out["rule/t"], out["rule/dt"] = t, dt
+    for k, tout in enumerate((0.0, 95.0, 100.0, 104.9, 105.0, 250.0)):
+        out[f"rule/tout{k}"] = np.array(tout)
+        out[f"rule/rows{k}"] = _to_write_particles({"t": t, "dt": dt, "particle_id": pid}, tout)
+
+    class Recorder:
+        path = "memory"
+
+        def __init__(self, outputdt):
+            self.outputdt, self.metadata, self.rows = outputdt, {}, []
+
+        def set_metadata(self, mesh):
+            pass
+
+        def write(self, pset, time):
+            d = pset._data
+            rows = _to_write_particles(d, time)
+            self.rows.append((time, {k: d[k][rows].copy() for k in ("particle_id", "t", "x", "y", "z")}))
+
+        def __enter__(self):
+            return self
+
+        def __exit__(self, *a):
+            pass
+
+    k = rh.kernels()
+
+    def DeleteParticle(particles, fieldset):
+        particles[particles.state >= 50].state = 30
+
+    for name, outputdt in OUTPUT_CASES.items():
+        c = tc.build(tc.CASES[name])
+        if outputdt is None:
+            outputdt = 3 * abs(c["dt"])
+        fs = rh.build_fieldset(lon=c["lon"], lat=c["lat"], depth=c["depth"], times=c["times"], U=c["U"], V=c["V"], W=c["W"],
+                               mesh=c["mesh"], constants=c["constants"], interp=c.get("interp", "linear"),
+                               padding=c.get("padding", ("low", "low", "high")))  # fmt: skip
+        ps = rh.make_pset(fs, x=c["x"], y=c["y"], z=c["z"], t=c["t"])
+        kern = [getattr(k, kn) for kn in c["kernels"]] + ([DeleteParticle] if c["delete_on_error"] else [])
+        rec = Recorder(outputdt)
+        seg = c["segments"][0]
+        ps.execute(kern, dt=c["dt"], output_file=rec, verbose_progress=False, **seg)
+        out[f"{name}/outputdt"] = np.array(outputdt)
+        out[f"{name}/times"] = np.array([r[0] for r in rec.rows])
+        for i, (_, cols) in enumerate(rec.rows):
+            for key, v in cols.items():
+                out[f"{name}/{i}/{key}"] = v
+        print(f"output {name}: {len(rec.rows)} writes, rows {[len(r[1]['t']) for r in rec.rows]}")
+    np.savez_compressed(os.path.join(GOLDEN, "output_rows.npz"), **out)
+
+
 if __name__ == "__main__":
     os.makedirs(GOLDEN, exist_ok=True)
     make_v3("linear", "v3_jit_linear.npz")
@@ -245,3 +316,4 @@ if __name__ == "__main__":
     make_v3("freeslip", "v3_jit_freeslip.npz")
     make_v3("nearest", "v3_jit_nearest.npz")
     make_ref_cases()
+    make_output_golden()

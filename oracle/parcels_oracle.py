@@ -638,6 +638,20 @@ def kernel_execute(pdata, fs: OFieldSet, kernels, endtime, dt, max_iters=None):
     return nsteps
 
 
+def to_write_particles(pdata, t):
+    """_core/particlefile.py:198-221 (``_to_write_particles``): rows written at output time ``t``."""
+    fin = np.isfinite(pdata["t"])
+    return np.where(
+        (
+            np.less_equal(t - np.abs(pdata["dt"] / 2), pdata["t"], where=fin, out=None)
+            & np.greater_equal(t + np.abs(pdata["dt"] / 2), pdata["t"], where=fin, out=None)
+            | (np.isnan(pdata["dt"]) & np.equal(t, pdata["t"], where=fin, out=None))
+        )
+        & np.isfinite(pdata["particle_id"])
+        & fin
+    )[0]
+
+
 def pset_execute(pdata, fs: OFieldSet, kernels, dt, runtime=None, endtime=None, outputdt=None, on_output=None):
     """_core/particleset.py:355-470 (outer loop) with float-second arguments
     (:497-585: start = first release time, or 0 / interval end when t is NaN)."""

@@ -6,6 +6,8 @@ whole per-particle time loop in hand-written sm_100a CUDA (``csrc/engine.cu``) t
 """
 
 from . import kernels
+
+__version__ = "0.1.0"
 from .fieldset import Field, FieldSet, VectorField, XGrid
 from .kernels import (
     AdvectionEE,
@@ -17,6 +19,7 @@ from .kernels import (
     DiffusionUniformKh,
 )
 from .particle import Particle, ParticleClass, Variable
+from .particlefile import ParticleFile, read_particlefile
 from .particleset import ParticleSet
 from .statuscodes import (
     FieldInterpolationError,
@@ -31,6 +34,6 @@ from .statuscodes import (
 __all__ = [
     "AdvectionEE", "AdvectionRK2", "AdvectionRK2_3D", "AdvectionRK4", "AdvectionRK4_3D", "DeleteParticle",
     "DiffusionUniformKh", "Field", "FieldInterpolationError", "FieldOutOfBoundError", "FieldOutOfBoundSurfaceError",
-    "FieldSet", "GeneralError", "GridSearchingError", "OutsideTimeInterval", "Particle", "ParticleClass", "ParticleSet", "Variable", "StatusCode",
+    "FieldSet", "GeneralError", "GridSearchingError", "OutsideTimeInterval", "Particle", "ParticleClass", "ParticleFile", "ParticleSet", "Variable", "read_particlefile", "StatusCode",
     "VectorField", "XGrid", "kernels",
 ]  # fmt: skip

@@ -92,6 +92,9 @@ SYMBOLS = {
     "pb_particles_snapshot": (C.c_int32, [_P]),
     "pb_particles_restore": (C.c_int32, [_P]),
     "pb_particles_count": (C.c_int64, [_P]),
+    "pb_output_select": (C.c_int32, [_P, C.c_double, C.c_double, C.POINTER(C.c_int64)]),
+    "pb_output_gather": (C.c_int32, [_P, C.c_int64, _P, _P, _P, _P, _P, _P]),
+    "pb_particles_remove_deleted": (C.c_int32, [_P, C.POINTER(C.c_int64)]),
     "pb_advect": (C.c_int32, [_P, C.POINTER(AdvectArgs), C.POINTER(Report)]),
     "pb_advect_async": (C.c_int32, [_P, C.POINTER(AdvectArgs)]),
     "pb_last_report": (C.c_int32, [_P, C.POINTER(Report)]),

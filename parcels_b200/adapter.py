@@ -53,4 +53,5 @@ def pset_from_parcels(ref_pset, fieldset: FieldSet, **kw) -> ParticleSet:
     d = ref_pset._data
     ps = ParticleSet(fieldset, x=d["x"], y=d["y"], z=d["z"], t=d["t"], particle_ids=d["particle_id"], **kw)
     ps._data = d  # share the reference's dict of ndarrays: results are written back in place
+    ps.eager_host = True  # ... at the end of every execute(), not on first access
     return ps

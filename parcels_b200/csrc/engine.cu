@@ -140,6 +140,103 @@ __global__ void mig_unpack(ParticlesDev dst, long long base, const MigRecord* __
     dst.t[j] = r.t; dst.state[j] = r.state; dst.ei[j] = r.ei; dst.pid[j] = r.pid;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// output path: order-preserving selection / compaction on the device.
+//   SEL_OUTPUT:  ParticleFile.write's rule (reference _core/particlefile.py:198-221, `_to_write_particles`):
+//                finite t and  t_out - |dt/2| <= t <= t_out + |dt/2|
+//   SEL_ALIVE:   state != Delete   (Kernel.remove_deleted + ParticleSet.remove_indices, kernel.py:98-106,
+//                particleset.py:247-250: np.delete keeps the storage order)
+// Three passes: per-block count, one-block scan of the block counts, per-block ordered scatter of the indices.
+// ------------------------------------------------------------------------------------------------
+enum { SEL_OUTPUT = 0, SEL_ALIVE = 1 };
+constexpr int SEL_BLOCK = 256;
+
+struct SelectRule {
+    int mode;
+    double lo, hi;  // SEL_OUTPUT: t_out -/+ |dt/2|
+};
+
+__device__ __forceinline__ bool sel_flag(const ParticlesDev& P, const SelectRule& r, long long i) {
+    if (r.mode == SEL_ALIVE) return P.state[i] != PB_DELETE;
+    const double t = P.t[i];
+    return isfinite(t) && r.lo <= t && r.hi >= t;
+}
+
+__global__ void __launch_bounds__(SEL_BLOCK) sel_count(ParticlesDev P, SelectRule r, unsigned int* __restrict__ block_counts) {
+    const long long i = (long long)blockIdx.x * SEL_BLOCK + threadIdx.x;
+    const bool f = i < P.n && sel_flag(P, r, i);
+    const int c = __syncthreads_count(f);
+    if (threadIdx.x == 0) block_counts[blockIdx.x] = (unsigned)c;
+}
+
+// exclusive scan of block_counts[0..nb) in place -> block_offsets (long long); total to *total.  One block.
+__global__ void __launch_bounds__(1024) sel_scan(const unsigned int* __restrict__ block_counts, long long* __restrict__ block_offsets,
+                                                 long long nb, long long* total) {
+    __shared__ long long warp_sums[32];
+    __shared__ long long carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (long long base = 0; base < nb; base += 1024) {
+        const long long i = base + threadIdx.x;
+        const long long v = i < nb ? (long long)block_counts[i] : 0;
+        long long incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const long long up = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += up;
+        }
+        if (lane == 31) warp_sums[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            long long w = warp_sums[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const long long up = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += up;
+            }
+            warp_sums[lane] = w;  // inclusive over warps
+        }
+        __syncthreads();
+        const long long before = carry + (warp ? warp_sums[warp - 1] : 0) + incl - v;
+        if (i < nb) block_offsets[i] = before;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = before + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = carry;
+}
+
+__global__ void __launch_bounds__(SEL_BLOCK) sel_scatter(ParticlesDev P, SelectRule r, const long long* __restrict__ block_offsets,
+                                                         long long* __restrict__ idx) {
+    __shared__ int warp_counts[SEL_BLOCK / 32];
+    const long long i = (long long)blockIdx.x * SEL_BLOCK + threadIdx.x;
+    const bool f = i < P.n && sel_flag(P, r, i);
+    const unsigned ballot = __ballot_sync(0xffffffffu, f);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) warp_counts[warp] = __popc(ballot);
+    __syncthreads();
+    if (f) {
+        int before = __popc(ballot & ((1u << lane) - 1u));
+        for (int w = 0; w < warp; ++w) before += warp_counts[w];
+        idx[block_offsets[blockIdx.x] + before] = i;
+    }
+}
+
+// compacted copies of the written columns (Particle variables with to_write: x, y, z, t, particle_id)
+__global__ void out_gather(ParticlesDev P, const long long* __restrict__ idx, long long m, float* x, float* y, float* z, double* t,
+                           long long* pid) {
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= m) return;
+    const long long i = idx[k];
+    if (x) x[k] = P.x[i];
+    if (y) y[k] = P.y[i];
+    if (z) z[k] = P.z[i];
+    if (t) t[k] = P.t[i];
+    if (pid) pid[k] = P.pid[i];
+}
+
 // ------------------------------------------------------------------------------------------------
 // host-side engine
 // ------------------------------------------------------------------------------------------------
@@ -189,6 +286,10 @@ struct pb_engine {
     // mode D (domain decomposition): alternate SoA for compaction, migration work buffers
     DevBuf ax, ay, az, adx, ady, adz, at, astate, aei, apid;
     DevBuf mdest, mkeep, mcount, mbounds;
+    // output path: block counts / offsets of the ordered selection, selected indices, compacted columns
+    DevBuf sblock, soffs, sidx, sout;
+    long long* h_sel_total = nullptr;  // pinned
+    long long n_selected = -1;
     int nranks = 1, rank = 0;
     long long n_keep = 0, n_send = 0;
     std::vector<long long> send_counts;
@@ -242,6 +343,7 @@ int32_t pb_engine_create(int32_t device, pb_engine** out) {
     CK(cudaEventCreate(&e->tev1));
     CK(cudaMalloc(&e->d_rep, sizeof(ReportDev)));
     CK(cudaMallocHost(&e->h_rep, sizeof(ReportDev)));
+    CK(cudaMallocHost(&e->h_sel_total, sizeof(long long)));
     *out = e;
     return PB_OK;
 }
@@ -258,6 +360,7 @@ void pb_engine_destroy(pb_engine* e) {
         b->release();
     if (e->d_rep) cudaFree(e->d_rep);
     if (e->h_rep) cudaFreeHost(e->h_rep);
+    if (e->h_sel_total) cudaFreeHost(e->h_sel_total);
     cudaEventDestroy(e->ev0);
     cudaEventDestroy(e->ev1);
     cudaStreamDestroy(e->copy_stream);
@@ -788,6 +891,102 @@ int32_t pb_decomp_set(pb_engine* e, int32_t nranks, int32_t rank, const double* 
 static ParticlesDev cur_particles(pb_engine* e) {
     return ParticlesDev{(float*)e->px.p, (float*)e->py.p, (float*)e->pz.p, (float*)e->pdx.p, (float*)e->pdy.p,
                         (float*)e->pdz.p, (double*)e->pt.p, (int*)e->pstate.p, (int*)e->pei.p, (long long*)e->ppid.p, e->n};
+}
+
+// ordered selection of the resident particles: indices to e->sidx, count returned
+static int32_t run_select(pb_engine* e, const SelectRule& r, long long* n_sel) {
+    CK(cudaSetDevice(e->device));
+    *n_sel = 0;
+    if (e->n == 0) return PB_OK;
+    const long long nb = (e->n + SEL_BLOCK - 1) / SEL_BLOCK;
+    int32_t rc;
+    if ((rc = e->sblock.ensure((size_t)nb * 4))) return rc;
+    if ((rc = e->soffs.ensure((size_t)(nb + 1) * 8))) return rc;
+    if ((rc = e->sidx.ensure((size_t)e->n * 8))) return rc;
+    const ParticlesDev P = cur_particles(e);
+    sel_count<<<(unsigned)nb, SEL_BLOCK, 0, e->stream>>>(P, r, (unsigned int*)e->sblock.p);
+    CK(cudaGetLastError());
+    long long* offs = (long long*)e->soffs.p;
+    sel_scan<<<1, 1024, 0, e->stream>>>((const unsigned int*)e->sblock.p, offs, nb, offs + nb);
+    CK(cudaGetLastError());
+    sel_scatter<<<(unsigned)nb, SEL_BLOCK, 0, e->stream>>>(P, r, offs, (long long*)e->sidx.p);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(e->h_sel_total, offs + nb, 8, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    *n_sel = *e->h_sel_total;
+    return PB_OK;
+}
+
+int32_t pb_output_select(pb_engine* e, double t_out, double dt, int64_t* n_selected) {
+    if (!e || !n_selected) return fail(PB_ERR_INVALID, "NULL argument");
+    if (e->pending) return fail(PB_ERR_STATE, "an advect call is pending: call pb_last_report first");
+    const double half = fabs(dt / 2);
+    long long m = 0;
+    int32_t rc = run_select(e, SelectRule{SEL_OUTPUT, t_out - half, t_out + half}, &m);
+    if (rc) return rc;
+    e->n_selected = m;
+    *n_selected = m;
+    return PB_OK;
+}
+
+int32_t pb_output_gather(pb_engine* e, int64_t n_selected, int64_t* index, float* x, float* y, float* z, double* t,
+                         int64_t* particle_id) {
+    if (!e) return fail(PB_ERR_INVALID, "engine is NULL");
+    if (e->n_selected < 0 || n_selected != e->n_selected)
+        return fail(PB_ERR_STATE, "gather of %lld rows but the last pb_output_select chose %lld", (long long)n_selected, e->n_selected);
+    if (particle_id && !e->have_pid && n_selected) return fail(PB_ERR_STATE, "no particle ids resident");
+    if (n_selected == 0) return PB_OK;
+    CK(cudaSetDevice(e->device));
+    const size_t m = (size_t)n_selected;
+    int32_t rc = e->sout.ensure(m * 28);  // x, y, z (4 B) + t, particle_id (8 B)
+    if (rc) return rc;
+    char* o = (char*)e->sout.p;
+    double* dt_ = (double*)o;                 // 8-byte columns first: keeps every column aligned
+    long long* dpid = (long long*)(o + m * 8);
+    float* dx = (float*)(o + m * 16);
+    float* dy = dx + m;
+    float* dz = dy + m;
+    out_gather<<<(unsigned)((m + 255) / 256), 256, 0, e->stream>>>(cur_particles(e), (const long long*)e->sidx.p, (long long)m,
+                                                                  x ? dx : nullptr, y ? dy : nullptr, z ? dz : nullptr,
+                                                                  t ? dt_ : nullptr, particle_id ? dpid : nullptr);
+    CK(cudaGetLastError());
+    if (x) CK(cudaMemcpyAsync(x, dx, m * 4, cudaMemcpyDeviceToHost, e->stream));
+    if (y) CK(cudaMemcpyAsync(y, dy, m * 4, cudaMemcpyDeviceToHost, e->stream));
+    if (z) CK(cudaMemcpyAsync(z, dz, m * 4, cudaMemcpyDeviceToHost, e->stream));
+    if (t) CK(cudaMemcpyAsync(t, dt_, m * 8, cudaMemcpyDeviceToHost, e->stream));
+    if (particle_id) CK(cudaMemcpyAsync(particle_id, dpid, m * 8, cudaMemcpyDeviceToHost, e->stream));
+    if (index) CK(cudaMemcpyAsync(index, e->sidx.p, m * 8, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return PB_OK;
+}
+
+int32_t pb_particles_remove_deleted(pb_engine* e, int64_t* n_left) {
+    if (!e || !n_left) return fail(PB_ERR_INVALID, "NULL argument");
+    if (e->pending) return fail(PB_ERR_STATE, "an advect call is pending: call pb_last_report first");
+    if (!e->have_pid && e->n) return fail(PB_ERR_STATE, "compaction needs particle_id resident");
+    long long keep = 0;
+    int32_t rc = run_select(e, SelectRule{SEL_ALIVE, 0.0, 0.0}, &keep);
+    if (rc) return rc;
+    e->n_selected = -1;
+    if (keep == e->n) { *n_left = keep; return PB_OK; }
+    const size_t cap = keep ? (size_t)keep : 1;
+    DevBuf* alt[10] = {&e->ax, &e->ay, &e->az, &e->adx, &e->ady, &e->adz, &e->at, &e->astate, &e->aei, &e->apid};
+    DevBuf* cur[10] = {&e->px, &e->py, &e->pz, &e->pdx, &e->pdy, &e->pdz, &e->pt, &e->pstate, &e->pei, &e->ppid};
+    const size_t es[10] = {4, 4, 4, 4, 4, 4, 8, 4, 4, 8};
+    for (int k = 0; k < 10; ++k)
+        if ((rc = alt[k]->ensure(cap * es[k]))) return rc;
+    ParticlesDev dst{(float*)e->ax.p, (float*)e->ay.p, (float*)e->az.p, (float*)e->adx.p, (float*)e->ady.p, (float*)e->adz.p,
+                     (double*)e->at.p, (int*)e->astate.p, (int*)e->aei.p, (long long*)e->apid.p, keep};
+    if (keep > 0) {
+        mig_compact<<<(unsigned)((keep + 255) / 256), 256, 0, e->stream>>>(cur_particles(e), dst, (const long long*)e->sidx.p, keep);
+        CK(cudaGetLastError());
+    }
+    CK(cudaStreamSynchronize(e->stream));
+    for (int k = 0; k < 10; ++k) std::swap(*cur[k], *alt[k]);
+    e->n = keep;
+    e->n_keep = keep;
+    *n_left = keep;
+    return PB_OK;
 }
 
 int32_t pb_migrate_count(pb_engine* e, int64_t* counts) {

@@ -137,6 +137,29 @@ class Engine:
             )
         )  # fmt: skip
 
+    # -- output path (device-side ParticleFile.write selection, ordered compaction) -----------------
+    OUTPUT_COLUMNS = {"x": np.float32, "y": np.float32, "z": np.float32, "t": np.float64, "particle_id": np.int64}
+
+    def output_select(self, t_out: float, dt: float) -> int:
+        m = C.c_int64()
+        check(self._lib.pb_output_select(self._h, float(t_out), float(dt), C.byref(m)))
+        return int(m.value)
+
+    def output_gather(self, n_selected: int, columns=("x", "y", "z", "t", "particle_id"), with_index=False) -> dict:
+        out = {k: np.empty(n_selected, dtype=self.OUTPUT_COLUMNS[k]) for k in columns}
+        idx = np.empty(n_selected, dtype=np.int64) if with_index else None
+        p = lambda k: ptr(out[k]) if k in out else None  # noqa: E731
+        check(self._lib.pb_output_gather(self._h, n_selected, None if idx is None else ptr(idx), p("x"), p("y"), p("z"), p("t"),
+                                         p("particle_id")))  # fmt: skip
+        if with_index:
+            out["index"] = idx
+        return out
+
+    def remove_deleted(self) -> int:
+        m = C.c_int64()
+        check(self._lib.pb_particles_remove_deleted(self._h, C.byref(m)))
+        return int(m.value)
+
     def snapshot(self):
         check(self._lib.pb_particles_snapshot(self._h))
 

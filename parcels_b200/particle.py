@@ -17,11 +17,30 @@ _CORE = (
 )  # fmt: skip
 
 
-class Variable:
-    """reference _core/particle.py:20-60 (name, dtype, initial)."""
+# file attributes of the written core variables (reference _core/particle.py:128-170)
+_CORE_ATTRS = {
+    "t": {"standard_name": "time", "units": "seconds", "axis": "T"},
+    "z": {"standard_name": "vertical coordinate", "units": "m", "positive": "down"},
+    "y": {"standard_name": "latitude", "units": "degrees_north", "axis": "Y"},
+    "x": {"standard_name": "longitude", "units": "degrees_east", "axis": "X"},
+    "particle_id": {"long_name": "Unique identifier for each particle", "cf_role": "trajectory_id"},
+}
 
-    def __init__(self, name, dtype=np.float32, initial=0, **_ignored):
-        self.name, self.dtype, self.initial = name, np.dtype(dtype), initial
+
+class Variable:
+    """reference _core/particle.py:20-66 (name, dtype, initial, to_write, attrs)."""
+
+    def __init__(self, name, dtype=np.float32, initial=0, to_write=True, attrs=None):
+        try:
+            dtype = np.dtype(dtype)
+        except (TypeError, ValueError) as e:
+            raise TypeError(f"Variable dtype must be a valid numpy dtype. Got {dtype=!r}") from e
+        if to_write not in (True, False):
+            raise ValueError(f"to_write must be one of [True, False]. Got {to_write=!r}")
+        attrs = {} if attrs is None else attrs
+        if not to_write and attrs != {}:
+            raise ValueError(f"Attributes cannot be set if {to_write=!r}.")
+        self.name, self.dtype, self.initial, self.to_write, self.attrs = name, dtype, initial, to_write, attrs
 
 
 class ParticleClass:
@@ -35,6 +54,11 @@ class ParticleClass:
     @property
     def variables(self):
         return _CORE + tuple((v.name, v.dtype) for v in self.extra)
+
+    def written_variables(self):
+        """Variables with ``to_write`` (reference _core/particlefile.py:193-194), in declaration order."""
+        core = [Variable(n, d, attrs=dict(_CORE_ATTRS[n])) for n, d in _CORE if n in _CORE_ATTRS]
+        return core + [v for v in self.extra if v.to_write]
 
     def add_variable(self, variable):
         new = [variable] if isinstance(variable, Variable) else list(variable)

@@ -130,6 +130,13 @@ class ParticleSet:
         self.seed = int(seed)  # Philox key of the Wiener increments (DiffusionUniformKh)
         self._rng_call = 0
         self._device_synced = False
+        # Device-resident intervals: between the output intervals of one execute() call the particle
+        # SoA lives in HBM only; the host arrays are refreshed on first access (the `_data` property).
+        self._host = None
+        self._host_stale = False
+        self.eager_host = False  # True: refresh the host arrays at the end of every execute() (shared-array adapters)
+        self._n_device = 0
+        self._stale_dt = 1.0
         self.last_report = None
         y = np.empty(0) if y is None else np.array(y).flatten()
         x = np.empty(0) if x is None else np.array(x).flatten()
@@ -167,12 +174,66 @@ class ParticleSet:
                 raise RuntimeError(f"Particle class does not have Variable {k}")
             self._data[k][:] = np.array(v).flatten()
 
+    # -- host mirror of the particle SoA --------------------------------------------------------
+    @property
+    def _data(self):
+        if self._host_stale:
+            self._sync_host()
+        return self._host
+
+    @_data.setter
+    def _data(self, value):
+        self._host = value
+        self._host_stale = False
+
+    def _sync_host(self):
+        """Bring the host arrays up to date with the device-resident set (sizes may differ after deletions)."""
+        eng = self.fieldset.engine(self.device)
+        d = self._host
+        if d is not None and len(d["x"]) == eng.particle_count():
+            # nothing was deleted: ids and order are unchanged, refresh the existing (possibly pinned) arrays in place
+            ei_last = np.empty(len(d["x"]), dtype=np.int32)
+            eng.download_particles(d, ei_last)
+            d["ei"][:, -1] = ei_last
+        else:
+            new = eng.download_all(ngrids=len(self.fieldset.gridset))
+            if d is None:
+                d = new
+            else:  # keep the dict object: it may be shared with the caller (adapter.pset_from_parcels)
+                d.update(new)
+        d["dt"][:] = self._stale_dt  # kernel.py:225-226
+        self._host = d
+        self._host_stale = False
+        self._device_synced = True
+
+    def _lazy_ok(self, plan) -> bool:
+        """Can the set stay device-resident across output intervals?  Built-in kernel lists on rectilinear grids with
+        the default Particle variables (extra variables live on the host; the curvilinear hint test needs host `ei`)."""
+        fs = self.fieldset
+        return not plan.stepwise and not fs.grid.curvilinear and fs.time_window is None and len(self._pclass.extra) == 0
+
+    def _output_columns(self, t, names, indices=None):
+        """Rows due for output at time ``t`` (reference `_to_write_particles`, _core/particlefile.py:198-221) of the
+        columns ``names`` -> (dict of compacted arrays, selected_on_device)."""
+        from .engine import Engine
+        from .particlefile import to_write_particles
+
+        if self._host_stale and indices is None and all(n in Engine.OUTPUT_COLUMNS for n in names):
+            eng = self.fieldset.engine(self.device)
+            m = eng.output_select(t, self._stale_dt)
+            return eng.output_gather(m, columns=tuple(names)), True
+        d = self._data
+        rows = to_write_particles(d, t) if indices is None else indices
+        return {n: d[n][rows] for n in names}, False
+
     # -- container protocol ----------------------------------------------------------------------
     def __len__(self):
-        return len(self._data["x"])
+        return self._n_device if self._host_stale else len(self._host["x"])
 
     def __getattr__(self, name):
-        data = self.__dict__.get("_data")
+        if name.startswith("_"):
+            raise AttributeError(name)
+        data = self._data if "_host" in self.__dict__ else None
         if data is not None and name in data:
             return data[name]
         raise AttributeError(name)
@@ -187,29 +248,40 @@ class ParticleSet:
             self._data[k] = np.delete(self._data[k], indices, axis=0)
 
     # -- the hot path ------------------------------------------------------------------------------
-    def _kernel_execute(self, plan: KernelPlan, endtime: float, dt: float, *, resident: bool = False):
+    def _kernel_execute(self, plan: KernelPlan, endtime: float, dt: float, *, resident: bool = False, lazy: bool = False):
         """Replaces ``Kernel.execute(pset, endtime, dt)`` (reference _core/kernel.py:174-247).
 
         ``resident=True`` (set by ``execute`` for the 2nd, 3rd, ... output interval of ONE call): the device
         copy of the particle SoA left by the previous interval is still exact -- nothing on the host can have
-        changed it in between -- so the host->device upload is skipped."""
-        d = self._data
-        n = len(self)
+        changed it in between -- so the host->device upload is skipped.
+
+        ``lazy=True`` (``_lazy_ok``): the result is NOT downloaded either; deleted particles are compacted on the
+        device and the host arrays are refreshed only when somebody reads them (``_data``)."""
         if plan.stepwise:
             from .stepwise import kernel_execute_stepwise
 
-            if n and np.isnan(d["t"]).any():
+            d = self._data
+            if len(self) and np.isnan(d["t"]).any():
                 raise ValueError("Time values cannot be NaN.")
             self._device_synced = False
             return kernel_execute_stepwise(self, plan, endtime, dt)
-        d["state"][:] = StatusCode.Evaluate
-        if n == 0:
-            return
-        if np.isnan(d["t"]).any():
-            bad = np.where(np.isnan(d["t"]))[0]
-            raise ValueError(f"Time values for particles with indices {bad} cannot be NaN.")  # field.py:396-398
         eng = self.fieldset.engine(self.device)
-        ei_last = np.ascontiguousarray(d["ei"][:, -1])
+        on_device = lazy and resident and self._host_stale and eng.particle_count() == self._n_device
+        if on_device:
+            # states are reset to Evaluate by the kernel itself (resume = 0); t cannot have become NaN on the device
+            n, d, ei_last = self._n_device, None, None
+            if n == 0:
+                return
+        else:
+            d = self._data
+            n = len(self)
+            d["state"][:] = StatusCode.Evaluate
+            if n == 0:
+                return
+            if np.isnan(d["t"]).any():
+                bad = np.where(np.isnan(d["t"]))[0]
+                raise ValueError(f"Time values for particles with indices {bad} cannot be NaN.")  # field.py:396-398
+            ei_last = np.ascontiguousarray(d["ei"][:, -1])
         self._rng_call += 1
         hint_all_zero = False
         g = self.fieldset.grid
@@ -225,29 +297,46 @@ class ParticleSet:
                                  kh=plan.kh, kh_spherical=plan.kh_spherical, kh_deg2m=plan.kh_deg2m, seed=self.seed,
                                  rng_call=self._rng_call, max_iters=max_iters, hint_all_zero=hint_all_zero)  # fmt: skip
 
-        if not (resident and self._device_synced and eng.particle_count() == n):
+        if not on_device and not (resident and self._device_synced and eng.particle_count() == n):
             eng.upload_particles(d, ei_last)
         self._device_synced = False
+        # start-of-interval state for the error replay: the host arrays, or (device-resident) a snapshot in HBM
+        can_raise = not plan.delete_on_error
+        if lazy and can_raise:
+            eng.snapshot()
+        rewind = eng.restore if lazy else (lambda: eng.upload_particles(d, ei_last))
         if self.fieldset.time_window is not None:
             rep = self._advect_windowed(eng, plan, d, dt, endtime, args)
         else:
             rep = eng.advect(args())
         if rep["n_error"] > 0 and self.fieldset.time_window is None:
             # The reference stops the whole set at the END of the first loop iteration in which any
-            # particle is in an error state (kernel.py:239-245).  Replay from the host copy up to and
-            # including that iteration so every particle is left exactly where the reference leaves it.
+            # particle is in an error state (kernel.py:239-245).  Replay from the start-of-interval copy up to
+            # and including that iteration so every particle is left exactly where the reference leaves it.
             k = rep["first_error_iter"]
-            eng.upload_particles(d, ei_last)
+            rewind()
             rep = eng.advect(args(max_iters=k + 1))
             if rep["n_out_of_time"] > 0:
                 # an out-of-interval sample flags the WHOLE evaluated view (index_search.py:85-86, field.py:31-44)
-                eng.upload_particles(d, ei_last)
+                rewind()
                 eng.advect(args(max_iters=k))
                 eng.flag_view_outside_time(dt, endtime)
         self.last_report = rep
-        eng.download_particles(d, ei_last)
-        d["ei"][:, -1] = ei_last
-        d["dt"][:] = dt  # kernel.py:225-226
+        self._stale_dt = dt
+        if lazy and rep["max_state"] < StatusCode.Error:
+            # nothing to raise: stay in HBM.  Deleted particles are dropped there, order preserved
+            # (Kernel.remove_deleted -> np.delete, kernel.py:98-106, particleset.py:247-250)
+            self._n_device = eng.remove_deleted() if (rep["n_deleted"] > 0 or rep["max_state"] == StatusCode.Delete) else n
+            self._host_stale = True
+            return
+        if lazy:
+            self._host_stale = True
+            self._n_device = n
+            d = self._data  # full download
+        else:
+            eng.download_particles(d, ei_last)
+            d["ei"][:, -1] = ei_last
+            d["dt"][:] = dt  # kernel.py:225-226
         # the device report says whether any particle was deleted / errored: the O(N) host scans of
         # kernel.py:98-106,239-245 only run when there is something to find
         self._device_synced = True  # host arrays == device arrays from here on (until the host compacts them)
@@ -333,6 +422,9 @@ class ParticleSet:
         if np.isnan(t).any():
             t[:] = start_time
         outputdt = _to_float_seconds(output_file.outputdt) if output_file is not None else None
+        if output_file is not None and hasattr(output_file, "set_metadata"):  # reference particleset.py:400-403
+            output_file.set_metadata(self.fieldset.grid.mesh)
+            output_file.metadata["parcels_kernels"] = plan.funcname
         next_output = None
         if output_file is not None:
             output_file.write(self, start_time)
@@ -340,15 +432,22 @@ class ParticleSet:
         time = start_time
         interval = 0
         self._device_synced = False  # between execute() calls the host owns the arrays
-        while sign_dt * (time - end_time) < 0:
-            if next_output is not None:
-                next_time = min(next_output, end_time) if sign_dt > 0 else max(next_output, end_time)
-            else:
-                next_time = end_time
-            self._kernel_execute(plan, next_time, dt, resident=interval > 0)
-            interval += 1
-            if next_output is not None and np.abs(next_time - next_output) < 0.001:
-                output_file.write(self, next_output)
-                if np.isfinite(outputdt):
-                    next_output += outputdt * sign_dt
-            time = next_time
+        lazy = self._lazy_ok(plan)
+        try:
+            while sign_dt * (time - end_time) < 0:
+                if next_output is not None:
+                    next_time = min(next_output, end_time) if sign_dt > 0 else max(next_output, end_time)
+                else:
+                    next_time = end_time
+                self._kernel_execute(plan, next_time, dt, resident=interval > 0, lazy=lazy)
+                interval += 1
+                if next_output is not None and np.abs(next_time - next_output) < 0.001:
+                    output_file.write(self, next_output)
+                    if np.isfinite(outputdt):
+                        next_output += outputdt * sign_dt
+                time = next_time
+        finally:
+            if output_file is not None and hasattr(output_file, "close"):  # `with output_file:` (particleset.py:444)
+                output_file.close()
+        if self.eager_host and self._host_stale:
+            self._sync_host()
