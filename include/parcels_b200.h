@@ -20,6 +20,7 @@ extern "C" {
 #endif
 
 #define PB_ABI_VERSION 1
+#define PB_MAX_FIELDS 16 /* field slots per engine: 0..2 = U, V, W; 3.. = scalar fields */
 
 typedef struct pb_engine pb_engine;
 
@@ -234,6 +235,18 @@ int32_t pb_last_report(pb_engine* e, pb_report* rep);
 int32_t pb_sample_velocity(pb_engine* e, int64_t n, const double* t, const double* z, const double* y, const double* x,
                            int32_t positions_are_f32, int32_t three_d, const int32_t* ei_hint, int32_t no_hint,
                            double* u, double* v, double* w, int32_t* ei_out, int32_t* state_out);
+
+/* ---- scalar sampling: replaces Field.eval / fieldset.P[particles] (_core/field.py:144-202) for fields on the
+ * rectilinear grid.  Scalar fields live in slots 3 .. PB_MAX_FIELDS-1 of pb_field_upload (0..2 are U, V, W);
+ * a field with one time level has no time dimension (no time search, field.py:112-117).  method: the field's
+ * ScalarInterpolator -- XLinear (_xinterpolators.py:112-153), XNearest (:515-560) or CGrid_Tracer (:335-383, uses
+ * the staggering offsets of pb_set_interpolation).  Index search, `ei` write-back and state codes are those of
+ * pb_sample_velocity; out-of-bounds samples are 0.  value_is_f32 (optional): 1 where NumPy's promotion makes the
+ * reference's value float32 (the value returned is that float32 number, widened). */
+enum pb_scalar_interp { PB_SCALAR_XLINEAR = 0, PB_SCALAR_XNEAREST = 1, PB_SCALAR_CGRID_TRACER = 2 };
+int32_t pb_sample_scalar(pb_engine* e, int32_t slot, int32_t method, int64_t n, const double* t, const double* z,
+                         const double* y, const double* x, int32_t positions_are_f32, const int32_t* ei_hint,
+                         double* value, int32_t* value_is_f32, int32_t* ei_out, int32_t* state_out);
 
 /* ---- multi-GPU mode D: X-slab domain decomposition with particle migration ------------
  * The reference has no distributed layer; this is new.  Each rank's engine holds the columns

@@ -309,6 +309,43 @@ def make_output_golden():
     np.savez_compressed(os.path.join(GOLDEN, "output_rows.npz"), **out)
 
 
+SCALAR_CASES = ("c2_small", "flat_f32c_f64d", "all_f32", "cgrid_rect_3d")
+
+
+def scalar_inputs(c, T, seed=3):
+    """The scalar field + sample times used by the scalar-eval fixtures (shared with the tests)."""
+    rng = np.random.default_rng(seed)
+    P = rng.uniform(-1, 1, (T,) + c["U"].shape[1:]).astype(c["U"].dtype)
+    tq = np.asarray(c["t"], dtype=np.float64) + (0.37 * c["times"][-1] if c["times"] is not None else 0.0)
+    return P, tq
+
+
+def make_scalar_golden():
+    """Field.eval of the reference (XLinear / XNearest / CGrid_Tracer, with and without a time dimension)."""
+    import warnings
+
+    import cases as tc
+    from oracle import ref_harness as rh
+
+    out = {}
+    for name in SCALAR_CASES:
+        c = tc.build(tc.CASES[name])
+        for T in (c["U"].shape[0], 1):
+            P, tq = scalar_inputs(c, T)
+            for how in ("linear", "nearest", "cgrid_tracer"):
+                fs = rh.build_fieldset(lon=c["lon"], lat=c["lat"], depth=c["depth"], times=c["times"], U=c["U"], V=c["V"],
+                                       W=c["W"], mesh=c["mesh"], padding=c.get("padding", ("low", "low", "high")),
+                                       interp=c.get("interp", "linear"), scalars={"P": (P, how)})  # fmt: skip
+                ps = rh.make_pset(fs, x=c["x"], y=c["y"], z=c["z"], t=c["t"])
+                with warnings.catch_warnings():
+                    warnings.simplefilter("ignore")
+                    val = fs.P.eval(tq, ps._data["z"], ps._data["y"], ps._data["x"], ps)
+                key = f"{name}/T{T}/{how}"
+                out[f"{key}/value"], out[f"{key}/state"], out[f"{key}/ei"] = val, ps._data["state"].copy(), ps._data["ei"].copy()
+        print(f"scalar {name}: done")
+    np.savez_compressed(os.path.join(GOLDEN, "scalar_eval.npz"), **out)
+
+
 if __name__ == "__main__":
     os.makedirs(GOLDEN, exist_ok=True)
     make_v3("linear", "v3_jit_linear.npz")
@@ -317,3 +354,4 @@ if __name__ == "__main__":
     make_v3("nearest", "v3_jit_nearest.npz")
     make_ref_cases()
     make_output_golden()
+    make_scalar_golden()

@@ -451,6 +451,52 @@ def eval_uvw(fs: OFieldSet, t, z, y, x, view: View | None, want3d: bool):
         return (0, 0, 0) if want3d else (0, 0)
 
 
+def cgrid_tracer(fs: OFieldSet, data, ti, tau, zi, yi, xi):
+    """_xinterpolators.py:335-383 (``CGrid_Tracer``): constant over the cell (the tracer point), linear in time."""
+    T, Z, Y, X = data.shape
+    off = fs.grid.offsets
+    zi = np.clip(zi + off["Z"], 0, Z - 1)
+    yi = np.clip(yi + off["Y"], 0, Y - 1)
+    xi = np.clip(xi + off["X"], 0, X - 1)
+    c0 = _take(data, ti, zi, yi, xi)
+    if bool(np.any(tau > 0)):
+        return c0 * (1 - tau) + _take(data, np.clip(ti + 1, 0, T - 1), zi, yi, xi) * tau
+    return c0
+
+
+def eval_scalar(fs: OFieldSet, data, method, t, z, y, x, view: View | None):
+    """_core/field.py:144-202 (``Field.eval`` + the error mapping of ``__getitem__``) for a scalar field ``data``
+    (T, Z, Y, X) on the fieldset's grid; ``method``: "linear" (XLinear), "nearest" (XNearest), "cgrid_tracer".
+    A field with one time level has no time dimension (field.py:112-117)."""
+    try:
+        ei = None if view is None else view.ei[:, -1]
+        z, y, x = np.atleast_1d(z), np.atleast_1d(y), np.atleast_1d(x)
+        if np.any(np.isnan(t)):
+            raise ValueError("Time values cannot be NaN")
+        ti, tau = search_time(fs.time if data.shape[0] > 1 else None, t)
+        (zi, zeta), (yi, eta), (xi, xsi) = grid_search(fs.grid, z, y, x, ei)
+        if view is not None:
+            e = view.ei
+            e[:, -1] = ravel_index(fs.grid, zi, yi, xi)
+            view.ei = e
+        _flag_positions(view, zi, yi, xi)
+        if method == "linear":
+            value = xlinear(data, ti, tau, zi, zeta, yi, eta, xi, xsi)
+        elif method == "nearest":
+            value = xnearest(data, ti, tau, zi, zeta, yi, eta, xi, xsi)
+        else:
+            value = cgrid_tracer(fs, data, ti, tau, zi, yi, xi)
+        if view is not None and view.n() > 0:
+            view.state = np.maximum(np.where(np.isnan(value), ERROR_INTERPOLATION, view.state), view.state)
+        oob = (xi < 0) | (yi < 0) | (zi < 0)
+        if np.any(oob):
+            value[oob] = 0.0
+        return value
+    except OutsideTimeInterval:
+        view.state = ERROR_OUTSIDE_TIME_INTERVAL
+        return 0
+
+
 def eval_constant(fs: OFieldSet, name, view: View):
     """``fieldset.Kh_zonal[particles]`` on the constant-field grid (lon=[0], lat=[0], no depth;
     _core/model.py:292-318): the grid search returns index 0 everywhere (index_search.py:45-46),

@@ -257,6 +257,7 @@ def build_fieldset(
     interp="linear",
     constants: dict[str, float] | None = None,
     radius=None,
+    scalars: dict | None = None,
 ):
     """Duck FieldSet around the reference's real ``Field``/``VectorField``/``XGrid``/interpolators.
 
@@ -284,11 +285,23 @@ def build_fieldset(
     data = {"U": DataArray(U, dims=dims, coords=coords), "V": DataArray(V, dims=dims, coords=coords)}
     if W is not None:
         data["W"] = DataArray(W, dims=dims, coords=coords)
+    # scalar fields on the same grid: name -> (array (T, Z, Y, X), "linear" | "nearest" | "cgrid_tracer")
+    smethod = {}
+    for sname, (sarr, how) in (scalars or {}).items():
+        sarr = np.asarray(sarr)
+        if sarr.shape[0] > 1:
+            data[sname] = DataArray(sarr, dims=("time", zname, "YG", "XG"), coords=coords)
+        else:
+            data[sname] = DataArray(sarr, dims=("mockT", zname, "YG", "XG"))
+        smethod[sname] = how
     model = _Model(grid, data, ti)
     fields = {}
+    from parcels.interpolators._xinterpolators import CGrid_Tracer
+    from parcels.interpolators._xinterpolators import XNearest as _XNearest
+
     for name in data:
         f = Field(name, model)
-        f.interp_method = XLinear()
+        f.interp_method = {"linear": XLinear, "nearest": _XNearest, "cgrid_tracer": CGrid_Tracer}[smethod.get(name, "linear")]()
         fields[name] = f
     from parcels.interpolators._base import VectorInterpolator
     from parcels.interpolators._xinterpolators import XFreeslip, XNearest, XPartialslip

@@ -99,6 +99,7 @@ SYMBOLS = {
     "pb_advect_async": (C.c_int32, [_P, C.POINTER(AdvectArgs)]),
     "pb_last_report": (C.c_int32, [_P, C.POINTER(Report)]),
     "pb_sample_velocity": (C.c_int32, [_P, C.c_int64, _P, _P, _P, _P, C.c_int32, C.c_int32, _P, C.c_int32, _P, _P, _P, _P, _P]),
+    "pb_sample_scalar": (C.c_int32, [_P, C.c_int32, C.c_int32, C.c_int64, _P, _P, _P, _P, C.c_int32, _P, _P, _P, _P, _P]),
     "pb_decomp_set": (C.c_int32, [_P, C.c_int32, C.c_int32, _P, C.c_int64, C.c_int32, C.c_int32]),
     "pb_migrate_count": (C.c_int32, [_P, _P]),
     "pb_migrate_pack": (C.c_int32, [_P, _P, C.c_int64]),

@@ -42,6 +42,11 @@ def from_parcels(ref_fieldset) -> FieldSet:
     W = getattr(ref_fieldset, "W", None)
     fs = FieldSet(grid, _values(U.data), _values(ref_fieldset.V.data), None if W is None else _values(W.data), time=time,
                   interp_method=SUPPORTED_VECTOR_INTERP[interp])
+    scalar = {"XLinear": "linear", "XNearest": "nearest", "CGrid_Tracer": "cgrid_tracer"}
+    for name, f in ref_fieldset.fields.items():
+        how = type(getattr(f, "interp_method", None)).__name__
+        if name not in ("U", "V", "W") and how in scalar and getattr(f, "grid", None) is g:
+            fs.add_field(name, _values(f.data), interp_method=scalar[how])  # sampled on the device (pb_sample_scalar)
     for name, f in ref_fieldset.fields.items():
         if type(getattr(f, "interp_method", None)).__name__ == "XConstantField":
             fs.add_constant_field(name, float(_values(f.data)[0, 0, 0, 0]), mesh="spherical" if f.grid._mesh.is_spherical() else "flat")

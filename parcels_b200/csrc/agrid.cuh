@@ -4,6 +4,8 @@
 //   0  XLinear_Velocity (:169-190)                      -- instantiated in agrid.cu (the tuned hot path)
 //   1  XFreeslip / XPartialslip (_Spatialslip, :385-495) -- instantiated in aslip.cu
 //   2  XNearest per component (:515-560)                -- instantiated in aslip.cu
+// and, with NC == 1, the scalar interpolators of Field.eval (_core/field.py:144-191) -- aslip.cu:
+//   3  XLinear (:112-153)      4  XNearest (:515-560)      5  CGrid_Tracer (:335-383)
 #pragma once
 #include "common.cuh"
 
@@ -240,12 +242,16 @@ __device__ __forceinline__ void eval_uvw(const GridDev& g, const FieldDev& f, Ev
     }
 
     using DV = typename decltype(e.cor)::S;  // float64 copies on float64 grids (exact), else the data dtype
-    if constexpr (MODE == 2) {
+    if constexpr (MODE == 2 || MODE == 4 || MODE == 5) {
 #ifdef PB_SMEM_CACHE
-        // XNearest per component (_xinterpolators.py:515-560): the node on the near side of each axis (bcoord <= 0.5:
-        // lower), linear in time, no unit conversion (the reference's XNearest_Velocity, tests/test_interpolation.py:279)
-        const int k = ((zeta <= (TZ)0.5) ? 0 : 4) + ((eta <= (TY)0.5) ? 0 : 2) + ((xsi <= (TX)0.5) ? 0 : 1);
-        Val q[3];
+        // One node of the cached block per component, linear in time, no unit conversion.
+        //   XNearest (_xinterpolators.py:515-560): the node on the near side of each axis (bcoord <= 0.5: lower);
+        //     as a vector interpolator this is the reference's XNearest_Velocity (tests/test_interpolation.py:279).
+        //   CGrid_Tracer (:335-383): the tracer point of the cell, index + SGRID offset (clipped like the block's
+        //     upper corner; an index with a negative sentinel is masked to 0 afterwards, field.py:189).
+        const int k = MODE == 5 ? (g.off_z ? 4 : 0) + (g.off_y ? 2 : 0) + (g.off_x ? 1 : 0)
+                                : ((zeta <= (TZ)0.5) ? 0 : 4) + ((eta <= (TY)0.5) ? 0 : 2) + ((xsi <= (TX)0.5) ? 0 : 1);
+        Val q[3] = {Val{0.0, false}, Val{0.0, false}, Val{0.0, false}};
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
             const DV c0 = e.cor.get(c, k);
@@ -253,8 +259,13 @@ __device__ __forceinline__ void eval_uvw(const GridDev& g, const FieldDev& f, Ev
             else q[c] = Val{(double)c0, std::is_same<D, float>::value};
         }
         u = q[0]; v = q[1];
-        w = NC == 3 ? q[NC - 1] : Val{0.0, u.f32};
+        w = NC == 3 ? q[2] : Val{0.0, u.f32};
 #endif
+    } else if constexpr (MODE == 3) {
+        DV blk[16];
+        e.cor.load(0, blk);
+        u = xlinear<DV, TT, TZ, TY, TX>(blk, tau, zeta, eta, xsi);  // scalar XLinear: the value as it is
+        v = Val{0.0, u.f32}; w = v;
     } else {
         DV blk[16];
         unsigned land = 0;

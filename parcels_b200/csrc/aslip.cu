@@ -64,3 +64,17 @@ static cudaError_t sample_mode(const SampleParams& p, bool coord_f64, bool data_
 cudaError_t launch_sample_agrid_alt(const SampleParams& p, int mode, bool coord_f64, bool data_f64, bool has_time, int nc, cudaStream_t s) {
     return mode == 1 ? sample_mode<1>(p, coord_f64, data_f64, has_time, nc, s) : sample_mode<2>(p, coord_f64, data_f64, has_time, nc, s);
 }
+
+template <class A, class D, int MODE>
+static cudaError_t scalar_ad(const SampleParams& p, bool ht, cudaStream_t s) {
+    return ht ? sample1<A, D, true, 1, MODE>(p, s) : sample1<A, D, false, 1, MODE>(p, s);
+}
+template <int MODE>
+static cudaError_t scalar_mode(const SampleParams& p, bool coord_f64, bool data_f64, bool has_time, cudaStream_t s) {
+    if (coord_f64) return data_f64 ? scalar_ad<double, double, MODE>(p, has_time, s) : scalar_ad<double, float, MODE>(p, has_time, s);
+    return data_f64 ? scalar_ad<float, double, MODE>(p, has_time, s) : scalar_ad<float, float, MODE>(p, has_time, s);
+}
+cudaError_t launch_sample_scalar(const SampleParams& p, int mode, bool coord_f64, bool data_f64, bool has_time, cudaStream_t s) {
+    if (mode == 3) return scalar_mode<3>(p, coord_f64, data_f64, has_time, s);
+    return mode == 4 ? scalar_mode<4>(p, coord_f64, data_f64, has_time, s) : scalar_mode<5>(p, coord_f64, data_f64, has_time, s);
+}

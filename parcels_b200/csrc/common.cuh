@@ -442,6 +442,7 @@ struct SampleParams {
     double* w;
     int* ei_out;
     int* state_out;
+    int* f32_out;        // may be NULL; 1 where NumPy's promotion gives the (first) value dtype float32
 };
 
 template <class Policy>
@@ -466,7 +467,10 @@ __global__ void sample_kernel(const SampleParams s) {
         if (s.pos_f32) Policy::template eval<float, float, float>(p, e, nh, s.t[i], (float)s.z[i], (float)s.y[i], (float)s.x[i], u, v, w);
         else Policy::template eval<double, double, double>(p, e, nh, s.t[i], s.z[i], s.y[i], s.x[i], u, v, w);
     }
-    s.u[i] = u.v; s.v[i] = v.v; s.w[i] = w.v;
+    s.u[i] = u.v;
+    if (s.v) s.v[i] = v.v;
+    if (s.w) s.w[i] = w.v;
+    if (s.f32_out) s.f32_out[i] = u.f32 ? 1 : 0;
     Policy::finish(e, p);
     s.ei_out[i] = e.ei;
     s.state_out[i] = e.state;
@@ -477,6 +481,8 @@ cudaError_t launch_agrid(const AdvectParams& p, bool coord_f64, bool data_f64, b
 cudaError_t launch_cgrid(const AdvectParams& p, bool coord_f64, bool data_f64, int nc, cudaStream_t s);
 // mode: 1 = _Spatialslip (g.slip_a/b), 2 = XNearest per component  (aslip.cu)
 cudaError_t launch_agrid_alt(const AdvectParams& p, int mode, bool coord_f64, bool data_f64, bool has_time, int nc, cudaStream_t s);
+// scalar Field.eval on a rectilinear grid, f.p[0] = the field: mode 3 XLinear, 4 XNearest, 5 CGrid_Tracer  (aslip.cu)
+cudaError_t launch_sample_scalar(const SampleParams& p, int mode, bool coord_f64, bool data_f64, bool has_time, cudaStream_t s);
 cudaError_t launch_sample_agrid_alt(const SampleParams& p, int mode, bool coord_f64, bool data_f64, bool has_time, int nc, cudaStream_t s);
 cudaError_t launch_precompute_cells(const void* lon, const void* lat, int ny, int nx, bool coord_f64, double* out, cudaStream_t s);
 cudaError_t launch_sample_agrid(const SampleParams& p, bool coord_f64, bool data_f64, bool has_time, int nc, cudaStream_t s);

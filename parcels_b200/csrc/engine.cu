@@ -270,10 +270,10 @@ struct pb_engine {
     bool have_grid = false;
     int coord_f64 = 0;
     // fields
-    DevBuf fbuf[3];
-    const void* fptr[3] = {nullptr, nullptr, nullptr};
-    int f_f64[3] = {0, 0, 0};
-    long long fshape[3][4] = {};
+    DevBuf fbuf[PB_MAX_FIELDS];       // slots 0..2: U, V, W; 3..: scalar fields (Field.eval)
+    const void* fptr[PB_MAX_FIELDS] = {};
+    int f_f64[PB_MAX_FIELDS] = {};
+    long long fshape[PB_MAX_FIELDS][4] = {};
     // time-slab streaming: ring of (window + 1) levels per component, loads on a dedicated copy stream
     int ring = 0;                    // 0: every level resident
     long long win_first = 0, win_n = 0;
@@ -355,7 +355,8 @@ void pb_engine_destroy(pb_engine* e) {
     for (DevBuf* b : {&e->ax, &e->ay, &e->az, &e->adx, &e->ady, &e->adz, &e->at, &e->astate, &e->aei, &e->apid, &e->mdest, &e->mkeep,
                       &e->mcount, &e->mbounds})
         b->release();
-    for (DevBuf* b : {&e->hqbox, &e->hbucket, &e->cellproj, &e->hkeys, &e->hstarts, &e->hcounts, &e->hfaces, &e->lon, &e->lat, &e->depth, &e->time, &e->fbuf[0], &e->fbuf[1], &e->fbuf[2], &e->px, &e->py, &e->pz,
+    for (DevBuf& b : e->fbuf) b.release();
+    for (DevBuf* b : {&e->hqbox, &e->hbucket, &e->cellproj, &e->hkeys, &e->hstarts, &e->hcounts, &e->hfaces, &e->lon, &e->lat, &e->depth, &e->time, &e->px, &e->py, &e->pz,
                       &e->pdx, &e->pdy, &e->pdz, &e->pt, &e->pstate, &e->pei, &e->ppid, &e->snap})
         b->release();
     if (e->d_rep) cudaFree(e->d_rep);
@@ -539,7 +540,7 @@ static int32_t set_field(pb_engine* e, int32_t slot, const void* dev, int32_t is
 int32_t pb_field_upload(pb_engine* e, int32_t slot, const void* data, int32_t data_is_f64, int64_t T, int64_t Z,
                         int64_t Y, int64_t X) {
     if (!e) return fail(PB_ERR_INVALID, "engine is NULL");
-    if (slot < 0 || slot > 2) return fail(PB_ERR_INVALID, "bad field slot %d", slot);
+    if (slot < 0 || slot >= PB_MAX_FIELDS) return fail(PB_ERR_INVALID, "bad field slot %d", slot);
     if (!data || T < 1 || Z < 1 || Y < 1 || X < 1) return fail(PB_ERR_INVALID, "bad field shape");
     if (T > INT_MAX || Z > INT_MAX || Y > INT_MAX || X > INT_MAX) return fail(PB_ERR_INVALID, "field dim too long");
     CK(cudaSetDevice(e->device));
@@ -553,7 +554,7 @@ int32_t pb_field_upload(pb_engine* e, int32_t slot, const void* data, int32_t da
 int32_t pb_field_attach_device(pb_engine* e, int32_t slot, const void* dev_data, int32_t data_is_f64, int64_t T,
                                int64_t Z, int64_t Y, int64_t X) {
     if (!e) return fail(PB_ERR_INVALID, "engine is NULL");
-    if (slot < 0 || slot > 2) return fail(PB_ERR_INVALID, "bad field slot %d", slot);
+    if (slot < 0 || slot >= PB_MAX_FIELDS) return fail(PB_ERR_INVALID, "bad field slot %d", slot);
     if (!dev_data || T < 1 || Z < 1 || Y < 1 || X < 1) return fail(PB_ERR_INVALID, "bad field shape");
     if (T > INT_MAX || Z > INT_MAX || Y > INT_MAX || X > INT_MAX) return fail(PB_ERR_INVALID, "field dim too long");
     e->fbuf[slot].release();
@@ -562,7 +563,7 @@ int32_t pb_field_attach_device(pb_engine* e, int32_t slot, const void* dev_data,
 
 int32_t pb_field_clear(pb_engine* e, int32_t slot) {
     if (!e) return fail(PB_ERR_INVALID, "engine is NULL");
-    if (slot < 0 || slot > 2) return fail(PB_ERR_INVALID, "bad field slot %d", slot);
+    if (slot < 0 || slot >= PB_MAX_FIELDS) return fail(PB_ERR_INVALID, "bad field slot %d", slot);
     e->fbuf[slot].release();
     e->fptr[slot] = nullptr;
     return PB_OK;
@@ -730,6 +731,56 @@ int32_t pb_sample_velocity(pb_engine* e, int64_t n, const double* t, const doubl
     for (int k = 0; k < 3; ++k) CK(cudaMemcpyAsync(dst[k], d + (4 + k) * n, n * 8, cudaMemcpyDeviceToHost, e->stream));
     CK(cudaMemcpyAsync(ei_out, di + n, n * 4, cudaMemcpyDeviceToHost, e->stream));
     CK(cudaMemcpyAsync(state_out, di + 2 * n, n * 4, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    cudaFree(d);
+    cudaFree(di);
+    return PB_OK;
+}
+
+int32_t pb_sample_scalar(pb_engine* e, int32_t slot, int32_t method, int64_t n, const double* t, const double* z, const double* y,
+                         const double* x, int32_t positions_are_f32, const int32_t* ei_hint, double* value, int32_t* value_is_f32,
+                         int32_t* ei_out, int32_t* state_out) {
+    if (!e) return fail(PB_ERR_INVALID, "engine is NULL");
+    if (n < 0 || (n && (!t || !z || !y || !x || !value || !ei_out || !state_out))) return fail(PB_ERR_INVALID, "NULL argument");
+    if (slot < 0 || slot >= PB_MAX_FIELDS || !e->fptr[slot]) return fail(PB_ERR_STATE, "no field in slot %d", slot);
+    if (method < PB_SCALAR_XLINEAR || method > PB_SCALAR_CGRID_TRACER) return fail(PB_ERR_INVALID, "unknown scalar interpolation %d", method);
+    if (!e->have_grid) return fail(PB_ERR_STATE, "grid not uploaded (pb_grid_upload_*)");
+    if (e->g.curvilinear) return fail(PB_ERR_INVALID, "scalar sampling is implemented for rectilinear grids");
+    if (e->ring && slot < 3) return fail(PB_ERR_INVALID, "U, V, W are time-windowed: sample them through pb_sample_velocity");
+    const long long T = e->fshape[slot][0], Z = e->fshape[slot][1], Y = e->fshape[slot][2], X = e->fshape[slot][3];
+    if ((X > 1 && X != e->g.nx) || (Y > 1 && Y != e->g.ny) || (Z > 1 && e->g.nz > 0 && Z != e->g.nz) || (T > 1 && T != e->g.nt))
+        return fail(PB_ERR_INVALID, "field shape (%lld,%lld,%lld,%lld) does not match grid nodes (nt=%d nz=%d ny=%d nx=%d)", T, Z, Y, X,
+                    e->g.nt, e->g.nz, e->g.ny, e->g.nx);
+    if (Z > 1 && e->g.nz == 0) return fail(PB_ERR_INVALID, "field has a depth dimension but the grid has no Z axis");
+    if (n == 0) return PB_OK;
+    CK(cudaSetDevice(e->device));
+    double* d = nullptr;  // t z y x value
+    int* di = nullptr;    // hint ei state f32
+    CK(cudaMalloc(&d, (size_t)n * 5 * sizeof(double)));
+    CK(cudaMalloc(&di, (size_t)n * 4 * sizeof(int)));
+    const double* src[4] = {t, z, y, x};
+    for (int k = 0; k < 4; ++k) CK(cudaMemcpyAsync(d + k * n, src[k], n * 8, cudaMemcpyHostToDevice, e->stream));
+    if (ei_hint) CK(cudaMemcpyAsync(di, ei_hint, n * 4, cudaMemcpyHostToDevice, e->stream));
+    SampleParams sp{};
+    sp.g = e->g;
+    FieldDev& f = sp.f;
+    f.p[0] = e->fptr[slot]; f.p[1] = f.p[2] = nullptr;
+    f.T = (int)T; f.Z = (int)Z; f.Y = (int)Y; f.X = (int)X;
+    f.sX = X > 1 ? 1 : 0; f.sY = Y > 1 ? X : 0; f.sZ = Z > 1 ? X * Y : 0; f.sT = T > 1 ? X * Y * Z : 0;
+    f.ring = (int)T; f.windowed = 0;
+    sp.n = n;
+    sp.t = d; sp.z = d + n; sp.y = d + 2 * n; sp.x = d + 3 * n;
+    sp.u = d + 4 * n; sp.v = nullptr; sp.w = nullptr;
+    sp.ei_hint = ei_hint ? di : nullptr;
+    sp.ei_out = di + n; sp.state_out = di + 2 * n; sp.f32_out = di + 3 * n;
+    sp.pos_f32 = positions_are_f32; sp.no_hint = ei_hint ? 0 : 1;
+    // a field without a time dimension has no time interval: no time search at all (field.py:112-117)
+    cudaError_t ce = launch_sample_scalar(sp, 3 + method, e->coord_f64 != 0, e->f_f64[slot] != 0, T > 1, e->stream);
+    if (ce != cudaSuccess) return fail(PB_ERR_CUDA, "sample_kernel launch failed: %s", cudaGetErrorString(ce));
+    CK(cudaMemcpyAsync(value, d + 4 * n, n * 8, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemcpyAsync(ei_out, di + n, n * 4, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemcpyAsync(state_out, di + 2 * n, n * 4, cudaMemcpyDeviceToHost, e->stream));
+    if (value_is_f32) CK(cudaMemcpyAsync(value_is_f32, di + 3 * n, n * 4, cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
     cudaFree(d);
     cudaFree(di);

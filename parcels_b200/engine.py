@@ -209,6 +209,24 @@ class Engine:
                                            ptr(hint), int(no_hint), ptr(u), ptr(v), ptr(w), ptr(ei), ptr(st)))  # fmt: skip
         return u, v, w, ei, st
 
+    SCALAR_METHODS = {"linear": 0, "nearest": 1, "cgrid_tracer": 2}  # enum pb_scalar_interp
+
+    def sample_scalar(self, slot, method, t, z, y, x, *, positions_are_f32=False, ei_hint=None):
+        """One ``Field.eval`` per sample on the device -> (value, ei, state); ``value`` has the dtype NumPy's
+        promotion gives the reference's result (float32 only if every sample's arithmetic is float32)."""
+        t, z, y, x = (np.ascontiguousarray(np.broadcast_to(np.asarray(a, dtype=np.float64), np.shape(x)).ravel()) for a in (t, z, y, x))
+        n = x.size
+        val = np.empty(n, dtype=np.float64)
+        f32 = np.empty(n, dtype=np.int32)
+        ei = np.empty(n, dtype=np.int32)
+        st = np.empty(n, dtype=np.int32)
+        hint = None if ei_hint is None else np.ascontiguousarray(ei_hint, dtype=np.int32)
+        check(self._lib.pb_sample_scalar(self._h, int(slot), self.SCALAR_METHODS[method], n, ptr(t), ptr(z), ptr(y), ptr(x),
+                                         int(positions_are_f32), ptr(hint), ptr(val), ptr(f32), ptr(ei), ptr(st)))  # fmt: skip
+        if n and f32.all():
+            val = val.astype(np.float32)
+        return val, ei, st
+
     # -- mode D: domain decomposition + migration ------------------------------------------------------
     def decomp_set(self, nranks, rank, bounds, xi_offset, left_is_global, right_is_global):
         b = np.ascontiguousarray(bounds, dtype=np.float64)

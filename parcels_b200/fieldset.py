@@ -6,6 +6,8 @@ the engine the first time a ParticleSet executes on it (reference: ``_core/field
 
 from __future__ import annotations
 
+import warnings
+
 import numpy as np
 
 from .engine import Engine
@@ -89,11 +91,59 @@ class XGrid:
 
 
 class Field:
-    def __init__(self, name, data, grid, fieldset):
+    """Scalar field on the fieldset's grid (reference ``_core/field.py:46-202``).  ``interp_method``: "linear" (XLinear),
+    "nearest" (XNearest), "cgrid_tracer" (CGrid_Tracer) or "constant" (XConstantField, a 1-node grid)."""
+
+    def __init__(self, name, data, grid, fieldset, interp_method="linear", slot=None):
         self.name = name
         self.data = data
         self.grid = grid
         self._fieldset = fieldset
+        self.interp_method = interp_method
+        self._slot = slot  # device field slot (include/parcels_b200.h: 0..2 = U, V, W; 3.. = scalar fields)
+
+    def eval(self, t, z, y, x, particles=None, *, device=None, positions_are_f32=None):
+        """``fieldset.P.eval(t, z, y, x[, particles])`` (reference _core/field.py:144-191), evaluated ON THE DEVICE
+        (``pb_sample_scalar``); out-of-bounds samples are 0.  With ``particles`` the search is hinted by, and writes
+        back, ``particles.ei[:, -1]`` and raises ``particles.state`` like the reference."""
+        from .statuscodes import StatusCode
+
+        fs = self._fieldset
+        z, y, x = (np.atleast_1d(a.__array__() if hasattr(a, "__array__") else a) for a in (z, y, x))
+        if self.interp_method == "constant":
+            # XConstantField on its 1-node grid (_xinterpolators.py:156-166, model.py:292-318): index 0 everywhere
+            if particles is not None:
+                particles.ei[:, -1] = 0
+            return float(np.asarray(self.data)[0, 0, 0, 0]) * np.ones_like(x)
+        if self._slot is None:
+            raise NotImplementedError(f"field {self.name!r} is not a sampled field of this FieldSet")
+        if self.name in ("U", "V", "W"):
+            warnings.warn("Sampling of velocities should normally be done using fieldset.UV or fieldset.UVW object; tread carefully",
+                          RuntimeWarning, stacklevel=2)  # fmt: skip
+        if device is None:
+            device = next(iter(fs._engines), 0)
+        t = np.atleast_1d(t.__array__() if hasattr(t, "__array__") else t)
+        if np.issubdtype(t.dtype, np.floating) and np.any(np.isnan(t)):
+            raise ValueError(f"Time values for particles with indices {np.where(np.isnan(t))[0]} cannot be NaN.")
+        if positions_are_f32 is None:
+            positions_are_f32 = all(a.dtype == np.float32 for a in (z, y, x))
+        hint = None if particles is None else np.ascontiguousarray(np.asarray(particles.ei)[:, -1])
+        val, ei, st = fs.engine(device).sample_scalar(self._slot, self.interp_method, t, z, y, x,
+                                                      positions_are_f32=positions_are_f32, ei_hint=hint)  # fmt: skip
+        if particles is not None:
+            particles.ei[:, -1] = ei
+            state = np.asarray(particles.state)
+            if np.any(st == StatusCode.ErrorOutsideTimeInterval):  # whole view flagged, 0 returned (field.py:31-44)
+                particles.state = StatusCode.ErrorOutsideTimeInterval
+                val[:] = 0
+            else:
+                particles.state = np.where(st >= StatusCode.Error, np.maximum(state, st), state)
+        return val.reshape(np.shape(x))
+
+    def __getitem__(self, key):
+        if hasattr(key, "_data") and not isinstance(key, tuple):  # a ParticleSet / ParticleSetView
+            return self.eval(key.t, key.z, key.y, key.x, key)
+        return self.eval(*key)
 
 
 class VectorField:
@@ -192,7 +242,7 @@ class FieldSet:
                 arr = np.asarray(arr)
             if len(arr.shape) != 4:
                 raise ValueError(f"{name} must be laid out (T, Z, Y, X); got shape {arr.shape}")
-            self.fields[name] = Field(name, arr, grid, self)
+            self.fields[name] = Field(name, arr, grid, self, slot={"U": 0, "V": 1, "W": 2}[name] if self.time_window is None else None)
         self.U, self.V, self.W = self.fields["U"], self.fields["V"], self.fields.get("W")
         self.UV = VectorField("UV", self.U, self.V)
         self.fields["UV"] = self.UV
@@ -233,9 +283,38 @@ class FieldSet:
         elif self._const_grid.mesh != mesh:
             raise NotImplementedError("constant fields on two different meshes")
         self.constants[name] = float(np.full((1, 1, 1, 1), value)[0, 0, 0, 0])
-        f = Field(name, np.full((1, 1, 1, 1), value), self._const_grid, self)
+        f = Field(name, np.full((1, 1, 1, 1), value), self._const_grid, self, interp_method="constant")
         self.fields[name] = f
         setattr(self, name, f)
+
+    def add_field(self, name, data, interp_method="linear"):
+        """Scalar field on the FieldSet's grid -- in the reference every data variable of the model's dataset is a
+        ``Field`` with its own ``interp_method`` (_core/fieldset.py:89-108, _core/field.py:102-134); here it is added
+        from an array laid out (T, Z, Y, X) with T == the time axis, or T == 1 for a field without a time dimension.
+        Sampled on the device: ``fieldset.<name>[particles]`` / ``.eval(t, z, y, x)``."""
+        from .engine import Engine
+
+        if interp_method not in Engine.SCALAR_METHODS:
+            raise ValueError(f"interp_method must be one of {sorted(Engine.SCALAR_METHODS)}. Got {interp_method!r}")
+        if name in self.fields:
+            raise ValueError(f"FieldSet already has a Field with name '{name}'")
+        if self.grid.curvilinear:
+            raise NotImplementedError("scalar fields are sampled on rectilinear grids")
+        data = np.ascontiguousarray(data)
+        if data.ndim != 4:
+            raise ValueError(f"{name} must be laid out (T, Z, Y, X); got shape {data.shape}")
+        if data.dtype not in (np.float32, np.float64):
+            data = data.astype(np.float64)
+        nt = 1 if self._time_s is None else self._time_s.size
+        if data.shape[0] not in (1, nt) or data.shape[1:] != self.U.data.shape[1:]:
+            raise ValueError(f"{name} has shape {data.shape}; expected ({nt} or 1, {', '.join(map(str, self.U.data.shape[1:]))})")
+        slot = 3 + sum(1 for f in self.fields.values() if isinstance(f, Field) and f._slot is not None and f._slot >= 3)
+        f = Field(name, data, self.grid, self, interp_method=interp_method, slot=slot)
+        self.fields[name] = f
+        setattr(self, name, f)
+        for eng in self._engines.values():
+            eng.upload_field(slot, data)
+        return f
 
     def add_context(self, name, value):
         if name in self.context:
@@ -261,6 +340,9 @@ class FieldSet:
                         eng.upload_field(slot, d)
                     else:
                         eng.window_create(slot, d.dtype, d.shape, self.time_window)
+            for f in self.fields.values():
+                if isinstance(f, Field) and f._slot is not None and f._slot >= 3:
+                    eng.upload_field(f._slot, f.data)
             self._win[device] = dict(first=0, n=0, resident=set())
             self._engines[device] = eng
         return eng

@@ -238,6 +238,20 @@ class ParticleSet:
             return data[name]
         raise AttributeError(name)
 
+    def __setattr__(self, name, value):
+        """`pset.state = ...` writes the particle variable (reference _core/particleset.py:170-176)."""
+        host = self.__dict__.get("_host")
+        if not name.startswith("_") and isinstance(host, dict) and name in host:
+            self._data[name][:] = value
+        else:
+            object.__setattr__(self, name, value)
+
+    def __getitem__(self, index):
+        """A write-through view on a subset (reference `pset[i]` / `pset[mask]`, _core/particleset.py:166-168)."""
+        from .particlesetview import ParticleSetView, _global_mask
+
+        return ParticleSetView(self._data, _global_mask(np.ones(len(self), dtype=bool), index), self.fieldset)
+
     @property
     def size(self):
         return len(self)

@@ -1,0 +1,79 @@
+"""GPU parity of scalar Field.eval (pb_sample_scalar): cell indices and states bit-exact, values bit-exact on the
+cases below (IEEE +,-,*,/ only, in the reference's order and dtype) -- against the oracle and against the
+reference's own outputs (tests/golden/scalar_eval.npz); plus a user sampling kernel in a mixed kernel list."""
+
+import os
+
+import numpy as np
+import pytest
+
+import parcels_b200 as pb
+from engine_run import make_fieldset
+from oracle import parcels_oracle as po
+from oracle.make_golden import SCALAR_CASES, scalar_inputs
+from oracle_run import load_case, oracle_fieldset
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", SCALAR_CASES)
+def test_scalar_eval_matches_oracle_and_reference(name, golden_dir):
+    g = np.load(os.path.join(golden_dir, "scalar_eval.npz"))
+    c = load_case(name)
+    ofs = oracle_fieldset(c)
+    for T in (c["U"].shape[0], 1):
+        P, tq = scalar_inputs(c, T)
+        for how in ("linear", "nearest", "cgrid_tracer"):
+            fs = make_fieldset(c)
+            fs.add_field("P", P, interp_method=how)
+            ps = pb.ParticleSet(fs, x=c["x"], y=c["y"], z=c["z"], t=c["t"])
+            val = fs.P.eval(tq, ps._data["z"], ps._data["y"], ps._data["x"], ps)
+            pd = po.create_particle_data(c["x"], c["y"], c["z"], c["t"])
+            oval = po.eval_scalar(ofs, P, how, tq, pd["z"], pd["y"], pd["x"], po.View(pd, np.ones(len(pd["x"]), dtype=bool)))
+            key = f"{name}/T{T}/{how}"
+            assert val.dtype == oval.dtype == g[f"{key}/value"].dtype, key
+            np.testing.assert_array_equal(ps._data["ei"], pd["ei"], err_msg=key)
+            np.testing.assert_array_equal(ps._data["state"], pd["state"], err_msg=key)
+            np.testing.assert_array_equal(val, oval, err_msg=key)
+            np.testing.assert_array_equal(val, g[f"{key}/value"], err_msg=key)
+            np.testing.assert_array_equal(ps._data["state"], g[f"{key}/state"], err_msg=key)
+            # float64 sample positions (an RK stage position), hinted by the cells just found
+            x2 = np.asarray(c["x"], dtype=np.float64) + 1e-3
+            v2 = fs.P.eval(tq, np.asarray(c["z"], dtype=np.float64), np.asarray(c["y"], dtype=np.float64), x2, ps)
+            pd2 = {k: v.copy() for k, v in pd.items()}
+            o2 = po.eval_scalar(ofs, P, how, tq, np.asarray(c["z"], dtype=np.float64), np.asarray(c["y"], dtype=np.float64), x2,
+                                po.View(pd2, np.ones(len(x2), dtype=bool)))  # fmt: skip
+            np.testing.assert_array_equal(v2, o2, err_msg=key + " f64")
+            np.testing.assert_array_equal(ps._data["ei"], pd2["ei"], err_msg=key + " f64")
+
+
+def test_user_sampling_kernel_in_a_mixed_list():
+    """The common idiom `particles.p = fieldset.P[particles]` after an advection kernel: the built-in runs on the device,
+    the sampling kernel's Field.eval too; compared with the oracle running the same list."""
+    c = load_case("flat_f32c_f64d")
+    P, _ = scalar_inputs(c, c["U"].shape[0])
+    fs = make_fieldset(c)
+    fs.add_field("P", P)
+    pclass = pb.Particle.add_variable(pb.Variable("p", np.float32, initial=0))
+    ps = pb.ParticleSet(fs, pclass=pclass, x=c["x"], y=c["y"], z=c["z"], t=c["t"])
+
+    def SampleP(particles, fieldset):
+        particles.p = fieldset.P[particles]
+
+    def DeleteErr(particles, fieldset):
+        particles[particles.state >= 50].state = 30
+
+    ps.execute([pb.AdvectionRK4_3D, SampleP, DeleteErr], dt=c["dt"], runtime=50.0)
+
+    ofs = oracle_fieldset(c)
+    pd = po.create_particle_data(c["x"], c["y"], c["z"], c["t"])
+    pd["p"] = np.zeros(len(pd["x"]), dtype=np.float32)
+
+    def OSample(p, fs_):
+        p.p = po.eval_scalar(fs_, P, "linear", p.t, p.z, p.y, p.x, p)
+
+    po.pset_execute(pd, ofs, [po.AdvectionRK4_3D, OSample, po.DeleteOnError], c["dt"], runtime=50.0)
+    assert len(ps) == len(pd["x"]) and len(ps) > 0
+    for k in ("particle_id", "state", "t", "ei", "x", "y", "z", "p"):
+        np.testing.assert_array_equal(ps._data[k], pd[k], err_msg=k)
+    assert np.abs(ps._data["p"]).max() > 0
