@@ -42,7 +42,8 @@ enum pb_scheme {
     PB_ADVECTION_RK2 = 2,     /* :20-27   */
     PB_ADVECTION_RK2_3D = 3,  /* :30-39   */
     PB_ADVECTION_RK4 = 4,     /* :42-55   */
-    PB_ADVECTION_RK4_3D = 5   /* :58-75   */
+    PB_ADVECTION_RK4_3D = 5,  /* :58-75   */
+    PB_ADVECTION_RK45 = 6     /* :85-155: adaptive step, own entry point pb_advect_rk45 */
 };
 
 /* Particle status codes written by the device: identical to _core/statuscodes.py:19-34. */
@@ -225,6 +226,28 @@ int32_t pb_advect(pb_engine* e, const pb_advect_args* args, pb_report* rep);
  * after pb_engine_synchronize() through pb_last_report(). */
 int32_t pb_advect_async(pb_engine* e, const pb_advect_args* args);
 int32_t pb_last_report(pb_engine* e, pb_report* rep);
+
+/* ---- AdvectionRK45 (kernels/_advection.py:85-155) under Kernel.execute's Repeat / next_dt state machine
+ * (_core/kernel.py:108-120,199-216,224-226): every particle carries its own dt and next_dt; a rejected step
+ * (error estimate kappa > tol) sets state Repeat and is retried with dt / 2 inside the same loop iteration; an
+ * accepted one may double next_dt; after the position update dt <- next_dt; dt is never reset to the nominal step.
+ * tol is in the units of the mesh (the reference divides fieldset.RK45_tol by deg2m on spherical meshes when the
+ * Kernel is built, kernel.py:144-145 -- the caller does the same).  dt_inout / next_dt_inout: host arrays of
+ * pb_particles_count() float64 (next_dt widened; next_dt_is_f32 = the Particle's next_dt Variable is float32, the
+ * default dtype, so assignments to it round to float32).  On return dt_inout holds particles.dt exactly as the
+ * reference leaves it, including its batch-level clamp of the particles that left the loop early (kernel.py:199-203).
+ * pb_report: particle_steps = accepted steps, cache_refills = field evaluations (6 per attempt), n_error = particles
+ * whose dt is 0 before endtime (state 50; the reference's loop never terminates on those).
+ * Rectilinear A-grid + XLinear_Velocity fields, fully resident. */
+typedef struct pb_rk45_args {
+    double dt;      /* nominal dt of ParticleSet.execute: only its sign is used (compute_time_direction) */
+    double endtime;
+    double tol, min_dt, max_dt; /* fieldset.RK45_tol (mesh units), RK45_min_dt, RK45_max_dt */
+    int64_t max_iters;          /* < 0: run to endtime */
+    int32_t next_dt_is_f32;
+    int32_t delete_on_error;
+} pb_rk45_args;
+int32_t pb_advect_rk45(pb_engine* e, const pb_rk45_args* args, double* dt_inout, double* next_dt_inout, pb_report* rep);
 
 /* VectorField.eval at n arbitrary sample points (fieldset.UV[t, z, y, x] / fieldset.UVW[...],
  * _core/field.py:250-304): time + grid search, interpolation, unit conversion, error states

@@ -346,6 +346,53 @@ def make_scalar_golden():
     np.savez_compressed(os.path.join(GOLDEN, "scalar_eval.npz"), **out)
 
 
+# name -> (RK45_tol in metres, RK45_min_dt, RK45_max_dt factor of |dt|, runtime, dt)
+RK45_CASES = {
+    "flat_f32c_f64d": (1e-4, 0.5, 4, 140.0, 10.0),
+    "c2_small": (0.5, 1.0, 4, 7200.0, 300.0),  # runs stay inside the fields' time axis (see DESIGN.md, RK45 waiver)
+    "all_f32": (0.2, 1.0, 4, 3600.0, 150.0),
+    "backward": (0.002, 7.0, 4, 5000.0, -600.0),
+    "c1_peninsula": (1e-6, 1.0, 8, 3600.0, 300.0),
+}
+
+
+def make_rk45_golden():
+    """AdvectionRK45 under the reference's own Kernel.execute (Repeat loop, next_dt, per-particle dt)."""
+    import warnings
+
+    import cases as tc
+    from oracle import ref_harness as rh
+
+    out = {}
+    for name, (tol, min_dt, fmax, runtime, dt) in RK45_CASES.items():
+        c = tc.build(tc.CASES[name])
+        fs = rh.build_fieldset(lon=c["lon"], lat=c["lat"], depth=c["depth"], times=c["times"], U=c["U"], V=c["V"], W=c["W"],
+                               mesh=c["mesh"])  # fmt: skip
+        fs.add_context("RK45_tol", tol)
+        fs.add_context("RK45_min_dt", min_dt)
+        fs.add_context("RK45_max_dt", fmax * abs(dt))
+        z = np.abs(np.asarray(c["z"]))
+        ps = rh.make_pset(fs, x=c["x"], y=c["y"], z=z, t=c["t"], extra_variables=[("next_dt", np.float32, 0)])
+        k = rh.kernels()
+        attempts = [0]
+        real = k.AdvectionRK45
+
+        def Counted(particles, fieldset, real=real, attempts=attempts):
+            attempts[0] += int(np.size(np.asarray(particles.state)))
+            real(particles, fieldset)
+
+        Counted.__name__ = "AdvectionRK45"
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            ps.execute(real, dt=dt, runtime=runtime, verbose_progress=False)
+        for key in ("x", "y", "z", "t", "dt", "next_dt", "state", "ei"):
+            out[f"{name}/{key}"] = ps._data[key]
+        out[f"{name}/tol_used"] = np.array(fs.context["RK45_tol"])  # after the reference's in-place unit conversion
+        print(f"rk45 {name}: states {np.unique(ps._data['state'])} dt {np.unique(ps._data['dt'])[:5]} "
+              f"next_dt {np.unique(ps._data['next_dt'])[:6]}")
+    np.savez_compressed(os.path.join(GOLDEN, "rk45.npz"), **out)
+
+
 if __name__ == "__main__":
     os.makedirs(GOLDEN, exist_ok=True)
     make_v3("linear", "v3_jit_linear.npz")
@@ -355,3 +402,4 @@ if __name__ == "__main__":
     make_ref_cases()
     make_output_golden()
     make_scalar_golden()
+    make_rk45_golden()

@@ -113,6 +113,7 @@ class OFieldSet:
         if self.time is not None and len(self.time) < 2:
             self.time = None  # model.py:511-515: a single time level => no time interval
         self.interp = interp
+        self.context = {}  # FieldSet.add_context (_core/fieldset.py:207-222), e.g. RK45_tol / RK45_min_dt / RK45_max_dt
         self.constants = dict(constants or {})
         self.const_spherical = grid.spherical if const_mesh is None else (const_mesh == "spherical")
         self.const_deg2m = DEG2M_EARTH if self.const_spherical else 1.0
@@ -530,6 +531,55 @@ def AdvectionRK4(p: View, fs: OFieldSet):
     p.dy = p.dy + (v1 + 2 * v2 + 2 * v3 + v4) / 6.0 * p.dt
 
 
+def AdvectionRK45(p: View, fs: OFieldSet):
+    """kernels/_advection.py:85-155.  ``fs.context``: RK45_tol (already in mesh units: the reference divides it by deg2m
+    on spherical meshes when the Kernel is built, kernel.py:144-145), RK45_min_dt, RK45_max_dt."""
+    tol, min_dt, max_dt = fs.context["RK45_tol"], fs.context["RK45_min_dt"], fs.context["RK45_max_dt"]
+    sign_dt = np.sign(p.dt)
+    c = [1.0 / 4.0, 3.0 / 8.0, 12.0 / 13.0, 1.0, 1.0 / 2.0]
+    A = [
+        [1.0 / 4.0, 0.0, 0.0, 0.0, 0.0],
+        [3.0 / 32.0, 9.0 / 32.0, 0.0, 0.0, 0.0],
+        [1932.0 / 2197.0, -7200.0 / 2197.0, 7296.0 / 2197.0, 0.0, 0.0],
+        [439.0 / 216.0, -8.0, 3680.0 / 513.0, -845.0 / 4104.0, 0.0],
+        [-8.0 / 27.0, 2.0, -3544.0 / 2565.0, 1859.0 / 4104.0, -11.0 / 40.0],
+    ]
+    b4 = [25.0 / 216.0, 0.0, 1408.0 / 2565.0, 2197.0 / 4104.0, -1.0 / 5.0]
+    b5 = [16.0 / 135.0, 0.0, 6656.0 / 12825.0, 28561.0 / 56430.0, -9.0 / 50.0, 2.0 / 55.0]
+    (u1, v1) = eval_uvw(fs, p.t, p.z, p.y, p.x, p, False)
+    x1 = p.x + u1 * A[0][0] * p.dt
+    y1 = p.y + v1 * A[0][0] * p.dt
+    (u2, v2) = eval_uvw(fs, p.t + c[0] * p.dt, p.z, y1, x1, p, False)
+    x2 = p.x + (u1 * A[1][0] + u2 * A[1][1]) * p.dt
+    y2 = p.y + (v1 * A[1][0] + v2 * A[1][1]) * p.dt
+    (u3, v3) = eval_uvw(fs, p.t + c[1] * p.dt, p.z, y2, x2, p, False)
+    x3 = p.x + (u1 * A[2][0] + u2 * A[2][1] + u3 * A[2][2]) * p.dt
+    y3 = p.y + (v1 * A[2][0] + v2 * A[2][1] + v3 * A[2][2]) * p.dt
+    (u4, v4) = eval_uvw(fs, p.t + c[2] * p.dt, p.z, y3, x3, p, False)
+    x4 = p.x + (u1 * A[3][0] + u2 * A[3][1] + u3 * A[3][2] + u4 * A[3][3]) * p.dt
+    y4 = p.y + (v1 * A[3][0] + v2 * A[3][1] + v3 * A[3][2] + v4 * A[3][3]) * p.dt
+    (u5, v5) = eval_uvw(fs, p.t + c[3] * p.dt, p.z, y4, x4, p, False)
+    x5 = p.x + (u1 * A[4][0] + u2 * A[4][1] + u3 * A[4][2] + u4 * A[4][3] + u5 * A[4][4]) * p.dt
+    y5 = p.y + (v1 * A[4][0] + v2 * A[4][1] + v3 * A[4][2] + v4 * A[4][3] + v5 * A[4][4]) * p.dt
+    (u6, v6) = eval_uvw(fs, p.t + c[4] * p.dt, p.z, y5, x5, p, False)
+    x_4th = (u1 * b4[0] + u2 * b4[1] + u3 * b4[2] + u4 * b4[3] + u5 * b4[4]) * p.dt
+    y_4th = (v1 * b4[0] + v2 * b4[1] + v3 * b4[2] + v4 * b4[3] + v5 * b4[4]) * p.dt
+    x_5th = (u1 * b5[0] + u2 * b5[1] + u3 * b5[2] + u4 * b5[3] + u5 * b5[4] + u6 * b5[5]) * p.dt
+    y_5th = (v1 * b5[0] + v2 * b5[1] + v3 * b5[2] + v4 * b5[3] + v5 * b5[4] + v6 * b5[5]) * p.dt
+    kappa = np.sqrt(np.pow(x_5th - x_4th, 2) + np.pow(y_5th - y_4th, 2))
+    good = (kappa <= tol) | (np.fabs(p.dt) <= np.fabs(min_dt))
+    p.dx = p.dx + np.where(good, x_5th, 0)
+    p.dy = p.dy + np.where(good, y_5th, 0)
+    inc = good & (kappa <= tol / 10) & (np.fabs(p.dt * 2) <= np.fabs(max_dt))
+    p.next_dt = np.where(inc, p.dt * 2, p.dt)
+    p.next_dt = np.where(np.abs(p.next_dt) > np.abs(max_dt), max_dt * sign_dt, p.next_dt)
+    p.state = np.where(good, EVALUATE, p.state)
+    rep = np.invert(good)
+    p.dt = np.where(rep, p.dt / 2, p.dt)
+    p.dt = np.where(np.abs(p.dt) < np.abs(min_dt), min_dt * sign_dt, p.dt)
+    p.state = np.where(rep, REPEAT, p.state)
+
+
 def AdvectionRK4_3D(p: View, fs: OFieldSet):
     """kernels/_advection.py:58-75."""
     (u1, v1, w1) = eval_uvw(fs, p.t, p.z, p.y, p.x, p, True)
@@ -645,6 +695,8 @@ def kernel_execute(pdata, fs: OFieldSet, kernels, endtime, dt, max_iters=None):
     pdata["state"][:] = EVALUATE
     nsteps = 0
     it = 0
+    rk45_mode = "RK45_tol" in getattr(fs, "context", {})
+    max_repeats = 10000
     while len(pdata["state"]) > 0 and np.any(np.isin(pdata["state"], [EVALUATE, REPEAT])):
         if max_iters is not None and it >= max_iters:
             break
@@ -660,6 +712,14 @@ def kernel_execute(pdata, fs: OFieldSet, kernels, endtime, dt, max_iters=None):
         nsteps += int(np.count_nonzero(ev))
         for f in kernels:
             f(View(pdata, ev), fs)
+            rep = pdata["state"] == REPEAT  # kernel.py:212-216
+            while np.any(rep):
+                if max_repeats is not None:  # testing aid: the reference has no bound
+                    max_repeats -= 1
+                    if max_repeats < 0:
+                        raise RuntimeError("Repeat loop does not terminate")
+                f(View(pdata, rep), fs)
+                rep = pdata["state"] == REPEAT
         upd = ev & np.isin(pdata["state"], [EVALUATE, SUCCESS])
         if np.any(upd):
             p = View(pdata, upd)
@@ -670,7 +730,10 @@ def kernel_execute(pdata, fs: OFieldSet, kernels, endtime, dt, max_iters=None):
             p.dx = 0
             p.dy = 0
             p.dz = 0
-        pdata["dt"][:] = dt
+            if rk45_mode:  # kernel.py:118-120: `if hasattr(self.fieldset, "RK45_tol")`
+                p.dt = p.next_dt
+        if not rk45_mode:  # kernel.py:224-226
+            pdata["dt"][:] = dt
         eol = (pdata["state"] == EVALUATE) & (pdata["t"] == endtime)
         pdata["state"][eol] = END_OF_LOOP
         dele = np.where(pdata["state"] == DELETE)[0]

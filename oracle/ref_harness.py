@@ -187,6 +187,11 @@ class _FieldSet:
         for k, v in fields.items():
             setattr(self, k, v)
 
+    def add_context(self, name, value):  # _core/fieldset.py:207-222
+        if name in self.context:
+            raise ValueError(f"FieldSet already has a context with name '{name}'")
+        self.context[name] = value
+
     def __getattr__(self, name):
         ctx = self.__dict__.get("context", {})
         if name in ctx:
@@ -351,8 +356,10 @@ def build_const_grid(mesh="flat", radius=None):
     return g
 
 
-def make_pset(fieldset, *, x, y, z, t=None):
+def make_pset(fieldset, *, x, y, z, t=None, extra_variables=(), **kwargs):
+    """``extra_variables``: (name, dtype, initial) tuples added to the default Particle (e.g. next_dt for RK45)."""
     install()
+    from parcels._core.particle import Particle, Variable
     from parcels._core.particleset import ParticleSet
 
     n = np.size(x)
@@ -360,6 +367,9 @@ def make_pset(fieldset, *, x, y, z, t=None):
         t = np.repeat(np.timedelta64(0, "s"), n)
     elif not isinstance(np.asarray(t).flat[0], np.timedelta64):
         t = (np.asarray(t, dtype=np.float64) * 1e9).astype("timedelta64[ns]")
+    if extra_variables:
+        pclass = Particle.add_variable([Variable(n_, dtype=d_, initial=i_) for n_, d_, i_ in extra_variables])
+        return ParticleSet(fieldset, pclass=pclass, x=x, y=y, z=z, t=t, **kwargs)
     return ParticleSet(fieldset, x=x, y=y, z=z, t=t)
 
 

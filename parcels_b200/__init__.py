@@ -15,6 +15,7 @@ from .kernels import (
     AdvectionRK2_3D,
     AdvectionRK4,
     AdvectionRK4_3D,
+    AdvectionRK45,
     DeleteParticle,
     DiffusionUniformKh,
 )
@@ -22,6 +23,7 @@ from .particle import Particle, ParticleClass, Variable
 from .particlefile import ParticleFile, read_particlefile
 from .particleset import ParticleSet
 from .statuscodes import (
+    KernelWarning,
     FieldInterpolationError,
     FieldOutOfBoundError,
     FieldOutOfBoundSurfaceError,
@@ -32,8 +34,8 @@ from .statuscodes import (
 )
 
 __all__ = [
-    "AdvectionEE", "AdvectionRK2", "AdvectionRK2_3D", "AdvectionRK4", "AdvectionRK4_3D", "DeleteParticle",
+    "AdvectionEE", "AdvectionRK2", "AdvectionRK2_3D", "AdvectionRK4", "AdvectionRK4_3D", "AdvectionRK45", "DeleteParticle",
     "DiffusionUniformKh", "Field", "FieldInterpolationError", "FieldOutOfBoundError", "FieldOutOfBoundSurfaceError",
-    "FieldSet", "GeneralError", "GridSearchingError", "OutsideTimeInterval", "Particle", "ParticleClass", "ParticleFile", "ParticleSet", "Variable", "read_particlefile", "StatusCode",
+    "FieldSet", "GeneralError", "GridSearchingError", "KernelWarning", "OutsideTimeInterval", "Particle", "ParticleClass", "ParticleFile", "ParticleSet", "Variable", "read_particlefile", "StatusCode",
     "VectorField", "XGrid", "kernels",
 ]  # fmt: skip

@@ -39,6 +39,19 @@ class AdvectArgs(C.Structure):
     ]
 
 
+class Rk45Args(C.Structure):
+    _fields_ = [
+        ("dt", C.c_double),
+        ("endtime", C.c_double),
+        ("tol", C.c_double),
+        ("min_dt", C.c_double),
+        ("max_dt", C.c_double),
+        ("max_iters", C.c_int64),
+        ("next_dt_is_f32", C.c_int32),
+        ("delete_on_error", C.c_int32),
+    ]
+
+
 class Report(C.Structure):
     _fields_ = [
         ("particle_steps", C.c_int64),
@@ -97,6 +110,7 @@ SYMBOLS = {
     "pb_particles_remove_deleted": (C.c_int32, [_P, C.POINTER(C.c_int64)]),
     "pb_advect": (C.c_int32, [_P, C.POINTER(AdvectArgs), C.POINTER(Report)]),
     "pb_advect_async": (C.c_int32, [_P, C.POINTER(AdvectArgs)]),
+    "pb_advect_rk45": (C.c_int32, [_P, _P, _P, _P, _P]),
     "pb_last_report": (C.c_int32, [_P, C.POINTER(Report)]),
     "pb_sample_velocity": (C.c_int32, [_P, C.c_int64, _P, _P, _P, _P, C.c_int32, C.c_int32, _P, C.c_int32, _P, _P, _P, _P, _P]),
     "pb_sample_scalar": (C.c_int32, [_P, C.c_int32, C.c_int32, C.c_int64, _P, _P, _P, _P, C.c_int32, _P, _P, _P, _P, _P]),

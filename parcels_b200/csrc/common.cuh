@@ -481,6 +481,11 @@ cudaError_t launch_agrid(const AdvectParams& p, bool coord_f64, bool data_f64, b
 cudaError_t launch_cgrid(const AdvectParams& p, bool coord_f64, bool data_f64, int nc, cudaStream_t s);
 // mode: 1 = _Spatialslip (g.slip_a/b), 2 = XNearest per component  (aslip.cu)
 cudaError_t launch_agrid_alt(const AdvectParams& p, int mode, bool coord_f64, bool data_f64, bool has_time, int nc, cudaStream_t s);
+// AdvectionRK45 + the Repeat / next_dt state machine (rk45.cu); dt / next_dt / iters: per-particle device arrays
+cudaError_t launch_rk45(const AdvectParams& p, double* dt, double* next_dt, int* iters, int next_dt_f32, double tol, double min_dt,
+                        double max_dt, bool coord_f64, bool data_f64, bool has_time, cudaStream_t s);
+cudaError_t launch_rk45_finalize(const ParticlesDev& P, double* dt, const int* iters, long long total_iters, double endtime, int sign,
+                                 cudaStream_t s);
 // scalar Field.eval on a rectilinear grid, f.p[0] = the field: mode 3 XLinear, 4 XNearest, 5 CGrid_Tracer  (aslip.cu)
 cudaError_t launch_sample_scalar(const SampleParams& p, int mode, bool coord_f64, bool data_f64, bool has_time, cudaStream_t s);
 cudaError_t launch_sample_agrid_alt(const SampleParams& p, int mode, bool coord_f64, bool data_f64, bool has_time, int nc, cudaStream_t s);

@@ -878,6 +878,57 @@ int32_t pb_advect(pb_engine* e, const pb_advect_args* a, pb_report* rep) {
     return PB_OK;
 }
 
+static ParticlesDev cur_particles(pb_engine* e);
+
+int32_t pb_advect_rk45(pb_engine* e, const pb_rk45_args* a, double* dt_inout, double* next_dt_inout, pb_report* rep) {
+    if (!e || !a || !rep) return fail(PB_ERR_INVALID, "NULL argument");
+    if (a->dt == 0.0 || a->dt != a->dt) return fail(PB_ERR_INVALID, "dt must be a non-zero number");
+    if (e->n && (!dt_inout || !next_dt_inout)) return fail(PB_ERR_INVALID, "NULL dt / next_dt array");
+    int32_t rc = check_fields(e, 2);
+    if (rc) return rc;
+    if (e->interp != PB_INTERP_XLINEAR_VELOCITY || e->g.curvilinear || e->ring || e->g.decomposed)
+        return fail(PB_ERR_INVALID, "AdvectionRK45 runs on resident rectilinear A-grid fields with XLinear_Velocity");
+    CK(cudaSetDevice(e->device));
+    const size_t n = (size_t)e->n;
+    DevBuf& buf = e->sout;  // dt, next_dt (f64), iters (i32)
+    if ((rc = buf.ensure(n ? n * 20 : 1))) return rc;
+    double* d_dt = (double*)buf.p;
+    double* d_ndt = d_dt + n;
+    int* d_it = (int*)(d_ndt + n);
+    if (n) {
+        CK(cudaMemcpyAsync(d_dt, dt_inout, n * 8, cudaMemcpyHostToDevice, e->stream));
+        CK(cudaMemcpyAsync(d_ndt, next_dt_inout, n * 8, cudaMemcpyHostToDevice, e->stream));
+    }
+    AdvectParams p{};
+    p.g = e->g;
+    fill_field_desc(e, p.f);
+    p.P = cur_particles(e);
+    p.scheme = PB_ADVECTION_RK45;
+    p.delete_on_error = a->delete_on_error;
+    p.dt = a->dt; p.endtime = a->endtime; p.max_iters = a->max_iters;
+    p.rep = e->d_rep;
+    zero_report(*e->h_rep);
+    CK(cudaMemcpyAsync(e->d_rep, e->h_rep, sizeof(ReportDev), cudaMemcpyHostToDevice, e->stream));
+    CK(cudaEventRecord(e->ev0, e->stream));
+    if (n) {
+        cudaError_t ce = launch_rk45(p, d_dt, d_ndt, d_it, a->next_dt_is_f32, a->tol, a->min_dt, a->max_dt, e->coord_f64 != 0,
+                                     e->f_f64[0] != 0, e->g.nt > 0, e->stream);
+        if (ce != cudaSuccess) return fail(PB_ERR_CUDA, "rk45_kernel launch failed: %s", cudaGetErrorString(ce));
+    }
+    CK(cudaEventRecord(e->ev1, e->stream));
+    CK(cudaMemcpyAsync(e->h_rep, e->d_rep, sizeof(ReportDev), cudaMemcpyDeviceToHost, e->stream));
+    e->pending = true;
+    if ((rc = pb_last_report(e, rep))) return rc;
+    if (n) {
+        cudaError_t ce = launch_rk45_finalize(p.P, d_dt, d_it, rep->max_iters_done, a->endtime, a->dt > 0 ? 1 : -1, e->stream);
+        if (ce != cudaSuccess) return fail(PB_ERR_CUDA, "rk45_finalize launch failed: %s", cudaGetErrorString(ce));
+        CK(cudaMemcpyAsync(dt_inout, d_dt, n * 8, cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaMemcpyAsync(next_dt_inout, d_ndt, n * 8, cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+    }
+    return PB_OK;
+}
+
 int32_t pb_flag_view_outside_time(pb_engine* e, double dt, double endtime) {
     if (!e) return fail(PB_ERR_INVALID, "engine is NULL");
     CK(cudaSetDevice(e->device));

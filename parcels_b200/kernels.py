@@ -14,6 +14,7 @@ __all__ = [
     "AdvectionRK2_3D",
     "AdvectionRK4",
     "AdvectionRK4_3D",
+    "AdvectionRK45",
     "DeleteParticle",
     "DiffusionUniformKh",
 ]
@@ -50,6 +51,12 @@ def AdvectionRK4_3D(particles, fieldset):  # reference kernels/_advection.py:58-
     _device_only("AdvectionRK4_3D")
 
 
+def AdvectionRK45(particles, fieldset):  # reference kernels/_advection.py:85-155
+    """Adaptive Runge-Kutta-Fehlberg 4(5) advection of (x, y) with fieldset.UV; needs a ``next_dt`` particle Variable and the
+    fieldset context RK45_tol (m), RK45_min_dt, RK45_max_dt (s)."""
+    _device_only("AdvectionRK45")
+
+
 def DiffusionUniformKh(particles, fieldset):  # reference kernels/_advectiondiffusion.py:120-153
     """Uniform-Kh Brownian displacement; needs constant fields Kh_zonal and Kh_meridional."""
     _device_only("DiffusionUniformKh")
@@ -64,3 +71,4 @@ def DeleteParticle(particles, fieldset):
 # scheme ids of include/parcels_b200.h (enum pb_scheme)
 SCHEMES = {"_none": 0, "AdvectionEE": 1, "AdvectionRK2": 2, "AdvectionRK2_3D": 3, "AdvectionRK4": 4, "AdvectionRK4_3D": 5}
 SCHEMES_3D = {"AdvectionRK2_3D", "AdvectionRK4_3D"}
+RK45 = 6  # PB_ADVECTION_RK45: own entry point (pb_advect_rk45), per-particle dt / next_dt

@@ -37,7 +37,7 @@ def _builtin_name(f):
     if n != "_none" and getattr(K, n, None) is f:
         return n
     mod = getattr(f, "__module__", "") or ""
-    if mod.startswith("parcels.kernels") and (n in K.SCHEMES or n == "DiffusionUniformKh") and n != "_none":
+    if mod.startswith("parcels.kernels") and (n in K.SCHEMES or n in ("DiffusionUniformKh", "AdvectionRK45")) and n != "_none":
         return n
     return None
 
@@ -51,7 +51,7 @@ def _delete_on_error(particles, fieldset):
 class KernelPlan:
     """The kernel list lowered to the fused device kernel's switches (include/parcels_b200.h)."""
 
-    def __init__(self, kernel_list, fieldset):
+    def __init__(self, kernel_list, fieldset, pclass=None):
         if isinstance(kernel_list, types.FunctionType):
             kernel_list = [kernel_list]
         if not isinstance(kernel_list, list):
@@ -73,6 +73,10 @@ class KernelPlan:
             names = names[:-1]
         if len(names) == 0 and self.diffusion:
             names = ["_none"]
+        self.rk45 = None
+        if "AdvectionRK45" in tokens:
+            self._setup_rk45(names, fieldset, pclass)
+            return
         self.stepwise = not (len(names) == 1 and names[0] in K.SCHEMES)
         if fieldset.time_window is not None and (self.stepwise or not self.delete_on_error):
             raise NotImplementedError("time-windowed FieldSets need a list of built-in kernels ending with the DeleteParticle token: "
@@ -113,6 +117,41 @@ class KernelPlan:
             g = fieldset.Kh_zonal.grid
             self.kh_spherical = g.is_spherical()
             self.kh_deg2m = g.deg2m
+
+
+def _setup_rk45(self, names, fieldset, pclass):
+    """AdvectionRK45 (reference _core/kernel.py:134-159 `check_fieldsets_in_kernels`): needs a `next_dt` Variable; missing
+    RK45_tol / RK45_min_dt / RK45_max_dt get the reference's defaults with a KernelWarning; on a spherical mesh the
+    tolerance is converted to degrees -- like the reference, in place, every time a kernel list is built."""
+    import warnings
+
+    from .statuscodes import KernelWarning
+
+    if names != ["AdvectionRK45"] or self.diffusion:
+        raise NotImplementedError("AdvectionRK45 runs fused on the device as [AdvectionRK45] or [AdvectionRK45, DeleteParticle]")
+    if pclass is None or "next_dt" not in [n for n, _ in pclass.variables]:
+        raise ValueError('ParticleClass requires a "next_dt" for AdvectionRK45 Kernel.')
+    if fieldset.grid.curvilinear or fieldset.interp_method != "linear" or fieldset.time_window is not None:
+        raise NotImplementedError("AdvectionRK45 is implemented for resident rectilinear A-grid fields (XLinear_Velocity)")
+    ctx = fieldset.context
+    if "RK45_tol" not in ctx:
+        warnings.warn("Setting RK45 tolerance to 10 m. Use fieldset.add_context('RK45_tol', [distance]) to change.", KernelWarning, stacklevel=4)
+        fieldset.add_context("RK45_tol", 10)
+    if fieldset.grid.is_spherical():
+        ctx["RK45_tol"] = ctx["RK45_tol"] / fieldset.grid.deg2m
+    if "RK45_min_dt" not in ctx:
+        warnings.warn("Setting RK45 minimum timestep to 1 s. Use fieldset.add_context('RK45_min_dt', [timestep]) to change.", KernelWarning, stacklevel=4)
+        fieldset.add_context("RK45_min_dt", 1)
+    if "RK45_max_dt" not in ctx:
+        warnings.warn("Setting RK45 maximum timestep to 1 day. Use fieldset.add_context('RK45_max_dt', [timestep]) to change.", KernelWarning, stacklevel=4)
+        fieldset.add_context("RK45_max_dt", 60 * 60 * 24)
+    self.rk45 = (float(ctx["RK45_tol"]), float(ctx["RK45_min_dt"]), float(ctx["RK45_max_dt"]))
+    self.stepwise = False
+    self.scheme_name, self.scheme = "AdvectionRK45", K.RK45
+    self.kh, self.kh_spherical, self.kh_deg2m = (0.0, 0.0), False, 1.0
+
+
+KernelPlan._setup_rk45 = _setup_rk45
 
 
 class ParticleSet:
@@ -210,7 +249,7 @@ class ParticleSet:
         """Can the set stay device-resident across output intervals?  Built-in kernel lists on rectilinear grids with
         the default Particle variables (extra variables live on the host; the curvilinear hint test needs host `ei`)."""
         fs = self.fieldset
-        return not plan.stepwise and not fs.grid.curvilinear and fs.time_window is None and len(self._pclass.extra) == 0
+        return not plan.stepwise and plan.rk45 is None and not fs.grid.curvilinear and fs.time_window is None and len(self._pclass.extra) == 0
 
     def _output_columns(self, t, names, indices=None):
         """Rows due for output at time ``t`` (reference `_to_write_particles`, _core/particlefile.py:198-221) of the
@@ -279,6 +318,8 @@ class ParticleSet:
                 raise ValueError("Time values cannot be NaN.")
             self._device_synced = False
             return kernel_execute_stepwise(self, plan, endtime, dt)
+        if plan.rk45 is not None:
+            return self._kernel_execute_rk45(plan, endtime, dt)
         eng = self.fieldset.engine(self.device)
         on_device = lazy and resident and self._host_stale and eng.particle_count() == self._n_device
         if on_device:
@@ -366,6 +407,40 @@ class ParticleSet:
                 if np.any(hit):
                     raise_for_state(code, d["z"][hit], d["y"][hit], d["x"][hit], d["t"][hit])
 
+    def _kernel_execute_rk45(self, plan, endtime, dt):
+        """``Kernel.execute`` with AdvectionRK45 (reference _core/kernel.py:108-120,190-245): per-particle dt / next_dt,
+        Repeat loop and step doubling run inside ONE device kernel (csrc/rk45.cu); dt is not reset to the nominal step."""
+        d = self._data
+        n = len(self)
+        self._device_synced = False
+        d["state"][:] = StatusCode.Evaluate
+        if n == 0:
+            return
+        if np.isnan(d["t"]).any():
+            raise ValueError(f"Time values for particles with indices {np.where(np.isnan(d['t']))[0]} cannot be NaN.")
+        eng = self.fieldset.engine(self.device)
+        ei_last = np.ascontiguousarray(d["ei"][:, -1])
+        eng.upload_particles(d, ei_last)
+        dt_arr = np.ascontiguousarray(d["dt"], dtype=np.float64)
+        ndt_arr = np.ascontiguousarray(d["next_dt"], dtype=np.float64)
+        tol, min_dt, max_dt = plan.rk45
+        rep = eng.advect_rk45(dt, endtime, tol, min_dt, max_dt, dt_arr, ndt_arr, next_dt_is_f32=d["next_dt"].dtype == np.float32,
+                              delete_on_error=plan.delete_on_error)  # fmt: skip
+        self.last_report = rep
+        eng.download_particles(d, ei_last)
+        d["ei"][:, -1] = ei_last
+        d["dt"][:] = dt_arr  # RK45 mode: dt is NOT reset to the nominal step (kernel.py:224-226)
+        d["next_dt"][:] = ndt_arr
+        if rep["n_error"] > 0:
+            stuck = np.where(d["state"] == StatusCode.Error)[0]
+            raise RuntimeError(f"AdvectionRK45: particles {stuck[:10]} have dt == 0 before endtime={endtime}; the reference's loop "
+                               "never terminates on them (kernel.py:199-203 clamps the dt of particles that finished an earlier "
+                               "interval to 0 and RK45 mode never restores it).  Reset pset.dt before continuing.")  # fmt: skip
+        if rep["max_state"] == StatusCode.Delete:
+            dele = np.where(d["state"] == StatusCode.Delete)[0]
+            if len(dele) > 0:
+                self.remove_indices(dele)
+
     def _advect_windowed(self, eng, plan, d, dt, endtime, args):
         """Time-slab streaming: advance until every particle reached ``endtime``, sliding the resident time
         levels as the particles' clock crosses them; the next level is copied while the kernel runs."""
@@ -400,7 +475,7 @@ class ParticleSet:
         """reference _core/particleset.py:355-470 (outer loop) and :497-585 (argument handling)."""
         if len(self) == 0:
             return
-        plan = KernelPlan(kernels, self.fieldset)
+        plan = KernelPlan(kernels, self.fieldset, self._pclass)
         try:
             dt = _to_float_seconds(dt)
             sign_dt = int(np.sign(dt))

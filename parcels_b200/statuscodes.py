@@ -93,3 +93,7 @@ ERRORS_TO_THROW = (
     StatusCode.ErrorGridSearching,
     StatusCode.Error,
 )
+
+
+class KernelWarning(RuntimeWarning):
+    """Warning that a kernel set a default for a missing setting (reference _core/warnings.py)."""
