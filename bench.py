@@ -68,6 +68,35 @@ def c2_field(nx=1440, ny=720, nz=50, nt=3, seed=1):
     return dict(lon=lon, lat=lat, depth=depth, times=times, U=U, V=V, W=W, mesh="spherical")
 
 
+def ns_field_device(device=0, nx=4320, ny=2160, nz=50, nt=3, seed=4):
+    """north-star target field (BASELINE.json north_star: "1e7 particles on a 1/12 deg 3D rectilinear field", 1 GPU):
+    the config-2 formulas at 4320 x 2160 x 50, T=3 -- 5.6 GB per component, 16.8 GB in all -- generated IN HBM with
+    torch and handed to the engine without a copy (FieldSet accepts __cuda_array_interface__ arrays)."""
+    import torch
+
+    dev = torch.device(f"cuda:{device}")
+    g = torch.Generator(device=dev).manual_seed(seed)
+    lon = np.linspace(-180.0, 180.0, nx)
+    lat = np.linspace(-80.0, 80.0, ny)
+    depth = 5500.0 * (np.linspace(0.0, 1.0, nz) ** 1.8)
+    times = np.arange(nt) * 86400.0
+    X = (2 * np.pi * torch.linspace(0, 1, nx, device=dev))[None, None, :]
+    Y = (2 * np.pi * torch.linspace(0, 1, ny, device=dev))[None, :, None]
+    Z = torch.linspace(0, 1, nz, device=dev)[:, None, None]
+    U, V, W = (torch.empty((nt, nz, ny, nx), dtype=torch.float32, device=dev) for _ in range(3))
+
+    def noise():
+        return torch.rand((nz, ny, nx), generator=g, device=dev, dtype=torch.float32) * 0.1 - 0.05
+
+    for k in range(nt):
+        T = float(k)
+        U[k] = torch.sin(3 * X + 0.3 * T) * torch.cos(2 * Y) * (1 - 0.5 * Z) * 0.6 + torch.cos(5 * Y + T) * 0.3 + noise()
+        V[k] = torch.cos(2 * X + 0.2 * T) * torch.sin(4 * Y) * (1 - 0.3 * Z) * 0.6 + torch.sin(3 * X) * 0.25 + noise()
+        W[k] = (torch.sin(2 * X) * torch.sin(3 * Y) * torch.sin(np.pi * Z) * float(np.cos(0.5 * T)) * 0.9 + noise()) * 1e-3
+    torch.cuda.synchronize(dev)
+    return dict(lon=lon, lat=lat, depth=depth, times=times, U=U, V=V, W=W, mesh="spherical")
+
+
 def c2_particles(field, n, seed):
     rng = np.random.default_rng(seed)
     return dict(x=rng.uniform(-170, 170, n), y=rng.uniform(-70, 70, n), z=rng.uniform(5, 5000, n), t=np.zeros(n))
@@ -241,6 +270,10 @@ WORKLOADS = {
                desc="BASELINE.json configs[1] -- AdvectionRK4_3D, rectilinear A-grid 1440x720x50 T=3 f32 U,V,W, spherical"),
     "c2_small": dict(field=c2_field, fkw=dict(nx=360, ny=180, nz=20, nt=3), particles=c2_particles, n=100_000, dt=600.0,
                      nsteps=144, kernels=["AdvectionRK4_3D"], bytes=832, desc="small functional variant of c2"),
+    "ns": dict(field=ns_field_device, fkw=dict(nx=4320, ny=2160, nz=50, nt=3), particles=c2_particles, n=10_000_000, dt=600.0,
+               nsteps=144, kernels=["AdvectionRK4_3D"], bytes=832, device_field=True,
+               desc="BASELINE.json north_star target -- AdvectionRK4_3D, 1e7 particles on a 1/12 deg rectilinear A-grid "
+                    "4320x2160x50 T=3 f32 U,V,W (16.8 GB, generated in HBM), spherical"),
     "c3": dict(field=c3_field, fkw=dict(nx=1442, ny=1021, nt=3), particles=c3_particles, n=10_000_000, dt=3600.0,
                nsteps=48, kernels=["AdvectionRK4"], bytes=320,
                desc="BASELINE.json configs[2] -- AdvectionRK4, curvilinear C-grid ORCA025 shape 1442x1021 T=3, f32 lon/lat, "
@@ -445,7 +478,11 @@ def main():
 
     if a.impl == "reference":
         if rank == 0:
-            run_reference_arm(a, w, w["field"](**w["fkw"]))
+            if w.get("device_field"):
+                print(json.dumps({"impl": "reference", "unavailable": f"workload {a.workload} builds its field in HBM; the CPU arm is "
+                                                                       "timed on --workload c2 (same kernels, same arithmetic)"}))  # fmt: skip
+            else:
+                run_reference_arm(a, w, w["field"](**w["fkw"]))
         return
 
     import torch
@@ -462,7 +499,12 @@ def main():
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
 
-    field = w["field"](**w["fkw"])
+    if w.get("device_field"):
+        torch.cuda.set_device(local_rank)
+        field = w["field"](device=local_rank, **w["fkw"])
+        a.no_cpu_baseline = True  # the NumPy / C arms need the field on the host: they are timed on c2
+    else:
+        field = w["field"](**w["fkw"])
     fs = pb.FieldSet.from_arrays(lon=field["lon"], lat=field["lat"], depth=field["depth"], time=field["times"],
                                  U=field["U"], V=field["V"], W=field["W"], mesh=field["mesh"],
                                  interp_method=field.get("interp", "linear"),
@@ -560,7 +602,7 @@ def main():
         return
     peak, peak_src = measured_peak()
     achieved = w["bytes"] * steps_per_launch / (kernel_ms * 1e-3) / 1e9
-    fbytes = sum(field[k].nbytes for k in ("U", "V", "W") if field.get(k) is not None)
+    fbytes = sum(int(np.prod(field[k].shape)) * 4 for k in ("U", "V", "W") if field.get(k) is not None)
     line = {
         "metric": METRIC, "value": value, "unit": "particle-steps/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": dev_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",

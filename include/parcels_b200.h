@@ -249,6 +249,32 @@ typedef struct pb_rk45_args {
 } pb_rk45_args;
 int32_t pb_advect_rk45(pb_engine* e, const pb_rk45_args* args, double* dt_inout, double* next_dt_inout, pb_report* rep);
 
+/* ---- AdvectionDiffusionM1 / AdvectionDiffusionEM (kernels/_advectiondiffusion.py:21-117) under Kernel.execute's loop:
+ * 2-D advection with fieldset.UV plus diffusion with the spatially varying diffusivity fields Kh_zonal / Kh_meridional
+ * -- scalar fields on the same rectilinear grid (XLinear), uploaded into slots >= 3 with pb_field_upload -- and their
+ * central-difference gradients over fieldset.dres.  Seven field evaluations per particle and step, each raising the
+ * particle's state and `ei` like Field.eval (_core/field.py:144-191); unit conversion of the diffusivities on spherical
+ * meshes as meters_to_degrees_zonal / _meridional (:11-18: float32 cos of the float32 latitude).  dres is the Python float
+ * the reference adds to the float32 positions (weak scalar: positions stay float32); deg2m_sq = pow(grid.deg2m, 2).
+ * The Wiener increments come from the engine's Philox4x32-10 stream keyed like pb_advect's DiffusionUniformKh (the
+ * reference draws from NumPy's global MT19937: statistical parity, bit parity of the deterministic part).
+ * Same loop semantics, max_iters replay contract and pb_report as pb_advect.  Resident rectilinear A-grid fields. */
+enum pb_advdiff_scheme { PB_ADVDIFF_M1 = 0, PB_ADVDIFF_EM = 1 };
+typedef struct pb_advdiff_args {
+    int32_t scheme;             /* enum pb_advdiff_scheme */
+    int32_t delete_on_error;
+    int32_t kh_zonal_slot;      /* field slots (>= 3) of Kh_zonal / Kh_meridional: same dtype, both with or both without time */
+    int32_t kh_meridional_slot;
+    double dt;
+    double endtime;
+    double dres;                /* fieldset.dres */
+    double deg2m_sq;            /* pow(Kh_meridional.grid.deg2m, 2); unused on flat meshes */
+    uint64_t seed;
+    uint64_t rng_call;
+    int64_t max_iters;          /* < 0: run to endtime */
+} pb_advdiff_args;
+int32_t pb_advect_diffusion(pb_engine* e, const pb_advdiff_args* args, pb_report* rep);
+
 /* VectorField.eval at n arbitrary sample points (fieldset.UV[t, z, y, x] / fieldset.UVW[...],
  * _core/field.py:250-304): time + grid search, interpolation, unit conversion, error states
  * (state_out starts at Evaluate and is raised like particles.state), ei_out = ravel_index of the cell.

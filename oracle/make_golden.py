@@ -393,6 +393,71 @@ def make_rk45_golden():
     np.savez_compressed(os.path.join(GOLDEN, "rk45.npz"), **out)
 
 
+# name -> (base case of tests/cases.py, kernel, Kh dtype, Kh fields have a time dimension, dt, runtime, delete-on-error, np.random seed)
+ADVDIFF_CASES = {
+    "m1_flat": ("flat_f32c_f64d", "AdvectionDiffusionM1", "f8", True, 10.0, 140.0, True, 1636),
+    "em_sph": ("c2_small", "AdvectionDiffusionEM", "f4", True, 600.0, 6000.0, True, 1234),
+    "m1_all_f32_static": ("all_f32", "AdvectionDiffusionM1", "f4", False, 300.0, 3300.0, True, 7),
+    "em_f64_static": ("rk2_3d", "AdvectionDiffusionEM", "f8", False, 50.0, 700.0, True, 8),
+    "m1_backward": ("backward", "AdvectionDiffusionM1", "f4", True, -600.0, 5400.0, True, 9),
+    "em_raise": ("raise_oob", "AdvectionDiffusionEM", "f8", True, 100.0, 1500.0, False, 10),
+}
+
+
+def advdiff_inputs(c, kdtype, ktime, seed=5):
+    """Kh_zonal / Kh_meridional (positive, smooth + noise, (T or 1, Z, Y, X)) and dres for an advection-diffusion case."""
+    rng = np.random.default_rng(seed)
+    T = c["U"].shape[0] if ktime else 1
+    shape = (T,) + c["U"].shape[1:]
+    ny, nx = shape[2], shape[3]
+    X = np.linspace(0, 1, nx)[None, None, None, :]
+    Y = np.linspace(0, 1, ny)[None, None, :, None]
+    scale = 40.0 if c["mesh"] == "flat" else 4000.0
+    kz = scale * (1.5 + np.tanh(6 * (X - 0.5)) + 0.3 * np.sin(5 * Y) + 0.2 * rng.uniform(-1, 1, shape))
+    km = scale * (1.5 + np.tanh(4 * (Y - 0.4)) + 0.3 * np.cos(7 * X) + 0.2 * rng.uniform(-1, 1, shape))
+    dres = float(np.float64(c["lon"][1]) - np.float64(c["lon"][0]))
+    return kz.astype(kdtype), km.astype(kdtype), dres
+
+
+def make_advdiff_golden():
+    """AdvectionDiffusionM1 / EM under the reference's own Kernel.execute; the Wiener increments are the reference's
+    (np.random.normal after np.random.seed): the oracle restatement draws the same stream."""
+    import warnings
+
+    import cases as tc
+    from oracle import ref_harness as rh
+
+    out = {}
+    for name, (base, kern, kd, ktime, dt, runtime, delete, rseed) in ADVDIFF_CASES.items():
+        c = tc.build(tc.CASES[base])
+        kz, km, dres = advdiff_inputs(c, kd, ktime)
+        fs = rh.build_fieldset(lon=c["lon"], lat=c["lat"], depth=c["depth"], times=c["times"], U=c["U"], V=c["V"], W=None,
+                               mesh=c["mesh"], scalars={"Kh_zonal": (kz, "linear"), "Kh_meridional": (km, "linear")})  # fmt: skip
+        fs.add_context("dres", dres)
+        z = np.abs(np.asarray(c["z"]))
+        ps = rh.make_pset(fs, x=c["x"], y=c["y"], z=z, t=c["t"])
+        k = rh.kernels()
+        kl = [getattr(k, kern)]
+        if delete:
+            def DeleteParticle(particles, fieldset):
+                particles.state = np.where(particles.state >= 50, 30, particles.state)
+
+            kl.append(DeleteParticle)
+        err = ""
+        np.random.seed(rseed)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            try:
+                ps.execute(kl, dt=dt, runtime=runtime, verbose_progress=False)
+            except Exception as e:  # noqa: BLE001 -- the reference's error classes
+                err = type(e).__name__
+        for key in ("particle_id", "x", "y", "z", "t", "dt", "state", "ei", "dx", "dy"):
+            out[f"{name}/{key}"] = ps._data[key]
+        out[f"{name}/error"] = np.array(err)
+        print(f"advdiff {name}: {len(ps._data['x'])} of {len(c['x'])} particles left, states {np.unique(ps._data['state'])}, error {err!r}")
+    np.savez_compressed(os.path.join(GOLDEN, "advdiff.npz"), **out)
+
+
 if __name__ == "__main__":
     os.makedirs(GOLDEN, exist_ok=True)
     make_v3("linear", "v3_jit_linear.npz")
@@ -403,3 +468,4 @@ if __name__ == "__main__":
     make_output_golden()
     make_scalar_golden()
     make_rk45_golden()
+    make_advdiff_golden()

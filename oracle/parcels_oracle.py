@@ -115,6 +115,7 @@ class OFieldSet:
         self.interp = interp
         self.context = {}  # FieldSet.add_context (_core/fieldset.py:207-222), e.g. RK45_tol / RK45_min_dt / RK45_max_dt
         self.constants = dict(constants or {})
+        self.scalars = {}  # scalar fields on the same grid: name -> (array (T, Z, Y, X), "linear" | "nearest" | "cgrid_tracer")
         self.const_spherical = grid.spherical if const_mesh is None else (const_mesh == "spherical")
         self.const_deg2m = DEG2M_EARTH if self.const_spherical else 1.0
 
@@ -657,6 +658,81 @@ class DiffusionUniformKh:
         by = np.sqrt(2 * kh_meridional)
         p.dx = p.dx + bx * dWx
         p.dy = p.dy + by * dWy
+
+
+class _AdvectionDiffusion:
+    """kernels/_advectiondiffusion.py:11-18,21-117 (``AdvectionDiffusionM1`` / ``AdvectionDiffusionEM``): 2-D
+    advection-diffusion with spatially varying diffusivity fields ``Kh_zonal`` / ``Kh_meridional`` (scalar fields on the
+    fieldset's grid, ``fs.scalars``) and the finite-difference step ``fs.context["dres"]``.  ``normal(view)`` supplies
+    the two N(0,1) draws per particle (default: the reference's legacy global RandomState, so that ``np.random.seed``
+    reproduces the reference bit for bit); tests inject the engine's Philox stream."""
+
+    scheme = "M1"
+
+    def __init__(self, normal=None):
+        self.normal = normal
+
+    def __call__(self, p: View, fs: OFieldSet):
+        if self.normal is None:
+            dWx = np.random.normal(0, np.sqrt(np.fabs(p.dt)))
+            dWy = np.random.normal(0, np.sqrt(np.fabs(p.dt)))
+        else:
+            zx, zy = self.normal(p)
+            dWx = zx * np.sqrt(np.fabs(p.dt))
+            dWy = zy * np.sqrt(np.fabs(p.dt))
+        dres = fs.context["dres"]
+        khz, mz = fs.scalars["Kh_zonal"]
+        khm, mm = fs.scalars["Kh_meridional"]
+        sph, deg2m = fs.grid.spherical, fs.grid.deg2m
+
+        def zonal(v, lat):  # meters_to_degrees_zonal (:11-13)
+            return v / pow(deg2m * np.cos(lat * np.pi / 180), 2)
+
+        def merid(v):  # meters_to_degrees_meridional (:16-18)
+            return v / pow(deg2m, 2)
+
+        if self.scheme == "EM":
+            u, v = eval_uvw(fs, p.t, p.z, p.y, p.x, p, False)
+        Kxp1 = eval_scalar(fs, khz, mz, p.t, p.z, p.y, p.x + dres, p)
+        Kxm1 = eval_scalar(fs, khz, mz, p.t, p.z, p.y, p.x - dres, p)
+        if sph:
+            Kxp1 = zonal(Kxp1, p.y)
+            Kxm1 = zonal(Kxm1, p.y)
+        dKdx = (Kxp1 - Kxm1) / (2 * dres)
+        if self.scheme == "M1":
+            u, v = eval_uvw(fs, p.t, p.z, p.y, p.x, p, False)
+        kh_zonal = eval_scalar(fs, khz, mz, p.t, p.z, p.y, p.x, p)
+        if sph:
+            kh_zonal = zonal(kh_zonal, p.y)
+        bx = np.sqrt(2 * kh_zonal)
+        Kyp1 = eval_scalar(fs, khm, mm, p.t, p.z, p.y + dres, p.x, p)
+        Kym1 = eval_scalar(fs, khm, mm, p.t, p.z, p.y - dres, p.x, p)
+        if sph:
+            Kyp1 = merid(Kyp1)
+            Kym1 = merid(Kym1)
+        dKdy = (Kyp1 - Kym1) / (2 * dres)
+        kh_meridional = eval_scalar(fs, khm, mm, p.t, p.z, p.y, p.x, p)
+        if sph:
+            kh_meridional = merid(kh_meridional)
+        by = np.sqrt(2 * kh_meridional)
+        if self.scheme == "M1":  # :64-66
+            p.dx = p.dx + (u * p.dt + 0.5 * dKdx * (dWx**2 + p.dt) + bx * dWx)
+            p.dy = p.dy + (v * p.dt + 0.5 * dKdy * (dWy**2 + p.dt) + by * dWy)
+        else:  # :85,101,115-117
+            ax = u + dKdx
+            ay = v + dKdy
+            p.dx = p.dx + (ax * p.dt + bx * dWx)
+            p.dy = p.dy + (ay * p.dt + by * dWy)
+
+
+class AdvectionDiffusionM1(_AdvectionDiffusion):
+    __name__ = "AdvectionDiffusionM1"
+    scheme = "M1"
+
+
+class AdvectionDiffusionEM(_AdvectionDiffusion):
+    __name__ = "AdvectionDiffusionEM"
+    scheme = "EM"
 
 
 def DeleteOnError(p: View, fs: OFieldSet):

@@ -10,6 +10,8 @@ from . import kernels
 __version__ = "0.1.0"
 from .fieldset import Field, FieldSet, VectorField, XGrid
 from .kernels import (
+    AdvectionDiffusionEM,
+    AdvectionDiffusionM1,
     AdvectionEE,
     AdvectionRK2,
     AdvectionRK2_3D,
@@ -34,7 +36,7 @@ from .statuscodes import (
 )
 
 __all__ = [
-    "AdvectionEE", "AdvectionRK2", "AdvectionRK2_3D", "AdvectionRK4", "AdvectionRK4_3D", "AdvectionRK45", "DeleteParticle",
+    "AdvectionDiffusionEM", "AdvectionDiffusionM1", "AdvectionEE", "AdvectionRK2", "AdvectionRK2_3D", "AdvectionRK4", "AdvectionRK4_3D", "AdvectionRK45", "DeleteParticle",
     "DiffusionUniformKh", "Field", "FieldInterpolationError", "FieldOutOfBoundError", "FieldOutOfBoundSurfaceError",
     "FieldSet", "GeneralError", "GridSearchingError", "KernelWarning", "OutsideTimeInterval", "Particle", "ParticleClass", "ParticleFile", "ParticleSet", "Variable", "read_particlefile", "StatusCode",
     "VectorField", "XGrid", "kernels",

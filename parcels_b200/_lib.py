@@ -52,6 +52,22 @@ class Rk45Args(C.Structure):
     ]
 
 
+class AdvDiffArgs(C.Structure):
+    _fields_ = [
+        ("scheme", C.c_int32),
+        ("delete_on_error", C.c_int32),
+        ("kh_zonal_slot", C.c_int32),
+        ("kh_meridional_slot", C.c_int32),
+        ("dt", C.c_double),
+        ("endtime", C.c_double),
+        ("dres", C.c_double),
+        ("deg2m_sq", C.c_double),
+        ("seed", C.c_uint64),
+        ("rng_call", C.c_uint64),
+        ("max_iters", C.c_int64),
+    ]
+
+
 class Report(C.Structure):
     _fields_ = [
         ("particle_steps", C.c_int64),
@@ -111,6 +127,7 @@ SYMBOLS = {
     "pb_advect": (C.c_int32, [_P, C.POINTER(AdvectArgs), C.POINTER(Report)]),
     "pb_advect_async": (C.c_int32, [_P, C.POINTER(AdvectArgs)]),
     "pb_advect_rk45": (C.c_int32, [_P, _P, _P, _P, _P]),
+    "pb_advect_diffusion": (C.c_int32, [_P, C.POINTER(AdvDiffArgs), C.POINTER(Report)]),
     "pb_last_report": (C.c_int32, [_P, C.POINTER(Report)]),
     "pb_sample_velocity": (C.c_int32, [_P, C.c_int64, _P, _P, _P, _P, C.c_int32, C.c_int32, _P, C.c_int32, _P, _P, _P, _P, _P]),
     "pb_sample_scalar": (C.c_int32, [_P, C.c_int32, C.c_int32, C.c_int64, _P, _P, _P, _P, C.c_int32, _P, _P, _P, _P, _P]),

@@ -486,6 +486,9 @@ cudaError_t launch_rk45(const AdvectParams& p, double* dt, double* next_dt, int*
                         double max_dt, bool coord_f64, bool data_f64, bool has_time, cudaStream_t s);
 cudaError_t launch_rk45_finalize(const ParticlesDev& P, double* dt, const int* iters, long long total_iters, double endtime, int sign,
                                  cudaStream_t s);
+// AdvectionDiffusionM1 (em = 0) / AdvectionDiffusionEM (em = 1) with the diffusivity fields fkz, fkm  (advdiff.cu)
+cudaError_t launch_advdiff(const AdvectParams& p, const FieldDev& fkz, const FieldDev& fkm, int em, double dres, double deg2m_sq,
+                           bool coord_f64, bool uv_f64, bool kh_f64, bool uv_time, bool kh_time, cudaStream_t s);
 // scalar Field.eval on a rectilinear grid, f.p[0] = the field: mode 3 XLinear, 4 XNearest, 5 CGrid_Tracer  (aslip.cu)
 cudaError_t launch_sample_scalar(const SampleParams& p, int mode, bool coord_f64, bool data_f64, bool has_time, cudaStream_t s);
 cudaError_t launch_sample_agrid_alt(const SampleParams& p, int mode, bool coord_f64, bool data_f64, bool has_time, int nc, cudaStream_t s);

@@ -929,6 +929,60 @@ int32_t pb_advect_rk45(pb_engine* e, const pb_rk45_args* a, double* dt_inout, do
     return PB_OK;
 }
 
+// FieldDev of a scalar field slot (p[0] only); validated against the grid like pb_sample_scalar does
+static int32_t scalar_field_desc(pb_engine* e, int32_t slot, FieldDev& f) {
+    if (slot < 3 || slot >= PB_MAX_FIELDS || !e->fptr[slot]) return fail(PB_ERR_STATE, "no scalar field in slot %d", slot);
+    const long long T = e->fshape[slot][0], Z = e->fshape[slot][1], Y = e->fshape[slot][2], X = e->fshape[slot][3];
+    if ((X > 1 && X != e->g.nx) || (Y > 1 && Y != e->g.ny) || (Z > 1 && e->g.nz > 0 && Z != e->g.nz) || (T > 1 && T != e->g.nt))
+        return fail(PB_ERR_INVALID, "field shape (%lld,%lld,%lld,%lld) does not match grid nodes (nt=%d nz=%d ny=%d nx=%d)", T, Z, Y, X,
+                    e->g.nt, e->g.nz, e->g.ny, e->g.nx);
+    if (Z > 1 && e->g.nz == 0) return fail(PB_ERR_INVALID, "field has a depth dimension but the grid has no Z axis");
+    f = FieldDev{};
+    f.p[0] = e->fptr[slot];
+    f.T = (int)T; f.Z = (int)Z; f.Y = (int)Y; f.X = (int)X;
+    f.sX = X > 1 ? 1 : 0; f.sY = Y > 1 ? X : 0; f.sZ = Z > 1 ? X * Y : 0; f.sT = T > 1 ? X * Y * Z : 0;
+    f.ring = (int)T; f.windowed = 0;
+    return PB_OK;
+}
+
+int32_t pb_advect_diffusion(pb_engine* e, const pb_advdiff_args* a, pb_report* rep) {
+    if (!e || !a || !rep) return fail(PB_ERR_INVALID, "NULL argument");
+    if (a->dt == 0.0 || a->dt != a->dt) return fail(PB_ERR_INVALID, "dt must be a non-zero number");
+    if (a->scheme != PB_ADVDIFF_M1 && a->scheme != PB_ADVDIFF_EM) return fail(PB_ERR_INVALID, "unknown advection-diffusion scheme %d", a->scheme);
+    if (!(a->dres == a->dres) || a->dres == 0.0) return fail(PB_ERR_INVALID, "dres must be a non-zero number");
+    int32_t rc = check_fields(e, 2);
+    if (rc) return rc;
+    if (e->interp != PB_INTERP_XLINEAR_VELOCITY || e->g.curvilinear || e->ring || e->g.decomposed)
+        return fail(PB_ERR_INVALID, "AdvectionDiffusionM1/EM run on resident rectilinear A-grid fields with XLinear_Velocity");
+    if (!e->have_pid) return fail(PB_ERR_STATE, "diffusion needs particle_id (RNG counter)");
+    FieldDev fkz, fkm;
+    if ((rc = scalar_field_desc(e, a->kh_zonal_slot, fkz))) return rc;
+    if ((rc = scalar_field_desc(e, a->kh_meridional_slot, fkm))) return rc;
+    if (e->f_f64[a->kh_zonal_slot] != e->f_f64[a->kh_meridional_slot] || (fkz.T > 1) != (fkm.T > 1))
+        return fail(PB_ERR_INVALID, "Kh_zonal and Kh_meridional must share dtype and time dimension");
+    CK(cudaSetDevice(e->device));
+    AdvectParams p{};
+    p.g = e->g;
+    fill_field_desc(e, p.f);
+    p.P = cur_particles(e);
+    p.delete_on_error = a->delete_on_error;
+    p.dt = a->dt; p.endtime = a->endtime; p.max_iters = a->max_iters;
+    p.seed = a->seed; p.rng_call = a->rng_call;
+    p.rep = e->d_rep;
+    zero_report(*e->h_rep);
+    CK(cudaMemcpyAsync(e->d_rep, e->h_rep, sizeof(ReportDev), cudaMemcpyHostToDevice, e->stream));
+    CK(cudaEventRecord(e->ev0, e->stream));
+    if (e->n > 0) {
+        cudaError_t ce = launch_advdiff(p, fkz, fkm, a->scheme == PB_ADVDIFF_EM, a->dres, a->deg2m_sq, e->coord_f64 != 0, e->f_f64[0] != 0,
+                                        e->f_f64[a->kh_zonal_slot] != 0, e->g.nt > 0, fkz.T > 1, e->stream);
+        if (ce != cudaSuccess) return fail(PB_ERR_CUDA, "advdiff_kernel launch failed: %s", cudaGetErrorString(ce));
+    }
+    CK(cudaEventRecord(e->ev1, e->stream));
+    CK(cudaMemcpyAsync(e->h_rep, e->d_rep, sizeof(ReportDev), cudaMemcpyDeviceToHost, e->stream));
+    e->pending = true;
+    return pb_last_report(e, rep);
+}
+
 int32_t pb_flag_view_outside_time(pb_engine* e, double dt, double endtime) {
     if (!e) return fail(PB_ERR_INVALID, "engine is NULL");
     CK(cudaSetDevice(e->device));

@@ -185,10 +185,24 @@ class Engine:
                           float(kh[0]), float(kh[1]), float(kh_deg2m), int(seed), int(rng_call), int(max_iters),
                           int(bool(hint_all_zero)), int(bool(resume)), int(bool(kernels_only)), 0)  # fmt: skip
 
-    def advect(self, args: AdvectArgs) -> dict:
+    def advect(self, args) -> dict:
+        """``Kernel.execute`` on the device: ``args`` from :meth:`make_args` (pb_advect) or :meth:`make_advdiff_args`
+        (pb_advect_diffusion: AdvectionDiffusionM1 / EM)."""
+        from ._lib import AdvDiffArgs
+
         rep = Report()
-        check(self._lib.pb_advect(self._h, C.byref(args), C.byref(rep)))
+        if isinstance(args, AdvDiffArgs):
+            check(self._lib.pb_advect_diffusion(self._h, C.byref(args), C.byref(rep)))
+        else:
+            check(self._lib.pb_advect(self._h, C.byref(args), C.byref(rep)))
         return _report_dict(rep)
+
+    @staticmethod
+    def make_advdiff_args(scheme, dt, endtime, *, kh_slots, dres, deg2m_sq, delete_on_error=False, seed=0, rng_call=0, max_iters=-1):
+        from ._lib import AdvDiffArgs
+
+        return AdvDiffArgs(int(scheme), int(delete_on_error), int(kh_slots[0]), int(kh_slots[1]), float(dt), float(endtime),
+                           float(dres), float(deg2m_sq), int(seed), int(rng_call), int(max_iters))  # fmt: skip
 
     def advect_rk45(self, dt, endtime, tol, min_dt, max_dt, dt_arr, next_dt_arr, *, next_dt_is_f32=True, delete_on_error=False,
                     max_iters=-1) -> dict:

@@ -44,6 +44,14 @@ def _to_seconds(time):
     return sec - sec[0], sec[0]
 
 
+def _is_device_array(a) -> bool:
+    """An array that already lives in HBM (torch CUDA tensor, CuPy array ...): exposes __cuda_array_interface__."""
+    try:
+        return isinstance(a.__cuda_array_interface__, dict)
+    except Exception:  # absent, or a torch CPU tensor (the property raises)
+        return False
+
+
 class XGrid:
     """Structured grid (rectilinear: 1-D lon/lat; depth optional).  ``xdim/ydim/zdim`` are cell
     counts as in the reference (``_core/xgrid.py:21-24,208-231``); they default to nodes - 1,
@@ -238,7 +246,7 @@ class FieldSet:
         for name, arr in (("U", U), ("V", V), ("W", W)):
             if arr is None:
                 continue
-            if self.time_window is None:
+            if self.time_window is None and not _is_device_array(arr):
                 arr = np.asarray(arr)
             if len(arr.shape) != 4:
                 raise ValueError(f"{name} must be laid out (T, Z, Y, X); got shape {arr.shape}")
@@ -336,7 +344,13 @@ class FieldSet:
             for slot, name in enumerate(("U", "V", "W")):
                 if name in self.fields:
                     d = self.fields[name].data
-                    if self.time_window is None:
+                    if _is_device_array(d):
+                        # already in HBM (e.g. a torch CUDA tensor): attached without a copy, kept alive by the engine
+                        cai = d.__cuda_array_interface__
+                        if cai.get("strides") is not None or cai["typestr"] not in ("<f4", "<f8"):
+                            raise ValueError(f"device field {name} must be C-contiguous float32/float64 (T, Z, Y, X)")
+                        eng.attach_field_device(slot, int(cai["data"][0]), cai["typestr"] == "<f8", tuple(cai["shape"]), keepalive=d)
+                    elif self.time_window is None:
                         eng.upload_field(slot, d)
                     else:
                         eng.window_create(slot, d.dtype, d.shape, self.time_window)

@@ -15,6 +15,8 @@ __all__ = [
     "AdvectionRK4",
     "AdvectionRK4_3D",
     "AdvectionRK45",
+    "AdvectionDiffusionM1",
+    "AdvectionDiffusionEM",
     "DeleteParticle",
     "DiffusionUniformKh",
 ]
@@ -57,6 +59,17 @@ def AdvectionRK45(particles, fieldset):  # reference kernels/_advection.py:85-15
     _device_only("AdvectionRK45")
 
 
+def AdvectionDiffusionM1(particles, fieldset):  # reference kernels/_advectiondiffusion.py:21-66
+    """2-D advection-diffusion, Milstein scheme of first order; needs scalar fields Kh_zonal and Kh_meridional on the
+    fieldset's grid (``FieldSet.add_field``) and the context value ``dres`` (finite-difference step for the Kh gradients)."""
+    _device_only("AdvectionDiffusionM1")
+
+
+def AdvectionDiffusionEM(particles, fieldset):  # reference kernels/_advectiondiffusion.py:69-117
+    """2-D advection-diffusion, Euler-Maruyama scheme; same requirements as AdvectionDiffusionM1."""
+    _device_only("AdvectionDiffusionEM")
+
+
 def DiffusionUniformKh(particles, fieldset):  # reference kernels/_advectiondiffusion.py:120-153
     """Uniform-Kh Brownian displacement; needs constant fields Kh_zonal and Kh_meridional."""
     _device_only("DiffusionUniformKh")
@@ -71,4 +84,5 @@ def DeleteParticle(particles, fieldset):
 # scheme ids of include/parcels_b200.h (enum pb_scheme)
 SCHEMES = {"_none": 0, "AdvectionEE": 1, "AdvectionRK2": 2, "AdvectionRK2_3D": 3, "AdvectionRK4": 4, "AdvectionRK4_3D": 5}
 SCHEMES_3D = {"AdvectionRK2_3D", "AdvectionRK4_3D"}
+ADVDIFF = {"AdvectionDiffusionM1": 0, "AdvectionDiffusionEM": 1}  # enum pb_advdiff_scheme: own entry point (pb_advect_diffusion)
 RK45 = 6  # PB_ADVECTION_RK45: own entry point (pb_advect_rk45), per-particle dt / next_dt

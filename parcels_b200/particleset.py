@@ -37,7 +37,7 @@ def _builtin_name(f):
     if n != "_none" and getattr(K, n, None) is f:
         return n
     mod = getattr(f, "__module__", "") or ""
-    if mod.startswith("parcels.kernels") and (n in K.SCHEMES or n in ("DiffusionUniformKh", "AdvectionRK45")) and n != "_none":
+    if mod.startswith("parcels.kernels") and (n in K.SCHEMES or n in K.ADVDIFF or n in ("DiffusionUniformKh", "AdvectionRK45")) and n != "_none":
         return n
     return None
 
@@ -74,8 +74,12 @@ class KernelPlan:
         if len(names) == 0 and self.diffusion:
             names = ["_none"]
         self.rk45 = None
+        self.advdiff = None
         if "AdvectionRK45" in tokens:
             self._setup_rk45(names, fieldset, pclass)
+            return
+        if any(n in K.ADVDIFF for n in tokens if n):
+            self._setup_advdiff(names, fieldset)
             return
         self.stepwise = not (len(names) == 1 and names[0] in K.SCHEMES)
         if fieldset.time_window is not None and (self.stepwise or not self.delete_on_error):
@@ -152,6 +156,40 @@ def _setup_rk45(self, names, fieldset, pclass):
 
 
 KernelPlan._setup_rk45 = _setup_rk45
+
+
+def _setup_advdiff(self, names, fieldset):
+    """AdvectionDiffusionM1 / AdvectionDiffusionEM (reference kernels/_advectiondiffusion.py:21-117): need the scalar fields
+    ``Kh_zonal`` / ``Kh_meridional`` on the fieldset's grid and the context value ``dres``."""
+    if len(names) != 1 or names[0] not in K.ADVDIFF or self.diffusion:
+        raise NotImplementedError("AdvectionDiffusionM1/EM run fused on the device as [kernel] or [kernel, DeleteParticle]")
+    from .fieldset import Field
+
+    kz, km = fieldset.fields.get("Kh_zonal"), fieldset.fields.get("Kh_meridional")
+    if not isinstance(kz, Field) or not isinstance(km, Field):
+        raise AttributeError(f"{names[0]} needs fields Kh_zonal and Kh_meridional (FieldSet.add_field)")
+    if kz._slot is None or km._slot is None or kz.interp_method != "linear" or km.interp_method != "linear":
+        raise NotImplementedError(f"{names[0]}: Kh_zonal / Kh_meridional must be XLinear scalar fields on the FieldSet's grid "
+                                  "(FieldSet.add_field(name, data)); constant fields have no gradient -- use DiffusionUniformKh")  # fmt: skip
+    if fieldset.grid.curvilinear or fieldset.interp_method != "linear" or fieldset.time_window is not None:
+        raise NotImplementedError(f"{names[0]} is implemented for resident rectilinear A-grid fields (XLinear_Velocity)")
+    if kz.data.dtype != km.data.dtype or (kz.data.shape[0] > 1) != (km.data.shape[0] > 1):
+        raise NotImplementedError("Kh_zonal and Kh_meridional must share dtype and time dimension")
+    if "dres" not in fieldset.context:
+        raise AttributeError(f"{names[0]} needs fieldset.add_context('dres', <resolution of the Kh gradient>)")
+    dres = fieldset.context["dres"]
+    if isinstance(dres, np.generic) or not isinstance(dres, (int, float)):
+        # a NumPy float64 scalar is a STRONG type: `particles.x + dres` would be a float64 array in the reference and the
+        # whole kernel would run in other dtypes; the reference's own usage passes a Python float (tests/test_diffusion.py:65)
+        raise NotImplementedError("fieldset.dres must be a Python float (fieldset.add_context('dres', float(...)))")
+    g = fieldset.grid
+    self.advdiff = dict(scheme=K.ADVDIFF[names[0]], kh_slots=(kz._slot, km._slot), dres=float(dres), deg2m_sq=pow(g.deg2m, 2))
+    self.stepwise = False
+    self.scheme_name, self.scheme = names[0], -2
+    self.kh, self.kh_spherical, self.kh_deg2m = (0.0, 0.0), False, 1.0
+
+
+KernelPlan._setup_advdiff = _setup_advdiff
 
 
 class ParticleSet:
@@ -348,6 +386,9 @@ class ParticleSet:
             hint_all_zero = not np.any((ei_last[evaluated].astype(np.int64) % g.xdim) != 0)
 
         def args(max_iters=-1):
+            if plan.advdiff is not None:
+                return eng.make_advdiff_args(dt=dt, endtime=endtime, delete_on_error=plan.delete_on_error, seed=self.seed,
+                                             rng_call=self._rng_call, max_iters=max_iters, **plan.advdiff)  # fmt: skip
             return eng.make_args(plan.scheme, dt, endtime, diffusion=plan.diffusion, delete_on_error=plan.delete_on_error,
                                  kh=plan.kh, kh_spherical=plan.kh_spherical, kh_deg2m=plan.kh_deg2m, seed=self.seed,
                                  rng_call=self._rng_call, max_iters=max_iters, hint_all_zero=hint_all_zero)  # fmt: skip

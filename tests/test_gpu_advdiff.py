@@ -1,0 +1,71 @@
+"""GPU parity (-m gpu) of AdvectionDiffusionM1 / AdvectionDiffusionEM (csrc/advdiff.cu, pb_advect_diffusion) against the
+CPU oracle fed the engine's own Philox stream: ids, states, times, surviving set and cell indices bit-exact; positions
+bit-exact on flat meshes, <= 4 float32 ulp on spherical meshes (CUDA cos / cosf vs glibc).  The oracle itself is pinned to
+the reference's outputs with the reference's RNG (tests/test_advdiff_cpu.py).  Statistical check against the reference's
+own test (tests/test_diffusion.py:49-81): zero mean, zonal skew > meridional skew on a field with a zonal Kh gradient."""
+
+import numpy as np
+import pytest
+
+from advdiff_run import run_engine_advdiff, run_oracle_advdiff
+from engine_run import ulp_diff_f32
+from oracle.make_golden import ADVDIFF_CASES
+from philox_ref import wiener_normals
+
+pytestmark = pytest.mark.gpu
+ERR_NAME = {60: "FieldOutOfBoundError", 61: "FieldOutOfBoundSurfaceError", 70: "OutsideTimeInterval", 51: "FieldInterpolationError"}
+FLAT = {"m1_flat", "em_f64_static", "em_raise"}
+
+
+@pytest.mark.parametrize("name", list(ADVDIFF_CASES))
+def test_advdiff_matches_oracle_with_same_normals(name):
+    seed = 4242
+    ps, err = run_engine_advdiff(name, seed=seed)
+    state = {"it": 0}
+
+    def normal(view):  # one Kernel.execute call (rng_call = 1), one normal pair per particle and loop iteration
+        zx, zy = wiener_normals(seed, 1, state["it"], view.particle_id)
+        state["it"] += 1
+        return zx, zy
+
+    pd, oerr = run_oracle_advdiff(name, normal=normal)
+    assert err == (ERR_NAME[oerr] if oerr else "")
+    d = ps._data
+    for key in ("particle_id", "state", "t", "dt", "ei"):
+        np.testing.assert_array_equal(d[key], pd[key], err_msg=f"{name}:{key}")
+    for key in ("x", "y", "z"):
+        if name in FLAT:
+            np.testing.assert_array_equal(d[key], pd[key], err_msg=f"{name}:{key}")
+        else:
+            ulps = ulp_diff_f32(d[key], pd[key])
+            assert ulps.max() <= 4, f"{name}:{key} differs by {ulps.max()} f32 ulp"
+
+
+@pytest.mark.parametrize("kernel", ["AdvectionDiffusionM1", "AdvectionDiffusionEM"])
+@pytest.mark.parametrize("mesh", ["spherical", "flat"])
+def test_spatially_varying_diffusion_statistics(mesh, kernel):
+    """The reference's test_fieldKh_SpatiallyVaryingDiffusion (tests/test_diffusion.py:49-81) on the device."""
+    from scipy import stats
+
+    import parcels_b200 as pb
+
+    ydim, xdim = 100, 200
+    conv = 1 / 1852.0 / 60 if mesh == "spherical" else 1
+    lon, lat = np.linspace(-1e6, 1e6, xdim), np.linspace(-1e6, 1e6, ydim)
+    if mesh == "spherical":
+        lon, lat = lon * conv, lat * conv
+    Z = np.zeros((2, 1, ydim, xdim), dtype=np.float32)
+    Kh = np.zeros((ydim, xdim), dtype=np.float32)
+    for x in range(xdim):
+        Kh[:, x] = np.tanh(lon[x] / lon[-1] * 10.0) * xdim / 2.0 + xdim / 2.0 + 100.0
+    fs = pb.FieldSet.from_arrays(lon=lon, lat=lat, time=np.array([0.0, 86400.0]), U=Z, V=Z, mesh=mesh)
+    fs.add_field("Kh_zonal", np.broadcast_to(Kh, (2, 1, ydim, xdim)).copy())
+    fs.add_field("Kh_meridional", np.broadcast_to(Kh, (2, 1, ydim, xdim)).copy())
+    fs.add_context("dres", float(lon[1] - lon[0]))
+    npart = 10000
+    ps = pb.ParticleSet(fs, x=np.zeros(npart), y=np.zeros(npart), seed=1636)
+    ps.execute(getattr(pb, kernel), runtime=3 * 3600.0, dt=3600.0)
+    tol = 2000 * conv
+    assert abs(np.mean(ps.x)) < tol and abs(np.mean(ps.y)) < tol
+    assert abs(stats.skew(ps.x)) > abs(stats.skew(ps.y))
+    assert np.std(ps.x) > 0 and np.all(ps.state == 1)
