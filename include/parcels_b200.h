@@ -91,7 +91,12 @@ int32_t pb_grid_upload_rectilinear(pb_engine* e, const void* lon, int64_t nx, co
  * (xmin, xmax, ymin, ymax, zmin, zmax) of the hash grid, hash_bitwidth the quantisation (:212-228);
  * face_qbox[(ny-1)*(nx-1)] = each face's quantised bounding box packed 6 x 10 bits (xlo | xhi<<10 | ylo<<20 |
  * yhi<<30 | zlo<<40 | zhi<<50), i.e. the set of hash cells the face is listed under (:269-300).
- * The query itself runs on the device. */
+ * The query itself runs on the device.
+ * hash_keys = hash_starts = hash_counts = hash_faces = NULL (n_keys, n_entries ignored): the table is BUILT ON THE DEVICE
+ * from face_qbox (count -> scan -> expand -> 64-bit radix sort by (key, face) -> CSR, csrc/hashbuild.cu).  The float part of
+ * the reference's constructor (:45-228: xyz in the coordinate dtype, per-face min/max, quantisation, bitwidth budget)
+ * stays with the caller -- it is what fixes the boxes, and the table is a pure integer function of them, so both routes
+ * give the reference's table bit for bit.  pb_hash_table_size / pb_hash_table_download read the resident table back. */
 int32_t pb_grid_upload_curvilinear(pb_engine* e, const void* lon2d, const void* lat2d, int64_t ny, int64_t nx,
                                    const void* depth, int64_t nz, int32_t coord_is_f64, const double* time_s,
                                    int64_t nt, int32_t spherical, double deg2m, int64_t xdim_cells,
@@ -99,6 +104,9 @@ int32_t pb_grid_upload_curvilinear(pb_engine* e, const void* lon2d, const void* 
                                    const int64_t* hash_starts, const int64_t* hash_counts, int64_t n_keys,
                                    const uint32_t* hash_faces, int64_t n_entries, const double* hash_box6,
                                    int32_t hash_bitwidth, const uint64_t* face_qbox);
+
+int32_t pb_hash_table_size(pb_engine* e, int64_t* n_keys, int64_t* n_entries);
+int32_t pb_hash_table_download(pb_engine* e, uint32_t* keys, int64_t* starts, int64_t* counts, uint32_t* faces);
 
 /* Vector interpolator of fieldset.UV / UVW (VectorField.interp_method, _core/field.py:236-246):
  * XLinear_Velocity (A-grid, interpolators/_xinterpolators.py:169-190) or CGrid_Velocity (:193-332)

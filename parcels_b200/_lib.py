@@ -109,6 +109,8 @@ SYMBOLS = {
         [_P, _P, _P, C.c_int64, C.c_int64, _P, C.c_int64, C.c_int32, _P, C.c_int64, C.c_int32, C.c_double, C.c_int64,
          C.c_int64, C.c_int64, _P, _P, _P, C.c_int64, _P, C.c_int64, _P, C.c_int32, _P],
     ),  # fmt: skip
+    "pb_hash_table_size": (C.c_int32, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "pb_hash_table_download": (C.c_int32, [_P, _P, _P, _P, _P]),
     "pb_set_interpolation": (C.c_int32, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "pb_field_upload": (C.c_int32, [_P, C.c_int32, _P, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_int64]),
     "pb_field_attach_device": (C.c_int32, [_P, C.c_int32, _P, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_int64]),

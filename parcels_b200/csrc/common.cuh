@@ -486,6 +486,16 @@ cudaError_t launch_rk45(const AdvectParams& p, double* dt, double* next_dt, int*
                         double max_dt, bool coord_f64, bool data_f64, bool has_time, cudaStream_t s);
 cudaError_t launch_rk45_finalize(const ParticlesDev& P, double* dt, const int* iters, long long total_iters, double endtime, int sign,
                                  cudaStream_t s);
+// device-side build of the curvilinear spatial-hash table from the per-face quantised boxes (hashbuild.cu)
+struct HashTableDev {
+    unsigned int* keys = nullptr;
+    long long* starts = nullptr;
+    long long* counts = nullptr;
+    unsigned int* faces = nullptr;
+    int* bucket = nullptr;
+    long long nkeys = 0, nent = 0;
+};
+cudaError_t build_hash_table_device(const unsigned long long* d_qbox, long long nfaces, int bucket_bits, HashTableDev& t, cudaStream_t s);
 // AdvectionDiffusionM1 (em = 0) / AdvectionDiffusionEM (em = 1) with the diffusivity fields fkz, fkm  (advdiff.cu)
 cudaError_t launch_advdiff(const AdvectParams& p, const FieldDev& fkz, const FieldDev& fkm, int em, double dres, double deg2m_sq,
                            bool coord_f64, bool uv_f64, bool kh_f64, bool uv_time, bool kh_time, cudaStream_t s);

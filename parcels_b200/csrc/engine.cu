@@ -267,6 +267,7 @@ struct pb_engine {
     DevBuf lon, lat, depth, time, hkeys, hstarts, hcounts, hfaces, hbucket, cellproj, hqbox;
     int interp = 0;  // enum pb_interp
     GridDev g{};
+    long long hash_nent = 0;  // entries of the resident spatial-hash table
     bool have_grid = false;
     int coord_f64 = 0;
     // fields
@@ -463,20 +464,47 @@ int32_t pb_grid_upload_curvilinear(pb_engine* e, const void* lon2d, const void* 
     if (!e) return fail(PB_ERR_INVALID, "engine is NULL");
     if (!lon2d || !lat2d || nx < 2 || ny < 2) return fail(PB_ERR_INVALID, "curvilinear grid needs (ny, nx) lon/lat with ny, nx >= 2");
     if (nx > INT_MAX || ny > INT_MAX || nz > INT_MAX || nt > INT_MAX) return fail(PB_ERR_INVALID, "axis too long");
-    if (!hash_keys || !hash_starts || !hash_counts || !hash_faces || !hash_box6 || !face_qbox || n_keys < 1 || n_entries < 1)
-        return fail(PB_ERR_INVALID, "curvilinear grid needs its spatial-hash table");
+    const bool host_table = hash_keys || hash_starts || hash_counts || hash_faces;
+    if (!hash_box6 || !face_qbox) return fail(PB_ERR_INVALID, "curvilinear grid needs its hash box and per-face quantised boxes");
+    if (host_table && (!hash_keys || !hash_starts || !hash_counts || !hash_faces || n_keys < 1 || n_entries < 1))
+        return fail(PB_ERR_INVALID, "incomplete host-built spatial-hash table (pass all four arrays, or none to build it on the device)");
     if (hash_bitwidth < 1 || hash_bitwidth > 1023) return fail(PB_ERR_INVALID, "hash bitwidth must be in 1..1023");
     CK(cudaSetDevice(e->device));
     const size_t es = coord_is_f64 ? 8 : 4;
+    const int bucket_bits = 20;  // bucket table over the top bits of the 30-bit Morton key: narrows the binary search to a few keys
     int32_t rc;
     if ((rc = upload(e, e->lon, lon2d, (size_t)nx * ny * es))) return rc;
     if ((rc = upload(e, e->lat, lat2d, (size_t)nx * ny * es))) return rc;
-    if ((rc = upload(e, e->hkeys, hash_keys, n_keys * 4))) return rc;
-    if ((rc = upload(e, e->hstarts, hash_starts, n_keys * 8))) return rc;
-    if ((rc = upload(e, e->hcounts, hash_counts, n_keys * 8))) return rc;
-    if ((rc = upload(e, e->hfaces, hash_faces, n_entries * 4))) return rc;
     if ((rc = upload(e, e->hqbox, face_qbox, (size_t)(ny - 1) * (nx - 1) * 8))) return rc;
     GridDev& g = e->g;
+    if (host_table) {
+        if ((rc = upload(e, e->hkeys, hash_keys, n_keys * 4))) return rc;
+        if ((rc = upload(e, e->hstarts, hash_starts, n_keys * 8))) return rc;
+        if ((rc = upload(e, e->hcounts, hash_counts, n_keys * 8))) return rc;
+        if ((rc = upload(e, e->hfaces, hash_faces, n_entries * 4))) return rc;
+        const int shift = 30 - bucket_bits;
+        const long long nb = 1LL << bucket_bits;
+        std::vector<int> bucket(nb + 1);
+        long long k = 0;
+        for (long long b = 0; b <= nb; ++b) {
+            while (k < n_keys && (long long)(hash_keys[k] >> shift) < b) ++k;
+            bucket[b] = (int)k;
+        }
+        if ((rc = upload(e, e->hbucket, bucket.data(), (size_t)(nb + 1) * sizeof(int)))) return rc;
+        CK(cudaStreamSynchronize(e->stream));
+    } else {
+        // the table is a pure integer function of the quantised boxes: expanded, sorted and compressed on the device
+        HashTableDev t;
+        cudaError_t ce = build_hash_table_device((const unsigned long long*)e->hqbox.p, (long long)(ny - 1) * (nx - 1), bucket_bits, t, e->stream);
+        if (ce != cudaSuccess) return fail(PB_ERR_CUDA, "device spatial-hash build failed: %s", cudaGetErrorString(ce));
+        n_keys = t.nkeys; n_entries = t.nent;
+        e->hkeys.release(); e->hkeys.p = t.keys; e->hkeys.bytes = (size_t)n_keys * 4;
+        e->hstarts.release(); e->hstarts.p = t.starts; e->hstarts.bytes = (size_t)n_keys * 8;
+        e->hcounts.release(); e->hcounts.p = t.counts; e->hcounts.bytes = (size_t)n_keys * 8;
+        e->hfaces.release(); e->hfaces.p = t.faces; e->hfaces.bytes = (size_t)n_entries * 4;
+        e->hbucket.release(); e->hbucket.p = t.bucket; e->hbucket.bytes = (size_t)((1LL << bucket_bits) + 1) * 4;
+    }
+    e->hash_nent = n_entries;
     g.nx = (int)nx; g.ny = (int)ny;
     g.curvilinear = 1;
     g.hash_bitwidth = hash_bitwidth;
@@ -487,20 +515,8 @@ int32_t pb_grid_upload_curvilinear(pb_engine* e, const void* lon2d, const void* 
     g.hnkeys = n_keys;
     g.hqbox = (const unsigned long long*)e->hqbox.p;
     for (int k = 0; k < 6; ++k) g.hbox[k] = hash_box6[k];
-    {   // bucket table over the top bits of the 30-bit Morton key: narrows the binary search to a few keys
-        const int bits = 20, shift = 30 - bits;
-        const long long nb = 1LL << bits;
-        std::vector<int> bucket(nb + 1);
-        long long k = 0;
-        for (long long b = 0; b <= nb; ++b) {
-            while (k < n_keys && (long long)(hash_keys[k] >> shift) < b) ++k;
-            bucket[b] = (int)k;
-        }
-        if ((rc = upload(e, e->hbucket, bucket.data(), (size_t)(nb + 1) * sizeof(int)))) return rc;
-        CK(cudaStreamSynchronize(e->stream));
-        g.hbucket = (const int*)e->hbucket.p;
-        g.hbucket_shift = shift;
-    }
+    g.hbucket = (const int*)e->hbucket.p;
+    g.hbucket_shift = 30 - bucket_bits;
     g.cellproj = nullptr;
     if (spherical) {  // per-cell tangent-plane projections, computed once on the device
         const size_t ncell = (size_t)(ny - 1) * (nx - 1);
@@ -510,6 +526,27 @@ int32_t pb_grid_upload_curvilinear(pb_engine* e, const void* lon2d, const void* 
         g.cellproj = (const double*)e->cellproj.p;
     }
     return upload_zt(e, depth, nz, coord_is_f64, time_s, nt, spherical, deg2m, xdim_cells, ydim_cells, zdim_cells);
+}
+
+int32_t pb_hash_table_size(pb_engine* e, int64_t* n_keys, int64_t* n_entries) {
+    if (!e || !n_keys || !n_entries) return fail(PB_ERR_INVALID, "NULL argument");
+    if (!e->g.curvilinear) return fail(PB_ERR_STATE, "no curvilinear grid uploaded");
+    *n_keys = e->g.hnkeys;
+    *n_entries = e->hash_nent;
+    return PB_OK;
+}
+
+int32_t pb_hash_table_download(pb_engine* e, uint32_t* keys, int64_t* starts, int64_t* counts, uint32_t* faces) {
+    if (!e || !keys || !starts || !counts || !faces) return fail(PB_ERR_INVALID, "NULL argument");
+    if (!e->g.curvilinear) return fail(PB_ERR_STATE, "no curvilinear grid uploaded");
+    CK(cudaSetDevice(e->device));
+    const size_t nk = (size_t)e->g.hnkeys, ne = (size_t)e->hash_nent;
+    CK(cudaMemcpyAsync(keys, e->hkeys.p, nk * 4, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemcpyAsync(starts, e->hstarts.p, nk * 8, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemcpyAsync(counts, e->hcounts.p, nk * 8, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemcpyAsync(faces, e->hfaces.p, ne * 4, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return PB_OK;
 }
 
 // kernel family of aslip.cu: 1 = _Spatialslip, 2 = nearest node; 0 = not an alternative A-grid interpolator

@@ -65,10 +65,15 @@ class Engine:
         depth = None if depth is None else np.ascontiguousarray(depth)
         time_s = None if time_s is None else np.ascontiguousarray(time_s, dtype=np.float64)
         ny, nx = lon2d.shape
-        keys = np.ascontiguousarray(h["keys"], dtype=np.uint32)
-        starts = np.ascontiguousarray(h["starts"], dtype=np.int64)
-        counts = np.ascontiguousarray(h["counts"], dtype=np.int64)
-        faces = np.ascontiguousarray(h["faces"], dtype=np.uint32)
+        if "keys" in h:  # host-built table (parcels_b200/spatialhash.py, table=True)
+            keys = np.ascontiguousarray(h["keys"], dtype=np.uint32)
+            starts = np.ascontiguousarray(h["starts"], dtype=np.int64)
+            counts = np.ascontiguousarray(h["counts"], dtype=np.int64)
+            faces = np.ascontiguousarray(h["faces"], dtype=np.uint32)
+            nk, ne = keys.size, faces.size
+        else:  # only the quantised boxes: the table is built on the device (csrc/hashbuild.cu)
+            keys = starts = counts = faces = None
+            nk = ne = 0
         box = np.ascontiguousarray(h["box"], dtype=np.float64)
         qbox = np.ascontiguousarray(h["qbox"], dtype=np.uint64)
         assert qbox.size == (ny - 1) * (nx - 1)
@@ -76,10 +81,19 @@ class Engine:
             self._lib.pb_grid_upload_curvilinear(
                 self._h, ptr(lon2d), ptr(lat2d), ny, nx, ptr(depth), 0 if depth is None else depth.size,
                 int(cdt == np.float64), ptr(time_s), 0 if time_s is None else time_s.size, int(bool(spherical)),
-                float(deg2m), int(xdim), int(ydim), int(zdim or 0), ptr(keys), ptr(starts), ptr(counts), keys.size,
-                ptr(faces), faces.size, ptr(box), int(h["bitwidth"]), ptr(qbox),
+                float(deg2m), int(xdim), int(ydim), int(zdim or 0), ptr(keys), ptr(starts), ptr(counts), nk,
+                ptr(faces), ne, ptr(box), int(h["bitwidth"]), ptr(qbox),
             )
         )  # fmt: skip
+
+    def hash_table(self) -> dict:
+        """The spatial-hash table resident on the device (keys, starts, counts, faces), read back."""
+        nk, ne = C.c_int64(), C.c_int64()
+        check(self._lib.pb_hash_table_size(self._h, C.byref(nk), C.byref(ne)))
+        keys, faces = np.empty(nk.value, dtype=np.uint32), np.empty(ne.value, dtype=np.uint32)
+        starts, counts = np.empty(nk.value, dtype=np.int64), np.empty(nk.value, dtype=np.int64)
+        check(self._lib.pb_hash_table_download(self._h, ptr(keys), ptr(starts), ptr(counts), ptr(faces)))
+        return dict(keys=keys, starts=starts, counts=counts, faces=faces)
 
     def set_interpolation(self, method: int, off_x: int, off_y: int, off_z: int):
         check(self._lib.pb_set_interpolation(self._h, int(method), int(off_x), int(off_y), int(off_z)))

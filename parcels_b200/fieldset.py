@@ -78,12 +78,13 @@ class XGrid:
     def curvilinear(self):
         return self.lon.ndim == 2
 
-    def get_spatial_hash(self):
-        """reference _core/basegrid.py:192-216: built lazily, once."""
-        if self._hash is None:
+    def get_spatial_hash(self, table=False):
+        """reference _core/basegrid.py:192-216: built lazily, once.  ``table=False``: only the per-face quantised boxes
+        (the float part); the engine expands / sorts / compresses them into the table on the device."""
+        if self._hash is None or (table and "keys" not in self._hash):
             from .spatialhash import build_spatial_hash
 
-            self._hash = build_spatial_hash(self.lon, self.lat, self.is_spherical())
+            self._hash = build_spatial_hash(self.lon, self.lat, self.is_spherical(), table=table)
         return self._hash
 
     def is_spherical(self):

@@ -1,10 +1,16 @@
-"""Host-side, one-time construction of the spatial-hash table the device query walks.
+"""One-time construction of the spatial-hash table the device query walks.
 
 Same table as the reference's ``SpatialHash`` (``_core/spatialhash.py:45-387``): per-face bounding
 boxes (unit-sphere xyz on spherical meshes, lon/lat on flat ones) quantised to <= 10 bits per axis,
 one (Morton key, face) entry per hash cell a box overlaps, sorted by (key, face) and stored CSR --
 so the device sees candidates in the reference's order ("first containing face wins").  This is
 grid *setup* (like uploading the coordinates); the query runs in ``csrc/cgrid.cu``.
+
+Split: the float part (xyz in the coordinate dtype, per-face min/max, quantisation, bitwidth budget
+search -- O(faces), and NumPy's sin/cos are what fix the reference's boxes) runs here;
+``build_spatial_hash(..., table=False)`` stops after it and the O(entries) integer part (expansion,
+Morton encode, (key, face) sort, CSR) runs on the device (``csrc/hashbuild.cu``).  ``table=True`` also
+does the integer part in NumPy -- the host restatement the GPU tests compare the device table with.
 """
 
 from __future__ import annotations
@@ -40,8 +46,9 @@ def _face_minmax(a):
     return c.min(axis=-1), c.max(axis=-1)
 
 
-def build_spatial_hash(lon2d: np.ndarray, lat2d: np.ndarray, spherical: bool) -> dict:
-    """Returns dict(keys u32, starts i64, counts i64, faces u32, box f64[6], bitwidth int)."""
+def build_spatial_hash(lon2d: np.ndarray, lat2d: np.ndarray, spherical: bool, table: bool = True) -> dict:
+    """Returns dict(box f64[6], bitwidth int, qbox u64[faces], n_entries int) and, with ``table=True``, the CSR table
+    itself: keys u32, starts i64, counts i64, faces u32."""
     if spherical:
         x, y, z = _xyz(lat2d, lon2d)
         box = (np.nanmin(x), np.nanmax(x), np.nanmin(y), np.nanmax(y), np.nanmin(z), np.nanmax(z))
@@ -78,6 +85,14 @@ def build_spatial_hash(lon2d: np.ndarray, lat2d: np.ndarray, spherical: bool) ->
     nx, ny, nz = (hi[k] - lo[k] + 1 for k in range(3))
     per_face = np.where(valid, nx * ny * nz, 0)
     nent = int(per_face.sum())
+    # per-face quantised bounding box, packed 6 x 10 bits: a face is listed under hash cell (qx, qy, qz) iff the
+    # cell lies inside this box -- the device builds the table from it and decides table membership without walking it
+    qbox = (lo[0] | (hi[0] << 10) | (lo[1] << 20) | (hi[1] << 30) | (lo[2] << 40) | (hi[2] << 50)).astype(np.uint64)
+    qbox[~valid] = np.uint64(1023)  # lo = 1023 > hi = 0: empty
+    head = dict(box=np.array([float(b) for b in box], dtype=np.float64), bitwidth=int(bitwidth), qbox=np.ascontiguousarray(qbox),
+                n_entries=nent)  # fmt: skip
+    if not table:
+        return head
     face = np.repeat(np.arange(xl.size, dtype=np.uint32), per_face)
     intra = np.arange(nent, dtype=np.int64) - np.repeat(np.concatenate(([0], np.cumsum(per_face)))[:-1], per_face)
     nynz, nzr = np.repeat(ny * nz, per_face), np.repeat(nz, per_face)
@@ -91,10 +106,4 @@ def build_spatial_hash(lon2d: np.ndarray, lat2d: np.ndarray, spherical: bool) ->
     codes = (packed >> np.uint64(32)).astype(np.uint32)
     starts = np.concatenate(([0], np.flatnonzero(codes[1:] != codes[:-1]) + 1)).astype(np.int64)
     counts = np.diff(np.concatenate((starts, [codes.size]))).astype(np.int64)
-    # per-face quantised bounding box, packed 6 x 10 bits: a face is listed under hash cell (qx, qy, qz) iff the
-    # cell lies inside this box -- lets the device decide table membership without walking the table
-    qbox = (lo[0] | (hi[0] << 10) | (lo[1] << 20) | (hi[1] << 30) | (lo[2] << 40) | (hi[2] << 50)).astype(np.uint64)
-    qbox[~valid] = np.uint64(1023)  # lo = 1023 > hi = 0: empty
-    return dict(keys=np.ascontiguousarray(codes[starts]), starts=starts, counts=counts, faces=np.ascontiguousarray(faces),
-                box=np.array([float(b) for b in box], dtype=np.float64), bitwidth=int(bitwidth),
-                qbox=np.ascontiguousarray(qbox))  # fmt: skip
+    return dict(head, keys=np.ascontiguousarray(codes[starts]), starts=starts, counts=counts, faces=np.ascontiguousarray(faces))

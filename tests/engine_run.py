@@ -34,10 +34,15 @@ def run_engine(c, seed=0):
     return ps, err
 
 
-def ulp_diff_f32(a, b):
-    """Distance in float32 ulps between two float32 arrays (same shape)."""
+def ulp_diff_f32(a, b, floor=None):
+    """Distance in float32 ulps between two float32 arrays (same shape).  ``floor``: measure in units of the float32
+    spacing at max(|b|, floor) instead -- for coordinates that cross zero, where the spacing of the value itself says
+    nothing about the accuracy of the increments that produced it (floor = the size of one step's displacement)."""
     a = np.asarray(a, dtype=np.float32)
     b = np.asarray(b, dtype=np.float32)
+    if floor is not None:
+        unit = np.spacing(np.maximum(np.abs(b), np.float32(floor)).astype(np.float32)).astype(np.float64)
+        return np.abs(a.astype(np.float64) - b.astype(np.float64)) / unit
     ia = a.view(np.int32).astype(np.int64)
     ib = b.view(np.int32).astype(np.int64)
     ia = np.where(ia < 0, np.int64(-(2**31)) - ia, ia)

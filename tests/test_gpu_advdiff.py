@@ -1,6 +1,8 @@
 """GPU parity (-m gpu) of AdvectionDiffusionM1 / AdvectionDiffusionEM (csrc/advdiff.cu, pb_advect_diffusion) against the
 CPU oracle fed the engine's own Philox stream: ids, states, times, surviving set and cell indices bit-exact; positions
-bit-exact on flat meshes, <= 4 float32 ulp on spherical meshes (CUDA cos / cosf vs glibc).  The oracle itself is pinned to
+bit-exact on flat meshes, <= 4 float32 ulp on spherical meshes (CUDA cos / cosf vs glibc) -- ulps of max(|x|, 0.05 deg): the
+longitudes of these cases cross zero, where a 1-ulp difference of one step's displacement (~0.05 deg) is many ulps of x itself
+(measured with the oracle alone: perturbing its float32 cos by 1 ulp moves a particle at x = -0.0008 by 150 of ITS ulps).  The oracle itself is pinned to
 the reference's outputs with the reference's RNG (tests/test_advdiff_cpu.py).  Statistical check against the reference's
 own test (tests/test_diffusion.py:49-81): zero mean, zonal skew > meridional skew on a field with a zonal Kh gradient."""
 
@@ -37,7 +39,7 @@ def test_advdiff_matches_oracle_with_same_normals(name):
         if name in FLAT:
             np.testing.assert_array_equal(d[key], pd[key], err_msg=f"{name}:{key}")
         else:
-            ulps = ulp_diff_f32(d[key], pd[key])
+            ulps = ulp_diff_f32(d[key], pd[key], floor=0.05)
             assert ulps.max() <= 4, f"{name}:{key} differs by {ulps.max()} f32 ulp"
 
 
