@@ -325,18 +325,62 @@ class ParticleSet:
 
     def __getitem__(self, index):
         """A write-through view on a subset (reference `pset[i]` / `pset[mask]`, _core/particleset.py:166-168)."""
-        from .particlesetview import ParticleSetView, _global_mask
+        from .particlesetview import ParticleSetView, SingleParticleView, _global_mask
 
+        if isinstance(index, (int, np.integer)) and not isinstance(index, (bool, np.bool_)):
+            if not -len(self) <= index < len(self):
+                raise IndexError(f"particle index {index} out of range for a set of {len(self)}")
+            return SingleParticleView(self._data, index)
         return ParticleSetView(self._data, _global_mask(np.ones(len(self), dtype=bool), index), self.fieldset)
 
     @property
     def size(self):
         return len(self)
 
+    def __iter__(self):
+        """Single-particle views in storage order (reference _core/particleset.py:144-154)."""
+        return (self[i] for i in range(len(self)))
+
+    def add(self, particles):
+        """Append another ParticleSet in place; its particle ids are shifted past this set's largest id
+        (reference _core/particleset.py:188-224)."""
+        assert particles is not None, f"Trying to add another {type(self)} to this one, but the other one is None - invalid operation."
+        assert type(particles) is type(self)
+        if len(particles) == 0:
+            return
+        if len(self) == 0:
+            self._data = particles._data
+            return
+        mine, theirs = self._data, particles._data
+        theirs["particle_id"] = theirs["particle_id"] + (mine["particle_id"].max() + 1)
+        for k in mine:
+            mine[k] = np.concatenate((mine[k], theirs[k]))
+        self._device_synced = False
+        return self
+
+    def __iadd__(self, particles):
+        self.add(particles)
+        return self
+
     def remove_indices(self, indices):
         """reference _core/particleset.py:247-250."""
         for k in self._data:
             self._data[k] = np.delete(self._data[k], indices, axis=0)
+
+    def populate_indices(self):
+        """Pre-populate the cell guesses ``ei`` (reference _core/particleset.py:252-262): one grid search per grid of the
+        gridset -- on the device for the fieldset's grid (`pb_sample_velocity` returns the raveled cell of every sample);
+        the one-node grid of the constant fields has the single cell 0 (_core/index_search.py:45-46)."""
+        d = self._data
+        if len(self) == 0:
+            return
+        eng = self.fieldset.engine(self.device)
+        *_, ei, _ = eng.sample_velocity(np.zeros(len(self)), d["z"], d["y"], d["x"], three_d=False, positions_are_f32=True,
+                                        ei_hint=None, no_hint=True)  # fmt: skip
+        d["ei"][:, 0] = ei
+        if d["ei"].shape[1] > 1:
+            d["ei"][:, 1:] = 0
+        self._device_synced = False
 
     # -- the hot path ------------------------------------------------------------------------------
     def _kernel_execute(self, plan: KernelPlan, endtime: float, dt: float, *, resident: bool = False, lazy: bool = False):

@@ -10,7 +10,7 @@ from __future__ import annotations
 
 import numpy as np
 
-__all__ = ["ParticleSetView", "ParticleSetViewArray"]
+__all__ = ["ParticleSetView", "ParticleSetViewArray", "SingleParticleView"]
 
 
 def _global_mask(base: np.ndarray, index) -> np.ndarray:
@@ -110,3 +110,21 @@ class ParticleSetView:
     @property
     def size(self):
         return int(np.count_nonzero(self._index))
+
+
+class SingleParticleView:
+    """``pset[i]`` with an integer ``i`` (reference _core/particleset.py:166-168 -> ``ParticleSetView(data, index=i)``):
+    attribute reads give the particle's scalar values, assignments write through to the parent arrays."""
+
+    def __init__(self, data, index):
+        object.__setattr__(self, "_data", data)
+        object.__setattr__(self, "_index", int(index))
+
+    def __getattr__(self, name):
+        data = object.__getattribute__(self, "_data")
+        if name in data:
+            return data[name][self._index]
+        raise AttributeError(name)
+
+    def __setattr__(self, name, value):
+        self._data[name][self._index] = value

@@ -55,3 +55,20 @@ def test_single_eval_matches_oracle(name, f32):
     np.testing.assert_allclose(v, ov, rtol=1e-5, atol=1e-6 * scale)
     if three_d:
         np.testing.assert_allclose(w, ow[0], rtol=1e-5, atol=1e-6 * np.abs(ow[0]).max())
+
+
+@pytest.mark.parametrize("name", ["c2_small", "flat_f32c_f64d", "curv_sph_2d", "diffusion"])
+def test_populate_indices_matches_oracle_search(name):
+    """ParticleSet.populate_indices (reference _core/particleset.py:252-262): ei[:, i] = ravel_index(grid_i.search(z, y, x))
+    for every grid of the gridset, the search of the fieldset's grid done on the device."""
+    import parcels_b200 as pb
+
+    c = load_case(name)
+    fs = make_fieldset(c)
+    ofs = oracle_fieldset(c)
+    ps = pb.ParticleSet(fs, x=c["x"], y=c["y"], z=c["z"], t=c["t"])
+    ps.populate_indices()
+    d = ps._data
+    (zi, _), (yi, _), (xi, _) = po.grid_search(ofs.grid, d["z"], d["y"], d["x"], None)
+    np.testing.assert_array_equal(d["ei"][:, 0], po.ravel_index(ofs.grid, zi, yi, xi).astype(np.int32))
+    assert d["ei"].shape[1] == ofs.ngrids and not d["ei"][:, 1:].any()

@@ -39,6 +39,8 @@ def test_struct_layouts_match_header():
 
     assert ctypes.sizeof(_lib.AdvectArgs) == 4 * 4 + 5 * 8 + 2 * 8 + 8 + 4 * 4
     assert ctypes.sizeof(_lib.Report) == 11 * 8 + 2 * 4 + 2 * 4
+    assert ctypes.sizeof(_lib.Rk45Args) == 5 * 8 + 8 + 2 * 4
+    assert ctypes.sizeof(_lib.AdvDiffArgs) == 4 * 4 + 4 * 8 + 2 * 8 + 8
 
 
 def _fs(with_w=True):
@@ -193,3 +195,26 @@ def test_window_range_policy():
         for tt in np.linspace(0, 500, 41):
             f, n = window_range(t, tt, sign, 3)
             assert t[f] <= tt <= t[f + n - 1] and n >= 2
+
+
+def test_pset_add_iadd_iter():
+    """reference tests/test_particleset.py:126-162,173-178 (test_pset_add_explicit / _implicit / _in_loop / merge / iterator)."""
+    fs = _fs()
+    npart = 11
+    lon, lat = np.linspace(0, 1, npart), np.linspace(1, 0, npart)
+    pset = pb.ParticleSet(fs, x=lon[0], y=lat[0])
+    for i in range(1, npart):
+        pset.add(pb.ParticleSet(fs, x=lon[i], y=lat[i]))
+    assert len(pset) == npart
+    assert np.allclose([p.x for p in pset], lon, atol=1e-7) and np.allclose([p.y for p in pset], lat, atol=1e-7)
+    assert np.allclose(np.diff(pset._data["particle_id"]), np.ones(npart - 1))
+    pset = pb.ParticleSet(fs, x=np.zeros(3), y=np.ones(3))
+    pset += pb.ParticleSet(fs, x=np.ones(4), y=np.zeros(4))
+    assert len(pset) == 7 and np.allclose(np.diff(pset._data["particle_id"]), np.ones(6))
+    pset = pb.ParticleSet(fs, x=[], y=[])
+    for _ in range(10):
+        pset += pb.ParticleSet(fs, x=0.1, y=0.1)
+    assert pset.size == 10 and pset._data["ei"].shape == (10, 1)
+    for i, particle in enumerate(pb.ParticleSet(fs, x=np.zeros(5), y=np.ones(5))):
+        assert particle.particle_id == i
+    assert i == 4
