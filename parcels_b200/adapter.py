@@ -13,7 +13,18 @@ import numpy as np
 from .fieldset import FieldSet, XGrid
 from .particleset import ParticleSet
 
-SUPPORTED_VECTOR_INTERP = {"XLinear_Velocity": "linear", "XFreeslip": "freeslip", "XPartialslip": "partialslip"}
+SUPPORTED_VECTOR_INTERP = {"XLinear_Velocity": "linear", "XFreeslip": "freeslip", "XPartialslip": "partialslip",
+                           "CGrid_Velocity": "cgrid_velocity", "XNearest_Velocity": "nearest"}  # fmt: skip
+
+
+def _padding(g):
+    """SGRID face-node padding of the X, Y, Z axes as the strings FieldSet takes; only LOW vs not-LOW matters to the
+    interpolators (reference interpolators/_xinterpolators.py:99-109, `_get_offsets_dictionary`)."""
+    md = g.sgrid_metadata
+    out = [str(getattr(fnp.padding, "value", fnp.padding)).lower() for fnp in md.face_dimensions[:2]]
+    vd = getattr(md, "vertical_dimensions", None)
+    out.append(str(getattr(vd[0].padding, "value", vd[0].padding)).lower() if vd else "high")
+    return tuple(out)
 
 
 def _values(da):
@@ -21,7 +32,8 @@ def _values(da):
 
 
 def from_parcels(ref_fieldset) -> FieldSet:
-    """reference FieldSet -> parcels_b200.FieldSet (rectilinear A-grid, XLinear_Velocity)."""
+    """reference FieldSet -> parcels_b200.FieldSet: rectilinear A-grids (XLinear_Velocity, XFreeslip, XPartialslip),
+    rectilinear and curvilinear C-grids (CGrid_Velocity), scalar fields, constant fields and the context constants."""
     U = ref_fieldset.U
     g = U.grid
     vf = getattr(ref_fieldset, "UVW", None) or ref_fieldset.UV
@@ -29,8 +41,8 @@ def from_parcels(ref_fieldset) -> FieldSet:
     if interp not in SUPPORTED_VECTOR_INTERP:
         raise NotImplementedError(f"vector interpolator {interp} is not on the engine (supported: {sorted(SUPPORTED_VECTOR_INTERP)})")
     lon, lat = np.asarray(g.lon), np.asarray(g.lat)
-    if lon.ndim != 1:
-        raise NotImplementedError("curvilinear grids are not on the engine yet")
+    if lon.ndim != 1 and interp != "CGrid_Velocity":
+        raise NotImplementedError("curvilinear grids are on the engine with CGrid_Velocity only")
     axes = list(g.axes)
     depth = np.asarray(g.depth) if "Z" in axes else None
     spherical = g._mesh.is_spherical()
@@ -41,15 +53,17 @@ def from_parcels(ref_fieldset) -> FieldSet:
         time = _values(U.data.time)
     W = getattr(ref_fieldset, "W", None)
     fs = FieldSet(grid, _values(U.data), _values(ref_fieldset.V.data), None if W is None else _values(W.data), time=time,
-                  interp_method=SUPPORTED_VECTOR_INTERP[interp])
+                  interp_method=SUPPORTED_VECTOR_INTERP[interp], padding=_padding(g))
     scalar = {"XLinear": "linear", "XNearest": "nearest", "CGrid_Tracer": "cgrid_tracer"}
     for name, f in ref_fieldset.fields.items():
         how = type(getattr(f, "interp_method", None)).__name__
-        if name not in ("U", "V", "W") and how in scalar and getattr(f, "grid", None) is g:
+        if name not in ("U", "V", "W") and how in scalar and getattr(f, "grid", None) is g and lon.ndim == 1:
             fs.add_field(name, _values(f.data), interp_method=scalar[how])  # sampled on the device (pb_sample_scalar)
     for name, f in ref_fieldset.fields.items():
         if type(getattr(f, "interp_method", None)).__name__ == "XConstantField":
             fs.add_constant_field(name, float(_values(f.data)[0, 0, 0, 0]), mesh="spherical" if f.grid._mesh.is_spherical() else "flat")
+    for name, value in dict(getattr(ref_fieldset, "context", {}) or {}).items():  # fieldset.add_context (_core/fieldset.py:207-222)
+        fs.add_context(name, value)
     return fs
 
 

@@ -136,9 +136,9 @@ __device__ __forceinline__ void load_corners(const GridDev& g, CGridCtx<A, D>& e
             e.pv[0] = q2.x; e.pv[1] = q2.y; e.pv[2] = q3.x; e.pv[3] = q3.y;
             e.eu[0] = q4.x; e.eu[1] = q4.y; e.eu[2] = q5.x;
             e.ev[0] = q5.y; e.ev[1] = q6.x; e.ev[2] = q6.y;
-        } else {
-            project_cell<A>(e.clon, e.clat, e.pu, e.pv, e.eu, e.ev);
         }
+        // (no on-the-fly fallback: pb_grid_upload_curvilinear always builds the table for spherical meshes, and keeping
+        //  project_cell's ~2000 SASS instructions out of the advect kernel is a quarter of its code size)
     }
 }
 
@@ -547,9 +547,11 @@ struct CurvPolicy {
         // -- _search_indices_curvilinear_2d (index_search.py:242-295): hint, (neighbours,) spatial hash
         Query q;
         q.x = x; q.y = y;
+        double cos_lat = 1.0;  // cos(deg2rad(y)) in float64: also the spherical conversion factor of a float64 position
         if (SPH) {
             const double la = deg2rad_np(y), lo = deg2rad_np(x);
             const double cl = cos_ool(la);
+            cos_lat = cl;
             q.qu_x = cos_ool(lo) * cl; q.qu_y = sin_ool(lo) * cl; q.qu_z = sin_ool(la);
         }
         double xsi = -1.0, eta = -1.0;
@@ -573,10 +575,21 @@ struct CurvPolicy {
             bool nb = false;
             if (hint_ok && isfinite(x) && isfinite(y)) {
                 const int hj = e.yi, hi = e.xi;
+                // the failed hint test says which way the point left the hinted cell: that neighbour is tested first
+                // (k = -1), the other seven only if it is not the one (non-overlapping cells: at most one can pass)
+                const int gdj = eta > 1 ? 1 : (eta < 0 ? -1 : 0);
+                const int gdi = xsi > 1 ? 1 : (xsi < 0 ? -1 : 0);
 #pragma unroll 1
-                for (int k = 0; k < 8 && !nb; ++k) {
-                    const int dj = (k < 3) ? -1 : ((k < 5) ? 0 : 1);
-                    const int di = (k == 0 || k == 3 || k == 5) ? -1 : ((k == 1 || k == 6) ? 0 : 1);
+                for (int k = -1; k < 8 && !nb; ++k) {
+                    int dj, di;
+                    if (k < 0) {
+                        dj = gdj; di = gdi;
+                        if ((dj | di) == 0) continue;
+                    } else {
+                        dj = (k < 3) ? -1 : ((k < 5) ? 0 : 1);
+                        di = (k == 0 || k == 3 || k == 5) ? -1 : ((k == 1 || k == 6) ? 0 : 1);
+                        if (dj == gdj && di == gdi) continue;
+                    }
                     const int j = hj + dj, i = hi + di;
                     if (j < 0 || i < 0 || j >= g.ny - 1 || i >= g.nx - 1) continue;
                     double cs, ce;
@@ -618,7 +631,7 @@ struct CurvPolicy {
         CGridPolicy<A, D, NC_>::load_faces(g, f, e, ti, zi, yi, xi);
         // spherical conversion factor in the dtype of the sampled y
         double conv = 1.0;
-        if (SPH) conv = xy_f32 ? (double)((float)g.deg2m * cosf_ool(deg2rad_np((float)y))) : g.deg2m * cos_ool(deg2rad_np(y));
+        if (SPH) conv = xy_f32 ? (double)((float)g.deg2m * cosf_ool(deg2rad_np((float)y))) : g.deg2m * cos_lat;
         Val wdummy;
         if constexpr (SPH || std::is_same<A, double>::value) {
             // every operand the face values meet is float64 (edge lengths are float64: float64 bcoords on a
