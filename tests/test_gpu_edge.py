@@ -1,0 +1,102 @@
+"""Edge cases of ParticleSet.execute on the device, transcribed from the reference's own tests
+(tests/test_particleset_execute.py:315-357,445-468, tests/test_advection.py:148-190): empty sets, a single particle,
+end-time landing with a dt that does not divide the run, per-particle start times in both time directions, everything
+deleted in the first step, dt reset, user kernels mixed in."""
+
+import numpy as np
+import pytest
+
+import parcels_b200 as pb
+
+pytestmark = pytest.mark.gpu
+
+
+def _fieldset(u=1.0, v=0.0, tmax=100.0, mesh="flat"):
+    lon, lat = np.linspace(0.0, 1000.0, 21), np.linspace(0.0, 500.0, 11)
+    U = np.full((2, 1, 11, 21), u, dtype=np.float32)
+    V = np.full((2, 1, 11, 21), v, dtype=np.float32)
+    return pb.FieldSet.from_arrays(lon=lon, lat=lat, time=np.array([0.0, tmax]), U=U, V=V, mesh=mesh)
+
+
+@pytest.mark.parametrize("starttime, endtime, dt", [(0, 10, 1), (0, 10, 3), (2, 16, 3), (20, 10, -1), (20, 0, -2), (5, 15, 1)])
+def test_execution_endtime(starttime, endtime, dt):
+    """reference test_execution_endtime: the last step is clamped so that t lands exactly on endtime."""
+    fs = _fieldset()
+    ps = pb.ParticleSet(fs, t=float(starttime), x=100.0, y=100.0)
+    ps.execute(pb.AdvectionRK4, endtime=float(endtime), dt=float(dt))
+    assert ps.t[0] == float(endtime) and ps.dt[0] == float(dt) and ps.state[0] == pb.StatusCode.EndofLoop
+    assert ps.x[0] == np.float32(100.0 + (endtime - starttime))  # u = 1 m/s, flat mesh: exact in float32
+
+
+@pytest.mark.parametrize("starttime, runtime, dt", [(0, 10, 1), (0, 10, 3), (2, 16, 3), (20, 10, -1), (20, 0, -2), (5, 15, 1)])
+@pytest.mark.parametrize("npart", [1, 10])
+def test_execution_runtime(starttime, runtime, dt, npart):
+    fs = _fieldset()
+    ps = pb.ParticleSet(fs, t=float(starttime), x=np.full(npart, 200.0), y=np.full(npart, 100.0))
+    ps.execute([pb.AdvectionEE, pb.DeleteParticle], runtime=float(runtime), dt=float(dt))
+    assert len(ps) == npart and np.all(np.abs(ps.t - starttime - runtime * np.sign(dt)) < 1e-3)
+
+
+def test_dont_run_particles_outside_starttime():
+    """reference test_dont_run_particles_outside_starttime, forward and backward (u = 1 m/s stands in for `x += 1`)."""
+    fs = _fieldset()
+    for sign, t0 in ((1, 0.0), (-1, 100.0)):
+        starts = np.array([t0 + sign * s for s in (0, 2, 10)])
+        end = t0 + sign * 8
+        ps = pb.ParticleSet(fs, x=np.full(3, 500.0), y=np.full(3, 100.0), t=starts)
+        ps.execute(pb.AdvectionRK4, dt=sign * 1.0, endtime=end)
+        np.testing.assert_array_equal(ps.x, np.float32([500 + sign * 8, 500 + sign * 6, 500]))
+        np.testing.assert_array_equal(ps.t, [end, end, starts[2]])  # the third particle has not been executed
+        np.testing.assert_array_equal(ps.state, [1, 1, 10])
+
+
+def test_empty_set_and_everything_deleted():
+    fs = _fieldset()
+    ps = pb.ParticleSet(fs, x=[], y=[])
+    ps.execute(pb.AdvectionRK4, runtime=10.0, dt=1.0)  # nothing to do, no error
+    assert len(ps) == 0
+    ps = pb.ParticleSet(fs, x=np.full(5, 2000.0), y=np.full(5, 100.0))  # all outside the domain
+    ps.execute([pb.AdvectionRK4, pb.DeleteParticle], runtime=10.0, dt=1.0)
+    assert len(ps) == 0 and ps._data["ei"].shape == (0, 1)
+    ps.execute([pb.AdvectionRK4, pb.DeleteParticle], runtime=10.0, dt=1.0)  # executing the emptied set again is a no-op
+    ps += pb.ParticleSet(fs, x=100.0, y=100.0)
+    ps.execute([pb.AdvectionRK4, pb.DeleteParticle], runtime=10.0, dt=1.0)
+    assert len(ps) == 1 and ps.x[0] == np.float32(110.0)
+    with pytest.raises(pb.FieldOutOfBoundError):  # without a handler the same start raises, like the reference
+        pb.ParticleSet(fs, x=np.full(5, 2000.0), y=np.full(5, 100.0)).execute(pb.AdvectionRK4, runtime=10.0, dt=1.0)
+
+
+def test_some_particles_throw_outofbounds_then_survivors_continue():
+    """reference test_some_particles_throw_outofbounds idea: particles leaving through the eastern edge are deleted, the others go on;
+    deletions happen in HBM between output intervals (order preserved)."""
+    fs = _fieldset(u=10.0)
+    x0 = np.linspace(100.0, 990.0, 90)
+    ps = pb.ParticleSet(fs, x=x0, y=np.full(90, 100.0))
+
+    class Out:
+        outputdt = 10.0
+        sizes = []
+
+        def write(self, pset, t):
+            self.sizes.append(len(pset))
+
+    ps.execute([pb.AdvectionRK4, pb.DeleteParticle], runtime=50.0, dt=1.0, output_file=Out())
+    keep = x0 + 500.0 <= 1000.0
+    assert Out.sizes[0] == 90 and Out.sizes[-1] == int(keep.sum()) and sorted(Out.sizes, reverse=True) == Out.sizes
+    np.testing.assert_array_equal(ps.particle_id, np.flatnonzero(keep))
+    np.testing.assert_allclose(ps.x, x0[keep] + 500.0, rtol=1e-6)
+
+
+def test_changing_dt_in_kernel_and_dt_reset():
+    """reference test_changing_dt_in_kernel: 3 steps for runtime 5 with dt 2 (the last one clamped), dt restored afterwards;
+    a user kernel mixed with a device kernel."""
+    fs = _fieldset(u=0.0)
+    calls = []
+
+    def KernelCounter(particles, fieldset):
+        calls.append(len(particles.x))
+        particles.dx += 1
+
+    ps = pb.ParticleSet(fs, x=np.zeros(1) + 10, y=np.zeros(1) + 10)
+    ps.execute([pb.AdvectionRK4, KernelCounter], dt=2.0, runtime=5.0)
+    assert ps.x[0] == 13 and ps.dt[0] == 2 and ps.t[0] == 5 and len(calls) == 3
