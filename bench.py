@@ -272,10 +272,15 @@ WORKLOADS = {
                      nsteps=144, kernels=["AdvectionRK4_3D"], bytes=832, desc="small functional variant of c2"),
     "ns": dict(field=ns_field_device, fkw=dict(nx=4320, ny=2160, nz=50, nt=3), particles=c2_particles, n=10_000_000, dt=600.0,
                nsteps=144, kernels=["AdvectionRK4_3D"], bytes=832, device_field=True,
+               roofline_note="real DRAM traffic is 15 % of the algorithmic bytes (per-lane corner cache); the kernel is issue- and "
+                             "refill-latency-bound (ncu, profiles/r01d_ncu_summary_ns.txt: issue slots 50 %, fp64 pipe 35 %, L2 hit 13 %)",
                desc="BASELINE.json north_star target -- AdvectionRK4_3D, 1e7 particles on a 1/12 deg rectilinear A-grid "
                     "4320x2160x50 T=3 f32 U,V,W (16.8 GB, generated in HBM), spherical"),
     "c3": dict(field=c3_field, fkw=dict(nx=1442, ny=1021, nt=3), particles=c3_particles, n=10_000_000, dt=3600.0,
                nsteps=48, kernels=["AdvectionRK4"], bytes=320,
+               roofline_note="not HBM-bound: 9 double-precision sin/cos + 5 sqrt + ~8 divisions per sample are the reference's own "
+                             "arithmetic (ncu, profiles/r01d_ncu_summary_c3_small.txt: DRAM 0.2 % of peak, L1/L2 hit 90 %, cos+sin 26 % of "
+                             "the executed instructions, issue slots 40 %, fp64 pipe 23 %)",
                desc="BASELINE.json configs[2] -- AdvectionRK4, curvilinear C-grid ORCA025 shape 1442x1021 T=3, f32 lon/lat, "
                     "CGrid_Velocity + hint/spatial-hash search, spherical"),
     "c3_small": dict(field=c3_field, fkw=dict(nx=362, ny=292, nt=3), particles=c3_particles, n=200_000, dt=3600.0,
@@ -619,7 +624,8 @@ def main():
         "gpu_launches": a.steps,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": dram_traffic_per_launch(a.workload), "peak_source": peak_src,
-                     "algorithmic_bytes_per_particle_step": w["bytes"], "particle_steps_per_launch": steps_per_launch},
+                     "algorithmic_bytes_per_particle_step": w["bytes"], "particle_steps_per_launch": steps_per_launch,
+                     **({"note": w["roofline_note"]} if "roofline_note" in w else {})},
         "clocks": clk.summary(),
     }  # fmt: skip
     if not a.no_cpu_baseline:

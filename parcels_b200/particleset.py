@@ -29,6 +29,12 @@ def _to_float_seconds(v):
     return float(v)
 
 
+def _has_nan(a) -> bool:
+    """np.isnan(a).any() without the temporary: one NaN-propagating reduction (an inf - inf false positive is re-checked)."""
+    s = a.sum() if len(a) else 0.0
+    return bool(s != s) and bool(np.isnan(a).any())
+
+
 def _builtin_name(f):
     """Name of the built-in kernel ``f`` stands for, or None for a user function.  Built-ins are this package's
     tokens (kernels.py, by identity) and the reference package's own kernel functions (by module + name); a user
@@ -415,7 +421,7 @@ class ParticleSet:
             d["state"][:] = StatusCode.Evaluate
             if n == 0:
                 return
-            if np.isnan(d["t"]).any():
+            if _has_nan(d["t"]):
                 bad = np.where(np.isnan(d["t"]))[0]
                 raise ValueError(f"Time values for particles with indices {bad} cannot be NaN.")  # field.py:396-398
             ei_last = np.ascontiguousarray(d["ei"][:, -1])
@@ -580,7 +586,10 @@ class ParticleSet:
         if runtime is None and endtime is None:
             raise ValueError("Either runtime or endtime must be provided.")
         t = self._data["t"]
-        first = (np.nanmin(t) if sign_dt == 1 else np.nanmax(t)) if not np.isnan(t).all() else np.nan
+        first = t.min() if sign_dt == 1 else t.max()  # NaN-propagating: one pass when no particle has an unset time
+        any_nan = bool(np.isnan(first))
+        if any_nan:
+            first = (np.nanmin(t) if sign_dt == 1 else np.nanmax(t)) if not np.isnan(t).all() else np.nan
         if endtime is not None:
             if isinstance(endtime, np.datetime64):
                 endtime = float((endtime - self.fieldset._time_origin) / np.timedelta64(1, "s"))
@@ -593,7 +602,7 @@ class ParticleSet:
         else:
             start_time = float(first)
         end_time = endtime if endtime is not None else start_time + sign_dt * runtime
-        if np.isnan(t).any():
+        if any_nan:
             t[:] = start_time
         outputdt = _to_float_seconds(output_file.outputdt) if output_file is not None else None
         if output_file is not None and hasattr(output_file, "set_metadata"):  # reference particleset.py:400-403
