@@ -300,7 +300,10 @@ int32_t pb_sample_velocity(pb_engine* e, int64_t n, const double* t, const doubl
  * the staggering offsets of pb_set_interpolation).  Index search, `ei` write-back and state codes are those of
  * pb_sample_velocity; out-of-bounds samples are 0.  value_is_f32 (optional): 1 where NumPy's promotion makes the
  * reference's value float32 (the value returned is that float32 number, widened). */
-enum pb_scalar_interp { PB_SCALAR_XLINEAR = 0, PB_SCALAR_XNEAREST = 1, PB_SCALAR_CGRID_TRACER = 2 };
+enum pb_scalar_interp {
+    PB_SCALAR_XLINEAR = 0, PB_SCALAR_XNEAREST = 1, PB_SCALAR_CGRID_TRACER = 2,
+    PB_SCALAR_XLINEAR_INVDIST_LAND = 3 /* XLinearInvdistLandTracer (:556-613): land corners (~0) left out */
+};
 int32_t pb_sample_scalar(pb_engine* e, int32_t slot, int32_t method, int64_t n, const double* t, const double* z,
                          const double* y, const double* x, int32_t positions_are_f32, const int32_t* ei_hint,
                          double* value, int32_t* value_is_f32, int32_t* ei_out, int32_t* state_out);

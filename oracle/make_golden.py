@@ -320,6 +320,25 @@ def scalar_inputs(c, T, seed=3):
     return P, tq
 
 
+def land_tracer_inputs(c, T, seed=4):
+    """Tracer field with blocks of land (exact zeros, growing with depth) for the XLinearInvdistLandTracer fixtures, and
+    sample points that include ocean nodes of partly-land cells (the exact-node branch)."""
+    rng = np.random.default_rng(seed)
+    shape = (T,) + c["U"].shape[1:]
+    P = (1.0 + rng.uniform(0, 1, shape)).astype(c["U"].dtype)
+    ny, nx = shape[2], shape[3]
+    r = rng.uniform(0, 1, (ny // 2 + 1, nx // 2 + 1))
+    for k in range(shape[1]):
+        land = np.kron(r < 0.3 + 0.05 * k, np.ones((2, 2), dtype=bool))[:ny, :nx]
+        P[:, k][..., land] = 0
+    x, y = np.array(c["x"], dtype=np.float64), np.array(c["y"], dtype=np.float64)
+    n = min(40, len(x))
+    jj, ii = rng.integers(0, ny, n), rng.integers(0, nx, n)
+    x[:n], y[:n] = np.asarray(c["lon"], dtype=np.float64)[ii], np.asarray(c["lat"], dtype=np.float64)[jj]  # exactly on nodes
+    tq = np.asarray(c["t"], dtype=np.float64) + (0.37 * c["times"][-1] if c["times"] is not None else 0.0)
+    return P, tq, x, y
+
+
 def make_scalar_golden():
     """Field.eval of the reference (XLinear / XNearest / CGrid_Tracer, with and without a time dimension)."""
     import warnings
@@ -342,6 +361,17 @@ def make_scalar_golden():
                     val = fs.P.eval(tq, ps._data["z"], ps._data["y"], ps._data["x"], ps)
                 key = f"{name}/T{T}/{how}"
                 out[f"{key}/value"], out[f"{key}/state"], out[f"{key}/ei"] = val, ps._data["state"].copy(), ps._data["ei"].copy()
+        for T in (c["U"].shape[0], 1):  # XLinearInvdistLandTracer on a field with land
+            P, tq, x, y = land_tracer_inputs(c, T)
+            fs = rh.build_fieldset(lon=c["lon"], lat=c["lat"], depth=c["depth"], times=c["times"], U=c["U"], V=c["V"], W=c["W"],
+                                   mesh=c["mesh"], padding=c.get("padding", ("low", "low", "high")),
+                                   interp=c.get("interp", "linear"), scalars={"P": (P, "linear_invdist_land")})  # fmt: skip
+            ps = rh.make_pset(fs, x=x, y=y, z=c["z"], t=c["t"])
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                val = fs.P.eval(tq, ps._data["z"], ps._data["y"], ps._data["x"], ps)
+            key = f"{name}/T{T}/linear_invdist_land"
+            out[f"{key}/value"], out[f"{key}/state"], out[f"{key}/ei"] = val, ps._data["state"].copy(), ps._data["ei"].copy()
         print(f"scalar {name}: done")
     np.savez_compressed(os.path.join(GOLDEN, "scalar_eval.npz"), **out)
 

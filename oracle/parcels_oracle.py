@@ -453,6 +453,36 @@ def eval_uvw(fs: OFieldSet, t, z, y, x, view: View | None, want3d: bool):
         return (0, 0, 0) if want3d else (0, 0)
 
 
+def xlinear_invdist_land(data, ti, tau, zi, zeta, yi, eta, xi, xsi):
+    """_xinterpolators.py:556-613 (``XLinearInvdistLandTracer``): XLinear, except where some of the gathered corners are
+    land (value ~ 0): all land -> 0; otherwise the inverse-squared-distance mean of the ocean corners, the distance
+    measured in (eta, xsi) only and summed over EVERY gathered time / depth level alike; a sample exactly on an ocean
+    corner takes the sum of that corner over the gathered levels (:603-610, as written in the reference)."""
+    values = xlinear(data, ti, tau, zi, zeta, yi, eta, xi, xsi)
+    corner, _ = _corner_block(data, ti, tau, zi, zeta, yi, xi)
+    land = np.isclose(corner, 0.0)
+    n_land = land.sum(axis=(0, 1, 2, 3))
+    n_all = corner.shape[0] * corner.shape[1] * 4
+    if np.any(n_land):
+        values[n_land == n_all] = 0.0
+        some = (n_land > 0) & (n_land < n_all)
+        if np.any(some):
+            jj = np.arange(2)[None, None, :, None, None]
+            ii = np.arange(2)[None, None, None, :, None]
+            d2 = (eta[None, None, None, None, :] - jj) ** 2 + (xsi[None, None, None, None, :] - ii) ** 2
+            ocean = ~land
+            with np.errstate(divide="ignore", invalid="ignore"):
+                inv = 1.0 / d2
+                num = np.where(ocean, corner * inv, 0.0).sum(axis=(0, 1, 2, 3))
+                den = np.where(ocean, inv, 0.0).sum(axis=(0, 1, 2, 3))
+                values[some] = num[some] / den[some]
+            on_node = (d2 == 0) & ocean
+            node_val = np.where(on_node, corner, 0.0).sum(axis=(0, 1, 2, 3))
+            pick = some & on_node.any(axis=(0, 1, 2, 3))
+            values[pick] = node_val[pick]
+    return values
+
+
 def cgrid_tracer(fs: OFieldSet, data, ti, tau, zi, yi, xi):
     """_xinterpolators.py:335-383 (``CGrid_Tracer``): constant over the cell (the tracer point), linear in time."""
     T, Z, Y, X = data.shape
@@ -486,6 +516,8 @@ def eval_scalar(fs: OFieldSet, data, method, t, z, y, x, view: View | None):
             value = xlinear(data, ti, tau, zi, zeta, yi, eta, xi, xsi)
         elif method == "nearest":
             value = xnearest(data, ti, tau, zi, zeta, yi, eta, xi, xsi)
+        elif method == "linear_invdist_land":
+            value = xlinear_invdist_land(data, ti, tau, zi, zeta, yi, eta, xi, xsi)
         else:
             value = cgrid_tracer(fs, data, ti, tau, zi, yi, xi)
         if view is not None and view.n() > 0:

@@ -301,12 +301,13 @@ def build_fieldset(
         smethod[sname] = how
     model = _Model(grid, data, ti)
     fields = {}
-    from parcels.interpolators._xinterpolators import CGrid_Tracer
+    from parcels.interpolators._xinterpolators import CGrid_Tracer, XLinearInvdistLandTracer
     from parcels.interpolators._xinterpolators import XNearest as _XNearest
 
     for name in data:
         f = Field(name, model)
-        f.interp_method = {"linear": XLinear, "nearest": _XNearest, "cgrid_tracer": CGrid_Tracer}[smethod.get(name, "linear")]()
+        f.interp_method = {"linear": XLinear, "nearest": _XNearest, "cgrid_tracer": CGrid_Tracer,
+                           "linear_invdist_land": XLinearInvdistLandTracer}[smethod.get(name, "linear")]()  # fmt: skip
         fields[name] = f
     from parcels.interpolators._base import VectorInterpolator
     from parcels.interpolators._xinterpolators import XFreeslip, XNearest, XPartialslip

@@ -54,7 +54,7 @@ def from_parcels(ref_fieldset) -> FieldSet:
     W = getattr(ref_fieldset, "W", None)
     fs = FieldSet(grid, _values(U.data), _values(ref_fieldset.V.data), None if W is None else _values(W.data), time=time,
                   interp_method=SUPPORTED_VECTOR_INTERP[interp], padding=_padding(g))
-    scalar = {"XLinear": "linear", "XNearest": "nearest", "CGrid_Tracer": "cgrid_tracer"}
+    scalar = {"XLinear": "linear", "XNearest": "nearest", "CGrid_Tracer": "cgrid_tracer", "XLinearInvdistLandTracer": "linear_invdist_land"}
     for name, f in ref_fieldset.fields.items():
         how = type(getattr(f, "interp_method", None)).__name__
         if name not in ("U", "V", "W") and how in scalar and getattr(f, "grid", None) is g and lon.ndim == 1:

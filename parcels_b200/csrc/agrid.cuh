@@ -5,7 +5,7 @@
 //   1  XFreeslip / XPartialslip (_Spatialslip, :385-495) -- instantiated in aslip.cu
 //   2  XNearest per component (:515-560)                -- instantiated in aslip.cu
 // and, with NC == 1, the scalar interpolators of Field.eval (_core/field.py:144-191) -- aslip.cu:
-//   3  XLinear (:112-153)      4  XNearest (:515-560)      5  CGrid_Tracer (:335-383)
+//   3  XLinear (:112-153)      4  XNearest (:515-560)      5  CGrid_Tracer (:335-383)      6  XLinearInvdistLandTracer (:556-613)
 #pragma once
 #include "common.cuh"
 
@@ -261,10 +261,41 @@ __device__ __forceinline__ void eval_uvw(const GridDev& g, const FieldDev& f, Ev
         u = q[0]; v = q[1];
         w = NC == 3 ? q[2] : Val{0.0, u.f32};
 #endif
-    } else if constexpr (MODE == 3) {
+    } else if constexpr (MODE == 3 || MODE == 6) {
         DV blk[16];
         e.cor.load(0, blk);
         u = xlinear<DV, TT, TZ, TY, TX>(blk, tau, zeta, eta, xsi);  // scalar XLinear: the value as it is
+        if constexpr (MODE == 6) {
+            // XLinearInvdistLandTracer (:556-613): corners ~ 0 are land.  All gathered corners land -> 0; some land -> the
+            // inverse-squared-distance mean of the ocean corners, distance in (eta, xsi) only, EVERY gathered time / depth
+            // level summed alike (t, z, y, x order); a sample exactly on an ocean node takes the sum of that node over
+            // the gathered levels.  The levels gathered are lenT x lenZ = (tau > 0) x (zeta > 0), per particle (DESIGN.md,
+            // waiver 1).  `eta_b - j_grid` is a float array minus an int64 array: float64 whatever the bcoord dtype.
+            const int nT = tau > 0 ? 2 : 1, nZ = zeta > 0 ? 2 : 1;
+            int n_land = 0;
+            double num = 0.0, den = 0.0, node_val = 0.0;
+            bool on_node = false;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                if ((k >> 3) >= nT || ((k >> 2) & 1) >= nZ) continue;
+                const DV c = blk[k];
+                const double dj = (double)eta - (double)((k >> 1) & 1), di = (double)xsi - (double)(k & 1);
+                const double d2 = dj * dj + di * di;
+                if (near_zero<D, DV>(c)) {
+                    ++n_land;
+                } else {
+                    const double inv = 1.0 / d2;
+                    num = num + (double)c * inv;
+                    den = den + inv;
+                    if (d2 == 0) { node_val = node_val + (double)c; on_node = true; }
+                }
+            }
+            const int n_all = nT * nZ * 4;
+            double r = u.v;
+            if (n_land == n_all) r = 0.0;
+            else if (n_land > 0) r = on_node ? node_val : num / den;
+            u.v = u.f32 ? (double)(float)r : r;  // assigned into the XLinear result array: keeps its dtype
+        }
         v = Val{0.0, u.f32}; w = v;
     } else {
         DV blk[16];

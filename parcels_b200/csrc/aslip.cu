@@ -76,5 +76,6 @@ static cudaError_t scalar_mode(const SampleParams& p, bool coord_f64, bool data_
 }
 cudaError_t launch_sample_scalar(const SampleParams& p, int mode, bool coord_f64, bool data_f64, bool has_time, cudaStream_t s) {
     if (mode == 3) return scalar_mode<3>(p, coord_f64, data_f64, has_time, s);
+    if (mode == 6) return scalar_mode<6>(p, coord_f64, data_f64, has_time, s);
     return mode == 4 ? scalar_mode<4>(p, coord_f64, data_f64, has_time, s) : scalar_mode<5>(p, coord_f64, data_f64, has_time, s);
 }

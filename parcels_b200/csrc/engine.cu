@@ -780,7 +780,7 @@ int32_t pb_sample_scalar(pb_engine* e, int32_t slot, int32_t method, int64_t n, 
     if (!e) return fail(PB_ERR_INVALID, "engine is NULL");
     if (n < 0 || (n && (!t || !z || !y || !x || !value || !ei_out || !state_out))) return fail(PB_ERR_INVALID, "NULL argument");
     if (slot < 0 || slot >= PB_MAX_FIELDS || !e->fptr[slot]) return fail(PB_ERR_STATE, "no field in slot %d", slot);
-    if (method < PB_SCALAR_XLINEAR || method > PB_SCALAR_CGRID_TRACER) return fail(PB_ERR_INVALID, "unknown scalar interpolation %d", method);
+    if (method < PB_SCALAR_XLINEAR || method > PB_SCALAR_XLINEAR_INVDIST_LAND) return fail(PB_ERR_INVALID, "unknown scalar interpolation %d", method);
     if (!e->have_grid) return fail(PB_ERR_STATE, "grid not uploaded (pb_grid_upload_*)");
     if (e->g.curvilinear) return fail(PB_ERR_INVALID, "scalar sampling is implemented for rectilinear grids");
     if (e->ring && slot < 3) return fail(PB_ERR_INVALID, "U, V, W are time-windowed: sample them through pb_sample_velocity");

@@ -249,7 +249,7 @@ class Engine:
                                            ptr(hint), int(no_hint), ptr(u), ptr(v), ptr(w), ptr(ei), ptr(st)))  # fmt: skip
         return u, v, w, ei, st
 
-    SCALAR_METHODS = {"linear": 0, "nearest": 1, "cgrid_tracer": 2}  # enum pb_scalar_interp
+    SCALAR_METHODS = {"linear": 0, "nearest": 1, "cgrid_tracer": 2, "linear_invdist_land": 3}  # enum pb_scalar_interp
 
     def sample_scalar(self, slot, method, t, z, y, x, *, positions_are_f32=False, ei_hint=None):
         """One ``Field.eval`` per sample on the device -> (value, ei, state); ``value`` has the dtype NumPy's

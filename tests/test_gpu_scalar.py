@@ -10,7 +10,7 @@ import pytest
 import parcels_b200 as pb
 from engine_run import make_fieldset
 from oracle import parcels_oracle as po
-from oracle.make_golden import SCALAR_CASES, scalar_inputs
+from oracle.make_golden import SCALAR_CASES, land_tracer_inputs, scalar_inputs
 from oracle_run import load_case, oracle_fieldset
 
 pytestmark = pytest.mark.gpu
@@ -45,6 +45,28 @@ def test_scalar_eval_matches_oracle_and_reference(name, golden_dir):
                                 po.View(pd2, np.ones(len(x2), dtype=bool)))  # fmt: skip
             np.testing.assert_array_equal(v2, o2, err_msg=key + " f64")
             np.testing.assert_array_equal(ps._data["ei"], pd2["ei"], err_msg=key + " f64")
+
+
+@pytest.mark.parametrize("name", SCALAR_CASES)
+def test_invdist_land_tracer_matches_oracle_and_reference(name, golden_dir):
+    """XLinearInvdistLandTracer on the device (MODE 6 of agrid.cuh) on a field with land, samples exactly on nodes included."""
+    g = np.load(os.path.join(golden_dir, "scalar_eval.npz"))
+    c = load_case(name)
+    ofs = oracle_fieldset(c)
+    for T in (c["U"].shape[0], 1):
+        P, tq, x, y = land_tracer_inputs(c, T)
+        fs = make_fieldset(c)
+        fs.add_field("P", P, interp_method="linear_invdist_land")
+        ps = pb.ParticleSet(fs, x=x, y=y, z=c["z"], t=c["t"])
+        val = fs.P.eval(tq, ps._data["z"], ps._data["y"], ps._data["x"], ps)
+        pd = po.create_particle_data(x, y, c["z"], c["t"])
+        oval = po.eval_scalar(ofs, P, "linear_invdist_land", tq, pd["z"], pd["y"], pd["x"], po.View(pd, np.ones(len(x), dtype=bool)))
+        key = f"{name}/T{T}/linear_invdist_land"
+        assert val.dtype == oval.dtype == g[f"{key}/value"].dtype, key
+        np.testing.assert_array_equal(ps._data["ei"], pd["ei"], err_msg=key)
+        np.testing.assert_array_equal(ps._data["state"], pd["state"], err_msg=key)
+        np.testing.assert_array_equal(val, oval, err_msg=key)
+        np.testing.assert_array_equal(val, g[f"{key}/value"], err_msg=key)
 
 
 def test_user_sampling_kernel_in_a_mixed_list():
