@@ -41,6 +41,8 @@ struct CGridCtx {
     int yi, xi;              // horizontal cell of the last search (curvilinear: -3 after a failed search)
     int kyi, kxi;            // cell whose corners are cached below (INT_MIN: none)
     A clon[4], clat[4];      // raw corner lon/lat, CCW from (yi, xi)
+    int uyi, uxi;            // curvilinear: cell whose unwrapped corner longitudes are cached in ulon (INT_MIN: none)
+    A ulon[4];               // corner longitudes wrapped to [-180, 180) and unwrapped relative to corner 0 (:230-233)
     double pu[4], pv[4];     // spherical curvilinear: corners projected on the cell's tangent plane
     double eu[3], ev[3];     //                        orthonormal basis of that plane
     int fti, fzi, fyi, fxi;  // key of the cached face values
@@ -234,6 +236,16 @@ __device__ __forceinline__ void hash_coords(const GridDev& g, PY y, PX x, unsign
     qz = quant<Q, A>(hz, g.hbox[4], g.hbox[5], g.hash_bitwidth);
 }
 
+// same for a float64 position on a spherical mesh whose unit vector is already known: the query vector of the point-in-cell
+// tests is cos(lon) cos(lat), sin(lon) cos(lat), sin(lat) of the same float64 radians -- the very expressions above
+template <class A>
+__device__ __forceinline__ void hash_coords_xyz(const GridDev& g, double hx, double hy, double hz, unsigned int& qx, unsigned int& qy,
+                                                unsigned int& qz) {
+    qx = quant<double, A>(hx, g.hbox[0], g.hbox[1], g.hash_bitwidth);
+    qy = quant<double, A>(hy, g.hbox[2], g.hbox[3], g.hash_bitwidth);
+    qz = quant<double, A>(hz, g.hbox[4], g.hbox[5], g.hash_bitwidth);
+}
+
 // is face (j, i) listed under hash cell (qx, qy, qz)?  (its quantised bounding box contains the cell)
 __device__ __forceinline__ bool face_listed(const GridDev& g, int j, int i, unsigned int qx, unsigned int qy, unsigned int qz) {
     const unsigned long long b = ldg(g.hqbox + (long long)j * (g.nx - 1) + i);
@@ -357,6 +369,7 @@ struct CGridPolicy {
         e.cx.lo = e.cx.hi = e.cy.lo = e.cy.hi = e.cz.lo = e.cz.hi = (A)0;
         e.ct.lo = e.ct.hi = 0.0;
         e.kyi = e.kxi = INT_MIN;
+        e.uyi = e.uxi = INT_MIN;
         e.fti = e.fzi = e.fyi = e.fxi = INT_MIN;
         e.ei = ei;
         // hint of the first search: unravel_index(ei) (basegrid.py:120-152,219-256), floor semantics
@@ -571,6 +584,7 @@ struct CurvPolicy {
             // points, jumps, no valid hint -- takes the exact hash path.
             unsigned int qx, qy, qz;
             if (xy_f32) hash_coords<A, float, float>(g, (float)y, (float)x, qx, qy, qz);
+            else if (SPH) hash_coords_xyz<A>(g, q.qu_x, q.qu_y, q.qu_z, qx, qy, qz);  // no second set of sin/cos
             else hash_coords<A, double, double>(g, y, x, qx, qy, qz);
             bool nb = false;
             if (hint_ok && isfinite(x) && isfinite(y)) {
@@ -619,14 +633,22 @@ struct CurvPolicy {
         load_corners(g, e, yi, xi);
         A px[4], py[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) { px[k] = e.clon[k]; py[k] = e.clat[k]; }
-        if (SPH) {  // corner longitudes unwrapped relative to corner 0 (:230-233)
+        for (int k = 0; k < 4; ++k) py[k] = e.clat[k];
+        if (SPH) {  // corner longitudes unwrapped relative to corner 0 (:230-233): a property of the cell, redone on a cell change only
+            if (e.uyi != yi || e.uxi != xi) {
+                e.uyi = yi; e.uxi = xi;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) px[k] = mod_np((A)(px[k] + (A)180.0), (A)360.0) - (A)180.0;
+                for (int k = 0; k < 4; ++k) e.ulon[k] = mod_np((A)(e.clon[k] + (A)180.0), (A)360.0) - (A)180.0;
 #pragma unroll
-            for (int k = 1; k < 4; ++k) if (px[k] - px[0] > (A)180) px[k] = px[k] - (A)360;
+                for (int k = 1; k < 4; ++k) if (e.ulon[k] - e.ulon[0] > (A)180) e.ulon[k] = e.ulon[k] - (A)360;
 #pragma unroll
-            for (int k = 1; k < 4; ++k) if (-px[k] + px[0] > (A)180) px[k] = px[k] + (A)360;
+                for (int k = 1; k < 4; ++k) if (-e.ulon[k] + e.ulon[0] > (A)180) e.ulon[k] = e.ulon[k] + (A)360;
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) px[k] = e.ulon[k];
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) px[k] = e.clon[k];
         }
         CGridPolicy<A, D, NC_>::load_faces(g, f, e, ti, zi, yi, xi);
         // spherical conversion factor in the dtype of the sampled y
