@@ -464,6 +464,9 @@ def main():
     ap.add_argument("--ref-step-seconds", type=float, default=5.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--sorted", action="store_true",
+                    help="experiment: release the particles ordered by grid cell (z, y, x) instead of randomly -- measures what "
+                         "spatial coherence between the lanes of a warp is worth (DESIGN.md 4, 'why not Morton-sort')")
     a = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -519,6 +522,13 @@ def main():
         fs.add_constant_field("Kh_zonal", w["kh"][0], mesh=field["mesh"])
         fs.add_constant_field("Kh_meridional", w["kh"][1], mesh=field["mesh"])
     parts = w["particles"](field, n_per_gpu, 1 + rank)  # weak scaling: every rank owns its own shard
+    if a.sorted and np.ndim(field["lon"]) == 1:
+        cell = np.searchsorted(field["lon"], parts["x"]).astype(np.int64)
+        cell += len(field["lon"]) * np.searchsorted(field["lat"], parts["y"])
+        if field["depth"] is not None:
+            cell += len(field["lon"]) * len(field["lat"]) * np.searchsorted(field["depth"], parts["z"])
+        order = np.argsort(cell, kind="stable")
+        parts = {k: v[order] for k, v in parts.items()}
     ps = pb.ParticleSet(fs, x=parts["x"], y=parts["y"], z=parts["z"], t=parts["t"], device=local_rank, seed=1234)
     init = {k: v.copy() for k, v in ps._data.items()}
     eng = fs.engine(local_rank)
@@ -613,7 +623,8 @@ def main():
         "ms_per_step": dev_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": {
-            "workload": f"{a.workload}: {w['desc']}; {n_per_gpu} particles/GPU, dt={dt:g} s x {nsteps} dt-steps per pass",
+            "workload": f"{a.workload}: {w['desc']}; {n_per_gpu} particles/GPU, dt={dt:g} s x {nsteps} dt-steps per pass"
+                        + ("; particles released in grid-cell order (--sorted experiment)" if a.sorted else ""),
             "kernels": w["kernels"] + ["DeleteParticle"], "particles_per_gpu": n_per_gpu, "dt_steps_per_pass": nsteps,
             "l2_policy": f"inputs larger than L2 ({fbytes / 1e9:.2f} GB field, {52 * n_per_gpu / 1e6:.0f} MB particle SoA; particles "
                          "re-seeded from an HBM snapshot every pass)",
