@@ -289,6 +289,7 @@ struct pb_engine {
     DevBuf mdest, mkeep, mcount, mbounds;
     // output path: block counts / offsets of the ordered selection, selected indices, compacted columns
     DevBuf sblock, soffs, sidx, sout;
+    DevBuf samp_d, samp_i;  // scratch of pb_sample_velocity / pb_sample_scalar (grown on demand, reused across calls)
     long long* h_sel_total = nullptr;  // pinned
     long long n_selected = -1;
     int nranks = 1, rank = 0;
@@ -358,7 +359,8 @@ void pb_engine_destroy(pb_engine* e) {
         b->release();
     for (DevBuf& b : e->fbuf) b.release();
     for (DevBuf* b : {&e->hqbox, &e->hbucket, &e->cellproj, &e->hkeys, &e->hstarts, &e->hcounts, &e->hfaces, &e->lon, &e->lat, &e->depth, &e->time, &e->px, &e->py, &e->pz,
-                      &e->pdx, &e->pdy, &e->pdz, &e->pt, &e->pstate, &e->pei, &e->ppid, &e->snap})
+                      &e->pdx, &e->pdy, &e->pdz, &e->pt, &e->pstate, &e->pei, &e->ppid, &e->snap, &e->sblock, &e->soffs, &e->sidx, &e->sout,
+                      &e->samp_d, &e->samp_i})
         b->release();
     if (e->d_rep) cudaFree(e->d_rep);
     if (e->h_rep) cudaFreeHost(e->h_rep);
@@ -742,10 +744,10 @@ int32_t pb_sample_velocity(pb_engine* e, int64_t n, const double* t, const doubl
     if (rc) return rc;
     if (n == 0) return PB_OK;
     CK(cudaSetDevice(e->device));
-    double* d = nullptr;  // t z y x u v w
-    int* di = nullptr;    // hint ei state
-    CK(cudaMalloc(&d, (size_t)n * 7 * sizeof(double)));
-    CK(cudaMalloc(&di, (size_t)n * 3 * sizeof(int)));
+    if ((rc = e->samp_d.ensure((size_t)n * 7 * sizeof(double)))) return rc;
+    if ((rc = e->samp_i.ensure((size_t)n * 3 * sizeof(int)))) return rc;
+    double* d = (double*)e->samp_d.p;  // t z y x u v w
+    int* di = (int*)e->samp_i.p;       // hint ei state
     const double* src[4] = {t, z, y, x};
     for (int k = 0; k < 4; ++k) CK(cudaMemcpyAsync(d + k * n, src[k], n * 8, cudaMemcpyHostToDevice, e->stream));
     if (ei_hint) CK(cudaMemcpyAsync(di, ei_hint, n * 4, cudaMemcpyHostToDevice, e->stream));
@@ -769,8 +771,6 @@ int32_t pb_sample_velocity(pb_engine* e, int64_t n, const double* t, const doubl
     CK(cudaMemcpyAsync(ei_out, di + n, n * 4, cudaMemcpyDeviceToHost, e->stream));
     CK(cudaMemcpyAsync(state_out, di + 2 * n, n * 4, cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
-    cudaFree(d);
-    cudaFree(di);
     return PB_OK;
 }
 
@@ -791,10 +791,11 @@ int32_t pb_sample_scalar(pb_engine* e, int32_t slot, int32_t method, int64_t n, 
     if (Z > 1 && e->g.nz == 0) return fail(PB_ERR_INVALID, "field has a depth dimension but the grid has no Z axis");
     if (n == 0) return PB_OK;
     CK(cudaSetDevice(e->device));
-    double* d = nullptr;  // t z y x value
-    int* di = nullptr;    // hint ei state f32
-    CK(cudaMalloc(&d, (size_t)n * 5 * sizeof(double)));
-    CK(cudaMalloc(&di, (size_t)n * 4 * sizeof(int)));
+    int32_t rc;
+    if ((rc = e->samp_d.ensure((size_t)n * 5 * sizeof(double)))) return rc;
+    if ((rc = e->samp_i.ensure((size_t)n * 4 * sizeof(int)))) return rc;
+    double* d = (double*)e->samp_d.p;  // t z y x value
+    int* di = (int*)e->samp_i.p;       // hint ei state f32
     const double* src[4] = {t, z, y, x};
     for (int k = 0; k < 4; ++k) CK(cudaMemcpyAsync(d + k * n, src[k], n * 8, cudaMemcpyHostToDevice, e->stream));
     if (ei_hint) CK(cudaMemcpyAsync(di, ei_hint, n * 4, cudaMemcpyHostToDevice, e->stream));
@@ -819,8 +820,6 @@ int32_t pb_sample_scalar(pb_engine* e, int32_t slot, int32_t method, int64_t n, 
     CK(cudaMemcpyAsync(state_out, di + 2 * n, n * 4, cudaMemcpyDeviceToHost, e->stream));
     if (value_is_f32) CK(cudaMemcpyAsync(value_is_f32, di + 3 * n, n * 4, cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
-    cudaFree(d);
-    cudaFree(di);
     return PB_OK;
 }
 
