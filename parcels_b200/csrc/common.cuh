@@ -157,9 +157,12 @@ __device__ __forceinline__ void wiener_normals(unsigned long long seed, unsigned
     double u1 = ((double)r[0] + 0.5) * two_m32;
     double u2 = ((double)r[1] + 0.5) * two_m32;
     double rad = sqrt(-2.0 * log(u1));
-    double ang = 6.283185307179586476925 * u2;
-    zx = rad * cos(ang);
-    zy = rad * sin(ang);
+    // cos / sin of 2 pi u2 through sincospi: exact argument reduction, no Payne-Hanek slow path in the kernel's code
+    // (the two were ~600 SASS instructions inside the time loop); differs from cos(6.283... * u2) by a few 1e-16
+    double s, c;
+    sincospi(2.0 * u2, &s, &c);
+    zx = rad * c;
+    zy = rad * s;
 }
 
 // ------------------------------------------------------------------------------------------------
