@@ -280,6 +280,8 @@ typedef struct pb_advdiff_args {
     uint64_t seed;
     uint64_t rng_call;
     int64_t max_iters;          /* < 0: run to endtime */
+    int32_t kernels_only;       /* 1: the kernel function of ONE loop iteration only (mixed lists, as in pb_advect_args) */
+    int32_t resume;             /* 1: particle states are NOT reset to Evaluate (the host drives the loop) */
 } pb_advdiff_args;
 int32_t pb_advect_diffusion(pb_engine* e, const pb_advdiff_args* args, pb_report* rep);
 

@@ -65,6 +65,8 @@ class AdvDiffArgs(C.Structure):
         ("seed", C.c_uint64),
         ("rng_call", C.c_uint64),
         ("max_iters", C.c_int64),
+        ("kernels_only", C.c_int32),
+        ("resume", C.c_int32),
     ]
 
 

@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(PB_BLOCK_THREADS, 2) advdiff_kernel(const AdvD
             extern __shared__ __align__(16) unsigned char pb_smem[];
             ek.cor.sm = reinterpret_cast<SK*>(pb_smem + (size_t)2 * 16 * sizeof(SU) * PB_BLOCK) + threadIdx.x;
         }
-        int state = PB_EVALUATE;  // kernel.py:188
+        int state = p.resume ? p.P.state[i] : (int)PB_EVALUATE;  // kernel.py:188
         eu.refills = 0; ek.refills = 0;
         eu.out_of_time = false; ek.out_of_time = false;
         const int sign = p.dt > 0 ? 1 : -1;
@@ -140,6 +140,7 @@ __global__ void __launch_bounds__(PB_BLOCK_THREADS, 2) advdiff_kernel(const AdvD
             dx = (float)((double)dx + sx);
             dy = (float)((double)dy + sy);
 
+            if (p.kernels_only) { ++it; break; }  // mixed lists: the host finishes the iteration (stepwise.py)
             if (p.delete_on_error && state >= 50) state = PB_DELETE;
             if (state == PB_EVALUATE || state == PB_SUCCESS) {  // kernel.py:108-116,220-222
                 x = x + dx; y = y + dy; z = z + dz;

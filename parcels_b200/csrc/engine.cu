@@ -1004,6 +1004,7 @@ int32_t pb_advect_diffusion(pb_engine* e, const pb_advdiff_args* a, pb_report* r
     p.delete_on_error = a->delete_on_error;
     p.dt = a->dt; p.endtime = a->endtime; p.max_iters = a->max_iters;
     p.seed = a->seed; p.rng_call = a->rng_call;
+    p.kernels_only = a->kernels_only; p.resume = a->resume;
     p.rep = e->d_rep;
     zero_report(*e->h_rep);
     CK(cudaMemcpyAsync(e->d_rep, e->h_rep, sizeof(ReportDev), cudaMemcpyHostToDevice, e->stream));

@@ -212,11 +212,13 @@ class Engine:
         return _report_dict(rep)
 
     @staticmethod
-    def make_advdiff_args(scheme, dt, endtime, *, kh_slots, dres, deg2m_sq, delete_on_error=False, seed=0, rng_call=0, max_iters=-1):
+    def make_advdiff_args(scheme, dt, endtime, *, kh_slots, dres, deg2m_sq, delete_on_error=False, seed=0, rng_call=0, max_iters=-1,
+                          kernels_only=False, resume=False):
         from ._lib import AdvDiffArgs
 
         return AdvDiffArgs(int(scheme), int(delete_on_error), int(kh_slots[0]), int(kh_slots[1]), float(dt), float(endtime),
-                           float(dres), float(deg2m_sq), int(seed), int(rng_call), int(max_iters))  # fmt: skip
+                           float(dres), float(deg2m_sq), int(seed), int(rng_call), int(max_iters), int(bool(kernels_only)),
+                           int(bool(resume)))  # fmt: skip
 
     def advect_rk45(self, dt, endtime, tol, min_dt, max_dt, dt_arr, next_dt_arr, *, next_dt_is_f32=True, delete_on_error=False,
                     max_iters=-1) -> dict:

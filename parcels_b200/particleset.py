@@ -84,9 +84,11 @@ class KernelPlan:
         if "AdvectionRK45" in tokens:
             self._setup_rk45(names, fieldset, pclass)
             return
-        if any(n in K.ADVDIFF for n in tokens if n):
-            self._setup_advdiff(names, fieldset)
+        if len(names) == 1 and names[0] in K.ADVDIFF and not self.diffusion:
+            self._setup_advdiff(names, fieldset)  # [kernel] or [kernel, DeleteParticle]: the whole loop in one launch
             return
+        if "DiffusionUniformKh" in tokens and any(n in K.ADVDIFF for n in tokens if n):
+            raise NotImplementedError("AdvectionDiffusionM1/EM already diffuse: combining them with DiffusionUniformKh is not supported")
         self.stepwise = not (len(names) == 1 and names[0] in K.SCHEMES)
         if fieldset.time_window is not None and (self.stepwise or not self.delete_on_error):
             raise NotImplementedError("time-windowed FieldSets need a list of built-in kernels ending with the DeleteParticle token: "
@@ -106,6 +108,8 @@ class KernelPlan:
                         self.items[-1][2] = True  # fused with the advection kernel right before it
                     else:
                         self.items.append(["device", K.SCHEMES["_none"], True, self])
+                elif n in K.ADVDIFF:  # mixed with user kernels: one device launch per step (kernels_only)
+                    self.items.append(["advdiff", _advdiff_params(fieldset, n)])
                 elif n == "DeleteParticle":
                     self.items.append(["python", _delete_on_error])
                 else:
@@ -164,32 +168,33 @@ def _setup_rk45(self, names, fieldset, pclass):
 KernelPlan._setup_rk45 = _setup_rk45
 
 
-def _setup_advdiff(self, names, fieldset):
+def _advdiff_params(fieldset, name):
     """AdvectionDiffusionM1 / AdvectionDiffusionEM (reference kernels/_advectiondiffusion.py:21-117): need the scalar fields
-    ``Kh_zonal`` / ``Kh_meridional`` on the fieldset's grid and the context value ``dres``."""
-    if len(names) != 1 or names[0] not in K.ADVDIFF or self.diffusion:
-        raise NotImplementedError("AdvectionDiffusionM1/EM run fused on the device as [kernel] or [kernel, DeleteParticle]")
+    ``Kh_zonal`` / ``Kh_meridional`` on the fieldset's grid and the context value ``dres`` -> arguments of pb_advect_diffusion."""
     from .fieldset import Field
 
     kz, km = fieldset.fields.get("Kh_zonal"), fieldset.fields.get("Kh_meridional")
     if not isinstance(kz, Field) or not isinstance(km, Field):
-        raise AttributeError(f"{names[0]} needs fields Kh_zonal and Kh_meridional (FieldSet.add_field)")
+        raise AttributeError(f"{name} needs fields Kh_zonal and Kh_meridional (FieldSet.add_field)")
     if kz._slot is None or km._slot is None or kz.interp_method != "linear" or km.interp_method != "linear":
-        raise NotImplementedError(f"{names[0]}: Kh_zonal / Kh_meridional must be XLinear scalar fields on the FieldSet's grid "
+        raise NotImplementedError(f"{name}: Kh_zonal / Kh_meridional must be XLinear scalar fields on the FieldSet's grid "
                                   "(FieldSet.add_field(name, data)); constant fields have no gradient -- use DiffusionUniformKh")  # fmt: skip
     if fieldset.grid.curvilinear or fieldset.interp_method != "linear" or fieldset.time_window is not None:
-        raise NotImplementedError(f"{names[0]} is implemented for resident rectilinear A-grid fields (XLinear_Velocity)")
+        raise NotImplementedError(f"{name} is implemented for resident rectilinear A-grid fields (XLinear_Velocity)")
     if kz.data.dtype != km.data.dtype or (kz.data.shape[0] > 1) != (km.data.shape[0] > 1):
         raise NotImplementedError("Kh_zonal and Kh_meridional must share dtype and time dimension")
     if "dres" not in fieldset.context:
-        raise AttributeError(f"{names[0]} needs fieldset.add_context('dres', <resolution of the Kh gradient>)")
+        raise AttributeError(f"{name} needs fieldset.add_context('dres', <resolution of the Kh gradient>)")
     dres = fieldset.context["dres"]
     if isinstance(dres, np.generic) or not isinstance(dres, (int, float)):
         # a NumPy float64 scalar is a STRONG type: `particles.x + dres` would be a float64 array in the reference and the
         # whole kernel would run in other dtypes; the reference's own usage passes a Python float (tests/test_diffusion.py:65)
         raise NotImplementedError("fieldset.dres must be a Python float (fieldset.add_context('dres', float(...)))")
-    g = fieldset.grid
-    self.advdiff = dict(scheme=K.ADVDIFF[names[0]], kh_slots=(kz._slot, km._slot), dres=float(dres), deg2m_sq=pow(g.deg2m, 2))
+    return dict(scheme=K.ADVDIFF[name], kh_slots=(kz._slot, km._slot), dres=float(dres), deg2m_sq=pow(fieldset.grid.deg2m, 2))
+
+
+def _setup_advdiff(self, names, fieldset):
+    self.advdiff = _advdiff_params(fieldset, names[0])
     self.stepwise = False
     self.scheme_name, self.scheme = names[0], -2
     self.kh, self.kh_spherical, self.kh_deg2m = (0.0, 0.0), False, 1.0

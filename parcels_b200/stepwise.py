@@ -33,7 +33,7 @@ def kernel_execute_stepwise(pset, plan, endtime: float, dt: float):
         d["dt"][:] = np.maximum(np.minimum(d["dt"], tte), 0) if sign == 1 else np.minimum(np.maximum(d["dt"], -tte), 0)
         steps += int(np.count_nonzero(evaluate))
         for item in plan.items:
-            if item[0] == "device":
+            if item[0] in ("device", "advdiff"):
                 _device_kernels(pset, eng, item, dt, endtime)
             else:
                 f = item[1]
@@ -71,7 +71,6 @@ def _device_kernels(pset, eng, item, dt, endtime):
     """One iteration of the built-in kernels ``item`` on the device: the kernel applies the reference's own
     evaluate mask (state in {Success, Evaluate} and time-to-endtime >= 0) and dt clamp, accumulates dx/dy/dz and
     updates state/ei; nothing else."""
-    _, scheme, diffusion, plan = item
     d = pset._data
     pset._rng_call += 1
     ei_last = np.ascontiguousarray(d["ei"][:, -1])
@@ -82,9 +81,15 @@ def _device_kernels(pset, eng, item, dt, endtime):
         evaluated = np.isin(d["state"], [StatusCode.Success, StatusCode.Evaluate]) & (sign * (endtime - d["t"]) >= 0)
         hint_all_zero = not np.any((ei_last[evaluated].astype(np.int64) % g.xdim) != 0)
     eng.upload_particles(d, ei_last)
-    rep = eng.advect(eng.make_args(scheme, dt, endtime, diffusion=diffusion, kh=plan.kh, kh_spherical=plan.kh_spherical,
-                                   kh_deg2m=plan.kh_deg2m, seed=pset.seed, rng_call=pset._rng_call, hint_all_zero=hint_all_zero,
-                                   resume=True, kernels_only=True))  # fmt: skip
+    if item[0] == "advdiff":  # AdvectionDiffusionM1 / EM (pb_advect_diffusion)
+        args = eng.make_advdiff_args(dt=dt, endtime=endtime, seed=pset.seed, rng_call=pset._rng_call, resume=True, kernels_only=True,
+                                     **item[1])  # fmt: skip
+    else:
+        _, scheme, diffusion, plan = item
+        args = eng.make_args(scheme, dt, endtime, diffusion=diffusion, kh=plan.kh, kh_spherical=plan.kh_spherical,
+                             kh_deg2m=plan.kh_deg2m, seed=pset.seed, rng_call=pset._rng_call, hint_all_zero=hint_all_zero,
+                             resume=True, kernels_only=True)  # fmt: skip
+    rep = eng.advect(args)
     eng.download_particles(d, ei_last)
     d["ei"][:, -1] = ei_last
     if rep["n_out_of_time"] > 0:  # the reference flags the whole evaluated view (index_search.py:85-86, field.py:31-44)

@@ -77,3 +77,46 @@ def test_spatially_varying_diffusion_statistics(mesh, kernel):
     assert abs(np.mean(x) - g * T) < 4 * sem, (np.mean(x), g * T, sem)
     assert abs(np.mean(y)) < 4 * sem
     assert abs(np.std(y) / sigma - 1) < 0.03 and abs(np.std(x) / sigma - 1) < 0.06
+
+
+def test_advdiff_in_a_mixed_list_matches_oracle():
+    """[AdvectionDiffusionEM, user kernel, user error handler]: the loop runs on the host (stepwise.py), the built-in still on the
+    device -- one pb_advect_diffusion(kernels_only) launch per step, its Wiener increments keyed by the launch counter."""
+    import parcels_b200 as pb
+    from engine_run import make_fieldset
+    from oracle import parcels_oracle as po
+    from oracle_run import oracle_fieldset
+
+    c, kern, kz, km, dres, dt, runtime, _, _ = case_inputs("em_f64_static")
+    seed = 77
+    fs = make_fieldset(c)
+    fs.add_field("Kh_zonal", kz)
+    fs.add_field("Kh_meridional", km)
+    fs.add_context("dres", dres)
+    ps = pb.ParticleSet(fs, x=c["x"], y=c["y"], z=c["z"], t=c["t"], seed=seed)
+
+    def Drift(particles, fieldset):
+        particles.dx += 1.5
+
+    def DeleteErr(particles, fieldset):
+        particles[particles.state >= 50].state = 30
+
+    ps.execute([getattr(pb, kern), Drift, DeleteErr], dt=dt, runtime=runtime)
+
+    ofs = oracle_fieldset(c)
+    ofs.scalars = {"Kh_zonal": (kz, "linear"), "Kh_meridional": (km, "linear")}
+    ofs.context["dres"] = dres
+    pd = po.create_particle_data(c["x"], c["y"], c["z"], c["t"])
+    launch = {"k": 0}
+
+    def normal(view):
+        launch["k"] += 1
+        return wiener_normals(seed, launch["k"], 0, view.particle_id)
+
+    def ODrift(p, fs_):
+        p.dx = p.dx + 1.5
+
+    po.pset_execute(pd, ofs, [getattr(po, kern)(normal), ODrift, po.DeleteOnError], dt, runtime=runtime)
+    assert len(ps) == len(pd["x"]) > 0 and launch["k"] == int(round(runtime / dt))
+    for key in ("particle_id", "state", "t", "ei", "x", "y", "z"):
+        np.testing.assert_array_equal(ps._data[key], pd[key], err_msg=key)
