@@ -35,6 +35,17 @@ def _has_nan(a) -> bool:
     return bool(s != s) and bool(np.isnan(a).any())
 
 
+def _hint_all_zero(ei_last, evaluated, xdim) -> bool:
+    """Curvilinear grids: True when the hinted xi (= ei % xdim) of EVERY evaluated particle is 0 -- the reference then skips
+    the hint test for the whole batch (`if np.any(xi)`, _core/index_search.py:269).  `evaluated(slice)` gives the mask of a
+    slice of the set; a non-zero hint among the first few thousand particles settles the (usual) answer without a full pass."""
+    head = slice(0, min(len(ei_last), 4096))
+    if np.any((ei_last[head][evaluated(head)].astype(np.int64) % xdim) != 0):
+        return False
+    full = slice(None)
+    return not np.any((ei_last[evaluated(full)].astype(np.int64) % xdim) != 0)
+
+
 def _builtin_name(f):
     """Name of the built-in kernel ``f`` stands for, or None for a user function.  Built-ins are this package's
     tokens (kernels.py, by identity) and the reference package's own kernel functions (by module + name); a user
@@ -437,8 +448,7 @@ class ParticleSet:
             # the reference skips the hint test for the WHOLE batch when every hinted xi is 0
             # (`if np.any(xi)`, _core/index_search.py:269), e.g. on the first eval of a fresh set
             sign = 1 if dt > 0 else -1
-            evaluated = sign * (endtime - d["t"]) >= 0
-            hint_all_zero = not np.any((ei_last[evaluated].astype(np.int64) % g.xdim) != 0)
+            hint_all_zero = _hint_all_zero(ei_last, lambda s_: sign * (endtime - d["t"][s_]) >= 0, g.xdim)
 
         def args(max_iters=-1):
             if plan.advdiff is not None:
@@ -484,6 +494,16 @@ class ParticleSet:
             self._host_stale = True
             self._n_device = n
             d = self._data  # full download
+        elif (rep["n_deleted"] > 0 and rep["max_state"] < StatusCode.Error and len(self._pclass.extra) == 0
+              and d["ei"].shape[1] == 1 and self.fieldset.time_window is None):  # fmt: skip
+            # deletions, nothing to raise: drop the deleted particles in HBM (order preserved, like np.delete) and download the
+            # compacted set -- instead of downloading everything and np.delete-ing every host array (kernel.py:98-106)
+            eng.remove_deleted()
+            new = eng.download_all(ngrids=1)
+            new["dt"][:] = dt  # kernel.py:225-226
+            d.update(new)  # keep the dict object: it may be shared with the caller (adapter.pset_from_parcels)
+            self._device_synced = True
+            return
         else:
             eng.download_particles(d, ei_last)
             d["ei"][:, -1] = ei_last

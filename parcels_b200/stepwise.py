@@ -77,9 +77,12 @@ def _device_kernels(pset, eng, item, dt, endtime):
     hint_all_zero = False
     g = pset.fieldset.grid
     if g.curvilinear:
+        from .particleset import _hint_all_zero
+
         sign = 1 if dt > 0 else -1
-        evaluated = np.isin(d["state"], [StatusCode.Success, StatusCode.Evaluate]) & (sign * (endtime - d["t"]) >= 0)
-        hint_all_zero = not np.any((ei_last[evaluated].astype(np.int64) % g.xdim) != 0)
+        hint_all_zero = _hint_all_zero(
+            ei_last, lambda s_: np.isin(d["state"][s_], [StatusCode.Success, StatusCode.Evaluate]) & (sign * (endtime - d["t"][s_]) >= 0), g.xdim
+        )
     eng.upload_particles(d, ei_last)
     if item[0] == "advdiff":  # AdvectionDiffusionM1 / EM (pb_advect_diffusion)
         args = eng.make_advdiff_args(dt=dt, endtime=endtime, seed=pset.seed, rng_call=pset._rng_call, resume=True, kernels_only=True,
