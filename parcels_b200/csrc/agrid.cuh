@@ -162,7 +162,9 @@ template <class A, class D, int NC>
 struct EvalCtx {
     AxisCell<A> cx, cy, cz;
     AxisCell<double> ct;
-#ifdef PB_SMEM_CACHE
+#if defined(PB_SMEM_CACHE) && defined(PB_SMEM_F32)
+    Corners<D, NC, false> cor;  // tuning variant: cached corners kept in the data dtype (half the shared memory, F2F per read)
+#elif defined(PB_SMEM_CACHE)
     Corners<D, NC, std::is_same<A, double>::value> cor;
 #else
     Corners<D, NC> cor;
@@ -273,7 +275,8 @@ __device__ __forceinline__ void eval_uvw(const GridDev& g, const FieldDev& f, Ev
             // waiver 1).  `eta_b - j_grid` is a float array minus an int64 array: float64 whatever the bcoord dtype.
             const int nT = tau > 0 ? 2 : 1, nZ = zeta > 0 ? 2 : 1;
             int n_land = 0;
-            double num = 0.0, den = 0.0, node_val = 0.0;
+            double num = 0.0, den = 0.0;
+            D node_val = 0;  // np.where(exact_mask, corner_data, 0.0) keeps the DATA dtype: a float32 field sums in float32
             bool on_node = false;
 #pragma unroll
             for (int k = 0; k < 16; ++k) {
@@ -287,13 +290,13 @@ __device__ __forceinline__ void eval_uvw(const GridDev& g, const FieldDev& f, Ev
                     const double inv = 1.0 / d2;
                     num = num + (double)c * inv;
                     den = den + inv;
-                    if (d2 == 0) { node_val = node_val + (double)c; on_node = true; }
+                    if (d2 == 0) { node_val = node_val + (D)c; on_node = true; }
                 }
             }
             const int n_all = nT * nZ * 4;
             double r = u.v;
             if (n_land == n_all) r = 0.0;
-            else if (n_land > 0) r = on_node ? node_val : num / den;
+            else if (n_land > 0) r = on_node ? (double)node_val : num / den;
             u.v = u.f32 ? (double)(float)r : r;  // assigned into the XLinear result array: keeps its dtype
         }
         v = Val{0.0, u.f32}; w = v;
