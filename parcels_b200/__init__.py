@@ -26,6 +26,7 @@ from .particlefile import ParticleFile, read_particlefile
 from .particleset import ParticleSet
 from .statuscodes import (
     KernelWarning,
+    ParticleSetWarning,
     FieldInterpolationError,
     FieldOutOfBoundError,
     FieldOutOfBoundSurfaceError,
@@ -38,6 +39,6 @@ from .statuscodes import (
 __all__ = [
     "AdvectionDiffusionEM", "AdvectionDiffusionM1", "AdvectionEE", "AdvectionRK2", "AdvectionRK2_3D", "AdvectionRK4", "AdvectionRK4_3D", "AdvectionRK45", "DeleteParticle",
     "DiffusionUniformKh", "Field", "FieldInterpolationError", "FieldOutOfBoundError", "FieldOutOfBoundSurfaceError",
-    "FieldSet", "GeneralError", "GridSearchingError", "KernelWarning", "OutsideTimeInterval", "Particle", "ParticleClass", "ParticleFile", "ParticleSet", "Variable", "read_particlefile", "StatusCode",
+    "FieldSet", "GeneralError", "GridSearchingError", "KernelWarning", "OutsideTimeInterval", "ParticleSetWarning", "Particle", "ParticleClass", "ParticleFile", "ParticleSet", "Variable", "read_particlefile", "StatusCode",
     "VectorField", "XGrid", "kernels",
 ]  # fmt: skip

@@ -262,6 +262,14 @@ class ParticleSet:
                 t = t.astype(np.float64)
         t = np.repeat(t, x.size) if t.size == 1 else t
         assert x.size == t.size, "t and positions (x, y, z) do not have the same lengths."
+        ti = fieldset.time_interval
+        if ti is not None and t.size and not np.isnan(t).all() and (np.any(t < 0) or np.any(t > ti[1] - ti[0])):
+            import warnings  # reference _core/particleset.py:485-494
+
+            from .statuscodes import ParticleSetWarning
+
+            warnings.warn("Some particles are set to be released outside the FieldSet's executable time domain.", ParticleSetWarning,
+                          stacklevel=2)  # fmt: skip
         self._data = create_particle_data(
             nparticles=x.size,
             ngrids=len(fieldset.gridset),
@@ -388,6 +396,23 @@ class ParticleSet:
         """reference _core/particleset.py:247-250."""
         for k in self._data:
             self._data[k] = np.delete(self._data[k], indices, axis=0)
+
+    @classmethod
+    def from_particlefile(cls, fieldset, pclass, filename, restart=True, restarttime=None, **kwargs):
+        raise NotImplementedError("ParticleSet.from_particlefile is not yet implemented in v4.")  # reference particleset.py:264-292
+
+    def data_indices(self, variable_name, compare_values, invert=False):
+        """Indices of the particles whose ``variable_name`` equals (one of) ``compare_values`` (reference particleset.py:294-319)."""
+        compare_values = np.array([compare_values]) if type(compare_values) not in [list, dict, np.ndarray] else compare_values
+        return np.where(np.isin(self._data[variable_name], compare_values, invert=invert))[0]
+
+    @property
+    def _error_particles(self):
+        return self.data_indices("state", [StatusCode.Success, StatusCode.Evaluate], invert=True)
+
+    @property
+    def _num_error_particles(self):
+        return np.sum(np.isin(self._data["state"], [StatusCode.Success, StatusCode.Evaluate], invert=True))
 
     def populate_indices(self):
         """Pre-populate the cell guesses ``ei`` (reference _core/particleset.py:252-262): one grid search per grid of the
@@ -630,6 +655,14 @@ class ParticleSet:
         if any_nan:
             t[:] = start_time
         outputdt = _to_float_seconds(output_file.outputdt) if output_file is not None else None
+        if outputdt and np.isfinite(outputdt) and len(t) <= 1_000_000 and np.any(np.isfinite(t) & ((t - start_time) % outputdt != 0)):
+            import warnings  # reference _core/particleset.py:473-482
+
+            from .statuscodes import ParticleSetWarning
+
+            warnings.warn("Some of the particles have a start time difference that is not a multiple of outputdt. This could cause the "
+                          "first output of some of the particles that start later in the simulation to be at a different time than "
+                          "expected.", ParticleSetWarning, stacklevel=2)  # fmt: skip
         if output_file is not None and hasattr(output_file, "set_metadata"):  # reference particleset.py:400-403
             output_file.set_metadata(self.fieldset.grid.mesh)
             output_file.metadata["parcels_kernels"] = plan.funcname

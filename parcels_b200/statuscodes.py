@@ -95,5 +95,9 @@ ERRORS_TO_THROW = (
 )
 
 
+class ParticleSetWarning(UserWarning):
+    """Issues in the construction of a ParticleSet (reference _core/warnings.py:14-17)."""
+
+
 class KernelWarning(RuntimeWarning):
     """Warning that a kernel set a default for a missing setting (reference _core/warnings.py)."""

@@ -218,3 +218,19 @@ def test_pset_add_iadd_iter():
     for i, particle in enumerate(pb.ParticleSet(fs, x=np.zeros(5), y=np.ones(5))):
         assert particle.particle_id == i
     assert i == 4
+
+
+def test_pset_warnings_and_index_helpers():
+    """reference tests/test_particleset.py:100-103 (release outside the time domain warns), data_indices / error-particle helpers
+    (_core/particleset.py:294-341), from_particlefile (not implemented in v4 either)."""
+    fs = _fs()
+    with pytest.warns(pb.ParticleSetWarning, match="Some particles are set to be released"):
+        pb.ParticleSet(fs, x=[0.5] * 3, y=[0.5] * 3, t=[0.0, 5.0, 20.0])
+    ps = pb.ParticleSet(fs, x=np.linspace(0, 1, 6), y=np.zeros(6))
+    ps._data["state"][:] = [0, 10, 50, 60, 30, 1]
+    np.testing.assert_array_equal(ps.data_indices("state", [50, 60]), [2, 3])
+    np.testing.assert_array_equal(ps.data_indices("state", 30), [4])
+    np.testing.assert_array_equal(ps._error_particles, [2, 3, 4, 5])
+    assert ps._num_error_particles == 4
+    with pytest.raises(NotImplementedError):
+        pb.ParticleSet.from_particlefile(fs, pb.Particle, "x.parquet")
