@@ -1,7 +1,9 @@
 /* parcels_b200.h -- C-ABI of libparcels_b200.so: the B200-native replacement for the hot path
- * ParticleSet.execute(AdvectionRK4 | AdvectionRK4_3D | AdvectionEE | AdvectionRK2[_3D]
- *                     [+ DiffusionUniformKh] [+ delete-on-error handler])
- * on rectilinear A-grids (XLinear_Velocity) and rectilinear / curvilinear C-grids (CGrid_Velocity).
+ * ParticleSet.execute(AdvectionRK4 | AdvectionRK4_3D | AdvectionEE | AdvectionRK2[_3D] [+ DiffusionUniformKh]
+ *                     | AdvectionRK45 | AdvectionDiffusionM1 | AdvectionDiffusionEM   [+ delete-on-error handler])
+ * on rectilinear A-grids (XLinear_Velocity, XFreeslip, XPartialslip, nearest node) and rectilinear / curvilinear
+ * C-grids (CGrid_Velocity), plus Field.eval / VectorField.eval sampling, the ParticleFile row selection and the
+ * multi-GPU particle migration.
  *
  * The reference (Parcels v4-alpha, pure Python/NumPy) has no FFI; this header DEFINES the
  * drop-in boundary.  Each entry point cites the reference interface it
