@@ -23,7 +23,7 @@ from .kernels import (
 )
 from .particle import Particle, ParticleClass, Variable
 from .particlefile import ParticleFile, read_particlefile
-from .particleset import ParticleSet
+from .particleset import Kernel, ParticleSet
 from .statuscodes import (
     KernelWarning,
     ParticleSetWarning,
@@ -39,6 +39,6 @@ from .statuscodes import (
 __all__ = [
     "AdvectionDiffusionEM", "AdvectionDiffusionM1", "AdvectionEE", "AdvectionRK2", "AdvectionRK2_3D", "AdvectionRK4", "AdvectionRK4_3D", "AdvectionRK45", "DeleteParticle",
     "DiffusionUniformKh", "Field", "FieldInterpolationError", "FieldOutOfBoundError", "FieldOutOfBoundSurfaceError",
-    "FieldSet", "GeneralError", "GridSearchingError", "KernelWarning", "OutsideTimeInterval", "ParticleSetWarning", "Particle", "ParticleClass", "ParticleFile", "ParticleSet", "Variable", "read_particlefile", "StatusCode",
+    "FieldSet", "GeneralError", "GridSearchingError", "Kernel", "KernelWarning", "OutsideTimeInterval", "ParticleSetWarning", "Particle", "ParticleClass", "ParticleFile", "ParticleSet", "Variable", "read_particlefile", "StatusCode",
     "VectorField", "XGrid", "kernels",
 ]  # fmt: skip

@@ -326,9 +326,19 @@ class FieldSet:
         return f
 
     def add_context(self, name, value):
+        """reference _core/fieldset.py:207-222; the value is then also an attribute (``fieldset.<name>``, :101-108)."""
+        if not isinstance(name, str) or not name.isidentifier():
+            raise ValueError(f"Expected a string that is a valid Python variable name, got {name!r}")
         if name in self.context:
             raise ValueError(f"FieldSet already has a context with name '{name}'")
         self.context[name] = value
+
+    def __getattr__(self, name):
+        """Context variables as attributes, as user kernels read them (``fieldset.dres``; reference _core/fieldset.py:101-108)."""
+        ctx = self.__dict__.get("context")
+        if ctx is not None and name in ctx:
+            return ctx[name]
+        raise AttributeError(f"FieldSet has no attribute '{name}'")
 
     # -- engine management: fields are uploaded once and stay resident in HBM --------------------
     def engine(self, device: int = 0) -> Engine:

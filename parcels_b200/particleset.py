@@ -17,7 +17,7 @@ from . import kernels as K
 from .particle import Particle, ParticleClass, create_particle_data
 from .statuscodes import ERRORS_TO_THROW, StatusCode, raise_for_state
 
-__all__ = ["ParticleSet"]
+__all__ = ["Kernel", "ParticleSet"]
 
 
 def _to_float_seconds(v):
@@ -65,6 +65,21 @@ def _delete_on_error(particles, fieldset):
     particles.state = np.where(s >= 50, StatusCode.Delete, s)
 
 
+def _assert_kernel_signature(f):
+    """A kernel function is ``f(particles, fieldset)`` (reference _python.py:33-52 `assert_same_function_signature` against
+    AdvectionRK4, called from Kernel.__init__, _core/kernel.py:69)."""
+    import inspect
+
+    params = list(inspect.signature(f).parameters.values())
+    if len(params) != 2:
+        raise ValueError(f"Kernel function must have 2 parameters, got {len(params)}")
+    for want, got in zip(("particles", "fieldset"), params, strict=True):
+        if got.kind != inspect.Parameter.POSITIONAL_OR_KEYWORD:
+            raise ValueError(f"Parameter '{got.name}' has incorrect parameter kind. Expected POSITIONAL_OR_KEYWORD, got {got.kind}")
+        if got.name != want:
+            raise ValueError(f"Parameter '{got.name}' has incorrect name. Expected '{want}', got '{got.name}'")
+
+
 class KernelPlan:
     """The kernel list lowered to the fused device kernel's switches (include/parcels_b200.h)."""
 
@@ -78,6 +93,7 @@ class KernelPlan:
         for f in kernel_list:
             if not isinstance(f, types.FunctionType):
                 raise TypeError(f"Argument `kernels` should be a function or list of functions. Got {type(f)}")
+            _assert_kernel_signature(f)
         self.funcname = "".join(f.__name__ for f in kernel_list)
         tokens = [_builtin_name(f) for f in kernel_list]  # None for user functions (recognised by identity, not by name)
         names = list(tokens)
@@ -212,6 +228,29 @@ def _setup_advdiff(self, names, fieldset):
 
 
 KernelPlan._setup_advdiff = _setup_advdiff
+
+
+class Kernel:
+    """``Kernel(kernels=[...], pset=pset)`` as in the reference (_core/kernel.py:40-96): validates the list (functions with the
+    ``(particles, fieldset)`` signature, RK45 prerequisites) and names it; ``pset.execute`` lowers the same list to device launches."""
+
+    def __init__(self, kernels, pset):
+        if not isinstance(kernels, list):
+            raise ValueError(f"kernels must be a list. Got {kernels=!r}")
+        for f in kernels:
+            if not isinstance(f, types.FunctionType):
+                raise TypeError(f"Argument `kernels` should be a function or list of functions. Got {type(f)}")
+            _assert_kernel_signature(f)
+        if len(kernels) == 0:
+            raise ValueError("List of `kernels` should have at least one function.")
+        self._fieldset = pset.fieldset
+        self._pclass = pset._pclass
+        self._plan = KernelPlan(kernels, pset.fieldset, pset._pclass)
+        self._kernels = kernels
+
+    funcname = property(lambda self: "".join(f.__name__ for f in self._kernels))
+    pclass = property(lambda self: self._pclass)
+    fieldset = property(lambda self: self._fieldset)
 
 
 class ParticleSet:

@@ -234,3 +234,71 @@ def test_pset_warnings_and_index_helpers():
     assert ps._num_error_particles == 4
     with pytest.raises(NotImplementedError):
         pb.ParticleSet.from_particlefile(fs, pb.Particle, "x.parquet")
+
+
+def test_kernel_object_and_signature_checks():
+    """reference tests/test_kernel.py:54-165 (test_kernel_init / _merging / _from_list / _from_list_error_checking /
+    test_RK45Kernel_error_no_next_dt / test_kernel_signature), against the host mirror's Kernel."""
+    fs = _fs()
+    pset = pb.ParticleSet(fs, x=[0.5], y=[0.5])
+
+    def MoveEast(particles, fieldset):
+        particles.dx += 0.1
+
+    def MoveNorth(particles, fieldset):
+        particles.dy += 0.1
+
+    pb.Kernel(kernels=[pb.AdvectionRK4], pset=pset)
+    merged = pb.Kernel(kernels=[pb.AdvectionRK4, MoveEast, MoveNorth], pset=pset)
+    assert merged.funcname == "AdvectionRK4MoveEastMoveNorth" and merged._kernels == [pb.AdvectionRK4, MoveEast, MoveNorth]
+    merged = pb.Kernel(kernels=[MoveEast, MoveNorth, pb.AdvectionRK4], pset=pset)
+    assert merged.funcname == "MoveEastMoveNorthAdvectionRK4" and len(merged._kernels) == 3
+    with pytest.raises(ValueError, match="List of `kernels` should have at least one function."):
+        pb.Kernel(kernels=[], pset=pset)
+    with pytest.raises(TypeError, match=r"Argument `kernels` should be a function or list of functions.*"):
+        pb.Kernel(kernels=[pb.AdvectionRK4, "something else"], pset=pset)
+    with pytest.raises(TypeError, match=r".* should be a function or list of functions.*"):
+        pb.Kernel(kernels=[pb.Kernel(kernels=[pb.AdvectionRK4], pset=pset), MoveEast, MoveNorth], pset=pset)
+    with pytest.raises(ValueError, match='ParticleClass requires a "next_dt" for AdvectionRK45 Kernel.'):
+        pb.Kernel(kernels=[pb.AdvectionRK45], pset=pset)
+
+    def good_kernel(particles, fieldset):
+        pass
+
+    def version_3_kernel(particle, fieldset, time):
+        pass
+
+    def version_3_kernel_without_time(particle, fieldset):
+        pass
+
+    def kernel_switched_args(fieldset, particle):
+        pass
+
+    def kernel_with_forced_kwarg(particles, *, fieldset=0):
+        pass
+
+    pb.Kernel(kernels=[good_kernel], pset=pset)
+    with pytest.raises(ValueError, match="Kernel function must have 2 parameters, got 3"):
+        pb.Kernel(kernels=[version_3_kernel], pset=pset)
+    with pytest.raises(ValueError, match="Parameter 'particle' has incorrect name. Expected 'particles', got 'particle'"):
+        pb.Kernel(kernels=[version_3_kernel_without_time], pset=pset)
+    with pytest.raises(ValueError, match="Parameter 'fieldset' has incorrect name. Expected 'particles', got 'fieldset'"):
+        pb.Kernel(kernels=[kernel_switched_args], pset=pset)
+    with pytest.raises(ValueError, match="Parameter 'fieldset' has incorrect parameter kind. Expected POSITIONAL_OR_KEYWORD, got KEYWORD_ONLY"):
+        pb.Kernel(kernels=[kernel_with_forced_kwarg], pset=pset)
+    with pytest.raises(ValueError, match="2 parameters"):  # execute() checks the same
+        pset.execute(version_3_kernel, dt=1.0, runtime=1.0)
+
+
+def test_fieldset_context_is_an_attribute():
+    """reference tests/test_kernel.py:27-51: `fieldset.add_context(name, v)` makes `fieldset.<name>` readable in kernels."""
+    fs = _fs()
+    fs.add_context("fix_lon", -0.5)
+    fs.add_context("func", lambda x: 2 * x)
+    assert fs.fix_lon == -0.5 and fs.func(3) == 6
+    with pytest.raises(AttributeError, match="FieldSet has no attribute 'nope'"):
+        fs.nope
+    with pytest.raises(ValueError, match="already has a context"):
+        fs.add_context("fix_lon", 1)
+    with pytest.raises(ValueError, match="valid Python variable name"):
+        fs.add_context("not a name", 1)
