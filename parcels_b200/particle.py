@@ -3,6 +3,8 @@ t f64; z, y, x, dz, dy, dx f32; particle_id i64; dt f64; state i32; plus ``ei`` 
 
 from __future__ import annotations
 
+import operator
+
 import numpy as np
 
 from .statuscodes import StatusCode
@@ -88,5 +90,17 @@ def create_particle_data(*, nparticles, ngrids, initial, pclass=None):
     for name, dt in pclass.variables:
         if name not in data:
             init = {"dt": 1.0, "state": StatusCode.Evaluate, **inits}.get(name, 0)
-            data[name] = np.full((nparticles,), init, dtype=dt)
+            if isinstance(init, operator.attrgetter):
+                # `Variable("age0", initial=attrgetter("t"))`: a copy of another variable's initial values, in THAT variable's
+                # dtype (reference _core/particle.py:212-215)
+                data[name] = data[init(_NameOf())].copy()
+            else:
+                data[name] = np.full((nparticles,), init, dtype=dt)
     return data
+
+
+class _NameOf:
+    """``attrgetter("x")(_NameOf())`` == "x" (reference _compat._attrgetter_helper)."""
+
+    def __getattr__(self, name):
+        return name

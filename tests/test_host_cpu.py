@@ -302,3 +302,36 @@ def test_fieldset_context_is_an_attribute():
         fs.add_context("fix_lon", 1)
     with pytest.raises(ValueError, match="valid Python variable name"):
         fs.add_context("not a name", 1)
+
+
+def test_pset_creation_like_the_reference():
+    """reference tests/test_particleset.py:21-98 (create_lon_lat, create_empty, with_pids, customvars, custominit via attrgetter /
+    on the pclass / overridden on the pset)."""
+    from operator import attrgetter
+
+    fs = _fs()
+    npart = 100
+    lon, lat = np.linspace(0, 1, npart, dtype=np.float32), np.linspace(1, 0, npart, dtype=np.float32)
+    pset = pb.ParticleSet(fs, x=lon, y=lat, pclass=pb.Particle)
+    assert np.allclose([p.x for p in pset], lon, rtol=1e-12) and np.allclose([p.y for p in pset], lat, rtol=1e-12)
+    empty = pb.ParticleSet(fs, pclass=pb.Particle)
+    empty.execute(pb.AdvectionRK4, endtime=1.0, dt=1.0)  # nothing to launch: no device needed
+    assert empty.size == 0
+    for offset in (0, 1, 200):
+        ids = np.arange(offset, npart + offset)
+        assert np.allclose([p.particle_id for p in pb.ParticleSet(fs, x=lon, y=lat, particle_ids=ids)], ids)
+    two = pb.Particle.add_variable([pb.Variable("sample_var"), pb.Variable("sample_var2")])
+    ps = pb.ParticleSet(fs, x=0, y=0, pclass=two, sample_var=5.0, sample_var2=10.0)
+    assert [p.sample_var for p in ps] == [5.0] and [p.sample_var2 for p in ps] == [10.0]
+    ps = pb.ParticleSet(fs, x=3, y=0, pclass=pb.Particle.add_variable(pb.Variable("sample_var", initial=attrgetter("x"))))
+    assert np.allclose([p.sample_var for p in ps], 3.0)
+    four = pb.Particle.add_variable(pb.Variable("sample_var", initial=4))
+    assert [p.sample_var for p in pb.ParticleSet(fs, x=0, y=0, pclass=four)] == [4.0]
+    assert [p.sample_var for p in pb.ParticleSet(fs, x=0, y=0, pclass=four, sample_var=5)] == [5.0]
+    with pytest.raises(RuntimeError, match="Particle class does not have Variable nope"):
+        pb.ParticleSet(fs, x=0, y=0, nope=3)
+    # default z: the depth level closest to zero (reference :188-215)
+    depths = np.concatenate([np.linspace(-9, -3, 3), np.linspace(2, 8, 3)])
+    z6 = np.zeros((1, 6, 4, 5), np.float32)
+    fsz = pb.FieldSet.from_arrays(lon=np.linspace(0, 1, 5), lat=np.linspace(0, 1, 4), depth=depths, U=z6, V=z6, mesh="flat")
+    assert np.isclose(pb.ParticleSet(fsz, x=[0], y=[0]).z[0], 2.0)
