@@ -55,3 +55,19 @@ def cell_centers(lon, lat):
     clat = 0.25 * (lat[:-1, :-1] + lat[:-1, 1:] + lat[1:, 1:] + lat[1:, :-1])
     jj, ii = np.meshgrid(np.arange(lon.shape[0] - 1), np.arange(lon.shape[1] - 1), indexing="ij")
     return clat.ravel(), clon.ravel(), jj.ravel(), ii.ravel()
+
+
+def stommel_gyre(xdim=200, ydim=200):
+    """Western-boundary-current gyre on an A-grid (reference _datasets/structured/generated.py:301-357): sea-surface height
+    P = (1 - exp(-x/eps) - x) pi sin(pi y) s and its geostrophic velocities, float32 arrays on a 10 000 km square."""
+    a = b = 10000 * 1e3
+    s = 0.05
+    lon = np.linspace(0, a, xdim, dtype=np.float32)
+    lat = np.linspace(0, b, ydim, dtype=np.float32)
+    eps = (1 / (11.6 * 86400)) / (2e-11 * a)
+    xi, yi = (lon / a).astype(np.float64)[None, :], (lat / b).astype(np.float64)[:, None]
+    g = 1 - np.exp(-xi / eps) - xi
+    P = (g * np.pi * np.sin(np.pi * yi) * s).astype(np.float32)
+    U = (-g * np.pi**2 * np.cos(np.pi * yi) * s).astype(np.float32)
+    V = ((np.exp(-xi / eps) / eps - 1) * np.pi * np.sin(np.pi * yi) * s).astype(np.float32)
+    return dict(lon=lon, lat=lat, U=U[None, None], V=V[None, None], P=P[None, None])

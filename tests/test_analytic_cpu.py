@@ -76,3 +76,24 @@ def test_brownian_std(mesh):
     np.testing.assert_allclose(np.std(pd["y"]), np.sqrt(2 * 50 * conv**2 * 7200), atol=tol)
     np.testing.assert_allclose(np.mean(pd["x"]), 0, atol=tol)
     np.testing.assert_allclose(np.mean(pd["y"]), 0, atol=tol)
+
+
+@pytest.mark.parametrize("name", ["AdvectionRK2", "AdvectionRK4", "AdvectionRK45"])
+def test_stommel_gyre_conserves_sea_surface_height(name):
+    """reference tests/test_advection.py:354-387 (A-grid): P sampled along the trajectory stays within rtol 0.1 of its start
+    value over one day of 30-minute steps."""
+    f = A.stommel_gyre()
+    fs = po.OFieldSet(po.OGrid(f["lon"], f["lat"], None, mesh="flat"), f["U"], f["V"])
+    x0 = np.linspace(10e3, 100e3, 2)
+    pd = po.create_particle_data(x0, np.full(2, 5000e3), np.zeros(2), 0.0)
+    if name == "AdvectionRK45":
+        fs.context.update(RK45_tol=0.1, RK45_min_dt=1, RK45_max_dt=24 * 60 * 60)
+        pd["next_dt"] = np.zeros(2, dtype=np.float32)
+        kern = po.AdvectionRK45
+    else:
+        kern = KERN[name][0]
+    p0 = po.eval_scalar(fs, f["P"], "linear", pd["t"], pd["z"], pd["y"], pd["x"], None).copy()
+    po.pset_execute(pd, fs, [kern], 1800.0, runtime=86400.0)
+    p1 = po.eval_scalar(fs, f["P"], "linear", pd["t"], pd["z"], pd["y"], pd["x"], None)
+    assert np.all(pd["t"] == 86400.0) and np.all(np.abs(pd["x"] - x0) + np.abs(pd["y"] - 5000e3) > 1e3)
+    np.testing.assert_allclose(p1, p0, rtol=0.1)
