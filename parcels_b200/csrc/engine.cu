@@ -1275,6 +1275,11 @@ int32_t pb_field_window_create(pb_engine* e, int32_t slot, int32_t data_is_f64, 
     const size_t level_bytes = (size_t)Z * Y * X * (data_is_f64 ? 8 : 4);
     int32_t rc = e->fbuf[slot].ensure(level_bytes * (size_t)(window_levels + 1));
     if (rc) return rc;
+    // A sample exactly on a time level t == time[k] has ti = k - 1, tau = 1 (side="left" search): level k - 1 is gathered and
+    // multiplied by (1 - tau) = 0.  It need not be resident for the result -- but its ring slot must hold FINITE values, or
+    // 0 * garbage = NaN flags the particle (found by oracle/hostsim, where "device" memory is malloc'ed, not zero pages)
+    CK(cudaMemsetAsync(e->fbuf[slot].p, 0, level_bytes * (size_t)(window_levels + 1), e->stream));
+    CK(cudaStreamSynchronize(e->stream));  // the level loads run on the copy stream: the zeros must be in place first
     e->ring = window_levels + 1;
     e->win_first = 0; e->win_n = 0;
     return set_field(e, slot, e->fbuf[slot].p, data_is_f64, T_total, Z, Y, X);

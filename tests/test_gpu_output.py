@@ -107,6 +107,9 @@ def test_resident_intervals_write_the_rows_the_reference_writes(name, golden_dir
     assert rec.on_device[0] is False and all(rec.on_device[1:])  # initial condition from the host, the rest from HBM
     np.testing.assert_array_equal([r[0] for r in rec.rows], g[f"{name}/times"])
     exact = c["mesh"] == "flat"
+    # ulps of max(|x|, 1 % of the coordinate range): the longitudes of the spherical case cross zero, where the spacing of
+    # the value itself says nothing about the accuracy of the increments that produced it
+    floor = {k: 0.01 * float(np.abs(np.asarray(c[k])).max()) or None for k in "xyz"}
     for i, (_, cols) in enumerate(rec.rows):
         np.testing.assert_array_equal(cols["particle_id"], g[f"{name}/{i}/particle_id"])
         np.testing.assert_array_equal(cols["t"], g[f"{name}/{i}/t"])
@@ -114,7 +117,7 @@ def test_resident_intervals_write_the_rows_the_reference_writes(name, golden_dir
             if exact:
                 np.testing.assert_array_equal(cols[k], g[f"{name}/{i}/{k}"])
             else:
-                assert ulp_diff_f32(cols[k], g[f"{name}/{i}/{k}"]).max() <= 2
+                assert ulp_diff_f32(cols[k], g[f"{name}/{i}/{k}"], floor=floor[k]).max() <= 2
     # the lazily refreshed host arrays equal the oracle's final state
     pd = po.create_particle_data(c["x"], c["y"], c["z"], c["t"])
     po.pset_execute(pd, oracle_fieldset(c), [getattr(po, c["kernels"][0]), po.DeleteOnError], c["dt"], outputdt=outputdt,
@@ -127,7 +130,7 @@ def test_resident_intervals_write_the_rows_the_reference_writes(name, golden_dir
         if exact:
             np.testing.assert_array_equal(ps._data[k], pd[k])
         else:
-            assert ulp_diff_f32(ps._data[k], pd[k]).max() <= 2
+            assert ulp_diff_f32(ps._data[k], pd[k], floor=floor[k]).max() <= 2
 
 
 def test_parquet_file_from_resident_set_equals_host_path(tmp_path):

@@ -1,0 +1,51 @@
+"""CPU (no GPU needed): the GPU parity tests run against the product's kernel SOURCES compiled for the host
+(oracle/hostsim: g++ build of parcels_b200/csrc behind the same C-ABI, one simulated thread at a time).
+
+This checks the LOGIC of the CUDA sources -- state machine, searches, interpolation arithmetic, error / delete / replay
+handling, output selection, hash build, host bindings -- against the oracle and the reference's golden outputs on machines
+without a GPU.  It is test infrastructure: the product never loads the simulation (it needs PB_LIB pointing at it AND
+PB_HOSTSIM_TEST=1), and the real parity statement is `pytest -m gpu` on the B200."""
+
+import os
+import shutil
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+pytestmark = pytest.mark.skipif(shutil.which(os.environ.get("CXX", "g++")) is None, reason="no C++ compiler for the host simulation")
+
+# needs two CUDA devices / torch CUDA tensors for the exchange buffers: not simulated
+DESELECT = ["tests/test_gpu_decomposed.py"]
+
+
+def _env(lib):
+    env = dict(os.environ, PB_LIB=lib, PB_HOSTSIM_TEST="1", PYTHONPATH=ROOT + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    return env
+
+
+def test_gpu_suite_passes_on_the_host_compiled_kernel_sources():
+    from oracle.hostsim import build as hb
+
+    lib = hb.build()
+    cmd = [sys.executable, "-m", "pytest", "tests", "-m", "gpu", "-q", "-x", "-p", "no:cacheprovider"]
+    for d in DESELECT:
+        cmd += ["--deselect", d]
+    res = subprocess.run(cmd, cwd=ROOT, env=_env(lib), capture_output=True, text=True, timeout=1500)
+    tail = "\n".join(res.stdout.splitlines()[-25:])
+    assert res.returncode == 0, tail + "\n" + res.stderr[-2000:]
+    assert " passed" in tail and "failed" not in tail, tail
+
+
+def test_simulation_is_inert_without_the_test_switch():
+    """The simulated device only exists for the harness: without PB_HOSTSIM_TEST=1 the library reports no device at all."""
+    from oracle.hostsim import build as hb
+
+    lib = hb.build()
+    code = ("import ctypes, sys; l = ctypes.CDLL(sys.argv[1]); l.pb_device_count.restype = ctypes.c_int32; "
+            "h = ctypes.c_void_p(); print(l.pb_device_count(), l.pb_engine_create(0, ctypes.byref(h)))")  # fmt: skip
+    env = {k: v for k, v in os.environ.items() if k != "PB_HOSTSIM_TEST"}
+    out = subprocess.run([sys.executable, "-c", code, lib], env=env, capture_output=True, text=True, timeout=120).stdout.split()
+    assert out[0] == "0" and int(out[1]) < 0, out
