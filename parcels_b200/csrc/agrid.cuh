@@ -371,6 +371,7 @@ template <class A, class D, bool HAS_TIME, int NC_, int MODE = 0>
 struct AGridPolicy {
     static constexpr int NC = NC_;
     static constexpr bool RUNTIME_DTYPE = false;  // interpolation arithmetic is typed on the position dtype
+    static constexpr bool F32_STAGES = (MODE == 2);  // nearest node: a stage value can be float32 at a float64 position
     using Ctx = EvalCtx<A, D, NC_>;
     __device__ static __forceinline__ void init(Ctx& e, const AdvectParams&, int ei) {
         e.cx.idx = e.cy.idx = e.cz.idx = e.ct.idx = -100;

@@ -362,6 +362,7 @@ template <class A, class D, int NC_>
 struct CGridPolicy {
     static constexpr int NC = NC_;
     static constexpr bool RUNTIME_DTYPE = false;
+    static constexpr bool F32_STAGES = false;
     using Ctx = CGridCtx<A, D>;
 
     __device__ static __forceinline__ void init(Ctx& e, const AdvectParams& p, int ei) {
@@ -520,6 +521,7 @@ template <class A, class D, int NC_, bool SPH>
 struct CurvPolicy {
     static constexpr int NC = NC_;
     static constexpr bool RUNTIME_DTYPE = true;
+    static constexpr bool F32_STAGES = false;
     using Ctx = CGridCtx<A, D>;
 
     __device__ static __forceinline__ void init(Ctx& e, const AdvectParams& p, int ei) { CGridPolicy<A, D, NC_>::init(e, p, ei); }

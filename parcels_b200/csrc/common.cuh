@@ -284,6 +284,9 @@ __global__ void __launch_bounds__(PB_BLOCK_THREADS, PB_MINBLOCKS) advect_kernel(
             // ---- advection kernel (kernels/_advection.py) ----
             Val u1, v1, w1, uk, vk, wk;
             double su, sv, sw;  // running RK4 sums, left to right
+            // F32_STAGES policies: the same sums in float32, valid while every term so far was float32
+            [[maybe_unused]] bool xf32 = false, yf32 = false, zf32 = false;
+            [[maybe_unused]] float sxf = 0.f, syf = 0.f, szf = 0.f;
             // with DiffusionUniformKh in the list, ei[:, -1] was overwritten with 0 for every particle by the
             // constant-field evals of the previous step: curvilinear hints are all zero again
             const bool nohint1 = (it == 0 && p.hint_all_zero) || (it > 0 && p.diffusion);
@@ -312,6 +315,10 @@ __global__ void __launch_bounds__(PB_BLOCK_THREADS, PB_MINBLOCKS) advect_kernel(
             if (nstage > 0) Policy::template eval<float, float, float>(p, e, nohint1, t, z, y, x, u1, v1, w1);
             su = u1.v; sv = v1.v; sw = w1.v;
             uk = u1; vk = v1; wk = w1;
+            if constexpr (Policy::F32_STAGES) {
+                xf32 = u1.f32; yf32 = v1.f32; zf32 = w1.f32;
+                sxf = (float)u1.v; syf = (float)v1.v; szf = (float)w1.v;
+            }
 #ifdef PB_UNROLL_STAGES
 #pragma unroll
 #else
@@ -332,13 +339,33 @@ __global__ void __launch_bounds__(PB_BLOCK_THREADS, PB_MINBLOCKS) advect_kernel(
                 }
                 if (nstage == 4) {
                     const double m = (k == 3) ? 1.0 : 2.0;  // u1 + 2*u2 + 2*u3 + u4
-                    su = su + m * uk.v; sv = sv + m * vk.v; sw = sw + m * wk.v;
+                    if constexpr (Policy::F32_STAGES) {
+                        const float mf = (float)m;
+                        if (xf32 && uk.f32) sxf = sxf + mf * (float)uk.v; else { if (xf32) su = (double)sxf; xf32 = false; }
+                        if (yf32 && vk.f32) syf = syf + mf * (float)vk.v; else { if (yf32) sv = (double)syf; yf32 = false; }
+                        if (zf32 && wk.f32) szf = szf + mf * (float)wk.v; else { if (zf32) sw = (double)szf; zf32 = false; }
+                        // a float64 term: the float32 partial sum is promoted (exactly) and the addition is float64 from here on;
+                        // a float32 term joining a float64 sum is promoted likewise (2 * float32 is exact in both)
+                        if (!xf32) su = su + m * uk.v;
+                        if (!yf32) sv = sv + m * vk.v;
+                        if (!zf32) sw = sw + m * wk.v;
+                    } else {
+                        su = su + m * uk.v; sv = sv + m * vk.v; sw = sw + m * wk.v;
+                    }
                 }
             }
             }
             double ddx, ddy, ddz;
             if (nstage == 4) {
-                ddx = su / 6.0 * dtp; ddy = sv / 6.0 * dtp; ddz = sw / 6.0 * dtp;
+                if constexpr (Policy::F32_STAGES) {
+                    // every stage value may be float32 (nearest-node sampling of float32 data at tau == 0 carries the DATA
+                    // dtype whatever the position dtype): `(u1 + 2*u2 + 2*u3 + u4) / 6.0` is then float32 arithmetic
+                    ddx = (xf32 ? (double)(sxf / 6.0f) : su / 6.0) * dtp;
+                    ddy = (yf32 ? (double)(syf / 6.0f) : sv / 6.0) * dtp;
+                    ddz = (zf32 ? (double)(szf / 6.0f) : sw / 6.0) * dtp;
+                } else {
+                    ddx = su / 6.0 * dtp; ddy = sv / 6.0 * dtp; ddz = sw / 6.0 * dtp;
+                }
             } else {  // EE: u1*dt ; RK2: u2*dt
                 ddx = uk.v * dtp; ddy = vk.v * dtp; ddz = wk.v * dtp;
             }

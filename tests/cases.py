@@ -180,6 +180,11 @@ CASES = {
     "freeslip_surface": dict(seed=34, kind="smooth", interp="freeslip", land="depth", surface=True, cdtype="f8", ddtype="f4",
                              mesh="flat", nx=19, ny=16, nz=5, nt=3, tstep=400.0, n=300, kernels=["AdvectionRK4"], dt=60.0,
                              segments=[dict(runtime=720.0)], delete=True, margin=0.02, umax=4.0),
+    # nearest node on float32 data without a time dimension: every RK stage value is float32, so the reference's
+    # (u1 + 2*u2 + 2*u3 + u4) / 6 is float32 arithmetic (found by scripts/fuzz_hostsim.py)
+    "nearest_f32_static": dict(seed=35, kind="smooth", interp="nearest", cdtype="f4", ddtype="f4", mesh="flat", nx=9, ny=14, nz=3,
+                               nt=1, tstep=1000.0, n=120, kernels=["AdvectionRK4_3D"], dt=600.0, segments=[dict(runtime=6000.0)],
+                               delete=True, margin=0.1, umax=3.0),
     "nearest_3d": dict(seed=33, kind="smooth", interp="nearest", cdtype="f8", ddtype="f4", mesh="spherical", nx=21, ny=17, nz=5,
                        nt=3, tstep=3600.0, n=300, kernels=["AdvectionRK4_3D"], dt=600.0, segments=[dict(runtime=7200.0)],
                        delete=True, margin=0.02, umax=10.0),

@@ -27,7 +27,7 @@ pytestmark = pytest.mark.gpu
 ERR_NAME = {60: "FieldOutOfBoundError", 61: "FieldOutOfBoundSurfaceError", 70: "OutsideTimeInterval",
             51: "FieldInterpolationError", 52: "GridSearchingError", 50: "GeneralError"}  # fmt: skip
 FLAT_EXACT = {"flat_f32c_f64d", "c1_peninsula", "delayed_partial", "raise_oob", "raise_time", "rk2_3d", "through_surface",
-              "cgrid_rect_3d", "freeslip_3d", "freeslip_surface"}
+              "cgrid_rect_3d", "freeslip_3d", "freeslip_surface", "nearest_f32_static"}
 # Curvilinear search: the reference's closed-form bilinear inverse amplifies last-ulp differences (np.dot's
 # BLAS summation order, libm vs libdevice trig) by the cell's condition number, and spatial-hash hits are
 # rounded to float32 (spatialhash.py:511) -- a flipped rounding moves a weight by 6e-8.  Stated tolerance:

@@ -49,3 +49,15 @@ def test_simulation_is_inert_without_the_test_switch():
     env = {k: v for k, v in os.environ.items() if k != "PB_HOSTSIM_TEST"}
     out = subprocess.run([sys.executable, "-c", code, lib], env=env, capture_output=True, text=True, timeout=120).stdout.split()
     assert out[0] == "0" and int(out[1]) < 0, out
+
+
+def test_differential_fuzz_of_the_kernel_sources_against_the_oracle():
+    """120 random rectilinear configurations (dtypes, meshes, 2-D / 3-D, schemes, interpolators, release patterns, time direction,
+    error handling; scripts/fuzz_hostsim.py): the host-compiled kernels and the oracle must agree on every one."""
+    from oracle.hostsim import build as hb
+
+    lib = hb.build()
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "fuzz_hostsim.py"), "120", "2026"], cwd=ROOT, env=_env(lib),
+                         capture_output=True, text=True, timeout=900)  # fmt: skip
+    assert res.returncode == 0, res.stderr[-2000:]
+    assert res.stdout.strip().endswith("120 cases, 0 with differences"), res.stdout[-3000:]
