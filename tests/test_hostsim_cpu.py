@@ -61,3 +61,15 @@ def test_differential_fuzz_of_the_kernel_sources_against_the_oracle():
                          capture_output=True, text=True, timeout=900)  # fmt: skip
     assert res.returncode == 0, res.stderr[-2000:]
     assert res.stdout.strip().endswith("120 cases, 0 with differences"), res.stdout[-3000:]
+
+
+def test_differential_fuzz_of_sampling_rk45_and_advection_diffusion():
+    """60 random cases of scalar Field.eval (four interpolators), AdvectionRK45 and AdvectionDiffusionM1 / EM
+    (scripts/fuzz_hostsim_more.py): host-compiled kernels == oracle."""
+    from oracle.hostsim import build as hb
+
+    lib = hb.build()
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "fuzz_hostsim_more.py"), "60", "2026"], cwd=ROOT, env=_env(lib),
+                         capture_output=True, text=True, timeout=900)  # fmt: skip
+    assert res.returncode == 0, res.stderr[-2000:]
+    assert res.stdout.strip().endswith("60 cases, 0 with differences"), res.stdout[-3000:]
