@@ -632,6 +632,10 @@ class ParticleSet:
         total = None
         first = True
         while True:
+            if not first and plan.diffusion:
+                # the Wiener increments are keyed by (particle, iteration OF THE LAUNCH, call): a resumed launch restarts its
+                # iteration count, so it gets its own call index -- otherwise the same increments would be drawn again
+                self._rng_call += 1
             a = args()
             a.resume = 0 if first else 1
             eng.advect_async(a)

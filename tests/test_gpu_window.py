@@ -57,3 +57,21 @@ def test_window_too_small_for_dt_is_an_error():
     f = _field()
     with pytest.raises(RuntimeError, match="widen time_window"):
         _run(f, 2, 5400.0, [dict(runtime=3 * 5400.0)], lambda n, r: np.zeros(n))  # one step spans 1.5 level intervals
+
+
+def test_windowed_diffusion_draws_fresh_increments_after_every_window_slide():
+    """Fused DiffusionUniformKh on a time-windowed field: a launch resumed after a window slide restarts its iteration count,
+    so it must not draw the Wiener increments of the previous launch again (Var = 2 K t; repeating the increments of each
+    1-hour window over 4 windows would double the standard deviation)."""
+    nt, n, K = 5, 4000, 100.0
+    lon, lat = np.linspace(-1e5, 1e5, 9), np.linspace(-1e5, 1e5, 7)
+    Z = np.zeros((nt, 1, 7, 9), dtype=np.float32)
+    fs = pb.FieldSet.from_arrays(lon=lon, lat=lat, time=np.arange(nt) * 3600.0, U=Z, V=Z, mesh="flat", time_window=2)
+    fs.add_constant_field("Kh_zonal", K, mesh="flat")
+    fs.add_constant_field("Kh_meridional", K, mesh="flat")
+    ps = pb.ParticleSet(fs, x=np.zeros(n), y=np.zeros(n), t=np.zeros(n), seed=5)
+    runtime = 4 * 3600.0
+    ps.execute([pb.AdvectionRK4, pb.DiffusionUniformKh, pb.DeleteParticle], dt=600.0, runtime=runtime)
+    assert len(ps) == n and np.all(ps.t == runtime)
+    sigma = np.sqrt(2 * K * runtime)
+    assert abs(np.std(ps.x) / sigma - 1) < 0.05 and abs(np.std(ps.y) / sigma - 1) < 0.05, (np.std(ps.x), np.std(ps.y), sigma)
