@@ -1,5 +1,6 @@
 """More differential fuzzing of the host-compiled kernel sources (oracle/hostsim) against the oracle: scalar Field.eval
-(XLinear / XNearest / CGrid_Tracer / XLinearInvdistLandTracer), AdvectionRK45, AdvectionDiffusionM1 / EM (same Philox normals).
+(XLinear / XNearest / CGrid_Tracer / XLinearInvdistLandTracer), AdvectionRK45, AdvectionDiffusionM1 / EM and fused
+DiffusionUniformKh (same Philox normals), time-slab streaming vs the resident field.
 Run:  PB_LIB=oracle/_build/hostsim/libparcels_b200_hostsim.so PB_HOSTSIM_TEST=1 python scripts/fuzz_hostsim_more.py [n] [seed]"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -158,12 +159,82 @@ def fuzz_advdiff(rng):
     return f"advdiff {kern} ktime={ktime} kd={np.dtype(kd).name}", spec, msg
 
 
+def fuzz_diffusion(rng):
+    """fused [advection, DiffusionUniformKh, DeleteParticle] over one or two execute() segments, same Philox normals"""
+    two_d = rng.random() < 0.5
+    spec, c = base_case(rng, two_d=two_d)
+    c["constants"] = {"Kh_zonal": float(rng.choice([10.0, 100.0])), "Kh_meridional": float(rng.choice([5.0, 50.0]))}
+    kern = str(rng.choice(["AdvectionRK4", "AdvectionEE", "AdvectionRK2"])) if two_d else str(rng.choice(["AdvectionRK4_3D", "AdvectionRK2_3D"]))
+    tmax = None if c["times"] is None else float(c["times"][-1])
+    dt = float(rng.choice([20.0, 100.0, 600.0])) * (1 if rng.random() < 0.8 else -1)
+    nseg = int(rng.choice([1, 2, 3]))
+    seg_rt = abs(dt) * int(rng.integers(1, 5))
+    if tmax is not None:
+        seg_rt = min(seg_rt, 0.9 * tmax / nseg)
+        c["t"] = np.full(len(c["x"]), 0.0 if dt > 0 else tmax)
+    seed = int(rng.integers(1, 10**6))
+    fs = make_fieldset(c)
+    ps = pb.ParticleSet(fs, x=c["x"], y=c["y"], z=c["z"], t=c["t"], seed=seed)
+    for _ in range(nseg):
+        ps.execute([getattr(pb, kern), pb.DiffusionUniformKh, pb.DeleteParticle], dt=dt, runtime=seg_rt)
+    ofs = oracle_fieldset(c)
+    pd = po.create_particle_data(c["x"], c["y"], c["z"], c["t"], ngrids=ofs.ngrids)
+    st = {"call": 0, "it": 0}
+
+    def normal(view):
+        zx, zy = wiener_normals(seed, st["call"], st["it"], view.particle_id)
+        st["it"] += 1
+        return zx, zy
+
+    for _ in range(nseg):
+        st["call"] += 1
+        st["it"] = 0
+        po.pset_execute(pd, ofs, [getattr(po, kern), po.DiffusionUniformKh(normal), po.DeleteOnError], dt, runtime=seg_rt)
+    msg = []
+    d = ps._data
+    if len(d["x"]) != len(pd["x"]):
+        return f"diffusion {kern} x{nseg}", spec, [f"survivors {len(d['x'])} vs {len(pd['x'])}"]
+    for key in ("particle_id", "state", "t", "ei"):
+        if not np.array_equal(d[key], pd[key]):
+            msg.append(key)
+    for key in "xyz":
+        start = np.asarray(c[key], dtype=np.float64)[pd["particle_id"]]
+        floor = max(float(np.abs(pd[key] - start).max()) if len(start) else 0.0, 0.01 * float(np.abs(np.asarray(c[key])).max()), 1e-30)
+        u = ulp_diff_f32(d[key], pd[key], floor=floor)
+        if u.size and u.max() > (1 if c["mesh"] == "flat" else 4):
+            msg.append(f"{key}: {u.max():.1f} ulp")
+    return f"diffusion {kern} x{nseg}", spec, msg
+
+
+def fuzz_window(rng):
+    """time-slab streaming == fully resident field, bit for bit (advection only)"""
+    spec, c = base_case(rng, two_d=False)
+    nt = int(rng.choice([4, 6]))
+    spec.update(nt=nt, tstep=600.0)
+    c = cases.build(spec)
+    tmax = float(c["times"][-1])
+    window = int(rng.choice([2, 3]))
+    sign = 1 if rng.random() < 0.7 else -1
+    dt = sign * float(rng.choice([100.0, 200.0, 300.0, 600.0]))  # divides the 600 s level spacing: aligned steps (window 2 needs that)
+    c["t"] = np.full(len(c["x"]), 0.0 if sign > 0 else tmax)
+    runtime = float(rng.choice([0.5, 0.8, 1.0])) * tmax
+    out = []
+    for w in (None, window):
+        fs = pb.FieldSet.from_arrays(lon=c["lon"], lat=c["lat"], depth=c["depth"], time=c["times"], U=c["U"], V=c["V"], W=c["W"],
+                                     mesh=c["mesh"], time_window=w)  # fmt: skip
+        ps = pb.ParticleSet(fs, x=c["x"], y=c["y"], z=c["z"], t=c["t"])
+        ps.execute([pb.AdvectionRK4_3D, pb.DeleteParticle], dt=dt, runtime=runtime)
+        out.append(ps._data)
+    msg = [k for k in ("particle_id", "state", "t", "ei", "x", "y", "z") if not np.array_equal(out[0][k], out[1][k])]
+    return f"window {window} dt={dt}", spec, msg
+
+
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 60
     rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
     bad = 0
     for k in range(n):
-        f = (fuzz_scalar, fuzz_rk45, fuzz_advdiff)[k % 3]
+        f = (fuzz_scalar, fuzz_rk45, fuzz_advdiff, fuzz_diffusion, fuzz_window)[k % 5]
         try:
             what, spec, msg = f(rng)
         except Exception as e:  # noqa: BLE001

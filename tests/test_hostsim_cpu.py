@@ -64,7 +64,8 @@ def test_differential_fuzz_of_the_kernel_sources_against_the_oracle():
 
 
 def test_differential_fuzz_of_sampling_rk45_and_advection_diffusion():
-    """60 random cases of scalar Field.eval (four interpolators), AdvectionRK45 and AdvectionDiffusionM1 / EM
+    """60 random cases of scalar Field.eval (four interpolators), AdvectionRK45, AdvectionDiffusionM1 / EM, fused
+    DiffusionUniformKh over several execute() calls, and time-slab streaming vs the resident field
     (scripts/fuzz_hostsim_more.py): host-compiled kernels == oracle."""
     from oracle.hostsim import build as hb
 
