@@ -229,12 +229,111 @@ def fuzz_window(rng):
     return f"window {window} dt={dt}", spec, msg
 
 
+def fuzz_output(rng):
+    """rows handed to the output file at every output time (device selection + compaction across resident intervals, deletions
+    in HBM) == the rows the oracle's outer loop selects"""
+    three = rng.random() < 0.5
+    spec, c = base_case(rng, two_d=not three)
+    kern = "AdvectionRK4_3D" if three else "AdvectionRK4"
+    tmax = None if c["times"] is None else float(c["times"][-1])
+    dt = float(rng.choice([50.0, 100.0, 300.0])) * (1 if rng.random() < 0.8 else -1)
+    nsteps = int(rng.integers(2, 14))
+    runtime = abs(dt) * nsteps
+    outputdt = abs(dt) * float(rng.choice([1, 2, 3, 2.5]))
+    n = len(c["x"])
+    if tmax is not None:
+        runtime = min(runtime, 0.9 * tmax)
+        lo = 0.0 if dt > 0 else tmax
+        c["t"] = lo + np.sign(dt) * np.round(rng.uniform(0, 0.3 * runtime, n) / abs(dt)) * abs(dt) * (rng.random() < 0.5)
+    delete = rng.random() < 0.8
+    rows_e, rows_o = [], []
+
+    class Rec:
+        pass
+
+    rec = Rec()
+    rec.outputdt = outputdt
+    rec.write = lambda pset, t: rows_e.append((float(t), pset._output_columns(float(t), ["t", "z", "y", "x", "particle_id"])[0]))
+    fs = make_fieldset(c)
+    ps = pb.ParticleSet(fs, x=c["x"], y=c["y"], z=c["z"], t=c["t"])
+    err = oerr = ""
+    try:
+        ps.execute([getattr(pb, kern)] + ([pb.DeleteParticle] if delete else []), dt=dt, runtime=runtime, output_file=rec)
+    except RuntimeError as e:
+        if type(e).__module__.startswith("parcels_b200._lib"):
+            raise
+        err = type(e).__name__
+    pd = po.create_particle_data(c["x"], c["y"], c["z"], c["t"])
+
+    def on_output(pdata, t):
+        r = po.to_write_particles(pdata, t)
+        rows_o.append((float(t), {k: pdata[k][r].copy() for k in ("t", "z", "y", "x", "particle_id")}))
+
+    try:
+        po.pset_execute(pd, oracle_fieldset(c), [getattr(po, kern)] + ([po.DeleteOnError] if delete else []), dt, runtime=runtime,
+                        outputdt=outputdt, on_output=on_output)  # fmt: skip
+    except po.OracleParticleError as e:
+        oerr = str(e.code)
+    msg = []
+    if bool(err) != bool(oerr):
+        msg.append(f"error {err!r} vs {oerr!r}")
+    if len(rows_e) != len(rows_o):
+        msg.append(f"{len(rows_e)} writes vs {len(rows_o)}")
+    for (te, ce), (to, co) in zip(rows_e, rows_o):
+        if te != to or not np.array_equal(ce["particle_id"], co["particle_id"]) or not np.array_equal(ce["t"], co["t"]):
+            msg.append(f"rows at t={te}/{to}")
+            break
+        for key in "xyz":
+            floor = 0.01 * float(np.abs(np.asarray(c[key])).max()) or None
+            u = ulp_diff_f32(ce[key], co[key], floor=floor)
+            if u.size and u.max() > (0 if c["mesh"] == "flat" else 4):
+                msg.append(f"{key} at t={te}: {u.max():.1f} ulp")
+    return f"output every {outputdt} dt={dt} delete={delete}", spec, msg
+
+
+def fuzz_stepwise(rng):
+    """mixed list [built-in, user kernel, user error handler]: host loop control + device kernels == oracle"""
+    three = rng.random() < 0.5
+    spec, c = base_case(rng, two_d=not three)
+    kern = str(rng.choice(["AdvectionRK4_3D", "AdvectionRK2_3D"])) if three else str(rng.choice(["AdvectionRK4", "AdvectionEE"]))
+    tmax = None if c["times"] is None else float(c["times"][-1])
+    dt = float(rng.choice([50.0, 100.0, 300.0])) * (1 if rng.random() < 0.8 else -1)
+    runtime = abs(dt) * int(rng.integers(1, 8))
+    if tmax is not None:
+        runtime = min(runtime, 0.9 * tmax)
+        c["t"] = np.full(len(c["x"]), 0.0 if dt > 0 else tmax)
+    lo, hi = float(c["lon"][1]), float(c["lon"][-2])
+
+    def Periodic(particles, fieldset):
+        xn = particles.x + particles.dx
+        particles.dx += np.where(xn > hi, lo - hi, 0.0) + np.where(xn < lo, hi - lo, 0.0)
+
+    def DeleteErr(particles, fieldset):
+        particles[particles.state >= 50].state = 30
+
+    fs = make_fieldset(c)
+    ps = pb.ParticleSet(fs, x=c["x"], y=c["y"], z=c["z"], t=c["t"])
+    ps.execute([getattr(pb, kern), Periodic, DeleteErr], dt=dt, runtime=runtime)
+    pd = po.create_particle_data(c["x"], c["y"], c["z"], c["t"])
+    po.pset_execute(pd, oracle_fieldset(c), [getattr(po, kern), Periodic, po.DeleteOnError], dt, runtime=runtime)
+    d = ps._data
+    if len(d["x"]) != len(pd["x"]):
+        return f"stepwise {kern}", spec, [f"survivors {len(d['x'])} vs {len(pd['x'])}"]
+    msg = [k for k in ("particle_id", "state", "t", "ei") if not np.array_equal(d[k], pd[k])]
+    for key in "xyz":
+        floor = 0.01 * float(np.abs(np.asarray(c[key])).max()) or None
+        u = ulp_diff_f32(d[key], pd[key], floor=floor)
+        if u.size and u.max() > (0 if c["mesh"] == "flat" else 4):
+            msg.append(f"{key}: {u.max():.1f} ulp")
+    return f"stepwise {kern} dt={dt}", spec, msg
+
+
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 60
     rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
     bad = 0
     for k in range(n):
-        f = (fuzz_scalar, fuzz_rk45, fuzz_advdiff, fuzz_diffusion, fuzz_window)[k % 5]
+        f = (fuzz_scalar, fuzz_rk45, fuzz_advdiff, fuzz_diffusion, fuzz_window, fuzz_output, fuzz_stepwise)[k % 7]
         try:
             what, spec, msg = f(rng)
         except Exception as e:  # noqa: BLE001

@@ -64,13 +64,13 @@ def test_differential_fuzz_of_the_kernel_sources_against_the_oracle():
 
 
 def test_differential_fuzz_of_sampling_rk45_and_advection_diffusion():
-    """60 random cases of scalar Field.eval (four interpolators), AdvectionRK45, AdvectionDiffusionM1 / EM, fused
-    DiffusionUniformKh over several execute() calls, and time-slab streaming vs the resident field
-    (scripts/fuzz_hostsim_more.py): host-compiled kernels == oracle."""
+    """70 random cases of scalar Field.eval (four interpolators), AdvectionRK45, AdvectionDiffusionM1 / EM, fused
+    DiffusionUniformKh over several execute() calls, time-slab streaming vs the resident field, the rows handed to the output
+    file at every output time, and mixed lists with user kernels (scripts/fuzz_hostsim_more.py): host-compiled kernels == oracle."""
     from oracle.hostsim import build as hb
 
     lib = hb.build()
-    res = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "fuzz_hostsim_more.py"), "60", "2026"], cwd=ROOT, env=_env(lib),
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "fuzz_hostsim_more.py"), "70", "2026"], cwd=ROOT, env=_env(lib),
                          capture_output=True, text=True, timeout=900)  # fmt: skip
     assert res.returncode == 0, res.stderr[-2000:]
-    assert res.stdout.strip().endswith("60 cases, 0 with differences"), res.stdout[-3000:]
+    assert res.stdout.strip().endswith("70 cases, 0 with differences"), res.stdout[-3000:]
