@@ -302,7 +302,8 @@ int32_t pb_sample_velocity(pb_engine* e, int64_t n, const double* t, const doubl
  * a field with one time level has no time dimension (no time search, field.py:112-117).  method: the field's
  * ScalarInterpolator -- XLinear (_xinterpolators.py:112-153), XNearest (:515-560) or CGrid_Tracer (:335-383, uses
  * the staggering offsets of pb_set_interpolation).  Index search, `ei` write-back and state codes are those of
- * pb_sample_velocity; out-of-bounds samples are 0.  value_is_f32 (optional): 1 where NumPy's promotion makes the
+ * pb_sample_velocity; out-of-bounds samples are 0.  On curvilinear grids: CGrid_Tracer and XNearest (the cell comes from the
+ * curvilinear search, ei_hint = NULL sends the whole batch through the spatial hash like the reference's `if np.any(xi)`).  value_is_f32 (optional): 1 where NumPy's promotion makes the
  * reference's value float32 (the value returned is that float32 number, widened). */
 enum pb_scalar_interp {
     PB_SCALAR_XLINEAR = 0, PB_SCALAR_XNEAREST = 1, PB_SCALAR_CGRID_TRACER = 2,

@@ -376,6 +376,40 @@ def make_scalar_golden():
     np.savez_compressed(os.path.join(GOLDEN, "scalar_eval.npz"), **out)
 
 
+SCALAR_CURV_CASES = ("curv_sph_2d", "curv_flat_2d", "curv_sph_3d", "curv_sph_f32")
+
+
+def make_scalar_curv_golden():
+    """Field.eval on CURVILINEAR grids (CGrid_Tracer / XNearest): a fresh set (every hinted xi is 0: the whole batch goes through the
+    spatial hash) and a second, displaced evaluation hinted by the cells just found."""
+    import warnings
+
+    import cases as tc
+    from oracle import ref_harness as rh
+
+    out = {}
+    for name in SCALAR_CURV_CASES:
+        c = tc.build(tc.CASES[name])
+        for T in (c["U"].shape[0], 1):
+            P, tq = scalar_inputs(c, T)
+            for how in ("nearest", "cgrid_tracer"):
+                fs = rh.build_fieldset(lon=c["lon"], lat=c["lat"], depth=c["depth"], times=c["times"], U=c["U"], V=c["V"], W=c["W"],
+                                       mesh=c["mesh"], padding=c.get("padding", ("low", "low", "high")), interp="cgrid_velocity",
+                                       scalars={"P": (P, how)})  # fmt: skip
+                ps = rh.make_pset(fs, x=c["x"], y=c["y"], z=c["z"], t=c["t"])
+                with warnings.catch_warnings():
+                    warnings.simplefilter("ignore")
+                    val = fs.P.eval(tq, ps._data["z"], ps._data["y"], ps._data["x"], ps)
+                    ei1 = ps._data["ei"].copy()
+                    x2 = np.asarray(ps._data["x"], dtype=np.float64) + 0.3 * float(np.abs(np.diff(np.asarray(c["lon"], dtype=np.float64), axis=1)).mean())
+                    val2 = fs.P.eval(tq, ps._data["z"], np.asarray(ps._data["y"], dtype=np.float64), x2, ps)
+                key = f"{name}/T{T}/{how}"
+                out[f"{key}/value"], out[f"{key}/ei"] = val, ei1
+                out[f"{key}/value2"], out[f"{key}/ei2"], out[f"{key}/state2"] = val2, ps._data["ei"].copy(), ps._data["state"].copy()
+        print(f"scalar curv {name}: done")
+    np.savez_compressed(os.path.join(GOLDEN, "scalar_eval_curv.npz"), **out)
+
+
 # name -> (RK45_tol in metres, RK45_min_dt, RK45_max_dt factor of |dt|, runtime, dt)
 RK45_CASES = {
     "flat_f32c_f64d": (1e-4, 0.5, 4, 140.0, 10.0),
@@ -497,5 +531,6 @@ if __name__ == "__main__":
     make_ref_cases()
     make_output_golden()
     make_scalar_golden()
+    make_scalar_curv_golden()
     make_rk45_golden()
     make_advdiff_golden()

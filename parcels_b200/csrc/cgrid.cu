@@ -702,6 +702,116 @@ struct CurvPolicy {
     }
 };
 
+// ------------------------------------------------------------------------------------------------
+// Scalar Field.eval on CURVILINEAR grids (reference _core/field.py:144-202): CGrid_Tracer (_xinterpolators.py:335-383, the
+// tracer point of the cell the curvilinear search finds -- NEMO temperature / salinity on an ORCA grid) and XNearest
+// (:515-560).  Neither does arithmetic on the barycentric coordinates, so the float32-typed coordinates of the reference's
+// hash path (DESIGN.md waiver 4) cannot show: values, cells and states are the reference's exactly.
+// The search below is CurvPolicy::eval_rt's (time, depth, hint -> neighbours -> spatial hash), restated for one sample so
+// that the advection kernel's code stays exactly what the profiles measured.
+// ------------------------------------------------------------------------------------------------
+template <class A, class D, bool SPH>
+__global__ void sample_scalar_curv_kernel(const SampleParams s, int mode /* 4: XNearest, 5: CGrid_Tracer */, int has_time) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= s.n) return;
+    const GridDev& g = s.g;
+    const FieldDev& f = s.f;
+    AdvectParams p{};
+    p.g = g;
+    CGridCtx<A, D> e;
+    CGridPolicy<A, D, 2>::init(e, p, s.ei_hint ? s.ei_hint[i] : 0);
+    e.uyi = e.uxi = INT_MIN;
+    int state = PB_EVALUATE;
+    const bool f32 = s.pos_f32 != 0;
+    const double t = s.t[i];
+    const double z = f32 ? (double)(float)s.z[i] : s.z[i], y = f32 ? (double)(float)s.y[i] : s.y[i], x = f32 ? (double)(float)s.x[i] : s.x[i];
+    double value = 0.0;
+    bool value_f32 = std::is_same<D, float>::value;
+    int ei = e.ei;
+    do {
+        // -- time (index_search.py:65-91); a field without a time dimension is not searched (field.py:112-117)
+        double tau = 0.0;
+        int ti = 0;
+        if (has_time) {
+            if (!(0 <= t && t <= g.time_len)) { state = PB_ERROR_OUTSIDE_TIME_INTERVAL; break; }
+            tau = axis_search<double, double>(g.time, g.nt, t, e.ct);
+            ti = e.ct.idx;
+        }
+        // -- depth
+        double zeta = 0.0;
+        int zi = 0;
+        if (g.nz > 0) {
+            zeta = f32 ? (double)axis_search<float, A>((const A*)g.depth, g.nz, (float)z, e.cz) : (double)axis_search<double, A>((const A*)g.depth, g.nz, z, e.cz);
+            zi = e.cz.idx;
+        }
+        // -- _search_indices_curvilinear_2d (index_search.py:242-295)
+        Query q;
+        q.x = x; q.y = y;
+        if (SPH) {
+            const double la = deg2rad_np(y), lo = deg2rad_np(x);
+            const double cl = cos_ool(la);
+            q.qu_x = cos_ool(lo) * cl; q.qu_y = sin_ool(lo) * cl; q.qu_z = sin_ool(la);
+        }
+        double xsi = -1.0, eta = -1.0;
+        int yi, xi;
+        const bool no_hint = s.no_hint || !s.ei_hint;
+        const bool hint_ok = !no_hint && e.yi >= 0 && e.xi >= 0 && e.yi < g.ny - 1 && e.xi < g.nx - 1;
+        bool found = false;
+        if (hint_ok) found = point_in_cell(g, e, e.yi, e.xi, q, xsi, eta);
+        if (found) {
+            yi = e.yi; xi = e.xi;
+        } else {
+            unsigned int qx, qy, qz;
+            if (f32) hash_coords<A, float, float>(g, (float)y, (float)x, qx, qy, qz);
+            else hash_coords<A, double, double>(g, y, x, qx, qy, qz);
+            hash_query(g, e, q, f32 ? isfinite((float)x) && isfinite((float)y) : isfinite(x) && isfinite(y), qx, qy, qz, yi, xi, xsi, eta);
+        }
+        long long r = (long long)yi * g.xdim + (long long)xi;
+        if (g.nz > 0) r += (long long)zi * (g.ydim * g.xdim);
+        ei = (int)r;
+        if (zi == -1) state = max(state, (int)PB_ERROR_OUT_OF_BOUNDS);
+        if (xi == -3 || yi == -3) state = max(state, (int)PB_ERROR_GRID_SEARCHING);
+        if (zi == -2) state = max(state, (int)PB_ERROR_THROUGH_SURFACE);
+        if (xi < 0 || yi < 0 || zi < 0) break;  // masked to 0 (field.py:189)
+        // -- the node: CGrid_Tracer = index + SGRID offset, XNearest = the near side of each axis; both clipped like the gathers
+        int kz, ky, kx;
+        if (mode == 5) {
+            kz = zi + g.off_z; ky = yi + g.off_y; kx = xi + g.off_x;
+        } else {
+            kz = zeta <= 0.5 ? zi : zi + 1; ky = eta <= 0.5 ? yi : yi + 1; kx = xsi <= 0.5 ? xi : xi + 1;
+        }
+        const long long oz = (long long)min(max(kz, 0), f.Z - 1) * f.sZ, oy = (long long)min(max(ky, 0), f.Y - 1) * f.sY,
+                        ox = (long long)min(max(kx, 0), f.X - 1) * f.sX;
+        const D* __restrict__ P = (const D*)f.p[0];
+        const D c0 = ldg(P + (long long)min(max(ti, 0), f.T - 1) * f.sT + oz + oy + ox);
+        if (tau > 0) {  // lenT == 2 (per sample, DESIGN.md waiver 1): linear in time in promote(D, float64)
+            const D c1 = ldg(P + up_idx(ti, f.T) * f.sT + oz + oy + ox);
+            value = (double)c0 * (1 - tau) + (double)c1 * tau;
+            value_f32 = false;
+        } else {
+            value = (double)c0;
+        }
+        if (value != value) state = max(state, (int)PB_ERROR_INTERPOLATION);
+    } while (false);
+    s.u[i] = value;
+    if (s.f32_out) s.f32_out[i] = value_f32 ? 1 : 0;
+    s.ei_out[i] = ei;
+    s.state_out[i] = state;
+}
+
+template <class A, class D>
+static cudaError_t scalar_curv_ad(const SampleParams& p, int mode, bool has_time, cudaStream_t s) {
+    const unsigned grid = (unsigned)((p.n + 127) / 128);
+    if (p.g.spherical) sample_scalar_curv_kernel<A, D, true><<<grid, 128, 0, s>>>(p, mode, has_time ? 1 : 0);
+    else sample_scalar_curv_kernel<A, D, false><<<grid, 128, 0, s>>>(p, mode, has_time ? 1 : 0);
+    return cudaGetLastError();
+}
+// mode: 4 XNearest, 5 CGrid_Tracer (the numbering of agrid.cuh)
+cudaError_t launch_sample_scalar_curv(const SampleParams& p, int mode, bool coord_f64, bool data_f64, bool has_time, cudaStream_t s) {
+    if (coord_f64) return data_f64 ? scalar_curv_ad<double, double>(p, mode, has_time, s) : scalar_curv_ad<double, float>(p, mode, has_time, s);
+    return data_f64 ? scalar_curv_ad<float, double>(p, mode, has_time, s) : scalar_curv_ad<float, float>(p, mode, has_time, s);
+}
+
 template <class Policy>
 static cudaError_t launch_policy(const AdvectParams& p, cudaStream_t s) {
     const int block = 128;

@@ -531,6 +531,8 @@ cudaError_t launch_advdiff(const AdvectParams& p, const FieldDev& fkz, const Fie
                            bool coord_f64, bool uv_f64, bool kh_f64, bool uv_time, bool kh_time, cudaStream_t s);
 // scalar Field.eval on a rectilinear grid, f.p[0] = the field: mode 3 XLinear, 4 XNearest, 5 CGrid_Tracer  (aslip.cu)
 cudaError_t launch_sample_scalar(const SampleParams& p, int mode, bool coord_f64, bool data_f64, bool has_time, cudaStream_t s);
+// scalar Field.eval on a curvilinear grid: mode 4 XNearest, 5 CGrid_Tracer  (cgrid.cu)
+cudaError_t launch_sample_scalar_curv(const SampleParams& p, int mode, bool coord_f64, bool data_f64, bool has_time, cudaStream_t s);
 cudaError_t launch_sample_agrid_alt(const SampleParams& p, int mode, bool coord_f64, bool data_f64, bool has_time, int nc, cudaStream_t s);
 cudaError_t launch_precompute_cells(const void* lon, const void* lat, int ny, int nx, bool coord_f64, double* out, cudaStream_t s);
 cudaError_t launch_sample_agrid(const SampleParams& p, bool coord_f64, bool data_f64, bool has_time, int nc, cudaStream_t s);

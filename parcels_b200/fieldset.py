@@ -52,6 +52,12 @@ def _is_device_array(a) -> bool:
         return False
 
 
+def _batch_skips_hint(grid, hint) -> bool:
+    """Curvilinear grids: the reference tests the hinted cells only `if np.any(xi)` (_core/index_search.py:269) -- when the hinted
+    xi of EVERY sample is 0 (a fresh ParticleSet) the whole batch goes straight to the spatial hash."""
+    return bool(grid.curvilinear and hint is not None and not np.any((np.asarray(hint).astype(np.int64) % grid.xdim) != 0))
+
+
 class XGrid:
     """Structured grid (rectilinear: 1-D lon/lat; depth optional).  ``xdim/ydim/zdim`` are cell
     counts as in the reference (``_core/xgrid.py:21-24,208-231``); they default to nodes - 1,
@@ -137,6 +143,8 @@ class Field:
         if positions_are_f32 is None:
             positions_are_f32 = all(a.dtype == np.float32 for a in (z, y, x))
         hint = None if particles is None else np.ascontiguousarray(np.asarray(particles.ei)[:, -1])
+        if _batch_skips_hint(fs.grid, hint):
+            hint = None
         val, ei, st = fs.engine(device).sample_scalar(self._slot, self.interp_method, t, z, y, x,
                                                       positions_are_f32=positions_are_f32, ei_hint=hint)  # fmt: skip
         if particles is not None:
@@ -176,8 +184,8 @@ class VectorField:
         hint = None
         if particles is not None:
             hint = np.ascontiguousarray(np.asarray(particles.ei)[:, -1])
-        u, v, w, ei, st = fs.engine(device).sample_velocity(t, z, y, x, three_d=self.W is not None,
-                                                            positions_are_f32=positions_are_f32, ei_hint=hint)  # fmt: skip
+        u, v, w, ei, st = fs.engine(device).sample_velocity(t, z, y, x, three_d=self.W is not None, positions_are_f32=positions_are_f32,
+                                                            ei_hint=hint, no_hint=_batch_skips_hint(fs.grid, hint))  # fmt: skip
         if particles is not None:
             from .statuscodes import StatusCode
 
@@ -307,8 +315,8 @@ class FieldSet:
             raise ValueError(f"interp_method must be one of {sorted(Engine.SCALAR_METHODS)}. Got {interp_method!r}")
         if name in self.fields:
             raise ValueError(f"FieldSet already has a Field with name '{name}'")
-        if self.grid.curvilinear:
-            raise NotImplementedError("scalar fields are sampled on rectilinear grids")
+        if self.grid.curvilinear and interp_method not in ("nearest", "cgrid_tracer"):
+            raise NotImplementedError("on curvilinear grids scalar fields are sampled with 'cgrid_tracer' (CGrid_Tracer) or 'nearest' (XNearest)")
         data = np.ascontiguousarray(data)
         if data.ndim != 4:
             raise ValueError(f"{name} must be laid out (T, Z, Y, X); got shape {data.shape}")

@@ -99,3 +99,32 @@ def test_user_sampling_kernel_in_a_mixed_list():
     for k in ("particle_id", "state", "t", "ei", "x", "y", "z", "p"):
         np.testing.assert_array_equal(ps._data[k], pd[k], err_msg=k)
     assert np.abs(ps._data["p"]).max() > 0
+
+
+@pytest.mark.parametrize("name", ["curv_sph_2d", "curv_flat_2d", "curv_sph_3d", "curv_sph_f32"])
+def test_scalar_eval_on_curvilinear_grids(name, golden_dir):
+    """CGrid_Tracer / XNearest on curvilinear C-grids (NEMO tracers on an ORCA grid): a fresh set -- the whole batch through the
+    spatial hash, like the reference -- and a displaced float64 evaluation hinted by the cells just found; values, cells and
+    states equal the oracle's and the reference's own (tests/golden/scalar_eval_curv.npz)."""
+    g = np.load(os.path.join(golden_dir, "scalar_eval_curv.npz"))
+    c = load_case(name)
+    ofs = oracle_fieldset(c)
+    for T in (c["U"].shape[0], 1):
+        P, tq = scalar_inputs(c, T)
+        for how in ("nearest", "cgrid_tracer"):
+            fs = make_fieldset(c)
+            fs.add_field("P", P, interp_method=how)
+            ps = pb.ParticleSet(fs, x=c["x"], y=c["y"], z=c["z"], t=c["t"])
+            v1 = fs.P.eval(tq, ps._data["z"], ps._data["y"], ps._data["x"], ps)
+            ei1 = ps._data["ei"].copy()
+            x2 = np.asarray(ps._data["x"], dtype=np.float64) + 0.3 * float(np.abs(np.diff(np.asarray(c["lon"], dtype=np.float64), axis=1)).mean())
+            v2 = fs.P.eval(tq, ps._data["z"], np.asarray(ps._data["y"], dtype=np.float64), x2, ps)
+            key = f"{name}/T{T}/{how}"
+            assert v1.dtype == g[f"{key}/value"].dtype and v2.dtype == g[f"{key}/value2"].dtype, key
+            np.testing.assert_array_equal(v1, g[f"{key}/value"], err_msg=key)
+            np.testing.assert_array_equal(ei1, g[f"{key}/ei"], err_msg=key)
+            np.testing.assert_array_equal(v2, g[f"{key}/value2"], err_msg=key + " second")
+            np.testing.assert_array_equal(ps._data["ei"], g[f"{key}/ei2"], err_msg=key + " second")
+            np.testing.assert_array_equal(ps._data["state"], g[f"{key}/state2"], err_msg=key + " second")
+    with pytest.raises(NotImplementedError, match="cgrid_tracer"):
+        make_fieldset(c).add_field("Q", P, interp_method="linear")
