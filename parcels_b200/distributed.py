@@ -128,6 +128,21 @@ class DecomposedFieldSet:
                                self.plan["right_global"])  # fmt: skip
 
 
+def _engine_memory_device(index: int):
+    """torch device of the buffers handed to the engine's pack / unpack kernels: the engine's GPU.  (Where torch sees no CUDA
+    device the engine can only be the host simulation of the test suite, oracle/hostsim, whose "device" memory is host memory.)"""
+    import torch
+
+    return torch.device(f"cuda:{index}") if torch.cuda.is_available() else torch.device("cpu")
+
+
+def _sync(device):
+    if device.type == "cuda":
+        import torch
+
+        torch.cuda.synchronize(device)
+
+
 def _exchange(eng, counts, dist, device):
     """One migration round: counts -> all_to_all -> records -> all_to_all -> unpack.  Returns #received.
 
@@ -150,7 +165,7 @@ def _exchange(eng, counts, dist, device):
         dist.all_to_all_single(recvbuf[: n_in * RECORD_BYTES], sendbuf[: n_out * RECORD_BYTES],
                                output_split_sizes=[int(c) * RECORD_BYTES for c in rc],
                                input_split_sizes=[int(c) * RECORD_BYTES for c in counts])  # fmt: skip
-        torch.cuda.synchronize(device)
+        _sync(device)
         eng.migrate_unpack(recvbuf.data_ptr(), n_in)
         return n_in
     sendbuf = torch.empty(max(n_out, 1) * RECORD_BYTES, dtype=torch.uint8, device=device)
@@ -163,7 +178,7 @@ def _exchange(eng, counts, dist, device):
     mine = b"".join(everyone[src][rank] for src in range(world))
     n_in = len(mine) // RECORD_BYTES
     recvbuf = torch.frombuffer(bytearray(mine) if mine else bytearray(RECORD_BYTES), dtype=torch.uint8).to(device)
-    torch.cuda.synchronize(device)
+    _sync(device)
     eng.migrate_unpack(recvbuf.data_ptr(), n_in)
     return n_in
 
@@ -183,7 +198,7 @@ def execute_decomposed(dfs: DecomposedFieldSet, pdata: dict, kernels, dt: float,
         raise NotImplementedError("domain-decomposed execution needs the DeleteParticle handler (errors cannot be replayed "
                                   "step-exactly across ranks)")  # fmt: skip
     eng = dfs.engine
-    device = torch.device(f"cuda:{dfs.device}")
+    device = _engine_memory_device(dfs.device)
     pdata["state"][:] = StatusCode.Evaluate
     pdata["dt"][:] = dt
     eng.upload_particles(pdata, np.ascontiguousarray(pdata["ei"][:, -1]))

@@ -17,7 +17,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 pytestmark = pytest.mark.skipif(shutil.which(os.environ.get("CXX", "g++")) is None, reason="no C++ compiler for the host simulation")
 
-# needs two CUDA devices / torch CUDA tensors for the exchange buffers: not simulated
+# the 2-rank domain-decomposed check runs separately below (fewer particles); the NCCL variant needs two real GPUs
 DESELECT = ["tests/test_gpu_decomposed.py"]
 
 
@@ -74,3 +74,16 @@ def test_differential_fuzz_of_sampling_rk45_and_advection_diffusion():
                          capture_output=True, text=True, timeout=900)  # fmt: skip
     assert res.returncode == 0, res.stderr[-2000:]
     assert res.stdout.strip().endswith("70 cases, 0 with differences"), res.stdout[-3000:]
+
+
+def test_domain_decomposed_migration_on_the_host_compiled_kernels():
+    """Mode D (X-slab decomposition, classify / pack / compact / unpack kernels, gloo all-to-all of the 48-byte records): 2 ranks,
+    each with its own simulated engine, reproduce the single-engine trajectories bit for bit (scripts/decomposed_check.py)."""
+    from oracle.hostsim import build as hb
+
+    lib = hb.build()
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29641", os.path.join(ROOT, "scripts", "decomposed_check.py"), "--same-gpu", "--particles", "3000"]  # fmt: skip
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT, env=_env(lib))
+    assert r.returncode == 0 and "PASS bit-exact" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+    assert " 0 migrations" not in r.stdout
