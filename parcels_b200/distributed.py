@@ -183,7 +183,8 @@ def _exchange(eng, counts, dist, device):
     return n_in
 
 
-def execute_decomposed(dfs: DecomposedFieldSet, pdata: dict, kernels, dt: float, endtime: float, dist, max_rounds=100000):
+def execute_decomposed(dfs: DecomposedFieldSet, pdata: dict, kernels, dt: float, endtime: float, dist, max_rounds=100000, seed=0,
+                       rng_call=1):
     """``Kernel.execute`` over a domain-decomposed field: ``pdata`` is ANY shard of the particle set (it is
     routed to the owners first).  Returns (local particle dict after the call, stats)."""
     import torch
@@ -192,8 +193,10 @@ def execute_decomposed(dfs: DecomposedFieldSet, pdata: dict, kernels, dt: float,
     from .statuscodes import StatusCode
 
     plan = KernelPlan(kernels, dfs.fs)
-    if plan.diffusion:
-        raise NotImplementedError("DiffusionUniformKh is not supported with domain decomposition yet")
+    # fused DiffusionUniformKh: the Wiener increments are keyed by (seed; particle id, iteration of the launch, call index).  Every
+    # migration round is a new launch on every rank (the round count is global), so the round number joins the call index and no
+    # particle ever draws the same increment twice, wherever it migrates.  (The stream differs from a single-GPU run's, whose
+    # iterations are not cut into rounds: statistically equivalent, not bit-identical -- the advection-only path is.)
     if not plan.delete_on_error:
         raise NotImplementedError("domain-decomposed execution needs the DeleteParticle handler (errors cannot be replayed "
                                   "step-exactly across ranks)")  # fmt: skip
@@ -212,7 +215,9 @@ def execute_decomposed(dfs: DecomposedFieldSet, pdata: dict, kernels, dt: float,
             _exchange(eng, counts, dist, device)
         elif not first:
             break
-        rep = eng.advect(eng.make_args(plan.scheme, dt, endtime, delete_on_error=True, resume=not first))
+        rep = eng.advect(eng.make_args(plan.scheme, dt, endtime, delete_on_error=True, resume=not first, diffusion=plan.diffusion,
+                                       kh=plan.kh, kh_spherical=plan.kh_spherical, kh_deg2m=plan.kh_deg2m, seed=seed,
+                                       rng_call=(int(rng_call) << 20) + stats["rounds"]))  # fmt: skip
         first = False
         stats["rounds"] += 1
         stats["particle_steps"] += rep["particle_steps"]

@@ -22,6 +22,7 @@ ap.add_argument("--same-gpu", action="store_true")
 ap.add_argument("--particles", type=int, default=20000)
 ap.add_argument("--halo", type=int, default=3)
 ap.add_argument("--umax", type=float, default=40.0, help="velocity scale: large => many slab crossings")
+ap.add_argument("--diffusion", action="store_true", help="fused DiffusionUniformKh on a field at rest: statistical check (Var = 2 K t)")
 a = ap.parse_args()
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 dev = 0 if a.same_gpu else int(os.environ.get("LOCAL_RANK", rank))
@@ -36,6 +37,32 @@ n = a.particles
 rng = np.random.default_rng(7)
 x, y, z = rng.uniform(-175, 175, n), rng.uniform(-70, 70, n), rng.uniform(5, 5000, n)
 dt, runtime = 600.0, 86400.0
+if a.diffusion:
+    # a field at rest and a large constant diffusivity: particles released on the slab boundary (lon 0, equator) diffuse across it
+    K, runtime = 1.0e5, 28800.0
+    for k in "UVW":
+        f[k] *= np.float32(0)
+    x, y, z = np.zeros(n), np.zeros(n), np.full(n, 100.0)
+    full = create_particle_data(nparticles=n, ngrids=2, initial=dict(x=x, y=y, z=z, t=np.zeros(n), particle_id=np.arange(n)))
+    dfs = D.DecomposedFieldSet(lon=f["lon"], lat=f["lat"], depth=f["depth"], time=f["times"], U=f["U"], V=f["V"], W=f["W"],
+                               mesh="spherical", rank=rank, world=world, halo_cells=a.halo, device=dev)
+    dfs.fs.add_constant_field("Kh_zonal", K, mesh="spherical")
+    dfs.fs.add_constant_field("Kh_meridional", K, mesh="spherical")
+    out, stats = D.execute_decomposed(dfs, D.shard_particles(full, rank, world), [pb.AdvectionRK4_3D, pb.DiffusionUniformKh, pb.DeleteParticle],
+                                      dt, runtime, dist, seed=11)
+    tot = D.allreduce_sum(stats["migrated"], dist, device="cpu" if a.same_gpu else f"cuda:{dev}")
+    merged = D.gather_particles(out, dist, dst=0)
+    ok = True
+    if rank == 0:
+        sigma = np.sqrt(2 * K * runtime) / dfs.fs.grid.deg2m  # degrees (cos(lat) ~ 1 at the equator)
+        sx, sy = float(np.std(merged["x"])), float(np.std(merged["y"]))
+        ok = (len(merged["x"]) == n and len(np.unique(merged["particle_id"])) == n and abs(sx / sigma - 1) < 0.06 and abs(sy / sigma - 1) < 0.06
+              and abs(float(np.mean(merged["x"]))) < 5 * sigma / np.sqrt(n) and tot > n / 4)  # fmt: skip
+        print(f"decomposed diffusion ({world} ranks): {len(merged['x'])} particles, {int(tot)} migrations, rounds={stats['rounds']}, "
+              f"std x {sx:.4f} y {sy:.4f} expected {sigma:.4f} -> {'PASS statistics' if ok else 'FAIL'}")
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if ok else 1)
 full = create_particle_data(nparticles=n, ngrids=1, initial=dict(x=x, y=y, z=z, t=np.zeros(n), particle_id=np.arange(n)))
 dfs = D.DecomposedFieldSet(lon=f["lon"], lat=f["lat"], depth=f["depth"], time=f["times"], U=f["U"], V=f["V"], W=f["W"],
                            mesh="spherical", rank=rank, world=world, halo_cells=a.halo, device=dev)

@@ -87,3 +87,15 @@ def test_domain_decomposed_migration_on_the_host_compiled_kernels():
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT, env=_env(lib))
     assert r.returncode == 0 and "PASS bit-exact" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
     assert " 0 migrations" not in r.stdout
+
+
+def test_domain_decomposed_diffusion_statistics_on_the_host_compiled_kernels():
+    """Fused DiffusionUniformKh under mode D: every migration round is a new launch with its own RNG call index, so particles that
+    hop between the ranks keep drawing fresh Wiener increments (Var = 2 K t, every particle accounted for once)."""
+    from oracle.hostsim import build as hb
+
+    lib = hb.build()
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29642", os.path.join(ROOT, "scripts", "decomposed_check.py"), "--same-gpu", "--particles", "3000", "--diffusion"]  # fmt: skip
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT, env=_env(lib))
+    assert r.returncode == 0 and "PASS statistics" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
