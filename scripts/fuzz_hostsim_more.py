@@ -15,9 +15,10 @@ from oracle_run import oracle_fieldset
 from philox_ref import wiener_normals
 
 warnings.simplefilter("ignore")
+ALL_INTERPS = ("linear", "linear", "freeslip", "partialslip", "nearest", "cgrid_velocity")
 
 
-def base_case(rng, two_d):
+def base_case(rng, two_d, interps=("linear",)):
     mesh = str(rng.choice(["flat", "spherical"]))
     nt = int(rng.choice([1, 2, 4]))
     spec = dict(seed=int(rng.integers(1, 10**6)), kind="smooth", cdtype=str(rng.choice(["f4", "f8"])), ddtype=str(rng.choice(["f4", "f8"])),
@@ -25,6 +26,13 @@ def base_case(rng, two_d):
                 tstep=float(rng.choice([500.0, 3600.0])), n=int(rng.integers(1, 120)), kernels=["AdvectionRK4" if two_d else "AdvectionRK4_3D"],
                 dt=100.0, segments=[dict(runtime=100.0)], delete=True, margin=float(rng.choice([-0.03, 0.05, 0.2])),
                 umax=float(rng.choice([0.5, 3.0])))  # fmt: skip
+    how = str(rng.choice(list(interps)))
+    if how == "nearest" and two_d:
+        how = "linear"
+    if how != "linear":
+        spec["interp"] = how
+    if how in ("freeslip", "partialslip"):
+        spec["land"] = True
     c = cases.build(spec)
     if two_d:
         c["W"] = None
@@ -162,7 +170,7 @@ def fuzz_advdiff(rng):
 def fuzz_diffusion(rng):
     """fused [advection, DiffusionUniformKh, DeleteParticle] over one or two execute() segments, same Philox normals"""
     two_d = rng.random() < 0.5
-    spec, c = base_case(rng, two_d=two_d)
+    spec, c = base_case(rng, two_d=two_d, interps=ALL_INTERPS)
     c["constants"] = {"Kh_zonal": float(rng.choice([10.0, 100.0])), "Kh_meridional": float(rng.choice([5.0, 50.0]))}
     kern = str(rng.choice(["AdvectionRK4", "AdvectionEE", "AdvectionRK2"])) if two_d else str(rng.choice(["AdvectionRK4_3D", "AdvectionRK2_3D"]))
     tmax = None if c["times"] is None else float(c["times"][-1])
@@ -233,7 +241,7 @@ def fuzz_output(rng):
     """rows handed to the output file at every output time (device selection + compaction across resident intervals, deletions
     in HBM) == the rows the oracle's outer loop selects"""
     three = rng.random() < 0.5
-    spec, c = base_case(rng, two_d=not three)
+    spec, c = base_case(rng, two_d=not three, interps=ALL_INTERPS)
     kern = "AdvectionRK4_3D" if three else "AdvectionRK4"
     tmax = None if c["times"] is None else float(c["times"][-1])
     dt = float(rng.choice([50.0, 100.0, 300.0])) * (1 if rng.random() < 0.8 else -1)
@@ -294,7 +302,7 @@ def fuzz_output(rng):
 def fuzz_stepwise(rng):
     """mixed list [built-in, user kernel, user error handler]: host loop control + device kernels == oracle"""
     three = rng.random() < 0.5
-    spec, c = base_case(rng, two_d=not three)
+    spec, c = base_case(rng, two_d=not three, interps=ALL_INTERPS)
     kern = str(rng.choice(["AdvectionRK4_3D", "AdvectionRK2_3D"])) if three else str(rng.choice(["AdvectionRK4", "AdvectionEE"]))
     tmax = None if c["times"] is None else float(c["times"][-1])
     dt = float(rng.choice([50.0, 100.0, 300.0])) * (1 if rng.random() < 0.8 else -1)
