@@ -256,6 +256,10 @@ typedef struct pb_rk45_args {
     int64_t max_iters;          /* < 0: run to endtime */
     int32_t next_dt_is_f32;
     int32_t delete_on_error;
+    int32_t kernels_only;       /* 1: ONE loop iteration's kernel work only -- the RK45 attempts of every evaluated particle until
+                                   its step is accepted (kernel.py:206-216), dx / dy, dt, next_dt, state, ei written back, no position
+                                   update, no batch-level dt clamp of finished particles (mixed lists: the host finishes the iteration) */
+    int32_t resume;             /* 1: particle states are NOT reset to Evaluate */
 } pb_rk45_args;
 int32_t pb_advect_rk45(pb_engine* e, const pb_rk45_args* args, double* dt_inout, double* next_dt_inout, pb_report* rep);
 

@@ -49,6 +49,8 @@ class Rk45Args(C.Structure):
         ("max_iters", C.c_int64),
         ("next_dt_is_f32", C.c_int32),
         ("delete_on_error", C.c_int32),
+        ("kernels_only", C.c_int32),
+        ("resume", C.c_int32),
     ]
 
 

@@ -943,6 +943,7 @@ int32_t pb_advect_rk45(pb_engine* e, const pb_rk45_args* a, double* dt_inout, do
     p.P = cur_particles(e);
     p.scheme = PB_ADVECTION_RK45;
     p.delete_on_error = a->delete_on_error;
+    p.kernels_only = a->kernels_only; p.resume = a->resume;
     p.dt = a->dt; p.endtime = a->endtime; p.max_iters = a->max_iters;
     p.rep = e->d_rep;
     zero_report(*e->h_rep);
@@ -958,8 +959,10 @@ int32_t pb_advect_rk45(pb_engine* e, const pb_rk45_args* a, double* dt_inout, do
     e->pending = true;
     if ((rc = pb_last_report(e, rep))) return rc;
     if (n) {
-        cudaError_t ce = launch_rk45_finalize(p.P, d_dt, d_it, rep->max_iters_done, a->endtime, a->dt > 0 ? 1 : -1, e->stream);
-        if (ce != cudaSuccess) return fail(PB_ERR_CUDA, "rk45_finalize launch failed: %s", cudaGetErrorString(ce));
+        if (!a->kernels_only) {  // (in a mixed list the host clamps every particle's dt at the top of each iteration itself)
+            cudaError_t ce = launch_rk45_finalize(p.P, d_dt, d_it, rep->max_iters_done, a->endtime, a->dt > 0 ? 1 : -1, e->stream);
+            if (ce != cudaSuccess) return fail(PB_ERR_CUDA, "rk45_finalize launch failed: %s", cudaGetErrorString(ce));
+        }
         CK(cudaMemcpyAsync(dt_inout, d_dt, n * 8, cudaMemcpyDeviceToHost, e->stream));
         CK(cudaMemcpyAsync(next_dt_inout, d_ndt, n * 8, cudaMemcpyDeviceToHost, e->stream));
         CK(cudaStreamSynchronize(e->stream));

@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(PB_BLOCK_THREADS, PB_MINBLOCKS) rk45_kernel(co
         double dt = q.dt[i], ndt = q.next_dt[i];
         typename Policy::Ctx e;
         Policy::init(e, p, p.P.ei[i]);
-        e.state = PB_EVALUATE;  // kernel.py:188
+        e.state = p.resume ? p.P.state[i] : (int)PB_EVALUATE;  // kernel.py:188
         e.refills = 0;
         e.out_of_time = false;
         const int sign = p.dt > 0 ? 1 : -1;  // compute_time_direction (kernel.py:186)
@@ -110,6 +110,7 @@ __global__ void __launch_bounds__(PB_BLOCK_THREADS, PB_MINBLOCKS) rk45_kernel(co
                 // clamped dt is below min_dt still advances t by min_dt in the position update
                 if (fabs(dt) < fabs(q.min_dt)) dt = q.min_dt * sgn_dt;
             } while (e.state == PB_REPEAT);
+            if (p.kernels_only) { ++it; break; }  // mixed lists: the host finishes the iteration (stepwise.py)
             if (p.delete_on_error && e.state >= 50) e.state = PB_DELETE;  // never true after RK45 (see the header comment)
             if (e.state == PB_EVALUATE || e.state == PB_SUCCESS) {
                 x = x + dx; y = y + dy; z = z + dz;

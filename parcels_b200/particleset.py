@@ -108,6 +108,7 @@ class KernelPlan:
             names = ["_none"]
         self.rk45 = None
         self.advdiff = None
+        self._kernel_list, self._tokens = kernel_list, tokens
         if "AdvectionRK45" in tokens:
             self._setup_rk45(names, fieldset, pclass)
             return
@@ -168,8 +169,9 @@ def _setup_rk45(self, names, fieldset, pclass):
 
     from .statuscodes import KernelWarning
 
-    if names != ["AdvectionRK45"] or self.diffusion:
-        raise NotImplementedError("AdvectionRK45 runs fused on the device as [AdvectionRK45] or [AdvectionRK45, DeleteParticle]")
+    fused = names == ["AdvectionRK45"] and not self.diffusion
+    if self.diffusion or any(n in K.SCHEMES or n in K.ADVDIFF or n == "DiffusionUniformKh" for n in names if n):
+        raise NotImplementedError("AdvectionRK45 combines with user kernels and the DeleteParticle token, not with other built-in kernels")
     if pclass is None or "next_dt" not in [n for n, _ in pclass.variables]:
         raise ValueError('ParticleClass requires a "next_dt" for AdvectionRK45 Kernel.')
     if fieldset.grid.curvilinear or fieldset.interp_method != "linear" or fieldset.time_window is not None:
@@ -187,9 +189,25 @@ def _setup_rk45(self, names, fieldset, pclass):
         warnings.warn("Setting RK45 maximum timestep to 1 day. Use fieldset.add_context('RK45_max_dt', [timestep]) to change.", KernelWarning, stacklevel=4)
         fieldset.add_context("RK45_max_dt", 60 * 60 * 24)
     self.rk45 = (float(ctx["RK45_tol"]), float(ctx["RK45_min_dt"]), float(ctx["RK45_max_dt"]))
-    self.stepwise = False
-    self.scheme_name, self.scheme = "AdvectionRK45", K.RK45
     self.kh, self.kh_spherical, self.kh_deg2m = (0.0, 0.0), False, 1.0
+    if fused:  # [AdvectionRK45] or [AdvectionRK45, DeleteParticle]: the whole loop in one launch
+        self.stepwise = False
+        self.scheme_name, self.scheme = "AdvectionRK45", K.RK45
+        return
+    # mixed with user kernels (the reference's own tests/test_advection.py:354-387: [AdvectionRK45, UpdateP]): the host drives the
+    # loop, every iteration's RK45 attempts run on the device (pb_advect_rk45 with kernels_only)
+    self.stepwise = True
+    self.scheme_name, self.scheme = "stepwise", -1
+    self.delete_on_error = False
+    self.items = []
+    for f, n in zip(self._kernel_list, self._tokens, strict=True):
+        if n == "AdvectionRK45":
+            self.items.append(["rk45", self.rk45])
+        elif n == "DeleteParticle":
+            self.items.append(["python", _delete_on_error])
+        else:
+            self.items.append(["python", f])
+    self.rk45 = None  # (fused-path marker)
 
 
 KernelPlan._setup_rk45 = _setup_rk45

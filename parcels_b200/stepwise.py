@@ -24,6 +24,9 @@ def kernel_execute_stepwise(pset, plan, endtime: float, dt: float):
     sign = 1 if dt > 0 else -1
     d["state"][:] = StatusCode.Evaluate
     steps = 0
+    # RK45 mode (reference kernel.py:118-120,224-226: `hasattr(fieldset, "RK45_tol")`): dt <- next_dt after the position update,
+    # and dt is NOT reset to the nominal step at the end of the iteration
+    rk45_mode = "RK45_tol" in fs.context
     while len(d["x"]) > 0 and np.any(np.isin(d["state"], [StatusCode.Evaluate, StatusCode.Repeat])):
         tte = sign * (endtime - d["t"])
         evaluate = np.isin(d["state"], [StatusCode.Success, StatusCode.Evaluate]) & (tte >= 0)
@@ -35,6 +38,8 @@ def kernel_execute_stepwise(pset, plan, endtime: float, dt: float):
         for item in plan.items:
             if item[0] in ("device", "advdiff"):
                 _device_kernels(pset, eng, item, dt, endtime)
+            elif item[0] == "rk45":
+                _device_rk45(pset, eng, item[1], dt, endtime)
             else:
                 f = item[1]
                 f(ParticleSetView(d, evaluate, fs), fs)
@@ -52,7 +57,10 @@ def kernel_execute_stepwise(pset, plan, endtime: float, dt: float):
             d["dx"][upd] = 0
             d["dy"][upd] = 0
             d["dz"][upd] = 0
-        d["dt"][:] = dt
+            if rk45_mode:
+                d["dt"][upd] = d["next_dt"][upd]
+        if not rk45_mode:
+            d["dt"][:] = dt
         d["state"][(d["state"] == StatusCode.Evaluate) & (d["t"] == endtime)] = StatusCode.EndofLoop
         dele = np.where(d["state"] == StatusCode.Delete)[0]
         if len(dele) > 0:
@@ -101,3 +109,24 @@ def _device_kernels(pset, eng, item, dt, endtime):
             sign * (endtime - d["t"]) >= 0
         )
         d["state"][view] = StatusCode.ErrorOutsideTimeInterval
+
+
+def _device_rk45(pset, eng, params, dt, endtime):
+    """One iteration of AdvectionRK45 on the device (``pb_advect_rk45`` with kernels_only): every evaluated particle's attempts until
+    its step is accepted -- the reference's `while state == Repeat` re-runs of the kernel (kernel.py:212-216) -- with dx / dy,
+    dt, next_dt, state and ei written back; the host does the position update and `dt <- next_dt`."""
+    d = pset._data
+    ei_last = np.ascontiguousarray(d["ei"][:, -1])
+    eng.upload_particles(d, ei_last)
+    dt_arr = np.ascontiguousarray(d["dt"], dtype=np.float64)
+    ndt_arr = np.ascontiguousarray(d["next_dt"], dtype=np.float64)
+    tol, min_dt, max_dt = params
+    rep = eng.advect_rk45(dt, endtime, tol, min_dt, max_dt, dt_arr, ndt_arr, next_dt_is_f32=d["next_dt"].dtype == np.float32,
+                          kernels_only=True, resume=True)  # fmt: skip
+    eng.download_particles(d, ei_last)
+    d["ei"][:, -1] = ei_last
+    d["dt"][:] = dt_arr
+    d["next_dt"][:] = ndt_arr
+    if rep["n_error"] > 0:
+        stuck = np.where(d["state"] == StatusCode.Error)[0]
+        raise RuntimeError(f"AdvectionRK45: particles {stuck[:10]} have dt == 0 before endtime={endtime}; reset pset.dt before continuing")

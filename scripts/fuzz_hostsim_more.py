@@ -47,6 +47,8 @@ def fuzz_scalar(rng):
     P[rng.uniform(size=P.shape) < 0.15] = 0  # land
     how = str(rng.choice(["linear", "nearest", "cgrid_tracer", "linear_invdist_land"]))
     n = len(c["x"])
+    if n == 1 and how == "linear_invdist_land":
+        how = "linear"  # a batch of ONE sample: NumPy's sum over the corner axes becomes a contiguous pairwise sum (DESIGN.md waiver 1)
     tmax = 0.0 if c["times"] is None else float(c["times"][-1])
     tq = rng.uniform(0, tmax, n) if tmax else np.zeros(n)
     # (the land tracer SUMS over the gathered levels: a batch mixing on-level and off-level samples is waiver 1 of DESIGN.md)
@@ -97,12 +99,21 @@ def fuzz_rk45(rng):
         fs.add_context(k_, v_)
     pclass = pb.Particle.add_variable(pb.Variable("next_dt", dtype=np.float32, initial=0))
     ps = pb.ParticleSet(fs, pclass=pclass, x=c["x"], y=c["y"], z=c["z"], t=c["t"])
-    ps.execute(pb.AdvectionRK45, dt=dt, runtime=runtime)
+    mixed = rng.random() < 0.4  # [AdvectionRK45, user kernel]: host loop control, RK45 attempts on the device
+
+    def Drift(particles, fieldset):
+        particles.dy += 0.25 * particles.dt
+
+    ps.execute([pb.AdvectionRK45, Drift] if mixed else pb.AdvectionRK45, dt=dt, runtime=runtime)
     ofs = oracle_fieldset(c)
     ofs.context.update(RK45_tol=tol / ofs.grid.deg2m if ofs.grid.spherical else tol, RK45_min_dt=min_dt, RK45_max_dt=max_dt)
     pd = po.create_particle_data(c["x"], c["y"], c["z"], c["t"])
     pd["next_dt"] = np.zeros(len(pd["x"]), dtype=np.float32)
-    po.pset_execute(pd, ofs, [po.AdvectionRK45], dt, runtime=runtime)
+
+    def ODrift(p, fs_):
+        p.dy = p.dy + 0.25 * p.dt
+
+    po.pset_execute(pd, ofs, [po.AdvectionRK45, ODrift] if mixed else [po.AdvectionRK45], dt, runtime=runtime)
     msg = []
     d = ps._data
     for key in ("particle_id", "state", "t", "dt", "next_dt", "ei"):
@@ -113,7 +124,7 @@ def fuzz_rk45(rng):
         u = ulp_diff_f32(d[key], pd[key], floor=floor)
         if u.size and u.max() > (0 if c["mesh"] == "flat" else 4):
             msg.append(f"{key}: {u.max():.1f} ulp")
-    return f"rk45 tol={tol} dt={dt}", spec, msg
+    return f"rk45 tol={tol} dt={dt} mixed={mixed}", spec, msg
 
 
 def fuzz_advdiff(rng):

@@ -9,8 +9,10 @@ import numpy as np
 import pytest
 
 import parcels_b200 as pb
+from oracle import parcels_oracle as po
 from engine_run import make_fieldset, ulp_diff_f32
 from oracle.make_golden import RK45_CASES
+from oracle_run import load_case, oracle_fieldset
 from test_rk45_cpu import run_oracle_rk45
 
 pytestmark = pytest.mark.gpu
@@ -102,3 +104,47 @@ def test_rk45_reports_particles_the_reference_would_spin_on():
     with pytest.raises(RuntimeError, match="never terminates"):
         ps.execute(pb.AdvectionRK45, dt=dt, runtime=runtime, output_file=Out())
     assert np.any(ps._data["dt"] == 0)
+
+
+@pytest.mark.parametrize("name", ["flat_f32c_f64d", "c1_peninsula"])
+def test_rk45_in_a_mixed_list_matches_oracle(name):
+    """[AdvectionRK45, user kernel] -- the reference's own Stommel test is written like this (tests/test_advection.py:354-387,
+    `[kernel, UpdateP]`): the host drives the loop (dt clamp, position update, dt <- next_dt), every iteration's RK45 attempts run
+    on the device (pb_advect_rk45 with kernels_only), the user kernel samples a scalar field there too."""
+    tol, min_dt, fmax, runtime, dt = RK45_CASES[name]
+    c = dict(load_case(name), W=None)
+    z = np.abs(np.asarray(c["z"]))
+    P = (c["U"] * 2 + 1).astype(c["U"].dtype)
+    fs = make_fieldset(c)
+    fs.add_field("P", P)
+    for k_, v_ in (("RK45_tol", tol), ("RK45_min_dt", min_dt), ("RK45_max_dt", fmax * abs(dt))):
+        fs.add_context(k_, v_)
+    pclass = pb.Particle.add_variable([pb.Variable("next_dt", dtype=np.float32, initial=0), pb.Variable("p", dtype=np.float32, initial=0),
+                                       pb.Variable("nsteps", dtype=np.int32, initial=0)])  # fmt: skip
+    ps = pb.ParticleSet(fs, pclass=pclass, x=c["x"], y=c["y"], z=z, t=c["t"])
+
+    def UpdateP(particles, fieldset):
+        particles.p = fieldset.P[particles]
+        particles.nsteps += 1
+
+    def DeleteErr(particles, fieldset):  # particles the sampler finds outside the domain
+        particles[particles.state >= 50].state = 30
+
+    ps.execute([pb.AdvectionRK45, UpdateP, DeleteErr], dt=dt, runtime=runtime)
+
+    ofs = oracle_fieldset(c)
+    ofs.context.update(RK45_tol=tol, RK45_min_dt=min_dt, RK45_max_dt=fmax * abs(dt))  # flat meshes: no unit conversion
+    pd = po.create_particle_data(c["x"], c["y"], z, c["t"])
+    pd["next_dt"] = np.zeros(len(pd["x"]), dtype=np.float32)
+    pd["p"] = np.zeros(len(pd["x"]), dtype=np.float32)
+    pd["nsteps"] = np.zeros(len(pd["x"]), dtype=np.int32)
+
+    def OUpdateP(p, fs_):
+        p.p = po.eval_scalar(fs_, P, "linear", p.t, p.z, p.y, p.x, p)
+        p.nsteps = p.nsteps + 1
+
+    po.pset_execute(pd, ofs, [po.AdvectionRK45, OUpdateP, po.DeleteOnError], dt, runtime=runtime)
+    d = ps._data
+    assert len(d["x"]) == len(pd["x"]) > 0 and d["nsteps"].max() > 1
+    for k in ("particle_id", "state", "t", "dt", "next_dt", "ei", "x", "y", "z", "p", "nsteps"):
+        np.testing.assert_array_equal(d[k], pd[k], err_msg=k)
