@@ -68,7 +68,7 @@ __device__ __forceinline__ Val bilinear(const C (&c)[4], TY eta, TX xsi) {
 // Z-lerp (only when zeta > 0: `lenZ`, _xinterpolators.py:131,141-145) then bilinear
 template <class C, class TZ, class TY, class TX>
 __device__ __forceinline__ Val zlerp_bilinear(const C (&c)[8], TZ zeta, TY eta, TX xsi) {
-    if (zeta > 0) {
+    if (!(zeta <= 0)) {  // zeta > 0 or NaN
         using R = prom_t<C, TZ>;
         R r[4];
 #pragma unroll
@@ -100,7 +100,7 @@ __device__ __forceinline__ Val xlinear(const D (&v)[16], TT tau, TZ zeta, TY eta
 #pragma unroll
             for (int k = 0; k < 8; ++k) r[k] = (double)v[k];
         }
-        if (zeta > 0) {
+        if (!(zeta <= 0)) {  // zeta > 0, or NaN (a NaN depth must poison the value like the reference's batch-level lerp does)
             const double omz = 1 - zeta;
 #pragma unroll
             for (int k = 0; k < 4; ++k) r[k] = r[k] * omz + r[4 + k] * zeta;

@@ -428,6 +428,11 @@ struct CGridPolicy {
             int s = e.state;
             if (xi == -1 || yi == -1 || zi == -1) s = max(s, (int)PB_ERROR_OUT_OF_BOUNDS);
             if (zi == -2) s = max(s, (int)PB_ERROR_THROUGH_SURFACE);
+            // a horizontal index -2 (left of the axis) is not an error in the reference: it interpolates with the wrapped index
+            // and masks the value afterwards -- but its NaN test comes first (field.py:288-290), and a non-finite barycentric
+            // coordinate (a position that is -inf or NaN) makes that value NaN whatever the gathered faces are: ErrorInterpolation
+            // (with valid indices the NaN test below finds it; this covers the early return)
+            if (!isfinite((double)xsi) || !isfinite((double)eta) || (NC_ == 3 && !isfinite((double)zeta))) s = max(s, (int)PB_ERROR_INTERPOLATION);
             e.state = s;
             if (xi < 0 || yi < 0 || zi < 0) { u = Val{0.0, false}; v = u; w = u; return; }
             px[0] = e.cx.lo; px[1] = e.cx.hi; px[2] = e.cx.hi; px[3] = e.cx.lo;  // _xinterpolators.py:218-220

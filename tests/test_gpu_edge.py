@@ -100,3 +100,28 @@ def test_changing_dt_in_kernel_and_dt_reset():
     ps = pb.ParticleSet(fs, x=np.zeros(1) + 10, y=np.zeros(1) + 10)
     ps.execute([pb.AdvectionRK4, KernelCounter], dt=2.0, runtime=5.0)
     assert ps.x[0] == 13 and ps.dt[0] == 2 and ps.t[0] == 5 and len(calls) == 3
+
+
+@pytest.mark.parametrize("name", ["c2_small", "flat_f32c_f64d", "cgrid_rect_3d", "freeslip_3d", "nearest_3d", "rk4_2d_in_3d", "curv_sph_2d"])
+@pytest.mark.parametrize("delete", [True, False])
+def test_non_finite_positions_are_flagged_like_the_reference(name, delete):
+    """Particles released at NaN / +inf / -inf coordinates: the reference's searches put NaN last, +-inf outside, and the NaN test
+    on the interpolated value comes BEFORE the out-of-bounds masking (field.py:288-290) -- e.g. x = -inf gives index -2 (not an
+    error by itself) and a NaN value: ErrorInterpolation; a NaN depth poisons the Z-lerp.  Same states, times, cells, survivors and
+    raised error as the oracle (found with the host-compiled kernels, oracle/hostsim)."""
+    import cases
+    from engine_run import run_engine
+    from oracle_run import run_oracle
+
+    err_name = {60: "FieldOutOfBoundError", 61: "FieldOutOfBoundSurfaceError", 70: "OutsideTimeInterval", 51: "FieldInterpolationError",
+                52: "GridSearchingError", 50: "GeneralError"}  # fmt: skip
+    for seed in (0, 3, 5):
+        rng = np.random.default_rng(seed)
+        c = cases.build(dict(cases.CASES[name], delete=delete, n=60))
+        for k, val in zip("xyzxyz", (np.nan, np.inf, -np.inf, -np.inf, -np.inf, np.nan)):
+            c[k][rng.integers(0, 60)] = val
+        ps, err = run_engine(c)
+        pd, oerr = run_oracle(c)
+        assert err == (err_name[oerr] if oerr else ""), (seed, err, oerr)
+        for key in ("particle_id", "state", "t", "ei"):
+            np.testing.assert_array_equal(ps._data[key], pd[key], err_msg=f"{name} seed {seed}: {key}")
