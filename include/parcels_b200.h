@@ -214,7 +214,8 @@ typedef struct pb_report {
     int64_t particle_steps;    /* particle-steps evaluated (one step = all RK stages)           */
     int64_t n_error;           /* particles that ended in a state >= 50                          */
     int64_t n_deleted;         /* particles that ended in state Delete (30)                     */
-    int64_t first_error_iter;  /* smallest loop iteration at which an error state arose, or -1  */
+    int64_t first_error_iter;  /* smallest loop iteration at which an error state arose (with delete_on_error: at which a
+                                * particle sampled outside the time interval), or -1 */
     int64_t n_out_of_time;     /* particles that sampled outside the time interval (state 70)    */
     int64_t max_iters_done;    /* largest per-particle iteration count                          */
     int64_t cache_refills;     /* corner-cache refills (diagnostic: HBM gathers actually made)   */
@@ -340,6 +341,10 @@ int32_t pb_particles_download_ids(pb_engine* e, int64_t n, int64_t* particle_id)
  * ErrorOutsideTimeInterval (70): the reference flags the WHOLE evaluated view when any particle
  * samples outside the time interval (_core/index_search.py:85-86, _core/field.py:31-44). */
 int32_t pb_flag_view_outside_time(pb_engine* e, double dt, double endtime);
+/* The same view under the DeleteParticle handler (state >= 50 -> Delete, reference tests' DeleteParticle kernel): every
+ * particle of the view ends in state Delete (30).  pb_report.first_error_iter of a delete_on_error launch that saw
+ * n_out_of_time > 0 is the iteration to replay to. */
+int32_t pb_delete_view_outside_time(pb_engine* e, double dt, double endtime);
 
 /* Pure helper used by tests: the engine's Philox4x32-10 + Box-Muller normals for
  * (seed, rng_call, iteration, particle_id), computed ON THE DEVICE. out = 2 doubles per id. */

@@ -143,6 +143,7 @@ SYMBOLS = {
     "pb_migrate_unpack": (C.c_int32, [_P, _P, C.c_int64]),
     "pb_particles_download_ids": (C.c_int32, [_P, C.c_int64, _P]),
     "pb_flag_view_outside_time": (C.c_int32, [_P, C.c_double, C.c_double]),
+    "pb_delete_view_outside_time": (C.c_int32, [_P, C.c_double, C.c_double]),
     "pb_debug_normals": (C.c_int32, [_P, C.c_uint64, C.c_uint64, C.c_int64, C.c_int64, _P, _P]),
 }
 

@@ -422,7 +422,9 @@ __global__ void __launch_bounds__(PB_BLOCK_THREADS, PB_MINBLOCKS) advect_kernel(
     const unsigned full = 0xffffffffu;
     unsigned long long s_steps = my_steps, s_ref = my_refills;
     unsigned n_err = errored, n_del = deleted, n_oot = oot, n_mig = migrate, n_ww = wait_window;
-    long long mx_it = my_iters, mn_err = err_iter;
+    // with the delete handler an out-of-interval sample is not an error of the lane, but the host still needs the iteration
+    // it happened in (the reference deletes the WHOLE evaluated view of that iteration, field.py:31-44)
+    long long mx_it = my_iters, mn_err = (oot && deleted) ? my_iters - 1 : err_iter;
     int mx_state = final_state;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {

@@ -56,13 +56,13 @@ static int32_t fail(int32_t code, const char* fmt, ...) {
     } while (0)
 
 // whole-view OutsideTimeInterval flag (index_search.py:85-86 + field.py:31-44)
-__global__ void flag_view_kernel(ParticlesDev P, double dt, double endtime) {
+__global__ void flag_view_kernel(ParticlesDev P, double dt, double endtime, int new_state) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.n) return;
     const int sign = dt > 0 ? 1 : -1;
     const int s = P.state[i];
     const double tte = sign * (endtime - P.t[i]);
-    if ((s == PB_SUCCESS || s == PB_EVALUATE) && tte >= 0) P.state[i] = PB_ERROR_OUTSIDE_TIME_INTERVAL;
+    if ((s == PB_SUCCESS || s == PB_EVALUATE) && tte >= 0) P.state[i] = new_state;
 }
 
 __global__ void normals_kernel(unsigned long long seed, unsigned long long rng_call, long long iter, long long n,
@@ -1025,18 +1025,24 @@ int32_t pb_advect_diffusion(pb_engine* e, const pb_advdiff_args* a, pb_report* r
     return pb_last_report(e, rep);
 }
 
-int32_t pb_flag_view_outside_time(pb_engine* e, double dt, double endtime) {
+static int32_t flag_view(pb_engine* e, double dt, double endtime, int new_state) {
     if (!e) return fail(PB_ERR_INVALID, "engine is NULL");
     CK(cudaSetDevice(e->device));
     if (e->n > 0) {
         ParticlesDev P{(float*)e->px.p, (float*)e->py.p, (float*)e->pz.p, (float*)e->pdx.p, (float*)e->pdy.p,
                        (float*)e->pdz.p, (double*)e->pt.p, (int*)e->pstate.p, (int*)e->pei.p, (long long*)e->ppid.p, e->n};
-        flag_view_kernel<<<(unsigned)((e->n + 255) / 256), 256, 0, e->stream>>>(P, dt, endtime);
+        flag_view_kernel<<<(unsigned)((e->n + 255) / 256), 256, 0, e->stream>>>(P, dt, endtime, new_state);
         CK(cudaGetLastError());
     }
     CK(cudaStreamSynchronize(e->stream));
     return PB_OK;
 }
+
+int32_t pb_flag_view_outside_time(pb_engine* e, double dt, double endtime) {
+    return flag_view(e, dt, endtime, PB_ERROR_OUTSIDE_TIME_INTERVAL);
+}
+
+int32_t pb_delete_view_outside_time(pb_engine* e, double dt, double endtime) { return flag_view(e, dt, endtime, PB_DELETE); }
 
 int32_t pb_debug_normals(pb_engine* e, uint64_t seed, uint64_t rng_call, int64_t iter, int64_t n,
                          const int64_t* particle_id, double* out) {

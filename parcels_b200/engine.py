@@ -306,6 +306,9 @@ class Engine:
     def flag_view_outside_time(self, dt, endtime):
         check(self._lib.pb_flag_view_outside_time(self._h, float(dt), float(endtime)))
 
+    def delete_view_outside_time(self, dt, endtime):
+        check(self._lib.pb_delete_view_outside_time(self._h, float(dt), float(endtime)))
+
     def debug_normals(self, seed, rng_call, it, particle_id):
         pid = np.ascontiguousarray(particle_id, dtype=np.int64)
         out = np.empty((pid.size, 2), dtype=np.float64)

@@ -544,8 +544,9 @@ class ParticleSet:
             eng.upload_particles(d, ei_last)
         self._device_synced = False
         # start-of-interval state for the error replay: the host arrays, or (device-resident) a snapshot in HBM
+        # (with the delete handler only an out-of-interval sample needs a replay: fields with a time axis)
         can_raise = not plan.delete_on_error
-        if lazy and can_raise:
+        if lazy and (can_raise or self.fieldset.time_interval is not None):
             eng.snapshot()
         rewind = eng.restore if lazy else (lambda: eng.upload_particles(d, ei_last))
         if self.fieldset.time_window is not None:
@@ -564,6 +565,18 @@ class ParticleSet:
                 rewind()
                 eng.advect(args(max_iters=k))
                 eng.flag_view_outside_time(dt, endtime)
+        elif plan.delete_on_error and rep["n_out_of_time"] > 0 and self.fieldset.time_window is None:
+            # Same whole-view rule under the DeleteParticle handler: every particle evaluated in the first iteration in which ANY
+            # particle sampled outside the time interval is flagged, hence deleted (field.py:31-44 then the handler) -- replay up
+            # to that iteration, then delete the view.  (The lanes deleted their own out-of-interval particle; the others ran on.)
+            k = rep["first_error_iter"]
+            rewind()
+            first = rep
+            rep = eng.advect(args(max_iters=k))
+            eng.delete_view_outside_time(dt, endtime)
+            rep["n_deleted"] += 1
+            rep["max_state"] = max(rep["max_state"], int(StatusCode.Delete))
+            rep["n_out_of_time"] = first["n_out_of_time"]
         self.last_report = rep
         self._stale_dt = dt
         if lazy and rep["max_state"] < StatusCode.Error:

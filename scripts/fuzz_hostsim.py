@@ -66,7 +66,7 @@ def random_spec(rng):
     if no_depth:
         spec["no_depth"] = True
     if nt > 1:
-        runtime = min(runtime, 0.9 * tmax)  # stay inside the time axis: an out-of-interval sample flags the reference's WHOLE view
+        runtime = min(runtime, 0.9 * tmax)
         spec["segments"] = [dict(runtime=runtime)]
         if dt > 0:
             lo, hi = 0.0, max(tmax - runtime - abs(dt), 0.0)
@@ -99,6 +99,14 @@ def main():
                     c["z"][pick[3]] = np.asarray(c["depth"], dtype=np.float64)[rng.integers(0, len(c["depth"]))]
                 if rng.random() < 0.3:
                     c[str(rng.choice(list("xyz")))][rng.integers(0, n)] = rng.choice([np.nan, np.inf, -np.inf])
+            if spec["kind"] == "smooth" and spec["nt"] > 1 and rng.random() < 0.3:
+                # a few releases just outside the fields' time interval: their first sample raises OutsideTimeInterval, which flags
+                # (with DeleteParticle: deletes) the reference's WHOLE evaluated view of that iteration (field.py:31-44)
+                runtime0 = spec["segments"][0]["runtime"]
+                delta = float(rng.uniform(0.05, 0.95)) * min(runtime0, 2 * abs(spec["dt"]))
+                pick = rng.integers(0, n, int(rng.integers(1, 3)))
+                c["t"] = np.asarray(c["t"], dtype=np.float64).copy()
+                c["t"][pick] = -delta if spec["dt"] > 0 else spec["tstep"] * (spec["nt"] - 1) + delta
             ps, err = run_engine(c)
             pd, oerr = run_oracle(c)
         except Exception as e:  # noqa: BLE001

@@ -125,3 +125,30 @@ def test_non_finite_positions_are_flagged_like_the_reference(name, delete):
         assert err == (err_name[oerr] if oerr else ""), (seed, err, oerr)
         for key in ("particle_id", "state", "t", "ei"):
             np.testing.assert_array_equal(ps._data[key], pd[key], err_msg=f"{name} seed {seed}: {key}")
+
+
+@pytest.mark.parametrize("sign", [1, -1])
+def test_out_of_interval_sample_deletes_the_whole_evaluated_view(sign):
+    """reference field.py:31-44 + the DeleteParticle handler: one particle released outside the fields' time interval raises
+    OutsideTimeInterval inside the vectorised eval, which flags EVERY particle evaluated in that iteration -- the handler
+    then deletes them all; only particles that were not being evaluated (released after this call's endtime) survive."""
+    from oracle import parcels_oracle as po
+
+    fs = _fieldset()
+    t_out, t_in, t_late = (-3.0, 0.0, 9.0) if sign > 0 else (103.0, 100.0, 91.0)
+    x = np.array([100.0, 200.0, 300.0, 400.0])
+    t = np.array([t_in, t_out, t_in + sign * 2.0, t_late])
+    with pytest.warns(pb.ParticleSetWarning):  # "released outside the FieldSet's executable time domain" (particleset.py:153-160)
+        ps = pb.ParticleSet(fs, x=x, y=np.full(4, 100.0), t=t)
+    ps.execute([pb.AdvectionRK4, pb.DeleteParticle], dt=sign * 1.0, runtime=10.0)  # endtime = t_out + sign * 10
+    assert ps.last_report["n_out_of_time"] == 1
+    np.testing.assert_array_equal(ps.particle_id, [3])
+    np.testing.assert_array_equal(ps.x, np.float32([400.0]))
+    np.testing.assert_array_equal(ps.t, [t_late])
+    # ... which is what the oracle's restatement of the reference does
+    U = np.ones((2, 1, 11, 21), dtype=np.float32)
+    ofs = po.OFieldSet(po.OGrid(np.linspace(0.0, 1000.0, 21), np.linspace(0.0, 500.0, 11), None, mesh="flat"), U, 0 * U, None,
+                       time=np.array([0.0, 100.0]))  # fmt: skip
+    pd = po.create_particle_data(x, np.full(4, 100.0), np.zeros(4), t)
+    po.pset_execute(pd, ofs, [po.AdvectionRK4, po.DeleteOnError], sign * 1.0, runtime=10.0)
+    np.testing.assert_array_equal(pd["particle_id"], [3])
