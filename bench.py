@@ -464,6 +464,9 @@ def main():
     ap.add_argument("--ref-step-seconds", type=float, default=5.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--pipeline", type=int, default=0,
+                    help="experiment: the end-to-end arm runs pb_advect_host with this many pipelined chunks and copies the "
+                         "result back with the same call (ParticleSet.pipeline_chunks, eager_host)")
     ap.add_argument("--sorted", action="store_true",
                     help="experiment: release the particles ordered by grid cell (z, y, x) instead of randomly -- measures what "
                          "spatial coherence between the lanes of a warp is worth (DESIGN.md 4, 'why not Morton-sort')")
@@ -590,6 +593,8 @@ def main():
             return torch.from_numpy(np.ascontiguousarray(v)).pin_memory().numpy()
 
         fresh = [{k: pinned(v) for k, v in init.items()} for _ in range(k_e2e)]  # host input batches, made before timing
+        if a.pipeline > 1:
+            ps.pipeline_chunks, ps.eager_host = a.pipeline, True
         for _ in range(min(a.warmup, 2)):
             ps._data = {k: v.copy() for k, v in init.items()}
             ps.execute(kernels, dt=dt, runtime=runtime)
@@ -609,6 +614,8 @@ def main():
         e2e = {"value": reduce(e2e_steps, "SUM") / e2e_s, "unit": "particle-steps/s", "h2d_bytes_per_step": n * (6 * 4 + 8 + 4 + 4 + 8),
                "d2h_bytes_per_step": n * (6 * 4 + 8 + 4 + 4), "steps": k_e2e,
                "api": f"parcels_b200.ParticleSet.execute([{', '.join(w['kernels'])}, DeleteParticle], dt={dt:g}, runtime={runtime:g})"}  # fmt: skip
+        if a.pipeline > 1:
+            e2e["pipeline_chunks"] = a.pipeline
 
     if dist is not None:
         dist.barrier()

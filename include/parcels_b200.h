@@ -238,6 +238,25 @@ int32_t pb_advect(pb_engine* e, const pb_advect_args* args, pb_report* rep);
 int32_t pb_advect_async(pb_engine* e, const pb_advect_args* args);
 int32_t pb_last_report(pb_engine* e, pb_report* rep);
 
+/* Kernel.execute on HOST particle arrays in one call (the shape of the reference's own call: pset._data in, pset._data out,
+ * _core/kernel.py:174-247), software-pipelined: the set is cut into `n_chunks` chunks (whole thread blocks; at most one per
+ * 37888 particles), each chunk is copied in, snapshotted (pb_particles_snapshot's layout, so pb_particles_restore rewinds the
+ * whole set), advected and -- when `download` != 0 -- copied back in one in-order stream, with up to four chunk streams in flight:
+ * the copies of one chunk run under the kernels of the others.  Equivalent to pb_particles_upload + pb_particles_snapshot +
+ * pb_advect (+ pb_particles_download): identical particle results and report; pb_report.kernel_ms is the device time of the whole
+ * pipelined pass, copies included.  The arrays play both roles (input, and output when `download`); dx / dy / dz may be NULL
+ * (zeros, not copied back); particle_id may be NULL without diffusion.  Page-locked host arrays make the copies fully
+ * asynchronous; pageable arrays work, with less overlap.  Not for time-windowed fieldsets. */
+typedef struct pb_particle_arrays {
+    float *x, *y, *z, *dx, *dy, *dz;
+    double* t;
+    int32_t* state;
+    int32_t* ei;
+    const int64_t* particle_id;
+} pb_particle_arrays;
+int32_t pb_advect_host(pb_engine* e, const pb_advect_args* args, int64_t n, const pb_particle_arrays* arrays, int32_t download,
+                       int32_t n_chunks, pb_report* rep);
+
 /* ---- AdvectionRK45 (kernels/_advection.py:85-155) under Kernel.execute's Repeat / next_dt state machine
  * (_core/kernel.py:108-120,199-216,224-226): every particle carries its own dt and next_dt; a rejected step
  * (error estimate kappa > tol) sets state Repeat and is retried with dt / 2 inside the same loop iteration; an

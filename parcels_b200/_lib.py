@@ -18,6 +18,12 @@ c_i32p = C.POINTER(C.c_int32)
 c_i64p = C.POINTER(C.c_int64)
 
 
+class ParticleArrays(C.Structure):
+    """pb_particle_arrays: the host columns of the particle SoA (pb_advect_host)."""
+
+    _fields_ = [(k, C.c_void_p) for k in ("x", "y", "z", "dx", "dy", "dz", "t", "state", "ei", "particle_id")]
+
+
 class AdvectArgs(C.Structure):
     _fields_ = [
         ("scheme", C.c_int32),
@@ -132,6 +138,7 @@ SYMBOLS = {
     "pb_particles_remove_deleted": (C.c_int32, [_P, C.POINTER(C.c_int64)]),
     "pb_advect": (C.c_int32, [_P, C.POINTER(AdvectArgs), C.POINTER(Report)]),
     "pb_advect_async": (C.c_int32, [_P, C.POINTER(AdvectArgs)]),
+    "pb_advect_host": (C.c_int32, [_P, C.POINTER(AdvectArgs), C.c_int64, C.POINTER(ParticleArrays), C.c_int32, C.c_int32, C.POINTER(Report)]),
     "pb_advect_rk45": (C.c_int32, [_P, _P, _P, _P, _P]),
     "pb_advect_diffusion": (C.c_int32, [_P, C.POINTER(AdvDiffArgs), C.POINTER(Report)]),
     "pb_last_report": (C.c_int32, [_P, C.POINTER(Report)]),

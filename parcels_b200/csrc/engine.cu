@@ -279,6 +279,11 @@ struct pb_engine {
     int ring = 0;                    // 0: every level resident
     long long win_first = 0, win_n = 0;
     cudaStream_t copy_stream = nullptr;
+    // pb_advect_host: one in-order stream per chunk slot (H2D -> kernel -> D2H), created on first use
+    static constexpr int PIPE = 4;
+    cudaStream_t pipe_stream[PIPE] = {};
+    cudaEvent_t pipe_done[PIPE] = {};
+    cudaEvent_t pipe_fork = nullptr;
     cudaEvent_t copy_done = nullptr;
     std::vector<double> time_host;   // seconds since the interval start
     // particles
@@ -368,6 +373,11 @@ void pb_engine_destroy(pb_engine* e) {
     cudaEventDestroy(e->ev0);
     cudaEventDestroy(e->ev1);
     cudaStreamDestroy(e->copy_stream);
+    for (int k = 0; k < pb_engine::PIPE; ++k) {
+        if (e->pipe_stream[k]) cudaStreamDestroy(e->pipe_stream[k]);
+        if (e->pipe_done[k]) cudaEventDestroy(e->pipe_done[k]);
+    }
+    if (e->pipe_fork) cudaEventDestroy(e->pipe_fork);
     cudaEventDestroy(e->copy_done);
     cudaEventDestroy(e->tev0);
     cudaEventDestroy(e->tev1);
@@ -825,10 +835,10 @@ int32_t pb_sample_scalar(pb_engine* e, int32_t slot, int32_t method, int64_t n, 
     return PB_OK;
 }
 
-int32_t pb_advect_async(pb_engine* e, const pb_advect_args* a) {
+// validation + kernel parameters shared by pb_advect_async and pb_advect_host (p.P is filled by the caller)
+static int32_t prepare_advect(pb_engine* e, const pb_advect_args* a, AdvectParams& p, int& nc) {
     if (!e || !a) return fail(PB_ERR_INVALID, "NULL argument");
     if (a->dt == 0.0 || a->dt != a->dt) return fail(PB_ERR_INVALID, "dt must be a non-zero number");
-    int nc;
     switch (a->scheme) {
         case PB_ADVECTION_NONE: case PB_ADVECTION_EE: case PB_ADVECTION_RK2: case PB_ADVECTION_RK4: nc = 2; break;
         case PB_ADVECTION_RK2_3D: case PB_ADVECTION_RK4_3D: nc = 3; break;
@@ -838,14 +848,8 @@ int32_t pb_advect_async(pb_engine* e, const pb_advect_args* a) {
         int32_t rc = check_fields(e, nc);
         if (rc) return rc;
     }
-    if (a->diffusion && !e->have_pid) return fail(PB_ERR_STATE, "diffusion needs particle_id (RNG counter)");
-    CK(cudaSetDevice(e->device));
-
-    AdvectParams p{};
     p.g = e->g;
     fill_field_desc(e, p.f);
-    p.P = ParticlesDev{(float*)e->px.p, (float*)e->py.p, (float*)e->pz.p, (float*)e->pdx.p, (float*)e->pdy.p,
-                       (float*)e->pdz.p, (double*)e->pt.p, (int*)e->pstate.p, (int*)e->pei.p, (long long*)e->ppid.p, e->n};
     p.scheme = a->scheme; p.diffusion = a->diffusion; p.delete_on_error = a->delete_on_error;
     p.kh_spherical = a->kh_spherical;
     p.dt = a->dt; p.endtime = a->endtime;
@@ -856,21 +860,125 @@ int32_t pb_advect_async(pb_engine* e, const pb_advect_args* a) {
     p.kernels_only = a->kernels_only;
     p.g.off_x = e->g.off_x; p.g.off_y = e->g.off_y; p.g.off_z = e->g.off_z;
     p.rep = e->d_rep;
+    return PB_OK;
+}
 
+static cudaError_t launch_advect_kernel(pb_engine* e, const AdvectParams& p, int nc, cudaStream_t stream) {
+    const int alt = agrid_alt_mode(e->interp);
+    return e->interp == PB_INTERP_CGRID_VELOCITY ? launch_cgrid(p, e->coord_f64 != 0, e->f_f64[0] != 0, nc, stream)
+           : alt ? launch_agrid_alt(p, alt, e->coord_f64 != 0, e->f_f64[0] != 0, e->g.nt > 0, nc, stream)
+                 : launch_agrid(p, e->coord_f64 != 0, e->f_f64[0] != 0, e->g.nt > 0, nc, stream);
+}
+
+int32_t pb_advect_async(pb_engine* e, const pb_advect_args* a) {
+    AdvectParams p{};
+    int nc = 2;
+    int32_t rc = prepare_advect(e, a, p, nc);
+    if (rc) return rc;
+    if (a->diffusion && !e->have_pid) return fail(PB_ERR_STATE, "diffusion needs particle_id (RNG counter)");
+    CK(cudaSetDevice(e->device));
+    p.P = ParticlesDev{(float*)e->px.p, (float*)e->py.p, (float*)e->pz.p, (float*)e->pdx.p, (float*)e->pdy.p,
+                       (float*)e->pdz.p, (double*)e->pt.p, (int*)e->pstate.p, (int*)e->pei.p, (long long*)e->ppid.p, e->n};
     zero_report(*e->h_rep);
     CK(cudaMemcpyAsync(e->d_rep, e->h_rep, sizeof(ReportDev), cudaMemcpyHostToDevice, e->stream));
     CK(cudaEventRecord(e->ev0, e->stream));
     if (e->n > 0) {
-        const int alt = agrid_alt_mode(e->interp);
-        cudaError_t ce = e->interp == PB_INTERP_CGRID_VELOCITY
-                             ? launch_cgrid(p, e->coord_f64 != 0, e->f_f64[0] != 0, nc, e->stream)
-                         : alt ? launch_agrid_alt(p, alt, e->coord_f64 != 0, e->f_f64[0] != 0, e->g.nt > 0, nc, e->stream)
-                               : launch_agrid(p, e->coord_f64 != 0, e->f_f64[0] != 0, e->g.nt > 0, nc, e->stream);
+        cudaError_t ce = launch_advect_kernel(e, p, nc, e->stream);
         if (ce != cudaSuccess) return fail(PB_ERR_CUDA, "advect_kernel launch failed: %s", cudaGetErrorString(ce));
     }
     CK(cudaEventRecord(e->ev1, e->stream));
     CK(cudaMemcpyAsync(e->h_rep, e->d_rep, sizeof(ReportDev), cudaMemcpyDeviceToHost, e->stream));
     e->pending = true;
+    return PB_OK;
+}
+
+// Kernel.execute on HOST particle arrays, software-pipelined: the set is cut into chunks, each chunk goes H2D -> start-of-interval
+// snapshot (D2D) -> advect kernel (-> D2H) in ONE in-order stream, and consecutive chunks use different streams, so the copies of
+// one chunk run under the kernels of the others (separate DMA engines per direction) and the kernels of neighbouring chunks fill
+// each other's tails.  No data-path dependency exists between particles, hence none between chunks; the report is accumulated
+// with the same atomics.  Equivalent to pb_particles_upload + pb_particles_snapshot + pb_advect (+ pb_particles_download).
+int32_t pb_advect_host(pb_engine* e, const pb_advect_args* a, int64_t n, const pb_particle_arrays* h, int32_t download,
+                       int32_t n_chunks, pb_report* rep) {
+    if (!e || !a || !h) return fail(PB_ERR_INVALID, "NULL argument");
+    if (n < 0) return fail(PB_ERR_INVALID, "n < 0");
+    if (n && (!h->x || !h->y || !h->z || !h->t || !h->state || !h->ei)) return fail(PB_ERR_INVALID, "NULL particle array");
+    if (e->ring) return fail(PB_ERR_STATE, "pb_advect_host does not drive time-slab streaming: use pb_particles_upload + pb_advect");
+    AdvectParams p{};
+    int nc = 2;
+    int32_t rc = prepare_advect(e, a, p, nc);
+    if (rc) return rc;
+    if (a->diffusion && !h->particle_id) return fail(PB_ERR_STATE, "diffusion needs particle_id (RNG counter)");
+    CK(cudaSetDevice(e->device));
+    if (!e->pipe_fork) {
+        CK(cudaEventCreateWithFlags(&e->pipe_fork, cudaEventDisableTiming));
+        for (int k = 0; k < pb_engine::PIPE; ++k) {
+            CK(cudaStreamCreateWithFlags(&e->pipe_stream[k], cudaStreamNonBlocking));
+            CK(cudaEventCreateWithFlags(&e->pipe_done[k], cudaEventDisableTiming));
+        }
+    }
+    CK(cudaStreamSynchronize(e->stream));  // the buffers may be re-allocated below: nothing of an earlier call may be in flight
+    struct Col { DevBuf* buf; const void* src; void* dst; size_t es; };
+    Col cols[10] = {{&e->px, h->x, h->x, 4}, {&e->py, h->y, h->y, 4}, {&e->pz, h->z, h->z, 4}, {&e->pdx, h->dx, h->dx, 4},
+                    {&e->pdy, h->dy, h->dy, 4}, {&e->pdz, h->dz, h->dz, 4}, {&e->pt, h->t, h->t, 8},
+                    {&e->pstate, h->state, h->state, 4}, {&e->pei, h->ei, h->ei, 4}, {&e->ppid, h->particle_id, nullptr, 8}};
+    for (int c = 0; c < 10; ++c)
+        if (c < 9 || h->particle_id) {
+            if ((rc = cols[c].buf->ensure(n ? (size_t)n * cols[c].es : 1))) return rc;
+        }
+    if ((rc = e->snap.ensure(n ? (size_t)n * 40 : 1))) return rc;
+    e->have_pid = h->particle_id != nullptr;
+    e->n = n;
+
+    zero_report(*e->h_rep);
+    CK(cudaMemcpyAsync(e->d_rep, e->h_rep, sizeof(ReportDev), cudaMemcpyHostToDevice, e->stream));
+    CK(cudaEventRecord(e->ev0, e->stream));
+    CK(cudaEventRecord(e->pipe_fork, e->stream));
+    // chunks of whole thread blocks; small sets are not cut
+    const long long align = 256 * 148;
+    long long chunks = n_chunks < 1 ? 1 : n_chunks;
+    long long per = n > 0 ? ((n + chunks - 1) / chunks + align - 1) / align * align : 0;
+    if (per <= 0) per = align;
+    const long long nchunk = n > 0 ? (n + per - 1) / per : 0;
+    const int nstream = (int)(nchunk < pb_engine::PIPE ? nchunk : pb_engine::PIPE);
+    for (int k = 0; k < nstream; ++k) CK(cudaStreamWaitEvent(e->pipe_stream[k], e->pipe_fork, 0));
+    for (long long c = 0; c < nchunk; ++c) {
+        cudaStream_t st = e->pipe_stream[c % pb_engine::PIPE];
+        const long long lo = c * per, m = (n - lo < per ? n - lo : per);
+        size_t snap_off = 0;
+        for (int k = 0; k < 10; ++k) {
+            char* dev = (char*)cols[k].buf->p + (size_t)lo * cols[k].es;
+            if (cols[k].src) CK(cudaMemcpyAsync(dev, (const char*)cols[k].src + (size_t)lo * cols[k].es, (size_t)m * cols[k].es, cudaMemcpyHostToDevice, st));
+            else if (k >= 3 && k <= 5) CK(cudaMemsetAsync(dev, 0, (size_t)m * 4, st));  // dx / dy / dz not given: zeros
+            if (k < 9) {  // start-of-interval copy in pb_particles_snapshot's layout (whole columns back to back)
+                CK(cudaMemcpyAsync((char*)e->snap.p + snap_off + (size_t)lo * cols[k].es, dev, (size_t)m * cols[k].es, cudaMemcpyDeviceToDevice, st));
+                snap_off += (size_t)n * cols[k].es;
+            }
+        }
+        p.P = ParticlesDev{(float*)e->px.p + lo, (float*)e->py.p + lo, (float*)e->pz.p + lo, (float*)e->pdx.p + lo, (float*)e->pdy.p + lo,
+                           (float*)e->pdz.p + lo, (double*)e->pt.p + lo, (int*)e->pstate.p + lo, (int*)e->pei.p + lo,
+                           e->have_pid ? (long long*)e->ppid.p + lo : (long long*)e->ppid.p, m};
+        cudaError_t ce = launch_advect_kernel(e, p, nc, st);
+        if (ce != cudaSuccess) return fail(PB_ERR_CUDA, "advect_kernel launch failed: %s", cudaGetErrorString(ce));
+    }
+    if (download)  // issued after every launch: a copy into pageable memory blocks the host until it is done
+        for (long long c = 0; c < nchunk; ++c) {
+            cudaStream_t st = e->pipe_stream[c % pb_engine::PIPE];
+            const long long lo = c * per, m = (n - lo < per ? n - lo : per);
+            for (int k = 0; k < 9; ++k)
+                if (cols[k].dst)
+                    CK(cudaMemcpyAsync((char*)cols[k].dst + (size_t)lo * cols[k].es, (char*)cols[k].buf->p + (size_t)lo * cols[k].es, (size_t)m * cols[k].es, cudaMemcpyDeviceToHost, st));
+        }
+    for (int k = 0; k < nstream; ++k) {
+        CK(cudaEventRecord(e->pipe_done[k], e->pipe_stream[k]));
+        CK(cudaStreamWaitEvent(e->stream, e->pipe_done[k], 0));
+    }
+    CK(cudaEventRecord(e->ev1, e->stream));
+    CK(cudaMemcpyAsync(e->h_rep, e->d_rep, sizeof(ReportDev), cudaMemcpyDeviceToHost, e->stream));
+    e->pending = true;
+    pb_report tmp;
+    rc = pb_last_report(e, &tmp);
+    if (rc) return rc;
+    if (rep) *rep = tmp;
     return PB_OK;
 }
 

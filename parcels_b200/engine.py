@@ -232,6 +232,21 @@ class Engine:
         check(self._lib.pb_advect_rk45(self._h, C.byref(a), ptr(dt_arr), ptr(next_dt_arr), C.byref(rep)))
         return _report_dict(rep)
 
+    def advect_host(self, args: AdvectArgs, d: dict, ei_last: np.ndarray, *, download: bool, n_chunks: int) -> dict:
+        """pb_advect_host: upload + start-of-interval snapshot + Kernel.execute (+ download into the same arrays), pipelined
+        chunk by chunk so that the copies run under the kernels."""
+        from ._lib import ParticleArrays
+
+        n = d["x"].shape[0]
+        for k, dt in (("x", np.float32), ("y", np.float32), ("z", np.float32), ("t", np.float64), ("state", np.int32)):
+            if d[k].dtype != dt:
+                raise TypeError(f"particle variable {k!r} must be {np.dtype(dt).name} (default Particle), got {d[k].dtype}")
+        h = ParticleArrays(*(C.cast(ptr(a), C.c_void_p) for a in (d["x"], d["y"], d["z"], d["dx"], d["dy"], d["dz"], d["t"], d["state"],
+                                                                   ei_last, d["particle_id"])))  # fmt: skip
+        rep = Report()
+        check(self._lib.pb_advect_host(self._h, C.byref(args), n, C.byref(h), int(bool(download)), int(n_chunks), C.byref(rep)))
+        return _report_dict(rep)
+
     def advect_async(self, args: AdvectArgs):
         check(self._lib.pb_advect_async(self._h, C.byref(args)))
 

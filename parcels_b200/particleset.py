@@ -9,6 +9,7 @@ trajectory; if the CUDA library or a GPU is missing, ``execute`` raises.
 from __future__ import annotations
 
 import datetime
+import os
 import types
 
 import numpy as np
@@ -276,6 +277,8 @@ class ParticleSet:
     ``ParticleSet(fieldset, pclass=Particle, t=, z=, y=, x=, particle_ids=)``; ``t`` may be
     float seconds, timedelta64 or (with a datetime time axis) datetime64."""
 
+    PIPELINE_MIN_PARTICLES = 262_144  # below this one chunk's kernel does not cover the copies of the next (pipeline_chunks)
+
     def __init__(self, fieldset, pclass=Particle, *, t=None, z=None, y=None, x=None, particle_ids=None, device=0,
                  seed=0, **kwargs):  # fmt: skip
         if not isinstance(pclass, ParticleClass):
@@ -291,6 +294,8 @@ class ParticleSet:
         self._host = None
         self._host_stale = False
         self.eager_host = False  # True: refresh the host arrays at the end of every execute() (shared-array adapters)
+        # > 1: Kernel.execute on host arrays runs as that many pipelined chunks (copies under kernels, pb_advect_host)
+        self.pipeline_chunks = int(os.environ.get("PB_PIPELINE_CHUNKS", "0"))
         self._n_device = 0
         self._stale_dt = 1.0
         self.last_report = None
@@ -356,9 +361,13 @@ class ParticleSet:
         d = self._host
         if d is not None and len(d["x"]) == eng.particle_count():
             # nothing was deleted: ids and order are unchanged, refresh the existing (possibly pinned) arrays in place
-            ei_last = np.empty(len(d["x"]), dtype=np.int32)
-            eng.download_particles(d, ei_last)
-            d["ei"][:, -1] = ei_last
+            ei_last = d["ei"][:, -1]  # the last grid's column: written in place when it is contiguous (one grid)
+            if ei_last.flags.c_contiguous:
+                eng.download_particles(d, ei_last)
+            else:
+                ei_last = np.empty(len(d["x"]), dtype=np.int32)
+                eng.download_particles(d, ei_last)
+                d["ei"][:, -1] = ei_last
         else:
             new = eng.download_all(ngrids=len(self.fieldset.gridset))
             if d is None:
@@ -519,7 +528,7 @@ class ParticleSet:
             d["state"][:] = StatusCode.Evaluate
             if n == 0:
                 return
-            if _has_nan(d["t"]):
+            if not self.__dict__.pop("_t_nan_free", False) and _has_nan(d["t"]):  # (execute() has just made that pass)
                 bad = np.where(np.isnan(d["t"]))[0]
                 raise ValueError(f"Time values for particles with indices {bad} cannot be NaN.")  # field.py:396-398
             ei_last = np.ascontiguousarray(d["ei"][:, -1])
@@ -540,17 +549,26 @@ class ParticleSet:
                                  kh=plan.kh, kh_spherical=plan.kh_spherical, kh_deg2m=plan.kh_deg2m, seed=self.seed,
                                  rng_call=self._rng_call, max_iters=max_iters, hint_all_zero=hint_all_zero)  # fmt: skip
 
-        if not on_device and not (resident and self._device_synced and eng.particle_count() == n):
+        needs_upload = not on_device and not (resident and self._device_synced and eng.particle_count() == n)
+        # host arrays in (and out): cut into chunks whose copies run under the kernels of the other chunks (pb_advect_host)
+        pipelined = (needs_upload and self.pipeline_chunks > 1 and n >= self.PIPELINE_MIN_PARTICLES and plan.advdiff is None
+                     and self.fieldset.time_window is None)  # fmt: skip
+        downloaded = False
+        if needs_upload and not pipelined:
             eng.upload_particles(d, ei_last)
         self._device_synced = False
         # start-of-interval state for the error replay: the host arrays, or (device-resident) a snapshot in HBM
         # (with the delete handler only an out-of-interval sample needs a replay: fields with a time axis)
         can_raise = not plan.delete_on_error
-        if lazy and (can_raise or self.fieldset.time_interval is not None):
+        if lazy and not pipelined and (can_raise or self.fieldset.time_interval is not None):
             eng.snapshot()
-        rewind = eng.restore if lazy else (lambda: eng.upload_particles(d, ei_last))
+        rewind = eng.restore if (lazy or pipelined) else (lambda: eng.upload_particles(d, ei_last))
         if self.fieldset.time_window is not None:
             rep = self._advect_windowed(eng, plan, d, dt, endtime, args)
+        elif pipelined:
+            # the result comes back with the same call when somebody is going to read it on the host anyway
+            downloaded = not lazy or self.eager_host
+            rep = eng.advect_host(args(), d, ei_last, download=downloaded, n_chunks=self.pipeline_chunks)
         else:
             rep = eng.advect(args())
         if rep["n_error"] > 0 and self.fieldset.time_window is None:
@@ -559,6 +577,7 @@ class ParticleSet:
             # and including that iteration so every particle is left exactly where the reference leaves it.
             k = rep["first_error_iter"]
             rewind()
+            downloaded = False
             rep = eng.advect(args(max_iters=k + 1))
             if rep["n_out_of_time"] > 0:
                 # an out-of-interval sample flags the WHOLE evaluated view (index_search.py:85-86, field.py:31-44)
@@ -571,6 +590,7 @@ class ParticleSet:
             # to that iteration, then delete the view.  (The lanes deleted their own out-of-interval particle; the others ran on.)
             k = rep["first_error_iter"]
             rewind()
+            downloaded = False
             first = rep
             rep = eng.advect(args(max_iters=k))
             eng.delete_view_outside_time(dt, endtime)
@@ -582,8 +602,14 @@ class ParticleSet:
         if lazy and rep["max_state"] < StatusCode.Error:
             # nothing to raise: stay in HBM.  Deleted particles are dropped there, order preserved
             # (Kernel.remove_deleted -> np.delete, kernel.py:98-106, particleset.py:247-250)
-            self._n_device = eng.remove_deleted() if (rep["n_deleted"] > 0 or rep["max_state"] == StatusCode.Delete) else n
-            self._host_stale = True
+            deletions = rep["n_deleted"] > 0 or rep["max_state"] == StatusCode.Delete
+            self._n_device = eng.remove_deleted() if deletions else n
+            if downloaded and not deletions:  # the pipelined call has already brought the result back: host == device
+                d["ei"][:, -1] = ei_last
+                d["dt"][:] = dt  # kernel.py:225-226
+                self._device_synced = True
+            else:
+                self._host_stale = True
             return
         if lazy:
             self._host_stale = True
@@ -600,7 +626,8 @@ class ParticleSet:
             self._device_synced = True
             return
         else:
-            eng.download_particles(d, ei_last)
+            if not downloaded:
+                eng.download_particles(d, ei_last)
             d["ei"][:, -1] = ei_last
             d["dt"][:] = dt  # kernel.py:225-226
         # the device report says whether any particle was deleted / errored: the O(N) host scans of
@@ -748,6 +775,7 @@ class ParticleSet:
         interval = 0
         self._device_synced = False  # between execute() calls the host owns the arrays
         lazy = self._lazy_ok(plan)
+        self.__dict__["_t_nan_free"] = True  # no NaN times (left) after the pass above: the first Kernel.execute need not look again
         try:
             while sign_dt * (time - end_time) < 0:
                 if next_output is not None:
@@ -762,6 +790,7 @@ class ParticleSet:
                         next_output += outputdt * sign_dt
                 time = next_time
         finally:
+            self.__dict__.pop("_t_nan_free", None)
             if output_file is not None and hasattr(output_file, "close"):  # `with output_file:` (particleset.py:444)
                 output_file.close()
         if self.eager_host and self._host_stale:
