@@ -268,7 +268,7 @@ int32_t pb_advect_host(pb_engine* e, const pb_advect_args* args, int64_t n, cons
  * reference leaves it, including its batch-level clamp of the particles that left the loop early (kernel.py:199-203).
  * pb_report: particle_steps = accepted steps, cache_refills = field evaluations (6 per attempt), n_error = particles
  * whose dt is 0 before endtime (state 50; the reference's loop never terminates on those).
- * Rectilinear A-grid + XLinear_Velocity fields, fully resident. */
+ * Fully resident fields: XLinear_Velocity on rectilinear A-grids, CGrid_Velocity on rectilinear and curvilinear C-grids. */
 typedef struct pb_rk45_args {
     double dt;      /* nominal dt of ParticleSet.execute: only its sign is used (compute_time_direction) */
     double endtime;
@@ -280,6 +280,8 @@ typedef struct pb_rk45_args {
                                    its step is accepted (kernel.py:206-216), dx / dy, dt, next_dt, state, ei written back, no position
                                    update, no batch-level dt clamp of finished particles (mixed lists: the host finishes the iteration) */
     int32_t resume;             /* 1: particle states are NOT reset to Evaluate */
+    int32_t hint_all_zero;      /* curvilinear grids, like the pb_advect_args field: the first evaluation of the call skips the hint test */
+    int32_t reserved;
 } pb_rk45_args;
 int32_t pb_advect_rk45(pb_engine* e, const pb_rk45_args* args, double* dt_inout, double* next_dt_inout, pb_report* rep);
 

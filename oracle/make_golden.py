@@ -417,6 +417,12 @@ RK45_CASES = {
     "all_f32": (0.2, 1.0, 4, 3600.0, 150.0),
     "backward": (0.002, 7.0, 4, 5000.0, -600.0),
     "c1_peninsula": (1e-6, 1.0, 8, 3600.0, 300.0),
+    # CGrid_Velocity: rectilinear (flat, spherical) and curvilinear (flat, spherical, float32 node coordinates) C-grids
+    "cgrid_rect_3d": (2e-4, 1.0, 4, 500.0, 25.0),
+    "cgrid_rect_sph": (2.0, 5.0, 4, 6000.0, 600.0),
+    "curv_flat_2d": (1e-4, 1.0, 4, 600.0, 60.0),
+    "curv_sph_2d": (20.0, 10.0, 4, 10800.0, 900.0),
+    "curv_sph_f32": (20.0, 10.0, 4, 6000.0, 600.0),
 }
 
 
@@ -431,7 +437,7 @@ def make_rk45_golden():
     for name, (tol, min_dt, fmax, runtime, dt) in RK45_CASES.items():
         c = tc.build(tc.CASES[name])
         fs = rh.build_fieldset(lon=c["lon"], lat=c["lat"], depth=c["depth"], times=c["times"], U=c["U"], V=c["V"], W=c["W"],
-                               mesh=c["mesh"])  # fmt: skip
+                               mesh=c["mesh"], interp=c.get("interp", "linear"), padding=c.get("padding", ("low", "low", "high")))  # fmt: skip
         fs.add_context("RK45_tol", tol)
         fs.add_context("RK45_min_dt", min_dt)
         fs.add_context("RK45_max_dt", fmax * abs(dt))

@@ -57,6 +57,8 @@ class Rk45Args(C.Structure):
         ("delete_on_error", C.c_int32),
         ("kernels_only", C.c_int32),
         ("resume", C.c_int32),
+        ("hint_all_zero", C.c_int32),
+        ("reserved", C.c_int32),
     ]
 
 

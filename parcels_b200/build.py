@@ -13,7 +13,7 @@ SOURCES = ["engine.cu", "agrid.cu", "aslip.cu", "rk45.cu", "advdiff.cu", "hashbu
 EXTRA_FLAGS = {"agrid.cu": ["-DPB_MINBLOCKS=4", "-DPB_SMEM_CACHE"], "aslip.cu": ["-DPB_MINBLOCKS=4", "-DPB_SMEM_CACHE"],
                "rk45.cu": ["-DPB_MINBLOCKS=3", "-DPB_SMEM_CACHE"], "advdiff.cu": ["-DPB_SMEM_CACHE"],
                "cgrid.cu": ["-DPB_MINBLOCKS=4"]}  # fmt: skip
-DEPS = [os.path.join(CSRC, f) for f in (*SOURCES, "common.cuh", "agrid.cuh")]
+DEPS = [os.path.join(CSRC, f) for f in (*SOURCES, "common.cuh", "agrid.cuh", "rk45.cuh")]
 OUT = os.path.join(HERE, "lib", "libparcels_b200.so")
 HEADER = os.path.join(os.path.dirname(HERE), "include", "parcels_b200.h")
 

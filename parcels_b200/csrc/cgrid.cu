@@ -8,6 +8,7 @@
 // time levels of U, V, W that CGrid_Velocity reads.  Everything is re-gathered from HBM only when the
 // particle changes cell / time level.
 #include "common.cuh"
+#include "rk45.cuh"
 
 // np.remainder for a positive divisor (floored modulo), in the array dtype
 __device__ __forceinline__ float mod_np(float a, float b) {
@@ -837,6 +838,25 @@ static cudaError_t launch_ad(const AdvectParams& p, int nc, cudaStream_t s) {
 cudaError_t launch_cgrid(const AdvectParams& p, bool coord_f64, bool data_f64, int nc, cudaStream_t s) {
     if (coord_f64) return data_f64 ? launch_ad<double, double>(p, nc, s) : launch_ad<double, float>(p, nc, s);
     return data_f64 ? launch_ad<float, double>(p, nc, s) : launch_ad<float, float>(p, nc, s);
+}
+
+// AdvectionRK45 on C-grids (rk45.cuh): rectilinear CGridPolicy and curvilinear CurvPolicy, 2-D (fieldset.UV)
+template <class Policy>
+static cudaError_t rk45_policy(const Rk45Params& q, cudaStream_t s) {
+    const int block = 128;
+    rk45_kernel<Policy><<<(unsigned)((q.base.P.n + block - 1) / block), block, 0, s>>>(q);
+    return cudaGetLastError();
+}
+template <class A, class D>
+static cudaError_t rk45_ad(const Rk45Params& q, cudaStream_t s) {
+    if (q.base.g.curvilinear) return q.base.g.spherical ? rk45_policy<CurvPolicy<A, D, 2, true>>(q, s) : rk45_policy<CurvPolicy<A, D, 2, false>>(q, s);
+    return rk45_policy<CGridPolicy<A, D, 2>>(q, s);
+}
+cudaError_t launch_rk45_cgrid(const AdvectParams& p, double* dt, double* next_dt, int* iters, int next_dt_f32, double tol, double min_dt,
+                              double max_dt, bool coord_f64, bool data_f64, cudaStream_t s) {
+    Rk45Params q{p, dt, next_dt, iters, next_dt_f32, tol, min_dt, max_dt};
+    if (coord_f64) return data_f64 ? rk45_ad<double, double>(q, s) : rk45_ad<double, float>(q, s);
+    return data_f64 ? rk45_ad<float, double>(q, s) : rk45_ad<float, float>(q, s);
 }
 
 template <class Policy>

@@ -1032,8 +1032,9 @@ int32_t pb_advect_rk45(pb_engine* e, const pb_rk45_args* a, double* dt_inout, do
     if (e->n && (!dt_inout || !next_dt_inout)) return fail(PB_ERR_INVALID, "NULL dt / next_dt array");
     int32_t rc = check_fields(e, 2);
     if (rc) return rc;
-    if (e->interp != PB_INTERP_XLINEAR_VELOCITY || e->g.curvilinear || e->ring || e->g.decomposed)
-        return fail(PB_ERR_INVALID, "AdvectionRK45 runs on resident rectilinear A-grid fields with XLinear_Velocity");
+    const bool cgrid = e->interp == PB_INTERP_CGRID_VELOCITY;
+    if (!(cgrid || (e->interp == PB_INTERP_XLINEAR_VELOCITY && !e->g.curvilinear)) || e->ring || e->g.decomposed)
+        return fail(PB_ERR_INVALID, "AdvectionRK45 runs on resident fields with XLinear_Velocity (rectilinear A-grid) or CGrid_Velocity");
     CK(cudaSetDevice(e->device));
     const size_t n = (size_t)e->n;
     DevBuf& buf = e->sout;  // dt, next_dt (f64), iters (i32)
@@ -1053,13 +1054,17 @@ int32_t pb_advect_rk45(pb_engine* e, const pb_rk45_args* a, double* dt_inout, do
     p.delete_on_error = a->delete_on_error;
     p.kernels_only = a->kernels_only; p.resume = a->resume;
     p.dt = a->dt; p.endtime = a->endtime; p.max_iters = a->max_iters;
+    p.hint_all_zero = a->hint_all_zero;
+    p.g.off_x = e->g.off_x; p.g.off_y = e->g.off_y; p.g.off_z = e->g.off_z;
     p.rep = e->d_rep;
     zero_report(*e->h_rep);
     CK(cudaMemcpyAsync(e->d_rep, e->h_rep, sizeof(ReportDev), cudaMemcpyHostToDevice, e->stream));
     CK(cudaEventRecord(e->ev0, e->stream));
     if (n) {
-        cudaError_t ce = launch_rk45(p, d_dt, d_ndt, d_it, a->next_dt_is_f32, a->tol, a->min_dt, a->max_dt, e->coord_f64 != 0,
-                                     e->f_f64[0] != 0, e->g.nt > 0, e->stream);
+        cudaError_t ce = cgrid ? launch_rk45_cgrid(p, d_dt, d_ndt, d_it, a->next_dt_is_f32, a->tol, a->min_dt, a->max_dt, e->coord_f64 != 0,
+                                                   e->f_f64[0] != 0, e->stream)
+                               : launch_rk45(p, d_dt, d_ndt, d_it, a->next_dt_is_f32, a->tol, a->min_dt, a->max_dt, e->coord_f64 != 0,
+                                             e->f_f64[0] != 0, e->g.nt > 0, e->stream);
         if (ce != cudaSuccess) return fail(PB_ERR_CUDA, "rk45_kernel launch failed: %s", cudaGetErrorString(ce));
     }
     CK(cudaEventRecord(e->ev1, e->stream));

@@ -175,8 +175,10 @@ def _setup_rk45(self, names, fieldset, pclass):
         raise NotImplementedError("AdvectionRK45 combines with user kernels and the DeleteParticle token, not with other built-in kernels")
     if pclass is None or "next_dt" not in [n for n, _ in pclass.variables]:
         raise ValueError('ParticleClass requires a "next_dt" for AdvectionRK45 Kernel.')
-    if fieldset.grid.curvilinear or fieldset.interp_method != "linear" or fieldset.time_window is not None:
-        raise NotImplementedError("AdvectionRK45 is implemented for resident rectilinear A-grid fields (XLinear_Velocity)")
+    if not ((fieldset.interp_method == "linear" and not fieldset.grid.curvilinear) or fieldset.interp_method == "cgrid_velocity") \
+            or fieldset.time_window is not None:  # fmt: skip
+        raise NotImplementedError("AdvectionRK45 is implemented for resident fields with XLinear_Velocity (rectilinear A-grids) or "
+                                  "CGrid_Velocity (rectilinear and curvilinear C-grids)")
     ctx = fieldset.context
     if "RK45_tol" not in ctx:
         warnings.warn("Setting RK45 tolerance to 10 m. Use fieldset.add_context('RK45_tol', [distance]) to change.", KernelWarning, stacklevel=4)
@@ -662,8 +664,12 @@ class ParticleSet:
         dt_arr = np.ascontiguousarray(d["dt"], dtype=np.float64)
         ndt_arr = np.ascontiguousarray(d["next_dt"], dtype=np.float64)
         tol, min_dt, max_dt = plan.rk45
+        hint_all_zero = False
+        if self.fieldset.grid.curvilinear:  # batch-level `if np.any(xi)` of the first evaluation (index_search.py:269)
+            sign = 1 if dt > 0 else -1
+            hint_all_zero = _hint_all_zero(ei_last, lambda s_: sign * (endtime - d["t"][s_]) >= 0, self.fieldset.grid.xdim)
         rep = eng.advect_rk45(dt, endtime, tol, min_dt, max_dt, dt_arr, ndt_arr, next_dt_is_f32=d["next_dt"].dtype == np.float32,
-                              delete_on_error=plan.delete_on_error)  # fmt: skip
+                              delete_on_error=plan.delete_on_error, hint_all_zero=hint_all_zero)  # fmt: skip
         self.last_report = rep
         eng.download_particles(d, ei_last)
         d["ei"][:, -1] = ei_last

@@ -121,8 +121,17 @@ def _device_rk45(pset, eng, params, dt, endtime):
     dt_arr = np.ascontiguousarray(d["dt"], dtype=np.float64)
     ndt_arr = np.ascontiguousarray(d["next_dt"], dtype=np.float64)
     tol, min_dt, max_dt = params
+    hint_all_zero = False
+    g = pset.fieldset.grid
+    if g.curvilinear:
+        from .particleset import _hint_all_zero
+
+        sign = 1 if dt > 0 else -1
+        hint_all_zero = _hint_all_zero(
+            ei_last, lambda s_: np.isin(d["state"][s_], [StatusCode.Success, StatusCode.Evaluate]) & (sign * (endtime - d["t"][s_]) >= 0), g.xdim
+        )
     rep = eng.advect_rk45(dt, endtime, tol, min_dt, max_dt, dt_arr, ndt_arr, next_dt_is_f32=d["next_dt"].dtype == np.float32,
-                          kernels_only=True, resume=True)  # fmt: skip
+                          kernels_only=True, resume=True, hint_all_zero=hint_all_zero)  # fmt: skip
     eng.download_particles(d, ei_last)
     d["ei"][:, -1] = ei_last
     d["dt"][:] = dt_arr

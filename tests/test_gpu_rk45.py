@@ -39,21 +39,27 @@ def test_rk45_matches_oracle_and_reference(name, golden_dir):
     c, ps, pd, steps, attempts = _engine_rk45(name)
     d = ps._data
     assert ps.last_report["particle_steps"] == steps
+    curv = name.startswith("curv")
+    exact = c["mesh"] == "flat" and not curv
     for ref in (pd, {k: g[f"{name}/{k}"] for k in ("x", "y", "z", "t", "dt", "next_dt", "state", "ei")}):
-        for k in ("state", "ei", "z"):
+        for k in ("state", "z") + (() if curv else ("ei",)):
             np.testing.assert_array_equal(d[k], ref[k], err_msg=f"{name}:{k}")
-        if c["mesh"] == "flat":
+        if exact:
             for k in ("x", "y", "t", "dt", "next_dt"):
                 np.testing.assert_array_equal(d[k], ref[k], err_msg=f"{name}:{k}")
-    if c["mesh"] == "flat":
+    if exact:
         assert ps.last_report["cache_refills"] == 6 * attempts  # field evaluations: same accept / reject sequence
     else:
-        # cos(lat) of libdevice vs glibc differs in the last ulp: positions to 2 ulp; an error estimate sitting exactly
-        # on the tolerance may flip one accept/reject decision, so step sizes are compared on (almost) all particles
+        # cos(lat) of libdevice vs glibc differs in the last ulp: positions to 2 ulp (curvilinear meshes: the 8 ulp of
+        # test_gpu_parity.CURV_ULP); an error estimate sitting exactly on the tolerance may flip one accept/reject decision,
+        # so step sizes (and, on curvilinear meshes, cells) are compared on (almost) all particles
+        same_path = (d["next_dt"] == pd["next_dt"]) & (d["t"] == pd["t"])
+        assert same_path.mean() > (0.95 if curv else 0.98)
         for k in ("x", "y"):
-            same_path = (d["next_dt"] == pd["next_dt"]) & (d["t"] == pd["t"])
-            assert same_path.mean() > 0.98
-            assert ulp_diff_f32(d[k][same_path], pd[k][same_path]).max() <= 2
+            floor = 0.01 * float(np.abs(np.asarray(c[k])).max())
+            assert ulp_diff_f32(d[k][same_path], pd[k][same_path], floor=floor if curv else None).max() <= (8 if curv else 2)
+        if curv:
+            assert (d["ei"][same_path] == pd["ei"][same_path]).mean() > 0.99
         np.testing.assert_array_equal(d["t"], pd["t"])
 
 
@@ -148,3 +154,26 @@ def test_rk45_in_a_mixed_list_matches_oracle(name):
     assert len(d["x"]) == len(pd["x"]) > 0 and d["nsteps"].max() > 1
     for k in ("particle_id", "state", "t", "dt", "next_dt", "ei", "x", "y", "z", "p", "nsteps"):
         np.testing.assert_array_equal(d[k], pd[k], err_msg=k)
+
+
+@pytest.mark.parametrize("name", ["cgrid_rect_sph", "curv_flat_2d", "curv_sph_2d"])
+def test_rk45_on_cgrids_in_a_mixed_list_equals_the_fused_run(name):
+    """CGrid_Velocity (rectilinear and curvilinear): [AdvectionRK45, user kernel] -- host loop control, every iteration's RK45
+    attempts on the device with the batch-level hint rule of the curvilinear search passed per iteration -- walks the same
+    accept / reject sequence as the single-launch run (which test_rk45_matches_oracle_and_reference pins to the reference)."""
+
+    def Count(particles, fieldset):
+        particles.nsteps += 1
+
+    _, fused, pd, steps, _ = _engine_rk45(name)
+    tol, min_dt, fmax, runtime, dt = RK45_CASES[name]
+    c = dict(load_case(name), W=None)
+    fs = make_fieldset(c)
+    for k_, v_ in (("RK45_tol", tol), ("RK45_min_dt", min_dt), ("RK45_max_dt", fmax * abs(dt))):
+        fs.add_context(k_, v_)
+    pclass = NEXT_DT.add_variable(pb.Variable("nsteps", dtype=np.int32, initial=0))
+    ps = pb.ParticleSet(fs, pclass=pclass, x=c["x"], y=c["y"], z=np.abs(np.asarray(c["z"])), t=c["t"])
+    ps.execute([pb.AdvectionRK45, Count], dt=dt, runtime=runtime)
+    assert ps.last_report["mode"] == "stepwise" and int(ps.nsteps.sum()) == steps
+    for k in ("x", "y", "z", "t", "dt", "next_dt", "state", "ei"):
+        np.testing.assert_array_equal(ps._data[k], fused._data[k], err_msg=f"{name}:{k}")
