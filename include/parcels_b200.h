@@ -268,7 +268,8 @@ int32_t pb_advect_host(pb_engine* e, const pb_advect_args* args, int64_t n, cons
  * reference leaves it, including its batch-level clamp of the particles that left the loop early (kernel.py:199-203).
  * pb_report: particle_steps = accepted steps, cache_refills = field evaluations (6 per attempt), n_error = particles
  * whose dt is 0 before endtime (state 50; the reference's loop never terminates on those).
- * Fully resident fields: XLinear_Velocity on rectilinear A-grids, CGrid_Velocity on rectilinear and curvilinear C-grids. */
+ * Fully resident fields: XLinear_Velocity / XFreeslip / XPartialslip on rectilinear A-grids, CGrid_Velocity on rectilinear and
+ * curvilinear C-grids. */
 typedef struct pb_rk45_args {
     double dt;      /* nominal dt of ParticleSet.execute: only its sign is used (compute_time_direction) */
     double endtime;

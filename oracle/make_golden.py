@@ -423,6 +423,10 @@ RK45_CASES = {
     "curv_flat_2d": (1e-4, 1.0, 4, 600.0, 60.0),
     "curv_sph_2d": (20.0, 10.0, 4, 10800.0, 900.0),
     "curv_sph_f32": (20.0, 10.0, 4, 6000.0, 600.0),
+    # XFreeslip / XPartialslip (land = nodes with U = V = 0)
+    "freeslip_3d": (2e-4, 1.0, 4, 500.0, 25.0),
+    "freeslip_surface": (1e-3, 1.0, 4, 700.0, 60.0),
+    "partialslip_sph": (2.0, 5.0, 4, 6000.0, 600.0),
 }
 
 

@@ -4,6 +4,7 @@
 #define PB_SMEM_CACHE
 #endif
 #include "agrid.cuh"
+#include "rk45.cuh"
 
 template <class A, class D, bool HT, int NC, int MODE>
 static cudaError_t launch1(const AdvectParams& p, cudaStream_t s) {
@@ -35,6 +36,29 @@ static cudaError_t launch_mode(const AdvectParams& p, bool coord_f64, bool data_
 }
 cudaError_t launch_agrid_alt(const AdvectParams& p, int mode, bool coord_f64, bool data_f64, bool has_time, int nc, cudaStream_t s) {
     return mode == 1 ? launch_mode<1>(p, coord_f64, data_f64, has_time, nc, s) : launch_mode<2>(p, coord_f64, data_f64, has_time, nc, s);
+}
+
+// AdvectionRK45 with XFreeslip / XPartialslip (rk45.cuh): 2-D, MODE 1
+template <class A, class D, bool HT>
+static cudaError_t rk45_slip1(const Rk45Params& q, cudaStream_t s) {
+    using Pol = AGridPolicy<A, D, HT, 2, 1>;
+    const size_t smem = (size_t)2 * 16 * sizeof(typename decltype(EvalCtx<A, D, 2>::cor)::S) * PB_BLOCK;
+    if (smem > 48 * 1024) {
+        cudaError_t ce = cudaFuncSetAttribute(rk45_kernel<Pol>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (ce != cudaSuccess) return ce;
+    }
+    rk45_kernel<Pol><<<(unsigned)((q.base.P.n + PB_BLOCK - 1) / PB_BLOCK), PB_BLOCK, smem, s>>>(q);
+    return cudaGetLastError();
+}
+cudaError_t launch_rk45_slip(const AdvectParams& p, double* dt, double* next_dt, int* iters, int next_dt_f32, double tol, double min_dt,
+                             double max_dt, bool coord_f64, bool data_f64, bool has_time, cudaStream_t s) {
+    Rk45Params q{p, dt, next_dt, iters, next_dt_f32, tol, min_dt, max_dt};
+    if (coord_f64) {
+        if (data_f64) return has_time ? rk45_slip1<double, double, true>(q, s) : rk45_slip1<double, double, false>(q, s);
+        return has_time ? rk45_slip1<double, float, true>(q, s) : rk45_slip1<double, float, false>(q, s);
+    }
+    if (data_f64) return has_time ? rk45_slip1<float, double, true>(q, s) : rk45_slip1<float, double, false>(q, s);
+    return has_time ? rk45_slip1<float, float, true>(q, s) : rk45_slip1<float, float, false>(q, s);
 }
 
 template <class A, class D, bool HT, int NC, int MODE>

@@ -516,6 +516,8 @@ cudaError_t launch_agrid_alt(const AdvectParams& p, int mode, bool coord_f64, bo
 // AdvectionRK45 + the Repeat / next_dt state machine (rk45.cu); dt / next_dt / iters: per-particle device arrays
 cudaError_t launch_rk45(const AdvectParams& p, double* dt, double* next_dt, int* iters, int next_dt_f32, double tol, double min_dt,
                         double max_dt, bool coord_f64, bool data_f64, bool has_time, cudaStream_t s);
+cudaError_t launch_rk45_slip(const AdvectParams& p, double* dt, double* next_dt, int* iters, int next_dt_f32, double tol, double min_dt,
+                             double max_dt, bool coord_f64, bool data_f64, bool has_time, cudaStream_t s);
 cudaError_t launch_rk45_cgrid(const AdvectParams& p, double* dt, double* next_dt, int* iters, int next_dt_f32, double tol, double min_dt,
                               double max_dt, bool coord_f64, bool data_f64, cudaStream_t s);
 cudaError_t launch_rk45_finalize(const ParticlesDev& P, double* dt, const int* iters, long long total_iters, double endtime, int sign,

@@ -1033,8 +1033,10 @@ int32_t pb_advect_rk45(pb_engine* e, const pb_rk45_args* a, double* dt_inout, do
     int32_t rc = check_fields(e, 2);
     if (rc) return rc;
     const bool cgrid = e->interp == PB_INTERP_CGRID_VELOCITY;
-    if (!(cgrid || (e->interp == PB_INTERP_XLINEAR_VELOCITY && !e->g.curvilinear)) || e->ring || e->g.decomposed)
-        return fail(PB_ERR_INVALID, "AdvectionRK45 runs on resident fields with XLinear_Velocity (rectilinear A-grid) or CGrid_Velocity");
+    const bool slip = agrid_alt_mode(e->interp) == 1;
+    if (!(cgrid || ((e->interp == PB_INTERP_XLINEAR_VELOCITY || slip) && !e->g.curvilinear)) || e->ring || e->g.decomposed)
+        return fail(PB_ERR_INVALID, "AdvectionRK45 runs on resident fields with XLinear_Velocity / XFreeslip / XPartialslip (rectilinear A-grid) "
+                                    "or CGrid_Velocity");
     CK(cudaSetDevice(e->device));
     const size_t n = (size_t)e->n;
     DevBuf& buf = e->sout;  // dt, next_dt (f64), iters (i32)
@@ -1063,8 +1065,10 @@ int32_t pb_advect_rk45(pb_engine* e, const pb_rk45_args* a, double* dt_inout, do
     if (n) {
         cudaError_t ce = cgrid ? launch_rk45_cgrid(p, d_dt, d_ndt, d_it, a->next_dt_is_f32, a->tol, a->min_dt, a->max_dt, e->coord_f64 != 0,
                                                    e->f_f64[0] != 0, e->stream)
-                               : launch_rk45(p, d_dt, d_ndt, d_it, a->next_dt_is_f32, a->tol, a->min_dt, a->max_dt, e->coord_f64 != 0,
-                                             e->f_f64[0] != 0, e->g.nt > 0, e->stream);
+                         : slip ? launch_rk45_slip(p, d_dt, d_ndt, d_it, a->next_dt_is_f32, a->tol, a->min_dt, a->max_dt, e->coord_f64 != 0,
+                                                  e->f_f64[0] != 0, e->g.nt > 0, e->stream)
+                                : launch_rk45(p, d_dt, d_ndt, d_it, a->next_dt_is_f32, a->tol, a->min_dt, a->max_dt, e->coord_f64 != 0,
+                                              e->f_f64[0] != 0, e->g.nt > 0, e->stream);
         if (ce != cudaSuccess) return fail(PB_ERR_CUDA, "rk45_kernel launch failed: %s", cudaGetErrorString(ce));
     }
     CK(cudaEventRecord(e->ev1, e->stream));

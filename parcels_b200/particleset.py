@@ -175,10 +175,10 @@ def _setup_rk45(self, names, fieldset, pclass):
         raise NotImplementedError("AdvectionRK45 combines with user kernels and the DeleteParticle token, not with other built-in kernels")
     if pclass is None or "next_dt" not in [n for n, _ in pclass.variables]:
         raise ValueError('ParticleClass requires a "next_dt" for AdvectionRK45 Kernel.')
-    if not ((fieldset.interp_method == "linear" and not fieldset.grid.curvilinear) or fieldset.interp_method == "cgrid_velocity") \
-            or fieldset.time_window is not None:  # fmt: skip
-        raise NotImplementedError("AdvectionRK45 is implemented for resident fields with XLinear_Velocity (rectilinear A-grids) or "
-                                  "CGrid_Velocity (rectilinear and curvilinear C-grids)")
+    if not ((fieldset.interp_method in ("linear", "freeslip", "partialslip") and not fieldset.grid.curvilinear)
+            or fieldset.interp_method == "cgrid_velocity") or fieldset.time_window is not None:  # fmt: skip
+        raise NotImplementedError("AdvectionRK45 is implemented for resident fields with XLinear_Velocity, XFreeslip or XPartialslip "
+                                  "(rectilinear A-grids) or CGrid_Velocity (rectilinear and curvilinear C-grids)")
     ctx = fieldset.context
     if "RK45_tol" not in ctx:
         warnings.warn("Setting RK45 tolerance to 10 m. Use fieldset.add_context('RK45_tol', [distance]) to change.", KernelWarning, stacklevel=4)

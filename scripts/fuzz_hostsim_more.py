@@ -83,7 +83,7 @@ def fuzz_scalar(rng):
 
 
 def fuzz_rk45(rng):
-    spec, c = base_case(rng, two_d=True, interps=("linear", "linear", "cgrid_velocity"))  # XLinear_Velocity and CGrid_Velocity
+    spec, c = base_case(rng, two_d=True, interps=("linear", "cgrid_velocity", "freeslip", "partialslip"))
     tmax = None if c["times"] is None else float(c["times"][-1])
     dt = float(rng.choice([50.0, 200.0])) * (1 if rng.random() < 0.8 else -1)
     nsteps = int(rng.integers(2, 10))
