@@ -207,7 +207,11 @@ typedef struct pb_advect_args {
                                   and return (dx/dy/dz accumulated, state/ei updated) WITHOUT the position
                                   update, EndofLoop and delete bookkeeping -- the host finishes the iteration
                                   (used when the kernel list also holds user Python kernels)              */
-    int32_t reserved;
+    int32_t first_eval_two_levels; /* 1: some evaluated particle of the call's FIRST loop iteration is not exactly on the first time
+                                  level (tau > 0) -- the reference then gathers two time levels for the WHOLE batch of that
+                                  evaluation (`lenT = 2 if any(tau > 0)`, _xinterpolators.py:130), which promotes the value of a
+                                  particle AT the first level to float64 (it matters on float32 grids only; later evaluations
+                                  cannot meet tau == 0 again) */
 } pb_advect_args;
 
 typedef struct pb_report {

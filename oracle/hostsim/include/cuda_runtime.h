@@ -58,6 +58,8 @@ inline T atomicAdd(T* p, T v) { T o = *p; *p = o + v; return o; }
 template <class T>
 inline T atomicMax(T* p, T v) { T o = *p; if (v > o) *p = v; return o; }
 template <class T>
+inline T atomicOr(T* p, T v) { T o = *p; *p = o | v; return o; }
+template <class T>
 inline T atomicMin(T* p, T v) { T o = *p; if (v < o) *p = v; return o; }
 
 inline long long __double_as_longlong(double d) { long long r; std::memcpy(&r, &d, 8); return r; }

@@ -41,7 +41,7 @@ class AdvectArgs(C.Structure):
         ("hint_all_zero", C.c_int32),
         ("resume", C.c_int32),
         ("kernels_only", C.c_int32),
-        ("reserved", C.c_int32),
+        ("first_eval_two_levels", C.c_int32),
     ]
 
 

@@ -67,8 +67,8 @@ __device__ __forceinline__ Val bilinear(const C (&c)[4], TY eta, TX xsi) {
 
 // Z-lerp (only when zeta > 0: `lenZ`, _xinterpolators.py:131,141-145) then bilinear
 template <class C, class TZ, class TY, class TX>
-__device__ __forceinline__ Val zlerp_bilinear(const C (&c)[8], TZ zeta, TY eta, TX xsi) {
-    if (!(zeta <= 0)) {  // zeta > 0 or NaN
+__device__ __forceinline__ Val zlerp_bilinear(const C (&c)[8], TZ zeta, TY eta, TX xsi, bool two_z) {
+    if (two_z) {
         using R = prom_t<C, TZ>;
         R r[4];
 #pragma unroll
@@ -86,13 +86,13 @@ __device__ __forceinline__ Val zlerp_bilinear(const C (&c)[8], TZ zeta, TY eta, 
 // The reference decides lenT/lenZ per batch (any(tau > 0)); per particle the arithmetic is the
 // same, and so is the dtype whenever the particles of a batch share their clock.
 template <class D, class TT, class TZ, class TY, class TX>
-__device__ __forceinline__ Val xlinear(const D (&v)[16], TT tau, TZ zeta, TY eta, TX xsi) {
+__device__ __forceinline__ Val xlinear(const D (&v)[16], TT tau, TZ zeta, TY eta, TX xsi, bool two_t, bool two_z) {
     if constexpr (std::is_same<TZ, double>::value && std::is_same<TY, double>::value && std::is_same<TX, double>::value) {
         // Every barycentric coordinate is float64 (float64 grid, or an RK stage position): all arithmetic
         // after the gather is float64 whatever D is, and a float32 corner value converts exactly.  One code
         // path; a skipped lerp just copies (x*(1-0) + y*0 == x would differ only for non-finite y).
         double r[8];
-        if (tau > 0) {
+        if (two_t) {
             const double omt = 1 - (double)tau;
 #pragma unroll
             for (int k = 0; k < 8; ++k) r[k] = (double)v[k] * omt + (double)v[8 + k] * (double)tau;
@@ -100,7 +100,7 @@ __device__ __forceinline__ Val xlinear(const D (&v)[16], TT tau, TZ zeta, TY eta
 #pragma unroll
             for (int k = 0; k < 8; ++k) r[k] = (double)v[k];
         }
-        if (!(zeta <= 0)) {  // zeta > 0, or NaN (a NaN depth must poison the value like the reference's batch-level lerp does)
+        if (two_z) {
             const double omz = 1 - zeta;
 #pragma unroll
             for (int k = 0; k < 4; ++k) r[k] = r[k] * omz + r[4 + k] * zeta;
@@ -108,17 +108,17 @@ __device__ __forceinline__ Val xlinear(const D (&v)[16], TT tau, TZ zeta, TY eta
         const double q = (1 - xsi) * (1 - eta) * r[0] + xsi * (1 - eta) * r[1] + (1 - xsi) * eta * r[2] + xsi * eta * r[3];
         return Val{q, false};
     } else {
-        if (tau > 0) {
+        if (two_t) {
             using R = prom_t<D, TT>;
             R r[8];
 #pragma unroll
             for (int k = 0; k < 8; ++k) r[k] = v[k] * (1 - tau) + v[8 + k] * tau;
-            return zlerp_bilinear<R, TZ, TY, TX>(r, zeta, eta, xsi);
+            return zlerp_bilinear<R, TZ, TY, TX>(r, zeta, eta, xsi, two_z);
         } else {
             D r[8];
 #pragma unroll
             for (int k = 0; k < 8; ++k) r[k] = v[k];
-            return zlerp_bilinear<D, TZ, TY, TX>(r, zeta, eta, xsi);
+            return zlerp_bilinear<D, TZ, TY, TX>(r, zeta, eta, xsi, two_z);
         }
     }
 }
@@ -176,6 +176,9 @@ struct EvalCtx {
     int ei;
     unsigned int refills;
     bool out_of_time;
+    // lenT / lenZ of the reference are decided per BATCH (`any(tau > 0)`, _xinterpolators.py:130-131): -1 = decide per particle
+    // (what a lane can know by itself), 0 / 1 = the batch's answer, given by whoever knows the batch (sampling pre-pass, host table)
+    signed char len_t, len_z;
 };
 
 // VectorField.eval for one particle (reference _core/field.py:250-304,307-405 with
@@ -244,6 +247,10 @@ __device__ __forceinline__ void eval_uvw(const GridDev& g, const FieldDev& f, Ev
     }
 
     using DV = typename decltype(e.cor)::S;  // float64 copies on float64 grids (exact), else the data dtype
+    // lenT / lenZ: the batch's decision when known, else the particle's own (zeta > 0 or NaN: a NaN depth must poison the value
+    // like a batch-level lerp does)
+    const bool two_t = e.len_t < 0 ? (tau > 0) : (e.len_t != 0);
+    const bool two_z = e.len_z < 0 ? !(zeta <= 0) : (e.len_z != 0);
     if constexpr (MODE == 2 || MODE == 4 || MODE == 5) {
 #ifdef PB_SMEM_CACHE
         // One node of the cached block per component, linear in time, no unit conversion.
@@ -257,7 +264,7 @@ __device__ __forceinline__ void eval_uvw(const GridDev& g, const FieldDev& f, Ev
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
             const DV c0 = e.cor.get(c, k);
-            if (tau > 0) q[c] = Val{(double)c0 * (1 - (double)tau) + (double)e.cor.get(c, 8 + k) * (double)tau, false};
+            if (two_t) q[c] = Val{(double)c0 * (1 - (double)tau) + (double)e.cor.get(c, 8 + k) * (double)tau, false};
             else q[c] = Val{(double)c0, std::is_same<D, float>::value};
         }
         u = q[0]; v = q[1];
@@ -266,14 +273,14 @@ __device__ __forceinline__ void eval_uvw(const GridDev& g, const FieldDev& f, Ev
     } else if constexpr (MODE == 3 || MODE == 6) {
         DV blk[16];
         e.cor.load(0, blk);
-        u = xlinear<DV, TT, TZ, TY, TX>(blk, tau, zeta, eta, xsi);  // scalar XLinear: the value as it is
+        u = xlinear<DV, TT, TZ, TY, TX>(blk, tau, zeta, eta, xsi, two_t, two_z);  // scalar XLinear: the value as it is
         if constexpr (MODE == 6) {
             // XLinearInvdistLandTracer (:556-613): corners ~ 0 are land.  All gathered corners land -> 0; some land -> the
             // inverse-squared-distance mean of the ocean corners, distance in (eta, xsi) only, EVERY gathered time / depth
             // level summed alike (t, z, y, x order); a sample exactly on an ocean node takes the sum of that node over
             // the gathered levels.  The levels gathered are lenT x lenZ = (tau > 0) x (zeta > 0), per particle (DESIGN.md,
             // waiver 1).  `eta_b - j_grid` is a float array minus an int64 array: float64 whatever the bcoord dtype.
-            const int nT = tau > 0 ? 2 : 1, nZ = zeta > 0 ? 2 : 1;
+            const int nT = two_t ? 2 : 1, nZ = (e.len_z < 0 ? (zeta > 0) : two_z) ? 2 : 1;
             int n_land = 0;
             double num = 0.0, den = 0.0;
             D node_val = 0;  // np.where(exact_mask, corner_data, 0.0) keeps the DATA dtype: a float32 field sums in float32
@@ -304,17 +311,17 @@ __device__ __forceinline__ void eval_uvw(const GridDev& g, const FieldDev& f, Ev
         DV blk[16];
         unsigned land = 0;
         e.cor.load(0, blk);
-        u = xlinear<DV, TT, TZ, TY, TX>(blk, tau, zeta, eta, xsi);
+        u = xlinear<DV, TT, TZ, TY, TX>(blk, tau, zeta, eta, xsi, two_t, two_z);
         if constexpr (MODE == 1) land = zero_mask<D, DV>(blk);
         e.cor.load(1, blk);
-        v = xlinear<DV, TT, TZ, TY, TX>(blk, tau, zeta, eta, xsi);
+        v = xlinear<DV, TT, TZ, TY, TX>(blk, tau, zeta, eta, xsi, two_t, two_z);
         if constexpr (MODE == 1) {
             // _Spatialslip (:385-480): damp the velocity component parallel to a cell edge whose nodes are all land
             // (U and V ~ 0 at the lower time level).  The reference looks at the second depth level when ANY particle
             // of the batch has zeta > 0; per particle that is zeta > 0 (identical unless a batch mixes particles
             // exactly on a depth level with others).  W's factors always use both levels (:460-470).
             land &= zero_mask<D, DV>(blk);
-            const unsigned l2 = (zeta > 0) ? (land & (land >> 4)) : land;  // bit y*2+x: land on every level looked at
+            const unsigned l2 = (e.len_z < 0 ? (zeta > 0) : two_z) ? (land & (land >> 4)) : land;  // bit y*2+x: land on every level looked at
             const unsigned lw = land & (land >> 4);
             const float a = g.slip_a, b = g.slip_b;
             const TX f_u = slip_factor<TX, TY>((TX)1, (l2 & 3u) == 3u, (l2 & 12u) == 12u, eta, a, b);
@@ -333,7 +340,7 @@ __device__ __forceinline__ void eval_uvw(const GridDev& g, const FieldDev& f, Ev
             }
             if (NC == 3) {
                 e.cor.load(NC - 1, blk);
-                w = xlinear<DV, TT, TZ, TY, TX>(blk, tau, zeta, eta, xsi);
+                w = xlinear<DV, TT, TZ, TY, TX>(blk, tau, zeta, eta, xsi, two_t, two_z);
                 TZ f_w = slip_factor<TZ, TY>((TZ)1, (lw & 3u) == 3u, (lw & 12u) == 12u, eta, a, b);
                 f_w = slip_factor<TZ, TX>(f_w, (lw & 5u) == 5u, (lw & 10u) == 10u, xsi, a, b);
                 w = mul_factor<TZ>(w, f_w);
@@ -353,7 +360,7 @@ __device__ __forceinline__ void eval_uvw(const GridDev& g, const FieldDev& f, Ev
             }
             if (NC == 3) {
                 e.cor.load(NC - 1, blk);
-                w = xlinear<DV, TT, TZ, TY, TX>(blk, tau, zeta, eta, xsi);
+                w = xlinear<DV, TT, TZ, TY, TX>(blk, tau, zeta, eta, xsi, two_t, two_z);
             } else {
                 w = Val{0.0, u.f32};
             }
@@ -372,6 +379,7 @@ struct AGridPolicy {
     static constexpr int NC = NC_;
     static constexpr bool RUNTIME_DTYPE = false;  // interpolation arithmetic is typed on the position dtype
     static constexpr bool F32_STAGES = (MODE == 2);  // nearest node: a stage value can be float32 at a float64 position
+    static constexpr bool BATCH_LEN_T = std::is_same<A, float>::value;  // float32 grid: a value's dtype depends on the batch's lenT
     using Ctx = EvalCtx<A, D, NC_>;
     __device__ static __forceinline__ void init(Ctx& e, const AdvectParams&, int ei) {
         e.cx.idx = e.cy.idx = e.cz.idx = e.ct.idx = -100;
@@ -387,6 +395,7 @@ struct AGridPolicy {
         e.last_tau = 0.0;
         e.searched = false;
         e.szi = e.syi = e.sxi = 0;
+        e.len_t = e.len_z = -1;
     }
     // ravel_index (basegrid.py:259-278) over the axes present; int64 arithmetic stored to int32
     __device__ static __forceinline__ void finish(Ctx& e, const AdvectParams& p) {

@@ -51,6 +51,7 @@ struct CGridCtx {
     int state, ei;
     unsigned int refills;
     bool out_of_time;
+    signed char len_t, len_z;  // lenT / lenZ of the batch when known (0 / 1), -1: decide per particle (see EvalCtx, agrid.cuh)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -364,6 +365,7 @@ struct CGridPolicy {
     static constexpr int NC = NC_;
     static constexpr bool RUNTIME_DTYPE = false;
     static constexpr bool F32_STAGES = false;
+    static constexpr bool BATCH_LEN_T = std::is_same<A, float>::value;
     using Ctx = CGridCtx<A, D>;
 
     __device__ static __forceinline__ void init(Ctx& e, const AdvectParams& p, int ei) {
@@ -373,6 +375,7 @@ struct CGridPolicy {
         e.kyi = e.kxi = INT_MIN;
         e.uyi = e.uxi = INT_MIN;
         e.fti = e.fzi = e.fyi = e.fxi = INT_MIN;
+        e.len_t = e.len_z = -1;
         e.ei = ei;
         // hint of the first search: unravel_index(ei) (basegrid.py:120-152,219-256), floor semantics
         const long long xd = p.g.xdim, yd = p.g.ydim;
@@ -503,7 +506,7 @@ struct CGridPolicy {
     __device__ static __forceinline__ void reduce_and_finish(const GridDev& g, Ctx& e, const A (&px)[4], const A (&py)[4], double tau,
                                                              TZ zeta, TY eta, TX xsi, PY y, Val& u, Val& v, Val& w) {
         const PY conv = SPH ? (PY)g.deg2m * cosx(deg2rad_np(y)) : (PY)1;
-        if (tau > 0) {  // lenT == 2: reduce over time in promote(D, float64)
+        if (e.len_t < 0 ? (tau > 0) : (e.len_t != 0)) {  // lenT == 2: reduce over time in promote(D, float64)
             const double omt = 1 - tau;
             cgrid_finish<SPH, double, A, TZ, TY, TX, PY, NC_>(g, px, py, e.fu[0] * omt + e.fu[2] * tau, e.fu[1] * omt + e.fu[3] * tau,
                                                               e.fv[0] * omt + e.fv[2] * tau, e.fv[1] * omt + e.fv[3] * tau,
@@ -528,6 +531,7 @@ struct CurvPolicy {
     static constexpr int NC = NC_;
     static constexpr bool RUNTIME_DTYPE = true;
     static constexpr bool F32_STAGES = false;
+    static constexpr bool BATCH_LEN_T = std::is_same<A, float>::value;
     using Ctx = CGridCtx<A, D>;
 
     __device__ static __forceinline__ void init(Ctx& e, const AdvectParams& p, int ei) { CGridPolicy<A, D, NC_>::init(e, p, ei); }
@@ -639,6 +643,7 @@ struct CurvPolicy {
 
         // -- CGrid_Velocity (_xinterpolators.py:193-332)
         load_corners(g, e, yi, xi);
+        const bool two_t = e.len_t < 0 ? (tau > 0) : (e.len_t != 0);  // lenT: the batch's decision when known
         A px[4], py[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) py[k] = e.clat[k];
@@ -667,7 +672,7 @@ struct CurvPolicy {
             // every operand the face values meet is float64 (edge lengths are float64: float64 bcoords on a
             // spherical mesh / float64 corner coordinates), so they convert exactly: ONE float64 code path
             double c[6];
-            if (tau > 0) {
+            if (two_t) {
                 const double omt = 1 - tau;
                 c[0] = e.fu[0] * omt + e.fu[2] * tau; c[1] = e.fu[1] * omt + e.fu[3] * tau;
                 c[2] = e.fv[0] * omt + e.fv[2] * tau; c[3] = e.fv[1] * omt + e.fv[3] * tau;
@@ -677,7 +682,7 @@ struct CurvPolicy {
             cgrid_finish<SPH, double, A, double, double, double, double, 2>(g, px, py, c[0], c[1], c[2], c[3], 0.0, 0.0, 0.0, eta, xsi,
                                                                             conv, u, v, wdummy);
         } else {  // flat mesh with float32 corner coordinates: edge lengths are float32, the face dtype matters
-            if (tau > 0) {
+            if (two_t) {
                 const double omt = 1 - tau;
                 cgrid_finish<SPH, double, A, double, double, double, double, 2>(g, px, py, e.fu[0] * omt + e.fu[2] * tau,
                                                                                 e.fu[1] * omt + e.fu[3] * tau, e.fv[0] * omt + e.fv[2] * tau,
@@ -689,7 +694,7 @@ struct CurvPolicy {
             }
         }
         if (NC_ == 3) {  // W: linear in zeta between the two Z faces (:316-330); dtype as NumPy would promote
-            const bool tl = tau > 0;
+            const bool tl = two_t;
             if (!tl && std::is_same<D, float>::value && zeta_f32) {
                 const float zf = (float)zeta;
                 const float wr = (float)e.fw[0] * (1 - zf) + (float)e.fw[1] * zf;
@@ -790,7 +795,7 @@ __global__ void sample_scalar_curv_kernel(const SampleParams s, int mode /* 4: X
                         ox = (long long)min(max(kx, 0), f.X - 1) * f.sX;
         const D* __restrict__ P = (const D*)f.p[0];
         const D c0 = ldg(P + (long long)min(max(ti, 0), f.T - 1) * f.sT + oz + oy + ox);
-        if (tau > 0) {  // lenT == 2 (per sample, DESIGN.md waiver 1): linear in time in promote(D, float64)
+        if (s.batch_flags ? ((*s.batch_flags & 1) != 0) : (tau > 0)) {  // lenT == 2 (the batch's decision, from the pre-pass): linear in time in promote(D, float64)
             const D c1 = ldg(P + up_idx(ti, f.T) * f.sT + oz + oy + ox);
             value = (double)c0 * (1 - tau) + (double)c1 * tau;
             value_f32 = false;

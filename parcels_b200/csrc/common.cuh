@@ -97,7 +97,7 @@ struct AdvectParams {
                         // the hint for the whole batch at the first eval (index_search.py:269-282)
     int resume;         // 1: continue a Kernel.execute call after a migration (states are NOT reset to Evaluate)
     int kernels_only;   // 1: one iteration's kernel functions only; the host does the position update etc.
-    int pad_;
+    int first_two_levels;  // the batch of the call's first evaluation has some tau > 0: lenT = 2 for every particle of it
     ReportDev* rep;
 };
 
@@ -303,6 +303,7 @@ __global__ void __launch_bounds__(PB_BLOCK_THREADS, PB_MINBLOCKS) advect_kernel(
                     const double ys = first ? (double)y : (double)y + (full ? vk.v : half_of(vk)) * dtp;
                     const double zs = (first || !three_d) ? (double)z : (double)z + (full ? wk.v : half_of(wk)) * dtp;
                     const double ts = first ? t : t + (full ? dtp : 0.5 * dtp);
+                    if constexpr (Policy::BATCH_LEN_T) e.len_t = (first && it == 0 && p.first_two_levels) ? 1 : -1;
                     Policy::eval_rt(p, e, first && nohint1, ts, zs, ys, xs, /*xy_f32=*/first, /*z_f32=*/first || !three_d, uk, vk, wk);
                     if (first) { su = uk.v; sv = vk.v; sw = wk.v; }
                     else if (nstage == 4) {
@@ -312,7 +313,11 @@ __global__ void __launch_bounds__(PB_BLOCK_THREADS, PB_MINBLOCKS) advect_kernel(
                 }
             } else {
             u1 = Val{0.0, false}; v1 = u1; w1 = u1;
+            // float32 grids: the value dtype of this evaluation depends on the BATCH's lenT (only the call's first iteration can
+            // hold a particle with tau == 0, i.e. exactly on the first time level; the host knows whether the others are too)
+            if constexpr (Policy::BATCH_LEN_T) e.len_t = (it == 0 && p.first_two_levels) ? 1 : -1;
             if (nstage > 0) Policy::template eval<float, float, float>(p, e, nohint1, t, z, y, x, u1, v1, w1);
+            if constexpr (Policy::BATCH_LEN_T) e.len_t = -1;
             su = u1.v; sv = v1.v; sw = w1.v;
             uk = u1; vk = v1; wk = w1;
             if constexpr (Policy::F32_STAGES) {
@@ -475,7 +480,40 @@ struct SampleParams {
     int* ei_out;
     int* state_out;
     int* f32_out;        // may be NULL; 1 where NumPy's promotion gives the (first) value dtype float32
+    // the reference's batch-level lenT / lenZ (`any(tau > 0)`, `any(zeta > 0)` over the samples of the call, _xinterpolators.py:130-131):
+    // device word written by sample_flags_kernel before the sampling kernel runs: bit 0 = any(tau > 0), bit 1 = any(zeta > 0);
+    // NULL = not known (every sample decides for itself)
+    const int* batch_flags;
 };
+
+// The batch-level part of one Field.eval / VectorField.eval call: the time search and the depth search of every sample, exactly
+// as the sampling kernel does them, reduced to `any(tau > 0)` and `any(zeta > 0)` (the reference's lenT / lenZ).
+template <class A>
+__global__ void sample_flags_kernel(const SampleParams s, int has_time, int* flags) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    int m = 0;
+    if (i < s.n) {
+        const GridDev& g = s.g;
+        if (has_time && g.nt > 0) {
+            const double t = s.t[i];
+            if (0 <= t && t <= g.time_len) {
+                AxisCell<double> c;
+                c.idx = -100; c.lo = c.hi = 0.0;
+                if (axis_search<double, double>(g.time, g.nt, t, c) > 0) m |= 1;
+            }
+        }
+        if (g.nz > 0) {
+            AxisCell<A> c;
+            c.idx = -100; c.lo = c.hi = (A)0;
+            const double zeta = s.pos_f32 ? (double)axis_search<float, A>((const A*)g.depth, g.nz, (float)s.z[i], c)
+                                          : (double)axis_search<double, A>((const A*)g.depth, g.nz, s.z[i], c);
+            if (zeta > 0) m |= 2;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m |= __shfl_xor_sync(0xffffffffu, m, o);
+    if ((threadIdx.x & 31) == 0 && m) atomicOr(flags, m);
+}
 
 template <class Policy>
 __global__ void sample_kernel(const SampleParams s) {
@@ -489,6 +527,11 @@ __global__ void sample_kernel(const SampleParams s) {
     e.state = PB_EVALUATE;
     e.refills = 0;
     e.out_of_time = false;
+    if (s.batch_flags) {  // the reference decides lenT / lenZ for the whole call
+        const int bf = *s.batch_flags;
+        e.len_t = (signed char)(bf & 1);
+        e.len_z = (signed char)((bf >> 1) & 1);
+    }
     Val u, v, w;
     const bool nh = s.no_hint || !s.ei_hint;
     if constexpr (Policy::RUNTIME_DTYPE) {

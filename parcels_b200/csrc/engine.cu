@@ -744,6 +744,17 @@ static int32_t check_fields(pb_engine* e, int nc) {
     return PB_OK;
 }
 
+// pre-pass of a sampling call: the reference's batch-level lenT / lenZ into the device word `flags` (see sample_flags_kernel)
+static int32_t launch_sample_flags(pb_engine* e, SampleParams& sp, bool has_time, int* flags) {
+    CK(cudaMemsetAsync(flags, 0, sizeof(int), e->stream));
+    const unsigned grid = (unsigned)((sp.n + 255) / 256);
+    if (e->coord_f64) sample_flags_kernel<double><<<grid, 256, 0, e->stream>>>(sp, has_time ? 1 : 0, flags);
+    else sample_flags_kernel<float><<<grid, 256, 0, e->stream>>>(sp, has_time ? 1 : 0, flags);
+    CK(cudaGetLastError());
+    sp.batch_flags = flags;
+    return PB_OK;
+}
+
 int32_t pb_sample_velocity(pb_engine* e, int64_t n, const double* t, const double* z, const double* y, const double* x,
                            int32_t positions_are_f32, int32_t three_d, const int32_t* ei_hint, int32_t no_hint, double* u,
                            double* v, double* w, int32_t* ei_out, int32_t* state_out) {
@@ -755,9 +766,9 @@ int32_t pb_sample_velocity(pb_engine* e, int64_t n, const double* t, const doubl
     if (n == 0) return PB_OK;
     CK(cudaSetDevice(e->device));
     if ((rc = e->samp_d.ensure((size_t)n * 7 * sizeof(double)))) return rc;
-    if ((rc = e->samp_i.ensure((size_t)n * 3 * sizeof(int)))) return rc;
+    if ((rc = e->samp_i.ensure(((size_t)n * 3 + 1) * sizeof(int)))) return rc;
     double* d = (double*)e->samp_d.p;  // t z y x u v w
-    int* di = (int*)e->samp_i.p;       // hint ei state
+    int* di = (int*)e->samp_i.p;       // hint ei state, batch flags
     const double* src[4] = {t, z, y, x};
     for (int k = 0; k < 4; ++k) CK(cudaMemcpyAsync(d + k * n, src[k], n * 8, cudaMemcpyHostToDevice, e->stream));
     if (ei_hint) CK(cudaMemcpyAsync(di, ei_hint, n * 4, cudaMemcpyHostToDevice, e->stream));
@@ -770,6 +781,7 @@ int32_t pb_sample_velocity(pb_engine* e, int64_t n, const double* t, const doubl
     sp.ei_hint = ei_hint ? di : nullptr;
     sp.ei_out = di + n; sp.state_out = di + 2 * n;
     sp.pos_f32 = positions_are_f32; sp.no_hint = no_hint;
+    if ((rc = launch_sample_flags(e, sp, e->g.nt > 0, di + 3 * n))) return rc;
     const int alt = agrid_alt_mode(e->interp);
     cudaError_t ce = e->interp == PB_INTERP_CGRID_VELOCITY
                          ? launch_sample_cgrid(sp, e->coord_f64 != 0, e->f_f64[0] != 0, nc, e->stream)
@@ -804,9 +816,9 @@ int32_t pb_sample_scalar(pb_engine* e, int32_t slot, int32_t method, int64_t n, 
     CK(cudaSetDevice(e->device));
     int32_t rc;
     if ((rc = e->samp_d.ensure((size_t)n * 5 * sizeof(double)))) return rc;
-    if ((rc = e->samp_i.ensure((size_t)n * 4 * sizeof(int)))) return rc;
+    if ((rc = e->samp_i.ensure(((size_t)n * 4 + 1) * sizeof(int)))) return rc;
     double* d = (double*)e->samp_d.p;  // t z y x value
-    int* di = (int*)e->samp_i.p;       // hint ei state f32
+    int* di = (int*)e->samp_i.p;       // hint ei state f32, batch flags
     const double* src[4] = {t, z, y, x};
     for (int k = 0; k < 4; ++k) CK(cudaMemcpyAsync(d + k * n, src[k], n * 8, cudaMemcpyHostToDevice, e->stream));
     if (ei_hint) CK(cudaMemcpyAsync(di, ei_hint, n * 4, cudaMemcpyHostToDevice, e->stream));
@@ -823,6 +835,7 @@ int32_t pb_sample_scalar(pb_engine* e, int32_t slot, int32_t method, int64_t n, 
     sp.ei_hint = ei_hint ? di : nullptr;
     sp.ei_out = di + n; sp.state_out = di + 2 * n; sp.f32_out = di + 3 * n;
     sp.pos_f32 = positions_are_f32; sp.no_hint = ei_hint ? 0 : 1;
+    if ((rc = launch_sample_flags(e, sp, T > 1, di + 4 * n))) return rc;
     // a field without a time dimension has no time interval: no time search at all (field.py:112-117)
     cudaError_t ce = e->g.curvilinear ? launch_sample_scalar_curv(sp, 3 + method, e->coord_f64 != 0, e->f_f64[slot] != 0, T > 1, e->stream)
                                       : launch_sample_scalar(sp, 3 + method, e->coord_f64 != 0, e->f_f64[slot] != 0, T > 1, e->stream);
@@ -858,6 +871,7 @@ static int32_t prepare_advect(pb_engine* e, const pb_advect_args* a, AdvectParam
     p.hint_all_zero = a->hint_all_zero;
     p.resume = a->resume;
     p.kernels_only = a->kernels_only;
+    p.first_two_levels = a->first_eval_two_levels;
     p.g.off_x = e->g.off_x; p.g.off_y = e->g.off_y; p.g.off_z = e->g.off_z;
     p.rep = e->d_rep;
     return PB_OK;

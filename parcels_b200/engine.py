@@ -194,10 +194,11 @@ class Engine:
     # -- hot path --------------------------------------------------------------------------------
     @staticmethod
     def make_args(scheme, dt, endtime, *, diffusion=False, delete_on_error=False, kh=(0.0, 0.0), kh_spherical=False,
-                  kh_deg2m=1.0, seed=0, rng_call=0, max_iters=-1, hint_all_zero=False, resume=False, kernels_only=False) -> AdvectArgs:  # fmt: skip
+                  kh_deg2m=1.0, seed=0, rng_call=0, max_iters=-1, hint_all_zero=False, resume=False, kernels_only=False,
+                  first_eval_two_levels=False) -> AdvectArgs:  # fmt: skip
         return AdvectArgs(int(scheme), int(diffusion), int(delete_on_error), int(kh_spherical), float(dt), float(endtime),
                           float(kh[0]), float(kh[1]), float(kh_deg2m), int(seed), int(rng_call), int(max_iters),
-                          int(bool(hint_all_zero)), int(bool(resume)), int(bool(kernels_only)), 0)  # fmt: skip
+                          int(bool(hint_all_zero)), int(bool(resume)), int(bool(kernels_only)), int(bool(first_eval_two_levels)))  # fmt: skip
 
     def advect(self, args) -> dict:
         """``Kernel.execute`` on the device: ``args`` from :meth:`make_args` (pb_advect) or :meth:`make_advdiff_args`

@@ -36,6 +36,18 @@ def _has_nan(a) -> bool:
     return bool(s != s) and bool(np.isnan(a).any())
 
 
+def _first_eval_two_levels(fieldset, t, evaluated) -> bool:
+    """float32 grids with a time axis: True when some evaluated particle is NOT exactly on the first time level.  The reference
+    decides `lenT = 2 if any(tau > 0)` for the whole batch of an evaluation (_xinterpolators.py:130); tau == 0 only AT the first
+    level (`_search_1d_array` is left-sided: any later level gives tau == 1), so only the first evaluation of a call can mix the
+    two cases -- and there a two-level batch promotes the value of a first-level particle to float64.  On float64 grids every
+    barycentric coordinate is float64 and the promotion changes nothing."""
+    if fieldset._time_s is None or fieldset.grid.lon.dtype != np.float32:
+        return False
+    te = t[evaluated]
+    return bool(te.size) and bool(np.any(te != float(fieldset._time_s[0])))
+
+
 def _hint_all_zero(ei_last, evaluated, xdim) -> bool:
     """Curvilinear grids: True when the hinted xi (= ei % xdim) of EVERY evaluated particle is 0 -- the reference then skips
     the hint test for the whole batch (`if np.any(xi)`, _core/index_search.py:269).  `evaluated(slice)` gives the mask of a
@@ -543,13 +555,16 @@ class ParticleSet:
             sign = 1 if dt > 0 else -1
             hint_all_zero = _hint_all_zero(ei_last, lambda s_: sign * (endtime - d["t"][s_]) >= 0, g.xdim)
 
+        two_levels = (not on_device) and _first_eval_two_levels(self.fieldset, d["t"], (1 if dt > 0 else -1) * (endtime - d["t"]) >= 0)
+
         def args(max_iters=-1):
             if plan.advdiff is not None:
                 return eng.make_advdiff_args(dt=dt, endtime=endtime, delete_on_error=plan.delete_on_error, seed=self.seed,
                                              rng_call=self._rng_call, max_iters=max_iters, **plan.advdiff)  # fmt: skip
             return eng.make_args(plan.scheme, dt, endtime, diffusion=plan.diffusion, delete_on_error=plan.delete_on_error,
                                  kh=plan.kh, kh_spherical=plan.kh_spherical, kh_deg2m=plan.kh_deg2m, seed=self.seed,
-                                 rng_call=self._rng_call, max_iters=max_iters, hint_all_zero=hint_all_zero)  # fmt: skip
+                                 rng_call=self._rng_call, max_iters=max_iters, hint_all_zero=hint_all_zero,
+                                 first_eval_two_levels=two_levels)  # fmt: skip
 
         needs_upload = not on_device and not (resident and self._device_synced and eng.particle_count() == n)
         # host arrays in (and out): cut into chunks whose copies run under the kernels of the other chunks (pb_advect_host)

@@ -96,10 +96,16 @@ def _device_kernels(pset, eng, item, dt, endtime):
         args = eng.make_advdiff_args(dt=dt, endtime=endtime, seed=pset.seed, rng_call=pset._rng_call, resume=True, kernels_only=True,
                                      **item[1])  # fmt: skip
     else:
+        from .particleset import _first_eval_two_levels
+
         _, scheme, diffusion, plan = item
+        sign_ = 1 if dt > 0 else -1
+        two_levels = _first_eval_two_levels(
+            pset.fieldset, d["t"], np.isin(d["state"], [StatusCode.Success, StatusCode.Evaluate]) & (sign_ * (endtime - d["t"]) >= 0)
+        )
         args = eng.make_args(scheme, dt, endtime, diffusion=diffusion, kh=plan.kh, kh_spherical=plan.kh_spherical,
                              kh_deg2m=plan.kh_deg2m, seed=pset.seed, rng_call=pset._rng_call, hint_all_zero=hint_all_zero,
-                             resume=True, kernels_only=True)  # fmt: skip
+                             resume=True, kernels_only=True, first_eval_two_levels=two_levels)  # fmt: skip
     rep = eng.advect(args)
     eng.download_particles(d, ei_last)
     d["ei"][:, -1] = ei_last

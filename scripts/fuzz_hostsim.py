@@ -107,6 +107,11 @@ def main():
                 pick = rng.integers(0, n, int(rng.integers(1, 3)))
                 c["t"] = np.asarray(c["t"], dtype=np.float64).copy()
                 c["t"][pick] = -delta if spec["dt"] > 0 else spec["tstep"] * (spec["nt"] - 1) + delta
+            elif spec["kind"] == "smooth" and spec["nt"] > 1 and spec["dt"] > 0 and rng.random() < 0.3:
+                # repeated release: some particles exactly on the first time level (tau == 0), the others later -- the reference's
+                # batch-level lenT then promotes the first-level particles' first sample (float32 grids)
+                later = float(rng.choice([0.5, 1.0, 2.0])) * spec["dt"]
+                c["t"] = np.where(rng.random(n) < 0.5, 0.0, later)
             ps, err = run_engine(c)
             pd, oerr = run_oracle(c)
         except Exception as e:  # noqa: BLE001

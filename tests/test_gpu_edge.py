@@ -152,3 +152,38 @@ def test_out_of_interval_sample_deletes_the_whole_evaluated_view(sign):
     pd = po.create_particle_data(x, np.full(4, 100.0), np.zeros(4), t)
     po.pset_execute(pd, ofs, [po.AdvectionRK4, po.DeleteOnError], sign * 1.0, runtime=10.0)
     np.testing.assert_array_equal(pd["particle_id"], [3])
+
+
+@pytest.mark.parametrize("interp", ["linear", "cgrid_velocity"])
+def test_first_level_particles_in_a_mixed_batch_are_promoted_like_the_reference(interp):
+    """float32 grid, repeated release: half of the set starts exactly on the first time level (tau == 0), the rest later.  The
+    reference decides `lenT = 2 if any(tau > 0)` for the whole batch (_xinterpolators.py:130), so the first-level particles'
+    first sample is float64 arithmetic -- alone in a batch it would be float32.  Bit-exact against the oracle, both through the
+    sampling API (exact batch flags from the pre-pass) and through ParticleSet.execute (the host tells the kernel)."""
+    import cases
+    from engine_run import make_fieldset, run_engine
+    from oracle import parcels_oracle as po
+    from oracle_run import oracle_fieldset, run_oracle
+
+    spec = dict(seed=5, kind="smooth", cdtype="f4", ddtype="f4", mesh="flat", nx=20, ny=15, nz=4, nt=4, tstep=600.0, n=4000,
+                kernels=["AdvectionRK4_3D"], dt=100.0, segments=[dict(runtime=100.0)], delete=True, margin=0.1, umax=3.0)  # fmt: skip
+    if interp != "linear":
+        spec["interp"] = interp
+    c = cases.build(spec)
+    n = len(c["x"])
+    c["t"] = np.where(np.arange(n) % 2 == 0, 0.0, 50.0)
+    # one evaluation of the whole batch
+    fs, ofs = make_fieldset(c), oracle_fieldset(c)
+    x32, y32, z32 = (np.asarray(c[k], dtype=np.float32) for k in "xyz")
+    got = fs.UVW.eval(c["t"], z32, y32, x32)
+    want = po.eval_uvw(ofs, c["t"], z32, y32, x32, None, True)
+    for a, b in zip(got, want):
+        np.testing.assert_array_equal(a, b)
+    alone = fs.UVW.eval(c["t"][::2], z32[::2], y32[::2], x32[::2])  # the first-level particles by themselves: float32 values
+    assert np.any(alone[0] != got[0][::2]) and np.all(alone[0] == alone[0].astype(np.float32))
+    # the whole run
+    ps, err = run_engine(c)
+    pd, oerr = run_oracle(c)
+    assert not err and oerr is None and len(ps) == len(pd["x"])
+    for k in ("particle_id", "state", "t", "ei", "x", "y", "z"):
+        np.testing.assert_array_equal(ps._data[k], pd[k], err_msg=k)
