@@ -286,7 +286,7 @@ typedef struct pb_rk45_args {
                                    update, no batch-level dt clamp of finished particles (mixed lists: the host finishes the iteration) */
     int32_t resume;             /* 1: particle states are NOT reset to Evaluate */
     int32_t hint_all_zero;      /* curvilinear grids, like the pb_advect_args field: the first evaluation of the call skips the hint test */
-    int32_t reserved;
+    int32_t first_eval_two_levels; /* like the pb_advect_args field (float32 grids); applies to the first attempt of the first iteration */
 } pb_rk45_args;
 int32_t pb_advect_rk45(pb_engine* e, const pb_rk45_args* args, double* dt_inout, double* next_dt_inout, pb_report* rep);
 
@@ -315,6 +315,8 @@ typedef struct pb_advdiff_args {
     int64_t max_iters;          /* < 0: run to endtime */
     int32_t kernels_only;       /* 1: the kernel function of ONE loop iteration only (mixed lists, as in pb_advect_args) */
     int32_t resume;             /* 1: particle states are NOT reset to Evaluate (the host drives the loop) */
+    int32_t first_eval_two_levels; /* like the pb_advect_args field (float32 grids): every sample of the first iteration */
+    int32_t reserved;
 } pb_advdiff_args;
 int32_t pb_advect_diffusion(pb_engine* e, const pb_advdiff_args* args, pb_report* rep);
 

@@ -249,7 +249,7 @@ __device__ __forceinline__ void eval_uvw(const GridDev& g, const FieldDev& f, Ev
     using DV = typename decltype(e.cor)::S;  // float64 copies on float64 grids (exact), else the data dtype
     // lenT / lenZ: the batch's decision when known, else the particle's own (zeta > 0 or NaN: a NaN depth must poison the value
     // like a batch-level lerp does)
-    const bool two_t = e.len_t < 0 ? (tau > 0) : (e.len_t != 0);
+    const bool two_t = HAS_TIME && (e.len_t < 0 ? (tau > 0) : (e.len_t != 0));  // (a field without a time axis: tau is all zeros)
     const bool two_z = e.len_z < 0 ? !(zeta <= 0) : (e.len_z != 0);
     if constexpr (MODE == 2 || MODE == 4 || MODE == 5) {
 #ifdef PB_SMEM_CACHE

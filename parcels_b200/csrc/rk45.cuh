@@ -61,7 +61,8 @@ __global__ void __launch_bounds__(PB_BLOCK_THREADS, PB_MINBLOCKS) rk45_kernel(co
                 Val u[6], v[6], wdummy;
                 // curvilinear grids: the reference skips the hint test of a whole batch whose hinted xi are all 0
                 // (index_search.py:269) -- the first evaluation of the call (the host passes hint_all_zero)
-                const bool nohint1 = it == 0 && first_attempt && p.hint_all_zero;
+                const bool first_batch = it == 0 && first_attempt;  // the first attempt of the first iteration: the whole evaluated view
+                const bool nohint1 = first_batch && p.hint_all_zero;
                 first_attempt = false;
                 if constexpr (Policy::RUNTIME_DTYPE) {
                     // ONE eval call site (the policy branches at run time on the position dtype): the six evaluations of the
@@ -79,10 +80,13 @@ __global__ void __launch_bounds__(PB_BLOCK_THREADS, PB_MINBLOCKS) rk45_kernel(co
                             ys = (double)y + sy * dt;
                             ts = t + c[k - 1] * dt;
                         }
+                        if constexpr (Policy::BATCH_LEN_T) e.len_t = (k == 0 && first_batch && p.first_two_levels) ? 1 : -1;
                         Policy::eval_rt(p, e, k == 0 && nohint1, ts, (double)z, ys, xs, /*xy_f32=*/k == 0, /*z_f32=*/true, u[k], v[k], wdummy);
                     }
                 } else {
+                if constexpr (Policy::BATCH_LEN_T) e.len_t = (first_batch && p.first_two_levels) ? 1 : -1;  // see common.cuh, stage 1
                 Policy::template eval<float, float, float>(p, e, nohint1, t, z, y, x, u[0], v[0], wdummy);
+                if constexpr (Policy::BATCH_LEN_T) e.len_t = -1;
 #pragma unroll 1
                 for (int k = 0; k < 5; ++k) {
                     double sx = mulc(u[0], A[k][0]), sy = mulc(v[0], A[k][0]);

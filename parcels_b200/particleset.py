@@ -560,7 +560,8 @@ class ParticleSet:
         def args(max_iters=-1):
             if plan.advdiff is not None:
                 return eng.make_advdiff_args(dt=dt, endtime=endtime, delete_on_error=plan.delete_on_error, seed=self.seed,
-                                             rng_call=self._rng_call, max_iters=max_iters, **plan.advdiff)  # fmt: skip
+                                             rng_call=self._rng_call, max_iters=max_iters, first_eval_two_levels=two_levels,
+                                             **plan.advdiff)  # fmt: skip
             return eng.make_args(plan.scheme, dt, endtime, diffusion=plan.diffusion, delete_on_error=plan.delete_on_error,
                                  kh=plan.kh, kh_spherical=plan.kh_spherical, kh_deg2m=plan.kh_deg2m, seed=self.seed,
                                  rng_call=self._rng_call, max_iters=max_iters, hint_all_zero=hint_all_zero,
@@ -683,8 +684,9 @@ class ParticleSet:
         if self.fieldset.grid.curvilinear:  # batch-level `if np.any(xi)` of the first evaluation (index_search.py:269)
             sign = 1 if dt > 0 else -1
             hint_all_zero = _hint_all_zero(ei_last, lambda s_: sign * (endtime - d["t"][s_]) >= 0, self.fieldset.grid.xdim)
+        two_levels = _first_eval_two_levels(self.fieldset, d["t"], (1 if dt > 0 else -1) * (endtime - d["t"]) >= 0)
         rep = eng.advect_rk45(dt, endtime, tol, min_dt, max_dt, dt_arr, ndt_arr, next_dt_is_f32=d["next_dt"].dtype == np.float32,
-                              delete_on_error=plan.delete_on_error, hint_all_zero=hint_all_zero)  # fmt: skip
+                              delete_on_error=plan.delete_on_error, hint_all_zero=hint_all_zero, first_eval_two_levels=two_levels)  # fmt: skip
         self.last_report = rep
         eng.download_particles(d, ei_last)
         d["ei"][:, -1] = ei_last

@@ -92,6 +92,8 @@ def fuzz_rk45(rng):
         runtime = min(runtime, 0.45 * tmax)  # RK45 waiver: stay inside the time axis
         t0 = 0.0 if dt > 0 else tmax
         c["t"] = np.full(len(c["x"]), t0 + (0.05 * tmax if dt > 0 else -0.05 * tmax))
+        if dt > 0 and rng.random() < 0.4:  # repeated release starting on the first time level: the reference's batch-level lenT
+            c["t"] = np.where(rng.random(len(c["x"])) < 0.5, 0.0, 0.05 * tmax)
     tol = float(rng.choice([1e-4, 1e-2, 1.0]))
     min_dt, max_dt = float(rng.choice([0.5, 5.0])), abs(dt) * float(rng.choice([2, 4]))
     fs = make_fieldset(c)
@@ -143,6 +145,8 @@ def fuzz_advdiff(rng):
     if tmax is not None:
         runtime = min(runtime, 0.9 * tmax)
         c["t"] = np.full(len(c["x"]), 0.0 if dt > 0 else tmax)
+        if dt > 0 and rng.random() < 0.4:  # repeated release starting on the first time level: the reference's batch-level lenT
+            c["t"] = np.where(rng.random(len(c["x"])) < 0.5, 0.0, abs(dt) * float(rng.choice([0.5, 1.0])))
     seed = int(rng.integers(1, 10**6))
     fs = make_fieldset(c)
     fs.add_field("Kh_zonal", kz)
@@ -191,6 +195,8 @@ def fuzz_diffusion(rng):
     if tmax is not None:
         seg_rt = min(seg_rt, 0.9 * tmax / nseg)
         c["t"] = np.full(len(c["x"]), 0.0 if dt > 0 else tmax)
+        if dt > 0 and rng.random() < 0.4:  # repeated release starting on the first time level: the reference's batch-level lenT
+            c["t"] = np.where(rng.random(len(c["x"])) < 0.5, 0.0, abs(dt) * float(rng.choice([0.5, 1.0])))
     seed = int(rng.integers(1, 10**6))
     fs = make_fieldset(c)
     ps = pb.ParticleSet(fs, x=c["x"], y=c["y"], z=c["z"], t=c["t"], seed=seed)
@@ -321,6 +327,8 @@ def fuzz_stepwise(rng):
     if tmax is not None:
         runtime = min(runtime, 0.9 * tmax)
         c["t"] = np.full(len(c["x"]), 0.0 if dt > 0 else tmax)
+        if dt > 0 and rng.random() < 0.4:  # repeated release starting on the first time level: the reference's batch-level lenT
+            c["t"] = np.where(rng.random(len(c["x"])) < 0.5, 0.0, abs(dt) * float(rng.choice([0.5, 1.0])))
     lo, hi = float(c["lon"][1]), float(c["lon"][-2])
 
     def Periodic(particles, fieldset):

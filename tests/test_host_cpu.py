@@ -41,7 +41,7 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(_lib.Report) == 11 * 8 + 2 * 4 + 2 * 4
     assert ctypes.sizeof(_lib.Rk45Args) == 5 * 8 + 8 + 6 * 4
     assert ctypes.sizeof(_lib.ParticleArrays) == 10 * 8
-    assert ctypes.sizeof(_lib.AdvDiffArgs) == 4 * 4 + 4 * 8 + 2 * 8 + 8 + 2 * 4
+    assert ctypes.sizeof(_lib.AdvDiffArgs) == 4 * 4 + 4 * 8 + 2 * 8 + 8 + 4 * 4
 
 
 def _fs(with_w=True):
