@@ -182,6 +182,8 @@ int32_t pb_output_gather(pb_engine* e, int64_t n_selected, int64_t* index, float
 int32_t pb_particles_remove_deleted(pb_engine* e, int64_t* n_left);
 
 /* ---- the hot path: replaces Kernel.execute(pset, endtime, dt) (_core/kernel.py:174-247) -- */
+#define PB_BATCH_FIRST_EVAL_TWO_T 1
+#define PB_BATCH_TWO_Z 2
 typedef struct pb_advect_args {
     int32_t scheme;            /* enum pb_scheme                                                */
     int32_t diffusion;         /* 1: DiffusionUniformKh fused after the advection kernel
@@ -207,11 +209,15 @@ typedef struct pb_advect_args {
                                   and return (dx/dy/dz accumulated, state/ei updated) WITHOUT the position
                                   update, EndofLoop and delete bookkeeping -- the host finishes the iteration
                                   (used when the kernel list also holds user Python kernels)              */
-    int32_t first_eval_two_levels; /* 1: some evaluated particle of the call's FIRST loop iteration is not exactly on the first time
-                                  level (tau > 0) -- the reference then gathers two time levels for the WHOLE batch of that
-                                  evaluation (`lenT = 2 if any(tau > 0)`, _xinterpolators.py:130), which promotes the value of a
-                                  particle AT the first level to float64 (it matters on float32 grids only; later evaluations
-                                  cannot meet tau == 0 again) */
+    int32_t batch_levels;      /* what the reference decides per BATCH of an evaluation and a lane cannot know by itself
+                                  (`lenT = 2 if any(tau > 0)`, `lenZ = 2 if any(zeta > 0)`, _xinterpolators.py:130-131,400-401):
+                                  PB_BATCH_FIRST_EVAL_TWO_T (1): some evaluated particle of the call's FIRST loop iteration is not
+                                    exactly on the first time level -- two time levels for the whole batch of that evaluation,
+                                    which promotes the value of a particle AT the first level to float64 (matters on float32
+                                    grids; tau == 0 exists only at the first level, so later evaluations cannot mix);
+                                  PB_BATCH_TWO_Z (2): some evaluated particle lies below the first depth level -- XFreeslip /
+                                    XPartialslip then test the second depth level for land for EVERY particle, also one that
+                                    sits exactly on the first level (taken as constant over the call) */
 } pb_advect_args;
 
 typedef struct pb_report {
@@ -286,7 +292,7 @@ typedef struct pb_rk45_args {
                                    update, no batch-level dt clamp of finished particles (mixed lists: the host finishes the iteration) */
     int32_t resume;             /* 1: particle states are NOT reset to Evaluate */
     int32_t hint_all_zero;      /* curvilinear grids, like the pb_advect_args field: the first evaluation of the call skips the hint test */
-    int32_t first_eval_two_levels; /* like the pb_advect_args field (float32 grids); applies to the first attempt of the first iteration */
+    int32_t batch_levels;       /* like the pb_advect_args field; the time bit applies to the first attempt of the first iteration */
 } pb_rk45_args;
 int32_t pb_advect_rk45(pb_engine* e, const pb_rk45_args* args, double* dt_inout, double* next_dt_inout, pb_report* rep);
 
@@ -315,7 +321,7 @@ typedef struct pb_advdiff_args {
     int64_t max_iters;          /* < 0: run to endtime */
     int32_t kernels_only;       /* 1: the kernel function of ONE loop iteration only (mixed lists, as in pb_advect_args) */
     int32_t resume;             /* 1: particle states are NOT reset to Evaluate (the host drives the loop) */
-    int32_t first_eval_two_levels; /* like the pb_advect_args field (float32 grids): every sample of the first iteration */
+    int32_t batch_levels;       /* like the pb_advect_args field; the time bit applies to every sample of the first iteration */
     int32_t reserved;
 } pb_advdiff_args;
 int32_t pb_advect_diffusion(pb_engine* e, const pb_advdiff_args* args, pb_report* rep);

@@ -41,7 +41,7 @@ class AdvectArgs(C.Structure):
         ("hint_all_zero", C.c_int32),
         ("resume", C.c_int32),
         ("kernels_only", C.c_int32),
-        ("first_eval_two_levels", C.c_int32),
+        ("batch_levels", C.c_int32),
     ]
 
 
@@ -58,7 +58,7 @@ class Rk45Args(C.Structure):
         ("kernels_only", C.c_int32),
         ("resume", C.c_int32),
         ("hint_all_zero", C.c_int32),
-        ("first_eval_two_levels", C.c_int32),
+        ("batch_levels", C.c_int32),
     ]
 
 
@@ -77,7 +77,7 @@ class AdvDiffArgs(C.Structure):
         ("max_iters", C.c_int64),
         ("kernels_only", C.c_int32),
         ("resume", C.c_int32),
-        ("first_eval_two_levels", C.c_int32),
+        ("batch_levels", C.c_int32),
         ("reserved", C.c_int32),
     ]
 

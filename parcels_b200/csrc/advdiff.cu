@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(PB_BLOCK_THREADS, 2) advdiff_kernel(const AdvD
             if constexpr (std::is_same<A, float>::value) {
                 // float32 grids: every sample of this kernel is taken at the particle's own time with float32 positions; in the
                 // call's first iteration the batch may mix tau == 0 (first time level) with tau > 0: lenT = 2 for all of it
-                const signed char lt = (it == 0 && p.first_two_levels) ? 1 : -1;
+                const signed char lt = (it == 0 && (p.batch_levels & 1)) ? 1 : -1;
                 eu.len_t = lt; ek.len_t = lt;
             }
 

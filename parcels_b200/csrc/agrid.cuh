@@ -380,6 +380,7 @@ struct AGridPolicy {
     static constexpr bool RUNTIME_DTYPE = false;  // interpolation arithmetic is typed on the position dtype
     static constexpr bool F32_STAGES = (MODE == 2);  // nearest node: a stage value can be float32 at a float64 position
     static constexpr bool BATCH_LEN_T = std::is_same<A, float>::value;  // float32 grid: a value's dtype depends on the batch's lenT
+    static constexpr bool BATCH_LEN_Z = (MODE == 1);  // _Spatialslip: the land test looks at lenZ depth levels
     using Ctx = EvalCtx<A, D, NC_>;
     __device__ static __forceinline__ void init(Ctx& e, const AdvectParams&, int ei) {
         e.cx.idx = e.cy.idx = e.cz.idx = e.ct.idx = -100;

@@ -366,6 +366,7 @@ struct CGridPolicy {
     static constexpr bool RUNTIME_DTYPE = false;
     static constexpr bool F32_STAGES = false;
     static constexpr bool BATCH_LEN_T = std::is_same<A, float>::value;
+    static constexpr bool BATCH_LEN_Z = false;
     using Ctx = CGridCtx<A, D>;
 
     __device__ static __forceinline__ void init(Ctx& e, const AdvectParams& p, int ei) {
@@ -532,6 +533,7 @@ struct CurvPolicy {
     static constexpr bool RUNTIME_DTYPE = true;
     static constexpr bool F32_STAGES = false;
     static constexpr bool BATCH_LEN_T = std::is_same<A, float>::value;
+    static constexpr bool BATCH_LEN_Z = false;
     using Ctx = CGridCtx<A, D>;
 
     __device__ static __forceinline__ void init(Ctx& e, const AdvectParams& p, int ei) { CGridPolicy<A, D, NC_>::init(e, p, ei); }

@@ -97,7 +97,7 @@ struct AdvectParams {
                         // the hint for the whole batch at the first eval (index_search.py:269-282)
     int resume;         // 1: continue a Kernel.execute call after a migration (states are NOT reset to Evaluate)
     int kernels_only;   // 1: one iteration's kernel functions only; the host does the position update etc.
-    int first_two_levels;  // the batch of the call's first evaluation has some tau > 0: lenT = 2 for every particle of it
+    int batch_levels;  // PB_BATCH_* bits: what the reference decides per batch of an evaluation (lenT of the first one, lenZ)
     ReportDev* rep;
 };
 
@@ -250,6 +250,9 @@ __global__ void __launch_bounds__(PB_BLOCK_THREADS, PB_MINBLOCKS) advect_kernel(
         e.state = p.resume ? p.P.state[i] : (int)PB_EVALUATE;  // kernel.py:188
         e.refills = 0;
         e.out_of_time = false;
+        if constexpr (Policy::BATCH_LEN_Z) {  // slip interpolators: the land test looks at the batch's depth levels
+            if (p.batch_levels & PB_BATCH_TWO_Z) e.len_z = 1;
+        }
 
         const int sign = p.dt > 0 ? 1 : -1;
         constexpr bool three_d = (Policy::NC == 3);  // RK4_3D / RK2_3D sample fieldset.UVW, the others fieldset.UV
@@ -303,7 +306,7 @@ __global__ void __launch_bounds__(PB_BLOCK_THREADS, PB_MINBLOCKS) advect_kernel(
                     const double ys = first ? (double)y : (double)y + (full ? vk.v : half_of(vk)) * dtp;
                     const double zs = (first || !three_d) ? (double)z : (double)z + (full ? wk.v : half_of(wk)) * dtp;
                     const double ts = first ? t : t + (full ? dtp : 0.5 * dtp);
-                    if constexpr (Policy::BATCH_LEN_T) e.len_t = (first && it == 0 && p.first_two_levels) ? 1 : -1;
+                    if constexpr (Policy::BATCH_LEN_T) e.len_t = (first && it == 0 && (p.batch_levels & 1)) ? 1 : -1;
                     Policy::eval_rt(p, e, first && nohint1, ts, zs, ys, xs, /*xy_f32=*/first, /*z_f32=*/first || !three_d, uk, vk, wk);
                     if (first) { su = uk.v; sv = vk.v; sw = wk.v; }
                     else if (nstage == 4) {
@@ -315,7 +318,7 @@ __global__ void __launch_bounds__(PB_BLOCK_THREADS, PB_MINBLOCKS) advect_kernel(
             u1 = Val{0.0, false}; v1 = u1; w1 = u1;
             // float32 grids: the value dtype of this evaluation depends on the BATCH's lenT (only the call's first iteration can
             // hold a particle with tau == 0, i.e. exactly on the first time level; the host knows whether the others are too)
-            if constexpr (Policy::BATCH_LEN_T) e.len_t = (it == 0 && p.first_two_levels) ? 1 : -1;
+            if constexpr (Policy::BATCH_LEN_T) e.len_t = (it == 0 && (p.batch_levels & 1)) ? 1 : -1;
             if (nstage > 0) Policy::template eval<float, float, float>(p, e, nohint1, t, z, y, x, u1, v1, w1);
             if constexpr (Policy::BATCH_LEN_T) e.len_t = -1;
             su = u1.v; sv = v1.v; sw = w1.v;

@@ -871,7 +871,7 @@ static int32_t prepare_advect(pb_engine* e, const pb_advect_args* a, AdvectParam
     p.hint_all_zero = a->hint_all_zero;
     p.resume = a->resume;
     p.kernels_only = a->kernels_only;
-    p.first_two_levels = a->first_eval_two_levels;
+    p.batch_levels = a->batch_levels;
     p.g.off_x = e->g.off_x; p.g.off_y = e->g.off_y; p.g.off_z = e->g.off_z;
     p.rep = e->d_rep;
     return PB_OK;
@@ -1071,7 +1071,7 @@ int32_t pb_advect_rk45(pb_engine* e, const pb_rk45_args* a, double* dt_inout, do
     p.kernels_only = a->kernels_only; p.resume = a->resume;
     p.dt = a->dt; p.endtime = a->endtime; p.max_iters = a->max_iters;
     p.hint_all_zero = a->hint_all_zero;
-    p.first_two_levels = a->first_eval_two_levels;
+    p.batch_levels = a->batch_levels;
     p.g.off_x = e->g.off_x; p.g.off_y = e->g.off_y; p.g.off_z = e->g.off_z;
     p.rep = e->d_rep;
     zero_report(*e->h_rep);
@@ -1142,7 +1142,7 @@ int32_t pb_advect_diffusion(pb_engine* e, const pb_advdiff_args* a, pb_report* r
     p.dt = a->dt; p.endtime = a->endtime; p.max_iters = a->max_iters;
     p.seed = a->seed; p.rng_call = a->rng_call;
     p.kernels_only = a->kernels_only; p.resume = a->resume;
-    p.first_two_levels = a->first_eval_two_levels;
+    p.batch_levels = a->batch_levels;
     p.rep = e->d_rep;
     zero_report(*e->h_rep);
     CK(cudaMemcpyAsync(e->d_rep, e->h_rep, sizeof(ReportDev), cudaMemcpyHostToDevice, e->stream));

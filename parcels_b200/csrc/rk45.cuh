@@ -43,6 +43,9 @@ __global__ void __launch_bounds__(PB_BLOCK_THREADS, PB_MINBLOCKS) rk45_kernel(co
         e.state = p.resume ? p.P.state[i] : (int)PB_EVALUATE;  // kernel.py:188
         e.refills = 0;
         e.out_of_time = false;
+        if constexpr (Policy::BATCH_LEN_Z) {
+            if (p.batch_levels & PB_BATCH_TWO_Z) e.len_z = 1;
+        }
         const int sign = p.dt > 0 ? 1 : -1;  // compute_time_direction (kernel.py:186)
         bool first_attempt = true;
         long long it = 0;
@@ -80,11 +83,11 @@ __global__ void __launch_bounds__(PB_BLOCK_THREADS, PB_MINBLOCKS) rk45_kernel(co
                             ys = (double)y + sy * dt;
                             ts = t + c[k - 1] * dt;
                         }
-                        if constexpr (Policy::BATCH_LEN_T) e.len_t = (k == 0 && first_batch && p.first_two_levels) ? 1 : -1;
+                        if constexpr (Policy::BATCH_LEN_T) e.len_t = (k == 0 && first_batch && (p.batch_levels & 1)) ? 1 : -1;
                         Policy::eval_rt(p, e, k == 0 && nohint1, ts, (double)z, ys, xs, /*xy_f32=*/k == 0, /*z_f32=*/true, u[k], v[k], wdummy);
                     }
                 } else {
-                if constexpr (Policy::BATCH_LEN_T) e.len_t = (first_batch && p.first_two_levels) ? 1 : -1;  // see common.cuh, stage 1
+                if constexpr (Policy::BATCH_LEN_T) e.len_t = (first_batch && (p.batch_levels & 1)) ? 1 : -1;  // see common.cuh, stage 1
                 Policy::template eval<float, float, float>(p, e, nohint1, t, z, y, x, u[0], v[0], wdummy);
                 if constexpr (Policy::BATCH_LEN_T) e.len_t = -1;
 #pragma unroll 1

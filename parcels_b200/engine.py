@@ -195,10 +195,10 @@ class Engine:
     @staticmethod
     def make_args(scheme, dt, endtime, *, diffusion=False, delete_on_error=False, kh=(0.0, 0.0), kh_spherical=False,
                   kh_deg2m=1.0, seed=0, rng_call=0, max_iters=-1, hint_all_zero=False, resume=False, kernels_only=False,
-                  first_eval_two_levels=False) -> AdvectArgs:  # fmt: skip
+                  batch_levels=0) -> AdvectArgs:  # fmt: skip
         return AdvectArgs(int(scheme), int(diffusion), int(delete_on_error), int(kh_spherical), float(dt), float(endtime),
                           float(kh[0]), float(kh[1]), float(kh_deg2m), int(seed), int(rng_call), int(max_iters),
-                          int(bool(hint_all_zero)), int(bool(resume)), int(bool(kernels_only)), int(bool(first_eval_two_levels)))  # fmt: skip
+                          int(bool(hint_all_zero)), int(bool(resume)), int(bool(kernels_only)), int(batch_levels))  # fmt: skip
 
     def advect(self, args) -> dict:
         """``Kernel.execute`` on the device: ``args`` from :meth:`make_args` (pb_advect) or :meth:`make_advdiff_args`
@@ -214,22 +214,22 @@ class Engine:
 
     @staticmethod
     def make_advdiff_args(scheme, dt, endtime, *, kh_slots, dres, deg2m_sq, delete_on_error=False, seed=0, rng_call=0, max_iters=-1,
-                          kernels_only=False, resume=False, first_eval_two_levels=False):
+                          kernels_only=False, resume=False, batch_levels=0):
         from ._lib import AdvDiffArgs
 
         return AdvDiffArgs(int(scheme), int(delete_on_error), int(kh_slots[0]), int(kh_slots[1]), float(dt), float(endtime),
                            float(dres), float(deg2m_sq), int(seed), int(rng_call), int(max_iters), int(bool(kernels_only)),
-                           int(bool(resume)), int(bool(first_eval_two_levels)), 0)  # fmt: skip
+                           int(bool(resume)), int(batch_levels), 0)  # fmt: skip
 
     def advect_rk45(self, dt, endtime, tol, min_dt, max_dt, dt_arr, next_dt_arr, *, next_dt_is_f32=True, delete_on_error=False,
-                    max_iters=-1, kernels_only=False, resume=False, hint_all_zero=False, first_eval_two_levels=False) -> dict:
+                    max_iters=-1, kernels_only=False, resume=False, hint_all_zero=False, batch_levels=0) -> dict:
         """AdvectionRK45 + Repeat / next_dt state machine; ``dt_arr`` / ``next_dt_arr`` (float64, C-contiguous) are
         updated in place to what the reference leaves in particles.dt / particles.next_dt."""
         from ._lib import Rk45Args
 
         a = Rk45Args(float(dt), float(endtime), float(tol), float(min_dt), float(max_dt), int(max_iters), int(next_dt_is_f32),
                      int(delete_on_error), int(bool(kernels_only)), int(bool(resume)), int(bool(hint_all_zero)),
-                     int(bool(first_eval_two_levels)))  # fmt: skip
+                     int(batch_levels))  # fmt: skip
         rep = Report()
         check(self._lib.pb_advect_rk45(self._h, C.byref(a), ptr(dt_arr), ptr(next_dt_arr), C.byref(rep)))
         return _report_dict(rep)

@@ -48,6 +48,20 @@ def _first_eval_two_levels(fieldset, t, evaluated) -> bool:
     return bool(te.size) and bool(np.any(te != float(fieldset._time_s[0])))
 
 
+def _batch_levels(fieldset, d, evaluated) -> int:
+    """``pb_advect_args.batch_levels``: the reference's per-batch decisions a lane cannot make by itself.
+    PB_BATCH_FIRST_EVAL_TWO_T (1): see `_first_eval_two_levels`.  PB_BATCH_TWO_Z (2): `lenZ = 2 if any(zeta > 0)`
+    (_xinterpolators.py:401) -- with XFreeslip / XPartialslip the land test then looks at the second depth level for every particle
+    of the batch (:426-447); zeta > 0 means below the first depth level (left-sided search), taken as constant over the call."""
+    flags = 1 if _first_eval_two_levels(fieldset, d["t"], evaluated) else 0
+    depth = fieldset.grid.depth
+    if fieldset.interp_method in ("freeslip", "partialslip") and depth is not None and len(depth) > 1:
+        ze = d["z"][evaluated]
+        if ze.size and np.any(ze > depth[0]):
+            flags |= 2
+    return flags
+
+
 def _hint_all_zero(ei_last, evaluated, xdim) -> bool:
     """Curvilinear grids: True when the hinted xi (= ei % xdim) of EVERY evaluated particle is 0 -- the reference then skips
     the hint test for the whole batch (`if np.any(xi)`, _core/index_search.py:269).  `evaluated(slice)` gives the mask of a
@@ -555,17 +569,21 @@ class ParticleSet:
             sign = 1 if dt > 0 else -1
             hint_all_zero = _hint_all_zero(ei_last, lambda s_: sign * (endtime - d["t"][s_]) >= 0, g.xdim)
 
-        two_levels = (not on_device) and _first_eval_two_levels(self.fieldset, d["t"], (1 if dt > 0 else -1) * (endtime - d["t"]) >= 0)
+        if on_device:  # a resident interval: no particle can be back on the first time level; the depth bit of the first interval holds
+            two_levels = self.__dict__.get("_batch_levels_resident", 0) & 2
+        else:
+            two_levels = _batch_levels(self.fieldset, d, (1 if dt > 0 else -1) * (endtime - d["t"]) >= 0)
+            self.__dict__["_batch_levels_resident"] = two_levels
 
         def args(max_iters=-1):
             if plan.advdiff is not None:
                 return eng.make_advdiff_args(dt=dt, endtime=endtime, delete_on_error=plan.delete_on_error, seed=self.seed,
-                                             rng_call=self._rng_call, max_iters=max_iters, first_eval_two_levels=two_levels,
+                                             rng_call=self._rng_call, max_iters=max_iters, batch_levels=two_levels,
                                              **plan.advdiff)  # fmt: skip
             return eng.make_args(plan.scheme, dt, endtime, diffusion=plan.diffusion, delete_on_error=plan.delete_on_error,
                                  kh=plan.kh, kh_spherical=plan.kh_spherical, kh_deg2m=plan.kh_deg2m, seed=self.seed,
                                  rng_call=self._rng_call, max_iters=max_iters, hint_all_zero=hint_all_zero,
-                                 first_eval_two_levels=two_levels)  # fmt: skip
+                                 batch_levels=two_levels)  # fmt: skip
 
         needs_upload = not on_device and not (resident and self._device_synced and eng.particle_count() == n)
         # host arrays in (and out): cut into chunks whose copies run under the kernels of the other chunks (pb_advect_host)
@@ -684,9 +702,9 @@ class ParticleSet:
         if self.fieldset.grid.curvilinear:  # batch-level `if np.any(xi)` of the first evaluation (index_search.py:269)
             sign = 1 if dt > 0 else -1
             hint_all_zero = _hint_all_zero(ei_last, lambda s_: sign * (endtime - d["t"][s_]) >= 0, self.fieldset.grid.xdim)
-        two_levels = _first_eval_two_levels(self.fieldset, d["t"], (1 if dt > 0 else -1) * (endtime - d["t"]) >= 0)
+        two_levels = _batch_levels(self.fieldset, d, (1 if dt > 0 else -1) * (endtime - d["t"]) >= 0)
         rep = eng.advect_rk45(dt, endtime, tol, min_dt, max_dt, dt_arr, ndt_arr, next_dt_is_f32=d["next_dt"].dtype == np.float32,
-                              delete_on_error=plan.delete_on_error, hint_all_zero=hint_all_zero, first_eval_two_levels=two_levels)  # fmt: skip
+                              delete_on_error=plan.delete_on_error, hint_all_zero=hint_all_zero, batch_levels=two_levels)  # fmt: skip
         self.last_report = rep
         eng.download_particles(d, ei_last)
         d["ei"][:, -1] = ei_last

@@ -92,20 +92,20 @@ def _device_kernels(pset, eng, item, dt, endtime):
             ei_last, lambda s_: np.isin(d["state"][s_], [StatusCode.Success, StatusCode.Evaluate]) & (sign * (endtime - d["t"][s_]) >= 0), g.xdim
         )
     eng.upload_particles(d, ei_last)
-    from .particleset import _first_eval_two_levels
+    from .particleset import _batch_levels
 
     sign_ = 1 if dt > 0 else -1
-    two_levels = _first_eval_two_levels(
-        pset.fieldset, d["t"], np.isin(d["state"], [StatusCode.Success, StatusCode.Evaluate]) & (sign_ * (endtime - d["t"]) >= 0)
+    two_levels = _batch_levels(
+        pset.fieldset, d, np.isin(d["state"], [StatusCode.Success, StatusCode.Evaluate]) & (sign_ * (endtime - d["t"]) >= 0)
     )
     if item[0] == "advdiff":  # AdvectionDiffusionM1 / EM (pb_advect_diffusion)
         args = eng.make_advdiff_args(dt=dt, endtime=endtime, seed=pset.seed, rng_call=pset._rng_call, resume=True, kernels_only=True,
-                                     first_eval_two_levels=two_levels, **item[1])  # fmt: skip
+                                     batch_levels=two_levels, **item[1])  # fmt: skip
     else:
         _, scheme, diffusion, plan = item
         args = eng.make_args(scheme, dt, endtime, diffusion=diffusion, kh=plan.kh, kh_spherical=plan.kh_spherical,
                              kh_deg2m=plan.kh_deg2m, seed=pset.seed, rng_call=pset._rng_call, hint_all_zero=hint_all_zero,
-                             resume=True, kernels_only=True, first_eval_two_levels=two_levels)  # fmt: skip
+                             resume=True, kernels_only=True, batch_levels=two_levels)  # fmt: skip
     rep = eng.advect(args)
     eng.download_particles(d, ei_last)
     d["ei"][:, -1] = ei_last
@@ -136,14 +136,14 @@ def _device_rk45(pset, eng, params, dt, endtime):
         hint_all_zero = _hint_all_zero(
             ei_last, lambda s_: np.isin(d["state"][s_], [StatusCode.Success, StatusCode.Evaluate]) & (sign * (endtime - d["t"][s_]) >= 0), g.xdim
         )
-    from .particleset import _first_eval_two_levels
+    from .particleset import _batch_levels
 
     sign_ = 1 if dt > 0 else -1
-    two_levels = _first_eval_two_levels(
-        pset.fieldset, d["t"], np.isin(d["state"], [StatusCode.Success, StatusCode.Evaluate]) & (sign_ * (endtime - d["t"]) >= 0)
+    two_levels = _batch_levels(
+        pset.fieldset, d, np.isin(d["state"], [StatusCode.Success, StatusCode.Evaluate]) & (sign_ * (endtime - d["t"]) >= 0)
     )
     rep = eng.advect_rk45(dt, endtime, tol, min_dt, max_dt, dt_arr, ndt_arr, next_dt_is_f32=d["next_dt"].dtype == np.float32,
-                          kernels_only=True, resume=True, hint_all_zero=hint_all_zero, first_eval_two_levels=two_levels)  # fmt: skip
+                          kernels_only=True, resume=True, hint_all_zero=hint_all_zero, batch_levels=two_levels)  # fmt: skip
     eng.download_particles(d, ei_last)
     d["ei"][:, -1] = ei_last
     d["dt"][:] = dt_arr

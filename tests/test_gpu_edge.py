@@ -187,3 +187,37 @@ def test_first_level_particles_in_a_mixed_batch_are_promoted_like_the_reference(
     assert not err and oerr is None and len(ps) == len(pd["x"])
     for k in ("particle_id", "state", "t", "ei", "x", "y", "z"):
         np.testing.assert_array_equal(ps._data[k], pd[k], err_msg=k)
+
+
+@pytest.mark.parametrize("interp", ["freeslip", "partialslip"])
+def test_slip_land_test_uses_the_depth_levels_of_the_batch(interp):
+    """XFreeslip / XPartialslip look for land on `lenZ` depth levels, and the reference decides `lenZ = 2 if any(zeta > 0)` per
+    batch (_xinterpolators.py:401,426-447): a particle exactly on the first depth level is treated differently when another
+    particle of the set lies deeper.  Field with 'land' (U = V = 0) at the first depth level only; half of the particles on that
+    level, half between the first two: bit-exact against the oracle (the host passes PB_BATCH_TWO_Z)."""
+    import cases
+    from engine_run import run_engine
+    from oracle_run import run_oracle
+
+    c = cases.build(dict(cases.CASES["freeslip_surface"], interp=interp, n=1500, land=False))
+    U, V = c["U"].copy(), c["V"].copy()
+    half = U.shape[2] // 2
+    U[:, 0, :half, :] = 0
+    V[:, 0, :half, :] = 0
+    c["U"], c["V"] = U, V
+    depth = np.asarray(c["depth"], dtype=np.float64)
+    c["z"] = np.where(np.arange(len(c["x"])) % 2 == 0, depth[0], 0.5 * (depth[0] + depth[1]))
+    ps, err = run_engine(c)
+    pd, oerr = run_oracle(c)
+    assert not err and oerr is None and len(ps) == len(pd["x"])
+    for k in ("particle_id", "state", "t", "ei", "x", "y", "z"):
+        np.testing.assert_array_equal(ps._data[k], pd[k], err_msg=k)
+    # ... and it is not a no-op: the first-level particles alone (lenZ == 1) end somewhere else
+    alone = dict(c)
+    for k in ("x", "y", "z", "t"):
+        alone[k] = np.asarray(c[k])[::2]
+    ps1, _ = run_engine(alone)
+    first = ps._data["particle_id"] % 2 == 0
+    ids = ps._data["particle_id"][first] // 2
+    keep = np.isin(ids, ps1._data["particle_id"])
+    assert np.any(ps._data["x"][first][keep] != ps1._data["x"][np.searchsorted(ps1._data["particle_id"], ids[keep])])
