@@ -44,7 +44,7 @@ def _first_eval_two_levels(fieldset, t, evaluated) -> bool:
     barycentric coordinate is float64 and the promotion changes nothing."""
     if fieldset._time_s is None or fieldset.grid.lon.dtype != np.float32:
         return False
-    te = t[evaluated]
+    te = t[evaluated() if callable(evaluated) else evaluated]
     return bool(te.size) and bool(np.any(te != float(fieldset._time_s[0])))
 
 
@@ -53,10 +53,10 @@ def _batch_levels(fieldset, d, evaluated) -> int:
     PB_BATCH_FIRST_EVAL_TWO_T (1): see `_first_eval_two_levels`.  PB_BATCH_TWO_Z (2): `lenZ = 2 if any(zeta > 0)`
     (_xinterpolators.py:401) -- with XFreeslip / XPartialslip the land test then looks at the second depth level for every particle
     of the batch (:426-447); zeta > 0 means below the first depth level (left-sided search), taken as constant over the call."""
-    flags = 1 if _first_eval_two_levels(fieldset, d["t"], evaluated) else 0
+    flags = 1 if _first_eval_two_levels(fieldset, d["t"], evaluated) else 0  # (`evaluated`: mask, or a callable making it on demand)
     depth = fieldset.grid.depth
     if fieldset.interp_method in ("freeslip", "partialslip") and depth is not None and len(depth) > 1:
-        ze = d["z"][evaluated]
+        ze = d["z"][evaluated() if callable(evaluated) else evaluated]
         if ze.size and np.any(ze > depth[0]):
             flags |= 2
     return flags
@@ -572,7 +572,7 @@ class ParticleSet:
         if on_device:  # a resident interval: no particle can be back on the first time level; the depth bit of the first interval holds
             two_levels = self.__dict__.get("_batch_levels_resident", 0) & 2
         else:
-            two_levels = _batch_levels(self.fieldset, d, (1 if dt > 0 else -1) * (endtime - d["t"]) >= 0)
+            two_levels = _batch_levels(self.fieldset, d, lambda: (1 if dt > 0 else -1) * (endtime - d["t"]) >= 0)
             self.__dict__["_batch_levels_resident"] = two_levels
 
         def args(max_iters=-1):
@@ -641,6 +641,7 @@ class ParticleSet:
             deletions = rep["n_deleted"] > 0 or rep["max_state"] == StatusCode.Delete
             self._n_device = eng.remove_deleted() if deletions else n
             if downloaded and not deletions:  # the pipelined call has already brought the result back: host == device
+                self._host_stale = False
                 d["ei"][:, -1] = ei_last
                 d["dt"][:] = dt  # kernel.py:225-226
                 self._device_synced = True
@@ -702,7 +703,7 @@ class ParticleSet:
         if self.fieldset.grid.curvilinear:  # batch-level `if np.any(xi)` of the first evaluation (index_search.py:269)
             sign = 1 if dt > 0 else -1
             hint_all_zero = _hint_all_zero(ei_last, lambda s_: sign * (endtime - d["t"][s_]) >= 0, self.fieldset.grid.xdim)
-        two_levels = _batch_levels(self.fieldset, d, (1 if dt > 0 else -1) * (endtime - d["t"]) >= 0)
+        two_levels = _batch_levels(self.fieldset, d, lambda: (1 if dt > 0 else -1) * (endtime - d["t"]) >= 0)
         rep = eng.advect_rk45(dt, endtime, tol, min_dt, max_dt, dt_arr, ndt_arr, next_dt_is_f32=d["next_dt"].dtype == np.float32,
                               delete_on_error=plan.delete_on_error, hint_all_zero=hint_all_zero, batch_levels=two_levels)  # fmt: skip
         self.last_report = rep

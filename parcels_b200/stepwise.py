@@ -96,7 +96,7 @@ def _device_kernels(pset, eng, item, dt, endtime):
 
     sign_ = 1 if dt > 0 else -1
     two_levels = _batch_levels(
-        pset.fieldset, d, np.isin(d["state"], [StatusCode.Success, StatusCode.Evaluate]) & (sign_ * (endtime - d["t"]) >= 0)
+        pset.fieldset, d, lambda: np.isin(d["state"], [StatusCode.Success, StatusCode.Evaluate]) & (sign_ * (endtime - d["t"]) >= 0)
     )
     if item[0] == "advdiff":  # AdvectionDiffusionM1 / EM (pb_advect_diffusion)
         args = eng.make_advdiff_args(dt=dt, endtime=endtime, seed=pset.seed, rng_call=pset._rng_call, resume=True, kernels_only=True,
@@ -140,7 +140,7 @@ def _device_rk45(pset, eng, params, dt, endtime):
 
     sign_ = 1 if dt > 0 else -1
     two_levels = _batch_levels(
-        pset.fieldset, d, np.isin(d["state"], [StatusCode.Success, StatusCode.Evaluate]) & (sign_ * (endtime - d["t"]) >= 0)
+        pset.fieldset, d, lambda: np.isin(d["state"], [StatusCode.Success, StatusCode.Evaluate]) & (sign_ * (endtime - d["t"]) >= 0)
     )
     rep = eng.advect_rk45(dt, endtime, tol, min_dt, max_dt, dt_arr, ndt_arr, next_dt_is_f32=d["next_dt"].dtype == np.float32,
                           kernels_only=True, resume=True, hint_all_zero=hint_all_zero, batch_levels=two_levels)  # fmt: skip
