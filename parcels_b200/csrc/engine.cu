@@ -451,8 +451,9 @@ int32_t pb_grid_upload_rectilinear(pb_engine* e, const void* lon, int64_t nx, co
                                    int64_t nt, int32_t spherical, double deg2m, int64_t xdim_cells,
                                    int64_t ydim_cells, int64_t zdim_cells) {
     if (!e) return fail(PB_ERR_INVALID, "engine is NULL");
-    if (!lon || !lat || nx < 2 || ny < 2)
-        return fail(PB_ERR_INVALID, "rectilinear grid needs lon and lat with >= 2 nodes (got nx=%lld ny=%lld)", (long long)nx, (long long)ny);
+    // a length-1 axis is allowed: the 1-D search returns index 0, coordinate 0 there (index_search.py:45-46)
+    if (!lon || !lat || nx < 1 || ny < 1)
+        return fail(PB_ERR_INVALID, "rectilinear grid needs lon and lat nodes (got nx=%lld ny=%lld)", (long long)nx, (long long)ny);
     if (nx > INT_MAX || ny > INT_MAX || nz > INT_MAX || nt > INT_MAX) return fail(PB_ERR_INVALID, "axis too long");
     CK(cudaSetDevice(e->device));
     const size_t es = coord_is_f64 ? 8 : 4;

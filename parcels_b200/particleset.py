@@ -27,6 +27,8 @@ def _to_float_seconds(v):
         return v.total_seconds()
     if isinstance(v, np.timedelta64):
         return float(v / np.timedelta64(1, "s"))
+    if isinstance(v, (np.datetime64, datetime.datetime)):
+        raise TypeError(f"a point in time is not a duration: {v!r}")
     return float(v)
 
 
@@ -768,7 +770,10 @@ class ParticleSet:
             raise ValueError(f"dt must be a non-zero datetime.timedelta or np.timedelta64 object, got {dt=!r}") from e
         self._data["dt"][:] = dt
         if runtime is not None:
-            runtime = _to_float_seconds(runtime)
+            try:
+                runtime = _to_float_seconds(runtime)
+            except (ValueError, TypeError) as e:  # reference _core/particleset.py:510-518
+                raise ValueError(f"The runtime must be a datetime.timedelta, np.timedelta64 or float object. Got {type(runtime)}") from e
             if runtime < 0:
                 raise ValueError(f"The runtime must be a non-negative timedelta or float. Got {runtime=!r}")
         ti = self.fieldset.time_interval
@@ -784,10 +789,18 @@ class ParticleSet:
         if any_nan:
             first = (np.nanmin(t) if sign_dt == 1 else np.nanmax(t)) if not np.isnan(t).all() else np.nan
         if endtime is not None:
-            if isinstance(endtime, np.datetime64):
-                endtime = float((endtime - self.fieldset._time_origin) / np.timedelta64(1, "s"))
-            else:
-                endtime = _to_float_seconds(endtime)
+            origin = self.fieldset._time_origin
+            stamped = isinstance(origin, (np.datetime64, np.timedelta64))
+            if stamped and type(endtime) is not type(origin):  # reference _core/particleset.py:545-549
+                raise ValueError(f"The endtime must be of the same type as the fieldset.time_interval start time. Got {endtime=!r} "
+                                 f"with a time axis starting at {origin!r}")
+            if stamped:
+                endtime = float((endtime - origin) / np.timedelta64(1, "s"))
+            else:  # a time axis given in seconds (this package's from_arrays): seconds
+                try:
+                    endtime = _to_float_seconds(endtime)
+                except TypeError as e:
+                    raise ValueError(f"The endtime must be of the same type as the fieldset.time_interval start time. Got {endtime=!r}") from e
             if ti is not None and not (ti[0] <= endtime <= ti[1]):
                 raise ValueError(f"Calculated/provided end time of {endtime!r} is not in fieldset time interval {ti!r}.")
         if np.isnan(first):

@@ -221,3 +221,30 @@ def test_slip_land_test_uses_the_depth_levels_of_the_batch(interp):
     ids = ps._data["particle_id"][first] // 2
     keep = np.isin(ids, ps1._data["particle_id"])
     assert np.any(ps._data["x"][first][keep] != ps1._data["x"][np.searchsorted(ps1._data["particle_id"], ids[keep])])
+
+
+@pytest.mark.parametrize("nx, ny, nz", [(1, 7, 5), (9, 1, 5), (1, 1, 4), (6, 7, 1)])
+@pytest.mark.parametrize("cdtype", [np.float32, np.float64])
+def test_axes_of_length_one(nx, ny, nz, cdtype):
+    """A coordinate axis with a single node: the reference's 1-D search returns index 0, coordinate 0 there
+    (index_search.py:45-46), every position is 'inside', the field is constant along that axis (reference
+    tests/test_advection.py::test_length1dimensions; the oracle agrees with the reference itself bit for bit on such grids)."""
+    from oracle import parcels_oracle as po
+
+    rng = np.random.default_rng(3)
+    lon = np.linspace(0, 4, nx).astype(cdtype) if nx > 1 else np.array([1.5], dtype=cdtype)
+    lat = np.linspace(0, 3, ny).astype(cdtype) if ny > 1 else np.array([0.5], dtype=cdtype)
+    depth = np.linspace(0, 10, nz).astype(cdtype) if nz > 1 else np.array([0.0], dtype=cdtype)
+    times = np.array([0.0, 100.0, 200.0])
+    U, V, W = (rng.uniform(-0.01, 0.01, (3, nz, ny, nx)).astype(np.float32) for _ in range(3))
+    n = 50
+    x, y, z = rng.uniform(0.2, 3.8, n), rng.uniform(0.2, 2.8, n), rng.uniform(0.5, 9.5, n)
+    fs = pb.FieldSet.from_arrays(lon=lon, lat=lat, depth=depth, time=times, U=U, V=V, W=W, mesh="flat")
+    ps = pb.ParticleSet(fs, x=x, y=y, z=z, t=np.zeros(n))
+    ps.execute([pb.AdvectionRK4_3D, pb.DeleteParticle], dt=10.0, runtime=150.0)
+    ofs = po.OFieldSet(po.OGrid(lon, lat, depth, mesh="flat"), U, V, W, time=times)
+    pd = po.create_particle_data(x, y, z, np.zeros(n))
+    po.pset_execute(pd, ofs, [po.AdvectionRK4_3D, po.DeleteOnError], 10.0, runtime=150.0)
+    assert len(ps) == len(pd["x"]) > 0
+    for k in ("particle_id", "state", "t", "ei", "x", "y", "z"):
+        np.testing.assert_array_equal(ps._data[k], pd[k], err_msg=k)
