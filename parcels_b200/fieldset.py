@@ -179,6 +179,8 @@ class VectorField:
             device = next(iter(fs._engines), 0)
         z, y, x = (np.atleast_1d(a.__array__() if hasattr(a, "__array__") else a) for a in (z, y, x))
         t = np.atleast_1d(t.__array__() if hasattr(t, "__array__") else t)
+        if np.issubdtype(t.dtype, np.floating) and np.any(np.isnan(t)):  # reference _core/field.py:396-398
+            raise ValueError(f"Time values for particles with indices {np.where(np.isnan(t))[0]} cannot be NaN.")
         if positions_are_f32 is None:
             positions_are_f32 = all(a.dtype == np.float32 for a in (z, y, x))
         hint = None

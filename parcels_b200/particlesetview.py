@@ -94,7 +94,9 @@ class ParticleSetView:
         data = object.__getattribute__(self, "_data")
         if name in data:
             return ParticleSetViewArray(data, self._index, name)
-        raise AttributeError(name)
+        if name.startswith("_"):
+            raise AttributeError(name)
+        raise KeyError(name)  # like the reference's `self._data[name]` (_core/particlesetview.py:28): an unknown Variable
 
     def __setattr__(self, name, value):
         if isinstance(value, ParticleSetViewArray):
