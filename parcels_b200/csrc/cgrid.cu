@@ -583,7 +583,10 @@ struct CurvPolicy {
         }
         double xsi = -1.0, eta = -1.0;
         int yi, xi;
-        const bool hint_ok = !no_hint && e.yi >= 0 && e.xi >= 0 && e.yi < g.ny - 1 && e.xi < g.nx - 1;
+        // `if np.any(xi)` (index_search.py:269): a batch whose hinted xi are ALL zero skips the hint test.  The host knows that for
+        // the first evaluation of a call (no_hint); a set of ONE particle knows it by itself at every evaluation.
+        const bool lone_zero = p.lone_particle && e.xi == 0;
+        const bool hint_ok = !no_hint && !lone_zero && e.yi >= 0 && e.xi >= 0 && e.yi < g.ny - 1 && e.xi < g.nx - 1;
         bool found = false;
         if (hint_ok) found = point_in_cell(g, e, e.yi, e.xi, q, xsi, eta);
         if (found) {

@@ -98,6 +98,8 @@ struct AdvectParams {
     int resume;         // 1: continue a Kernel.execute call after a migration (states are NOT reset to Evaluate)
     int kernels_only;   // 1: one iteration's kernel functions only; the host does the position update etc.
     int batch_levels;  // PB_BATCH_* bits: what the reference decides per batch of an evaluation (lenT of the first one, lenZ)
+    int lone_particle; // the whole set is ONE particle (not: this launch's chunk): it is its own batch for `if np.any(xi)` (cgrid.cu)
+    int pad2_;
     ReportDev* rep;
 };
 

@@ -894,6 +894,7 @@ int32_t pb_advect_async(pb_engine* e, const pb_advect_args* a) {
     CK(cudaSetDevice(e->device));
     p.P = ParticlesDev{(float*)e->px.p, (float*)e->py.p, (float*)e->pz.p, (float*)e->pdx.p, (float*)e->pdy.p,
                        (float*)e->pdz.p, (double*)e->pt.p, (int*)e->pstate.p, (int*)e->pei.p, (long long*)e->ppid.p, e->n};
+    p.lone_particle = e->n == 1;
     zero_report(*e->h_rep);
     CK(cudaMemcpyAsync(e->d_rep, e->h_rep, sizeof(ReportDev), cudaMemcpyHostToDevice, e->stream));
     CK(cudaEventRecord(e->ev0, e->stream));
@@ -943,6 +944,7 @@ int32_t pb_advect_host(pb_engine* e, const pb_advect_args* a, int64_t n, const p
     if ((rc = e->snap.ensure(n ? (size_t)n * 40 : 1))) return rc;
     e->have_pid = h->particle_id != nullptr;
     e->n = n;
+    p.lone_particle = n == 1;
 
     zero_report(*e->h_rep);
     CK(cudaMemcpyAsync(e->d_rep, e->h_rep, sizeof(ReportDev), cudaMemcpyHostToDevice, e->stream));
@@ -1073,6 +1075,7 @@ int32_t pb_advect_rk45(pb_engine* e, const pb_rk45_args* a, double* dt_inout, do
     p.dt = a->dt; p.endtime = a->endtime; p.max_iters = a->max_iters;
     p.hint_all_zero = a->hint_all_zero;
     p.batch_levels = a->batch_levels;
+    p.lone_particle = e->n == 1;
     p.g.off_x = e->g.off_x; p.g.off_y = e->g.off_y; p.g.off_z = e->g.off_z;
     p.rep = e->d_rep;
     zero_report(*e->h_rep);

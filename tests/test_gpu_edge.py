@@ -248,3 +248,26 @@ def test_axes_of_length_one(nx, ny, nz, cdtype):
     assert len(ps) == len(pd["x"]) > 0
     for k in ("particle_id", "state", "t", "ei", "x", "y", "z"):
         np.testing.assert_array_equal(ps._data[k], pd[k], err_msg=k)
+
+
+@pytest.mark.parametrize("name", ["curv_flat_2d", "curv_sph_2d"])
+def test_lone_particle_in_the_first_cell_column_always_goes_through_the_hash(name):
+    """`if np.any(xi)` (reference index_search.py:269): when every hinted xi of a batch is 0 the hint test is skipped and the
+    spatial hash answers (float32-rounded cell coordinates).  A set of ONE particle sitting in the first column of a
+    curvilinear grid is such a batch at every evaluation, not only at the first of a call."""
+    import cases
+    from engine_run import run_engine, ulp_diff_f32
+    from oracle_run import run_oracle
+
+    c0 = cases.build(cases.CASES[name])
+    lon2, lat2 = np.asarray(c0["lon"]), np.asarray(c0["lat"])
+    j = lon2.shape[0] // 2
+    c = dict(c0, U=c0["U"] * 0.02, V=c0["V"] * 0.02)  # slow flow: the particle stays in column 0 for the whole run
+    c["x"], c["y"] = np.array([0.5 * (lon2[j, 0] + lon2[j + 1, 1])]), np.array([0.5 * (lat2[j, 0] + lat2[j + 1, 1])])
+    c["z"], c["t"] = np.asarray(c0["z"])[:1], np.asarray(c0["t"])[:1]
+    ps, err = run_engine(c)
+    pd, oerr = run_oracle(c)
+    assert not err and oerr is None and len(ps) == len(pd["x"]) == 1
+    assert ps._data["ei"][0, -1] == pd["ei"][0, -1] and ps._data["ei"][0, -1] % (lon2.shape[1] - 1) == 0
+    for k in "xy":
+        assert ulp_diff_f32(ps._data[k], pd[k]).max() <= (0 if name == "curv_flat_2d" else 8), k
