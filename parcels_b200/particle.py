@@ -29,10 +29,22 @@ _CORE_ATTRS = {
 }
 
 
+def _assert_str_and_python_varname(name):
+    """reference _core/utils/string.py (via _core/particle.py:42)"""
+    import keyword
+
+    if not isinstance(name, str):
+        raise TypeError(f"Expected a string for variable name, got {type(name).__name__} instead.")
+    if not name.isidentifier() or keyword.iskeyword(name):
+        raise ValueError(f"Received invalid Python variable name {name!r}: not a valid identifier. HINT: avoid using spaces, special "
+                         "characters, and starting with a number.")  # fmt: skip
+
+
 class Variable:
     """reference _core/particle.py:20-66 (name, dtype, initial, to_write, attrs)."""
 
     def __init__(self, name, dtype=np.float32, initial=0, to_write=True, attrs=None):
+        _assert_str_and_python_varname(name)
         try:
             dtype = np.dtype(dtype)
         except (TypeError, ValueError) as e:
@@ -42,60 +54,78 @@ class Variable:
         attrs = {} if attrs is None else attrs
         if not to_write and attrs != {}:
             raise ValueError(f"Attributes cannot be set if {to_write=!r}.")
-        self.name, self.dtype, self.initial, self.to_write, self.attrs = name, dtype, initial, to_write, attrs
+        self._name, self.dtype, self.initial, self.to_write, self.attrs = name, dtype, initial, to_write, attrs
+
+    name = property(lambda self: self._name)
+
+    def __repr__(self):  # reference _repr_utils.variable_repr
+        return f"Variable(name={self.name!r}, dtype={self.dtype!r}, initial={self.initial!r}, to_write={self.to_write!r}, attrs={self.attrs!r})"
 
 
 class ParticleClass:
-    """The default Particle plus optional extra variables (reference ``Particle.add_variable``,
-    _core/particle.py:95-113).  Extra variables live in host arrays only: the device kernels never touch
-    them, user Python kernels can (they stay aligned through deletions)."""
+    """A class of particles: a list of ``Variable`` objects (reference _core/particle.py:69-113).  The built-in kernels use the
+    variables of the default ``Particle``; any further variable lives in host arrays only -- the device kernels never touch it,
+    user Python kernels can (it stays aligned through deletions)."""
 
-    def __init__(self, extra=()):
-        self.extra = tuple(extra)
+    def __init__(self, variables):
+        if not isinstance(variables, list):
+            raise TypeError(f"Expected list of Variable objects, got {type(variables)}")
+        if not all(isinstance(var, Variable) for var in variables):
+            raise ValueError(f"All items in variables must be instances of Variable. Got {variables=!r}")
+        self.variables = variables
 
     @property
-    def variables(self):
-        return _CORE + tuple((v.name, v.dtype) for v in self.extra)
+    def extra(self):
+        """the variables the default Particle does not have"""
+        return tuple(v for v in self.variables if v.name not in _CORE_NAMES)
 
     def written_variables(self):
         """Variables with ``to_write`` (reference _core/particlefile.py:193-194), in declaration order."""
-        core = [Variable(n, d, attrs=dict(_CORE_ATTRS[n])) for n, d in _CORE if n in _CORE_ATTRS]
-        return core + [v for v in self.extra if v.to_write]
+        return [v for v in self.variables if v.to_write]
 
     def add_variable(self, variable):
         new = [variable] if isinstance(variable, Variable) else list(variable)
-        names = {n for n, _ in self.variables}
+        for v in new:
+            if not isinstance(v, Variable):
+                raise TypeError(f"Expected Variable, got {type(v)}")
+        names = {v.name for v in self.variables}
         for v in new:
             if v.name in names:
                 raise ValueError(f"Variable name already exists: {v.name}")
-        return ParticleClass(self.extra + tuple(new))
+        return ParticleClass(variables=self.variables + new)
 
-    def __repr__(self):
-        return "Particle(" + ", ".join(f"{n}:{np.dtype(d).name}" for n, d in self.variables) + ")"
-
-
-Particle = ParticleClass()
+    def __repr__(self):  # reference _repr_utils.particleclass_repr
+        return "\n".join(repr(v) for v in self.variables)
 
 
-def create_particle_data(*, nparticles, ngrids, initial, pclass=None):
+_CORE_NAMES = {n for n, _ in _CORE}
+# the default Particle (reference _core/particle.py:123-178): only the variables with file attributes are written
+Particle = ParticleClass(variables=[
+    Variable(n, d, initial={"dt": 1.0, "state": StatusCode.Evaluate}.get(n, 0), to_write=n in _CORE_ATTRS, attrs=dict(_CORE_ATTRS.get(n, {})))
+    for n, d in _CORE
+])  # fmt: skip
+
+
+def create_particle_data(*, nparticles, ngrids, initial=None, pclass=None):
+    """reference _core/particle.py:182-222: one array per Variable of the class (+ ``ei`` (N, ngrids) int32)"""
     pclass = pclass or Particle
-    dtypes = dict(pclass.variables)
-    inits = {v.name: v.initial for v in pclass.extra}
+    initial = {} if initial is None else initial
+    dtypes = {v.name: v.dtype for v in pclass.variables}
     data = {"ei": np.zeros((nparticles, ngrids), dtype=np.int32)}
     for k, v in initial.items():
         v = np.asarray(v)
         if v.shape != (nparticles,):
             raise ValueError(f"Initial value for {k} must have shape ({nparticles},). Got {v.shape=}")
         data[k] = np.ascontiguousarray(v.astype(dtypes[k]))
-    for name, dt in pclass.variables:
-        if name not in data:
-            init = {"dt": 1.0, "state": StatusCode.Evaluate, **inits}.get(name, 0)
+    for var in pclass.variables:
+        if var.name not in data:
+            init = var.initial
             if isinstance(init, operator.attrgetter):
                 # `Variable("age0", initial=attrgetter("t"))`: a copy of another variable's initial values, in THAT variable's
                 # dtype (reference _core/particle.py:212-215)
-                data[name] = data[init(_NameOf())].copy()
+                data[var.name] = data[init(_NameOf())].copy()
             else:
-                data[name] = np.full((nparticles,), init, dtype=dt)
+                data[var.name] = np.full((nparticles,), init, dtype=var.dtype)
     return data
 
 

@@ -201,7 +201,7 @@ def _setup_rk45(self, names, fieldset, pclass):
     fused = names == ["AdvectionRK45"] and not self.diffusion
     if self.diffusion or any(n in K.SCHEMES or n in K.ADVDIFF or n == "DiffusionUniformKh" for n in names if n):
         raise NotImplementedError("AdvectionRK45 combines with user kernels and the DeleteParticle token, not with other built-in kernels")
-    if pclass is None or "next_dt" not in [n for n, _ in pclass.variables]:
+    if pclass is None or "next_dt" not in [v.name for v in pclass.variables]:
         raise ValueError('ParticleClass requires a "next_dt" for AdvectionRK45 Kernel.')
     if not ((fieldset.interp_method in ("linear", "freeslip", "partialslip") and not fieldset.grid.curvilinear)
             or fieldset.interp_method == "cgrid_velocity") or fieldset.time_window is not None:  # fmt: skip
