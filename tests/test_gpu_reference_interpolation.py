@@ -91,3 +91,39 @@ def test_interpolation_mesh_type(mesh):
     u, v = fieldset.UV[time, 0, lat, 0]
     assert np.isclose(u, u_expected, atol=1e-7)
     assert v == 0.0
+
+
+def _ramp_fieldset():
+    """lon = [1, 2, 3, 4, 5] (the array of the reference's tests/test_xgrid.py::test_search_1d_array*), P = lon: the sampled value of
+    XLinear is lon[xi] + xsi * (lon[xi + 1] - lon[xi]), the returned cell index is xi (one row of cells)."""
+    lon = np.array([1.0, 2.0, 3.0, 4.0, 5.0])
+    P = np.broadcast_to(lon, (1, 1, 2, 5)).copy()
+    fs = pb.FieldSet.from_arrays(lon=lon, lat=np.array([0.0, 1.0]), U=np.zeros_like(P), V=np.zeros_like(P), mesh="flat")
+    fs.add_field("P", P)
+    return fs, lon
+
+
+@pytest.mark.parametrize("x, expected_xi, expected_xsi", [((1.1, 2.1), (0, 1), (0.1, 0.1)), (2.1, 1, 0.1), (3.1, 2, 0.1), (4.5, 3, 0.5)])
+def test_search_1d_array(x, expected_xi, expected_xsi):
+    fs, lon = _ramp_fieldset()
+    x = np.atleast_1d(np.asarray(x, dtype=np.float64))
+    val, ei, st = fs.engine(0).sample_scalar(fs.P._slot, "linear", np.zeros_like(x), np.zeros_like(x), np.full_like(x, 0.5), x, positions_are_f32=False, ei_hint=None)
+    np.testing.assert_array_equal(ei, np.atleast_1d(expected_xi))
+    np.testing.assert_allclose(val - lon[ei], np.atleast_1d(expected_xsi))
+    assert np.all(st == pb.StatusCode.Evaluate)
+
+
+@pytest.mark.parametrize("x, expected_state", [(-0.1, pb.StatusCode.Evaluate), (6.5, pb.StatusCode.ErrorOutOfBounds), ((-0.1, 2.5), None), ((6.5, 1), None)])
+def test_search_1d_array_out_of_bounds(x, expected_state):
+    """LEFT_OUT_OF_BOUNDS (-2) is not an error state in the reference for X / Y (field.py:327-356), RIGHT_OUT_OF_BOUNDS (-1) is
+    ErrorOutOfBounds; either way the sampled value is 0 (field.py:359-370) and in-bounds samples of the same call are unaffected."""
+    fs, lon = _ramp_fieldset()
+    x = np.atleast_1d(np.asarray(x, dtype=np.float64))
+    val, ei, st = fs.engine(0).sample_scalar(fs.P._slot, "linear", np.zeros_like(x), np.zeros_like(x), np.full_like(x, 0.5), x, positions_are_f32=False, ei_hint=None)
+    inside = (x >= 1) & (x <= 5)
+    assert np.all(val[~inside] == 0.0)
+    np.testing.assert_allclose(val[inside], x[inside])
+    np.testing.assert_array_equal(st[x > 5], pb.StatusCode.ErrorOutOfBounds)
+    np.testing.assert_array_equal(st[x < 1], pb.StatusCode.Evaluate)
+    if expected_state is not None:
+        assert st[0] == expected_state
