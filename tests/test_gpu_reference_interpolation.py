@@ -127,3 +127,31 @@ def test_search_1d_array_out_of_bounds(x, expected_state):
     np.testing.assert_array_equal(st[x < 1], pb.StatusCode.Evaluate)
     if expected_state is not None:
         assert st[0] == expected_state
+
+
+def test_grid_indexing_fpoints():
+    """reference tests/test_index_search.py::test_grid_indexing_fpoints on the device: on the `2d_left_unrolled_cone` curvilinear
+    mesh (reference _datasets/structured/generic.py:76-100, flat), every F-point nudged by 1e-5 is found in the cell it is the
+    lower-left corner of (or its left / lower neighbour when the nudge barely crosses), and that cell's corners bracket it."""
+    X, Y = 30, 60
+    XG, YG = np.arange(X), np.arange(Y) * 0.25
+    LON, LAT = np.meshgrid(XG, YG)
+    pivot = (-10.0, 0.0)
+    r = np.sqrt((LON - pivot[0]) ** 2 + (LAT - pivot[1]) ** 2) * 1.2
+    theta = np.arctan2(LAT - pivot[1], XG.min() - pivot[0]) * 1.2
+    lon, lat = r * np.cos(theta) + pivot[0], r * np.sin(theta) + pivot[1]
+    z = np.zeros((1, 1, Y, X))
+    fs = pb.FieldSet.from_arrays(lon=lon, lat=lat, U=z, V=z, mesh="flat", interp_method="cgrid_velocity")
+    ydim, xdim = Y - 1, X - 1  # cell counts
+    jj, ii = np.meshgrid(np.arange(ydim - 1), np.arange(xdim - 1), indexing="ij")
+    jj, ii = jj.ravel(), ii.ravel()
+    x, y = lon[jj, ii] + 0.00001, lat[jj, ii] + 0.00001
+    u, v, w, ei, st = fs.engine(0).sample_velocity(0.0, 0.0, y, x, three_d=False, positions_are_f32=False, no_hint=True)
+    assert np.all(st == pb.StatusCode.Evaluate)
+    yi, xi = ei // xdim, ei % xdim
+    # the reference accepts the neighbour below / to the left when eta / xsi > 0.9 there: the cell found must be one of those
+    assert np.all((yi == jj) | (yi == jj - 1)) and np.all((xi == ii) | (xi == ii - 1))
+    cell_lon = np.stack([lon[yi, xi], lon[yi, xi + 1], lon[yi + 1, xi + 1], lon[yi + 1, xi]])
+    cell_lat = np.stack([lat[yi, xi], lat[yi, xi + 1], lat[yi + 1, xi + 1], lat[yi + 1, xi]])
+    assert np.all((x > cell_lon.min(axis=0)) & (x < cell_lon.max(axis=0)))
+    assert np.all((y > cell_lat.min(axis=0)) & (y < cell_lat.max(axis=0)))
