@@ -58,6 +58,32 @@ def _batch_skips_hint(grid, hint) -> bool:
     return bool(grid.curvilinear and hint is not None and not np.any((np.asarray(hint).astype(np.int64) % grid.xdim) != 0))
 
 
+class SphericalMesh:
+    """``mesh=SphericalMesh(radius=...)`` (reference _core/mesh.py:23-51): a spherical mesh with a configurable planetary radius in
+    metres (default: the Earth's, for which a degree of arc is exactly 1852 * 60 m)."""
+
+    def __init__(self, radius=EARTH_RADIUS):
+        if not isinstance(radius, (int, float, np.number)) or isinstance(radius, bool):
+            raise TypeError(f"radius must be a number, got {type(radius).__name__}")
+        if radius <= 0:
+            raise ValueError(f"radius must be positive, got {radius}")
+        self.radius = radius
+
+    deg2m = property(lambda self: self.radius * np.pi / 180.0)
+
+    def is_spherical(self):
+        return True
+
+    def __eq__(self, other):
+        return isinstance(other, SphericalMesh) and self.radius == other.radius
+
+    def __hash__(self):
+        return hash((True, self.radius))
+
+    def __repr__(self):
+        return f"SphericalMesh(radius={self.radius!r})"
+
+
 class XGrid:
     """Structured grid (rectilinear: 1-D lon/lat; depth optional).  ``xdim/ydim/zdim`` are cell
     counts as in the reference (``_core/xgrid.py:21-24,208-231``); they default to nodes - 1,
@@ -71,8 +97,10 @@ class XGrid:
             raise ValueError("lon/lat must both be 1-D (rectilinear) or both 2-D (curvilinear, shape (ny, nx))")
         if self.lon.ndim == 2 and self.lon.shape != self.lat.shape:
             raise ValueError("curvilinear lon and lat must share one shape (ny, nx)")
+        if isinstance(mesh, SphericalMesh):  # reference: mesh=SphericalMesh(radius=...)
+            mesh, radius = "spherical", (mesh.radius if radius is None else radius)
         if mesh not in ("flat", "spherical"):
-            raise ValueError(f"mesh must be 'flat' or 'spherical'. Got {mesh!r}")
+            raise ValueError(f"mesh must be 'flat', 'spherical' or a SphericalMesh. Got {mesh!r}")
         self.mesh = mesh
         self.radius = (EARTH_RADIUS if radius is None else radius) if mesh == "spherical" else None
         self.xdim = self.lon.shape[-1] - 1 if xdim is None else xdim
