@@ -1,8 +1,7 @@
 """The reference's own ``tests/test_particlefile.py``, transcribed (same names, same assertions) for the part that goes through
 ``ParticleSet.execute(..., output_file=ParticleFile(...))`` and ``ParticleFile.write``.  The `t` column is read as the stored
 float64 seconds (the reference's reader decodes it to timestamps with polars, which is not installed here; the CF attributes
-that decoding needs are checked by tests/test_output_cpu.py).  Left out: tests marked skip / xfail in the reference, and the
-constructor / path-mode tests that tests/test_output_cpu.py::test_particlefile_constructor_checks already transcribes."""
+that decoding needs are checked by tests/test_output_cpu.py).  Left out: tests marked skip / xfail in the reference and the one whose body is `...`."""
 
 from contextlib import nullcontext as does_not_raise
 from datetime import datetime, timedelta
@@ -233,3 +232,65 @@ def test_pset_execute_outputdt_backwards(fieldset, tmp_path):
     outputdt, runtime, dt = timedelta(hours=1), timedelta(days=2), -timedelta(minutes=5)
     df = _setup_pset_execute(fieldset, outputdt, tmp_path, runtime=runtime, dt=dt)
     np.testing.assert_equal(np.diff(df[df["particle_id"] == 0]["t"]), -outputdt.seconds)
+
+
+def test_particlefile_init(tmp_parquet):
+    ParticleFile(tmp_parquet, outputdt=np.timedelta64(1, "s"))
+
+
+def test_particlefile_init_existing_path_modes(fieldset, tmp_parquet):
+    pset = ParticleSet(fieldset, pclass=Particle, x=0, y=0)
+    first_file = ParticleFile(tmp_parquet, outputdt=np.timedelta64(1, "s"))
+    pset.execute(DoNothing, runtime=np.timedelta64(10, "s"), dt=np.timedelta64(1, "s"), output_file=first_file)
+    df_first = pd.read_parquet(tmp_parquet)
+    with pytest.raises(ValueError, match="already exists"):
+        ParticleFile(tmp_parquet, outputdt=np.timedelta64(1, "s"))
+    overwrite_file = ParticleFile(tmp_parquet, outputdt=np.timedelta64(1, "s"), mode="w")
+    pset.execute(DoNothing, runtime=np.timedelta64(10, "s"), dt=np.timedelta64(1, "s"), output_file=overwrite_file)
+    df_overwrite = pd.read_parquet(tmp_parquet)
+    assert len(df_first) == len(df_overwrite)
+
+
+def test_particlefile_init_existing_path_no_mode(tmp_parquet):
+    tmp_parquet.touch()
+    with pytest.raises(ValueError, match="already exists"):
+        ParticleFile(tmp_parquet, outputdt=np.timedelta64(1, "s"))
+
+
+def test_particlefile_init_nonexistent_parent(tmp_path):
+    path = tmp_path / "nonexistent_dir" / "file.parquet"
+    with pytest.raises(ValueError, match="does not exist"):
+        ParticleFile(path, outputdt=np.timedelta64(1, "s"))
+
+
+def test_particlefile_init_invalid_mode(tmp_parquet):
+    with pytest.raises(ValueError, match="Invalid mode value"):
+        ParticleFile(tmp_parquet, outputdt=np.timedelta64(1, "s"), mode="something-else")
+
+
+@pytest.mark.parametrize("name", ["path", "outputdt"])
+def test_particlefile_readonly_attrs(tmp_parquet, name):
+    pfile = ParticleFile(tmp_parquet, outputdt=np.timedelta64(1, "s"))
+    with pytest.raises(AttributeError, match="property .* of 'ParticleFile' object has no setter"):
+        setattr(pfile, name, "something")
+
+
+def test_particlefile_init_invalid(tmp_path):
+    path = tmp_path / "file.not-parquet"
+    with pytest.raises(ValueError, match="file extension must be '.parquet'"):
+        ParticleFile(path, outputdt=np.timedelta64(1, "s"))
+
+
+def test_particlefile_readable_after_kernel_error(fieldset, tmp_parquet):
+    """Parquet output file must be readable even if the kernel raises an error mid-execution (reference GH-2713)."""
+    from parcels_b200 import StatusCode
+
+    def ErrorKernel(particles, fieldset):
+        particles.state = StatusCode.Error
+
+    pset = ParticleSet(fieldset, pclass=Particle, x=0, y=0)
+    ofile = ParticleFile(tmp_parquet, outputdt=np.timedelta64(1, "s"))
+    with pytest.raises(RuntimeError, match="General error occurred at"):
+        pset.execute(ErrorKernel, runtime=np.timedelta64(10, "s"), dt=np.timedelta64(1, "s"), output_file=ofile)
+    df = pd.read_parquet(tmp_parquet)
+    assert len(df) >= 1  # at least the initial condition was written
