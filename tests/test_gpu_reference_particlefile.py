@@ -294,3 +294,28 @@ def test_particlefile_readable_after_kernel_error(fieldset, tmp_parquet):
         pset.execute(ErrorKernel, runtime=np.timedelta64(10, "s"), dt=np.timedelta64(1, "s"), output_file=ofile)
     df = pd.read_parquet(tmp_parquet)
     assert len(df) >= 1  # at least the initial condition was written
+
+
+@pytest.mark.parametrize("particle", [
+    Particle,
+    pb.ParticleClass(variables=[
+        Variable("lon", dtype=np.float32, attrs={"standard_name": "longitude", "units": "degrees_east", "axis": "X"}),
+        Variable("lat", dtype=np.float32, attrs={"standard_name": "latitude", "units": "degrees_north", "axis": "Y"}),
+        Variable("z", dtype=np.float32, attrs={"standard_name": "vertical coordinate", "units": "m", "positive": "down"}),
+    ]),
+])  # fmt: skip
+def test_particle_schema(particle, fieldset, tmp_parquet):
+    """the schema of the written table: one field per writable Variable, its attrs as field metadata, CF time attributes on `t`
+    (the reference calls its get_schema(particle, {}, TimeInterval(...)); here: the schema ParticleFile builds for a fieldset
+    with a datetime time axis)"""
+    s = ParticleFile(tmp_parquet, outputdt=1.0)._schema(particle, fieldset)
+    written_variables = [v for v in particle.variables if v.to_write]
+    assert len(s.names) == len(written_variables)
+    for variable, pyarrow_field in zip(written_variables, s, strict=False):
+        assert variable.name == pyarrow_field.name
+        if variable.name != "t":
+            assert variable.attrs == {k.decode(): v.decode() for k, v in pyarrow_field.metadata.items()}
+        else:
+            assert b"units" in pyarrow_field.metadata
+            assert b"calendar" in pyarrow_field.metadata
+        assert pa.from_numpy_dtype(variable.dtype) == pyarrow_field.type
