@@ -69,8 +69,15 @@ def from_parcels(ref_fieldset) -> FieldSet:
 
 def pset_from_parcels(ref_pset, fieldset: FieldSet, **kw) -> ParticleSet:
     """reference ParticleSet -> parcels_b200.ParticleSet sharing the SAME SoA arrays."""
+    from .particle import _CORE_NAMES, Particle, Variable
+
     d = ref_pset._data
-    ps = ParticleSet(fieldset, x=d["x"], y=d["y"], z=d["z"], t=d["t"], particle_ids=d["particle_id"], **kw)
+    # every key of the shared SoA is a Variable of the set's class: extra variables (Particle.add_variable in the reference)
+    # must be known here so that deletions go through remove_indices over ALL keys and the set is not kept device-resident
+    # with host-only columns (the compacted-download shortcut only handles the default Particle)
+    extra = [Variable(k, v.dtype) for k, v in d.items() if k not in _CORE_NAMES and k != "ei"]
+    pclass = Particle.add_variable(extra) if extra else Particle
+    ps = ParticleSet(fieldset, pclass, x=d["x"], y=d["y"], z=d["z"], t=d["t"], particle_ids=d["particle_id"], **kw)
     ps._data = d  # share the reference's dict of ndarrays: results are written back in place
     ps.eager_host = True  # ... at the end of every execute(), not on first access
     return ps

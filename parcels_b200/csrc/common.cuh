@@ -152,9 +152,10 @@ __host__ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1,
 __device__ __forceinline__ void wiener_normals(unsigned long long seed, unsigned long long rng_call, long long iter,
                                                long long pid, double& zx, double& zy) {
     uint32_t r[4];
-    // counter = (pid_lo, pid_hi, iteration, call index); key = seed
+    // counter = (pid_lo, pid_hi, iteration, call index lo); key = seed, with the HIGH word of the 64-bit call index folded into
+    // key word 1 (mode D packs (call << 20) + round into it: distinct calls must never share a counter)
     philox4x32_10((uint32_t)pid, (uint32_t)((unsigned long long)pid >> 32), (uint32_t)iter, (uint32_t)rng_call,
-                  (uint32_t)seed, (uint32_t)(seed >> 32), r);
+                  (uint32_t)seed, (uint32_t)(seed >> 32) ^ (uint32_t)(rng_call >> 32), r);
     const double two_m32 = 2.3283064365386963e-10;  // 2^-32
     double u1 = ((double)r[0] + 0.5) * two_m32;
     double u2 = ((double)r[1] + 0.5) * two_m32;

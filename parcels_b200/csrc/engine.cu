@@ -289,6 +289,7 @@ struct pb_engine {
     // particles
     DevBuf px, py, pz, pdx, pdy, pdz, pt, pstate, pei, ppid;
     DevBuf snap;  // snapshot of all particle arrays
+    long long snap_n = -1;  // particle count the snapshot was taken at (-1: none); any change of the resident set invalidates it
     // mode D (domain decomposition): alternate SoA for compaction, migration work buffers
     DevBuf ax, ay, az, adx, ady, adz, at, astate, aei, apid;
     DevBuf mdest, mkeep, mcount, mbounds;
@@ -641,6 +642,7 @@ int32_t pb_particles_upload(pb_engine* e, int64_t n, const float* x, const float
     e->have_pid = particle_id != nullptr;
     if (particle_id && (rc = upload(e, e->ppid, particle_id, n * 8))) return rc;
     e->n = n;
+    e->snap_n = -1;
     CK(cudaStreamSynchronize(e->stream));
     return PB_OK;
 }
@@ -683,6 +685,7 @@ int32_t pb_particles_snapshot(pb_engine* e) {
         if (n) CK(cudaMemcpyAsync(s + off, c.src, n * c.es, cudaMemcpyDeviceToDevice, e->stream));
         off += n * c.es;
     }
+    e->snap_n = (long long)n;
     return PB_OK;
 }
 
@@ -690,7 +693,9 @@ int32_t pb_particles_restore(pb_engine* e) {
     if (!e) return fail(PB_ERR_INVALID, "engine is NULL");
     CK(cudaSetDevice(e->device));
     const size_t n = (size_t)e->n;
-    if (e->snap.bytes < n * 40) return fail(PB_ERR_STATE, "no snapshot to restore");
+    // the layout is whole columns at offsets that are multiples of the n AT SNAPSHOT TIME: a snapshot of another set size is garbage
+    if (e->snap_n != (long long)n || e->snap.bytes < n * 40)
+        return fail(PB_ERR_STATE, "no snapshot of the resident set to restore (snapshot of %lld particles, %lld resident)", e->snap_n, (long long)n);
     char* s = (char*)e->snap.p;
     struct { void* dst; size_t es; } a[] = {{e->px.p, 4}, {e->py.p, 4}, {e->pz.p, 4}, {e->pdx.p, 4}, {e->pdy.p, 4},
                                             {e->pdz.p, 4}, {e->pt.p, 8}, {e->pstate.p, 4}, {e->pei.p, 4}};
@@ -944,6 +949,7 @@ int32_t pb_advect_host(pb_engine* e, const pb_advect_args* a, int64_t n, const p
     if ((rc = e->snap.ensure(n ? (size_t)n * 40 : 1))) return rc;
     e->have_pid = h->particle_id != nullptr;
     e->n = n;
+    e->snap_n = n;  // the chunks below write the start-of-interval copy
     p.lone_particle = n == 1;
 
     zero_report(*e->h_rep);
@@ -1325,6 +1331,7 @@ int32_t pb_particles_remove_deleted(pb_engine* e, int64_t* n_left) {
     CK(cudaStreamSynchronize(e->stream));
     for (int k = 0; k < 10; ++k) std::swap(*cur[k], *alt[k]);
     e->n = keep;
+    e->snap_n = -1;
     e->n_keep = keep;
     *n_left = keep;
     return PB_OK;
@@ -1401,6 +1408,7 @@ int32_t pb_migrate_unpack(pb_engine* e, const void* recvbuf_dev, int64_t n_in) {
     CK(cudaStreamSynchronize(e->stream));
     for (int k = 0; k < 10; ++k) std::swap(*cur[k], *alt[k]);
     e->n = n_new;
+    e->snap_n = -1;
     e->n_send = 0; e->n_keep = n_new;
     return PB_OK;
 }

@@ -23,6 +23,22 @@ class Engine:
         self._h = h
         self.device = int(device)
         self._keep = []  # device tensors attached by pointer must outlive the engine's use
+        self._owner = None  # weakref to the ParticleSet whose particles are resident in this engine's SoA
+
+    def claim(self, pset):
+        """The engine holds ONE resident particle SoA.  Before another ParticleSet uploads into it, the set that was
+        resident brings its host arrays up to date (its only copy may live here after a lazy execute()) and forgets
+        that the device mirrors it -- every ParticleSet on a FieldSet keeps independent data, as in the reference."""
+        import weakref
+
+        prev = self._owner() if self._owner is not None else None
+        if prev is not None and prev is not pset:
+            prev._release_device()
+        if prev is not pset:
+            self._owner = weakref.ref(pset)
+
+    def owned_by(self, pset) -> bool:
+        return self._owner is not None and self._owner() is pset
 
     def close(self):
         if getattr(self, "_h", None):

@@ -385,9 +385,18 @@ class ParticleSet:
         self._host = value
         self._host_stale = False
 
+    def _release_device(self):
+        """Another ParticleSet is about to use this engine's resident SoA (Engine.claim): fetch what only lives there."""
+        if self._host_stale:
+            self._sync_host()
+        self._device_synced = False
+
     def _sync_host(self):
         """Bring the host arrays up to date with the device-resident set (sizes may differ after deletions)."""
         eng = self.fieldset.engine(self.device)
+        if not eng.owned_by(self):
+            raise RuntimeError("the device-resident particles of this ParticleSet were overwritten by another ParticleSet "
+                               "(engine ownership lost before the host arrays were refreshed)")
         d = self._host
         if d is not None and len(d["x"]) == eng.particle_count():
             # nothing was deleted: ids and order are unchanged, refresh the existing (possibly pinned) arrays in place
@@ -546,6 +555,7 @@ class ParticleSet:
         if plan.rk45 is not None:
             return self._kernel_execute_rk45(plan, endtime, dt)
         eng = self.fieldset.engine(self.device)
+        eng.claim(self)  # a ParticleSet that was resident here is synced to its host arrays first
         on_device = lazy and resident and self._host_stale and eng.particle_count() == self._n_device
         if on_device:
             # states are reset to Evaluate by the kernel itself (resume = 0); t cannot have become NaN on the device
@@ -696,6 +706,7 @@ class ParticleSet:
         if np.isnan(d["t"]).any():
             raise ValueError(f"Time values for particles with indices {np.where(np.isnan(d['t']))[0]} cannot be NaN.")
         eng = self.fieldset.engine(self.device)
+        eng.claim(self)
         ei_last = np.ascontiguousarray(d["ei"][:, -1])
         eng.upload_particles(d, ei_last)
         dt_arr = np.ascontiguousarray(d["dt"], dtype=np.float64)
@@ -784,10 +795,10 @@ class ParticleSet:
         if runtime is None and endtime is None:
             raise ValueError("Either runtime or endtime must be provided.")
         t = self._data["t"]
-        first = t.min() if sign_dt == 1 else t.max()  # NaN-propagating: one pass when no particle has an unset time
+        # `particle_release_times.min()` / `.max()` (reference particleset.py:541-544) PROPAGATE NaN: as soon as one release time
+        # is unset the start time is the fieldset's start (`_get_start_time`, :575-585) and EVERY particle's t is set to it (:413-414)
+        first = t.min() if sign_dt == 1 else t.max()
         any_nan = bool(np.isnan(first))
-        if any_nan:
-            first = (np.nanmin(t) if sign_dt == 1 else np.nanmax(t)) if not np.isnan(t).all() else np.nan
         if endtime is not None:
             origin = self.fieldset._time_origin
             stamped = isinstance(origin, (np.datetime64, np.timedelta64))

@@ -21,6 +21,7 @@ def kernel_execute_stepwise(pset, plan, endtime: float, dt: float):
     d = pset._data
     fs = pset.fieldset
     eng = fs.engine(pset.device)
+    eng.claim(pset)
     sign = 1 if dt > 0 else -1
     d["state"][:] = StatusCode.Evaluate
     steps = 0

@@ -35,7 +35,7 @@ def wiener_normals(seed, rng_call, it, particle_id):
     r0, r1, _, _ = philox4x32_10(
         (pid & MASK).astype(np.uint32), (pid >> np.uint64(32)).astype(np.uint32),
         np.full(n, np.uint32(it & 0xFFFFFFFF)), np.full(n, np.uint32(rng_call & 0xFFFFFFFF)),
-        seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF,
+        seed & 0xFFFFFFFF, ((seed >> 32) ^ (rng_call >> 32)) & 0xFFFFFFFF,
     )  # fmt: skip
     u1 = (r0.astype(np.float64) + 0.5) * 2.0**-32
     u2 = (r1.astype(np.float64) + 0.5) * 2.0**-32
