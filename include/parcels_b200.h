@@ -234,7 +234,7 @@ typedef struct pb_report {
     double wait_t_min;         /* smallest / largest time of those particles (valid when n_wait_window > 0) */
     double wait_t_max;
     int32_t max_state;
-    int32_t reserved;
+    int32_t kernel_variant;    /* 0: generic kernel family; 1: specialised RK4 kernel (float64 grid, float32 interleaved data) */
     float kernel_ms;           /* CUDA-event time of the advection kernel on the engine stream   */
     float reserved2;
 } pb_report;

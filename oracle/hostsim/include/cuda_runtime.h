@@ -52,6 +52,13 @@ inline T __ldg(const T* p) { return *p; }
 struct double2 {
     double x, y;
 };
+struct float2 {
+    float x, y;
+};
+struct alignas(16) float4 {
+    float x, y, z, w;
+};
+inline double __longlong_as_double(long long v) { double r; std::memcpy(&r, &v, 8); return r; }
 
 template <class T>
 inline T atomicAdd(T* p, T v) { T o = *p; *p = o + v; return o; }

@@ -78,7 +78,7 @@ class AdvDiffArgs(C.Structure):
         ("kernels_only", C.c_int32),
         ("resume", C.c_int32),
         ("batch_levels", C.c_int32),
-        ("reserved", C.c_int32),
+        ("kernel_variant", C.c_int32),
     ]
 
 
@@ -96,7 +96,7 @@ class Report(C.Structure):
         ("wait_t_min", C.c_double),
         ("wait_t_max", C.c_double),
         ("max_state", C.c_int32),
-        ("reserved", C.c_int32),
+        ("kernel_variant", C.c_int32),
         ("kernel_ms", C.c_float),
         ("reserved2", C.c_float),
     ]

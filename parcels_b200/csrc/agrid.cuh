@@ -378,6 +378,7 @@ template <class A, class D, bool HAS_TIME, int NC_, int MODE = 0>
 struct AGridPolicy {
     static constexpr int NC = NC_;
     static constexpr bool RUNTIME_DTYPE = false;  // interpolation arithmetic is typed on the position dtype
+    static constexpr bool FAST_RK4 = false;
     static constexpr bool F32_STAGES = (MODE == 2);  // nearest node: a stage value can be float32 at a float64 position
     static constexpr bool BATCH_LEN_T = std::is_same<A, float>::value;  // float32 grid: a value's dtype depends on the batch's lenT
     static constexpr bool BATCH_LEN_Z = (MODE == 1);  // _Spatialslip: the land test looks at lenZ depth levels

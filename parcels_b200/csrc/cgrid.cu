@@ -364,6 +364,7 @@ template <class A, class D, int NC_>
 struct CGridPolicy {
     static constexpr int NC = NC_;
     static constexpr bool RUNTIME_DTYPE = false;
+    static constexpr bool FAST_RK4 = false;
     static constexpr bool F32_STAGES = false;
     static constexpr bool BATCH_LEN_T = std::is_same<A, float>::value;
     static constexpr bool BATCH_LEN_Z = false;
@@ -531,6 +532,7 @@ template <class A, class D, int NC_, bool SPH>
 struct CurvPolicy {
     static constexpr int NC = NC_;
     static constexpr bool RUNTIME_DTYPE = true;
+    static constexpr bool FAST_RK4 = false;
     static constexpr bool F32_STAGES = false;
     static constexpr bool BATCH_LEN_T = std::is_same<A, float>::value;
     static constexpr bool BATCH_LEN_Z = false;

@@ -58,6 +58,10 @@ struct FieldDev {
     int ring;
     int windowed;
     double win_t0, win_t1;     // the resident levels cover sample times win_t0 <= t <= win_t1
+    // node-interleaved copy of U, V, W (one 16-byte {u, v, w, 0} record per grid node, same (T, Z, Y, X) node order), built on the
+    // device when float32 fields are uploaded: a corner-block refill of the hot kernel (afast.cu) is 16 vector loads instead of 48
+    // scalar ones.  NULL when there is none (float64 data, time-windowed fields).
+    const void* il;
 };
 __device__ __forceinline__ long long tslot(const FieldDev& f, long long level) { return f.windowed ? level % f.ring : level; }
 
@@ -296,7 +300,27 @@ __global__ void __launch_bounds__(PB_BLOCK_THREADS, PB_MINBLOCKS) advect_kernel(
             // with DiffusionUniformKh in the list, ei[:, -1] was overwritten with 0 for every particle by the
             // constant-field evals of the previous step: curvilinear hints are all zero again
             const bool nohint1 = (it == 0 && p.hint_all_zero) || (it > 0 && p.diffusion);
-            if constexpr (Policy::RUNTIME_DTYPE) {
+            if constexpr (Policy::FAST_RK4) {
+                // afast.cu: float64 grid, float32 data -- every stage value is float64 (Val::f32 never set), one eval site,
+                // odd stages renew the T-lerped block, even stages reuse it (stages 2/3 and 4/next-1 share their sample time)
+                su = sv = sw = 0.0;
+                uk = Val{0.0, false}; vk = uk; wk = uk;
+#pragma unroll 1
+                for (int k = 0; k < 4; ++k) {
+                    const bool full = (k == 3);
+                    const bool first = (k == 0);
+                    const double xs = first ? (double)x : (double)x + (full ? uk.v : uk.v * 0.5) * dtp;
+                    const double ys = first ? (double)y : (double)y + (full ? vk.v : vk.v * 0.5) * dtp;
+                    const double zs = (first || !three_d) ? (double)z : (double)z + (full ? wk.v : wk.v * 0.5) * dtp;
+                    const double ts = first ? t : t + (full ? dtp : 0.5 * dtp);
+                    Policy::eval_fast(p, e, k, ts, zs, ys, xs, uk.v, vk.v, wk.v);
+                    if (first) { su = uk.v; sv = vk.v; sw = wk.v; }
+                    else {
+                        const double m = (k == 3) ? 1.0 : 2.0;  // u1 + 2*u2 + 2*u3 + u4
+                        su = su + m * uk.v; sv = sv + m * vk.v; sw = sw + m * wk.v;
+                    }
+                }
+            } else if constexpr (Policy::RUNTIME_DTYPE) {
                 // One eval call site (the policy branches at run time where the position dtype matters):
                 // keeps the heavy curvilinear search + C-grid code in the instruction cache.
                 su = sv = sw = 0.0;
@@ -559,6 +583,10 @@ __global__ void sample_kernel(const SampleParams s) {
 
 // launchers implemented in agrid.cu / cgrid.cu (one translation unit per grid family keeps nvcc parallel)
 cudaError_t launch_agrid(const AdvectParams& p, bool coord_f64, bool data_f64, bool has_time, int nc, cudaStream_t s);
+// afast.cu: the specialised RK4 kernel (float64 grid, float32 node-interleaved data, time axis); `ok` tells whether it applies
+bool agrid_fast_applies(const AdvectParams& p, bool coord_f64, bool data_f64, bool has_time, int nc);
+cudaError_t launch_agrid_fast(const AdvectParams& p, int nc, cudaStream_t s);
+cudaError_t launch_interleave(const float* u, const float* v, const float* w, long long nodes, void* out, cudaStream_t s);
 cudaError_t launch_cgrid(const AdvectParams& p, bool coord_f64, bool data_f64, int nc, cudaStream_t s);
 // mode: 1 = _Spatialslip (g.slip_a/b), 2 = XNearest per component  (aslip.cu)
 cudaError_t launch_agrid_alt(const AdvectParams& p, int mode, bool coord_f64, bool data_f64, bool has_time, int nc, cudaStream_t s);

@@ -26,6 +26,7 @@
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <type_traits>
@@ -275,6 +276,10 @@ struct pb_engine {
     const void* fptr[PB_MAX_FIELDS] = {};
     int f_f64[PB_MAX_FIELDS] = {};
     long long fshape[PB_MAX_FIELDS][4] = {};
+    // node-interleaved {u, v, w, 0} copy of U, V, W for the specialised RK4 kernel (afast.cu); rebuilt when a component changes
+    DevBuf il;
+    bool il_valid = false;
+    int last_variant = 0;  // kernel family of the last advect launch: 0 generic, 1 specialised RK4 (afast.cu)
     // time-slab streaming: ring of (window + 1) levels per component, loads on a dedicated copy stream
     int ring = 0;                    // 0: every level resident
     long long win_first = 0, win_n = 0;
@@ -364,6 +369,7 @@ void pb_engine_destroy(pb_engine* e) {
                       &e->mcount, &e->mbounds})
         b->release();
     for (DevBuf& b : e->fbuf) b.release();
+    e->il.release();
     for (DevBuf* b : {&e->hqbox, &e->hbucket, &e->cellproj, &e->hkeys, &e->hstarts, &e->hcounts, &e->hfaces, &e->lon, &e->lat, &e->depth, &e->time, &e->px, &e->py, &e->pz,
                       &e->pdx, &e->pdy, &e->pdz, &e->pt, &e->pstate, &e->pei, &e->ppid, &e->snap, &e->sblock, &e->soffs, &e->sidx, &e->sout,
                       &e->samp_d, &e->samp_i})
@@ -583,6 +589,7 @@ int32_t pb_set_interpolation(pb_engine* e, int32_t method, int32_t off_x, int32_
 
 static int32_t set_field(pb_engine* e, int32_t slot, const void* dev, int32_t is_f64, int64_t T, int64_t Z, int64_t Y, int64_t X) {
     e->fptr[slot] = dev;
+    if (slot < 3) e->il_valid = false;
     e->f_f64[slot] = is_f64 ? 1 : 0;
     e->fshape[slot][0] = T; e->fshape[slot][1] = Z; e->fshape[slot][2] = Y; e->fshape[slot][3] = X;
     return PB_OK;
@@ -617,6 +624,7 @@ int32_t pb_field_clear(pb_engine* e, int32_t slot) {
     if (slot < 0 || slot >= PB_MAX_FIELDS) return fail(PB_ERR_INVALID, "bad field slot %d", slot);
     e->fbuf[slot].release();
     e->fptr[slot] = nullptr;
+    if (slot < 3) e->il_valid = false;
     return PB_OK;
 }
 
@@ -719,6 +727,7 @@ static void fill_field_desc(pb_engine* e, FieldDev& f) {
     f.sT = T > 1 ? X * Y * Z : 0;
     f.ring = e->ring ? e->ring : (int)T;
     f.windowed = e->ring ? 1 : 0;
+    f.il = (e->il_valid && !e->ring) ? e->il.p : nullptr;
     f.win_t0 = 0.0; f.win_t1 = 0.0;
     if (e->ring && e->win_n > 0 && !e->time_host.empty()) {
         f.win_t0 = e->time_host[e->win_first];
@@ -854,6 +863,30 @@ int32_t pb_sample_scalar(pb_engine* e, int32_t slot, int32_t method, int64_t n, 
     return PB_OK;
 }
 
+// The specialised RK4 kernel (afast.cu) gathers from a node-interleaved {u, v, w, 0} copy of the float32 fields: built here, on
+// the device, the first time an RK4 launch can use it (float64 rectilinear grid, XLinear_Velocity, every level resident).
+static bool fast_kernel_enabled() {
+    const char* v = getenv("PB_DISABLE_FAST_KERNEL");  // A/B switch of the parity tests and variant sweeps
+    return !(v && v[0] == '1');
+}
+static int32_t ensure_interleaved(pb_engine* e, int scheme) {
+    if (e->il_valid) return PB_OK;
+    if (!(scheme == PB_ADVECTION_RK4 || scheme == PB_ADVECTION_RK4_3D) || !fast_kernel_enabled()) return PB_OK;
+    if (e->interp != PB_INTERP_XLINEAR_VELOCITY || e->g.curvilinear || !e->coord_f64 || e->ring || e->f_f64[0] || e->g.nt < 2) return PB_OK;
+    if (!e->fptr[0] || !e->fptr[1]) return PB_OK;
+    const long long nodes = e->fshape[0][0] * e->fshape[0][1] * e->fshape[0][2] * e->fshape[0][3];
+    const bool have_w = e->fptr[2] && !e->f_f64[2] && e->fshape[2][0] == e->fshape[0][0] && e->fshape[2][1] == e->fshape[0][1] &&
+                        e->fshape[2][2] == e->fshape[0][2] && e->fshape[2][3] == e->fshape[0][3];
+    if (e->fptr[2] && !have_w) return PB_OK;  // (a W of another dtype / shape: the generic kernel's own checks apply)
+    int32_t rc = e->il.ensure((size_t)nodes * 16);
+    if (rc) return rc;
+    cudaError_t ce = launch_interleave((const float*)e->fptr[0], (const float*)e->fptr[1], have_w ? (const float*)e->fptr[2] : nullptr,
+                                       nodes, e->il.p, e->stream);
+    if (ce != cudaSuccess) return fail(PB_ERR_CUDA, "interleave_kernel launch failed: %s", cudaGetErrorString(ce));
+    e->il_valid = true;
+    return PB_OK;
+}
+
 // validation + kernel parameters shared by pb_advect_async and pb_advect_host (p.P is filled by the caller)
 static int32_t prepare_advect(pb_engine* e, const pb_advect_args* a, AdvectParams& p, int& nc) {
     if (!e || !a) return fail(PB_ERR_INVALID, "NULL argument");
@@ -863,11 +896,13 @@ static int32_t prepare_advect(pb_engine* e, const pb_advect_args* a, AdvectParam
         case PB_ADVECTION_RK2_3D: case PB_ADVECTION_RK4_3D: nc = 3; break;
         default: return fail(PB_ERR_INVALID, "unknown scheme %d", a->scheme);
     }
+    int32_t rc2;
     {
         int32_t rc = check_fields(e, nc);
         if (rc) return rc;
     }
     p.g = e->g;
+    if ((rc2 = ensure_interleaved(e, a->scheme))) return rc2;
     fill_field_desc(e, p.f);
     p.scheme = a->scheme; p.diffusion = a->diffusion; p.delete_on_error = a->delete_on_error;
     p.kh_spherical = a->kh_spherical;
@@ -885,6 +920,12 @@ static int32_t prepare_advect(pb_engine* e, const pb_advect_args* a, AdvectParam
 
 static cudaError_t launch_advect_kernel(pb_engine* e, const AdvectParams& p, int nc, cudaStream_t stream) {
     const int alt = agrid_alt_mode(e->interp);
+    if (e->interp == PB_INTERP_XLINEAR_VELOCITY && fast_kernel_enabled() &&
+        agrid_fast_applies(p, e->coord_f64 != 0, e->f_f64[0] != 0, e->g.nt > 0, nc)) {
+        e->last_variant = 1;
+        return launch_agrid_fast(p, nc, stream);
+    }
+    e->last_variant = 0;
     return e->interp == PB_INTERP_CGRID_VELOCITY ? launch_cgrid(p, e->coord_f64 != 0, e->f_f64[0] != 0, nc, stream)
            : alt ? launch_agrid_alt(p, alt, e->coord_f64 != 0, e->f_f64[0] != 0, e->g.nt > 0, nc, stream)
                  : launch_agrid(p, e->coord_f64 != 0, e->f_f64[0] != 0, e->g.nt > 0, nc, stream);
@@ -1027,6 +1068,7 @@ int32_t pb_last_report(pb_engine* e, pb_report* rep) {
             memcpy(&o.wait_t_max, &hi, 8);
         }
         o.max_state = r.max_state;
+        o.kernel_variant = e->last_variant;
         float ms = 0.f;
         CK(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
         o.kernel_ms = ms;

@@ -1,0 +1,25 @@
+#!/bin/bash
+# r02b: first B200 run of the specialised RK4 kernel (afast.cu): parity, A/B timing against the generic kernel, ncu
+tag=${1:-r02b}
+out=gpurun_out
+mkdir -p $out
+python -m pytest tests/test_gpu_fast_kernel.py tests/test_gpu_ownership.py tests/test_gpu_parity.py -m gpu -x -q > $out/${tag}_tests.log 2>&1; echo "pytest rc=$?" >> $out/${tag}_tests.log
+tail -3 $out/${tag}_tests.log
+for w in c2 ns c4; do
+  st=5; [ $w = c2 ] && st=20
+  python bench.py --workload $w --steps $st --warmup 3 --no-cpu-baseline --no-e2e > $out/${tag}_bench_${w}_fast.json 2> $out/${tag}_bench_${w}.err
+  PB_DISABLE_FAST_KERNEL=1 python bench.py --workload $w --steps $st --warmup 3 --no-cpu-baseline --no-e2e > $out/${tag}_bench_${w}_generic.json 2>> $out/${tag}_bench_${w}.err
+done
+ncu --set full --clock-control none --import-source on -k regex:advect_kernel -s 3 -c 1 -o $out/${tag}_advect_c2 -f \
+    python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > $out/${tag}_ncu_c2.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:advect_kernel -s 1 -c 1 -o $out/${tag}_advect_ns -f \
+    python bench.py --workload ns --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > $out/${tag}_ncu_ns.log 2>&1
+for f in $out/${tag}_bench_*.json; do echo "$f: $(python - "$f" <<'PY'
+import json, sys
+try:
+    d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
+    print(f"value {d['value']:.3e}  kernel_ms {d['config']['kernel_ms_per_launch']:.2f} refills {d['config']['corner_cache_refills_per_launch']} deleted {d['config']['deleted_per_launch']}")
+except Exception as e:
+    print("unreadable:", e)
+PY
+)"; done
