@@ -129,7 +129,8 @@ struct AFastPolicy {
     static constexpr int NL = NV / 2;             // T-lerped values per component
     static constexpr int RAW_CHUNKS = NC * NV / 4;  // float4 columns
     static constexpr int LRP_CHUNKS = NC * NL / 2;  // double2 columns
-    static constexpr size_t SMEM = (size_t)(RAW_CHUNKS + LRP_CHUNKS) * 16 * PB_FAST_BLOCK;
+    static constexpr int RCP_CHUNKS = 2;            // double2 columns: {1 / dz, 1 / dy}, {1 / dx, 1 / dt} of the current cells
+    static constexpr size_t SMEM = (size_t)(RAW_CHUNKS + LRP_CHUNKS + RCP_CHUNKS) * 16 * PB_FAST_BLOCK;
     static constexpr bool RUNTIME_DTYPE = false;
     static constexpr bool FAST_RK4 = true;
     static constexpr bool F32_STAGES = false;
@@ -139,6 +140,10 @@ struct AFastPolicy {
 
     __device__ static __forceinline__ double2* lrp(const Ctx& e) {
         return reinterpret_cast<double2*>(e.raw + (size_t)RAW_CHUNKS * PB_FAST_BLOCK);
+    }
+    // reciprocals of the cell widths (correctly rounded: computed by a division when the cell changes), for div_by_cached
+    __device__ static __forceinline__ double2* rcp(const Ctx& e) {
+        return reinterpret_cast<double2*>(e.raw + (size_t)(RAW_CHUNKS + LRP_CHUNKS) * PB_FAST_BLOCK);
     }
 
     __device__ static __forceinline__ void init(Ctx& e, const AdvectParams&, int ei) {
@@ -220,21 +225,40 @@ struct AFastPolicy {
                 u = v = w = 0.0;
                 return;
             }
-            const int oti = e.ct.idx, ozi = e.cz.idx, oyi = e.cy.idx, oxi = e.cx.idx;  // key of the raw block
-            if (oti >= 0 && !(e.ct.lo == e.ct.lo)) e.ct.idx = -100;  // (a poisoned cell is not a neighbour-search seed)
-            if (ozi >= 0 && !(e.cz.lo == e.cz.lo)) e.cz.idx = -100;
-            if (oyi >= 0 && !(e.cy.lo == e.cy.lo)) e.cy.idx = -100;
-            if (oxi >= 0 && !(e.cx.lo == e.cx.lo)) e.cx.idx = -100;
-            axis_locate(g.time, g.nt, ts, e.ct);
-            const int ti = e.ct.idx;
+            // (the cells are worked on in copies and written back at the end of the side path: the hit path then shares its
+            // registers with the values of the previous evaluation instead of receiving them through moves)
+            AxisCell<double> ct = e.ct, cz = e.cz, cy = e.cy, cx = e.cx;
+            const int oti = ct.idx, ozi = cz.idx, oyi = cy.idx, oxi = cx.idx;  // key of the raw block
+            const double wt = ct.hi - ct.lo, wz = cz.hi - cz.lo, wy = cy.hi - cy.lo, wx = cx.hi - cx.lo;  // (NaN for a poisoned cell)
+            if (oti >= 0 && !(ct.lo == ct.lo)) ct.idx = -100;  // (a poisoned cell is not a neighbour-search seed)
+            if (ozi >= 0 && !(cz.lo == cz.lo)) cz.idx = -100;
+            if (oyi >= 0 && !(cy.lo == cy.lo)) cy.idx = -100;
+            if (oxi >= 0 && !(cx.lo == cx.lo)) cx.idx = -100;
+            axis_locate(g.time, g.nt, ts, ct);
+            const int ti = ct.idx;
             int zi = 0;
             if (HZ) {
-                axis_locate((const double*)g.depth, g.nz, zs, e.cz);
-                zi = e.cz.idx;
+                axis_locate((const double*)g.depth, g.nz, zs, cz);
+                zi = cz.idx;
             }
-            axis_locate((const double*)g.lat, g.ny, ys, e.cy);
-            axis_locate((const double*)g.lon, g.nx, xs, e.cx);
-            const int yi = e.cy.idx, xi = e.cx.idx;
+            axis_locate((const double*)g.lat, g.ny, ys, cy);
+            axis_locate((const double*)g.lon, g.nx, xs, cx);
+            const int yi = cy.idx, xi = cx.idx;
+            {   // cell widths changed: new reciprocals (the division itself: correctly rounded)
+                double2* const rp = rcp(e);
+                const double nwt = ct.hi - ct.lo, nwz = cz.hi - cz.lo, nwy = cy.hi - cy.lo, nwx = cx.hi - cx.lo;
+                if ((HZ && !(nwz == wz)) || !(nwy == wy)) {
+                    double2 d;
+                    d.x = 1.0 / nwz; d.y = 1.0 / nwy;
+                    rp[0] = d;
+                }
+                if (!(nwx == wx) || !(nwt == wt)) {
+                    double2 d;
+                    d.x = 1.0 / nwx; d.y = 1.0 / nwt;
+                    rp[PB_FAST_BLOCK] = d;
+                }
+            }
+            e.ct = ct; e.cz = cz; e.cy = cy; e.cx = cx;
             if (g.decomposed) {  // mode D: a sentinel at a slab edge that is not the edge of the global domain = halo too small
                 if ((xi == -2 && !g.left_global) || (xi == -1 && !g.right_global)) e.state = max(e.state, 99);
             }
@@ -273,15 +297,17 @@ struct AFastPolicy {
             lerp_now = true;  // (an even stage after a cell change: its block has to be lerped for this sample time first)
         }
         // ---------------- straight-line path: every cell is current, 0 < bcoord <= 1 on every axis ----------------
-        const double zeta = HZ ? (zs - e.cz.lo) / (e.cz.hi - e.cz.lo) : 0.0;   // index_search.py:57 (denominator in the axis dtype)
-        const double eta = (ys - e.cy.lo) / (e.cy.hi - e.cy.lo);
-        const double xsi = (xs - e.cx.lo) / (e.cx.hi - e.cx.lo);
+        // bcoord = (x - lo) / (hi - lo), index_search.py:57 (denominator in the axis dtype), with the cell width's cached reciprocal
+        const double2 r_zy = rcp(e)[0], r_xt = rcp(e)[PB_FAST_BLOCK];
+        const double zeta = HZ ? div_by_cached(zs - e.cz.lo, e.cz.hi - e.cz.lo, r_zy.x) : 0.0;
+        const double eta = div_by_cached(ys - e.cy.lo, e.cy.hi - e.cy.lo, r_zy.y);
+        const double xsi = div_by_cached(xs - e.cx.lo, e.cx.hi - e.cx.lo, r_xt.x);
         const double omz = 1 - zeta;
         const double w00 = (1 - xsi) * (1 - eta), w01 = xsi * (1 - eta), w10 = (1 - xsi) * eta, w11 = xsi * eta;
         double2* const lp = lrp(e);
         double q[3] = {0.0, 0.0, 0.0};
         if (lerp_now) {
-            const double tau = (ts - e.ct.lo) / (e.ct.hi - e.ct.lo);
+            const double tau = div_by_cached(ts - e.ct.lo, e.ct.hi - e.ct.lo, r_xt.y);
             const double omt = 1 - tau;
 #pragma unroll
             for (int c = 0; c < NC; ++c) {
@@ -329,7 +355,7 @@ struct AFastPolicy {
         if (k == 0) conv = (double)((float)g.deg2m * cos_np(deg2rad_np((float)ys)));
         else conv = g.deg2m * cos_np(deg2rad_np(ys));
         u = u / conv;
-        v = v / g.deg2m;
+        v = div_by_cached_guarded(v, g.deg2m, g.inv_deg2m);
     }
 
     // the generic skeleton's entry point is not used by a FAST_RK4 policy

@@ -23,6 +23,7 @@ struct GridDev {
     int spherical;
     int pad_;
     double deg2m;
+    double inv_deg2m;  // RN(1 / deg2m), for div_by_cached
     double time_len;  // time[nt-1] - time[0]
     long long xdim, ydim, zdim;  // cell counts for ravel_index
     // curvilinear grids (lon/lat are 2-D (ny, nx) arrays) + the spatial hash of _core/spatialhash.py
@@ -221,6 +222,26 @@ __device__ __forceinline__ long long up_idx(int i, int n) {  // np.clip(i + 1, 0
     return (long long)min(max(i + 1, 0), n - 1);
 }
 
+// a / b, correctly rounded, for a divisor whose correctly rounded reciprocal r = RN(1 / b) is at hand (a cached cell width, a
+// constant): q0 = RN(a r) is within 2 ulp of a / b, the first residual correction leaves it within 1/2 ulp + 2^-105 (faithful), and for
+// a faithful q and r = RN(1 / b) Markstein's correcting step  q + (a - b q) r  (residual exact by FMA) rounds to RN(a / b) -- the
+// same final step as the hardware-assisted division sequence, without its reciprocal refinement.  Explicit fma(): unaffected by
+// -fmad=false.  Valid while no intermediate leaves the normal range; oracle/division_check.c checks 4e8 cases against `/`.
+__device__ __forceinline__ double div_by_cached(double a, double b, double r) {
+    double q = a * r;
+    double e = fma(-b, q, a);
+    q = fma(e, r, q);
+    e = fma(-b, q, a);
+    return fma(e, r, q);
+}
+// the same for numerators that come from DATA (velocities): zeros (land), non-finite values and values near the ends of the
+// exponent range take the division itself
+__device__ __forceinline__ double div_by_cached_guarded(double a, double b, double r) {
+    const double m = fabs(a);
+    if (m >= 1e-280 && m <= 1e280) return div_by_cached(a, b, r);
+    return a == 0.0 ? a : a / b;
+}
+
 // u * 0.5 keeps u's dtype (Python float is weak)
 __device__ __forceinline__ double half_of(const Val& a) { return a.f32 ? (double)((float)a.v * 0.5f) : a.v * 0.5; }
 
@@ -250,7 +271,6 @@ __global__ void __launch_bounds__(PB_BLOCK_THREADS, PB_MINBLOCKS) advect_kernel(
         float x = p.P.x[i], y = p.P.y[i], z = p.P.z[i];
         float dx = p.P.dx[i], dy = p.P.dy[i], dz = p.P.dz[i];
         double t = p.P.t[i];
-        const long long pid = p.diffusion ? p.P.pid[i] : 0;
 
         typename Policy::Ctx e;
         Policy::init(e, p, p.P.ei[i]);
@@ -399,7 +419,14 @@ __global__ void __launch_bounds__(PB_BLOCK_THREADS, PB_MINBLOCKS) advect_kernel(
                     ddy = (yf32 ? (double)(syf / 6.0f) : sv / 6.0) * dtp;
                     ddz = (zf32 ? (double)(szf / 6.0f) : sw / 6.0) * dtp;
                 } else {
-                    ddx = su / 6.0 * dtp; ddy = sv / 6.0 * dtp; ddz = sw / 6.0 * dtp;
+                    if constexpr (Policy::FAST_RK4) {  // (u1 + 2 u2 + 2 u3 + u4) / 6.0 with the constant's reciprocal: same quotient
+                        constexpr double r6 = 1.0 / 6.0;
+                        ddx = div_by_cached_guarded(su, 6.0, r6) * dtp;
+                        ddy = div_by_cached_guarded(sv, 6.0, r6) * dtp;
+                        ddz = three_d ? div_by_cached_guarded(sw, 6.0, r6) * dtp : 0.0;
+                    } else {
+                        ddx = su / 6.0 * dtp; ddy = sv / 6.0 * dtp; ddz = sw / 6.0 * dtp;
+                    }
                 }
             } else {  // EE: u1*dt ; RK2: u2*dt
                 ddx = uk.v * dtp; ddy = vk.v * dtp; ddz = wk.v * dtp;
@@ -411,7 +438,7 @@ __global__ void __launch_bounds__(PB_BLOCK_THREADS, PB_MINBLOCKS) advect_kernel(
             // ---- DiffusionUniformKh (kernels/_advectiondiffusion.py:120-153) ----
             if (p.diffusion) {
                 double zx, zy;
-                wiener_normals(p.seed, p.rng_call, it, pid, zx, zy);
+                wiener_normals(p.seed, p.rng_call, it, p.P.pid[i], zx, zy);  // (the id is read when needed: one register pair less in the loop)
                 const double sq = sqrt(fabs(dtp));
                 const double dWx = zx * sq, dWy = zy * sq;
                 double khz = p.kh_zonal, khm = p.kh_meridional;

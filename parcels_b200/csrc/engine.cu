@@ -294,7 +294,8 @@ struct pb_engine {
     // particles
     DevBuf px, py, pz, pdx, pdy, pdz, pt, pstate, pei, ppid;
     DevBuf snap;  // snapshot of all particle arrays
-    long long snap_n = -1;  // particle count the snapshot was taken at (-1: none); any change of the resident set invalidates it
+    long long snap_n = -1;  // particle count the snapshot was taken at (-1: none); a new upload / compaction invalidates it
+    bool snap_pid = false;  // the snapshot holds the particle ids too
     // mode D (domain decomposition): alternate SoA for compaction, migration work buffers
     DevBuf ax, ay, az, adx, ady, adz, at, astate, aei, apid;
     DevBuf mdest, mkeep, mcount, mbounds;
@@ -445,6 +446,7 @@ static int32_t upload_zt(pb_engine* e, const void* depth, int64_t nz, int32_t co
     g.nz = (int)nz; g.nt = (int)nt;
     g.spherical = spherical ? 1 : 0;
     g.deg2m = spherical ? deg2m : 1.0;
+    g.inv_deg2m = 1.0 / g.deg2m;  // correctly rounded (host division): div_by_cached in afast.cu
     g.time_len = nt ? tnorm[nt - 1] : 0.0;
     e->time_host = tnorm;
     g.xdim = xdim_cells; g.ydim = ydim_cells; g.zdim = zdim_cells;
@@ -679,11 +681,13 @@ int32_t pb_particles_download_ids(pb_engine* e, int64_t n, int64_t* particle_id)
     return PB_OK;
 }
 
+// Snapshot layout: whole columns back to back at offsets that are multiples of the particle count AT SNAPSHOT TIME --
+// x y z dx dy dz (4 B) t (8 B) state ei (4 B) = 40 B per particle, then particle_id (8 B) when ids are resident.
 int32_t pb_particles_snapshot(pb_engine* e) {
     if (!e) return fail(PB_ERR_INVALID, "engine is NULL");
     CK(cudaSetDevice(e->device));
     const size_t n = (size_t)e->n;
-    int32_t rc = e->snap.ensure(n ? n * 40 : 1);
+    int32_t rc = e->snap.ensure(n ? n * 48 : 1);
     if (rc) return rc;
     char* s = (char*)e->snap.p;
     struct { void* src; size_t es; } a[] = {{e->px.p, 4}, {e->py.p, 4}, {e->pz.p, 4}, {e->pdx.p, 4}, {e->pdy.p, 4},
@@ -693,25 +697,40 @@ int32_t pb_particles_snapshot(pb_engine* e) {
         if (n) CK(cudaMemcpyAsync(s + off, c.src, n * c.es, cudaMemcpyDeviceToDevice, e->stream));
         off += n * c.es;
     }
+    if (e->have_pid && n) CK(cudaMemcpyAsync(s + off, e->ppid.p, n * 8, cudaMemcpyDeviceToDevice, e->stream));
     e->snap_n = (long long)n;
+    e->snap_pid = e->have_pid;
     return PB_OK;
 }
 
+// Restores the resident set to the snapshot: columns AND particle count (a domain-decomposed pass changes the count through
+// migration; the ids travel with the particles and come back with the snapshot).
 int32_t pb_particles_restore(pb_engine* e) {
     if (!e) return fail(PB_ERR_INVALID, "engine is NULL");
     CK(cudaSetDevice(e->device));
-    const size_t n = (size_t)e->n;
-    // the layout is whole columns at offsets that are multiples of the n AT SNAPSHOT TIME: a snapshot of another set size is garbage
-    if (e->snap_n != (long long)n || e->snap.bytes < n * 40)
-        return fail(PB_ERR_STATE, "no snapshot of the resident set to restore (snapshot of %lld particles, %lld resident)", e->snap_n, (long long)n);
+    if (e->snap_n < 0 || e->snap.bytes < (size_t)e->snap_n * (e->snap_pid ? 48 : 40))
+        return fail(PB_ERR_STATE, "no snapshot of the resident set to restore (the set was replaced or compacted since pb_particles_snapshot)");
+    if (e->pending) return fail(PB_ERR_STATE, "an advect call is pending: call pb_last_report first");
+    const size_t n = (size_t)e->snap_n;
+    if (e->snap_n != e->n && !e->snap_pid)
+        return fail(PB_ERR_STATE, "snapshot of %lld particles without ids cannot replace %lld resident ones", e->snap_n, (long long)e->n);
     char* s = (char*)e->snap.p;
-    struct { void* dst; size_t es; } a[] = {{e->px.p, 4}, {e->py.p, 4}, {e->pz.p, 4}, {e->pdx.p, 4}, {e->pdy.p, 4},
-                                            {e->pdz.p, 4}, {e->pt.p, 8}, {e->pstate.p, 4}, {e->pei.p, 4}};
+    struct { DevBuf* dst; size_t es; } a[] = {{&e->px, 4}, {&e->py, 4}, {&e->pz, 4}, {&e->pdx, 4}, {&e->pdy, 4},
+                                              {&e->pdz, 4}, {&e->pt, 8}, {&e->pstate, 4}, {&e->pei, 4}};
     size_t off = 0;
     for (auto& c : a) {
-        if (n) CK(cudaMemcpyAsync(c.dst, s + off, n * c.es, cudaMemcpyDeviceToDevice, e->stream));
+        int32_t rc = c.dst->ensure(n ? n * c.es : 1);  // (after a migration the current buffers may be the smaller alternates)
+        if (rc) return rc;
+        if (n) CK(cudaMemcpyAsync(c.dst->p, s + off, n * c.es, cudaMemcpyDeviceToDevice, e->stream));
         off += n * c.es;
     }
+    if (e->snap_pid) {
+        int32_t rc = e->ppid.ensure(n ? n * 8 : 1);
+        if (rc) return rc;
+        if (n) CK(cudaMemcpyAsync(e->ppid.p, s + off, n * 8, cudaMemcpyDeviceToDevice, e->stream));
+        e->have_pid = true;
+    }
+    e->n = (long long)n;
     return PB_OK;
 }
 
@@ -987,8 +1006,9 @@ int32_t pb_advect_host(pb_engine* e, const pb_advect_args* a, int64_t n, const p
         if (c < 9 || h->particle_id) {
             if ((rc = cols[c].buf->ensure(n ? (size_t)n * cols[c].es : 1))) return rc;
         }
-    if ((rc = e->snap.ensure(n ? (size_t)n * 40 : 1))) return rc;
+    if ((rc = e->snap.ensure(n ? (size_t)n * 48 : 1))) return rc;
     e->have_pid = h->particle_id != nullptr;
+    e->snap_pid = e->have_pid;
     e->n = n;
     e->snap_n = n;  // the chunks below write the start-of-interval copy
     p.lone_particle = n == 1;
@@ -1013,7 +1033,7 @@ int32_t pb_advect_host(pb_engine* e, const pb_advect_args* a, int64_t n, const p
             char* dev = (char*)cols[k].buf->p + (size_t)lo * cols[k].es;
             if (cols[k].src) CK(cudaMemcpyAsync(dev, (const char*)cols[k].src + (size_t)lo * cols[k].es, (size_t)m * cols[k].es, cudaMemcpyHostToDevice, st));
             else if (k >= 3 && k <= 5) CK(cudaMemsetAsync(dev, 0, (size_t)m * 4, st));  // dx / dy / dz not given: zeros
-            if (k < 9) {  // start-of-interval copy in pb_particles_snapshot's layout (whole columns back to back)
+            if (k < 9 || cols[k].src) {  // start-of-interval copy in pb_particles_snapshot's layout (whole columns back to back)
                 CK(cudaMemcpyAsync((char*)e->snap.p + snap_off + (size_t)lo * cols[k].es, dev, (size_t)m * cols[k].es, cudaMemcpyDeviceToDevice, st));
                 snap_off += (size_t)n * cols[k].es;
             }
@@ -1373,7 +1393,7 @@ int32_t pb_particles_remove_deleted(pb_engine* e, int64_t* n_left) {
     CK(cudaStreamSynchronize(e->stream));
     for (int k = 0; k < 10; ++k) std::swap(*cur[k], *alt[k]);
     e->n = keep;
-    e->snap_n = -1;
+    if (!e->snap_pid) e->snap_n = -1;  // (a snapshot with ids restores the whole pre-compaction set, count included)
     e->n_keep = keep;
     *n_left = keep;
     return PB_OK;
@@ -1450,7 +1470,7 @@ int32_t pb_migrate_unpack(pb_engine* e, const void* recvbuf_dev, int64_t n_in) {
     CK(cudaStreamSynchronize(e->stream));
     for (int k = 0; k < 10; ++k) std::swap(*cur[k], *alt[k]);
     e->n = n_new;
-    e->snap_n = -1;
+    if (!e->snap_pid) e->snap_n = -1;
     e->n_send = 0; e->n_keep = n_new;
     return PB_OK;
 }

@@ -144,21 +144,28 @@ def _sync(device):
 
 
 def _exchange(eng, counts, dist, device):
-    """One migration round: counts -> all_to_all -> records -> all_to_all -> unpack.  Returns #received.
+    """One migration round: every rank's per-destination counts -> ONE all-gather (each rank then knows what it sends, what it
+    receives and whether anybody moves at all) -> records packed on the device -> all_to_all -> unpack.
+    Returns (#records moving on ALL ranks, #received here).
 
-    NCCL: both all-to-alls run on device buffers (records never touch the host).  gloo (CPU tests / two
+    NCCL: the count matrix and the records stay on the device (records never touch the host).  gloo (CPU tests / two
     ranks sharing one GPU): the same device-side pack/unpack kernels, records staged through the host."""
     import torch
 
     world = dist.get_world_size()
     rank = dist.get_rank()
     n_out = int(counts.sum())
-    if dist.get_backend() == "nccl":
-        send_counts = torch.as_tensor(counts, dtype=torch.int64, device=device)
-        recv_counts = torch.empty(world, dtype=torch.int64, device=device)
-        dist.all_to_all_single(recv_counts, send_counts)
-        rc = recv_counts.cpu().numpy()
-        n_in = int(rc.sum())
+    nccl = dist.get_backend() == "nccl"
+    mine = torch.as_tensor(counts, dtype=torch.int64, device=device if nccl else "cpu")
+    matrix = torch.empty(world * world, dtype=torch.int64, device=mine.device)  # [src * world + dst]
+    dist.all_gather_into_tensor(matrix, mine)
+    m = matrix.cpu().numpy().reshape(world, world)
+    total = int(m.sum())
+    if total == 0:
+        return 0, 0
+    rc = m[:, rank]
+    n_in = int(rc.sum())
+    if nccl:
         sendbuf = torch.empty(max(n_out, 1) * RECORD_BYTES, dtype=torch.uint8, device=device)
         recvbuf = torch.empty(max(n_in, 1) * RECORD_BYTES, dtype=torch.uint8, device=device)
         eng.migrate_pack(sendbuf.data_ptr(), n_out)  # synchronises the engine stream before NCCL touches the buffer
@@ -167,7 +174,7 @@ def _exchange(eng, counts, dist, device):
                                input_split_sizes=[int(c) * RECORD_BYTES for c in counts])  # fmt: skip
         _sync(device)
         eng.migrate_unpack(recvbuf.data_ptr(), n_in)
-        return n_in
+        return total, n_in
     sendbuf = torch.empty(max(n_out, 1) * RECORD_BYTES, dtype=torch.uint8, device=device)
     eng.migrate_pack(sendbuf.data_ptr(), n_out)
     host = sendbuf[: n_out * RECORD_BYTES].cpu().numpy()
@@ -175,46 +182,36 @@ def _exchange(eng, counts, dist, device):
     chunks = [host[offs[r] : offs[r + 1]].tobytes() for r in range(world)]
     everyone = [None] * world
     dist.all_gather_object(everyone, chunks)
-    mine = b"".join(everyone[src][rank] for src in range(world))
-    n_in = len(mine) // RECORD_BYTES
-    recvbuf = torch.frombuffer(bytearray(mine) if mine else bytearray(RECORD_BYTES), dtype=torch.uint8).to(device)
+    got = b"".join(everyone[src][rank] for src in range(world))
+    assert len(got) == n_in * RECORD_BYTES
+    recvbuf = torch.frombuffer(bytearray(got) if got else bytearray(RECORD_BYTES), dtype=torch.uint8).to(device)
     _sync(device)
     eng.migrate_unpack(recvbuf.data_ptr(), n_in)
-    return n_in
+    return total, n_in
 
 
-def execute_decomposed(dfs: DecomposedFieldSet, pdata: dict, kernels, dt: float, endtime: float, dist, max_rounds=100000, seed=0,
-                       rng_call=1):
-    """``Kernel.execute`` over a domain-decomposed field: ``pdata`` is ANY shard of the particle set (it is
-    routed to the owners first).  Returns (local particle dict after the call, stats)."""
-    import torch
+def run_decomposed_resident(dfs: DecomposedFieldSet, plan, dt: float, endtime: float, dist, max_rounds=100000, seed=0, rng_call=1):
+    """The rounds of one ``Kernel.execute`` over a domain-decomposed field on the particles RESIDENT in the rank's engine (uploaded
+    with ``upload_decomposed`` or restored from a snapshot): advect until every particle reached ``endtime`` or left the slab ->
+    classify / count -> exchange -> resume ... until nobody moves.  Nothing crosses PCIe except the count matrix.  Returns stats."""
+    import time
 
-    from .particleset import KernelPlan
-    from .statuscodes import StatusCode
-
-    plan = KernelPlan(kernels, dfs.fs)
-    # fused DiffusionUniformKh: the Wiener increments are keyed by (seed; particle id, iteration of the launch, call index).  Every
-    # migration round is a new launch on every rank (the round count is global), so the round number joins the call index and no
-    # particle ever draws the same increment twice, wherever it migrates.  (The stream differs from a single-GPU run's, whose
-    # iterations are not cut into rounds: statistically equivalent, not bit-identical -- the advection-only path is.)
-    if not plan.delete_on_error:
-        raise NotImplementedError("domain-decomposed execution needs the DeleteParticle handler (errors cannot be replayed "
-                                  "step-exactly across ranks)")  # fmt: skip
     eng = dfs.engine
     device = _engine_memory_device(dfs.device)
-    pdata["state"][:] = StatusCode.Evaluate
-    pdata["dt"][:] = dt
-    eng.upload_particles(pdata, np.ascontiguousarray(pdata["ei"][:, -1]))
-    stats = dict(rounds=0, migrated=0, particle_steps=0, kernel_ms=0.0)
+    stats = dict(rounds=0, migrated=0, particle_steps=0, kernel_ms=0.0, exchange_ms=0.0)
     first = True
     for _ in range(max_rounds):
+        t0 = time.perf_counter()
         counts = eng.migrate_count()
-        moving = allreduce_sum(float(counts.sum()), dist, device)
-        if moving > 0:
-            stats["migrated"] += int(counts.sum())
-            _exchange(eng, counts, dist, device)
-        elif not first:
+        total, _ = _exchange(eng, counts, dist, device)
+        stats["exchange_ms"] += 1e3 * (time.perf_counter() - t0)
+        stats["migrated"] += int(counts.sum())
+        if total == 0 and not first:
             break
+        # fused DiffusionUniformKh: the Wiener increments are keyed by (seed; particle id, iteration of the launch, call index).  Every
+        # migration round is a new launch on every rank (the round count is global), so the round number joins the call index and no
+        # particle ever draws the same increment twice, wherever it migrates.  (The stream differs from a single-GPU run's, whose
+        # iterations are not cut into rounds: statistically equivalent, not bit-identical -- the advection-only path is.)
         rep = eng.advect(eng.make_args(plan.scheme, dt, endtime, delete_on_error=True, resume=not first, diffusion=plan.diffusion,
                                        kh=plan.kh, kh_spherical=plan.kh_spherical, kh_deg2m=plan.kh_deg2m, seed=seed,
                                        rng_call=(int(rng_call) << 20) + stats["rounds"]))  # fmt: skip
@@ -222,10 +219,45 @@ def execute_decomposed(dfs: DecomposedFieldSet, pdata: dict, kernels, dt: float,
         stats["rounds"] += 1
         stats["particle_steps"] += rep["particle_steps"]
         stats["kernel_ms"] += rep["kernel_ms"]
+        if rep["max_state"] == 99:  # every rank raises in the same round or the next count exchange would hang: agree first
+            stats["halo_violation"] = True
         if allreduce_max(float(rep["max_state"] == 99), dist, device) > 0:
             raise RuntimeError("halo violation: a stage position left the owned+halo columns; increase halo_cells or reduce dt")
-    out = eng.download_all(ngrids=pdata["ei"].shape[1])
+    return stats
+
+
+def decomposed_plan(dfs: DecomposedFieldSet, kernels):
+    from .particleset import KernelPlan
+
+    plan = KernelPlan(kernels, dfs.fs)
+    if not plan.delete_on_error:
+        raise NotImplementedError("domain-decomposed execution needs the DeleteParticle handler (errors cannot be replayed "
+                                  "step-exactly across ranks)")  # fmt: skip
+    return plan
+
+
+def upload_decomposed(dfs: DecomposedFieldSet, pdata: dict, dt: float):
+    from .statuscodes import StatusCode
+
+    pdata["state"][:] = StatusCode.Evaluate
+    pdata["dt"][:] = dt
+    dfs.engine.upload_particles(pdata, np.ascontiguousarray(pdata["ei"][:, -1]))
+
+
+def download_decomposed(dfs: DecomposedFieldSet, dt: float, ngrids=1) -> dict:
+    from .statuscodes import StatusCode
+
+    out = dfs.engine.download_all(ngrids=ngrids)
     out["dt"][:] = dt
     keep = out["state"] != StatusCode.Delete
-    out = {k: v[keep] for k, v in out.items()}
-    return out, stats
+    return {k: v[keep] for k, v in out.items()}
+
+
+def execute_decomposed(dfs: DecomposedFieldSet, pdata: dict, kernels, dt: float, endtime: float, dist, max_rounds=100000, seed=0,
+                       rng_call=1):
+    """``Kernel.execute`` over a domain-decomposed field: ``pdata`` is ANY shard of the particle set (it is
+    routed to the owners first).  Returns (local particle dict after the call, stats)."""
+    plan = decomposed_plan(dfs, kernels)
+    upload_decomposed(dfs, pdata, dt)
+    stats = run_decomposed_resident(dfs, plan, dt, endtime, dist, max_rounds=max_rounds, seed=seed, rng_call=rng_call)
+    return download_decomposed(dfs, dt, ngrids=pdata["ei"].shape[1]), stats

@@ -1,0 +1,86 @@
+"""Parity at the BASELINE configurations' STATED sizes ("parity is never checked on a BASELINE config at its stated
+size"): the full 1440 x 720 x 50 float64-axis grid of config 2 (also with the fused diffusion of config 4), the ORCA025-shape
+1021 x 1442 curvilinear mesh of config 3 (1.47 M faces: the bit-width budget search and the 2^20-entry bucket table only bite
+there) -- 20 000 particles each against the oracle, through the same routine bench.py prints as `parity_sample` -- and the
+device-built spatial-hash table against the host / reference construction at that size.
+
+Too big for the host simulation of the kernel sources (the CPU suite's run of the GPU tests skips this file)."""
+
+import os
+
+import numpy as np
+import pytest
+
+import bench
+import parcels_b200 as pb
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(os.environ.get("PB_HOSTSIM_TEST") == "1", reason="full-size workloads: real GPU only")]
+
+N = 20_000
+
+
+@pytest.fixture(scope="module")
+def c2():
+    w = bench.WORKLOADS["c2"]
+    field = w["field"](**w["fkw"])
+    fs = pb.FieldSet.from_arrays(lon=field["lon"], lat=field["lat"], depth=field["depth"], time=field["times"], U=field["U"], V=field["V"],
+                                 W=field["W"], mesh=field["mesh"])  # fmt: skip
+    yield field, fs
+    fs.release()
+
+
+def _check(par, *, deletions_expected=False):
+    assert par["ids_equal"], par
+    assert par["state_mismatch"] == 0 and par["t_mismatch"] == 0 and par["ei_mismatch"] == 0, par
+    assert par["max_ulp"] <= par["tolerance_ulp"], par
+    assert par["deleted_gpu"] == par["deleted_oracle"]
+    if deletions_expected:
+        assert par["deleted_gpu"] > 0
+    assert par["ok"]
+
+
+def test_config2_full_grid_against_the_oracle(c2):
+    field, fs = c2
+    par, cpu = bench.parity_and_cpu_baseline("c2", bench.WORKLOADS["c2"], field, fs, 0, N)
+    _check(par)
+    assert cpu["value"] > 0
+
+
+def test_config4_fused_diffusion_on_the_full_grid_against_the_oracle_fed_the_philox_normals(c2):
+    field, fs = c2
+    w = bench.WORKLOADS["c4"]
+    fs.add_constant_field("Kh_zonal", w["kh"][0], mesh=field["mesh"])
+    fs.add_constant_field("Kh_meridional", w["kh"][1], mesh=field["mesh"])
+    par, _ = bench.parity_and_cpu_baseline("c4", w, field, fs, 0, N)
+    _check(par)
+
+
+@pytest.fixture(scope="module")
+def c3():
+    w = bench.WORKLOADS["c3"]
+    field = w["field"](**w["fkw"])
+    fs = pb.FieldSet.from_arrays(lon=field["lon"], lat=field["lat"], depth=None, time=field["times"], U=field["U"], V=field["V"], W=None,
+                                 mesh=field["mesh"], interp_method=field["interp"], padding=field["padding"])  # fmt: skip
+    yield field, fs
+    fs.release()
+
+
+def test_config3_orca025_mesh_against_the_oracle(c3):
+    """ids of the survivors, states, times, cells bit-exact; positions <= 8 float32 ulp; the SAME particles are lost to state 52 /
+    deleted on both sides (the reference itself loses ~1 in 20 000 samples near cell edges there)."""
+    field, fs = c3
+    par, _ = bench.parity_and_cpu_baseline("c3", bench.WORKLOADS["c3"], field, fs, 0, N)
+    _check(par)
+
+
+def test_orca025_hash_table_built_on_the_device_equals_the_host_table(c3):
+    """csrc/hashbuild.cu (count -> scan -> expand -> radix sort -> CSR) vs parcels_b200/spatialhash.py (the reference's own NumPy
+    construction, _core/spatialhash.py:212-387) on the 1020 x 1441 faces: keys, starts, counts and the candidate order."""
+    from parcels_b200.spatialhash import build_spatial_hash
+
+    field, fs = c3
+    dev = fs.engine(0).hash_table()
+    host = build_spatial_hash(field["lon"], field["lat"], True, table=True)
+    assert dev["keys"].size > 3_000_000 and dev["faces"].size > 10_000_000
+    for k in ("keys", "starts", "counts", "faces"):
+        np.testing.assert_array_equal(dev[k], host[k], err_msg=k)

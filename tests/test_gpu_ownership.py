@@ -109,6 +109,28 @@ def test_restore_refuses_a_snapshot_of_another_set_size():
     eng.snapshot()
     eng.restore()
     d3 = {k: v[:3].copy() for k, v in d.items()}
-    eng.upload_particles(d3, np.zeros(3, dtype=np.int32))
+    eng.upload_particles(d3, np.zeros(3, dtype=np.int32))  # another set: the snapshot of the old one is void
     with pytest.raises(EngineError):
         eng.restore()
+
+
+def test_snapshot_survives_compaction_and_restores_count_and_ids():
+    """pb_particles_snapshot holds the whole set (ids included): after pb_particles_remove_deleted changed the count, restore
+    brings back the pre-compaction set -- what a domain-decomposed bench pass needs (migration changes the count every pass)."""
+    from parcels_b200.particle import create_particle_data
+    from parcels_b200.statuscodes import StatusCode
+
+    fs = _fieldset()
+    eng = fs.engine(0)
+    d = create_particle_data(nparticles=5, ngrids=1, initial=dict(x=np.linspace(10, 50, 5), y=np.full(5, 1.0), z=np.zeros(5), t=np.zeros(5),
+                                                                  particle_id=np.array([11, 12, 13, 14, 15])))  # fmt: skip
+    d["state"][[1, 3]] = StatusCode.Delete
+    eng.upload_particles(d, np.zeros(5, dtype=np.int32))
+    eng.snapshot()
+    assert eng.remove_deleted() == 3
+    assert eng.download_all()["particle_id"].tolist() == [11, 13, 15]
+    eng.restore()
+    back = eng.download_all()
+    assert eng.particle_count() == 5 and back["particle_id"].tolist() == [11, 12, 13, 14, 15]
+    np.testing.assert_array_equal(back["x"], d["x"])
+    np.testing.assert_array_equal(back["state"], d["state"])

@@ -32,3 +32,21 @@ def test_c_port_matches_numpy_oracle(mesh):
             np.testing.assert_array_equal(pd[k], ref[k], err_msg=k)
         else:
             assert ulp_diff_f32(pd[k], ref[k]).max() <= 1, k
+
+
+def test_cached_reciprocal_division_equals_the_division(tmp_path):
+    """csrc/common.cuh div_by_cached (q = a r + two residual corrections, r = RN(1 / b)) is the correctly rounded quotient:
+    4e7 cases of oracle/division_check.c (cell-width quotients, random mantissas, the constant divisors 111120 and 6,
+    quotients next to rounding midpoints) agree with `/` bit for bit."""
+    import os
+    import shutil
+    import subprocess
+
+    cc = shutil.which(os.environ.get("CC", "gcc"))
+    if cc is None:
+        pytest.skip("no C compiler")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "division_check")
+    subprocess.run([cc, "-O2", "-mfma", "-ffp-contract=off", os.path.join(root, "oracle", "division_check.c"), "-o", exe, "-lm"], check=True)
+    res = subprocess.run([exe, "40000000"], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0 and "bad5=0" in res.stdout, res.stdout + res.stderr
