@@ -8,6 +8,7 @@ whole per-particle time loop in hand-written sm_100a CUDA (``csrc/engine.cu``) t
 from . import kernels
 
 __version__ = "0.1.0"
+from .install import install, uninstall
 from .fieldset import EARTH_RADIUS, Field, FieldSet, SphericalMesh, VectorField, XGrid
 from .kernels import (
     AdvectionDiffusionEM,
@@ -40,5 +41,5 @@ __all__ = [
     "AdvectionDiffusionEM", "AdvectionDiffusionM1", "AdvectionEE", "AdvectionRK2", "AdvectionRK2_3D", "AdvectionRK4", "AdvectionRK4_3D", "AdvectionRK45", "DeleteParticle",
     "DiffusionUniformKh", "Field", "FieldInterpolationError", "FieldOutOfBoundError", "FieldOutOfBoundSurfaceError",
     "FieldSet", "GeneralError", "GridSearchingError", "Kernel", "KernelWarning", "OutsideTimeInterval", "ParticleSetWarning", "Particle", "ParticleClass", "ParticleFile", "ParticleSet", "Variable", "read_particlefile", "StatusCode",
-    "EARTH_RADIUS", "SphericalMesh", "VectorField", "XGrid", "kernels",
+    "EARTH_RADIUS", "SphericalMesh", "VectorField", "XGrid", "kernels", "install", "uninstall",
 ]  # fmt: skip

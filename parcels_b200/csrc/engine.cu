@@ -710,8 +710,7 @@ int32_t pb_particles_restore(pb_engine* e) {
     CK(cudaSetDevice(e->device));
     if (e->snap_n < 0 || e->snap.bytes < (size_t)e->snap_n * (e->snap_pid ? 48 : 40))
         return fail(PB_ERR_STATE, "no snapshot of the resident set to restore (the set was replaced or compacted since pb_particles_snapshot)");
-    if (e->pending) return fail(PB_ERR_STATE, "an advect call is pending: call pb_last_report first");
-    const size_t n = (size_t)e->snap_n;
+    const size_t n = (size_t)e->snap_n;  // (stream-ordered after a pending advect launch: restore + launch sequences need no host sync)
     if (e->snap_n != e->n && !e->snap_pid)
         return fail(PB_ERR_STATE, "snapshot of %lld particles without ids cannot replace %lld resident ones", e->snap_n, (long long)e->n);
     char* s = (char*)e->snap.p;

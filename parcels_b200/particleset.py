@@ -211,7 +211,8 @@ def _setup_rk45(self, names, fieldset, pclass):
     if "RK45_tol" not in ctx:
         warnings.warn("Setting RK45 tolerance to 10 m. Use fieldset.add_context('RK45_tol', [distance]) to change.", KernelWarning, stacklevel=4)
         fieldset.add_context("RK45_tol", 10)
-    if fieldset.grid.is_spherical():
+    if fieldset.grid.is_spherical() and not getattr(fieldset, "_context_is_reference", False):
+        # (under parcels_b200.install() the context mirrors the reference FieldSet's, whose own Kernel.__init__ has converted it)
         ctx["RK45_tol"] = ctx["RK45_tol"] / fieldset.grid.deg2m
     if "RK45_min_dt" not in ctx:
         warnings.warn("Setting RK45 minimum timestep to 1 s. Use fieldset.add_context('RK45_min_dt', [timestep]) to change.", KernelWarning, stacklevel=4)
