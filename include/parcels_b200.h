@@ -385,6 +385,17 @@ int32_t pb_delete_view_outside_time(pb_engine* e, double dt, double endtime);
 int32_t pb_debug_normals(pb_engine* e, uint64_t seed, uint64_t rng_call, int64_t iter, int64_t n,
                          const int64_t* particle_id, double* out);
 
+/* ---- host-side passes of Kernel.execute / ParticleSet.execute over the particle columns, multi-threaded ----------------
+ * The reference makes a few whole-column passes per call on the host: `pset._data["dt"][:] = dt` (_core/particleset.py:405,
+ * _core/kernel.py:225-226), `particle_release_times.min() / .max()` (_core/particleset.py:541-544), `state[:] = Evaluate`
+ * (_core/kernel.py:188).  At 1e7 particles a single NumPy thread spends longer on them than the device on the copies; these
+ * helpers split the column over a few host threads (memory-bandwidth bound).  No engine, no device. */
+int32_t pb_host_fill_f64(double* p, int64_t n, double value);
+int32_t pb_host_fill_i32(int32_t* p, int64_t n, int32_t value);
+/* min and max of p[0..n) ignoring NaNs; *has_nan = 1 when any element is NaN (NumPy's min / max then return NaN);
+ * n == 0: *mn = +inf, *mx = -inf */
+int32_t pb_host_min_max_f64(const double* p, int64_t n, double* mn, double* mx, int32_t* has_nan);
+
 #ifdef __cplusplus
 }
 #endif

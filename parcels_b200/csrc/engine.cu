@@ -28,6 +28,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <string>
 #include <type_traits>
 #include <vector>
@@ -321,6 +322,28 @@ static void zero_report(ReportDev& r) {
     r.first_error_iter = LLONG_MAX;
     r.wait_t_min_bits = ~0ULL;
 }
+
+// host-side column passes (pb_host_*): a column split over a few C++ threads
+#ifndef PB_HOSTSIM
+#include <thread>
+template <class F>
+static void host_parallel(int64_t n, F&& f) {
+    // a few threads saturate one socket's memory channels; small columns are not worth a thread start (~20 us each)
+    int nt = (int)std::min<int64_t>(8, std::max<int64_t>(1, n / (1 << 19)));
+    const unsigned hc = std::thread::hardware_concurrency();
+    if (hc && (unsigned)nt > hc) nt = (int)hc;
+    if (nt <= 1) { f(0, 0, n); return; }
+    std::vector<std::thread> th;
+    const int64_t per = (n + nt - 1) / nt;
+    for (int k = 1; k < nt; ++k) th.emplace_back([=, &f] { f(k, std::min<int64_t>(n, k * per), std::min<int64_t>(n, (k + 1) * per)); });
+    f(0, 0, std::min<int64_t>(n, per));
+    for (auto& t : th) t.join();
+}
+#else
+template <class F>
+static void host_parallel(int64_t n, F&& f) { f(0, 0, n); }
+#endif
+
 
 extern "C" {
 
@@ -1523,6 +1546,44 @@ int32_t pb_field_window_set(pb_engine* e, int64_t first_level, int64_t n_levels)
     CK(cudaEventRecord(e->copy_done, e->copy_stream));
     CK(cudaStreamWaitEvent(e->stream, e->copy_done, 0));
     e->win_first = first_level; e->win_n = n_levels;
+    return PB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host-side column passes (see include/parcels_b200.h): plain C++ threads, no device
+// ------------------------------------------------------------------------------------------------
+int32_t pb_host_fill_f64(double* p, int64_t n, double value) {
+    if (n < 0 || (n && !p)) return fail(PB_ERR_INVALID, "bad argument");
+    host_parallel(n, [=](int, int64_t lo, int64_t hi) { for (int64_t i = lo; i < hi; ++i) p[i] = value; });
+    return PB_OK;
+}
+
+int32_t pb_host_fill_i32(int32_t* p, int64_t n, int32_t value) {
+    if (n < 0 || (n && !p)) return fail(PB_ERR_INVALID, "bad argument");
+    host_parallel(n, [=](int, int64_t lo, int64_t hi) { for (int64_t i = lo; i < hi; ++i) p[i] = value; });
+    return PB_OK;
+}
+
+int32_t pb_host_min_max_f64(const double* p, int64_t n, double* mn, double* mx, int32_t* has_nan) {
+    if (n < 0 || (n && !p) || !mn || !mx || !has_nan) return fail(PB_ERR_INVALID, "bad argument");
+    double lo_[8], hi_[8];
+    int nan_[8];
+    for (int k = 0; k < 8; ++k) { lo_[k] = HUGE_VAL; hi_[k] = -HUGE_VAL; nan_[k] = 0; }
+    host_parallel(n, [&](int k, int64_t lo, int64_t hi) {
+        double a = HUGE_VAL, b = -HUGE_VAL;
+        int any = 0;
+        for (int64_t i = lo; i < hi; ++i) {
+            const double v = p[i];
+            any |= (v != v);
+            a = v < a ? v : a;  // (comparisons with NaN are false: NaNs are skipped)
+            b = v > b ? v : b;
+        }
+        lo_[k] = a; hi_[k] = b; nan_[k] = any;
+    });
+    double a = HUGE_VAL, b = -HUGE_VAL;
+    int any = 0;
+    for (int k = 0; k < 8; ++k) { a = lo_[k] < a ? lo_[k] : a; b = hi_[k] > b ? hi_[k] : b; any |= nan_[k]; }
+    *mn = a; *mx = b; *has_nan = any;
     return PB_OK;
 }
 

@@ -32,6 +32,41 @@ def _to_float_seconds(v):
     return float(v)
 
 
+def _fill(a, value):
+    """``a[:] = value``; whole float64 / int32 columns of a large set go through the library's multi-threaded pass
+    (pb_host_fill_*): at 1e7 particles one NumPy thread needs longer for `dt[:] = dt` than the device for the copies."""
+    if a.size >= (1 << 20) and a.flags.c_contiguous and a.dtype in (np.float64, np.int32):
+        from . import _lib
+
+        lib = _lib.load()
+        if a.dtype == np.float64:
+            _lib.check(lib.pb_host_fill_f64(_lib.ptr(a), a.size, float(value)))
+        else:
+            _lib.check(lib.pb_host_fill_i32(_lib.ptr(a), a.size, int(value)))
+    else:
+        a[:] = value
+
+
+def _min_or_max(t, want_min: bool) -> float:
+    """``t.min()`` / ``t.max()`` with NumPy's NaN propagation (any NaN -> NaN); large columns multi-threaded."""
+    if t.size >= (1 << 20) and t.flags.c_contiguous and t.dtype == np.float64:
+        import ctypes as C
+
+        from . import _lib
+
+        mn, mx, nan = C.c_double(), C.c_double(), C.c_int32()
+        _lib.check(_lib.load().pb_host_min_max_f64(_lib.ptr(t), t.size, C.byref(mn), C.byref(mx), C.byref(nan)))
+        return float("nan") if nan.value else (mn.value if want_min else mx.value)
+    return float(t.min() if want_min else t.max())
+
+
+def _store_ei(d, ei_last):
+    """``d["ei"][:, -1] = ei_last`` -- unless ``ei_last`` IS that column (one grid: the contiguous view the download wrote into)."""
+    col = d["ei"][:, -1]
+    if not (col.flags.c_contiguous and col.ctypes.data == ei_last.ctypes.data):
+        col[:] = ei_last
+
+
 def _has_nan(a) -> bool:
     """np.isnan(a).any() without the temporary: one NaN-propagating reduction (an inf - inf false positive is re-checked)."""
     s = a.sum() if len(a) else 0.0
@@ -326,7 +361,8 @@ class ParticleSet:
         self._host_stale = False
         self.eager_host = False  # True: refresh the host arrays at the end of every execute() (shared-array adapters)
         # > 1: Kernel.execute on host arrays runs as that many pipelined chunks (copies under kernels, pb_advect_host)
-        self.pipeline_chunks = int(os.environ.get("PB_PIPELINE_CHUNKS", "0"))
+        # (default 8: measured on the B200, profiles/README.md r02 -- copies of one chunk run under the kernels of the others)
+        self.pipeline_chunks = int(os.environ.get("PB_PIPELINE_CHUNKS", "8"))
         self._n_device = 0
         self._stale_dt = 1.0
         self.last_report = None
@@ -407,14 +443,14 @@ class ParticleSet:
             else:
                 ei_last = np.empty(len(d["x"]), dtype=np.int32)
                 eng.download_particles(d, ei_last)
-                d["ei"][:, -1] = ei_last
+                _store_ei(d, ei_last)
         else:
             new = eng.download_all(ngrids=len(self.fieldset.gridset))
             if d is None:
                 d = new
             else:  # keep the dict object: it may be shared with the caller (adapter.pset_from_parcels)
                 d.update(new)
-        d["dt"][:] = self._stale_dt  # kernel.py:225-226
+        _fill(d["dt"], self._stale_dt)  # kernel.py:225-226
         self._host = d
         self._host_stale = False
         self._device_synced = True
@@ -566,7 +602,10 @@ class ParticleSet:
         else:
             d = self._data
             n = len(self)
-            d["state"][:] = StatusCode.Evaluate
+            # kernel.py:188 `state[:] = Evaluate`: the device kernel resets the states itself (resume = 0) and every path below
+            # writes the states it ends with back to the host -- only the windowed path resumes launches from host-visible states
+            if self.fieldset.time_window is not None:
+                d["state"][:] = StatusCode.Evaluate
             if n == 0:
                 return
             if not self.__dict__.pop("_t_nan_free", False) and _has_nan(d["t"]):  # (execute() has just made that pass)
@@ -655,8 +694,8 @@ class ParticleSet:
             self._n_device = eng.remove_deleted() if deletions else n
             if downloaded and not deletions:  # the pipelined call has already brought the result back: host == device
                 self._host_stale = False
-                d["ei"][:, -1] = ei_last
-                d["dt"][:] = dt  # kernel.py:225-226
+                _store_ei(d, ei_last)
+                _fill(d["dt"], dt)  # kernel.py:225-226
                 self._device_synced = True
             else:
                 self._host_stale = True
@@ -678,7 +717,7 @@ class ParticleSet:
         else:
             if not downloaded:
                 eng.download_particles(d, ei_last)
-            d["ei"][:, -1] = ei_last
+            _store_ei(d, ei_last)
             d["dt"][:] = dt  # kernel.py:225-226
         # the device report says whether any particle was deleted / errored: the O(N) host scans of
         # kernel.py:98-106,239-245 only run when there is something to find
@@ -722,7 +761,7 @@ class ParticleSet:
                               delete_on_error=plan.delete_on_error, hint_all_zero=hint_all_zero, batch_levels=two_levels)  # fmt: skip
         self.last_report = rep
         eng.download_particles(d, ei_last)
-        d["ei"][:, -1] = ei_last
+        _store_ei(d, ei_last)
         d["dt"][:] = dt_arr  # RK45 mode: dt is NOT reset to the nominal step (kernel.py:224-226)
         d["next_dt"][:] = ndt_arr
         if rep["n_error"] > 0:
@@ -780,7 +819,7 @@ class ParticleSet:
             assert sign_dt in (-1, 1)
         except (ValueError, TypeError, AssertionError) as e:
             raise ValueError(f"dt must be a non-zero datetime.timedelta or np.timedelta64 object, got {dt=!r}") from e
-        self._data["dt"][:] = dt
+        _fill(self._data["dt"], dt)
         if runtime is not None:
             try:
                 runtime = _to_float_seconds(runtime)
@@ -798,7 +837,7 @@ class ParticleSet:
         t = self._data["t"]
         # `particle_release_times.min()` / `.max()` (reference particleset.py:541-544) PROPAGATE NaN: as soon as one release time
         # is unset the start time is the fieldset's start (`_get_start_time`, :575-585) and EVERY particle's t is set to it (:413-414)
-        first = t.min() if sign_dt == 1 else t.max()
+        first = _min_or_max(t, sign_dt == 1)
         any_nan = bool(np.isnan(first))
         if endtime is not None:
             origin = self.fieldset._time_origin
