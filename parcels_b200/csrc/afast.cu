@@ -373,16 +373,20 @@ bool agrid_fast_applies(const AdvectParams& p, bool coord_f64, bool data_f64, bo
     return p.g.nt >= 2 && p.g.nx >= 2 && p.g.ny >= 2;
 }
 
-template <int NC, bool HZ>
-static cudaError_t launch_fast1(const AdvectParams& p, cudaStream_t s) {
+template <int NC, bool HZ, bool DIFF>
+static cudaError_t launch_fast2(const AdvectParams& p, cudaStream_t s) {
     using Pol = AFastPolicy<NC, HZ>;
     const long long grid = (p.P.n + PB_FAST_BLOCK - 1) / PB_FAST_BLOCK;
     if (Pol::SMEM > 48 * 1024) {
-        cudaError_t ce = cudaFuncSetAttribute(advect_kernel<Pol>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Pol::SMEM);
+        cudaError_t ce = cudaFuncSetAttribute(advect_kernel<Pol, DIFF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Pol::SMEM);
         if (ce != cudaSuccess) return ce;
     }
-    advect_kernel<Pol><<<(unsigned)grid, PB_FAST_BLOCK, Pol::SMEM, s>>>(p);
+    advect_kernel<Pol, DIFF><<<(unsigned)grid, PB_FAST_BLOCK, Pol::SMEM, s>>>(p);
     return cudaGetLastError();
+}
+template <int NC, bool HZ>
+static cudaError_t launch_fast1(const AdvectParams& p, cudaStream_t s) {
+    return p.diffusion ? launch_fast2<NC, HZ, true>(p, s) : launch_fast2<NC, HZ, false>(p, s);
 }
 
 cudaError_t launch_agrid_fast(const AdvectParams& p, int nc, cudaStream_t s) {

@@ -258,14 +258,15 @@ __device__ __forceinline__ double half_of(const Val& a) { return a.f32 ? (double
 #else
 #define PB_BLOCK_THREADS 128
 #endif
-template <class Policy>
+// DIFF = false compiles the kernel without the DiffusionUniformKh block (the specialised RK4 kernel is instantiated both ways:
+// the advection-only hot path carries neither the Philox / Box-Muller code nor its loop-invariant registers)
+template <class Policy, bool DIFF = true>
 __global__ void __launch_bounds__(PB_BLOCK_THREADS, PB_MINBLOCKS) advect_kernel(const AdvectParams p) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    unsigned long long my_steps = 0, my_refills = 0;
+    unsigned long long my_steps = 0, my_refills = 0;  // (my_steps = the lane's iteration count, set on exit)
     int final_state = 0;
     long long my_iters = 0;
     bool errored = false, deleted = false, oot = false, migrate = false, wait_window = false;
-    long long err_iter = LLONG_MAX;
 
     if (i < p.P.n) {
         float x = p.P.x[i], y = p.P.y[i], z = p.P.z[i];
@@ -286,6 +287,13 @@ __global__ void __launch_bounds__(PB_BLOCK_THREADS, PB_MINBLOCKS) advect_kernel(
         const int nstage = (p.scheme == PB_ADVECTION_NONE) ? 0 : (p.scheme == PB_ADVECTION_EE) ? 1 : ((p.scheme == PB_ADVECTION_RK2 || p.scheme == PB_ADVECTION_RK2_3D) ? 2 : 4);
 
         bool ei_zeroed = false;
+        // DiffusionUniformKh: what does not change from step to step -- sqrt(|dt|) of the nominal step (the clamped last step takes
+        // its own) and the meridional coefficient sqrt(2 Kh_meridional [/ deg2m^2]) -- is computed once (same operations, same values)
+        [[maybe_unused]] double diff_sq = 0.0, diff_by = 0.0;
+        if (DIFF && p.diffusion) {
+            diff_sq = sqrt(fabs(p.dt));
+            diff_by = sqrt(2 * (p.kh_spherical ? p.kh_meridional / (p.kh_deg2m * p.kh_deg2m) : p.kh_meridional));
+        }
         long long it = 0;
         for (;; ++it) {
             if (p.max_iters >= 0 && it >= p.max_iters) break;
@@ -309,7 +317,6 @@ __global__ void __launch_bounds__(PB_BLOCK_THREADS, PB_MINBLOCKS) advect_kernel(
                     }
                 }
             }
-            my_steps++;
 
             // ---- advection kernel (kernels/_advection.py) ----
             Val u1, v1, w1, uk, vk, wk;
@@ -319,7 +326,7 @@ __global__ void __launch_bounds__(PB_BLOCK_THREADS, PB_MINBLOCKS) advect_kernel(
             [[maybe_unused]] float sxf = 0.f, syf = 0.f, szf = 0.f;
             // with DiffusionUniformKh in the list, ei[:, -1] was overwritten with 0 for every particle by the
             // constant-field evals of the previous step: curvilinear hints are all zero again
-            const bool nohint1 = (it == 0 && p.hint_all_zero) || (it > 0 && p.diffusion);
+            const bool nohint1 = (it == 0 && p.hint_all_zero) || (it > 0 && DIFF && p.diffusion);
             if constexpr (Policy::FAST_RK4) {
                 // afast.cu: float64 grid, float32 data -- every stage value is float64 (Val::f32 never set), one eval site,
                 // odd stages renew the T-lerped block, even stages reuse it (stages 2/3 and 4/next-1 share their sample time)
@@ -436,19 +443,18 @@ __global__ void __launch_bounds__(PB_BLOCK_THREADS, PB_MINBLOCKS) advect_kernel(
             if (three_d) dz = (float)((double)dz + ddz);
 
             // ---- DiffusionUniformKh (kernels/_advectiondiffusion.py:120-153) ----
-            if (p.diffusion) {
+            if (DIFF && p.diffusion) {
                 double zx, zy;
                 wiener_normals(p.seed, p.rng_call, it, p.P.pid[i], zx, zy);  // (the id is read when needed: one register pair less in the loop)
-                const double sq = sqrt(fabs(dtp));
+                const double sq = dtp == p.dt ? diff_sq : sqrt(fabs(dtp));
                 const double dWx = zx * sq, dWy = zy * sq;
-                double khz = p.kh_zonal, khm = p.kh_meridional;
+                double khz = p.kh_zonal;
                 if (p.kh_spherical) {
                     const float ang = (y * (float)3.14159265358979323846) / 180.0f;  // lat * np.pi / 180 in f32
                     const float m = (float)p.kh_deg2m * cosf(ang);
                     khz = khz / (double)(m * m);
-                    khm = khm / (p.kh_deg2m * p.kh_deg2m);
                 }
-                const double bx = sqrt(2 * khz), by = sqrt(2 * khm);
+                const double bx = sqrt(2 * khz), by = diff_by;
                 dx = (float)((double)dx + bx * dWx);
                 dy = (float)((double)dy + by * dWy);
                 ei_zeroed = true;  // the constant-field evals overwrite ei[:, -1] with cell 0 (model.py:292-318)
@@ -465,11 +471,12 @@ __global__ void __launch_bounds__(PB_BLOCK_THREADS, PB_MINBLOCKS) advect_kernel(
             }
             if (e.state == PB_EVALUATE && t == p.endtime) e.state = PB_END_OF_LOOP;  // :229-230
             if (e.state == PB_DELETE) { deleted = true; ++it; break; }
-            if (e.state >= 50) { errored = true; err_iter = it; ++it; break; }
+            if (e.state >= 50) { errored = true; ++it; break; }
         }
         Policy::finish(e, p);
         if (ei_zeroed) e.ei = 0;
         my_iters = it;
+        my_steps = (unsigned long long)it;  // every counted iteration evaluated the kernels once (breaks before that do not count)
         my_refills = e.refills;
         oot = e.out_of_time;
         final_state = e.state;
@@ -486,7 +493,7 @@ __global__ void __launch_bounds__(PB_BLOCK_THREADS, PB_MINBLOCKS) advect_kernel(
     unsigned n_err = errored, n_del = deleted, n_oot = oot, n_mig = migrate, n_ww = wait_window;
     // with the delete handler an out-of-interval sample is not an error of the lane, but the host still needs the iteration
     // it happened in (the reference deletes the WHOLE evaluated view of that iteration, field.py:31-44)
-    long long mx_it = my_iters, mn_err = (oot && deleted) ? my_iters - 1 : err_iter;
+    long long mx_it = my_iters, mn_err = ((oot && deleted) || errored) ? my_iters - 1 : LLONG_MAX;  // the iteration the error arose in
     int mx_state = final_state;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
