@@ -395,6 +395,12 @@ int32_t pb_host_fill_i32(int32_t* p, int64_t n, int32_t value);
 /* min and max of p[0..n) ignoring NaNs; *has_nan = 1 when any element is NaN (NumPy's min / max then return NaN);
  * n == 0: *mn = +inf, *mx = -inf */
 int32_t pb_host_min_max_f64(const double* p, int64_t n, double* mn, double* mx, int32_t* has_nan);
+/* Kernel.remove_deleted -> ParticleSet.remove_indices (_core/kernel.py:98-106, _core/particleset.py:247-250: np.delete on every
+ * column) for host arrays: rows with state == delete_state are dropped from `ncols` columns, order preserved, out of place
+ * (src[c] -> dst[c], row_bytes[c] bytes per row, dst sized for pb_host_count_keep rows); the rows are split over host threads. */
+int64_t pb_host_count_keep(const int32_t* state, int64_t n, int32_t delete_state);
+int32_t pb_host_compact(const int32_t* state, int64_t n, int32_t delete_state, int32_t ncols, const void* const* src,
+                        void* const* dst, const int64_t* row_bytes);
 
 #ifdef __cplusplus
 }

@@ -1587,4 +1587,50 @@ int32_t pb_host_min_max_f64(const double* p, int64_t n, double* mn, double* mx, 
     return PB_OK;
 }
 
+int64_t pb_host_count_keep(const int32_t* state, int64_t n, int32_t delete_state) {
+    if (n < 0 || (n && !state)) return -1;
+    long long part[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    host_parallel(n, [&](int k, int64_t lo, int64_t hi) {
+        long long c = 0;
+        for (int64_t i = lo; i < hi; ++i) c += state[i] != delete_state;
+        part[k] = c;
+    });
+    long long tot = 0;
+    for (int k = 0; k < 8; ++k) tot += part[k];
+    return tot;
+}
+
+int32_t pb_host_compact(const int32_t* state, int64_t n, int32_t delete_state, int32_t ncols, const void* const* src,
+                        void* const* dst, const int64_t* row_bytes) {
+    if (n < 0 || ncols < 0 || (n && !state) || (ncols && (!src || !dst || !row_bytes))) return fail(PB_ERR_INVALID, "bad argument");
+    // pass 1: kept rows per thread segment (the segments of pass 2 are the same: host_parallel is deterministic in n)
+    int64_t seg_lo[8], seg_keep[8];
+    for (int k = 0; k < 8; ++k) { seg_lo[k] = -1; seg_keep[k] = 0; }
+    host_parallel(n, [&](int k, int64_t lo, int64_t hi) {
+        int64_t c = 0;
+        for (int64_t i = lo; i < hi; ++i) c += state[i] != delete_state;
+        seg_lo[k] = lo; seg_keep[k] = c;
+    });
+    int64_t offs[8], acc = 0;
+    for (int k = 0; k < 8; ++k) { offs[k] = acc; acc += seg_keep[k]; }
+    // pass 2: every thread copies the kept RUNS of its segment (deletions are sparse: long memcpy runs)
+    host_parallel(n, [&](int k, int64_t lo, int64_t hi) {
+        int64_t out = offs[k], i = lo;
+        while (i < hi) {
+            while (i < hi && state[i] == delete_state) ++i;
+            int64_t j = i;
+            while (j < hi && state[j] != delete_state) ++j;
+            if (j > i) {
+                for (int c = 0; c < ncols; ++c) {
+                    const int64_t rb = row_bytes[c];
+                    memcpy((char*)dst[c] + out * rb, (const char*)src[c] + i * rb, (size_t)((j - i) * rb));
+                }
+                out += j - i;
+            }
+            i = j;
+        }
+    });
+    return PB_OK;
+}
+
 }  // extern "C"

@@ -328,11 +328,22 @@ class Engine:
         """Download the resident particle set (its size may have changed through migration)."""
         from .particle import create_particle_data
 
+        from .particle import _CORE
+
         n = self.particle_count()
-        d = create_particle_data(nparticles=n, ngrids=ngrids, initial={})
-        ei_last = np.zeros(n, dtype=np.int32)
-        self.download_particles(d, ei_last)
-        d["ei"][:, -1] = ei_last
+        if n < (1 << 16):
+            d = create_particle_data(nparticles=n, ngrids=ngrids, initial={})
+        else:  # every column below is overwritten by the download: no initial-value fills (11 passes over a large set)
+            d = {name: np.empty(n, dtype=dt) for name, dt in _CORE}
+            d["dt"][:] = 1.0  # (the caller sets the nominal dt)
+            d["ei"] = np.zeros((n, ngrids), dtype=np.int32) if ngrids > 1 else np.empty((n, 1), dtype=np.int32)
+        if ngrids == 1:
+            ei_last = d["ei"][:, 0]  # contiguous: the download writes the column in place
+            self.download_particles(d, ei_last)
+        else:
+            ei_last = np.zeros(n, dtype=np.int32)
+            self.download_particles(d, ei_last)
+            d["ei"][:, -1] = ei_last
         check(self._lib.pb_particles_download_ids(self._h, n, ptr(d["particle_id"])))
         return d
 

@@ -60,6 +60,36 @@ def _min_or_max(t, want_min: bool) -> float:
     return float(t.min() if want_min else t.max())
 
 
+def _remove_deleted_host(d: dict) -> int:
+    """Kernel.remove_deleted on host arrays (reference _core/kernel.py:98-106 -> np.delete on every column,
+    _core/particleset.py:247-250): drops the rows with state == Delete from EVERY column of ``d`` (the dict object is kept,
+    its arrays are replaced, as np.delete does).  Large sets go through the library's multi-threaded compaction."""
+    state = d["state"]
+    n = len(state)
+    if n >= (1 << 20) and all(v.flags.c_contiguous and len(v) == n for v in d.values()) and state.dtype == np.int32:
+        import ctypes as C
+
+        from . import _lib
+
+        lib = _lib.load()
+        keep = int(lib.pb_host_count_keep(_lib.ptr(state), n, int(StatusCode.Delete)))
+        if keep == n:
+            return 0
+        names = list(d)
+        new = {k: np.empty((keep, *d[k].shape[1:]), dtype=d[k].dtype) for k in names}
+        src = (C.c_void_p * len(names))(*(d[k].ctypes.data for k in names))
+        dst = (C.c_void_p * len(names))(*(new[k].ctypes.data for k in names))
+        rb = (C.c_int64 * len(names))(*(d[k].strides[0] if d[k].ndim > 1 else d[k].itemsize for k in names))
+        _lib.check(lib.pb_host_compact(_lib.ptr(state), n, int(StatusCode.Delete), len(names), src, dst, rb))
+        d.update(new)
+        return n - keep
+    dele = np.where(state == StatusCode.Delete)[0]
+    if len(dele):
+        for k in d:
+            d[k] = np.delete(d[k], dele, axis=0)
+    return len(dele)
+
+
 def _store_ei(d, ei_last):
     """``d["ei"][:, -1] = ei_last`` -- unless ``ei_last`` IS that column (one grid: the contiguous view the download wrote into)."""
     col = d["ei"][:, -1]
@@ -704,7 +734,7 @@ class ParticleSet:
             self._host_stale = True
             self._n_device = n
             d = self._data  # full download
-        elif (rep["n_deleted"] > 0 and rep["max_state"] < StatusCode.Error and len(self._pclass.extra) == 0
+        elif (rep["n_deleted"] > 0 and rep["max_state"] < StatusCode.Error and len(self._pclass.extra) == 0 and not downloaded
               and d["ei"].shape[1] == 1 and self.fieldset.time_window is None):  # fmt: skip
             # deletions, nothing to raise: drop the deleted particles in HBM (order preserved, like np.delete) and download the
             # compacted set -- instead of downloading everything and np.delete-ing every host array (kernel.py:98-106)
@@ -723,10 +753,7 @@ class ParticleSet:
         # kernel.py:98-106,239-245 only run when there is something to find
         self._device_synced = True  # host arrays == device arrays from here on (until the host compacts them)
         if rep["n_deleted"] > 0 or rep["max_state"] == StatusCode.Delete:
-            dele = np.where(d["state"] == StatusCode.Delete)[0]
-            if len(dele) > 0:
-                self.remove_indices(dele)
-                d = self._data
+            if _remove_deleted_host(d) > 0:
                 self._device_synced = False
         if rep["max_state"] >= StatusCode.Error:
             for code in ERRORS_TO_THROW:

@@ -32,7 +32,11 @@ def c2():
 def _check(par, *, deletions_expected=False):
     assert par["ids_equal"], par
     assert par["state_mismatch"] == 0 and par["t_mismatch"] == 0 and par["ei_mismatch"] == 0, par
-    assert par["max_ulp"] <= par["tolerance_ulp"], par
+    if "tolerance_quantile" in par:  # C-grid: the interpolant is discontinuous across cell faces (bench.parity_and_cpu_baseline)
+        assert par["outside_tolerance"] <= (1 - par["tolerance_quantile"]) * par["survivors_gpu"], par
+        assert par["max_ulp"] <= 256, par  # ... and even the outliers stay within a face discontinuity (metres)
+    else:
+        assert par["max_ulp"] <= par["tolerance_ulp"], par
     assert par["deleted_gpu"] == par["deleted_oracle"]
     if deletions_expected:
         assert par["deleted_gpu"] > 0

@@ -336,3 +336,37 @@ def test_pset_creation_like_the_reference():
     z6 = np.zeros((1, 6, 4, 5), np.float32)
     fsz = pb.FieldSet.from_arrays(lon=np.linspace(0, 1, 5), lat=np.linspace(0, 1, 4), depth=depths, U=z6, V=z6, mesh="flat")
     assert np.isclose(pb.ParticleSet(fsz, x=[0], y=[0]).z[0], 2.0)
+
+
+def test_host_column_passes_match_numpy():
+    """pb_host_fill_* / pb_host_min_max_f64 / pb_host_compact (multi-threaded host passes over particle columns; no device):
+    the results NumPy gives for `a[:] = v`, `a.min()` / `a.max()` with NaN propagation and np.delete on every column."""
+    import parcels_b200.particleset as P
+    from parcels_b200.statuscodes import StatusCode
+
+    rng = np.random.default_rng(0)
+    n = (1 << 21) + 12345
+    a = np.empty(n)
+    P._fill(a, 600.0)
+    assert a[0] == 600.0 and a[-1] == 600.0 and np.all(a == 600.0)
+    s = np.empty(n, dtype=np.int32)
+    P._fill(s, 10)
+    assert np.all(s == 10)
+    t = rng.uniform(-5.0, 7.0, n)
+    assert P._min_or_max(t, True) == t.min() and P._min_or_max(t, False) == t.max()
+    t[n // 3] = np.nan
+    assert np.isnan(P._min_or_max(t, True)) and np.isnan(P._min_or_max(t, False))
+    # compaction: every column of the SoA incl. the 2-D `ei` and an extra variable, order preserved
+    d = {"x": rng.random(n, dtype=np.float32), "t": rng.random(n), "particle_id": np.arange(n, dtype=np.int64),
+         "state": np.full(n, int(StatusCode.Evaluate), dtype=np.int32), "ei": rng.integers(0, 1000, (n, 2)).astype(np.int32),
+         "age": rng.random(n).astype(np.float32)}  # fmt: skip
+    dele = np.sort(rng.choice(n, 5000, replace=False))
+    dele = np.concatenate([dele, [0, n - 1]])
+    d["state"][dele] = int(StatusCode.Delete)
+    want = {k: np.delete(v, np.where(d["state"] == int(StatusCode.Delete))[0], axis=0) for k, v in d.items()}
+    ref = d
+    removed = P._remove_deleted_host(d)
+    assert removed == len(np.unique(dele)) and d is ref
+    for k in want:
+        assert d[k].shape == want[k].shape and np.array_equal(d[k], want[k]), k
+    assert P._remove_deleted_host(d) == 0
