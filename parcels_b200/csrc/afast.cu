@@ -102,16 +102,36 @@ __device__ __noinline__ double special_component(const float4* col, double tau, 
     return xlinear<float, double, double, double, double>(blk, tau, zeta, eta, xsi, two_t != 0, two_z != 0).v;
 }
 
+// a 16-byte shared-memory load the compiler must issue where it is written (no hoisting, no store-to-load forwarding)
+__device__ __forceinline__ double2 lds_volatile(const double2* p) {
+#ifdef PB_HOSTSIM
+    return *p;
+#else
+    double2 r;
+    const unsigned a = (unsigned)__cvta_generic_to_shared(p);
+    asm volatile("ld.volatile.shared.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "r"(a));
+    return r;
+#endif
+}
+
 // ------------------------------------------------------------------------------------------------
 // per-lane state
 // ------------------------------------------------------------------------------------------------
+// Everything a lane caches lives in SHARED MEMORY as 16-byte columns [chunk][lane] (LDS.128 / STS.128, conflict-free):
+//   raw block (float32)            NC * NV / 4 chunks
+//   T-lerped block (float64)       NC * NL / 2 chunks
+//   cells: {lo, hi} of z, y, x, t  4 chunks      -- read by the hit test of every evaluation, written by the side path only
+//   reciprocals of the cell widths 2 chunks      -- {1 / dz, 1 / dy}, {1 / dx, 1 / dt}, for div_by_cached
+// = 480 B per lane for UVW.  Keeping the cells out of the registers matters twice: the side path (which rewrites them) no longer
+// forces register-to-register copies onto the hit path (measured: 80 moves per evaluation, profiles/README.md r02d), and the
+// kernel's loop-carried state fits the register file without spills.  One 480-thread block per SM (15 warps).
 // A cell that the straight-line path may use has lo < hi finite and idx >= 0; after a search that ended on a sentinel
 // (or on the first node of the axis, bcoord == 0) lo = hi = NaN so that `x > lo && x <= hi` fails and the lane takes the
 // side path again at its next evaluation.
 struct FastCtx {
-    AxisCell<double> cx, cy, cz, ct;  // cx.idx etc. are also the key of the raw block and the indices `ei` is raveled from
+    int ti, zi, yi, xi;       // cell indices of the last search (-100: none): key of the raw block, and what `ei` is raveled from
     double lerp_t;            // sample time the T-lerped block in shared memory belongs to (-1: none)
-    float4* raw;              // this lane's column of raw chunks   [NC * NV / 4][PB_FAST_BLOCK]; lerped chunks follow
+    float4* raw;              // this lane's column of 16-byte chunks (raw block first, see the layout above)
     bool searched;
     int state;
     int ei;
@@ -129,8 +149,9 @@ struct AFastPolicy {
     static constexpr int NL = NV / 2;             // T-lerped values per component
     static constexpr int RAW_CHUNKS = NC * NV / 4;  // float4 columns
     static constexpr int LRP_CHUNKS = NC * NL / 2;  // double2 columns
+    static constexpr int CELL_CHUNKS = 4;           // double2 columns {lo, hi}: z, y, x, t
     static constexpr int RCP_CHUNKS = 2;            // double2 columns: {1 / dz, 1 / dy}, {1 / dx, 1 / dt} of the current cells
-    static constexpr size_t SMEM = (size_t)(RAW_CHUNKS + LRP_CHUNKS + RCP_CHUNKS) * 16 * PB_FAST_BLOCK;
+    static constexpr size_t SMEM = (size_t)(RAW_CHUNKS + LRP_CHUNKS + CELL_CHUNKS + RCP_CHUNKS) * 16 * PB_FAST_BLOCK;
     static constexpr bool RUNTIME_DTYPE = false;
     static constexpr bool FAST_RK4 = true;
     static constexpr bool F32_STAGES = false;
@@ -141,17 +162,24 @@ struct AFastPolicy {
     __device__ static __forceinline__ double2* lrp(const Ctx& e) {
         return reinterpret_cast<double2*>(e.raw + (size_t)RAW_CHUNKS * PB_FAST_BLOCK);
     }
+    // cell k (0: z, 1: y, 2: x, 3: t) as {lo, hi}
+    __device__ static __forceinline__ double2* cell(const Ctx& e, int k) {
+        return reinterpret_cast<double2*>(e.raw + (size_t)(RAW_CHUNKS + LRP_CHUNKS + k) * PB_FAST_BLOCK);
+    }
     // reciprocals of the cell widths (correctly rounded: computed by a division when the cell changes), for div_by_cached
     __device__ static __forceinline__ double2* rcp(const Ctx& e) {
-        return reinterpret_cast<double2*>(e.raw + (size_t)(RAW_CHUNKS + LRP_CHUNKS) * PB_FAST_BLOCK);
+        return reinterpret_cast<double2*>(e.raw + (size_t)(RAW_CHUNKS + LRP_CHUNKS + CELL_CHUNKS) * PB_FAST_BLOCK);
     }
 
     __device__ static __forceinline__ void init(Ctx& e, const AdvectParams&, int ei) {
         const double nan = __longlong_as_double(0x7ff8000000000000LL);
-        e.cx.idx = e.cy.idx = e.cz.idx = e.ct.idx = -100;
-        e.cx.lo = e.cx.hi = e.cy.lo = e.cy.hi = e.cz.lo = e.cz.hi = e.ct.lo = e.ct.hi = nan;
+        e.ti = e.zi = e.yi = e.xi = -100;
         extern __shared__ __align__(16) unsigned char pb_smem[];
         e.raw = reinterpret_cast<float4*>(pb_smem) + threadIdx.x;
+        double2 d;
+        d.x = nan; d.y = nan;
+#pragma unroll
+        for (int k = 0; k < CELL_CHUNKS; ++k) *cell(e, k) = d;
         e.lerp_t = -1.0;  // valid sample times are >= 0
         e.ei = ei;
         e.searched = false;
@@ -160,10 +188,10 @@ struct AFastPolicy {
     // ravel_index (basegrid.py:259-278) over the axes present of the last completed search; int64 arithmetic stored to int32
     __device__ static __forceinline__ void finish(Ctx& e, const AdvectParams& p) {
         if (!e.searched) return;
-        int gxi = e.cx.idx;
+        int gxi = e.xi;
         if (p.g.decomposed && gxi >= 0) gxi += p.g.xi_offset;  // mode D: local column -> global column
-        long long r = (long long)e.cy.idx * p.g.xdim + (long long)gxi;
-        if (p.g.nz > 0) r += (long long)(HZ ? e.cz.idx : 0) * (p.g.ydim * p.g.xdim);
+        long long r = (long long)e.yi * p.g.xdim + (long long)gxi;
+        if (p.g.nz > 0) r += (long long)(HZ ? e.zi : 0) * (p.g.ydim * p.g.xdim);
         e.ei = (int)r;
     }
 
@@ -213,11 +241,22 @@ struct AFastPolicy {
         const GridDev& g = p.g;
         const FieldDev& f = p.f;
         const bool renew = (k & 1) != 0;  // odd stages sample a new time: the T-lerped block is renewed; even stages reuse it
-        bool hit = xs > e.cx.lo && xs <= e.cx.hi && ys > e.cy.lo && ys <= e.cy.hi;
-        if (HZ) hit = hit && zs > e.cz.lo && zs <= e.cz.hi;
-        hit = hit && (renew ? (ts > e.ct.lo && ts <= e.ct.hi) : (ts == e.lerp_t));
-        bool lerp_now = renew;
-        if (!hit) {
+        // The cells are READ FROM SHARED MEMORY at every evaluation, on purpose: without this barrier the compiler keeps them in
+        // registers across evaluations (they only change in the side path) and pays for it with ~80 register moves per evaluation
+        // on the hit path plus spills of the particle state (volatile loads: neither NVVM nor ptxas may forward them).
+        bool lerp_now = renew, retried = false;
+        double2 bz, by, bx, bt;  // {lo, hi} of the current cells
+        // At most two trips: the hit test; on a miss the side path (which rewrites the cells IN SHARED MEMORY) and the test again.
+        // The cell values used below have ONE definition -- these loads -- so no register copies are needed where the paths join.
+        for (;;) {
+            bz = HZ ? lds_volatile(cell(e, 0)) : double2{0.0, 0.0};
+            by = lds_volatile(cell(e, 1));
+            bx = lds_volatile(cell(e, 2));
+            bt = (renew || retried) ? lds_volatile(cell(e, 3)) : double2{0.0, 0.0};  // (even stages test the cached lerp's time)
+            bool hit = xs > bx.x && xs <= bx.y && ys > by.x && ys <= by.y;
+            if (HZ) hit = hit && zs > bz.x && zs <= bz.y;
+            hit = hit && (renew ? (ts > bt.x && ts <= bt.y) : (ts == e.lerp_t));
+            if (hit || retried) break;
             // ---------------- side path: searches, states, refill; special samples are finished here ----------------
             if (!(0 <= ts && ts <= g.time_len)) {  // OutsideTimeInterval (index_search.py:85-86): state 70, sample (0, 0, 0)
                 e.state = PB_ERROR_OUTSIDE_TIME_INTERVAL;
@@ -225,9 +264,8 @@ struct AFastPolicy {
                 u = v = w = 0.0;
                 return;
             }
-            // (the cells are worked on in copies and written back at the end of the side path: the hit path then shares its
-            // registers with the values of the previous evaluation instead of receiving them through moves)
-            AxisCell<double> ct = e.ct, cz = e.cz, cy = e.cy, cx = e.cx;
+            if (!renew) bt = lds_volatile(cell(e, 3));
+            AxisCell<double> ct{e.ti, bt.x, bt.y}, cz{e.zi, bz.x, bz.y}, cy{e.yi, by.x, by.y}, cx{e.xi, bx.x, bx.y};
             const int oti = ct.idx, ozi = cz.idx, oyi = cy.idx, oxi = cx.idx;  // key of the raw block
             const double wt = ct.hi - ct.lo, wz = cz.hi - cz.lo, wy = cy.hi - cy.lo, wx = cx.hi - cx.lo;  // (NaN for a poisoned cell)
             if (oti >= 0 && !(ct.lo == ct.lo)) ct.idx = -100;  // (a poisoned cell is not a neighbour-search seed)
@@ -258,7 +296,7 @@ struct AFastPolicy {
                     rp[PB_FAST_BLOCK] = d;
                 }
             }
-            e.ct = ct; e.cz = cz; e.cy = cy; e.cx = cx;
+            e.ti = ti; e.zi = zi; e.yi = yi; e.xi = xi;
             if (g.decomposed) {  // mode D: a sentinel at a slab edge that is not the edge of the global domain = halo too small
                 if ((xi == -2 && !g.left_global) || (xi == -1 && !g.right_global)) e.state = max(e.state, 99);
             }
@@ -272,10 +310,22 @@ struct AFastPolicy {
             }
             // special: a sentinel index, or a sample not strictly inside (lo, hi] of the time / depth cell (tau or zeta == 0 on the
             // first node: lenT / lenZ == 1 for this particle, _xinterpolators.py:130-131; NaN; a degenerate cell)
-            const bool t_in = ts > e.ct.lo && ts <= e.ct.hi, z_in = !HZ || (zs > e.cz.lo && zs <= e.cz.hi);
-            if (xi < 0 || yi < 0 || zi < 0 || !t_in || !z_in) {
-                const double tau = axis_bcoord(g.nt, ts, e.ct), zeta = HZ ? axis_bcoord(g.nz, zs, e.cz) : 0.0;
-                const double eta = axis_bcoord(g.ny, ys, e.cy), xsi = axis_bcoord(g.nx, xs, e.cx);
+            const bool t_in = ts > ct.lo && ts <= ct.hi, z_in = !HZ || (zs > cz.lo && zs <= cz.hi);
+            const bool special = xi < 0 || yi < 0 || zi < 0 || !t_in || !z_in;
+            {   // write the cells back; the ones a special sample involved are poisoned so that the lane comes back here next time
+                const double nan = __longlong_as_double(0x7ff8000000000000LL);
+                double2 d;
+                d.x = ct.lo; d.y = ct.hi; if (!t_in) { d.x = nan; d.y = nan; }
+                *cell(e, 3) = d;
+                if (HZ) { d.x = cz.lo; d.y = cz.hi; if (zi < 0 || !z_in) { d.x = nan; d.y = nan; } *cell(e, 0) = d; }
+                d.x = cy.lo; d.y = cy.hi; if (yi < 0) { d.x = nan; d.y = nan; }
+                *cell(e, 1) = d;
+                d.x = cx.lo; d.y = cx.hi; if (xi < 0) { d.x = nan; d.y = nan; }
+                *cell(e, 2) = d;
+            }
+            if (special) {
+                const double tau = axis_bcoord(g.nt, ts, ct), zeta = HZ ? axis_bcoord(g.nz, zs, cz) : 0.0;
+                const double eta = axis_bcoord(g.ny, ys, cy), xsi = axis_bcoord(g.nx, xs, cx);
                 const bool two_t = tau > 0;             // lenT, per particle (float64 grid: no dtype depends on the batch)
                 const bool two_z = HZ && !(zeta <= 0);  // lenZ, per particle (a NaN depth must poison the value)
                 u = special_component<NV>(e.raw, tau, zeta, eta, xsi, two_t, two_z);
@@ -285,29 +335,24 @@ struct AFastPolicy {
                 if (u != u || v != v || w != w) s = max(s, (int)PB_ERROR_INTERPOLATION);
                 if (xi < 0 || yi < 0 || zi < 0) { u = 0.0; v = 0.0; w = 0.0; }
                 e.state = s;
-                // the cells involved are poisoned so that the lane comes back here at its next evaluation
-                const double nan = __longlong_as_double(0x7ff8000000000000LL);
-                if (!t_in) { e.ct.lo = nan; e.ct.hi = nan; }
-                if (HZ && (zi < 0 || !z_in)) { e.cz.lo = nan; e.cz.hi = nan; }
-                if (yi < 0) { e.cy.lo = nan; e.cy.hi = nan; }
-                if (xi < 0) { e.cx.lo = nan; e.cx.hi = nan; }
                 return;
             }
             e.state = s;
             lerp_now = true;  // (an even stage after a cell change: its block has to be lerped for this sample time first)
+            retried = true;
         }
         // ---------------- straight-line path: every cell is current, 0 < bcoord <= 1 on every axis ----------------
         // bcoord = (x - lo) / (hi - lo), index_search.py:57 (denominator in the axis dtype), with the cell width's cached reciprocal
         const double2 r_zy = rcp(e)[0], r_xt = rcp(e)[PB_FAST_BLOCK];
-        const double zeta = HZ ? div_by_cached(zs - e.cz.lo, e.cz.hi - e.cz.lo, r_zy.x) : 0.0;
-        const double eta = div_by_cached(ys - e.cy.lo, e.cy.hi - e.cy.lo, r_zy.y);
-        const double xsi = div_by_cached(xs - e.cx.lo, e.cx.hi - e.cx.lo, r_xt.x);
+        const double zeta = HZ ? div_by_cached(zs - bz.x, bz.y - bz.x, r_zy.x) : 0.0;
+        const double eta = div_by_cached(ys - by.x, by.y - by.x, r_zy.y);
+        const double xsi = div_by_cached(xs - bx.x, bx.y - bx.x, r_xt.x);
         const double omz = 1 - zeta;
         const double w00 = (1 - xsi) * (1 - eta), w01 = xsi * (1 - eta), w10 = (1 - xsi) * eta, w11 = xsi * eta;
         double2* const lp = lrp(e);
         double q[3] = {0.0, 0.0, 0.0};
         if (lerp_now) {
-            const double tau = div_by_cached(ts - e.ct.lo, e.ct.hi - e.ct.lo, r_xt.y);
+            const double tau = div_by_cached(ts - bt.x, bt.y - bt.x, r_xt.y);
             const double omt = 1 - tau;
 #pragma unroll
             for (int c = 0; c < NC; ++c) {
