@@ -670,6 +670,8 @@ def run_decomposed_bench(a, rank, local_rank, world, dist, workload="c5"):
     fs = pb.FieldSet.from_arrays(lon=f["lon"][f["lo"] : f["hi"] + 1].copy(), lat=f["lat"], depth=f["depth"], time=f["times"],
                                  U=f["U"], V=f["V"], W=f["W"], mesh="spherical", xdim=f["lon"].size - 1)  # fmt: skip
     dfs = D.DecomposedFieldSet.from_slab(fs, f["plan"], rank=rank, world=world, device=local_rank)
+    if a.mode_d_transport == "p2p":  # in-kernel migration over peer memory: the advection kernel delivers the leavers itself
+        D.connect_p2p(dfs, dist, max(n_per_gpu // 8, 4096))
     rng = np.random.default_rng(100 + rank)
     b = f["plan"]["bounds"]
     # every rank seeds its particles inside its own slab (as a domain-decomposed application would); whatever
@@ -743,8 +745,11 @@ def run_decomposed_bench(a, rank, local_rank, world, dist, workload="c5"):
         "workload": f"{workload}: BASELINE.json configs[4] -- AdvectionRK4_3D, rectilinear {dims['nx']}x{dims['ny']}x{dims['nz']} "
                     f"T={dims['nt']} f32 field DOMAIN-DECOMPOSED into {world} X-slabs (+{halo} halo columns), {n_per_gpu} "
                     f"particles/GPU seeded in the rank's own slab, NCCL all-to-all-v migration; dt={dt:g} s x {nsteps} steps",
-        "timed_region": "particles resident in HBM (restored from a snapshot every pass): advect kernels + migration rounds (classify / "
-                        "count all-gather / pack / all-to-all-v / unpack), wall clock between barrier + synchronize, max over ranks",
+        "transport": st.get("transport"),
+        "timed_region": "particles resident in HBM (restored from a snapshot every pass): advect kernels + migration rounds (p2p: records "
+                        "stored into the new owner's inbox by the advection kernel over NVLink, one 2-value all-reduce + compact/append "
+                        "per round; collective: classify / count all-gather / pack / all-to-all-v / unpack), wall clock between "
+                        "barrier + synchronize, max over ranks",
         "e2e": {"value": e_steps / e_t, "unit": "particle-steps/s", "steps": k_e2e, "h2d_bytes_per_step": n * 48 * world,
                 "d2h_bytes_per_step": n * 48 * world, "timed_region": "host particle arrays in, host arrays out"},
         "migrations_per_pass": tot_mig / steps, "advect_rounds_per_pass": rounds, "particles_after_pass": n_after,
@@ -753,7 +758,7 @@ def run_decomposed_bench(a, rank, local_rank, world, dist, workload="c5"):
     }  # fmt: skip
 
 
-def decomposed_bitexact_check(rank, local_rank, world, dist, n=200_000):
+def decomposed_bitexact_check(rank, local_rank, world, dist, n=200_000, transport="p2p"):
     """Mode D over NCCL against ONE GPU, bit for bit (scripts/decomposed_check.py inside the bench, so that the driver's
     multi-GPU box exercises it): a small field cut into `world` slabs, many slab crossings."""
     import parcels_b200 as pb
@@ -769,6 +774,8 @@ def decomposed_bitexact_check(rank, local_rank, world, dist, n=200_000):
     full = create_particle_data(nparticles=n, ngrids=1, initial=dict(x=x, y=y, z=z, t=np.zeros(n), particle_id=np.arange(n)))
     dfs = D.DecomposedFieldSet(lon=f["lon"], lat=f["lat"], depth=f["depth"], time=f["times"], U=f["U"], V=f["V"], W=f["W"],
                                mesh="spherical", rank=rank, world=world, halo_cells=3, device=local_rank)
+    if transport == "p2p":
+        D.connect_p2p(dfs, dist, n // 4)
     out, stats = D.execute_decomposed(dfs, D.shard_particles(full, rank, world), [pb.AdvectionRK4_3D, pb.DeleteParticle], dt, runtime, dist)
     tot = D.allreduce_sum(stats["migrated"], dist, device=f"cuda:{local_rank}")
     merged = D.gather_particles(out, dist, dst=0)
@@ -783,7 +790,7 @@ def decomposed_bitexact_check(rank, local_rank, world, dist, n=200_000):
     ref = ps._data
     bad = [k for k in ("particle_id", "state", "t", "ei", "x", "y", "z") if not (merged[k].shape == ref[k].shape and np.array_equal(merged[k], ref[k]))]
     fs.release()
-    return {"particles": n, "survivors": int(len(ref["x"])), "migrations": int(tot), "rounds": stats["rounds"], "backend": dist.get_backend(),
+    return {"particles": n, "survivors": int(len(ref["x"])), "migrations": int(tot), "rounds": stats["rounds"], "backend": dist.get_backend(), "transport": stats["transport"],
             "bit_exact_vs_one_gpu": not bad, "mismatching_columns": bad}  # fmt: skip
 
 
@@ -805,6 +812,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip parity_sample / cpu_baseline (the oracle legs)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-mode-d", action="store_true", help="N > 1: skip the domain-decomposed block")
+    ap.add_argument("--mode-d-transport", default="p2p", choices=["p2p", "collective"],
+                    help="mode D: p2p = in-kernel migration over peer memory (CUDA IPC + NVLink), collective = NCCL all-to-all-v")
     ap.add_argument("--pipeline", type=int, default=-1,
                     help="chunks of the pipelined host-array path of the end-to-end arm (ParticleSet.pipeline_chunks; -1: the library default)")
     ap.add_argument("--sorted", action="store_true",
@@ -844,7 +853,7 @@ def main():
             raise SystemExit("workload c5 is the domain-decomposed mode: launch with torchrun on >= 2 GPUs")
         with ClockSampler(local_rank) as clk:
             md = run_decomposed_bench(a, rank, local_rank, world, dist, name)
-        chk = decomposed_bitexact_check(rank, local_rank, world, dist)
+        chk = decomposed_bitexact_check(rank, local_rank, world, dist, transport=a.mode_d_transport)
         dist.barrier()
         dist.destroy_process_group()
         if rank == 0:
@@ -875,7 +884,7 @@ def main():
     if world > 1 and not a.no_mode_d:
         torch.cuda.empty_cache()
         mode_d = run_decomposed_bench(a, rank, local_rank, world, dist, "c5" if name == "ns" else "c5_small")
-        chk = decomposed_bitexact_check(rank, local_rank, world, dist)
+        chk = decomposed_bitexact_check(rank, local_rank, world, dist, transport=a.mode_d_transport)
         if mode_d is not None:
             mode_d["bitexact_check"] = chk
     if dist is not None:

@@ -367,6 +367,23 @@ int32_t pb_decomp_set(pb_engine* e, int32_t nranks, int32_t rank, const double* 
 int32_t pb_migrate_count(pb_engine* e, int64_t* counts /* [nranks] records to send to each rank */);
 int32_t pb_migrate_pack(pb_engine* e, void* sendbuf_dev, int64_t capacity_records);
 int32_t pb_migrate_unpack(pb_engine* e, const void* recvbuf_dev, int64_t n_in);
+
+/* In-kernel migration over peer memory (one box: NVLink / NVSwitch).  No reference counterpart.  Every rank owns an INBOX
+ * (two slots of `capacity_records` 48-byte records + an arrival counter each) in its own HBM; its peers map it through CUDA IPC.
+ * Once connected, pb_advect itself delivers a particle that left the owned slab: the lane claims a slot in the new owner's inbox
+ * with one system-scope atomic and stores the record there (pb_report.n_migrate = records delivered + records that found the
+ * inbox full and wait on this rank for the next round).  There is no pack pass and no all-to-all.
+ * Set-up:  pb_migrate_p2p_init (allocates the inbox; returns its 64-byte IPC handle and, for peers living in the SAME process,
+ *          its address) -> the caller exchanges handles / addresses (e.g. torch.distributed.all_gather_object) ->
+ *          pb_migrate_p2p_connect(handles[nranks * 64] or NULL, local_bases[nranks] or NULL; a non-zero local base wins).
+ * Round:   pb_advect(resume = round > 0) on every rank -> a BARRIER that orders every rank's kernel before the next call
+ *          (e.g. the all-reduce of n_migrate that also decides termination) -> pb_migrate_p2p_finish: drops the delivered
+ *          records from the resident set (order-preserving), appends the arrivals, flips to the other inbox slot.  Every rank
+ *          calls it in every round.  Repeat until the all-reduced n_migrate is 0. */
+#define PB_IPC_HANDLE_BYTES 64
+int32_t pb_migrate_p2p_init(pb_engine* e, int64_t capacity_records, uint8_t* ipc_handle /* [64] or NULL */, uint64_t* local_base /* or NULL */);
+int32_t pb_migrate_p2p_connect(pb_engine* e, const uint8_t* ipc_handles, const uint64_t* local_bases);
+int32_t pb_migrate_p2p_finish(pb_engine* e, int64_t* n_arrived, int64_t* n_resident);
 #define PB_MIGRATION_RECORD_BYTES 48
 /* particle ids in device order (after migrations the order on a rank is arbitrary) */
 int32_t pb_particles_download_ids(pb_engine* e, int64_t n, int64_t* particle_id);

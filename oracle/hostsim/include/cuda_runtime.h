@@ -63,6 +63,8 @@ inline double __longlong_as_double(long long v) { double r; std::memcpy(&r, &v, 
 template <class T>
 inline T atomicAdd(T* p, T v) { T o = *p; *p = o + v; return o; }
 template <class T>
+inline T atomicAdd_system(T* p, T v) { T o = *p; *p = o + v; return o; }
+template <class T>
 inline T atomicMax(T* p, T v) { T o = *p; if (v > o) *p = v; return o; }
 template <class T>
 inline T atomicOr(T* p, T v) { T o = *p; *p = o | v; return o; }
@@ -123,6 +125,14 @@ inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) {
     return cudaSuccess;
 }
 inline cudaError_t cudaGetLastError() { return cudaSuccess; }
+// CUDA IPC: the simulated "device" memory is private to the process -- peers of the same process are linked by address
+struct cudaIpcMemHandle_t {
+    char reserved[64];
+};
+enum { cudaIpcMemLazyEnablePeerAccess = 1 };
+inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t* h, void*) { std::memset(h, 0, sizeof(*h)); return cudaSuccess; }
+inline cudaError_t cudaIpcOpenMemHandle(void**, cudaIpcMemHandle_t, unsigned) { return cudaErrorInvalidValue; }
+inline cudaError_t cudaIpcCloseMemHandle(void*) { return cudaSuccess; }
 inline const char* cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error" : "hostsim error"; }
 template <class T>
 inline cudaError_t cudaMalloc(T** p, size_t n) { *p = (T*)std::malloc(n ? n : 1); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }

@@ -90,10 +90,39 @@ struct ParticlesDev {
     long long n;
 };
 
+// mode D, in-kernel migration over peer memory (NVLink): every rank owns a double-buffered INBOX in its HBM that its peers map
+// (CUDA IPC); a lane whose particle left the owned slab claims a slot in the new owner's inbox with one system-scope atomic and
+// stores the 48-byte record there itself -- the exchange runs inside the advection kernel, there is no pack pass and no
+// all-to-all.  Layout of an inbox allocation: [header 0][header 1][cap records of slot 0][cap records of slot 1].
+constexpr int PB_MIG_MAX_RANKS = 16;
+constexpr int PB_MIG_HEADER_BYTES = 256;       // one header per slot: the arrival counter (+ padding to its own sectors)
+constexpr int PB_STATE_MIGRATED = 97;          // engine-internal: the record now lives on another rank (dropped by pb_migrate_p2p_finish)
+struct MigRecord {  // 48 B per migrating particle
+    double t;
+    long long pid;
+    float x, y, z, dx, dy, dz;
+    int state, ei;
+};
+struct MigDev {
+    unsigned char* peer[PB_MIG_MAX_RANKS];  // base of every rank's inbox allocation as mapped into THIS process (own one included)
+    const double* bounds;                   // nranks + 1 slab edges
+    long long cap;                          // records per inbox slot
+    int nranks, rank;
+    int slot;                               // inbox slot of this round (0 / 1, flipped by every pb_migrate_p2p_finish)
+    int on;
+};
+__host__ __device__ __forceinline__ unsigned long long* mig_counter(unsigned char* base, int slot) {
+    return reinterpret_cast<unsigned long long*>(base + (size_t)slot * PB_MIG_HEADER_BYTES);
+}
+__host__ __device__ __forceinline__ MigRecord* mig_records(unsigned char* base, int slot, long long cap) {
+    return reinterpret_cast<MigRecord*>(base + 2 * (size_t)PB_MIG_HEADER_BYTES + (size_t)slot * (size_t)cap * sizeof(MigRecord));
+}
+
 struct AdvectParams {
     GridDev g;
     FieldDev f;
     ParticlesDev P;
+    MigDev mig;
     int scheme, diffusion, delete_on_error, kh_spherical;
     double dt, endtime, kh_zonal, kh_meridional, kh_deg2m;
     unsigned long long seed, rng_call;
@@ -485,6 +514,26 @@ __global__ void __launch_bounds__(PB_BLOCK_THREADS, PB_MINBLOCKS) advect_kernel(
         p.P.t[i] = t;
         p.P.state[i] = e.state;
         p.P.ei[i] = e.ei;
+        if (migrate && p.mig.on) {
+            // in-kernel migration: new owner = the slab that holds x (rank 0 owns (-inf, b1), the last rank [b_{n-1}, +inf));
+            // a NaN x has no owner: it stays (and is not counted as a mover)
+            const double xd = (double)x;
+            int r = 0;
+            while (r + 1 < p.mig.nranks && xd >= p.mig.bounds[r + 1]) ++r;
+            if (xd != xd || r == p.mig.rank) migrate = false;
+            else {
+                unsigned char* const base = p.mig.peer[r];
+                const unsigned long long slot = atomicAdd_system(mig_counter(base, p.mig.slot), 1ULL);
+                if (slot < (unsigned long long)p.mig.cap) {  // (a full inbox: the particle waits here for the next round)
+                    MigRecord rec;
+                    rec.t = t; rec.pid = p.P.pid[i];
+                    rec.x = x; rec.y = y; rec.z = z; rec.dx = dx; rec.dy = dy; rec.dz = dz;
+                    rec.state = e.state; rec.ei = e.ei;
+                    mig_records(base, p.mig.slot, p.mig.cap)[slot] = rec;
+                    p.P.state[i] = PB_STATE_MIGRATED;
+                }
+            }
+        }
     }
 
     // ---- report: warp-reduce then one atomic per warp ----

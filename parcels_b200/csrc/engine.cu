@@ -81,12 +81,7 @@ __global__ void normals_kernel(unsigned long long seed, unsigned long long rng_c
 // ------------------------------------------------------------------------------------------------
 // migration kernels (mode D)
 // ------------------------------------------------------------------------------------------------
-struct MigRecord {  // 48 B per migrating particle
-    double t;
-    long long pid;
-    float x, y, z, dx, dy, dz;
-    int state, ei;
-};
+// (MigRecord: common.cuh)
 
 // dest[i] = destination rank of particle i, or -1 if it stays.  A particle moves iff it still has to be
 // advanced (state Evaluate) and its x lies outside this rank's owned interval [bounds[rank], bounds[rank+1]).
@@ -151,7 +146,8 @@ __global__ void mig_unpack(ParticlesDev dst, long long base, const MigRecord* __
 //                particleset.py:247-250: np.delete keeps the storage order)
 // Three passes: per-block count, one-block scan of the block counts, per-block ordered scatter of the indices.
 // ------------------------------------------------------------------------------------------------
-enum { SEL_OUTPUT = 0, SEL_ALIVE = 1 };
+//   SEL_RESIDENT: state != PB_STATE_MIGRATED  (mode D with in-kernel migration: the record was stored in its new owner's inbox)
+enum { SEL_OUTPUT = 0, SEL_ALIVE = 1, SEL_RESIDENT = 2 };
 constexpr int SEL_BLOCK = 256;
 
 struct SelectRule {
@@ -161,6 +157,7 @@ struct SelectRule {
 
 __device__ __forceinline__ bool sel_flag(const ParticlesDev& P, const SelectRule& r, long long i) {
     if (r.mode == SEL_ALIVE) return P.state[i] != PB_DELETE;
+    if (r.mode == SEL_RESIDENT) return P.state[i] != PB_STATE_MIGRATED;
     const double t = P.t[i];
     return isfinite(t) && r.lo <= t && r.hi >= t;
 }
@@ -305,6 +302,14 @@ struct pb_engine {
     DevBuf samp_d, samp_i;  // scratch of pb_sample_velocity / pb_sample_scalar (grown on demand, reused across calls)
     long long* h_sel_total = nullptr;  // pinned
     long long n_selected = -1;
+    // in-kernel migration over peer memory: own inbox allocation, every rank's inbox as mapped here, the slot of this round
+    unsigned char* mig_base = nullptr;
+    unsigned char* mig_peer[PB_MIG_MAX_RANKS] = {};
+    bool mig_ipc_opened[PB_MIG_MAX_RANKS] = {};
+    long long mig_cap = 0;
+    int mig_slot = 0;
+    bool mig_on = false;
+    unsigned long long* h_mig_count = nullptr;  // pinned
     int nranks = 1, rank = 0;
     long long n_keep = 0, n_send = 0;
     std::vector<long long> send_counts;
@@ -398,6 +403,10 @@ void pb_engine_destroy(pb_engine* e) {
                       &e->pdx, &e->pdy, &e->pdz, &e->pt, &e->pstate, &e->pei, &e->ppid, &e->snap, &e->sblock, &e->soffs, &e->sidx, &e->sout,
                       &e->samp_d, &e->samp_i})
         b->release();
+    for (int r = 0; r < PB_MIG_MAX_RANKS; ++r)
+        if (e->mig_ipc_opened[r]) cudaIpcCloseMemHandle(e->mig_peer[r]);
+    if (e->mig_base) cudaFree(e->mig_base);
+    if (e->h_mig_count) cudaFreeHost(e->h_mig_count);
     if (e->d_rep) cudaFree(e->d_rep);
     if (e->h_rep) cudaFreeHost(e->h_rep);
     if (e->h_sel_total) cudaFreeHost(e->h_sel_total);
@@ -956,6 +965,15 @@ static int32_t prepare_advect(pb_engine* e, const pb_advect_args* a, AdvectParam
     p.batch_levels = a->batch_levels;
     p.g.off_x = e->g.off_x; p.g.off_y = e->g.off_y; p.g.off_z = e->g.off_z;
     p.rep = e->d_rep;
+    if (e->mig_on && e->g.decomposed) {
+        if (!e->have_pid) return fail(PB_ERR_STATE, "migration needs particle_id");
+        for (int r = 0; r < e->nranks; ++r) p.mig.peer[r] = e->mig_peer[r];
+        p.mig.bounds = (const double*)e->mbounds.p;
+        p.mig.cap = e->mig_cap;
+        p.mig.nranks = e->nranks; p.mig.rank = e->rank;
+        p.mig.slot = e->mig_slot;
+        p.mig.on = 1;
+    }
     return PB_OK;
 }
 
@@ -1497,6 +1515,104 @@ int32_t pb_migrate_unpack(pb_engine* e, const void* recvbuf_dev, int64_t n_in) {
     return PB_OK;
 }
 
+
+// ---- in-kernel migration over peer memory (NVLink / NVSwitch) ----
+// The advection kernel itself stores a leaving particle's record into the new owner's inbox (common.cuh, MigDev); the host side
+// is the set-up (allocate the inbox, exchange CUDA-IPC handles, map the peers) and, once per round and AFTER a barrier that
+// orders every rank's kernel before it, pb_migrate_p2p_finish: drop the records that left, append the arrivals, flip the slot.
+int32_t pb_migrate_p2p_init(pb_engine* e, int64_t capacity_records, uint8_t* ipc_handle, uint64_t* local_base) {
+    if (!e || capacity_records < 1) return fail(PB_ERR_INVALID, "bad argument");
+    if (e->nranks < 2 || !e->g.decomposed) return fail(PB_ERR_STATE, "pb_decomp_set (>= 2 ranks) not called");
+    if (e->nranks > PB_MIG_MAX_RANKS) return fail(PB_ERR_INVALID, "in-kernel migration supports <= %d ranks", PB_MIG_MAX_RANKS);
+    if (e->mig_base) return fail(PB_ERR_STATE, "pb_migrate_p2p_init called twice");
+    CK(cudaSetDevice(e->device));
+    const size_t bytes = 2 * (size_t)PB_MIG_HEADER_BYTES + 2 * (size_t)capacity_records * sizeof(MigRecord);
+    void* p = nullptr;
+    CK(cudaMalloc(&p, bytes));  // (its own allocation: IPC handles export whole allocations)
+    e->mig_base = (unsigned char*)p;
+    CK(cudaMemsetAsync(p, 0, 2 * (size_t)PB_MIG_HEADER_BYTES, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    e->mig_cap = capacity_records;
+    e->mig_slot = 0;
+    if (!e->h_mig_count) CK(cudaMallocHost((void**)&e->h_mig_count, 8));
+    if (ipc_handle) {
+        cudaIpcMemHandle_t h;
+        CK(cudaIpcGetMemHandle(&h, p));
+        static_assert(sizeof(h) == PB_IPC_HANDLE_BYTES, "cudaIpcMemHandle_t size");
+        memcpy(ipc_handle, &h, sizeof(h));
+    }
+    if (local_base) *local_base = (uint64_t)(uintptr_t)p;
+    return PB_OK;
+}
+
+int32_t pb_migrate_p2p_connect(pb_engine* e, const uint8_t* ipc_handles, const uint64_t* local_bases) {
+    if (!e || (!ipc_handles && !local_bases)) return fail(PB_ERR_INVALID, "NULL argument");
+    if (!e->mig_base) return fail(PB_ERR_STATE, "pb_migrate_p2p_init not called");
+    CK(cudaSetDevice(e->device));
+    for (int r = 0; r < e->nranks; ++r) {
+        if (r == e->rank) { e->mig_peer[r] = e->mig_base; continue; }
+        if (local_bases && local_bases[r]) {  // a peer engine of THIS process: its pointer is valid here as it is
+            e->mig_peer[r] = (unsigned char*)(uintptr_t)local_bases[r];
+            continue;
+        }
+        if (!ipc_handles) return fail(PB_ERR_INVALID, "no handle for rank %d", r);
+        cudaIpcMemHandle_t h;
+        memcpy(&h, ipc_handles + (size_t)r * PB_IPC_HANDLE_BYTES, sizeof(h));
+        void* q = nullptr;
+        cudaError_t ce = cudaIpcOpenMemHandle(&q, h, cudaIpcMemLazyEnablePeerAccess);
+        if (ce != cudaSuccess) return fail(PB_ERR_CUDA, "cudaIpcOpenMemHandle(rank %d): %s", r, cudaGetErrorString(ce));
+        e->mig_peer[r] = (unsigned char*)q;
+        e->mig_ipc_opened[r] = true;
+    }
+    e->mig_on = true;
+    return PB_OK;
+}
+
+int32_t pb_migrate_p2p_finish(pb_engine* e, int64_t* n_in_out, int64_t* n_now) {
+    if (!e) return fail(PB_ERR_INVALID, "engine is NULL");
+    if (!e->mig_on) return fail(PB_ERR_STATE, "pb_migrate_p2p_connect not called");
+    if (e->pending) return fail(PB_ERR_STATE, "an advect call is pending: call pb_last_report first");
+    CK(cudaSetDevice(e->device));
+    const int slot = e->mig_slot;
+    CK(cudaMemcpyAsync(e->h_mig_count, mig_counter(e->mig_base, slot), 8, cudaMemcpyDeviceToHost, e->stream));
+    long long keep = 0;
+    int32_t rc = run_select(e, SelectRule{SEL_RESIDENT, 0.0, 0.0}, &keep);  // (synchronises the stream: the count above is in)
+    if (rc) return rc;
+    if (e->n == 0) CK(cudaStreamSynchronize(e->stream));
+    e->n_selected = -1;
+    const unsigned long long arrived = *e->h_mig_count;
+    const long long n_in = (long long)(arrived < (unsigned long long)e->mig_cap ? arrived : (unsigned long long)e->mig_cap);
+    if (keep != e->n || n_in > 0) {
+        const long long n_new = keep + n_in;
+        const size_t cap = n_new ? (size_t)n_new : 1;
+        DevBuf* alt[10] = {&e->ax, &e->ay, &e->az, &e->adx, &e->ady, &e->adz, &e->at, &e->astate, &e->aei, &e->apid};
+        DevBuf* cur[10] = {&e->px, &e->py, &e->pz, &e->pdx, &e->pdy, &e->pdz, &e->pt, &e->pstate, &e->pei, &e->ppid};
+        const size_t es[10] = {4, 4, 4, 4, 4, 4, 8, 4, 4, 8};
+        for (int k = 0; k < 10; ++k)
+            if ((rc = alt[k]->ensure(cap * es[k] + (cap * es[k]) / 4))) return rc;
+        ParticlesDev dst{(float*)e->ax.p, (float*)e->ay.p, (float*)e->az.p, (float*)e->adx.p, (float*)e->ady.p, (float*)e->adz.p,
+                         (double*)e->at.p, (int*)e->astate.p, (int*)e->aei.p, (long long*)e->apid.p, n_new};
+        if (keep > 0) {
+            mig_compact<<<(unsigned)((keep + 255) / 256), 256, 0, e->stream>>>(cur_particles(e), dst, (const long long*)e->sidx.p, keep);
+            CK(cudaGetLastError());
+        }
+        if (n_in > 0) {
+            mig_unpack<<<(unsigned)((n_in + 255) / 256), 256, 0, e->stream>>>(dst, keep, mig_records(e->mig_base, slot, e->mig_cap), n_in);
+            CK(cudaGetLastError());
+        }
+        CK(cudaStreamSynchronize(e->stream));
+        for (int k = 0; k < 10; ++k) std::swap(*cur[k], *alt[k]);
+        e->n = n_new;
+        if (!e->snap_pid) e->snap_n = -1;
+        e->n_keep = n_new;
+    }
+    // this slot is written again two rounds from now, after at least one more barrier: reset its counter now
+    CK(cudaMemsetAsync(mig_counter(e->mig_base, slot), 0, 8, e->stream));
+    e->mig_slot ^= 1;
+    if (n_in_out) *n_in_out = n_in;
+    if (n_now) *n_now = e->n;
+    return PB_OK;
+}
 
 // ------------------------------------------------------------------------------------------------
 // time-slab streaming: GPU analogue of the reference's WindowedArray

@@ -5,11 +5,19 @@ contiguously by rank.  Particles do not interact on this path, so the step loop 
 ``torch.distributed`` only assembles results / timings (NCCL on GPUs, gloo in the CPU tests).
 
 Mode D (domain decomposition, config 5): the rectilinear field is cut into X-slabs (+ halo columns), one per
-GPU; a particle is advanced by the rank that owns its longitude and MIGRATES when it leaves the slab:
-device-side classify/pack kernels (``csrc/engine.cu``) -> counts exchanged with ``all_to_all_single`` ->
-48-byte particle records exchanged with ``all_to_all_single`` (NCCL over NVLink) -> device-side
-compact+append -> the kernel resumes.  Trajectories are bit-identical to a single-GPU run because every
-particle-step sees the same grid values (the slab is a slice of the global axis; ``ei`` stays global).
+GPU; a particle is advanced by the rank that owns its longitude and MIGRATES when it leaves the slab.
+Two transports:
+
+* **peer memory (default over NCCL, one box)** -- ``connect_p2p``: every rank owns an inbox in its HBM that its
+  peers map through CUDA IPC; the ADVECTION KERNEL ITSELF stores a leaving particle's 48-byte record into the new
+  owner's inbox over NVLink (one system-scope atomic claims the slot), so the exchange overlaps the advection of
+  the stayers and there is no classify / pack pass and no all-to-all.  Per round the host does one tiny
+  all-reduce (the barrier that also decides termination) and ``migrate_p2p_finish`` (compact + append).
+* **collectives (gloo tests, fallback)** -- device-side classify/pack kernels (``csrc/engine.cu``) -> count
+  matrix all-gather -> 48-byte records exchanged with ``all_to_all_single`` -> device-side compact+append.
+
+Trajectories are bit-identical to a single-GPU run either way because every particle-step sees the same grid
+values (the slab is a slice of the global axis; ``ei`` stays global).
 """
 
 from __future__ import annotations
@@ -190,15 +198,69 @@ def _exchange(eng, counts, dist, device):
     return total, n_in
 
 
+def connect_p2p(dfs: DecomposedFieldSet, dist, capacity_records: int):
+    """Set up in-kernel migration over peer memory for ``dfs`` (every rank calls it): allocate the inbox, all-gather the CUDA-IPC
+    handles, map the peers.  ``capacity_records``: arrivals one rank can take per round (a full inbox only delays the overflow by
+    a round).  From here on ``run_decomposed_resident`` uses the peer-memory rounds."""
+    handle, _ = dfs.engine.migrate_p2p_init(capacity_records)
+    everyone = [None] * dist.get_world_size()
+    dist.all_gather_object(everyone, handle)
+    dfs.engine.migrate_p2p_connect(handles=everyone)
+    dfs.p2p = True
+
+
+def _advect_args(eng, plan, dt, endtime, first, seed, rng_call, rounds):
+    # fused DiffusionUniformKh: the Wiener increments are keyed by (seed; particle id, iteration of the launch, call index).  Every
+    # migration round is a new launch on every rank (the round count is global), so the round number joins the call index and no
+    # particle ever draws the same increment twice, wherever it migrates.  (The stream differs from a single-GPU run's, whose
+    # iterations are not cut into rounds: statistically equivalent, not bit-identical -- the advection-only path is.)
+    return eng.make_args(plan.scheme, dt, endtime, delete_on_error=True, resume=not first, diffusion=plan.diffusion, kh=plan.kh,
+                         kh_spherical=plan.kh_spherical, kh_deg2m=plan.kh_deg2m, seed=seed, rng_call=(int(rng_call) << 20) + rounds)  # fmt: skip
+
+
+def run_decomposed_p2p(dfs: DecomposedFieldSet, plan, dt: float, endtime: float, dist, max_rounds=100000, seed=0, rng_call=1):
+    """The rounds of one ``Kernel.execute`` with in-kernel migration: advect (leavers are delivered to their new owners by the
+    kernel itself) -> all-reduce of (#movers, halo flag) = the barrier that orders every rank's kernel before anybody reads an
+    inbox -> ``migrate_p2p_finish`` -> resume ... until nobody moved."""
+    import time
+
+    import torch
+
+    eng = dfs.engine
+    device = _engine_memory_device(dfs.device)
+    stats = dict(rounds=0, migrated=0, particle_steps=0, kernel_ms=0.0, exchange_ms=0.0, transport="peer memory (in-kernel)")
+    for _ in range(max_rounds):
+        rep = eng.advect(_advect_args(eng, plan, dt, endtime, stats["rounds"] == 0, seed, rng_call, stats["rounds"]))
+        t0 = time.perf_counter()
+        flags = torch.tensor([float(rep["n_migrate"]), float(rep["max_state"] == 99)], dtype=torch.float64,
+                             device=device if dist.get_backend() == "nccl" else "cpu")
+        dist.all_reduce(flags, op=dist.ReduceOp.SUM)
+        moved, halo = (int(v) for v in flags.cpu().tolist())
+        eng.migrate_p2p_finish()
+        stats["exchange_ms"] += 1e3 * (time.perf_counter() - t0)
+        stats["rounds"] += 1
+        stats["migrated"] += int(rep["n_migrate"])
+        stats["particle_steps"] += rep["particle_steps"]
+        stats["kernel_ms"] += rep["kernel_ms"]
+        if halo:
+            stats["halo_violation"] = True
+            raise RuntimeError("halo violation: a stage position left the owned+halo columns; increase halo_cells or reduce dt")
+        if moved == 0:
+            break
+    return stats
+
+
 def run_decomposed_resident(dfs: DecomposedFieldSet, plan, dt: float, endtime: float, dist, max_rounds=100000, seed=0, rng_call=1):
     """The rounds of one ``Kernel.execute`` over a domain-decomposed field on the particles RESIDENT in the rank's engine (uploaded
     with ``upload_decomposed`` or restored from a snapshot): advect until every particle reached ``endtime`` or left the slab ->
     classify / count -> exchange -> resume ... until nobody moves.  Nothing crosses PCIe except the count matrix.  Returns stats."""
     import time
 
+    if getattr(dfs, "p2p", False):
+        return run_decomposed_p2p(dfs, plan, dt, endtime, dist, max_rounds=max_rounds, seed=seed, rng_call=rng_call)
     eng = dfs.engine
     device = _engine_memory_device(dfs.device)
-    stats = dict(rounds=0, migrated=0, particle_steps=0, kernel_ms=0.0, exchange_ms=0.0)
+    stats = dict(rounds=0, migrated=0, particle_steps=0, kernel_ms=0.0, exchange_ms=0.0, transport="collectives (all_to_all_single)")
     first = True
     for _ in range(max_rounds):
         t0 = time.perf_counter()
@@ -208,13 +270,7 @@ def run_decomposed_resident(dfs: DecomposedFieldSet, plan, dt: float, endtime: f
         stats["migrated"] += int(counts.sum())
         if total == 0 and not first:
             break
-        # fused DiffusionUniformKh: the Wiener increments are keyed by (seed; particle id, iteration of the launch, call index).  Every
-        # migration round is a new launch on every rank (the round count is global), so the round number joins the call index and no
-        # particle ever draws the same increment twice, wherever it migrates.  (The stream differs from a single-GPU run's, whose
-        # iterations are not cut into rounds: statistically equivalent, not bit-identical -- the advection-only path is.)
-        rep = eng.advect(eng.make_args(plan.scheme, dt, endtime, delete_on_error=True, resume=not first, diffusion=plan.diffusion,
-                                       kh=plan.kh, kh_spherical=plan.kh_spherical, kh_deg2m=plan.kh_deg2m, seed=seed,
-                                       rng_call=(int(rng_call) << 20) + stats["rounds"]))  # fmt: skip
+        rep = eng.advect(_advect_args(eng, plan, dt, endtime, first, seed, rng_call, stats["rounds"]))
         first = False
         stats["rounds"] += 1
         stats["particle_steps"] += rep["particle_steps"]

@@ -321,6 +321,29 @@ class Engine:
     def migrate_unpack(self, recvbuf_ptr: int, n_in: int):
         check(self._lib.pb_migrate_unpack(self._h, C.c_void_p(recvbuf_ptr), int(n_in)))
 
+    # in-kernel migration over peer memory (pb_migrate_p2p_*, include/parcels_b200.h)
+    def migrate_p2p_init(self, capacity_records: int):
+        """Allocate this engine's inbox.  Returns (64-byte CUDA-IPC handle, device address of the inbox)."""
+        handle = np.zeros(64, dtype=np.uint8)
+        base = np.zeros(1, dtype=np.uint64)
+        check(self._lib.pb_migrate_p2p_init(self._h, int(capacity_records), ptr(handle), ptr(base)))
+        return handle.tobytes(), int(base[0])
+
+    def migrate_p2p_connect(self, handles=None, local_bases=None):
+        """handles: one 64-byte IPC handle per rank (peers in other processes); local_bases: inbox addresses of peers that live
+        in this process (0 = not local)."""
+        h = None if handles is None else np.frombuffer(b"".join(handles), dtype=np.uint8).copy()
+        b = None if local_bases is None else np.ascontiguousarray(local_bases, dtype=np.uint64)
+        assert (h is None or h.size == 64 * self._nranks) and (b is None or b.size == self._nranks)
+        check(self._lib.pb_migrate_p2p_connect(self._h, ptr(h), ptr(b)))
+        self.p2p = True
+
+    def migrate_p2p_finish(self):
+        """After the barrier of a round: drop what left, append what arrived.  Returns (arrivals, resident count)."""
+        out = np.zeros(2, dtype=np.int64)
+        check(self._lib.pb_migrate_p2p_finish(self._h, ptr(out[0:1]), ptr(out[1:2])))
+        return int(out[0]), int(out[1])
+
     def particle_count(self) -> int:
         return int(self._lib.pb_particles_count(self._h))
 

@@ -22,6 +22,9 @@ ap.add_argument("--same-gpu", action="store_true")
 ap.add_argument("--particles", type=int, default=20000)
 ap.add_argument("--halo", type=int, default=3)
 ap.add_argument("--umax", type=float, default=40.0, help="velocity scale: large => many slab crossings")
+ap.add_argument("--transport", default="auto", choices=["auto", "p2p", "collective"],
+                help="p2p: in-kernel migration over peer memory (CUDA IPC; default over NCCL); collective: classify / pack / all-to-all")
+ap.add_argument("--inbox", type=int, default=0, help="p2p: records per inbox slot (default: the particle count; small values exercise the overflow path)")
 ap.add_argument("--diffusion", action="store_true", help="fused DiffusionUniformKh on a field at rest: statistical check (Var = 2 K t)")
 a = ap.parse_args()
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
@@ -29,6 +32,7 @@ dev = 0 if a.same_gpu else int(os.environ.get("LOCAL_RANK", rank))
 if torch.cuda.is_available():  # (not under the host simulation of the test suite, oracle/hostsim)
     torch.cuda.set_device(dev)
 dist.init_process_group("gloo" if a.same_gpu else "nccl")
+p2p = a.transport == "p2p" or (a.transport == "auto" and not a.same_gpu)
 
 f = bench.c2_field(nx=120, ny=60, nz=12, nt=3)
 f["U"] *= np.float32(a.umax)
@@ -48,6 +52,8 @@ if a.diffusion:
                                mesh="spherical", rank=rank, world=world, halo_cells=a.halo, device=dev)
     dfs.fs.add_constant_field("Kh_zonal", K, mesh="spherical")
     dfs.fs.add_constant_field("Kh_meridional", K, mesh="spherical")
+    if p2p:
+        D.connect_p2p(dfs, dist, a.inbox or n)
     out, stats = D.execute_decomposed(dfs, D.shard_particles(full, rank, world), [pb.AdvectionRK4_3D, pb.DiffusionUniformKh, pb.DeleteParticle],
                                       dt, runtime, dist, seed=11)
     tot = D.allreduce_sum(stats["migrated"], dist, device="cpu" if a.same_gpu else f"cuda:{dev}")
@@ -66,6 +72,8 @@ if a.diffusion:
 full = create_particle_data(nparticles=n, ngrids=1, initial=dict(x=x, y=y, z=z, t=np.zeros(n), particle_id=np.arange(n)))
 dfs = D.DecomposedFieldSet(lon=f["lon"], lat=f["lat"], depth=f["depth"], time=f["times"], U=f["U"], V=f["V"], W=f["W"],
                            mesh="spherical", rank=rank, world=world, halo_cells=a.halo, device=dev)
+if p2p:
+    D.connect_p2p(dfs, dist, a.inbox or n)
 mine = D.shard_particles(full, rank, world)  # arbitrary shard: routed to the owners by the first migration round
 out, stats = D.execute_decomposed(dfs, mine, [pb.AdvectionRK4_3D, pb.DeleteParticle], dt, runtime, dist)
 tot = D.allreduce_sum(stats["migrated"], dist, device="cpu" if a.same_gpu else f"cuda:{dev}")
@@ -89,7 +97,7 @@ if rank == 0:
                 print("   count", len(bad), "first:", [(int(merged["particle_id"][b]), merged[k][b].tolist(), ref[k][b].tolist(),
                                                         float(merged["x"][b]), float(ref["x"][b])) for b in bad[:6]])
     print(f"decomposed({world} ranks, backend={dist.get_backend()}): {len(ref['x'])} survivors, {int(tot)} migrations, "
-          f"rounds={stats['rounds']} -> {'PASS bit-exact' if ok else 'FAIL'}")
+          f"rounds={stats['rounds']}, transport={stats['transport']} -> {'PASS bit-exact' if ok else 'FAIL'}")
 dist.barrier()
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)

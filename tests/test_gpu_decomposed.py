@@ -31,3 +31,76 @@ def test_decomposed_two_ranks_nccl():
         pytest.skip("needs 2 GPUs")
     r = _run([], 29632)
     assert r.returncode == 0 and "PASS bit-exact" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_decomposed_two_ranks_one_gpu_in_kernel_migration_ipc():
+    """Two processes on cuda:0: each maps the other's inbox through CUDA IPC and the advection kernel delivers the leavers itself."""
+    import torch
+
+    if not torch.cuda.is_available():
+        pytest.skip("CUDA IPC needs a real device (the in-process variant below covers the logic under the host simulation)")
+    r = _run(["--same-gpu", "--transport", "p2p"], 29633)
+    assert r.returncode == 0 and "PASS bit-exact" in r.stdout and "peer memory" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+    assert " 0 migrations" not in r.stdout
+    # a tiny inbox: most leavers find it full and wait for a later round -- same trajectories, more rounds
+    r = _run(["--same-gpu", "--transport", "p2p", "--inbox", "64"], 29634)
+    assert r.returncode == 0 and "PASS bit-exact" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("inbox", [20000, 50])
+def test_in_kernel_migration_three_slabs_one_process(inbox):
+    """Three slab engines of ONE process linked by address (pb_migrate_p2p_connect's local bases): the rounds of
+    distributed.run_decomposed_p2p driven by hand, bit-exact against the undecomposed run."""
+    import sys
+
+    import numpy as np
+
+    sys.path[:0] = [ROOT]
+    import bench
+    import parcels_b200 as pb
+    from parcels_b200 import distributed as D
+    from parcels_b200.particle import create_particle_data
+
+    world, n = 3, 6000
+    f = bench.c2_field(nx=120, ny=60, nz=12, nt=3)
+    f["U"] *= np.float32(40.0)
+    f["V"] *= np.float32(40.0)
+    rng = np.random.default_rng(7)
+    x, y, z = rng.uniform(-175, 175, n), rng.uniform(-70, 70, n), rng.uniform(5, 5000, n)
+    dt, runtime = 600.0, 86400.0
+    kernels = [pb.AdvectionRK4_3D, pb.DeleteParticle]
+    full = create_particle_data(nparticles=n, ngrids=1, initial=dict(x=x, y=y, z=z, t=np.zeros(n), particle_id=np.arange(n)))
+    slabs = [D.DecomposedFieldSet(lon=f["lon"], lat=f["lat"], depth=f["depth"], time=f["times"], U=f["U"], V=f["V"], W=f["W"],
+                                  mesh="spherical", rank=r, world=world, halo_cells=3, device=0) for r in range(world)]  # fmt: skip
+    bases = [s.engine.migrate_p2p_init(inbox)[1] for s in slabs]
+    for s in slabs:
+        s.engine.migrate_p2p_connect(local_bases=bases)
+    plans = [D.decomposed_plan(s, kernels) for s in slabs]
+    for r, s in enumerate(slabs):
+        D.upload_decomposed(s, D.shard_particles(full, r, world), dt)  # arbitrary shards: the first launch routes them
+    rounds = migrated = 0
+    while True:
+        reps = [s.engine.advect(D._advect_args(s.engine, plans[r], dt, runtime, rounds == 0, 0, 1, rounds)) for r, s in enumerate(slabs)]
+        for s in slabs:  # (every kernel of the round has finished: the barrier of the multi-process protocol)
+            s.engine.migrate_p2p_finish()
+        rounds += 1
+        moved = sum(rp["n_migrate"] for rp in reps)
+        migrated += moved
+        assert all(rp["max_state"] != 99 for rp in reps)
+        if moved == 0:
+            break
+        assert rounds < 2000
+    assert migrated > n // 10
+    assert sum(s.engine.particle_count() for s in slabs) <= n
+    outs = [D.download_decomposed(s, dt) for s in slabs]
+    merged = {k: np.concatenate([o[k] for o in outs], axis=0) for k in outs[0]}
+    order = np.argsort(merged["particle_id"], kind="stable")
+    merged = {k: v[order] for k, v in merged.items()}
+    fs = pb.FieldSet.from_arrays(lon=f["lon"], lat=f["lat"], depth=f["depth"], time=f["times"], U=f["U"], V=f["V"], W=f["W"], mesh="spherical")
+    ps = pb.ParticleSet(fs, x=x, y=y, z=z, t=np.zeros(n), device=0)
+    ps.execute(kernels, dt=dt, runtime=runtime)
+    ref = ps._data
+    for k in ("particle_id", "state", "t", "ei", "x", "y", "z"):
+        assert merged[k].shape == ref[k].shape and np.array_equal(merged[k], ref[k]), k
+    if inbox < 1000:
+        assert rounds > 5  # the full-inbox path was taken
