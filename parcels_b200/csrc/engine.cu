@@ -35,6 +35,21 @@
 
 #include "common.cuh"
 
+// NVTX ranges per phase (upload / advect / download / migrate / output ...): visible in Nsight Systems / ncu --nvtx, free when no
+// tool is attached (header-only nvtx3: the injection library is looked up at the first call)
+#ifndef PB_HOSTSIM
+#include <nvtx3/nvToolsExt.h>
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
+#else
+struct NvtxRange {
+    explicit NvtxRange(const char*) {}
+};
+#endif
+#define PB_RANGE(name) NvtxRange pb_nvtx_range_(name)
+
 // ------------------------------------------------------------------------------------------------
 // error plumbing
 // ------------------------------------------------------------------------------------------------
@@ -491,6 +506,7 @@ int32_t pb_grid_upload_rectilinear(pb_engine* e, const void* lon, int64_t nx, co
                                    const void* depth, int64_t nz, int32_t coord_is_f64, const double* time_s,
                                    int64_t nt, int32_t spherical, double deg2m, int64_t xdim_cells,
                                    int64_t ydim_cells, int64_t zdim_cells) {
+    PB_RANGE("pb_grid_upload_rectilinear");
     if (!e) return fail(PB_ERR_INVALID, "engine is NULL");
     // a length-1 axis is allowed: the 1-D search returns index 0, coordinate 0 there (index_search.py:45-46)
     if (!lon || !lat || nx < 1 || ny < 1)
@@ -515,6 +531,7 @@ int32_t pb_grid_upload_curvilinear(pb_engine* e, const void* lon2d, const void* 
                                    const int64_t* hash_counts, int64_t n_keys, const uint32_t* hash_faces,
                                    int64_t n_entries, const double* hash_box6, int32_t hash_bitwidth,
                                    const uint64_t* face_qbox) {
+    PB_RANGE("pb_grid_upload_curvilinear");
     if (!e) return fail(PB_ERR_INVALID, "engine is NULL");
     if (!lon2d || !lat2d || nx < 2 || ny < 2) return fail(PB_ERR_INVALID, "curvilinear grid needs (ny, nx) lon/lat with ny, nx >= 2");
     if (nx > INT_MAX || ny > INT_MAX || nz > INT_MAX || nt > INT_MAX) return fail(PB_ERR_INVALID, "axis too long");
@@ -631,6 +648,7 @@ static int32_t set_field(pb_engine* e, int32_t slot, const void* dev, int32_t is
 
 int32_t pb_field_upload(pb_engine* e, int32_t slot, const void* data, int32_t data_is_f64, int64_t T, int64_t Z,
                         int64_t Y, int64_t X) {
+    PB_RANGE("pb_field_upload");
     if (!e) return fail(PB_ERR_INVALID, "engine is NULL");
     if (slot < 0 || slot >= PB_MAX_FIELDS) return fail(PB_ERR_INVALID, "bad field slot %d", slot);
     if (!data || T < 1 || Z < 1 || Y < 1 || X < 1) return fail(PB_ERR_INVALID, "bad field shape");
@@ -665,6 +683,7 @@ int32_t pb_field_clear(pb_engine* e, int32_t slot) {
 int32_t pb_particles_upload(pb_engine* e, int64_t n, const float* x, const float* y, const float* z, const float* dx,
                             const float* dy, const float* dz, const double* t, const int32_t* state, const int32_t* ei,
                             const int64_t* particle_id) {
+    PB_RANGE("pb_particles_upload");
     if (!e) return fail(PB_ERR_INVALID, "engine is NULL");
     if (n < 0) return fail(PB_ERR_INVALID, "n < 0");
     if (n && (!x || !y || !z || !t || !state || !ei)) return fail(PB_ERR_INVALID, "NULL particle array");
@@ -691,6 +710,7 @@ int32_t pb_particles_upload(pb_engine* e, int64_t n, const float* x, const float
 
 int32_t pb_particles_download(pb_engine* e, int64_t n, float* x, float* y, float* z, float* dx, float* dy, float* dz,
                               double* t, int32_t* state, int32_t* ei) {
+    PB_RANGE("pb_particles_download");
     if (!e) return fail(PB_ERR_INVALID, "engine is NULL");
     if (n != e->n) return fail(PB_ERR_INVALID, "download of %lld particles but %lld are resident", (long long)n, (long long)e->n);
     CK(cudaSetDevice(e->device));
@@ -716,6 +736,7 @@ int32_t pb_particles_download_ids(pb_engine* e, int64_t n, int64_t* particle_id)
 // Snapshot layout: whole columns back to back at offsets that are multiples of the particle count AT SNAPSHOT TIME --
 // x y z dx dy dz (4 B) t (8 B) state ei (4 B) = 40 B per particle, then particle_id (8 B) when ids are resident.
 int32_t pb_particles_snapshot(pb_engine* e) {
+    PB_RANGE("pb_particles_snapshot");
     if (!e) return fail(PB_ERR_INVALID, "engine is NULL");
     CK(cudaSetDevice(e->device));
     const size_t n = (size_t)e->n;
@@ -738,6 +759,7 @@ int32_t pb_particles_snapshot(pb_engine* e) {
 // Restores the resident set to the snapshot: columns AND particle count (a domain-decomposed pass changes the count through
 // migration; the ids travel with the particles and come back with the snapshot).
 int32_t pb_particles_restore(pb_engine* e) {
+    PB_RANGE("pb_particles_restore");
     if (!e) return fail(PB_ERR_INVALID, "engine is NULL");
     CK(cudaSetDevice(e->device));
     if (e->snap_n < 0 || e->snap.bytes < (size_t)e->snap_n * (e->snap_pid ? 48 : 40))
@@ -823,6 +845,7 @@ static int32_t launch_sample_flags(pb_engine* e, SampleParams& sp, bool has_time
 int32_t pb_sample_velocity(pb_engine* e, int64_t n, const double* t, const double* z, const double* y, const double* x,
                            int32_t positions_are_f32, int32_t three_d, const int32_t* ei_hint, int32_t no_hint, double* u,
                            double* v, double* w, int32_t* ei_out, int32_t* state_out) {
+    PB_RANGE("pb_sample_velocity");
     if (!e) return fail(PB_ERR_INVALID, "engine is NULL");
     if (n < 0 || (n && (!t || !z || !y || !x || !u || !v || !w || !ei_out || !state_out))) return fail(PB_ERR_INVALID, "NULL argument");
     const int nc = three_d ? 3 : 2;
@@ -864,6 +887,7 @@ int32_t pb_sample_velocity(pb_engine* e, int64_t n, const double* t, const doubl
 int32_t pb_sample_scalar(pb_engine* e, int32_t slot, int32_t method, int64_t n, const double* t, const double* z, const double* y,
                          const double* x, int32_t positions_are_f32, const int32_t* ei_hint, double* value, int32_t* value_is_f32,
                          int32_t* ei_out, int32_t* state_out) {
+    PB_RANGE("pb_sample_scalar");
     if (!e) return fail(PB_ERR_INVALID, "engine is NULL");
     if (n < 0 || (n && (!t || !z || !y || !x || !value || !ei_out || !state_out))) return fail(PB_ERR_INVALID, "NULL argument");
     if (slot < 0 || slot >= PB_MAX_FIELDS || !e->fptr[slot]) return fail(PB_ERR_STATE, "no field in slot %d", slot);
@@ -991,6 +1015,7 @@ static cudaError_t launch_advect_kernel(pb_engine* e, const AdvectParams& p, int
 }
 
 int32_t pb_advect_async(pb_engine* e, const pb_advect_args* a) {
+    PB_RANGE("pb_advect_async");
     AdvectParams p{};
     int nc = 2;
     int32_t rc = prepare_advect(e, a, p, nc);
@@ -1020,6 +1045,7 @@ int32_t pb_advect_async(pb_engine* e, const pb_advect_args* a) {
 // with the same atomics.  Equivalent to pb_particles_upload + pb_particles_snapshot + pb_advect (+ pb_particles_download).
 int32_t pb_advect_host(pb_engine* e, const pb_advect_args* a, int64_t n, const pb_particle_arrays* h, int32_t download,
                        int32_t n_chunks, pb_report* rep) {
+    PB_RANGE("pb_advect_host");
     if (!e || !a || !h) return fail(PB_ERR_INVALID, "NULL argument");
     if (n < 0) return fail(PB_ERR_INVALID, "n < 0");
     if (n && (!h->x || !h->y || !h->z || !h->t || !h->state || !h->ei)) return fail(PB_ERR_INVALID, "NULL particle array");
@@ -1107,6 +1133,7 @@ int32_t pb_advect_host(pb_engine* e, const pb_advect_args* a, int64_t n, const p
 }
 
 int32_t pb_last_report(pb_engine* e, pb_report* rep) {
+    PB_RANGE("pb_last_report");
     if (!e || !rep) return fail(PB_ERR_INVALID, "NULL argument");
     if (e->pending) {
         CK(cudaSetDevice(e->device));
@@ -1152,6 +1179,7 @@ int32_t pb_advect(pb_engine* e, const pb_advect_args* a, pb_report* rep) {
 static ParticlesDev cur_particles(pb_engine* e);
 
 int32_t pb_advect_rk45(pb_engine* e, const pb_rk45_args* a, double* dt_inout, double* next_dt_inout, pb_report* rep) {
+    PB_RANGE("pb_advect_rk45");
     if (!e || !a || !rep) return fail(PB_ERR_INVALID, "NULL argument");
     if (a->dt == 0.0 || a->dt != a->dt) return fail(PB_ERR_INVALID, "dt must be a non-zero number");
     if (e->n && (!dt_inout || !next_dt_inout)) return fail(PB_ERR_INVALID, "NULL dt / next_dt array");
@@ -1231,6 +1259,7 @@ static int32_t scalar_field_desc(pb_engine* e, int32_t slot, FieldDev& f) {
 }
 
 int32_t pb_advect_diffusion(pb_engine* e, const pb_advdiff_args* a, pb_report* rep) {
+    PB_RANGE("pb_advect_diffusion");
     if (!e || !a || !rep) return fail(PB_ERR_INVALID, "NULL argument");
     if (a->dt == 0.0 || a->dt != a->dt) return fail(PB_ERR_INVALID, "dt must be a non-zero number");
     if (a->scheme != PB_ADVDIFF_M1 && a->scheme != PB_ADVDIFF_EM) return fail(PB_ERR_INVALID, "unknown advection-diffusion scheme %d", a->scheme);
@@ -1367,6 +1396,7 @@ static int32_t run_select(pb_engine* e, const SelectRule& r, long long* n_sel) {
 }
 
 int32_t pb_output_select(pb_engine* e, double t_out, double dt, int64_t* n_selected) {
+    PB_RANGE("pb_output_select");
     if (!e || !n_selected) return fail(PB_ERR_INVALID, "NULL argument");
     if (e->pending) return fail(PB_ERR_STATE, "an advect call is pending: call pb_last_report first");
     const double half = fabs(dt / 2);
@@ -1380,6 +1410,7 @@ int32_t pb_output_select(pb_engine* e, double t_out, double dt, int64_t* n_selec
 
 int32_t pb_output_gather(pb_engine* e, int64_t n_selected, int64_t* index, float* x, float* y, float* z, double* t,
                          int64_t* particle_id) {
+    PB_RANGE("pb_output_gather");
     if (!e) return fail(PB_ERR_INVALID, "engine is NULL");
     if (e->n_selected < 0 || n_selected != e->n_selected)
         return fail(PB_ERR_STATE, "gather of %lld rows but the last pb_output_select chose %lld", (long long)n_selected, e->n_selected);
@@ -1410,6 +1441,7 @@ int32_t pb_output_gather(pb_engine* e, int64_t n_selected, int64_t* index, float
 }
 
 int32_t pb_particles_remove_deleted(pb_engine* e, int64_t* n_left) {
+    PB_RANGE("pb_particles_remove_deleted");
     if (!e || !n_left) return fail(PB_ERR_INVALID, "NULL argument");
     if (e->pending) return fail(PB_ERR_STATE, "an advect call is pending: call pb_last_report first");
     if (!e->have_pid && e->n) return fail(PB_ERR_STATE, "compaction needs particle_id resident");
@@ -1440,6 +1472,7 @@ int32_t pb_particles_remove_deleted(pb_engine* e, int64_t* n_left) {
 }
 
 int32_t pb_migrate_count(pb_engine* e, int64_t* counts) {
+    PB_RANGE("pb_migrate_count");
     if (!e || !counts) return fail(PB_ERR_INVALID, "NULL argument");
     if (e->nranks < 1 || e->mbounds.bytes == 0) return fail(PB_ERR_STATE, "pb_decomp_set not called");
     if (!e->have_pid && e->n) return fail(PB_ERR_STATE, "migration needs particle_id");
@@ -1464,6 +1497,7 @@ int32_t pb_migrate_count(pb_engine* e, int64_t* counts) {
 }
 
 int32_t pb_migrate_pack(pb_engine* e, void* sendbuf_dev, int64_t capacity_records) {
+    PB_RANGE("pb_migrate_pack");
     if (!e) return fail(PB_ERR_INVALID, "engine is NULL");
     if (e->n_send > capacity_records) return fail(PB_ERR_INVALID, "send buffer holds %lld records, %lld needed", (long long)capacity_records, e->n_send);
     if (e->n_send && !sendbuf_dev) return fail(PB_ERR_INVALID, "NULL send buffer");
@@ -1486,6 +1520,7 @@ int32_t pb_migrate_pack(pb_engine* e, void* sendbuf_dev, int64_t capacity_record
 }
 
 int32_t pb_migrate_unpack(pb_engine* e, const void* recvbuf_dev, int64_t n_in) {
+    PB_RANGE("pb_migrate_unpack");
     if (!e || n_in < 0 || (n_in && !recvbuf_dev)) return fail(PB_ERR_INVALID, "bad argument");
     CK(cudaSetDevice(e->device));
     const long long n_new = e->n_keep + n_in;
@@ -1569,6 +1604,7 @@ int32_t pb_migrate_p2p_connect(pb_engine* e, const uint8_t* ipc_handles, const u
 }
 
 int32_t pb_migrate_p2p_finish(pb_engine* e, int64_t* n_in_out, int64_t* n_now) {
+    PB_RANGE("pb_migrate_p2p_finish");
     if (!e) return fail(PB_ERR_INVALID, "engine is NULL");
     if (!e->mig_on) return fail(PB_ERR_STATE, "pb_migrate_p2p_connect not called");
     if (e->pending) return fail(PB_ERR_STATE, "an advect call is pending: call pb_last_report first");
@@ -1642,6 +1678,7 @@ int32_t pb_field_window_create(pb_engine* e, int32_t slot, int32_t data_is_f64, 
 }
 
 int32_t pb_field_window_load(pb_engine* e, int32_t slot, int64_t level, const void* host_level_data) {
+    PB_RANGE("pb_field_window_load");
     if (!e || !host_level_data) return fail(PB_ERR_INVALID, "NULL argument");
     if (slot < 0 || slot > 2 || !e->ring || !e->fptr[slot]) return fail(PB_ERR_STATE, "pb_field_window_create first");
     if (level < 0 || level >= e->fshape[slot][0]) return fail(PB_ERR_INVALID, "time level %lld out of range", (long long)level);
