@@ -200,14 +200,20 @@ def make_v3(interp_name: str, out_name: str):
     print(out_name, {k: v.shape for k, v in nc.items()}, gold["lon"].shape, "NaN frac", np.isnan(gold["lon"]).mean())
 
 
-def make_ref_cases():
+def make_ref_cases(only=None):
+    """only: names to (re)generate, merged into the existing file (``python -m oracle.make_golden ref_cases name ...``)."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import cases  # tests/cases.py: seeded input generators shared by tests and this script
 
     from . import ref_harness as rh
 
     out = {}
+    if only:
+        with np.load(os.path.join(GOLDEN, "ref_cases.npz")) as old:
+            out = {k: old[k] for k in old.files if k.split("/")[0] not in only}
     for name, spec in cases.CASES.items():
+        if only and name not in only:
+            continue
         c = cases.build(spec)
         fs = rh.build_fieldset(
             lon=c["lon"], lat=c["lat"], depth=c["depth"], times=c["times"], U=c["U"], V=c["V"], W=c["W"],
@@ -534,6 +540,9 @@ def make_advdiff_golden():
 
 if __name__ == "__main__":
     os.makedirs(GOLDEN, exist_ok=True)
+    if len(sys.argv) > 2 and sys.argv[1] == "ref_cases":
+        make_ref_cases(only=set(sys.argv[2:]))
+        sys.exit(0)
     make_v3("linear", "v3_jit_linear.npz")
     make_v3("cgrid_velocity", "v3_jit_cgrid.npz")
     make_v3("freeslip", "v3_jit_freeslip.npz")

@@ -41,8 +41,8 @@ def from_parcels(ref_fieldset) -> FieldSet:
     if interp not in SUPPORTED_VECTOR_INTERP:
         raise NotImplementedError(f"vector interpolator {interp} is not on the engine (supported: {sorted(SUPPORTED_VECTOR_INTERP)})")
     lon, lat = np.asarray(g.lon), np.asarray(g.lat)
-    if lon.ndim != 1 and interp != "CGrid_Velocity":
-        raise NotImplementedError("curvilinear grids are on the engine with CGrid_Velocity only")
+    if lon.ndim != 1 and interp not in ("CGrid_Velocity", "XLinear_Velocity"):
+        raise NotImplementedError("curvilinear grids are on the engine with CGrid_Velocity and XLinear_Velocity only")
     axes = list(g.axes)
     depth = np.asarray(g.depth) if "Z" in axes else None
     spherical = g._mesh.is_spherical()

@@ -412,7 +412,7 @@ struct AFastPolicy {
 // launch
 // ------------------------------------------------------------------------------------------------
 bool agrid_fast_applies(const AdvectParams& p, bool coord_f64, bool data_f64, bool has_time, int nc) {
-    if (!coord_f64 || data_f64 || !has_time || !p.f.il || p.f.windowed) return false;
+    if (!coord_f64 || data_f64 || !has_time || !p.f.il || p.f.windowed || p.g.curvilinear) return false;
     if (!(p.scheme == PB_ADVECTION_RK4 || p.scheme == PB_ADVECTION_RK4_3D)) return false;
     if (nc == 3 && p.g.nz < 2) return false;
     return p.g.nt >= 2 && p.g.nx >= 2 && p.g.ny >= 2;

@@ -703,3 +703,6 @@ cudaError_t launch_sample_agrid_alt(const SampleParams& p, int mode, bool coord_
 cudaError_t launch_precompute_cells(const void* lon, const void* lat, int ny, int nx, bool coord_f64, double* out, cudaStream_t s);
 cudaError_t launch_sample_agrid(const SampleParams& p, bool coord_f64, bool data_f64, bool has_time, int nc, cudaStream_t s);
 cudaError_t launch_sample_cgrid(const SampleParams& p, bool coord_f64, bool data_f64, int nc, cudaStream_t s);
+// XLinear_Velocity behind the curvilinear search (curva.cu)
+cudaError_t launch_curv_agrid(const AdvectParams& p, bool coord_f64, bool data_f64, int nc, cudaStream_t s);
+cudaError_t launch_sample_curv_agrid(const SampleParams& p, bool coord_f64, bool data_f64, int nc, cudaStream_t s);

@@ -826,8 +826,8 @@ static int32_t check_fields(pb_engine* e, int nc) {
                     e->g.nt, e->g.nz, e->g.ny, e->g.nx);
     if ((T > 1) != (e->g.nt > 0)) return fail(PB_ERR_INVALID, "field has %lld time levels but the grid time axis has %d", T, e->g.nt);
     if (Z > 1 && e->g.nz == 0) return fail(PB_ERR_INVALID, "field has a depth dimension but the grid has no Z axis");
-    if (e->g.curvilinear && e->interp != PB_INTERP_CGRID_VELOCITY)
-        return fail(PB_ERR_INVALID, "curvilinear grids are only supported with CGrid_Velocity interpolation");
+    if (e->g.curvilinear && e->interp != PB_INTERP_CGRID_VELOCITY && e->interp != PB_INTERP_XLINEAR_VELOCITY)
+        return fail(PB_ERR_INVALID, "curvilinear grids are supported with CGrid_Velocity and XLinear_Velocity interpolation");
     return PB_OK;
 }
 
@@ -873,6 +873,7 @@ int32_t pb_sample_velocity(pb_engine* e, int64_t n, const double* t, const doubl
     const int alt = agrid_alt_mode(e->interp);
     cudaError_t ce = e->interp == PB_INTERP_CGRID_VELOCITY
                          ? launch_sample_cgrid(sp, e->coord_f64 != 0, e->f_f64[0] != 0, nc, e->stream)
+                     : e->g.curvilinear ? launch_sample_curv_agrid(sp, e->coord_f64 != 0, e->f_f64[0] != 0, nc, e->stream)
                      : alt ? launch_sample_agrid_alt(sp, alt, e->coord_f64 != 0, e->f_f64[0] != 0, e->g.nt > 0, nc, e->stream)
                            : launch_sample_agrid(sp, e->coord_f64 != 0, e->f_f64[0] != 0, e->g.nt > 0, nc, e->stream);
     if (ce != cudaSuccess) return fail(PB_ERR_CUDA, "sample_kernel launch failed: %s", cudaGetErrorString(ce));
@@ -1010,6 +1011,7 @@ static cudaError_t launch_advect_kernel(pb_engine* e, const AdvectParams& p, int
     }
     e->last_variant = 0;
     return e->interp == PB_INTERP_CGRID_VELOCITY ? launch_cgrid(p, e->coord_f64 != 0, e->f_f64[0] != 0, nc, stream)
+           : e->g.curvilinear ? launch_curv_agrid(p, e->coord_f64 != 0, e->f_f64[0] != 0, nc, stream)
            : alt ? launch_agrid_alt(p, alt, e->coord_f64 != 0, e->f_f64[0] != 0, e->g.nt > 0, nc, stream)
                  : launch_agrid(p, e->coord_f64 != 0, e->f_f64[0] != 0, e->g.nt > 0, nc, stream);
 }

@@ -267,8 +267,8 @@ class FieldSet:
                  time_window=None):  # fmt: skip
         if interp_method not in INTERP_METHODS:
             raise NotImplementedError(f"interp_method {interp_method!r}: this engine has {sorted(INTERP_METHODS)}")
-        if grid.curvilinear and interp_method != "cgrid_velocity":
-            raise NotImplementedError("curvilinear grids are supported with CGrid_Velocity only")
+        if grid.curvilinear and interp_method not in ("cgrid_velocity", "linear"):
+            raise NotImplementedError("curvilinear grids are supported with CGrid_Velocity and XLinear_Velocity")
         self.interp_method = interp_method
         # time-slab streaming: keep only `time_window` consecutive time levels in HBM (U/V/W may then be any
         # array-like indexable by level: np.memmap, a lazy loader ...); None = every level resident

@@ -12,6 +12,6 @@ for tag in "$@"; do
 done
 wait
 for tag in "$@"; do
-  nvcc -shared -gencode arch=compute_100a,code=sm_100a -o lib/libparcels_b200_$tag.so lib/obj/engine.o lib/obj/afast_$tag.o lib/obj/agrid.o lib/obj/cgrid.o lib/obj/aslip.o lib/obj/rk45.o lib/obj/advdiff.o lib/obj/hashbuild.o -ldl
+  nvcc -shared -gencode arch=compute_100a,code=sm_100a -o lib/libparcels_b200_$tag.so lib/obj/engine.o lib/obj/afast_$tag.o lib/obj/agrid.o lib/obj/cgrid.o lib/obj/aslip.o lib/obj/rk45.o lib/obj/advdiff.o lib/obj/hashbuild.o lib/obj/curva.o -ldl
 done
 ls lib/*.so

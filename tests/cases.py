@@ -162,6 +162,15 @@ CASES = {
                         kernels=["AdvectionRK4_3D"], dt=600.0, segments=[dict(runtime=7200.0)], delete=True, umax=15.0),
     "curv_sph_f32": dict(seed=24, kind="curv", cdtype="f4", mesh="spherical", nx=31, ny=23, nz=1, nt=2, tstep=7200.0, n=300,
                          kernels=["AdvectionRK4"], dt=600.0, segments=[dict(runtime=7200.0)], delete=True, umax=15.0),
+    # ---- A-grid interpolation (XLinear_Velocity) on curvilinear meshes: the same search, _xinterpolators.py:112-190 on its result ----
+    "curv_lin_flat_2d": dict(seed=41, kind="curv", interp="linear", cdtype="f8", mesh="flat", nx=31, ny=23, nz=1, nt=3, tstep=600.0,
+                             n=400, kernels=["AdvectionRK4"], dt=60.0, segments=[dict(runtime=600.0)], delete=True, umax=1.5),
+    "curv_lin_sph_3d": dict(seed=42, kind="curv", interp="linear", cdtype="f8", mesh="spherical", nx=31, ny=23, nz=6, nt=3,
+                            tstep=3600.0, n=400, kernels=["AdvectionRK4_3D"], dt=600.0, segments=[dict(runtime=7200.0)],
+                            delete=True, umax=15.0),
+    "curv_lin_sph_f32": dict(seed=43, kind="curv", interp="linear", cdtype="f4", mesh="spherical", nx=31, ny=23, nz=5, nt=2,
+                             tstep=7200.0, n=300, kernels=["AdvectionRK4"], dt=600.0, segments=[dict(runtime=7200.0)],
+                             delete=True, umax=15.0),
     "cgrid_rect_3d": dict(seed=25, kind="smooth", interp="cgrid_velocity", cdtype="f4", ddtype="f8", mesh="flat", nx=16,
                           ny=13, nz=6, nt=4, tstep=200.0, n=400, kernels=["AdvectionRK4_3D"], dt=50.0,
                           segments=[dict(runtime=600.0)], delete=True, margin=-0.02, umax=4.0),
@@ -221,7 +230,7 @@ def build(spec):
         x, y = points_in_mesh(rng, lon, lat, n)
         z = rng.uniform(2.0, 190.0, n) if nz > 1 else np.zeros(n)
         out.update(lon=lon, lat=lat, depth=depth, times=np.arange(nt) * spec["tstep"], U=U, V=V, W=W, x=x, y=y, z=z,
-                   t=np.zeros(n), interp="cgrid_velocity", padding=("low", "low", "high"))  # fmt: skip
+                   t=np.zeros(n), interp=spec.get("interp", "cgrid_velocity"), padding=("low", "low", "high"))  # fmt: skip
         return out
     cd = np.dtype(spec["cdtype"])
     dd = np.dtype(spec["ddtype"])

@@ -24,7 +24,7 @@ from oracle_run import load_case, oracle_fieldset
 pytestmark = pytest.mark.gpu
 
 NAMES = ["c2_small", "flat_f32c_f64d", "all_f32", "c1_peninsula", "cgrid_rect_3d", "cgrid_rect_sph", "curv_flat_2d",
-         "curv_sph_2d", "curv_sph_3d", "curv_sph_f32", "freeslip_3d", "partialslip_sph", "nearest_3d", "freeslip_surface"]  # fmt: skip
+         "curv_sph_2d", "curv_sph_3d", "curv_sph_f32", "curv_lin_flat_2d", "curv_lin_sph_3d", "curv_lin_sph_f32", "freeslip_3d", "partialslip_sph", "nearest_3d", "freeslip_surface"]  # fmt: skip
 
 
 def _assert_values(name, c, f32_positions, got, want, what):
