@@ -42,6 +42,7 @@ inline unsigned __shfl_xor_sync(unsigned, unsigned, int) { return 0; }
 inline long long __shfl_xor_sync(unsigned, long long v, int) { return v; }
 inline int __shfl_xor_sync(unsigned, int v, int) { return v; }
 inline long long __shfl_up_sync(unsigned, long long v, int) { return v; }  // only in kernels hostsim replaces (sel_scan)
+#define __grid_constant__
 inline void __syncthreads() {}
 inline int __syncthreads_count(int p) { return p ? 1 : 0; }
 inline unsigned __ballot_sync(unsigned, int p) { return p ? 1u : 0u; }
@@ -54,6 +55,9 @@ struct double2 {
 };
 struct float2 {
     float x, y;
+};
+struct alignas(16) int4 {
+    int x, y, z, w;
 };
 struct alignas(16) float4 {
     float x, y, z, w;

@@ -1,0 +1,351 @@
+// afast2.cu -- second schedule of the headline hot path (AdvectionRK4 / AdvectionRK4_3D with XLinear_Velocity on a rectilinear
+// A-grid with FLOAT64 coordinates, FLOAT32 data and a time axis: reference kernels/_advection.py:42-75,
+// interpolators/_xinterpolators.py:78-190, _core/field.py:250-405).  Same arithmetic, operation by operation, as afast.cu and the
+// generic AGridPolicy<double, float, true, NC, 0>; what changed is where the instructions go (ncu of afast.cu on config 2,
+// profiles/README.md r02f: 2119 warp-instructions per warp and dt-step of which 763 are the reference's float64 operations,
+// 215 register-to-register moves, 99 selects, ~260 branch / reconvergence instructions; a side-path trip costs 443 instructions,
+// a quarter of them moves):
+//
+//  * The four RK4 stages are WRITTEN OUT (compile-time stage index): no loop-carried copies of the stage values, no selects on
+//    the stage number, "renew or reuse the T-lerped block" decided at compile time.
+//  * The side path (cell change, sentinel index, first node of an axis, outside the time axis) is ONE out-of-line function
+//    shared by the four sites.  Everything it reads or writes that outlives an evaluation lives in the lane's shared-memory
+//    columns (raw block, T-lerped block, cells, reciprocals and now the cell indices too), so it has no register interface
+//    with the hit path beyond its arguments: the hit path's register allocation no longer pays for it.  The kernel
+//    parameters reach it by address (`__grid_constant__`).
+//  * cos(latitude) of the unit conversion (_xinterpolators.py:182) is common.cuh's cos_np: one odd polynomial, 16 float64
+//    instructions instead of ~60 of all kinds (every A-grid kernel uses it, so the schedules stay bit-identical to each other).
+#include "afast.cuh"
+
+struct SideResult {
+    double u, v, w;
+    int state;
+    int flags;  // SIDE_*
+};
+enum { SIDE_FINAL = 1, SIDE_OUT_OF_TIME = 2, SIDE_REFILLED = 4, SIDE_SEARCHED = 8 };
+
+struct Fast2Ctx {
+    double lerp_t;  // sample time the T-lerped block in shared memory belongs to (-1: none)
+    float4* raw;    // this lane's column of 16-byte chunks
+    int state;
+    int ei;
+    unsigned int refills;
+    bool searched;
+    bool out_of_time;
+    signed char len_t, len_z;  // (interface of the generic kernel skeleton; unused here)
+};
+
+// NC: components sampled (2: fieldset.UV, 3: fieldset.UVW).  HZ: the grid has a depth axis with >= 2 levels.
+template <int NC_, bool HZ>
+struct AFast2Policy {
+    static constexpr int NC = NC_;
+    static constexpr int NV = HZ ? 16 : 8;          // raw values per component: (t, [z,] y, x) corners
+    static constexpr int NL = NV / 2;               // T-lerped values per component
+    static constexpr int RAW_CHUNKS = NC * NV / 4;  // float4 columns
+    static constexpr int LRP_CHUNKS = NC * NL / 2;  // double2 columns
+    static constexpr int CELL_CHUNKS = 4;           // double2 columns {lo, hi}: z, y, x, t
+    static constexpr int RCP_CHUNKS = 2;            // {1 / dz, 1 / dy}, {1 / dx, 1 / dt} of the current cells
+    static constexpr int IDX_CHUNKS = 1;            // int4 {ti, zi, yi, xi} of the last search (-100: none)
+    static constexpr size_t SMEM = (size_t)(RAW_CHUNKS + LRP_CHUNKS + CELL_CHUNKS + RCP_CHUNKS + IDX_CHUNKS) * 16 * PB_FAST_BLOCK;
+    static constexpr bool RUNTIME_DTYPE = false;
+    static constexpr bool FAST_RK4 = true;
+    static constexpr bool FAST_UNROLLED = true;
+    static constexpr bool F32_STAGES = false;
+    static constexpr bool BATCH_LEN_T = false;
+    static constexpr bool BATCH_LEN_Z = false;
+    using Ctx = Fast2Ctx;
+
+    __device__ static __forceinline__ double2* lrp(float4* raw) { return reinterpret_cast<double2*>(raw + (size_t)RAW_CHUNKS * PB_FAST_BLOCK); }
+    __device__ static __forceinline__ double2* cell(float4* raw, int k) {  // 0: z, 1: y, 2: x, 3: t
+        return reinterpret_cast<double2*>(raw + (size_t)(RAW_CHUNKS + LRP_CHUNKS + k) * PB_FAST_BLOCK);
+    }
+    __device__ static __forceinline__ double2* rcp(float4* raw) {
+        return reinterpret_cast<double2*>(raw + (size_t)(RAW_CHUNKS + LRP_CHUNKS + CELL_CHUNKS) * PB_FAST_BLOCK);
+    }
+    __device__ static __forceinline__ int4* idx(float4* raw) {
+        return reinterpret_cast<int4*>(raw + (size_t)(RAW_CHUNKS + LRP_CHUNKS + CELL_CHUNKS + RCP_CHUNKS) * PB_FAST_BLOCK);
+    }
+
+    __device__ static __forceinline__ void init(Ctx& e, const AdvectParams&, int ei) {
+        const double nan = __longlong_as_double(0x7ff8000000000000LL);
+        extern __shared__ __align__(16) unsigned char pb_smem[];
+        e.raw = reinterpret_cast<float4*>(pb_smem) + threadIdx.x;
+        double2 d;
+        d.x = nan; d.y = nan;
+#pragma unroll
+        for (int k = 0; k < CELL_CHUNKS; ++k) *cell(e.raw, k) = d;
+        int4 none;
+        none.x = none.y = none.z = none.w = -100;
+        *idx(e.raw) = none;
+        e.lerp_t = -1.0;  // valid sample times are >= 0
+        e.ei = ei;
+        e.searched = false;
+        e.len_t = e.len_z = -1;
+    }
+    // ravel_index (basegrid.py:259-278) over the axes present of the last completed search; int64 arithmetic stored to int32
+    __device__ static __forceinline__ void finish(Ctx& e, const AdvectParams& p) {
+        if (!e.searched) return;
+        const int4 ix = *idx(e.raw);
+        int gxi = ix.w;
+        if (p.g.decomposed && gxi >= 0) gxi += p.g.xi_offset;  // mode D: local column -> global column
+        long long r = (long long)ix.z * p.g.xdim + (long long)gxi;
+        if (p.g.nz > 0) r += (long long)(HZ ? ix.y : 0) * (p.g.ydim * p.g.xdim);
+        e.ei = (int)r;
+    }
+
+    // gather the (t, z, y, x) corner block of every component from the node-interleaved copy into this lane's raw columns
+    __device__ static __forceinline__ void refill(const FieldDev& f, float4* raw, int ti, int zi, int yi, int xi) {
+        const long long ot[2] = {wrap_idx(ti, f.T) * f.sT, up_idx(ti, f.T) * f.sT};
+        const long long oz[2] = {wrap_idx(zi, f.Z) * f.sZ, up_idx(zi, f.Z) * f.sZ};
+        const long long oy[2] = {wrap_idx(yi, f.Y) * f.sY, up_idx(yi, f.Y) * f.sY};
+        const long long ox[2] = {wrap_idx(xi, f.X) * f.sX, up_idx(xi, f.X) * f.sX};
+        const float4* __restrict__ base = (const float4*)f.il;
+#pragma unroll
+        for (int pl = 0; pl < NV / 4; ++pl) {
+            // chunk pl of a component holds k = 4 pl .. 4 pl + 3,  k = (t * 2 + z) * 4 + y * 2 + x (HZ) | t * 4 + y * 2 + x
+            const long long o = ot[HZ ? (pl >> 1) : pl] + (HZ ? oz[pl & 1] : 0);
+            const float4 n00 = ldg(base + o + oy[0] + ox[0]), n01 = ldg(base + o + oy[0] + ox[1]);
+            const float4 n10 = ldg(base + o + oy[1] + ox[0]), n11 = ldg(base + o + oy[1] + ox[1]);
+            float4 q;
+            q.x = n00.x; q.y = n01.x; q.z = n10.x; q.w = n11.x;
+            raw[(0 * (NV / 4) + pl) * PB_FAST_BLOCK] = q;
+            q.x = n00.y; q.y = n01.y; q.z = n10.y; q.w = n11.y;
+            raw[(1 * (NV / 4) + pl) * PB_FAST_BLOCK] = q;
+            if (NC == 3) {
+                q.x = n00.z; q.y = n01.z; q.z = n10.z; q.w = n11.z;
+                raw[(2 * (NV / 4) + pl) * PB_FAST_BLOCK] = q;
+            }
+        }
+    }
+
+    // ---------------- side path: searches, states, refill; special samples are finished here ----------------
+    // Out of line, one copy for the four stages.  Reads and rewrites the lane's cells / reciprocals / indices / raw block in shared
+    // memory; what the caller has in registers comes in as arguments and goes back through `out`.
+    __device__ static __noinline__ void side_path(const AdvectParams* pp, float4* raw, int k, double ts, double zs, double ys, double xs,
+                                                  int state, SideResult* out) {
+        const GridDev& g = pp->g;
+        const FieldDev& f = pp->f;
+        int flags = 0;
+        if (!(0 <= ts && ts <= g.time_len)) {  // OutsideTimeInterval (index_search.py:85-86): state 70, sample (0, 0, 0)
+            out->u = out->v = out->w = 0.0;
+            out->state = PB_ERROR_OUTSIDE_TIME_INTERVAL;
+            out->flags = SIDE_FINAL | SIDE_OUT_OF_TIME;
+            return;
+        }
+        const double2 bz = HZ ? *cell(raw, 0) : double2{0.0, 0.0}, by = *cell(raw, 1), bx = *cell(raw, 2), bt = *cell(raw, 3);
+        const int4 old = *idx(raw);  // key of the raw block: {ti, zi, yi, xi}
+        AxisCell<double> ct{old.x, bt.x, bt.y}, cz{old.y, bz.x, bz.y}, cy{old.z, by.x, by.y}, cx{old.w, bx.x, bx.y};
+        const double wt = ct.hi - ct.lo, wz = cz.hi - cz.lo, wy = cy.hi - cy.lo, wx = cx.hi - cx.lo;  // (NaN for a poisoned cell)
+        if (old.x >= 0 && !(ct.lo == ct.lo)) ct.idx = -100;  // (a poisoned cell is not a neighbour-search seed)
+        if (old.y >= 0 && !(cz.lo == cz.lo)) cz.idx = -100;
+        if (old.z >= 0 && !(cy.lo == cy.lo)) cy.idx = -100;
+        if (old.w >= 0 && !(cx.lo == cx.lo)) cx.idx = -100;
+        axis_locate(g.time, g.nt, ts, ct);
+        const int ti = ct.idx;
+        int zi = 0;
+        if (HZ) {
+            axis_locate((const double*)g.depth, g.nz, zs, cz);
+            zi = cz.idx;
+        }
+        axis_locate((const double*)g.lat, g.ny, ys, cy);
+        axis_locate((const double*)g.lon, g.nx, xs, cx);
+        const int yi = cy.idx, xi = cx.idx;
+        {   // cell widths changed: new reciprocals (the division itself: correctly rounded)
+            double2* const rp = rcp(raw);
+            const double nwt = ct.hi - ct.lo, nwz = cz.hi - cz.lo, nwy = cy.hi - cy.lo, nwx = cx.hi - cx.lo;
+            if ((HZ && !(nwz == wz)) || !(nwy == wy)) {
+                double2 d;
+                d.x = 1.0 / nwz; d.y = 1.0 / nwy;
+                rp[0] = d;
+            }
+            if (!(nwx == wx) || !(nwt == wt)) {
+                double2 d;
+                d.x = 1.0 / nwx; d.y = 1.0 / nwt;
+                rp[PB_FAST_BLOCK] = d;
+            }
+        }
+        int4 now;
+        now.x = ti; now.y = zi; now.z = yi; now.w = xi;
+        *idx(raw) = now;
+        flags |= SIDE_SEARCHED;
+        if (g.decomposed) {  // mode D: a sentinel at a slab edge that is not the edge of the global domain = halo too small
+            if ((xi == -2 && !g.left_global) || (xi == -1 && !g.right_global)) state = max(state, 99);
+        }
+        int s = state;
+        if (xi == -1 || yi == -1 || zi == -1) s = max(s, (int)PB_ERROR_OUT_OF_BOUNDS);  // field.py:327-356
+        if (zi == -2) s = max(s, (int)PB_ERROR_THROUGH_SURFACE);
+        if (old.x != ti || (HZ && old.y != zi) || old.z != yi || old.w != xi) {
+            refill(f, raw, ti, zi, yi, xi);
+            flags |= SIDE_REFILLED;
+        }
+        // special: a sentinel index, or a sample not strictly inside (lo, hi] of the time / depth cell (tau or zeta == 0 on the
+        // first node: lenT / lenZ == 1 for this particle, _xinterpolators.py:130-131; NaN; a degenerate cell)
+        const bool t_in = ts > ct.lo && ts <= ct.hi, z_in = !HZ || (zs > cz.lo && zs <= cz.hi);
+        const bool special = xi < 0 || yi < 0 || zi < 0 || !t_in || !z_in;
+        {   // write the cells back; the ones a special sample involved are poisoned so that the lane comes back here next time
+            const double nan = __longlong_as_double(0x7ff8000000000000LL);
+            double2 d;
+            d.x = ct.lo; d.y = ct.hi; if (!t_in) { d.x = nan; d.y = nan; }
+            *cell(raw, 3) = d;
+            if (HZ) { d.x = cz.lo; d.y = cz.hi; if (zi < 0 || !z_in) { d.x = nan; d.y = nan; } *cell(raw, 0) = d; }
+            d.x = cy.lo; d.y = cy.hi; if (yi < 0) { d.x = nan; d.y = nan; }
+            *cell(raw, 1) = d;
+            d.x = cx.lo; d.y = cx.hi; if (xi < 0) { d.x = nan; d.y = nan; }
+            *cell(raw, 2) = d;
+        }
+        if (special) {
+            const double tau = axis_bcoord(g.nt, ts, ct), zeta = HZ ? axis_bcoord(g.nz, zs, cz) : 0.0;
+            const double eta = axis_bcoord(g.ny, ys, cy), xsi = axis_bcoord(g.nx, xs, cx);
+            const bool two_t = tau > 0;             // lenT, per particle (float64 grid: no dtype depends on the batch)
+            const bool two_z = HZ && !(zeta <= 0);  // lenZ, per particle (a NaN depth must poison the value)
+            double u = special_component<NV>(raw, tau, zeta, eta, xsi, two_t, two_z);
+            double v = special_component<NV>(raw + (NV / 4) * PB_FAST_BLOCK, tau, zeta, eta, xsi, two_t, two_z);
+            double w = NC == 3 ? special_component<NV>(raw + 2 * (NV / 4) * PB_FAST_BLOCK, tau, zeta, eta, xsi, two_t, two_z) : 0.0;
+            if (g.spherical) spherical(g, k == 0, ys, u, v);
+            if (u != u || v != v || w != w) s = max(s, (int)PB_ERROR_INTERPOLATION);
+            if (xi < 0 || yi < 0 || zi < 0) { u = 0.0; v = 0.0; w = 0.0; }
+            out->u = u; out->v = v; out->w = w;
+            flags |= SIDE_FINAL;
+        }
+        out->state = s;
+        out->flags = flags;
+    }
+
+    // Z-lerp (:141-145) and bilinear (:147-152, left to right) of one component's T-lerped values
+    __device__ static __forceinline__ double zxy(const double (&L)[NL], double zeta, double omz, double w00, double w01, double w10, double w11) {
+        double r[4];
+        if (HZ) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) r[j] = L[j] * omz + L[4 + j] * zeta;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) r[j] = L[j];
+        }
+        return w00 * r[0] + w01 * r[1] + w10 * r[2] + w11 * r[3];
+    }
+
+    // One VectorField.eval (field.py:250-304) at RK4 stage K's position (K is a compile-time constant: the four call sites of the
+    // kernel skeleton are four straight-line copies of the hit path)
+    template <int K>
+    __device__ static __forceinline__ void eval_fast(const AdvectParams& p, Ctx& e, const double ts, const double zs, const double ys,
+                                                     const double xs, double& u, double& v, double& w) {
+        const GridDev& g = p.g;
+        constexpr bool renew = (K & 1) != 0;  // odd stages sample a new time: the T-lerped block is renewed; even stages reuse it
+        float4* const raw = e.raw;
+        bool lerp_now = renew;
+        double2 bz, by, bx, bt;  // {lo, hi} of the current cells
+        // The cells are READ FROM SHARED MEMORY at every evaluation, on purpose (volatile loads: neither NVVM nor ptxas may forward
+        // them): they only change in the side path, and keeping them in registers across evaluations costs moves and spills.
+#pragma unroll 1
+        for (int trip = 0;; ++trip) {
+            bz = HZ ? lds_volatile(cell(raw, 0)) : double2{0.0, 0.0};
+            by = lds_volatile(cell(raw, 1));
+            bx = lds_volatile(cell(raw, 2));
+            bt = (renew || trip) ? lds_volatile(cell(raw, 3)) : double2{0.0, 0.0};  // (even stages test the cached lerp's time)
+            bool hit = xs > bx.x && xs <= bx.y && ys > by.x && ys <= by.y;
+            if (HZ) hit = hit && zs > bz.x && zs <= bz.y;
+            hit = hit && (renew ? (ts > bt.x && ts <= bt.y) : (ts == e.lerp_t));
+            if (hit || trip) break;
+            SideResult r;
+            side_path(&p, raw, K, ts, zs, ys, xs, e.state, &r);
+            e.state = r.state;
+            if (r.flags & SIDE_OUT_OF_TIME) e.out_of_time = true;
+            if (r.flags & SIDE_SEARCHED) e.searched = true;
+            if (r.flags & SIDE_REFILLED) { e.refills++; e.lerp_t = -1.0; }
+            if (r.flags & SIDE_FINAL) {
+                u = r.u; v = r.v; w = r.w;
+                return;
+            }
+            lerp_now = true;  // (an even stage after a cell change: its block has to be lerped for this sample time first)
+        }
+        // ---------------- straight-line path: every cell is current, 0 < bcoord <= 1 on every axis ----------------
+        // bcoord = (x - lo) / (hi - lo), index_search.py:57 (denominator in the axis dtype), with the cell width's cached reciprocal
+        const double2 r_zy = rcp(raw)[0], r_xt = rcp(raw)[PB_FAST_BLOCK];
+        const double zeta = HZ ? div_by_cached(zs - bz.x, bz.y - bz.x, r_zy.x) : 0.0;
+        const double eta = div_by_cached(ys - by.x, by.y - by.x, r_zy.y);
+        const double xsi = div_by_cached(xs - bx.x, bx.y - bx.x, r_xt.x);
+        const double omz = 1 - zeta;
+        const double w00 = (1 - xsi) * (1 - eta), w01 = xsi * (1 - eta), w10 = (1 - xsi) * eta, w11 = xsi * eta;
+        double2* const lp = lrp(raw);
+        double q[3] = {0.0, 0.0, 0.0};
+        if (lerp_now) {
+            const double tau = div_by_cached(ts - bt.x, bt.y - bt.x, r_xt.y);
+            const double omt = 1 - tau;
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+                float lo_t[NL], hi_t[NL];
+#pragma unroll
+                for (int j = 0; j < NL / 4; ++j) {
+                    const float4 a = raw[(c * (NV / 4) + j) * PB_FAST_BLOCK];
+                    const float4 b = raw[(c * (NV / 4) + NL / 4 + j) * PB_FAST_BLOCK];
+                    lo_t[4 * j] = a.x; lo_t[4 * j + 1] = a.y; lo_t[4 * j + 2] = a.z; lo_t[4 * j + 3] = a.w;
+                    hi_t[4 * j] = b.x; hi_t[4 * j + 1] = b.y; hi_t[4 * j + 2] = b.z; hi_t[4 * j + 3] = b.w;
+                }
+                double L[NL];
+#pragma unroll
+                for (int j = 0; j < NL; ++j) L[j] = (double)lo_t[j] * omt + (double)hi_t[j] * tau;  // _xinterpolators.py:135-139
+#pragma unroll
+                for (int j = 0; j < NL / 2; ++j) {
+                    double2 d;
+                    d.x = L[2 * j]; d.y = L[2 * j + 1];
+                    lp[(c * (NL / 2) + j) * PB_FAST_BLOCK] = d;
+                }
+                q[c] = zxy(L, zeta, omz, w00, w01, w10, w11);
+            }
+            e.lerp_t = ts;
+        } else {
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+                double L[NL];
+#pragma unroll
+                for (int j = 0; j < NL / 2; ++j) {
+                    const double2 d = lp[(c * (NL / 2) + j) * PB_FAST_BLOCK];
+                    L[2 * j] = d.x; L[2 * j + 1] = d.y;
+                }
+                q[c] = zxy(L, zeta, omz, w00, w01, w10, w11);
+            }
+        }
+        u = q[0]; v = q[1]; w = NC == 3 ? q[2] : 0.0;
+        if (g.spherical) spherical(g, K == 0, ys, u, v);
+        if (u != u || v != v || w != w) e.state = max(e.state, (int)PB_ERROR_INTERPOLATION);  // field.py:288-290
+    }
+
+    // u /= deg2m * cos(deg2rad(y)); v /= deg2m (_xinterpolators.py:182-184).  Stage 1 samples at the particle's own float32
+    // latitude: the factor is float32 arithmetic there (and the float64 value is divided by its float64 promotion).
+    __device__ static __forceinline__ void spherical(const GridDev& g, bool first, double ys, double& u, double& v) {
+        double conv;
+        if (first) conv = (double)((float)g.deg2m * cos_np(deg2rad_np((float)ys)));
+        else conv = g.deg2m * cos_np(deg2rad_np(ys));
+        u = u / conv;
+        v = div_by_cached_guarded(v, g.deg2m, g.inv_deg2m);
+    }
+
+    // the generic skeleton's entry point is not used by a FAST_RK4 policy
+    template <class PZ, class PY, class PX>
+    __device__ static __forceinline__ void eval(const AdvectParams&, Ctx&, bool, double, PZ, PY, PX, Val&, Val&, Val&) {}
+};
+
+// ------------------------------------------------------------------------------------------------
+// launch
+// ------------------------------------------------------------------------------------------------
+template <int NC, bool HZ, bool DIFF>
+static cudaError_t launch_fast2(const AdvectParams& p, cudaStream_t s) {
+    using Pol = AFast2Policy<NC, HZ>;
+    const long long grid = (p.P.n + PB_FAST_BLOCK - 1) / PB_FAST_BLOCK;
+    if (Pol::SMEM > 48 * 1024) {
+        cudaError_t ce = cudaFuncSetAttribute(advect_kernel<Pol, DIFF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Pol::SMEM);
+        if (ce != cudaSuccess) return ce;
+    }
+    advect_kernel<Pol, DIFF><<<(unsigned)grid, PB_FAST_BLOCK, Pol::SMEM, s>>>(p);
+    return cudaGetLastError();
+}
+template <int NC, bool HZ>
+static cudaError_t launch_fast1(const AdvectParams& p, cudaStream_t s) {
+    return p.diffusion ? launch_fast2<NC, HZ, true>(p, s) : launch_fast2<NC, HZ, false>(p, s);
+}
+
+cudaError_t launch_agrid_fast2(const AdvectParams& p, int nc, cudaStream_t s) {
+    const bool hz = p.g.nz >= 2;
+    if (nc == 3) return launch_fast1<3, true>(p, s);
+    return hz ? launch_fast1<2, true>(p, s) : launch_fast1<2, false>(p, s);
+}

@@ -154,7 +154,34 @@ __device__ __forceinline__ T ldg(const T* p) {
 __device__ __forceinline__ float deg2rad_np(float x) { return x * (float)(3.14159265358979323846 / 180.0); }
 __device__ __forceinline__ double deg2rad_np(double x) { return x * (3.14159265358979323846 / 180.0); }
 __device__ __forceinline__ float cos_np(float x) { return cosf(x); }
-__device__ __forceinline__ double cos_np(double x) { return cos(x); }
+// np.cos of a float64 LATITUDE in radians (the unit conversion of _xinterpolators.py:182): cos(x) = sin(pi/2 - |x|) as ONE odd
+// polynomial on [0, pi/2] -- no quadrant logic, no integer work: 16 float64 instructions where CUDA's cos() is ~60 of all
+// kinds.  Max error 1.9 ulp against long double on 2.5e6 latitudes (CUDA documents 2 ulp for its own cos; NumPy's SIMD
+// cos is <= 1 ulp): far inside the position tolerance of spherical meshes (2 float32 ulp).  Anything that is not a latitude
+// (|x| > pi/2, NaN) takes cos().  PB_FAST_COS=0 builds with cos() for A/B runs.
+static __device__ __noinline__ double cos_cold(double x) { return cos(x); }
+__device__ __forceinline__ double cos_np(double x) {
+#if defined(PB_FAST_COS) && PB_FAST_COS == 0
+    return cos(x);
+#else
+    const double ax = fabs(x);
+    if (!(ax <= 1.5707963267948968)) return cos_cold(x);
+    const double r = (1.5707963267948966 - ax) + 6.123233995736766e-17;  // pi/2 = hi + lo; hi - |x| is exact for |x| >= pi/4
+    const double s = r * r;
+    double p = -3.8681701706306841e-23;      // -1/23!
+    p = fma(p, s, 1.9572941063391263e-20);   //  1/21!
+    p = fma(p, s, -8.2206352466243295e-18);  // -1/19!
+    p = fma(p, s, 2.8114572543455206e-15);   //  1/17!
+    p = fma(p, s, -7.6471637318198164e-13);  // -1/15!
+    p = fma(p, s, 1.6059043836821613e-10);   //  1/13!
+    p = fma(p, s, -2.5052108385441720e-08);  // -1/11!
+    p = fma(p, s, 2.7557319223985893e-06);   //  1/9!
+    p = fma(p, s, -1.9841269841269841e-04);  // -1/7!
+    p = fma(p, s, 8.3333333333333332e-03);   //  1/5!
+    p = fma(p, s, -1.6666666666666666e-01);  // -1/3!
+    return fma(r * s, p, r);
+#endif
+}
 
 // A value with NumPy's dtype tag: interpolated velocities are float32 only when grid coordinates,
 // field data and the sampled position are all float32 (stage 1) -- the tag decides in which
@@ -289,8 +316,22 @@ __device__ __forceinline__ double half_of(const Val& a) { return a.f32 ? (double
 #endif
 // DIFF = false compiles the kernel without the DiffusionUniformKh block (the specialised RK4 kernel is instantiated both ways:
 // the advection-only hot path carries neither the Philox / Box-Muller code nor its loop-invariant registers)
+// whether a policy is a FAST_RK4 one whose four stages are written out (afast2.cu)
+template <class P, class = void>
+struct FastUnrolled : std::false_type {};
+template <class P>
+struct FastUnrolled<P, std::void_t<decltype(P::FAST_UNROLLED)>> : std::integral_constant<bool, P::FAST_UNROLLED> {};
+template <class P>
+constexpr bool fast_unrolled_v = FastUnrolled<P>::value;
+
+// (PB_MAXNREG: a tuning build caps the registers directly -- __launch_bounds__ only offers the caps 65536 / threads rounds to)
+#ifdef PB_MAXNREG
+#define PB_KERNEL_BOUNDS __maxnreg__(PB_MAXNREG)
+#else
+#define PB_KERNEL_BOUNDS __launch_bounds__(PB_BLOCK_THREADS, PB_MINBLOCKS)
+#endif
 template <class Policy, bool DIFF = true>
-__global__ void __launch_bounds__(PB_BLOCK_THREADS, PB_MINBLOCKS) advect_kernel(const AdvectParams p) {
+__global__ void PB_KERNEL_BOUNDS advect_kernel(const __grid_constant__ AdvectParams p) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long my_steps = 0, my_refills = 0;  // (my_steps = the lane's iteration count, set on exit)
     int final_state = 0;
@@ -356,7 +397,24 @@ __global__ void __launch_bounds__(PB_BLOCK_THREADS, PB_MINBLOCKS) advect_kernel(
             // with DiffusionUniformKh in the list, ei[:, -1] was overwritten with 0 for every particle by the
             // constant-field evals of the previous step: curvilinear hints are all zero again
             const bool nohint1 = (it == 0 && p.hint_all_zero) || (it > 0 && DIFF && p.diffusion);
-            if constexpr (Policy::FAST_RK4) {
+            if constexpr (fast_unrolled_v<Policy>) {
+                // afast2.cu: the same four evaluations as below written out, stage index at compile time (no loop-carried copies of
+                // the stage values, no selects on the stage number); operation for operation the arithmetic of the loop form
+                uk = Val{0.0, false}; vk = uk; wk = uk;
+                const double xd = (double)x, yd = (double)y, zd = (double)z;
+                const double th = t + 0.5 * dtp;
+                Policy::template eval_fast<0>(p, e, t, zd, yd, xd, uk.v, vk.v, wk.v);
+                su = uk.v; sv = vk.v; sw = wk.v;
+                double xs = xd + (uk.v * 0.5) * dtp, ys = yd + (vk.v * 0.5) * dtp, zs = three_d ? zd + (wk.v * 0.5) * dtp : zd;
+                Policy::template eval_fast<1>(p, e, th, zs, ys, xs, uk.v, vk.v, wk.v);
+                su = su + 2.0 * uk.v; sv = sv + 2.0 * vk.v; sw = sw + 2.0 * wk.v;
+                xs = xd + (uk.v * 0.5) * dtp; ys = yd + (vk.v * 0.5) * dtp; zs = three_d ? zd + (wk.v * 0.5) * dtp : zd;
+                Policy::template eval_fast<2>(p, e, th, zs, ys, xs, uk.v, vk.v, wk.v);
+                su = su + 2.0 * uk.v; sv = sv + 2.0 * vk.v; sw = sw + 2.0 * wk.v;
+                xs = xd + uk.v * dtp; ys = yd + vk.v * dtp; zs = three_d ? zd + wk.v * dtp : zd;
+                Policy::template eval_fast<3>(p, e, t + dtp, zs, ys, xs, uk.v, vk.v, wk.v);
+                su = su + 1.0 * uk.v; sv = sv + 1.0 * vk.v; sw = sw + 1.0 * wk.v;
+            } else if constexpr (Policy::FAST_RK4) {
                 // afast.cu: float64 grid, float32 data -- every stage value is float64 (Val::f32 never set), one eval site,
                 // odd stages renew the T-lerped block, even stages reuse it (stages 2/3 and 4/next-1 share their sample time)
                 su = sv = sw = 0.0;
@@ -669,6 +727,7 @@ cudaError_t launch_agrid(const AdvectParams& p, bool coord_f64, bool data_f64, b
 // afast.cu: the specialised RK4 kernel (float64 grid, float32 node-interleaved data, time axis); `ok` tells whether it applies
 bool agrid_fast_applies(const AdvectParams& p, bool coord_f64, bool data_f64, bool has_time, int nc);
 cudaError_t launch_agrid_fast(const AdvectParams& p, int nc, cudaStream_t s);
+cudaError_t launch_agrid_fast2(const AdvectParams& p, int nc, cudaStream_t s);  // afast2.cu: stages written out, side path out of line
 cudaError_t launch_interleave(const float* u, const float* v, const float* w, long long nodes, void* out, cudaStream_t s);
 cudaError_t launch_cgrid(const AdvectParams& p, bool coord_f64, bool data_f64, int nc, cudaStream_t s);
 // mode: 1 = _Spatialslip (g.slip_a/b), 2 = XNearest per component  (aslip.cu)

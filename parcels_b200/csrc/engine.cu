@@ -944,6 +944,11 @@ static bool fast_kernel_enabled() {
     const char* v = getenv("PB_DISABLE_FAST_KERNEL");  // A/B switch of the parity tests and variant sweeps
     return !(v && v[0] == '1');
 }
+// which specialised RK4 kernel: 2 (default) = afast2.cu (stages written out, side path out of line), 1 = afast.cu
+static int fast_kernel_version() {
+    const char* v = getenv("PB_FAST_KERNEL");
+    return (v && v[0] == '1') ? 1 : 2;
+}
 static int32_t ensure_interleaved(pb_engine* e, int scheme) {
     if (e->il_valid) return PB_OK;
     if (!(scheme == PB_ADVECTION_RK4 || scheme == PB_ADVECTION_RK4_3D) || !fast_kernel_enabled()) return PB_OK;
@@ -1006,8 +1011,8 @@ static cudaError_t launch_advect_kernel(pb_engine* e, const AdvectParams& p, int
     const int alt = agrid_alt_mode(e->interp);
     if (e->interp == PB_INTERP_XLINEAR_VELOCITY && fast_kernel_enabled() &&
         agrid_fast_applies(p, e->coord_f64 != 0, e->f_f64[0] != 0, e->g.nt > 0, nc)) {
-        e->last_variant = 1;
-        return launch_agrid_fast(p, nc, stream);
+        e->last_variant = fast_kernel_version();
+        return e->last_variant == 2 ? launch_agrid_fast2(p, nc, stream) : launch_agrid_fast(p, nc, stream);
     }
     e->last_variant = 0;
     return e->interp == PB_INTERP_CGRID_VELOCITY ? launch_cgrid(p, e->coord_f64 != 0, e->f_f64[0] != 0, nc, stream)

@@ -78,8 +78,10 @@ def _case(seed):
                 three_d=three_d, seed=seed)
 
 
-def _run(c, fast: bool):
+def _run(c, fast: int):
+    """fast: 0 = the generic kernel, 1 = afast.cu (stage loop), 2 = afast2.cu (stages written out; the library default)"""
     os.environ["PB_DISABLE_FAST_KERNEL"] = "0" if fast else "1"
+    os.environ["PB_FAST_KERNEL"] = str(fast or 2)
     try:
         f = c["field"]
         fs = pb.FieldSet.from_arrays(lon=f["lon"], lat=f["lat"], depth=f["depth"], time=f["times"], U=f["U"], V=f["V"],
@@ -106,20 +108,22 @@ def _run(c, fast: bool):
         return {k: np.array(ps._data[k]) for k in KEYS}, err, reps
     finally:
         os.environ.pop("PB_DISABLE_FAST_KERNEL", None)
+        os.environ.pop("PB_FAST_KERNEL", None)
 
 
+@pytest.mark.parametrize("version", [2, 1])
 @pytest.mark.parametrize("seed", range(60))
-def test_fast_kernel_equals_generic_kernel_bit_for_bit(seed):
+def test_fast_kernel_equals_generic_kernel_bit_for_bit(seed, version):
     c = _case(1000 + seed)
-    a, ea, ra = _run(c, fast=True)
-    b, eb, rb = _run(c, fast=False)
+    a, ea, ra = _run(c, fast=version)
+    b, eb, rb = _run(c, fast=0)
     assert ea == eb
     for k in KEYS:
         np.testing.assert_array_equal(a[k].view(np.uint8), b[k].view(np.uint8), err_msg=f"{k} (seed {seed})")
     for x_, y_ in zip(ra, rb, strict=True):
         for k in ("particle_steps", "n_error", "n_deleted", "first_error_iter", "n_out_of_time", "max_state"):
             assert x_[k] == y_[k], (k, x_[k], y_[k])
-        assert x_["kernel_variant"] == 1 and y_["kernel_variant"] == 0
+        assert x_["kernel_variant"] == version and y_["kernel_variant"] == 0
 
 
 def test_fast_kernel_is_the_one_that_runs_and_refills_less_often_than_it_samples():
@@ -133,7 +137,7 @@ def test_fast_kernel_is_the_one_that_runs_and_refills_less_often_than_it_samples
     ps = pb.ParticleSet(fs, x=rng.uniform(5e3, 3.5e4, n), y=rng.uniform(-5e3, 2e4, n), z=rng.uniform(10, 700, n), t=np.zeros(n))
     ps.execute([pb.AdvectionRK4_3D, pb.DeleteParticle], dt=60.0, runtime=3600.0)
     rep = ps.last_report
-    assert rep["kernel_variant"] == 1
+    assert rep["kernel_variant"] == 2
     assert rep["particle_steps"] == n * 60
     assert 0 < rep["cache_refills"] < rep["particle_steps"] // 4
 
