@@ -132,9 +132,10 @@ def c2_particles(field, n, seed):
     return dict(x=rng.uniform(-170, 170, n), y=rng.uniform(-70, 70, n), z=rng.uniform(5, 5000, n), t=np.zeros(n))
 
 
-def c3_field(nx=1442, ny=1021, nt=3, seed=2):
+def c3_field(nx=1442, ny=1021, nt=3, seed=2, nz=1):
     """config 3: curvilinear C-grid of ORCA025 shape (ny, nx) = (1021, 1442): rotated-pole mesh with a
-    tanh-stretched latitude, f32 node coordinates (NEMO style), NEMO staggering (offsets X=1, Y=1), 2-D."""
+    tanh-stretched latitude, f32 node coordinates (NEMO style), NEMO staggering (offsets X=1, Y=1); 2-D, or with nz > 1
+    depth levels and a W component (the 3-D curvilinear path at ORCA size)."""
     rng = np.random.default_rng(seed)
     lam = np.deg2rad(np.linspace(-70.0, 70.0, nx))[None, :]          # rotated longitude
     s = np.linspace(-1.0, 1.0, ny)[:, None]
@@ -149,14 +150,19 @@ def c3_field(nx=1442, ny=1021, nt=3, seed=2):
     I = np.linspace(0, 2 * np.pi, nx, dtype=np.float32)[None, None, None, :]
     J = np.linspace(0, 2 * np.pi, ny, dtype=np.float32)[None, None, :, None]
     T = np.arange(nt, dtype=np.float32)[:, None, None, None]
-    shape = (nt, 1, ny, nx)
+    shape = (nt, nz, ny, nx)
+    K = (np.float32(1.0) - np.float32(0.6) * np.linspace(0, 1, nz, dtype=np.float32))[None, :, None, None]  # weaker flow at depth
 
     def noise():
         return rng.random(shape, dtype=np.float32) * np.float32(0.1) - np.float32(0.05)
 
-    U = (np.float32(0.5) * np.sin(3 * I + 0.4 * T) * np.cos(2 * J) + np.float32(0.2) * np.cos(4 * J) + noise()).astype(np.float32)
-    V = (np.float32(0.5) * np.cos(2 * I) * np.sin(3 * J + 0.3 * T) + np.float32(0.2) * np.sin(5 * I) + noise()).astype(np.float32)
-    return dict(lon=lon, lat=lat, depth=None, times=times, U=U, V=V, W=None, mesh="spherical", interp="cgrid_velocity",
+    U = ((np.float32(0.5) * np.sin(3 * I + 0.4 * T) * np.cos(2 * J) + np.float32(0.2) * np.cos(4 * J)) * K + noise()).astype(np.float32)
+    V = ((np.float32(0.5) * np.cos(2 * I) * np.sin(3 * J + 0.3 * T) + np.float32(0.2) * np.sin(5 * I)) * K + noise()).astype(np.float32)
+    depth = W = None
+    if nz > 1:
+        depth = (5000.0 * np.linspace(0.0, 1.0, nz) ** 1.7).astype(np.float32)
+        W = ((np.float32(2e-3) * np.sin(2 * I) * np.sin(3 * J) * np.cos(np.float32(0.5) * T)) * K + np.float32(1e-2) * noise()).astype(np.float32)
+    return dict(lon=lon, lat=lat, depth=depth, times=times, U=U, V=V, W=W, mesh="spherical", interp="cgrid_velocity",
                 padding=("low", "low", "high"))  # fmt: skip
 
 
@@ -173,7 +179,9 @@ def c3_particles(field, n, seed):
         return ((1 - fj) * (1 - fi) * a[j0, i0] + (1 - fj) * fi * a[j0, i0 + 1] + fj * fi * a[j0 + 1, i0 + 1]
                 + fj * (1 - fi) * a[j0 + 1, i0])  # fmt: skip
 
-    return dict(x=bl(lon), y=bl(lat), z=np.zeros(n), t=np.zeros(n))
+    depth = field.get("depth")
+    z = np.zeros(n) if depth is None else rng.uniform(float(depth[1]), float(depth[-2]), n)
+    return dict(x=bl(lon), y=bl(lat), z=z, t=np.zeros(n))
 
 
 def _hash_noise(t, z, y, x, salt):
@@ -231,6 +239,14 @@ WORKLOADS = {
                              "arithmetic (profiles/README.md: DRAM < 1 % of peak, cos+sin a quarter of the executed instructions)",
                desc="BASELINE.json configs[2] -- AdvectionRK4, 1e7 particles, curvilinear C-grid ORCA025 shape 1442x1021 T=3, "
                     "f32 lon/lat, CGrid_Velocity + hint/spatial-hash search, spherical"),
+    "c3_3d": dict(field=c3_field, fkw=dict(nx=1442, ny=1021, nt=2, nz=31), particles=c3_particles, n=10_000_000, dt=3600.0,
+                  nsteps=24, kernels=["AdvectionRK4_3D"], bytes=384, ulp=8, ulp_quantile=0.999,
+                  desc="SURVEY 8 row f-4 -- AdvectionRK4_3D on the curvilinear C-grid of ORCA025 shape with 31 depth levels "
+                       "(1442x1021x31 T=2 f32 U,V,W, 1.1 GB), 1e7 particles, CGrid_Velocity + W linear between the Z faces"),
+    "c3_orca12": dict(field=c3_field, fkw=dict(nx=4322, ny=3059, nt=2), particles=c3_particles, n=10_000_000, dt=1200.0,
+                      nsteps=48, kernels=["AdvectionRK4"], bytes=320, ulp=8, ulp_quantile=0.999,
+                      desc="SURVEY 8 row f-4 -- AdvectionRK4 on a curvilinear C-grid of ORCA12 shape 4322x3059 (13.2 M faces in the "
+                           "spatial hash) T=2, 1e7 particles"),
     "c3_small": dict(field=c3_field, fkw=dict(nx=362, ny=292, nt=3), particles=c3_particles, n=200_000, dt=3600.0,
                      nsteps=48, kernels=["AdvectionRK4"], bytes=320, ulp=8, desc="small functional variant of c3"),
     "c4": dict(field=c2_field, fkw=dict(nx=1440, ny=720, nz=50, nt=3), particles=c2_particles, n=10_000_000, dt=600.0,
@@ -247,7 +263,7 @@ C5 = {"c5": dict(dims=dict(nx=4320, ny=2160, nz=50, nt=2), n=12_500_000), "c5_sm
 
 def config_block(name, w, n_per_gpu):
     """`config` of the JSON line: what BOTH arms run (the reference arm prints the same dict)."""
-    fbytes = {"ns": 16.8, "c2": 1.87, "c4": 1.87, "c3": 0.035}.get(name)
+    fbytes = {"ns": 16.8, "c2": 1.87, "c4": 1.87, "c3": 0.035, "c3_3d": 1.1, "c3_orca12": 0.21}.get(name)
     return {
         "workload": f"{name}: {w['desc']}; dt={w['dt']:g} s x {w['nsteps']} dt-steps per pass",
         "kernels": w["kernels"] + ["DeleteParticle"],
@@ -375,12 +391,12 @@ def parity_and_cpu_baseline(name, w, field, fs, device, n_sample, seed_gpu=1234)
     parts = w["particles"](field, n_sample, 1)
     normal = None
     if "DiffusionUniformKh" in w["kernels"]:
-        from philox_ref import wiener_normals  # NumPy restatement of the device's Philox stream: same Wiener increments for the oracle
+        from philox_ref import device_normals  # the engine's own Wiener increments (pb_debug_normals) for the oracle
 
         st = {"it": 0}
 
         def normal(view):
-            zx, zy = wiener_normals(seed_gpu, 1, st["it"], view.particle_id)  # (seed; call 1 of a fresh ParticleSet, iteration, id)
+            zx, zy = device_normals(seed_gpu, 1, st["it"], view.particle_id, device=device)  # (seed; call 1 of a fresh ParticleSet, iteration, id)
             st["it"] += 1
             return zx, zy
 

@@ -83,6 +83,13 @@ inline void sincospi(double x, double* s, double* c) {  // exact reduction to [-
     *s = std::sin(3.14159265358979323846 * r);
     *c = std::cos(3.14159265358979323846 * r);
 }
+inline void sincospif(float x, float* s, float* c) {
+    float r = std::fmod(x, 2.0f);
+    if (r > 1.0f) r -= 2.0f;
+    if (r < -1.0f) r += 2.0f;
+    *s = std::sin(3.14159265358979323846f * r);
+    *c = std::cos(3.14159265358979323846f * r);
+}
 using std::isfinite;
 // CUDA's min / max accept mixed integer types
 inline int min(int a, int b) { return a < b ? a : b; }

@@ -1,4 +1,10 @@
-// afast2.cu -- second schedule of the headline hot path (AdvectionRK4 / AdvectionRK4_3D with XLinear_Velocity on a rectilinear
+// afast2.cu -- EXPERIMENT (opt-in: PB_FAST_KERNEL=2), measured SLOWER than afast.cu and kept for the record: it executes 19 %
+// fewer instructions (1716 vs 2119 per warp and dt-step on config 2) but its four written-out stages + out-of-line side path are
+// 5000 SASS instructions = 80 KB, past the 32 KB L1.5 instruction cache: `stall_no_inst` becomes the top stall (ncu,
+// profiles/README.md r02g) -- config 2 17.0 vs 16.4 ms, 1/12 deg 259 vs 205 ms, fused diffusion 396 vs 224 ms.  The lesson
+// (hot loop < 2000 instructions) shaped the later changes to afast.cu, the diffusion block and the curvilinear kernel.
+//
+// second schedule of the headline hot path (AdvectionRK4 / AdvectionRK4_3D with XLinear_Velocity on a rectilinear
 // A-grid with FLOAT64 coordinates, FLOAT32 data and a time axis: reference kernels/_advection.py:42-75,
 // interpolators/_xinterpolators.py:78-190, _core/field.py:250-405).  Same arithmetic, operation by operation, as afast.cu and the
 // generic AGridPolicy<double, float, true, NC, 0>; what changed is where the instructions go (ncu of afast.cu on config 2,

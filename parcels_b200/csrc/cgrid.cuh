@@ -31,7 +31,55 @@ static __device__ __noinline__ double sin_ool(double x) { return sin(x); }
 static __device__ __noinline__ float cosf_ool(float x) { return cosf(x); }
 static __device__ __noinline__ float sinf_ool(float x) { return sinf(x); }
 __device__ __forceinline__ float cosx(float x) { return cosf_ool(x); }
-__device__ __forceinline__ double cosx(double x) { return cos_ool(x); }
+__device__ __forceinline__ double cosx(double x) { return cos_np(x); }  // (a latitude: common.cuh's polynomial, inline)
+// Per-sample trigonometry of the curvilinear search (ncu, profiles/README.md r02f: the out-of-line cos / sin above were 33 % of the
+// executed instructions of config 3 -- 24 + 8 calls of ~70 instructions per warp and step).  The query's unit vector needs
+// sin / cos of a LATITUDE (|x| <= pi/2: one odd polynomial each, like cos_np) and of a LONGITUDE (|x| <= 4 pi: one shared
+// quadrant reduction + the two fdlibm kernel polynomials on [-pi/4, pi/4]); <= 2 ulp like CUDA's own, anything outside those
+// ranges takes sincos().  The one-time per-cell table (project_cell) keeps CUDA's sin / cos.
+static __device__ __noinline__ void sincos_cold(double x, double* s, double* c) { sincos(x, s, c); }
+__device__ __forceinline__ double sin_lat(double x) {
+    if (!(fabs(x) <= 1.5707963267948968)) { double s, c; sincos_cold(x, &s, &c); return s; }
+    const double z = x * x;
+    double p = -3.8681701706306841e-23;      // -1/23!
+    p = fma(p, z, 1.9572941063391263e-20);
+    p = fma(p, z, -8.2206352466243295e-18);
+    p = fma(p, z, 2.8114572543455206e-15);
+    p = fma(p, z, -7.6471637318198164e-13);
+    p = fma(p, z, 1.6059043836821613e-10);
+    p = fma(p, z, -2.5052108385441720e-08);
+    p = fma(p, z, 2.7557319223985893e-06);
+    p = fma(p, z, -1.9841269841269841e-04);
+    p = fma(p, z, 8.3333333333333332e-03);
+    p = fma(p, z, -1.6666666666666666e-01);
+    return fma(x * z, p, x);
+}
+__device__ __forceinline__ void sincos_lon(double x, double& sn, double& cs) {
+    if (!(fabs(x) <= 13.0)) { sincos_cold(x, &sn, &cs); return; }
+    const double t = x * 0.63661977236758138 + 6755399441055744.0;  // round(x * 2 / pi) by the 1.5 * 2^52 trick
+    const double kf = t - 6755399441055744.0;
+    const int k = (int)kf;
+    double r = fma(-kf, 1.5707963267948966, x);  // Cody-Waite, pi/2 = hi + lo (|k| <= 8)
+    r = fma(-kf, 6.123233995736766e-17, r);
+    const double z = r * r;
+    double ps = 1.58969099521155010221e-10;  // fdlibm __kernel_sin / __kernel_cos coefficients
+    ps = fma(ps, z, -2.50507602534068634195e-08);
+    ps = fma(ps, z, 2.75573137070700676789e-06);
+    ps = fma(ps, z, -1.98412698298579493134e-04);
+    ps = fma(ps, z, 8.33333333332248946124e-03);
+    ps = fma(ps, z, -1.66666666666666324348e-01);
+    const double s0 = fma(r * z, ps, r);
+    double pc = -1.13596475577881948265e-11;
+    pc = fma(pc, z, 2.08757232129817482790e-09);
+    pc = fma(pc, z, -2.75573143513906633035e-07);
+    pc = fma(pc, z, 2.48015872894767294178e-05);
+    pc = fma(pc, z, -1.38888888888741095749e-03);
+    pc = fma(pc, z, 4.16666666666666019037e-02);
+    const double c0 = fma(z, fma(z, pc, -0.5), 1.0);
+    const double a = (k & 1) ? c0 : s0, b = (k & 1) ? s0 : c0;  // quadrant k & 3: (s, c), (c, -s), (-s, -c), (-c, s)
+    sn = (k & 2) ? -a : a;
+    cs = ((k + 1) & 2) ? -b : b;
+}
 __device__ __forceinline__ float sinx(float x) { return sinf_ool(x); }
 __device__ __forceinline__ double sinx(double x) { return sin_ool(x); }
 __device__ __forceinline__ float sqrt_np(float x) { return sqrtf(x); }
@@ -622,9 +670,11 @@ struct CurvPolicy {
         double cos_lat = 1.0;  // cos(deg2rad(y)) in float64: also the spherical conversion factor of a float64 position
         if (SPH) {
             const double la = deg2rad_np(y), lo = deg2rad_np(x);
-            const double cl = cos_ool(la);
+            const double cl = cos_np(la);
             cos_lat = cl;
-            q.qu_x = cos_ool(lo) * cl; q.qu_y = sin_ool(lo) * cl; q.qu_z = sin_ool(la);
+            double sl, cl2;
+            sincos_lon(lo, sl, cl2);
+            q.qu_x = cl2 * cl; q.qu_y = sl * cl; q.qu_z = sin_lat(la);
         }
         double xsi = -1.0, eta = -1.0;
         int yi, xi;
@@ -824,8 +874,10 @@ __global__ void sample_scalar_curv_kernel(const SampleParams s, int mode /* 4: X
         q.x = x; q.y = y;
         if (SPH) {
             const double la = deg2rad_np(y), lo = deg2rad_np(x);
-            const double cl = cos_ool(la);
-            q.qu_x = cos_ool(lo) * cl; q.qu_y = sin_ool(lo) * cl; q.qu_z = sin_ool(la);
+            const double cl = cos_np(la);
+            double sl, cl2;
+            sincos_lon(lo, sl, cl2);
+            q.qu_x = cl2 * cl; q.qu_y = sl * cl; q.qu_z = sin_lat(la);
         }
         double xsi = -1.0, eta = -1.0;
         int yi, xi;

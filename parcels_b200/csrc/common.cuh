@@ -217,16 +217,19 @@ __device__ __forceinline__ void wiener_normals(unsigned long long seed, unsigned
     // key word 1 (mode D packs (call << 20) + round into it: distinct calls must never share a counter)
     philox4x32_10((uint32_t)pid, (uint32_t)((unsigned long long)pid >> 32), (uint32_t)iter, (uint32_t)rng_call,
                   (uint32_t)seed, (uint32_t)(seed >> 32) ^ (uint32_t)(rng_call >> 32), r);
-    const double two_m32 = 2.3283064365386963e-10;  // 2^-32
-    double u1 = ((double)r[0] + 0.5) * two_m32;
-    double u2 = ((double)r[1] + 0.5) * two_m32;
-    double rad = sqrt(-2.0 * log(u1));
-    // cos / sin of 2 pi u2 through sincospi: exact argument reduction, no Payne-Hanek slow path in the kernel's code
-    // (the two were ~600 SASS instructions inside the time loop); differs from cos(6.283... * u2) by a few 1e-16
-    double s, c;
-    sincospi(2.0 * u2, &s, &c);
-    zx = rad * c;
-    zy = rad * s;
+    // Box-Muller in FLOAT32 (round 2): the increment is a random number whose stream differs from NumPy's MT19937 anyway (DESIGN.md
+    // waiver 3), so its last 29 bits buy nothing -- but the float64 log + sqrt + sincospi were ~300 of the ~750 instructions per
+    // particle and step that DiffusionUniformKh adds (ncu, profiles/README.md r02f c4).  logf / sqrtf / sincospif are accurate to
+    // 1-2 float32 ulp; u1 keeps its 2^-33 tail resolution (small counter values convert exactly: |z| reaches 6.8 as before).
+    // Everything that USES the increment stays the reference's float64 arithmetic.
+    const float two_m32 = 2.3283064365386963e-10f;  // 2^-32
+    const float u1 = ((float)r[0] + 0.5f) * two_m32;
+    const float u2 = ((float)r[1] + 0.5f) * two_m32;
+    const float rad = sqrtf(-2.0f * logf(u1));
+    float s, c;
+    sincospif(2.0f * u2, &s, &c);
+    zx = (double)(rad * c);
+    zy = (double)(rad * s);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -12,7 +12,7 @@ import parcels_b200 as pb
 from engine_run import make_fieldset, ulp_diff_f32
 from oracle import parcels_oracle as po
 from oracle_run import oracle_fieldset
-from philox_ref import wiener_normals
+from philox_ref import device_normals, wiener_normals
 
 warnings.simplefilter("ignore")
 ALL_INTERPS = ("linear", "linear", "freeslip", "partialslip", "nearest", "cgrid_velocity")
@@ -161,7 +161,7 @@ def fuzz_advdiff(rng):
     st = {"it": 0}
 
     def normal(view):
-        zx, zy = wiener_normals(seed, 1, st["it"], view.particle_id)
+        zx, zy = device_normals(seed, 1, st["it"], view.particle_id)
         st["it"] += 1
         return zx, zy
 
@@ -207,7 +207,7 @@ def fuzz_diffusion(rng):
     st = {"call": 0, "it": 0}
 
     def normal(view):
-        zx, zy = wiener_normals(seed, st["call"], st["it"], view.particle_id)
+        zx, zy = device_normals(seed, st["call"], st["it"], view.particle_id)
         st["it"] += 1
         return zx, zy
 

@@ -37,8 +37,29 @@ def wiener_normals(seed, rng_call, it, particle_id):
         np.full(n, np.uint32(it & 0xFFFFFFFF)), np.full(n, np.uint32(rng_call & 0xFFFFFFFF)),
         seed & 0xFFFFFFFF, ((seed >> 32) ^ (rng_call >> 32)) & 0xFFFFFFFF,
     )  # fmt: skip
-    u1 = (r0.astype(np.float64) + 0.5) * 2.0**-32
-    u2 = (r1.astype(np.float64) + 0.5) * 2.0**-32
-    rad = np.sqrt(-2.0 * np.log(u1))
-    ang = 6.283185307179586476925 * u2
-    return rad * np.cos(ang), rad * np.sin(ang)
+    # float32 Box-Muller like the device (common.cuh wiener_normals); logf / sinf / cosf of NumPy and CUDA agree to 1-2 float32 ulp,
+    # so this restatement equals the device's increments to ~1e-6 relative -- the parity tests inject the DEVICE's own
+    # increments (device_normals below) into the oracle, this function pins the stream's integer part and its statistics
+    f32 = np.float32
+    u1 = (r0.astype(f32) + f32(0.5)) * f32(2.0**-32)
+    u2 = (r1.astype(f32) + f32(0.5)) * f32(2.0**-32)
+    rad = np.sqrt(f32(-2.0) * np.log(u1))
+    ang = (f32(2.0) * u2).astype(np.float64) * np.pi
+    return (rad * np.cos(ang).astype(f32)).astype(np.float64), (rad * np.sin(ang).astype(f32)).astype(np.float64)
+
+
+_ENGINE = {}
+
+
+def device_normals(seed, rng_call, it, particle_id, device=0):
+    """The engine's own Wiener increments for (seed; call, iteration, particle ids) -- pb_debug_normals runs the very device
+    function the kernels call.  Feeding these to the oracle pins the DETERMINISTIC part of the diffusion kernels bit for bit."""
+    from parcels_b200.engine import Engine
+
+    if device not in _ENGINE:
+        _ENGINE[device] = Engine(device)
+    pid = np.asarray(particle_id, dtype=np.int64)
+    if pid.size == 0:
+        return np.zeros(0), np.zeros(0)
+    out = _ENGINE[device].debug_normals(seed=seed, rng_call=rng_call, it=it, particle_id=pid)
+    return out[:, 0].copy(), out[:, 1].copy()

@@ -14,7 +14,7 @@ import pytest
 from advdiff_run import case_inputs, run_engine_advdiff, run_oracle_advdiff
 from engine_run import ulp_diff_f32
 from oracle.make_golden import ADVDIFF_CASES
-from philox_ref import wiener_normals
+from philox_ref import device_normals, wiener_normals
 
 pytestmark = pytest.mark.gpu
 ERR_NAME = {60: "FieldOutOfBoundError", 61: "FieldOutOfBoundSurfaceError", 70: "OutsideTimeInterval", 51: "FieldInterpolationError"}
@@ -28,7 +28,7 @@ def test_advdiff_matches_oracle_with_same_normals(name):
     state = {"it": 0}
 
     def normal(view):  # one Kernel.execute call (rng_call = 1), one normal pair per particle and loop iteration
-        zx, zy = wiener_normals(seed, 1, state["it"], view.particle_id)
+        zx, zy = device_normals(seed, 1, state["it"], view.particle_id)
         state["it"] += 1
         return zx, zy
 
@@ -111,7 +111,7 @@ def test_advdiff_in_a_mixed_list_matches_oracle():
 
     def normal(view):
         launch["k"] += 1
-        return wiener_normals(seed, launch["k"], 0, view.particle_id)
+        return device_normals(seed, launch["k"], 0, view.particle_id)
 
     def ODrift(p, fs_):
         p.dx = p.dx + 1.5

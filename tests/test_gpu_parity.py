@@ -20,7 +20,7 @@ import cases
 from engine_run import make_fieldset, run_engine, ulp_diff_f32
 from oracle import parcels_oracle as po
 from oracle_run import load_case, run_oracle
-from philox_ref import wiener_normals
+from philox_ref import device_normals, wiener_normals
 
 pytestmark = pytest.mark.gpu
 
@@ -116,8 +116,9 @@ def test_device_philox_matches_numpy_restatement():
     pid = np.array([0, 1, 2, 12345, 2**33 + 7, 10**12], dtype=np.int64)
     dev = eng.debug_normals(seed=0xDEADBEEFCAFE, rng_call=3, it=17, particle_id=pid)
     zx, zy = wiener_normals(0xDEADBEEFCAFE, 3, 17, pid)
-    np.testing.assert_allclose(dev[:, 0], zx, rtol=1e-12, atol=1e-14)
-    np.testing.assert_allclose(dev[:, 1], zy, rtol=1e-12, atol=1e-14)
+    # float32 Box-Muller on both sides: logf / sincospif of CUDA against NumPy's float32 log / sin / cos
+    np.testing.assert_allclose(dev[:, 0], zx, rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(dev[:, 1], zy, rtol=2e-5, atol=2e-6)
 
 
 def test_fused_diffusion_matches_oracle_with_same_normals():
@@ -133,7 +134,7 @@ def test_fused_diffusion_matches_oracle_with_same_normals():
     state = {"call": 1, "it": 0}
 
     def normal(view):
-        zx, zy = wiener_normals(seed, state["call"], state["it"], view.particle_id)
+        zx, zy = device_normals(seed, state["call"], state["it"], view.particle_id)
         state["it"] += 1
         calls["n"] += 1
         return zx, zy
