@@ -210,16 +210,13 @@ struct AFastPolicy {
             {   // cell widths changed: new reciprocals (the division itself: correctly rounded)
                 double2* const rp = rcp(e);
                 const double nwt = ct.hi - ct.lo, nwz = cz.hi - cz.lo, nwy = cy.hi - cy.lo, nwx = cx.hi - cx.lo;
-                if ((HZ && !(nwz == wz)) || !(nwy == wy)) {
-                    double2 d;
-                    d.x = 1.0 / nwz; d.y = 1.0 / nwy;
-                    rp[0] = d;
-                }
-                if (!(nwx == wx) || !(nwt == wt)) {
-                    double2 d;
-                    d.x = 1.0 / nwx; d.y = 1.0 / nwt;
-                    rp[PB_FAST_BLOCK] = d;
-                }
+                // (one division per axis whose cell width changed -- a particle crosses one face at a time: usually one of the four)
+                double* const r0 = reinterpret_cast<double*>(rp);
+                double* const r1 = reinterpret_cast<double*>(rp + PB_FAST_BLOCK);
+                if (HZ && !(nwz == wz)) r0[0] = 1.0 / nwz;
+                if (!(nwy == wy)) r0[1] = 1.0 / nwy;
+                if (!(nwx == wx)) r1[0] = 1.0 / nwx;
+                if (!(nwt == wt)) r1[1] = 1.0 / nwt;
             }
             e.ti = ti; e.zi = zi; e.yi = yi; e.xi = xi;
             if (g.decomposed) {  // mode D: a sentinel at a slab edge that is not the edge of the global domain = halo too small

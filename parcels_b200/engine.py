@@ -167,6 +167,9 @@ class Engine:
             )
         )  # fmt: skip
 
+    def download_ids(self, particle_id: np.ndarray):
+        check(self._lib.pb_particles_download_ids(self._h, particle_id.shape[0], ptr(particle_id)))
+
     # -- output path (device-side ParticleFile.write selection, ordered compaction) -----------------
     OUTPUT_COLUMNS = {"x": np.float32, "y": np.float32, "z": np.float32, "t": np.float64, "particle_id": np.int64}
 

@@ -15,7 +15,7 @@ import types
 import numpy as np
 
 from . import kernels as K
-from .particle import Particle, ParticleClass, create_particle_data
+from .particle import _CORE, Particle, ParticleClass, create_particle_data
 from .statuscodes import ERRORS_TO_THROW, StatusCode, raise_for_state
 
 __all__ = ["Kernel", "ParticleSet"]
@@ -58,6 +58,9 @@ def _min_or_max(t, want_min: bool) -> float:
         _lib.check(_lib.load().pb_host_min_max_f64(_lib.ptr(t), t.size, C.byref(mn), C.byref(mx), C.byref(nan)))
         return float("nan") if nan.value else (mn.value if want_min else mx.value)
     return float(t.min() if want_min else t.max())
+
+
+_CORE_NAMES = {name for name, _ in _CORE} | {"ei"}
 
 
 def _remove_deleted_host(d: dict) -> int:
@@ -734,12 +737,17 @@ class ParticleSet:
             self._host_stale = True
             self._n_device = n
             d = self._data  # full download
-        elif (rep["n_deleted"] > 0 and rep["max_state"] < StatusCode.Error and len(self._pclass.extra) == 0 and not downloaded
-              and d["ei"].shape[1] == 1 and self.fieldset.time_window is None):  # fmt: skip
+        elif (rep["n_deleted"] > 0 and rep["max_state"] < StatusCode.Error and len(self._pclass.extra) == 0
+              and d["ei"].shape[1] == 1 and self.fieldset.time_window is None and set(d) == _CORE_NAMES
+              and all(v.flags.c_contiguous for v in d.values())):  # fmt: skip
             # deletions, nothing to raise: drop the deleted particles in HBM (order preserved, like np.delete) and download the
-            # compacted set -- instead of downloading everything and np.delete-ing every host array (kernel.py:98-106)
-            eng.remove_deleted()
-            new = eng.download_all(ngrids=1)
+            # compacted set INTO THE PREFIX of the existing host arrays (views of the same -- possibly pinned -- buffers: no 11
+            # fresh columns to fault in, no np.delete pass over every host array, kernel.py:98-106).  Also after a pipelined call
+            # that already brought the uncompacted result back: a second, compacted D2H is cheaper than compacting on the host.
+            keep = eng.remove_deleted()
+            new = {k: v[:keep] for k, v in d.items()}
+            eng.download_particles(new, new["ei"][:, -1])
+            eng.download_ids(new["particle_id"])
             new["dt"][:] = dt  # kernel.py:225-226
             d.update(new)  # keep the dict object: it may be shared with the caller (adapter.pset_from_parcels)
             self._device_synced = True
