@@ -385,9 +385,10 @@ def make_scalar_golden():
 SCALAR_CURV_CASES = ("curv_sph_2d", "curv_flat_2d", "curv_sph_3d", "curv_sph_f32")
 
 
-def make_scalar_curv_golden():
-    """Field.eval on CURVILINEAR grids (CGrid_Tracer / XNearest): a fresh set (every hinted xi is 0: the whole batch goes through the
-    spatial hash) and a second, displaced evaluation hinted by the cells just found."""
+def make_scalar_curv_golden(methods=("nearest", "cgrid_tracer"), out_name="scalar_eval_curv.npz"):
+    """Field.eval on CURVILINEAR grids (CGrid_Tracer / XNearest; XLinear in its own file, ``python -m oracle.make_golden
+    scalar_curv_linear``): a fresh set (every hinted xi is 0: the whole batch goes through the spatial hash) and a second,
+    displaced evaluation hinted by the cells just found."""
     import warnings
 
     import cases as tc
@@ -398,7 +399,7 @@ def make_scalar_curv_golden():
         c = tc.build(tc.CASES[name])
         for T in (c["U"].shape[0], 1):
             P, tq = scalar_inputs(c, T)
-            for how in ("nearest", "cgrid_tracer"):
+            for how in methods:
                 fs = rh.build_fieldset(lon=c["lon"], lat=c["lat"], depth=c["depth"], times=c["times"], U=c["U"], V=c["V"], W=c["W"],
                                        mesh=c["mesh"], padding=c.get("padding", ("low", "low", "high")), interp="cgrid_velocity",
                                        scalars={"P": (P, how)})  # fmt: skip
@@ -413,7 +414,7 @@ def make_scalar_curv_golden():
                 out[f"{key}/value"], out[f"{key}/ei"] = val, ei1
                 out[f"{key}/value2"], out[f"{key}/ei2"], out[f"{key}/state2"] = val2, ps._data["ei"].copy(), ps._data["state"].copy()
         print(f"scalar curv {name}: done")
-    np.savez_compressed(os.path.join(GOLDEN, "scalar_eval_curv.npz"), **out)
+    np.savez_compressed(os.path.join(GOLDEN, out_name), **out)
 
 
 # name -> (RK45_tol in metres, RK45_min_dt, RK45_max_dt factor of |dt|, runtime, dt)
@@ -540,6 +541,10 @@ def make_advdiff_golden():
 
 if __name__ == "__main__":
     os.makedirs(GOLDEN, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "scalar_curv_linear":
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        make_scalar_curv_golden(methods=("linear",), out_name="scalar_eval_curv_linear.npz")
+        sys.exit(0)
     if len(sys.argv) > 2 and sys.argv[1] == "ref_cases":
         make_ref_cases(only=set(sys.argv[2:]))
         sys.exit(0)

@@ -836,7 +836,7 @@ struct CurvPolicy {
 // that the advection kernel's code stays exactly what the profiles measured.
 // ------------------------------------------------------------------------------------------------
 template <class A, class D, bool SPH>
-__global__ void sample_scalar_curv_kernel(const SampleParams s, int mode /* 4: XNearest, 5: CGrid_Tracer */, int has_time) {
+__global__ void sample_scalar_curv_kernel(const SampleParams s, int mode /* 3: XLinear, 4: XNearest, 5: CGrid_Tracer */, int has_time) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= s.n) return;
     const GridDev& g = s.g;
@@ -900,6 +900,42 @@ __global__ void sample_scalar_curv_kernel(const SampleParams s, int mode /* 4: X
         if (xi == -3 || yi == -3) state = max(state, (int)PB_ERROR_GRID_SEARCHING);
         if (zi == -2) state = max(state, (int)PB_ERROR_THROUGH_SURFACE);
         if (xi < 0 || yi < 0 || zi < 0) break;  // masked to 0 (field.py:189)
+        if (mode == 3) {
+            // -- XLinear (_xinterpolators.py:112-153) on the searched cell: T-lerp, Z-lerp, bilinear in NumPy's dtypes.  xsi / eta are
+            // the closed-form inverse's float64 values (float32-ROUNDED after a hash hit: DESIGN.md waiver 4), so the value is float64.
+            const int bf = s.batch_flags ? *s.batch_flags : -1;
+            const bool two_t = has_time && (bf >= 0 ? (bf & 1) != 0 : (tau > 0));
+            const bool two_z = g.nz > 0 && (bf >= 0 ? (bf & 2) != 0 : !(zeta <= 0));
+            const bool zeta_f32 = f32 && std::is_same<A, float>::value;
+            const long long ot[2] = {wrap_idx(ti, f.T) * f.sT, up_idx(ti, f.T) * f.sT};
+            const long long oz[2] = {wrap_idx(zi, f.Z) * f.sZ, up_idx(zi, f.Z) * f.sZ};
+            const long long oy[2] = {wrap_idx(yi, f.Y) * f.sY, up_idx(yi, f.Y) * f.sY};
+            const long long ox[2] = {wrap_idx(xi, f.X) * f.sX, up_idx(xi, f.X) * f.sX};
+            const D* __restrict__ P = (const D*)f.p[0];
+            const double omt = 1 - tau;
+            double rr[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const long long o = oy[k >> 1] + ox[k & 1];
+                const D a0 = ldg(P + ot[0] + oz[0] + o), a1 = ldg(P + ot[0] + oz[1] + o);
+                if (!two_t && std::is_same<D, float>::value && zeta_f32) {  // float32 data, float32 zeta: the Z-lerp is float32
+                    const float zf = (float)zeta;
+                    rr[k] = two_z ? (double)((float)a0 * (1 - zf) + (float)a1 * zf) : (double)a0;
+                } else {
+                    double lo = (double)a0, hi = (double)a1;
+                    if (two_t) {
+                        lo = lo * omt + (double)ldg(P + ot[1] + oz[0] + o) * tau;
+                        hi = hi * omt + (double)ldg(P + ot[1] + oz[1] + o) * tau;
+                    }
+                    const double omz = zeta_f32 ? (double)(1 - (float)zeta) : 1 - zeta;
+                    rr[k] = two_z ? lo * omz + hi * zeta : lo;
+                }
+            }
+            value = (1 - xsi) * (1 - eta) * rr[0] + xsi * (1 - eta) * rr[1] + (1 - xsi) * eta * rr[2] + xsi * eta * rr[3];
+            value_f32 = false;
+            if (value != value) state = max(state, (int)PB_ERROR_INTERPOLATION);
+            break;
+        }
         // -- the node: CGrid_Tracer = index + SGRID offset, XNearest = the near side of each axis; both clipped like the gathers
         int kz, ky, kx;
         if (mode == 5) {

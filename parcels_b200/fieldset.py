@@ -345,8 +345,9 @@ class FieldSet:
             raise ValueError(f"interp_method must be one of {sorted(Engine.SCALAR_METHODS)}. Got {interp_method!r}")
         if name in self.fields:
             raise ValueError(f"FieldSet already has a Field with name '{name}'")
-        if self.grid.curvilinear and interp_method not in ("nearest", "cgrid_tracer"):
-            raise NotImplementedError("on curvilinear grids scalar fields are sampled with 'cgrid_tracer' (CGrid_Tracer) or 'nearest' (XNearest)")
+        if self.grid.curvilinear and interp_method not in ("linear", "nearest", "cgrid_tracer"):
+            raise NotImplementedError("on curvilinear grids scalar fields are sampled with 'linear' (XLinear), 'cgrid_tracer' (CGrid_Tracer) "
+                                      "or 'nearest' (XNearest)")
         data = np.ascontiguousarray(data)
         if data.ndim != 4:
             raise ValueError(f"{name} must be laid out (T, Z, Y, X); got shape {data.shape}")

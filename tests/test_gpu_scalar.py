@@ -127,4 +127,32 @@ def test_scalar_eval_on_curvilinear_grids(name, golden_dir):
             np.testing.assert_array_equal(ps._data["ei"], g[f"{key}/ei2"], err_msg=key + " second")
             np.testing.assert_array_equal(ps._data["state"], g[f"{key}/state2"], err_msg=key + " second")
     with pytest.raises(NotImplementedError, match="cgrid_tracer"):
-        make_fieldset(c).add_field("Q", P, interp_method="linear")
+        make_fieldset(c).add_field("Q", P, interp_method="linear_invdist_land")
+
+
+@pytest.mark.parametrize("name", ["curv_sph_2d", "curv_flat_2d", "curv_sph_3d", "curv_sph_f32"])
+def test_xlinear_scalar_eval_on_curvilinear_grids(name, golden_dir):
+    """XLinear behind the curvilinear search (an A-grid tracer on 2-D lon / lat), against the reference's own values
+    (tests/golden/scalar_eval_curv_linear.npz): cells and states bit-exact; values within 64 float32 ulp of the field's range --
+    the barycentric coordinates come out of the closed-form bilinear inverse (last-ulp trig differences amplified, hash hits
+    rounded to float32: the curvilinear tolerance of the trajectory tests), and the reference's float32-TYPED coordinates after
+    a hash hit (DESIGN.md waiver 4) are float32-rounded float64 values here, so the value is always float64."""
+    g = np.load(os.path.join(golden_dir, "scalar_eval_curv_linear.npz"))
+    c = load_case(name)
+    for T in (c["U"].shape[0], 1):
+        P, tq = scalar_inputs(c, T)
+        fs = make_fieldset(c)
+        fs.add_field("P", P, interp_method="linear")
+        ps = pb.ParticleSet(fs, x=c["x"], y=c["y"], z=c["z"], t=c["t"])
+        v1 = fs.P.eval(tq, ps._data["z"], ps._data["y"], ps._data["x"], ps)
+        ei1 = ps._data["ei"].copy()
+        x2 = np.asarray(ps._data["x"], dtype=np.float64) + 0.3 * float(np.abs(np.diff(np.asarray(c["lon"], dtype=np.float64), axis=1)).mean())
+        v2 = fs.P.eval(tq, ps._data["z"], np.asarray(ps._data["y"], dtype=np.float64), x2, ps)
+        key = f"{name}/T{T}/linear"
+        tol = 64 * np.finfo(np.float32).eps * float(np.abs(P).max())
+        np.testing.assert_array_equal(ei1, g[f"{key}/ei"], err_msg=key)
+        np.testing.assert_array_equal(ps._data["ei"], g[f"{key}/ei2"], err_msg=key + " second")
+        np.testing.assert_array_equal(ps._data["state"], g[f"{key}/state2"], err_msg=key + " second")
+        np.testing.assert_allclose(v1, g[f"{key}/value"].astype(np.float64), rtol=0, atol=tol, err_msg=key)
+        np.testing.assert_allclose(v2, g[f"{key}/value2"].astype(np.float64), rtol=0, atol=tol, err_msg=key + " second")
+        assert np.abs(g[f"{key}/value"]).max() > 0
