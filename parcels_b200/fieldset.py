@@ -137,11 +137,12 @@ class Field:
     """Scalar field on the fieldset's grid (reference ``_core/field.py:46-202``).  ``interp_method``: "linear" (XLinear),
     "nearest" (XNearest), "cgrid_tracer" (CGrid_Tracer) or "constant" (XConstantField, a 1-node grid)."""
 
-    def __init__(self, name, data, grid, fieldset, interp_method="linear", slot=None):
+    def __init__(self, name, data, grid, fieldset, interp_method="linear", slot=None, host=None):
         self.name = name
         self.data = data
         self.grid = grid
         self._fieldset = fieldset
+        self._host = host  # who keeps this field's grid in HBM: the FieldSet (None) or an _ExtraGrid of it
         self.interp_method = interp_method
         self._slot = slot  # device field slot (include/parcels_b200.h: 0..2 = U, V, W; 3.. = scalar fields)
 
@@ -170,11 +171,14 @@ class Field:
             raise ValueError(f"Time values for particles with indices {np.where(np.isnan(t))[0]} cannot be NaN.")
         if positions_are_f32 is None:
             positions_are_f32 = all(a.dtype == np.float32 for a in (z, y, x))
+        # the reference hints EVERY field's search with the last `ei` column, whatever the field's grid (`igrid` stays -1,
+        # _core/field.py:101,173) and writes that field's cell back into it
         hint = None if particles is None else np.ascontiguousarray(np.asarray(particles.ei)[:, -1])
-        if _batch_skips_hint(fs.grid, hint):
+        host = self._host or fs
+        if _batch_skips_hint(self.grid, hint):
             hint = None
-        val, ei, st = fs.engine(device).sample_scalar(self._slot, self.interp_method, t, z, y, x,
-                                                      positions_are_f32=positions_are_f32, ei_hint=hint)  # fmt: skip
+        val, ei, st = host.engine(device).sample_scalar(self._slot, self.interp_method, t, z, y, x,
+                                                        positions_are_f32=positions_are_f32, ei_hint=hint)  # fmt: skip
         if particles is not None:
             particles.ei[:, -1] = ei
             state = np.asarray(particles.state)
@@ -237,6 +241,38 @@ class VectorField:
         return self.eval(*key)
 
 
+class _ExtraGrid:
+    """A further XGrid of the FieldSet (reference: every Field carries its own grid, _core/field.py:102-134; the gridset is the
+    list of distinct grids, _core/fieldset.py:225-235) with the scalar fields that live on it.  Each grid is resident in its own
+    device engine (grid axes / spatial hash + field slots 3..15); the advection kernels only ever see the velocity grid."""
+
+    def __init__(self, grid, time_s):
+        self.grid, self.time_s = grid, time_s
+        self.fields = []
+        self._engines = {}
+
+    def engine(self, device: int = 0) -> Engine:
+        eng = self._engines.get(device)
+        if eng is None:
+            eng = Engine(device)
+            g = self.grid
+            if g.curvilinear:
+                eng.upload_curvilinear_grid(g.lon, g.lat, g.depth, self.time_s, g.is_spherical(), g.deg2m, g.xdim, g.ydim, g.zdim,
+                                            g.get_spatial_hash())  # fmt: skip
+            else:
+                eng.upload_rectilinear_grid(g.lon, g.lat, g.depth, self.time_s, g.is_spherical(), g.deg2m, g.xdim, g.ydim, g.zdim)
+            eng.set_interpolation(INTERP_METHODS["cgrid_velocity" if g.curvilinear else "linear"], 1, 1, 0)
+            for f in self.fields:
+                eng.upload_field(f._slot, f.data)
+            self._engines[device] = eng
+        return eng
+
+    def release(self):
+        for e in self._engines.values():
+            e.close()
+        self._engines.clear()
+
+
 class _ConstantGrid:
     """Grid of the constant fields (reference _core/model.py:292-318): one node, own mesh."""
 
@@ -281,6 +317,7 @@ class FieldSet:
         self.constants = {}
         self.context = {}
         self._const_grid = None
+        self._extra_grids = []  # _ExtraGrid: scalar fields on grids other than the velocity grid
         self._time_s, self._time_origin = _to_seconds(time)
         for name, arr in (("U", U), ("V", V), ("W", W)):
             if arr is None:
@@ -319,7 +356,7 @@ class FieldSet:
 
     @property
     def gridset(self):
-        return [self.grid] + ([self._const_grid] if self._const_grid is not None else [])
+        return [self.grid] + [x.grid for x in self._extra_grids] + ([self._const_grid] if self._const_grid is not None else [])
 
     def add_constant_field(self, name, value, mesh="spherical"):
         """reference _core/fieldset.py:175-205."""
@@ -334,17 +371,20 @@ class FieldSet:
         self.fields[name] = f
         setattr(self, name, f)
 
-    def add_field(self, name, data, interp_method="linear"):
-        """Scalar field on the FieldSet's grid -- in the reference every data variable of the model's dataset is a
-        ``Field`` with its own ``interp_method`` (_core/fieldset.py:89-108, _core/field.py:102-134); here it is added
-        from an array laid out (T, Z, Y, X) with T == the time axis, or T == 1 for a field without a time dimension.
-        Sampled on the device: ``fieldset.<name>[particles]`` / ``.eval(t, z, y, x)``."""
+    def add_field(self, name, data, interp_method="linear", grid=None, time=None):
+        """Scalar field -- in the reference every data variable of the model's dataset is a ``Field`` with its own ``grid`` and
+        ``interp_method`` (_core/fieldset.py:89-108, _core/field.py:102-134); here it is added from an array laid out
+        (T, Z, Y, X) with T == the time axis, or T == 1 for a field without a time dimension.  ``grid``: an ``XGrid`` other than
+        the velocity grid (a second entry of ``fieldset.gridset``; ``time`` = that field's own time axis, default: the
+        fieldset's).  Sampled on the device: ``fieldset.<name>[particles]`` / ``.eval(t, z, y, x)``."""
         from .engine import Engine
 
         if interp_method not in Engine.SCALAR_METHODS:
             raise ValueError(f"interp_method must be one of {sorted(Engine.SCALAR_METHODS)}. Got {interp_method!r}")
         if name in self.fields:
             raise ValueError(f"FieldSet already has a Field with name '{name}'")
+        if grid is not None and grid is not self.grid:
+            return self._add_field_on_grid(name, data, interp_method, grid, time)
         if self.grid.curvilinear and interp_method not in ("linear", "nearest", "cgrid_tracer"):
             raise NotImplementedError("on curvilinear grids scalar fields are sampled with 'linear' (XLinear), 'cgrid_tracer' (CGrid_Tracer) "
                                       "or 'nearest' (XNearest)")
@@ -356,12 +396,44 @@ class FieldSet:
         nt = 1 if self._time_s is None else self._time_s.size
         if data.shape[0] not in (1, nt) or data.shape[1:] != self.U.data.shape[1:]:
             raise ValueError(f"{name} has shape {data.shape}; expected ({nt} or 1, {', '.join(map(str, self.U.data.shape[1:]))})")
-        slot = 3 + sum(1 for f in self.fields.values() if isinstance(f, Field) and f._slot is not None and f._slot >= 3)
+        slot = 3 + sum(1 for f in self.fields.values() if isinstance(f, Field) and f._host is None and f._slot is not None and f._slot >= 3)
         f = Field(name, data, self.grid, self, interp_method=interp_method, slot=slot)
         self.fields[name] = f
         setattr(self, name, f)
         for eng in self._engines.values():
             eng.upload_field(slot, data)
+        return f
+
+    def _add_field_on_grid(self, name, data, interp_method, grid, time):
+        if not isinstance(grid, XGrid):
+            raise TypeError(f"grid must be an XGrid, got {type(grid).__name__}")
+        if grid.curvilinear and interp_method not in ("linear", "nearest", "cgrid_tracer"):
+            raise NotImplementedError("on curvilinear grids scalar fields are sampled with 'linear', 'cgrid_tracer' or 'nearest'")
+        data = np.ascontiguousarray(data)
+        if data.ndim != 4:
+            raise ValueError(f"{name} must be laid out (T, Z, Y, X); got shape {data.shape}")
+        if data.dtype not in (np.float32, np.float64):
+            data = data.astype(np.float64)
+        time_s = self._time_s if time is None else _to_seconds(time)[0]
+        nt = 1 if time_s is None else time_s.size
+        nz = 1 if grid.depth is None else len(grid.depth)
+        ny, nx = (grid.lon.shape if grid.curvilinear else (len(grid.lat), len(grid.lon)))
+        if data.shape[0] not in (1, nt) or data.shape[1] not in (1, nz) or data.shape[2:] != (ny, nx):
+            raise ValueError(f"{name} has shape {data.shape}; expected ({nt} or 1, {nz} or 1, {ny}, {nx}) on its grid")
+        host = next((x for x in self._extra_grids if x.grid is grid), None)
+        if host is None:
+            host = _ExtraGrid(grid, time_s)
+            self._extra_grids.append(host)
+        elif (host.time_s is None) != (time_s is None) or (time_s is not None and not np.array_equal(host.time_s, time_s)):
+            raise NotImplementedError("fields on one grid share one time axis")
+        if len(host.fields) >= 13:
+            raise NotImplementedError("at most 13 scalar fields per grid")
+        f = Field(name, data, grid, self, interp_method=interp_method, slot=3 + len(host.fields), host=host)
+        host.fields.append(f)
+        self.fields[name] = f
+        setattr(self, name, f)
+        for eng in host._engines.values():
+            eng.upload_field(f._slot, data)
         return f
 
     def add_context(self, name, value):
@@ -405,7 +477,7 @@ class FieldSet:
                     else:
                         eng.window_create(slot, d.dtype, d.shape, self.time_window)
             for f in self.fields.values():
-                if isinstance(f, Field) and f._slot is not None and f._slot >= 3:
+                if isinstance(f, Field) and f._host is None and f._slot is not None and f._slot >= 3:
                     eng.upload_field(f._slot, f.data)
             self._win[device] = dict(first=0, n=0, resident=set())
             self._engines[device] = eng
@@ -445,3 +517,5 @@ class FieldSet:
         for e in self._engines.values():
             e.close()
         self._engines.clear()
+        for x in self._extra_grids:
+            x.release()
