@@ -43,6 +43,7 @@ inline long long __shfl_xor_sync(unsigned, long long v, int) { return v; }
 inline int __shfl_xor_sync(unsigned, int v, int) { return v; }
 inline long long __shfl_up_sync(unsigned, long long v, int) { return v; }  // only in kernels hostsim replaces (sel_scan)
 #define __grid_constant__
+#define __constant__ const
 inline void __syncthreads() {}
 inline int __syncthreads_count(int p) { return p ? 1 : 0; }
 inline unsigned __ballot_sync(unsigned, int p) { return p ? 1u : 0u; }

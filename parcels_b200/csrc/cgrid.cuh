@@ -40,20 +40,13 @@ __device__ __forceinline__ double cosx(double x) { return cos_np(x); }  // (a la
 static __device__ __noinline__ void sincos_cold(double x, double* s, double* c) { sincos(x, s, c); }
 __device__ __forceinline__ double sin_lat(double x) {
     if (!(fabs(x) <= 1.5707963267948968)) { double s, c; sincos_cold(x, &s, &c); return s; }
-    const double z = x * x;
-    double p = -3.8681701706306841e-23;      // -1/23!
-    p = fma(p, z, 1.9572941063391263e-20);
-    p = fma(p, z, -8.2206352466243295e-18);
-    p = fma(p, z, 2.8114572543455206e-15);
-    p = fma(p, z, -7.6471637318198164e-13);
-    p = fma(p, z, 1.6059043836821613e-10);
-    p = fma(p, z, -2.5052108385441720e-08);
-    p = fma(p, z, 2.7557319223985893e-06);
-    p = fma(p, z, -1.9841269841269841e-04);
-    p = fma(p, z, 8.3333333333333332e-03);
-    p = fma(p, z, -1.6666666666666666e-01);
-    return fma(x * z, p, x);
+    return sin_poly_pio2(x);
 }
+// fdlibm __kernel_sin / __kernel_cos coefficients (highest first), in constant memory like PB_SIN_TAYLOR
+static __constant__ double PB_KSIN[6] = {1.58969099521155010221e-10, -2.50507602534068634195e-08, 2.75573137070700676789e-06,
+                                         -1.98412698298579493134e-04, 8.33333333332248946124e-03, -1.66666666666666324348e-01};
+static __constant__ double PB_KCOS[6] = {-1.13596475577881948265e-11, 2.08757232129817482790e-09, -2.75573143513906633035e-07,
+                                         2.48015872894767294178e-05, -1.38888888888741095749e-03, 4.16666666666666019037e-02};
 __device__ __forceinline__ void sincos_lon(double x, double& sn, double& cs) {
     if (!(fabs(x) <= 13.0)) { sincos_cold(x, &sn, &cs); return; }
     const double t = x * 0.63661977236758138 + 6755399441055744.0;  // round(x * 2 / pi) by the 1.5 * 2^52 trick
@@ -62,19 +55,10 @@ __device__ __forceinline__ void sincos_lon(double x, double& sn, double& cs) {
     double r = fma(-kf, 1.5707963267948966, x);  // Cody-Waite, pi/2 = hi + lo (|k| <= 8)
     r = fma(-kf, 6.123233995736766e-17, r);
     const double z = r * r;
-    double ps = 1.58969099521155010221e-10;  // fdlibm __kernel_sin / __kernel_cos coefficients
-    ps = fma(ps, z, -2.50507602534068634195e-08);
-    ps = fma(ps, z, 2.75573137070700676789e-06);
-    ps = fma(ps, z, -1.98412698298579493134e-04);
-    ps = fma(ps, z, 8.33333333332248946124e-03);
-    ps = fma(ps, z, -1.66666666666666324348e-01);
+    double ps = PB_KSIN[0], pc = PB_KCOS[0];
+#pragma unroll
+    for (int j = 1; j < 6; ++j) { ps = fma(ps, z, PB_KSIN[j]); pc = fma(pc, z, PB_KCOS[j]); }
     const double s0 = fma(r * z, ps, r);
-    double pc = -1.13596475577881948265e-11;
-    pc = fma(pc, z, 2.08757232129817482790e-09);
-    pc = fma(pc, z, -2.75573143513906633035e-07);
-    pc = fma(pc, z, 2.48015872894767294178e-05);
-    pc = fma(pc, z, -1.38888888888741095749e-03);
-    pc = fma(pc, z, 4.16666666666666019037e-02);
     const double c0 = fma(z, fma(z, pc, -0.5), 1.0);
     const double a = (k & 1) ? c0 : s0, b = (k & 1) ? s0 : c0;  // quadrant k & 3: (s, c), (c, -s), (-s, -c), (-c, s)
     sn = (k & 2) ? -a : a;

@@ -160,26 +160,27 @@ __device__ __forceinline__ float cos_np(float x) { return cosf(x); }
 // cos is <= 1 ulp): far inside the position tolerance of spherical meshes (2 float32 ulp).  Anything that is not a latitude
 // (|x| > pi/2, NaN) takes cos().  PB_FAST_COS=0 builds with cos() for A/B runs.
 static __device__ __noinline__ double cos_cold(double x) { return cos(x); }
+// Taylor coefficients of sin(r) / r in r^2, highest first: -1/23!, 1/21!, ..., -1/3!.  In CONSTANT memory on purpose: as literals the
+// compiler materialises each through two UMOVs (ncu, r02h: 13 % of the curvilinear kernel's executed instructions); from the
+// constant bank they are an operand of the DFMA itself.
+static __constant__ double PB_SIN_TAYLOR[11] = {-3.8681701706306841e-23, 1.9572941063391263e-20, -8.2206352466243295e-18, 2.8114572543455206e-15,
+                                                -7.6471637318198164e-13, 1.6059043836821613e-10, -2.5052108385441720e-08, 2.7557319223985893e-06,
+                                                -1.9841269841269841e-04, 8.3333333333333332e-03, -1.6666666666666666e-01};
+// sin(r) for |r| <= pi/2: r + r^3 P(r^2)
+__device__ __forceinline__ double sin_poly_pio2(double r) {
+    const double s = r * r;
+    double p = PB_SIN_TAYLOR[0];
+#pragma unroll
+    for (int k = 1; k < 11; ++k) p = fma(p, s, PB_SIN_TAYLOR[k]);
+    return fma(r * s, p, r);
+}
 __device__ __forceinline__ double cos_np(double x) {
 #if defined(PB_FAST_COS) && PB_FAST_COS == 0
     return cos(x);
 #else
     const double ax = fabs(x);
     if (!(ax <= 1.5707963267948968)) return cos_cold(x);
-    const double r = (1.5707963267948966 - ax) + 6.123233995736766e-17;  // pi/2 = hi + lo; hi - |x| is exact for |x| >= pi/4
-    const double s = r * r;
-    double p = -3.8681701706306841e-23;      // -1/23!
-    p = fma(p, s, 1.9572941063391263e-20);   //  1/21!
-    p = fma(p, s, -8.2206352466243295e-18);  // -1/19!
-    p = fma(p, s, 2.8114572543455206e-15);   //  1/17!
-    p = fma(p, s, -7.6471637318198164e-13);  // -1/15!
-    p = fma(p, s, 1.6059043836821613e-10);   //  1/13!
-    p = fma(p, s, -2.5052108385441720e-08);  // -1/11!
-    p = fma(p, s, 2.7557319223985893e-06);   //  1/9!
-    p = fma(p, s, -1.9841269841269841e-04);  // -1/7!
-    p = fma(p, s, 8.3333333333333332e-03);   //  1/5!
-    p = fma(p, s, -1.6666666666666666e-01);  // -1/3!
-    return fma(r * s, p, r);
+    return sin_poly_pio2((1.5707963267948966 - ax) + 6.123233995736766e-17);  // pi/2 = hi + lo; hi - |x| is exact for |x| >= pi/4
 #endif
 }
 
