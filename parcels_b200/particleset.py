@@ -114,6 +114,9 @@ def _first_eval_two_levels(fieldset, t, evaluated) -> bool:
     barycentric coordinate is float64 and the promotion changes nothing."""
     if fieldset._time_s is None or fieldset.grid.lon.dtype != np.float32:
         return False
+    t0 = float(fieldset._time_s[0])
+    if t.size >= (1 << 20) and _min_or_max(t, True) == t0 and _min_or_max(t, False) == t0:
+        return False  # every particle sits on the first level (the usual fresh set): no masked copies of a large column
     te = t[evaluated() if callable(evaluated) else evaluated]
     return bool(te.size) and bool(np.any(te != float(fieldset._time_s[0])))
 
@@ -139,6 +142,8 @@ def _hint_all_zero(ei_last, evaluated, xdim) -> bool:
     head = slice(0, min(len(ei_last), 4096))
     if np.any((ei_last[head][evaluated(head)].astype(np.int64) % xdim) != 0):
         return False
+    if not ei_last.any():  # a fresh set: every hint is 0 (one pass over the int32 column, no masked / widened copies)
+        return True
     full = slice(None)
     return not np.any((ei_last[evaluated(full)].astype(np.int64) % xdim) != 0)
 
