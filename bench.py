@@ -132,6 +132,13 @@ def c2_particles(field, n, seed):
     return dict(x=rng.uniform(-170, 170, n), y=rng.uniform(-70, 70, n), z=rng.uniform(5, 5000, n), t=np.zeros(n))
 
 
+def dense_particles(field, n, seed):
+    """a dense release (the common Parcels use: a cloud in a patch): 4 deg x 4 deg x the upper 200 m -- on the 1/12 deg grid
+    48 x 48 x ~12 cells, hundreds of particles per cell, so the lanes of a warp share cells and cache lines"""
+    rng = np.random.default_rng(seed)
+    return dict(x=rng.uniform(-32, -28, n), y=rng.uniform(38, 42, n), z=rng.uniform(5, 200, n), t=np.zeros(n))
+
+
 def c3_field(nx=1442, ny=1021, nt=3, seed=2, nz=1):
     """config 3: curvilinear C-grid of ORCA025 shape (ny, nx) = (1021, 1442): rotated-pole mesh with a
     tanh-stretched latitude, f32 node coordinates (NEMO style), NEMO staggering (offsets X=1, Y=1); 2-D, or with nz > 1
@@ -224,6 +231,10 @@ WORKLOADS = {
                nsteps=144, kernels=["AdvectionRK4_3D"], bytes=832, device_field=True, ulp=8, roofline_note=NOTE_AGRID,
                desc="BASELINE.json north_star target -- AdvectionRK4_3D, 1e7 particles on a 1/12 deg rectilinear A-grid "
                     "4320x2160x50 T=3 f32 U,V,W (16.8 GB), f64 axes, spherical"),
+    "ns_dense": dict(field=ns_field, fkw=dict(nx=4320, ny=2160, nz=50, nt=3), particles=dense_particles, n=10_000_000, dt=600.0,
+                     nsteps=144, kernels=["AdvectionRK4_3D"], bytes=832, device_field=True, ulp=8, roofline_note=NOTE_AGRID,
+                     desc="dense release on the north-star field: 1e7 particles in a 4 deg x 4 deg x 200 m patch of the 1/12 deg "
+                          "rectilinear A-grid (hundreds of particles per cell), AdvectionRK4_3D"),
     "ns_small": dict(field=ns_field, fkw=dict(nx=480, ny=240, nz=20, nt=3), particles=c2_particles, n=200_000, dt=600.0,
                      nsteps=144, kernels=["AdvectionRK4_3D"], bytes=832, device_field=True, ulp=2,
                      desc="small functional variant of ns (480x240x20)"),
@@ -263,7 +274,7 @@ C5 = {"c5": dict(dims=dict(nx=4320, ny=2160, nz=50, nt=2), n=12_500_000), "c5_sm
 
 def config_block(name, w, n_per_gpu):
     """`config` of the JSON line: what BOTH arms run (the reference arm prints the same dict)."""
-    fbytes = {"ns": 16.8, "c2": 1.87, "c4": 1.87, "c3": 0.035, "c3_3d": 1.1, "c3_orca12": 0.21}.get(name)
+    fbytes = {"ns": 16.8, "ns_dense": 16.8, "c2": 1.87, "c4": 1.87, "c3": 0.035, "c3_3d": 1.1, "c3_orca12": 0.21}.get(name)
     return {
         "workload": f"{name}: {w['desc']}; dt={w['dt']:g} s x {w['nsteps']} dt-steps per pass",
         "kernels": w["kernels"] + ["DeleteParticle"],
@@ -760,7 +771,9 @@ def run_decomposed_bench(a, rank, local_rank, world, dist, workload="c5"):
         "value": value, "unit": "particle-steps/s", "ms_per_step": 1e3 * tot_t / steps, "steps": steps, "warmup": warmup,
         "workload": f"{workload}: BASELINE.json configs[4] -- AdvectionRK4_3D, rectilinear {dims['nx']}x{dims['ny']}x{dims['nz']} "
                     f"T={dims['nt']} f32 field DOMAIN-DECOMPOSED into {world} X-slabs (+{halo} halo columns), {n_per_gpu} "
-                    f"particles/GPU seeded in the rank's own slab, NCCL all-to-all-v migration; dt={dt:g} s x {nsteps} steps",
+                    f"particles/GPU seeded in the rank's own slab, migration "
+                    f"{'inside the advection kernel over peer memory (CUDA IPC + NVLink)' if a.mode_d_transport == 'p2p' else 'by NCCL all-to-all-v'}"
+                    f"; dt={dt:g} s x {nsteps} steps",
         "transport": st.get("transport"),
         "timed_region": "particles resident in HBM (restored from a snapshot every pass): advect kernels + migration rounds (p2p: records "
                         "stored into the new owner's inbox by the advection kernel over NVLink, one 2-value all-reduce + compact/append "
