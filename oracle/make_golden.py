@@ -482,6 +482,9 @@ ADVDIFF_CASES = {
     "em_f64_static": ("rk2_3d", "AdvectionDiffusionEM", "f8", False, 50.0, 700.0, True, 8),
     "m1_backward": ("backward", "AdvectionDiffusionM1", "f4", True, -600.0, 5400.0, True, 9),
     "em_raise": ("raise_oob", "AdvectionDiffusionEM", "f8", True, 100.0, 1500.0, False, 10),
+    # fieldset.UV with CGrid_Velocity on rectilinear C-grids (the kernels are grid-agnostic, _advectiondiffusion.py:21-117)
+    "m1_cgrid_flat": ("cgrid_rect_3d", "AdvectionDiffusionM1", "f8", True, 50.0, 550.0, True, 11),
+    "em_cgrid_sph": ("cgrid_rect_sph", "AdvectionDiffusionEM", "f4", True, 600.0, 6000.0, True, 12),
 }
 
 
@@ -500,20 +503,27 @@ def advdiff_inputs(c, kdtype, ktime, seed=5):
     return kz.astype(kdtype), km.astype(kdtype), dres
 
 
-def make_advdiff_golden():
+def make_advdiff_golden(only=None):
     """AdvectionDiffusionM1 / EM under the reference's own Kernel.execute; the Wiener increments are the reference's
-    (np.random.normal after np.random.seed): the oracle restatement draws the same stream."""
+    (np.random.normal after np.random.seed): the oracle restatement draws the same stream.
+    only: names to (re)generate, merged into the existing file (``python -m oracle.make_golden advdiff name ...``)."""
     import warnings
 
     import cases as tc
     from oracle import ref_harness as rh
 
     out = {}
+    if only:
+        with np.load(os.path.join(GOLDEN, "advdiff.npz")) as old:
+            out = {k: old[k] for k in old.files if k.split("/")[0] not in only}
     for name, (base, kern, kd, ktime, dt, runtime, delete, rseed) in ADVDIFF_CASES.items():
+        if only and name not in only:
+            continue
         c = tc.build(tc.CASES[base])
         kz, km, dres = advdiff_inputs(c, kd, ktime)
         fs = rh.build_fieldset(lon=c["lon"], lat=c["lat"], depth=c["depth"], times=c["times"], U=c["U"], V=c["V"], W=None,
-                               mesh=c["mesh"], scalars={"Kh_zonal": (kz, "linear"), "Kh_meridional": (km, "linear")})  # fmt: skip
+                               mesh=c["mesh"], interp=c.get("interp", "linear"), padding=c.get("padding", ("low", "low", "high")),
+                               scalars={"Kh_zonal": (kz, "linear"), "Kh_meridional": (km, "linear")})  # fmt: skip
         fs.add_context("dres", dres)
         z = np.abs(np.asarray(c["z"]))
         ps = rh.make_pset(fs, x=c["x"], y=c["y"], z=z, t=c["t"])
@@ -544,6 +554,10 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "scalar_curv_linear":
         sys.path.insert(0, os.path.join(ROOT, "tests"))
         make_scalar_curv_golden(methods=("linear",), out_name="scalar_eval_curv_linear.npz")
+        sys.exit(0)
+    if len(sys.argv) > 2 and sys.argv[1] == "advdiff":
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        make_advdiff_golden(only=set(sys.argv[2:]))
         sys.exit(0)
     if len(sys.argv) > 2 and sys.argv[1] == "ref_cases":
         make_ref_cases(only=set(sys.argv[2:]))

@@ -1,7 +1,8 @@
 // advdiff.cu -- AdvectionDiffusionM1 / AdvectionDiffusionEM (reference kernels/_advectiondiffusion.py:11-18,21-117)
-// inside Kernel.execute's loop (reference _core/kernel.py:174-247), one lane per particle, on rectilinear A-grids:
-// fieldset.UV with XLinear_Velocity (AGridPolicy MODE 0) and the scalar diffusivity fields Kh_zonal / Kh_meridional
-// with XLinear (MODE 3) on the same grid.
+// inside Kernel.execute's loop (reference _core/kernel.py:174-247), one lane per particle, on rectilinear grids:
+// fieldset.UV with XLinear_Velocity (AGridPolicy MODE 0) or -- the kernels are grid-agnostic in the reference -- with
+// CGrid_Velocity (CGridPolicy, cgrid.cuh), and the scalar diffusivity fields Kh_zonal / Kh_meridional with XLinear (MODE 3)
+// on the same grid.
 //
 // Per particle and loop iteration the reference evaluates, at float32 positions (particles.x + fieldset.dres is a
 // float32 array plus a weak Python float):
@@ -15,6 +16,7 @@
 #define PB_SMEM_CACHE
 #endif
 #include "agrid.cuh"
+#include "cgrid.cuh"
 
 struct AdvDiffParams {
     AdvectParams base;  // grid, UV field, particles, dt, endtime, seed, rng_call, max_iters, delete_on_error, report
@@ -42,10 +44,11 @@ __device__ __forceinline__ Val v_div_f32(const Val& a, float c) { return a.f32 ?
 __device__ __forceinline__ Val v_mul_weak(double c, const Val& a) { return a.f32 ? Val{(double)((float)c * (float)a.v), true} : Val{c * a.v, false}; }
 __device__ __forceinline__ Val v_sqrt(const Val& a) { return a.f32 ? Val{(double)sqrtf((float)a.v), true} : Val{sqrt(a.v), false}; }
 
-template <class A, class D, class DK, bool HT, bool KHT>
+// CG: fieldset.UV is a CGrid_Velocity field (its two-face cache lives in registers: no shared-memory UV block)
+template <class A, class D, class DK, bool HT, bool KHT, bool CG>
 __global__ void __launch_bounds__(PB_BLOCK_THREADS, 2) advdiff_kernel(const AdvDiffParams q) {
     const AdvectParams& p = q.base;
-    using PolUV = AGridPolicy<A, D, HT, 2, 0>;
+    using PolUV = typename std::conditional<CG, CGridPolicy<A, D, 2>, AGridPolicy<A, D, HT, 2, 0>>::type;
     using PolK = AGridPolicy<A, DK, KHT, 1, 3>;
     using SU = typename decltype(EvalCtx<A, D, 2>::cor)::S;
     using SK = typename decltype(EvalCtx<A, DK, 1>::cor)::S;
@@ -68,7 +71,7 @@ __global__ void __launch_bounds__(PB_BLOCK_THREADS, 2) advdiff_kernel(const AdvD
         PolK::init(ek, p, p.P.ei[i]);
         {   // the scalar context's corner block lives behind the UV blocks of the whole thread block
             extern __shared__ __align__(16) unsigned char pb_smem[];
-            ek.cor.sm = reinterpret_cast<SK*>(pb_smem + (size_t)2 * 16 * sizeof(SU) * PB_BLOCK) + threadIdx.x;
+            ek.cor.sm = reinterpret_cast<SK*>(pb_smem + (CG ? (size_t)0 : (size_t)2 * 16 * sizeof(SU) * PB_BLOCK)) + threadIdx.x;
         }
         int state = p.resume ? p.P.state[i] : (int)PB_EVALUATE;  // kernel.py:188
         eu.refills = 0; ek.refills = 0;
@@ -199,33 +202,36 @@ __global__ void __launch_bounds__(PB_BLOCK_THREADS, 2) advdiff_kernel(const AdvD
     }
 }
 
-template <class A, class D, class DK, bool HT, bool KHT>
+template <class A, class D, class DK, bool HT, bool KHT, bool CG>
 static cudaError_t launch1(const AdvDiffParams& q, cudaStream_t s) {
     using SU = typename decltype(EvalCtx<A, D, 2>::cor)::S;
     using SK = typename decltype(EvalCtx<A, DK, 1>::cor)::S;
-    const size_t smem = ((size_t)2 * 16 * sizeof(SU) + (size_t)16 * sizeof(SK)) * PB_BLOCK;
+    const size_t smem = ((CG ? (size_t)0 : (size_t)2 * 16 * sizeof(SU)) + (size_t)16 * sizeof(SK)) * PB_BLOCK;
     if (smem > 48 * 1024) {
-        cudaError_t ce = cudaFuncSetAttribute(advdiff_kernel<A, D, DK, HT, KHT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t ce = cudaFuncSetAttribute(advdiff_kernel<A, D, DK, HT, KHT, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (ce != cudaSuccess) return ce;
     }
-    advdiff_kernel<A, D, DK, HT, KHT><<<(unsigned)((q.base.P.n + PB_BLOCK - 1) / PB_BLOCK), PB_BLOCK, smem, s>>>(q);
+    advdiff_kernel<A, D, DK, HT, KHT, CG><<<(unsigned)((q.base.P.n + PB_BLOCK - 1) / PB_BLOCK), PB_BLOCK, smem, s>>>(q);
     return cudaGetLastError();
 }
 
-template <class A, class D, class DK>
+template <class A, class D, class DK, bool CG>
 static cudaError_t launch_t(const AdvDiffParams& q, bool ht, bool kht, cudaStream_t s) {
-    if (ht) return kht ? launch1<A, D, DK, true, true>(q, s) : launch1<A, D, DK, true, false>(q, s);
-    return launch1<A, D, DK, false, false>(q, s);  // no time axis on the grid: no field can have a time dimension
+    if (CG) {  // (CGridPolicy handles the time axis at run time: the HT instantiation only types the unused A-grid context)
+        return kht ? launch1<A, D, DK, true, true, CG>(q, s) : launch1<A, D, DK, true, false, CG>(q, s);
+    }
+    if (ht) return kht ? launch1<A, D, DK, true, true, CG>(q, s) : launch1<A, D, DK, true, false, CG>(q, s);
+    return launch1<A, D, DK, false, false, CG>(q, s);  // no time axis on the grid: no field can have a time dimension
 }
-template <class A>
+template <class A, bool CG>
 static cudaError_t launch_a(const AdvDiffParams& q, bool d64, bool k64, bool ht, bool kht, cudaStream_t s) {
-    if (d64) return k64 ? launch_t<A, double, double>(q, ht, kht, s) : launch_t<A, double, float>(q, ht, kht, s);
-    return k64 ? launch_t<A, float, double>(q, ht, kht, s) : launch_t<A, float, float>(q, ht, kht, s);
+    if (d64) return k64 ? launch_t<A, double, double, CG>(q, ht, kht, s) : launch_t<A, double, float, CG>(q, ht, kht, s);
+    return k64 ? launch_t<A, float, double, CG>(q, ht, kht, s) : launch_t<A, float, float, CG>(q, ht, kht, s);
 }
 
 // scheme 0 = M1, 1 = EM.  uv_/kh_: dtype and time dimension of U,V and of the two Kh fields.
 cudaError_t launch_advdiff(const AdvectParams& p, const FieldDev& fkz, const FieldDev& fkm, int em, double dres, double deg2m_sq,
-                           bool coord_f64, bool uv_f64, bool kh_f64, bool uv_time, bool kh_time, cudaStream_t s) {
+                           bool coord_f64, bool uv_f64, bool kh_f64, bool uv_time, bool kh_time, bool cgrid, cudaStream_t s) {
     AdvDiffParams q{};
     q.base = p;
     q.fkz = fkz; q.fkm = fkm;
@@ -235,5 +241,6 @@ cudaError_t launch_advdiff(const AdvectParams& p, const FieldDev& fkz, const Fie
     q.two_dres = 2 * dres;
     q.deg2m = p.g.deg2m;
     q.deg2m_sq = deg2m_sq;
-    return coord_f64 ? launch_a<double>(q, uv_f64, kh_f64, uv_time, kh_time, s) : launch_a<float>(q, uv_f64, kh_f64, uv_time, kh_time, s);
+    if (cgrid) return coord_f64 ? launch_a<double, true>(q, uv_f64, kh_f64, uv_time, kh_time, s) : launch_a<float, true>(q, uv_f64, kh_f64, uv_time, kh_time, s);
+    return coord_f64 ? launch_a<double, false>(q, uv_f64, kh_f64, uv_time, kh_time, s) : launch_a<float, false>(q, uv_f64, kh_f64, uv_time, kh_time, s);
 }

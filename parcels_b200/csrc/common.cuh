@@ -757,7 +757,7 @@ struct HashTableDev {
 cudaError_t build_hash_table_device(const unsigned long long* d_qbox, long long nfaces, int bucket_bits, HashTableDev& t, cudaStream_t s);
 // AdvectionDiffusionM1 (em = 0) / AdvectionDiffusionEM (em = 1) with the diffusivity fields fkz, fkm  (advdiff.cu)
 cudaError_t launch_advdiff(const AdvectParams& p, const FieldDev& fkz, const FieldDev& fkm, int em, double dres, double deg2m_sq,
-                           bool coord_f64, bool uv_f64, bool kh_f64, bool uv_time, bool kh_time, cudaStream_t s);
+                           bool coord_f64, bool uv_f64, bool kh_f64, bool uv_time, bool kh_time, bool cgrid, cudaStream_t s);
 // scalar Field.eval on a rectilinear grid, f.p[0] = the field: mode 3 XLinear, 4 XNearest, 5 CGrid_Tracer  (aslip.cu)
 cudaError_t launch_sample_scalar(const SampleParams& p, int mode, bool coord_f64, bool data_f64, bool has_time, cudaStream_t s);
 // scalar Field.eval on a curvilinear grid: mode 4 XNearest, 5 CGrid_Tracer  (cgrid.cu)

@@ -1275,8 +1275,8 @@ int32_t pb_advect_diffusion(pb_engine* e, const pb_advdiff_args* a, pb_report* r
     if (!(a->dres == a->dres) || a->dres == 0.0) return fail(PB_ERR_INVALID, "dres must be a non-zero number");
     int32_t rc = check_fields(e, 2);
     if (rc) return rc;
-    if (e->interp != PB_INTERP_XLINEAR_VELOCITY || e->g.curvilinear || e->ring || e->g.decomposed)
-        return fail(PB_ERR_INVALID, "AdvectionDiffusionM1/EM run on resident rectilinear A-grid fields with XLinear_Velocity");
+    if ((e->interp != PB_INTERP_XLINEAR_VELOCITY && e->interp != PB_INTERP_CGRID_VELOCITY) || e->g.curvilinear || e->ring || e->g.decomposed)
+        return fail(PB_ERR_INVALID, "AdvectionDiffusionM1/EM run on resident rectilinear fields with XLinear_Velocity or CGrid_Velocity");
     if (!e->have_pid) return fail(PB_ERR_STATE, "diffusion needs particle_id (RNG counter)");
     FieldDev fkz, fkm;
     if ((rc = scalar_field_desc(e, a->kh_zonal_slot, fkz))) return rc;
@@ -1299,7 +1299,8 @@ int32_t pb_advect_diffusion(pb_engine* e, const pb_advdiff_args* a, pb_report* r
     CK(cudaEventRecord(e->ev0, e->stream));
     if (e->n > 0) {
         cudaError_t ce = launch_advdiff(p, fkz, fkm, a->scheme == PB_ADVDIFF_EM, a->dres, a->deg2m_sq, e->coord_f64 != 0, e->f_f64[0] != 0,
-                                        e->f_f64[a->kh_zonal_slot] != 0, e->g.nt > 0, fkz.T > 1, e->stream);
+                                        e->f_f64[a->kh_zonal_slot] != 0, e->g.nt > 0, fkz.T > 1, e->interp == PB_INTERP_CGRID_VELOCITY,
+                                        e->stream);
         if (ce != cudaSuccess) return fail(PB_ERR_CUDA, "advdiff_kernel launch failed: %s", cudaGetErrorString(ce));
     }
     CK(cudaEventRecord(e->ev1, e->stream));

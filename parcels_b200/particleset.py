@@ -329,8 +329,8 @@ def _advdiff_params(fieldset, name):
     if kz._slot is None or km._slot is None or kz.interp_method != "linear" or km.interp_method != "linear":
         raise NotImplementedError(f"{name}: Kh_zonal / Kh_meridional must be XLinear scalar fields on the FieldSet's grid "
                                   "(FieldSet.add_field(name, data)); constant fields have no gradient -- use DiffusionUniformKh")  # fmt: skip
-    if fieldset.grid.curvilinear or fieldset.interp_method != "linear" or fieldset.time_window is not None:
-        raise NotImplementedError(f"{name} is implemented for resident rectilinear A-grid fields (XLinear_Velocity)")
+    if fieldset.grid.curvilinear or fieldset.interp_method not in ("linear", "cgrid_velocity") or fieldset.time_window is not None:
+        raise NotImplementedError(f"{name} is implemented for resident rectilinear fields (XLinear_Velocity or CGrid_Velocity)")
     if kz.data.dtype != km.data.dtype or (kz.data.shape[0] > 1) != (km.data.shape[0] > 1):
         raise NotImplementedError("Kh_zonal and Kh_meridional must share dtype and time dimension")
     if "dres" not in fieldset.context:

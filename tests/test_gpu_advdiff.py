@@ -18,7 +18,7 @@ from philox_ref import device_normals, wiener_normals
 
 pytestmark = pytest.mark.gpu
 ERR_NAME = {60: "FieldOutOfBoundError", 61: "FieldOutOfBoundSurfaceError", 70: "OutsideTimeInterval", 51: "FieldInterpolationError"}
-FLAT = {"m1_flat", "em_f64_static", "em_raise"}
+FLAT = {"m1_flat", "em_f64_static", "em_raise", "m1_cgrid_flat"}
 
 
 @pytest.mark.parametrize("name", list(ADVDIFF_CASES))
