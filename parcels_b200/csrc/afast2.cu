@@ -1,26 +1,18 @@
-// afast2.cu -- EXPERIMENT (opt-in: PB_FAST_KERNEL=2), measured SLOWER than afast.cu and kept for the record: it executes 19 %
-// fewer instructions (1716 vs 2119 per warp and dt-step on config 2) but its four written-out stages + out-of-line side path are
-// 5000 SASS instructions = 80 KB, past the 32 KB L1.5 instruction cache: `stall_no_inst` becomes the top stall (ncu,
-// profiles/README.md r02g) -- config 2 17.0 vs 16.4 ms, 1/12 deg 259 vs 205 ms, fused diffusion 396 vs 224 ms.  The lesson
-// (hot loop < 2000 instructions) shaped the later changes to afast.cu, the diffusion block and the curvilinear kernel.
+// afast2.cu -- second schedule of the headline hot path (opt-in: PB_FAST_KERNEL=2; AdvectionRK4 / AdvectionRK4_3D with
+// XLinear_Velocity on a rectilinear A-grid with FLOAT64 coordinates, FLOAT32 data and a time axis: reference
+// kernels/_advection.py:42-75, interpolators/_xinterpolators.py:78-190, _core/field.py:250-405).  Same arithmetic, operation by
+// operation, as afast.cu and the generic AGridPolicy<double, float, true, NC, 0> (bit-identical: tests/test_gpu_fast_kernel.py).
 //
-// second schedule of the headline hot path (AdvectionRK4 / AdvectionRK4_3D with XLinear_Velocity on a rectilinear
-// A-grid with FLOAT64 coordinates, FLOAT32 data and a time axis: reference kernels/_advection.py:42-75,
-// interpolators/_xinterpolators.py:78-190, _core/field.py:250-405).  Same arithmetic, operation by operation, as afast.cu and the
-// generic AGridPolicy<double, float, true, NC, 0>; what changed is where the instructions go (ncu of afast.cu on config 2,
-// profiles/README.md r02f: 2119 warp-instructions per warp and dt-step of which 763 are the reference's float64 operations,
-// 215 register-to-register moves, 99 selects, ~260 branch / reconvergence instructions; a side-path trip costs 443 instructions,
-// a quarter of them moves):
-//
-//  * The four RK4 stages are WRITTEN OUT (compile-time stage index): no loop-carried copies of the stage values, no selects on
-//    the stage number, "renew or reuse the T-lerped block" decided at compile time.
-//  * The side path (cell change, sentinel index, first node of an axis, outside the time axis) is ONE out-of-line function
-//    shared by the four sites.  Everything it reads or writes that outlives an evaluation lives in the lane's shared-memory
-//    columns (raw block, T-lerped block, cells, reciprocals and now the cell indices too), so it has no register interface
-//    with the hit path beyond its arguments: the hit path's register allocation no longer pays for it.  The kernel
-//    parameters reach it by address (`__grid_constant__`).
-//  * cos(latitude) of the unit conversion (_xinterpolators.py:182) is common.cuh's cos_np: one odd polynomial, 16 float64
-//    instructions instead of ~60 of all kinds (every A-grid kernel uses it, so the schedules stay bit-identical to each other).
+// History (profiles/README.md r02g): the first form wrote all FOUR stages out (compile-time stage index) with the side path out of
+// line: 19 % fewer instructions than afast.cu (1716 vs 2119 per warp and dt-step on config 2) -- and 4 % to 77 % SLOWER, because
+// 5000 SASS instructions = 80 KB no longer fit the 32 KB L1.5 instruction cache (`stall_no_inst` on top).  This form keeps what
+// the experiment showed to be cheap and fits the cache:
+//  * the loop body is TWO stages -- a reusing (even) and a renewing (odd) one, "renew or reuse the T-lerped block" decided at
+//    compile time -- and runs twice per step: half the loop-carried copies of afast.cu's four-trip loop, ~1300 hot instructions;
+//  * the side path (cell change, sentinel index, first node of an axis, outside the time axis) is ONE out-of-line function shared
+//    by both sites.  Everything it reads or writes that outlives an evaluation lives in the lane's shared-memory columns (raw
+//    block, T-lerped block, cells, reciprocals, cell indices), so it has no register interface with the hit path beyond its
+//    arguments.  The kernel parameters reach it by address (`__grid_constant__`).
 #include "afast.cuh"
 
 struct SideResult {
@@ -230,13 +222,13 @@ struct AFast2Policy {
         return w00 * r[0] + w01 * r[1] + w10 * r[2] + w11 * r[3];
     }
 
-    // One VectorField.eval (field.py:250-304) at RK4 stage K's position (K is a compile-time constant: the four call sites of the
-    // kernel skeleton are four straight-line copies of the hit path)
-    template <int K>
-    __device__ static __forceinline__ void eval_fast(const AdvectParams& p, Ctx& e, const double ts, const double zs, const double ys,
-                                                     const double xs, double& u, double& v, double& w) {
+    // One VectorField.eval (field.py:250-304) at an RK4 stage position.  RENEW is a compile-time constant: the kernel skeleton's
+    // loop body holds two copies of the hit path -- a reusing (even) and a renewing (odd) stage -- and runs twice per step
+    template <bool RENEW>
+    __device__ static __forceinline__ void eval_fast(const AdvectParams& p, Ctx& e, const bool first, const double ts, const double zs,
+                                                     const double ys, const double xs, double& u, double& v, double& w) {
         const GridDev& g = p.g;
-        constexpr bool renew = (K & 1) != 0;  // odd stages sample a new time: the T-lerped block is renewed; even stages reuse it
+        constexpr bool renew = RENEW;  // odd stages sample a new time: the T-lerped block is renewed; even stages reuse it
         float4* const raw = e.raw;
         bool lerp_now = renew;
         double2 bz, by, bx, bt;  // {lo, hi} of the current cells
@@ -253,7 +245,7 @@ struct AFast2Policy {
             hit = hit && (renew ? (ts > bt.x && ts <= bt.y) : (ts == e.lerp_t));
             if (hit || trip) break;
             SideResult r;
-            side_path(&p, raw, K, ts, zs, ys, xs, e.state, &r);
+            side_path(&p, raw, first ? 0 : 1, ts, zs, ys, xs, e.state, &r);
             e.state = r.state;
             if (r.flags & SIDE_OUT_OF_TIME) e.out_of_time = true;
             if (r.flags & SIDE_SEARCHED) e.searched = true;
@@ -312,7 +304,7 @@ struct AFast2Policy {
             }
         }
         u = q[0]; v = q[1]; w = NC == 3 ? q[2] : 0.0;
-        if (g.spherical) spherical(g, K == 0, ys, u, v);
+        if (g.spherical) spherical(g, first, ys, u, v);
         if (u != u || v != v || w != w) e.state = max(e.state, (int)PB_ERROR_INTERPOLATION);  // field.py:288-290
     }
 

@@ -402,22 +402,28 @@ __global__ void PB_KERNEL_BOUNDS advect_kernel(const __grid_constant__ AdvectPar
             // constant-field evals of the previous step: curvilinear hints are all zero again
             const bool nohint1 = (it == 0 && p.hint_all_zero) || (it > 0 && DIFF && p.diffusion);
             if constexpr (fast_unrolled_v<Policy>) {
-                // afast2.cu: the same four evaluations as below written out, stage index at compile time (no loop-carried copies of
-                // the stage values, no selects on the stage number); operation for operation the arithmetic of the loop form
+                // afast2.cu: a two-stage loop body (an even stage that reuses the T-lerped block, an odd one that renews it), run
+                // twice per step; operation for operation the arithmetic of the four-trip loop below
+                su = sv = sw = 0.0;
                 uk = Val{0.0, false}; vk = uk; wk = uk;
                 const double xd = (double)x, yd = (double)y, zd = (double)z;
                 const double th = t + 0.5 * dtp;
-                Policy::template eval_fast<0>(p, e, t, zd, yd, xd, uk.v, vk.v, wk.v);
-                su = uk.v; sv = vk.v; sw = wk.v;
-                double xs = xd + (uk.v * 0.5) * dtp, ys = yd + (vk.v * 0.5) * dtp, zs = three_d ? zd + (wk.v * 0.5) * dtp : zd;
-                Policy::template eval_fast<1>(p, e, th, zs, ys, xs, uk.v, vk.v, wk.v);
-                su = su + 2.0 * uk.v; sv = sv + 2.0 * vk.v; sw = sw + 2.0 * wk.v;
-                xs = xd + (uk.v * 0.5) * dtp; ys = yd + (vk.v * 0.5) * dtp; zs = three_d ? zd + (wk.v * 0.5) * dtp : zd;
-                Policy::template eval_fast<2>(p, e, th, zs, ys, xs, uk.v, vk.v, wk.v);
-                su = su + 2.0 * uk.v; sv = sv + 2.0 * vk.v; sw = sw + 2.0 * wk.v;
-                xs = xd + uk.v * dtp; ys = yd + vk.v * dtp; zs = three_d ? zd + wk.v * dtp : zd;
-                Policy::template eval_fast<3>(p, e, t + dtp, zs, ys, xs, uk.v, vk.v, wk.v);
-                su = su + 1.0 * uk.v; sv = sv + 1.0 * vk.v; sw = sw + 1.0 * wk.v;
+#pragma unroll 1
+                for (int j = 0; j < 2; ++j) {
+                    const bool first = (j == 0);
+                    // stage 1 (the particle's own position and time) or stage 3 (half a step with stage 2's velocities)
+                    double xs = first ? xd : xd + (uk.v * 0.5) * dtp, ys = first ? yd : yd + (vk.v * 0.5) * dtp;
+                    double zs = (first || !three_d) ? zd : zd + (wk.v * 0.5) * dtp;
+                    Policy::template eval_fast<false>(p, e, first, first ? t : th, zs, ys, xs, uk.v, vk.v, wk.v);
+                    if (first) { su = uk.v; sv = vk.v; sw = wk.v; }
+                    else { su = su + 2.0 * uk.v; sv = sv + 2.0 * vk.v; sw = sw + 2.0 * wk.v; }
+                    // stage 2 (half a step with stage 1's velocities) or stage 4 (a full step with stage 3's)
+                    xs = xd + (first ? uk.v * 0.5 : uk.v) * dtp; ys = yd + (first ? vk.v * 0.5 : vk.v) * dtp;
+                    zs = three_d ? zd + (first ? wk.v * 0.5 : wk.v) * dtp : zd;
+                    Policy::template eval_fast<true>(p, e, false, first ? th : t + dtp, zs, ys, xs, uk.v, vk.v, wk.v);
+                    const double m = first ? 2.0 : 1.0;  // u1 + 2*u2 + 2*u3 + u4
+                    su = su + m * uk.v; sv = sv + m * vk.v; sw = sw + m * wk.v;
+                }
             } else if constexpr (Policy::FAST_RK4) {
                 // afast.cu: float64 grid, float32 data -- every stage value is float64 (Val::f32 never set), one eval site,
                 // odd stages renew the T-lerped block, even stages reuse it (stages 2/3 and 4/next-1 share their sample time)
