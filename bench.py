@@ -697,8 +697,10 @@ def run_decomposed_bench(a, rank, local_rank, world, dist, workload="c5"):
     fs = pb.FieldSet.from_arrays(lon=f["lon"][f["lo"] : f["hi"] + 1].copy(), lat=f["lat"], depth=f["depth"], time=f["times"],
                                  U=f["U"], V=f["V"], W=f["W"], mesh="spherical", xdim=f["lon"].size - 1)  # fmt: skip
     dfs = D.DecomposedFieldSet.from_slab(fs, f["plan"], rank=rank, world=world, device=local_rank)
+    p2p_error = ""
     if a.mode_d_transport == "p2p":  # in-kernel migration over peer memory: the advection kernel delivers the leavers itself
-        D.connect_p2p(dfs, dist, max(n_per_gpu // 8, 4096))
+        if not D.connect_p2p(dfs, dist, max(n_per_gpu // 8, 4096)):
+            p2p_error = dfs.p2p_error  # every rank agreed to stay on the collectives
     rng = np.random.default_rng(100 + rank)
     b = f["plan"]["bounds"]
     # every rank seeds its particles inside its own slab (as a domain-decomposed application would); whatever
@@ -774,7 +776,7 @@ def run_decomposed_bench(a, rank, local_rank, world, dist, workload="c5"):
                     f"particles/GPU seeded in the rank's own slab, migration "
                     f"{'inside the advection kernel over peer memory (CUDA IPC + NVLink)' if a.mode_d_transport == 'p2p' else 'by NCCL all-to-all-v'}"
                     f"; dt={dt:g} s x {nsteps} steps",
-        "transport": st.get("transport"),
+        "transport": st.get("transport"), **({"p2p_unavailable": p2p_error} if p2p_error else {}),
         "timed_region": "particles resident in HBM (restored from a snapshot every pass): advect kernels + migration rounds (p2p: records "
                         "stored into the new owner's inbox by the advection kernel over NVLink, one 2-value all-reduce + compact/append "
                         "per round; collective: classify / count all-gather / pack / all-to-all-v / unpack), wall clock between "
@@ -912,10 +914,13 @@ def main():
     mode_d = None
     if world > 1 and not a.no_mode_d:
         torch.cuda.empty_cache()
-        mode_d = run_decomposed_bench(a, rank, local_rank, world, dist, "c5" if name == "ns" else "c5_small")
-        chk = decomposed_bitexact_check(rank, local_rank, world, dist, transport=a.mode_d_transport)
-        if mode_d is not None:
-            mode_d["bitexact_check"] = chk
+        try:  # (the mode R line above is printed whatever happens in here)
+            mode_d = run_decomposed_bench(a, rank, local_rank, world, dist, "c5" if name == "ns" else "c5_small")
+            chk = decomposed_bitexact_check(rank, local_rank, world, dist, transport=a.mode_d_transport)
+            if mode_d is not None:
+                mode_d["bitexact_check"] = chk
+        except Exception as ex:  # noqa: BLE001 -- reported in the line
+            mode_d = {"error": f"{type(ex).__name__}: {ex}"[:400]} if rank == 0 else None
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

@@ -384,6 +384,8 @@ int32_t pb_migrate_unpack(pb_engine* e, const void* recvbuf_dev, int64_t n_in);
 int32_t pb_migrate_p2p_init(pb_engine* e, int64_t capacity_records, uint8_t* ipc_handle /* [64] or NULL */, uint64_t* local_base /* or NULL */);
 int32_t pb_migrate_p2p_connect(pb_engine* e, const uint8_t* ipc_handles, const uint64_t* local_bases);
 int32_t pb_migrate_p2p_finish(pb_engine* e, int64_t* n_arrived, int64_t* n_resident);
+/* back to the collective transport (a peer could not be mapped): pb_advect stops delivering by itself; the inbox stays allocated */
+int32_t pb_migrate_p2p_disable(pb_engine* e);
 #define PB_MIGRATION_RECORD_BYTES 48
 /* particle ids in device order (after migrations the order on a rank is arbitrary) */
 int32_t pb_particles_download_ids(pb_engine* e, int64_t n, int64_t* particle_id);

@@ -155,6 +155,7 @@ SYMBOLS = {
     "pb_migrate_p2p_init": (C.c_int32, [_P, C.c_int64, _P, _P]),
     "pb_migrate_p2p_connect": (C.c_int32, [_P, _P, _P]),
     "pb_migrate_p2p_finish": (C.c_int32, [_P, _P, _P]),
+    "pb_migrate_p2p_disable": (C.c_int32, [_P]),
     "pb_particles_download_ids": (C.c_int32, [_P, C.c_int64, _P]),
     "pb_flag_view_outside_time": (C.c_int32, [_P, C.c_double, C.c_double]),
     "pb_delete_view_outside_time": (C.c_int32, [_P, C.c_double, C.c_double]),

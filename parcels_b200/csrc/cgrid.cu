@@ -27,7 +27,9 @@ template <class Policy>
 static cudaError_t launch_policy(const AdvectParams& p, cudaStream_t s) {
     const int block = 128;
     const long long grid = (p.P.n + block - 1) / block;
-    advect_kernel<Policy><<<(unsigned)grid, block, 0, s>>>(p);
+    // (advection-only launches carry neither the Philox / Box-Muller code nor its registers in the time loop)
+    if (Policy::RUNTIME_DTYPE && !p.diffusion) advect_kernel<Policy, false><<<(unsigned)grid, block, 0, s>>>(p);
+    else advect_kernel<Policy><<<(unsigned)grid, block, 0, s>>>(p);
     return cudaGetLastError();
 }
 

@@ -314,6 +314,26 @@ __device__ __forceinline__ void hash_query(const GridDev& g, CGridCtx<A, D>& e, 
     }
 }
 
+// The same query OUT OF LINE for the advection kernels (a hash query happens 0.03 times per warp and dt-step on config 3, but its
+// ~350 instructions -- with their own copy of the point-in-cell test -- sat in the middle of the time loop: ncu `stall_no_inst`).
+// It works on a private cell cache (by-value interface: the caller's context stays in registers) and returns in registers; the
+// caller's cache then reloads the found cell once.
+struct HashHit {
+    double xsi, eta;
+    int yi, xi;
+};
+template <class A, class D>
+static __device__ __noinline__ HashHit hash_query_cold(const GridDev* gp, double qx_, double qy_, double ux, double uy, double uz, int finite,
+                                                       unsigned int qx, unsigned int qy, unsigned int qz) {
+    CGridCtx<A, D> e;
+    e.kyi = e.kxi = INT_MIN;
+    Query q;
+    q.x = qx_; q.y = qy_; q.qu_x = ux; q.qu_y = uy; q.qu_z = uz;
+    HashHit r;
+    hash_query(*gp, e, q, finite != 0, qx, qy, qz, r.yi, r.xi, r.xsi, r.eta);
+    return r;
+}
+
 // ------------------------------------------------------------------------------------------------
 // CGrid_Velocity arithmetic (typed like NumPy: A corner coords, C face values, TY/TX bcoords)
 // ------------------------------------------------------------------------------------------------
@@ -651,6 +671,7 @@ struct CurvPolicy {
         // -- _search_indices_curvilinear_2d (index_search.py:242-295): hint, (neighbours,) spatial hash
         Query q;
         q.x = x; q.y = y;
+        q.qu_x = q.qu_y = q.qu_z = 0.0;
         double cos_lat = 1.0;  // cos(deg2rad(y)) in float64: also the spherical conversion factor of a float64 position
         if (SPH) {
             const double la = deg2rad_np(y), lo = deg2rad_np(x);
@@ -712,7 +733,11 @@ struct CurvPolicy {
                     }
                 }
             }
-            if (!nb) hash_query(g, e, q, xy_f32 ? isfinite((float)x) && isfinite((float)y) : isfinite(x) && isfinite(y), qx, qy, qz, yi, xi, xsi, eta);
+            if (!nb) {
+                const HashHit hh = hash_query_cold<A, D>(&p.g, q.x, q.y, q.qu_x, q.qu_y, q.qu_z,
+                                                         xy_f32 ? isfinite((float)x) && isfinite((float)y) : isfinite(x) && isfinite(y), qx, qy, qz);
+                yi = hh.yi; xi = hh.xi; xsi = hh.xsi; eta = hh.eta;
+            }
         }
         e.yi = yi; e.xi = xi;
         long long r = (long long)yi * g.xdim + (long long)xi;

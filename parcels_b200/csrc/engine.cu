@@ -1613,6 +1613,12 @@ int32_t pb_migrate_p2p_connect(pb_engine* e, const uint8_t* ipc_handles, const u
     return PB_OK;
 }
 
+int32_t pb_migrate_p2p_disable(pb_engine* e) {
+    if (!e) return fail(PB_ERR_INVALID, "engine is NULL");
+    e->mig_on = false;
+    return PB_OK;
+}
+
 int32_t pb_migrate_p2p_finish(pb_engine* e, int64_t* n_in_out, int64_t* n_now) {
     PB_RANGE("pb_migrate_p2p_finish");
     if (!e) return fail(PB_ERR_INVALID, "engine is NULL");

@@ -198,15 +198,35 @@ def _exchange(eng, counts, dist, device):
     return total, n_in
 
 
-def connect_p2p(dfs: DecomposedFieldSet, dist, capacity_records: int):
+def connect_p2p(dfs: DecomposedFieldSet, dist, capacity_records: int) -> bool:
     """Set up in-kernel migration over peer memory for ``dfs`` (every rank calls it): allocate the inbox, all-gather the CUDA-IPC
     handles, map the peers.  ``capacity_records``: arrivals one rank can take per round (a full inbox only delays the overflow by
-    a round).  From here on ``run_decomposed_resident`` uses the peer-memory rounds."""
-    handle, _ = dfs.engine.migrate_p2p_init(capacity_records)
+    a round).  Returns True when EVERY rank is connected -- from then on ``run_decomposed_resident`` uses the peer-memory rounds;
+    if any rank could not allocate or map (no peer access between two devices, IPC disabled in a container ...) all ranks agree
+    to stay on the collective transport and the reason is kept in ``dfs.p2p_error``."""
+    from ._lib import EngineError
+
+    err, handle = "", b""
+    try:
+        handle, _ = dfs.engine.migrate_p2p_init(capacity_records)
+    except EngineError as e:
+        err = str(e)
     everyone = [None] * dist.get_world_size()
-    dist.all_gather_object(everyone, handle)
-    dfs.engine.migrate_p2p_connect(handles=everyone)
-    dfs.p2p = True
+    dist.all_gather_object(everyone, (handle, err))
+    errors = [e for _, e in everyone if e]
+    if not errors:
+        try:
+            dfs.engine.migrate_p2p_connect(handles=[h for h, _ in everyone])
+        except EngineError as e:
+            err = str(e)
+    flags = [None] * dist.get_world_size()
+    dist.all_gather_object(flags, err)
+    errors += [e for e in flags if e]
+    dfs.p2p = not errors
+    dfs.p2p_error = errors[0] if errors else ""
+    if errors:
+        dfs.engine.p2p_disable()
+    return dfs.p2p
 
 
 def _advect_args(eng, plan, dt, endtime, first, seed, rng_call, rounds):

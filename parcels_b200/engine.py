@@ -341,6 +341,11 @@ class Engine:
         check(self._lib.pb_migrate_p2p_connect(self._h, ptr(h), ptr(b)))
         self.p2p = True
 
+    def p2p_disable(self):
+        """Leave the peer-memory transport (some rank could not connect): the kernels stop delivering by themselves."""
+        check(self._lib.pb_migrate_p2p_disable(self._h))
+        self.p2p = False
+
     def migrate_p2p_finish(self):
         """After the barrier of a round: drop what left, append what arrived.  Returns (arrivals, resident count)."""
         out = np.zeros(2, dtype=np.int64)
