@@ -734,9 +734,13 @@ struct CurvPolicy {
                 }
             }
             if (!nb) {
+#ifdef PB_HASH_INLINE  // (tuning build: the query inlined into the time loop, as before round 2's r02l)
+                hash_query(g, e, q, xy_f32 ? isfinite((float)x) && isfinite((float)y) : isfinite(x) && isfinite(y), qx, qy, qz, yi, xi, xsi, eta);
+#else
                 const HashHit hh = hash_query_cold<A, D>(&p.g, q.x, q.y, q.qu_x, q.qu_y, q.qu_z,
                                                          xy_f32 ? isfinite((float)x) && isfinite((float)y) : isfinite(x) && isfinite(y), qx, qy, qz);
                 yi = hh.yi; xi = hh.xi; xsi = hh.xsi; eta = hh.eta;
+#endif
             }
         }
         e.yi = yi; e.xi = xi;

@@ -12,6 +12,15 @@ for w in c2 ns c4; do
     python scripts/bench_summary.py --brief "v$v $w" $out/${tag}_v${v}_$w.json
   done
 done
+for v in default cginl cg4 default cginl; do
+  lib=parcels_b200/lib/libparcels_b200_$v.so; [ $v = default ] && lib=parcels_b200/lib/libparcels_b200.so
+  PB_LIB=$PWD/$lib python bench.py --workload c3 --steps 4 --warmup 3 --no-cpu-baseline --no-e2e --extras "" > $out/${tag}_c3_$v.json 2>> $out/${tag}_sweep.err
+  python scripts/bench_summary.py --brief "c3 $v" $out/${tag}_c3_$v.json
+done
+PB_LIB=$PWD/parcels_b200/lib/libparcels_b200_cginl.so python bench.py --workload c3_3d --steps 4 --warmup 3 --no-cpu-baseline --no-e2e --extras "" > $out/${tag}_c3_3d_cginl.json 2>> $out/${tag}_sweep.err
+python scripts/bench_summary.py --brief "c3_3d cginl" $out/${tag}_c3_3d_cginl.json
+python bench.py --workload c3_3d --steps 4 --warmup 3 --no-cpu-baseline --no-e2e --extras "" > $out/${tag}_c3_3d_default.json 2>> $out/${tag}_sweep.err
+python scripts/bench_summary.py --brief "c3_3d default" $out/${tag}_c3_3d_default.json
 PB_FAST_KERNEL=2 timeout 600 ncu --set full --clock-control none --import-source on -k regex:advect_kernel -s 3 -c 1 -o $out/${tag}_advect_v2_c2 -f \
     python bench.py --workload c2 --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --extras "" > $out/${tag}_ncu_c2.log 2>&1
 python scripts/ncu_summary.py $out/${tag}_advect_v2_c2.ncu-rep > $out/${tag}_ncu_summary_v2_c2.txt 2>&1
