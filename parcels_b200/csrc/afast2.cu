@@ -119,8 +119,12 @@ struct AFast2Policy {
     // ---------------- side path: searches, states, refill; special samples are finished here ----------------
     // Out of line, one copy for the four stages.  Reads and rewrites the lane's cells / reciprocals / indices / raw block in shared
     // memory; what the caller has in registers comes in as arguments and goes back through `out`.
-    __device__ static __noinline__ void side_path(const AdvectParams* pp, float4* raw, int k, double ts, double zs, double ys, double xs,
-                                                  int state, SideResult* out) {
+#ifdef PB_SIDE_INLINE  // (tuning build: two inline copies of the side path, one per evaluation site of the loop body)
+    __device__ static __forceinline__
+#else
+    __device__ static __noinline__
+#endif
+    void side_path(const AdvectParams* pp, float4* raw, int k, double ts, double zs, double ys, double xs, int state, SideResult* out) {
         const GridDev& g = pp->g;
         const FieldDev& f = pp->f;
         int flags = 0;

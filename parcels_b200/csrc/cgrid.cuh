@@ -314,10 +314,9 @@ __device__ __forceinline__ void hash_query(const GridDev& g, CGridCtx<A, D>& e, 
     }
 }
 
-// The same query OUT OF LINE for the advection kernels (a hash query happens 0.03 times per warp and dt-step on config 3, but its
-// ~350 instructions -- with their own copy of the point-in-cell test -- sat in the middle of the time loop: ncu `stall_no_inst`).
-// It works on a private cell cache (by-value interface: the caller's context stays in registers) and returns in registers; the
-// caller's cache then reloads the found cell once.
+// The same query OUT OF LINE (tuning build -DPB_HASH_COLD; an experiment that lost: a hash query happens 0.03 times per warp and
+// dt-step on config 3 and its ~350 instructions sit in the middle of the time loop, but calling it costs spills of the caller's
+// live registers -- 188.7 vs 160.8 ms).  It works on a private cell cache (by-value interface) and returns in registers.
 struct HashHit {
     double xsi, eta;
     int yi, xi;
@@ -734,7 +733,8 @@ struct CurvPolicy {
                 }
             }
             if (!nb) {
-#ifdef PB_HASH_INLINE  // (tuning build: the query inlined into the time loop, as before round 2's r02l)
+#ifndef PB_HASH_COLD  // measured (profiles/README.md r02l): the query inlined in the time loop 160.8 ms on config 3, out of line
+                      // (hash_query_cold: registers spilled around the call) 188.7 ms -- inline is the build
                 hash_query(g, e, q, xy_f32 ? isfinite((float)x) && isfinite((float)y) : isfinite(x) && isfinite(y), qx, qy, qz, yi, xi, xsi, eta);
 #else
                 const HashHit hh = hash_query_cold<A, D>(&p.g, q.x, q.y, q.qu_x, q.qu_y, q.qu_z,
