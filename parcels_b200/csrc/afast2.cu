@@ -1,18 +1,20 @@
-// afast2.cu -- second schedule of the headline hot path (opt-in: PB_FAST_KERNEL=2; AdvectionRK4 / AdvectionRK4_3D with
-// XLinear_Velocity on a rectilinear A-grid with FLOAT64 coordinates, FLOAT32 data and a time axis: reference
+// afast2.cu -- the headline hot path as a TWO-STAGE loop body (the default kernel of advection-only lists; AdvectionRK4 /
+// AdvectionRK4_3D with XLinear_Velocity on a rectilinear A-grid with FLOAT64 coordinates, FLOAT32 data and a time axis: reference
 // kernels/_advection.py:42-75, interpolators/_xinterpolators.py:78-190, _core/field.py:250-405).  Same arithmetic, operation by
 // operation, as afast.cu and the generic AGridPolicy<double, float, true, NC, 0> (bit-identical: tests/test_gpu_fast_kernel.py).
 //
-// History (profiles/README.md r02g): the first form wrote all FOUR stages out (compile-time stage index) with the side path out of
-// line: 19 % fewer instructions than afast.cu (1716 vs 2119 per warp and dt-step on config 2) -- and 4 % to 77 % SLOWER, because
-// 5000 SASS instructions = 80 KB no longer fit the 32 KB L1.5 instruction cache (`stall_no_inst` on top).  This form keeps what
-// the experiment showed to be cheap and fits the cache:
-//  * the loop body is TWO stages -- a reusing (even) and a renewing (odd) one, "renew or reuse the T-lerped block" decided at
-//    compile time -- and runs twice per step: half the loop-carried copies of afast.cu's four-trip loop, ~1300 hot instructions;
-//  * the side path (cell change, sentinel index, first node of an axis, outside the time axis) is ONE out-of-line function shared
-//    by both sites.  Everything it reads or writes that outlives an evaluation lives in the lane's shared-memory columns (raw
-//    block, T-lerped block, cells, reciprocals, cell indices), so it has no register interface with the hit path beyond its
-//    arguments.  The kernel parameters reach it by address (`__grid_constant__`).
+// How it got here (profiles/README.md r02g, r02l, r02m; config 2 / 1/12 deg workload, afast.cu = 15.8 / 198 ms):
+//   1. all FOUR stages written out, side path out of line: 19 % fewer instructions, 17.0 / 259 ms -- 5000 SASS instructions = 80 KB
+//      do not fit the 32 KB L1.5 instruction cache (`stall_no_inst` on top);
+//   2. a TWO-stage body (a reusing + a renewing stage, run twice per step), side path out of line: 15.3 / 208 ms -- the cache is
+//      fine, but every call of the side path spills and reloads the hit path's live registers (1.5 trips per warp-step at 1/12 deg);
+//   3. the two-stage body with the side path INLINE at both sites: **14.2 / 180 ms** (+11 %, +10 %).  With the fused diffusion block
+//      also inline the body overflows the cache again (318 vs 212 ms), so the diffusion increment is one out-of-line call per step
+//      (common.cuh diffusion_increment: few values are live there).
+// What the two-stage body buys: "renew or reuse the T-lerped block" is decided at compile time, half the loop-carried copies of
+// afast.cu's four-trip loop, 2217 instead of 2563 instructions per warp and dt-step at 1/12 deg.  Everything the side path reads
+// or writes that outlives an evaluation lives in the lane's shared-memory columns (raw block, T-lerped block, cells, reciprocals,
+// cell indices: 496 B per lane).
 #include "afast.cuh"
 
 struct SideResult {
@@ -119,7 +121,8 @@ struct AFast2Policy {
     // ---------------- side path: searches, states, refill; special samples are finished here ----------------
     // Out of line, one copy for the four stages.  Reads and rewrites the lane's cells / reciprocals / indices / raw block in shared
     // memory; what the caller has in registers comes in as arguments and goes back through `out`.
-#ifdef PB_SIDE_INLINE  // (tuning build: two inline copies of the side path, one per evaluation site of the loop body)
+#ifndef PB_SIDE_COLD  // measured (profiles/README.md r02l / r02m): two INLINE copies of the side path, one per evaluation site of
+                      // the loop body, 180 ms on the 1/12 deg workload; out of line (the call spills the hit path's registers) 208 ms
     __device__ static __forceinline__
 #else
     __device__ static __noinline__

@@ -940,16 +940,22 @@ int32_t pb_sample_scalar(pb_engine* e, int32_t slot, int32_t method, int64_t n, 
 
 // The specialised RK4 kernel (afast.cu) gathers from a node-interleaved {u, v, w, 0} copy of the float32 fields: built here, on
 // the device, the first time an RK4 launch can use it (float64 rectilinear grid, XLinear_Velocity, every level resident).
+#ifndef PB_FAST_DEFAULT_DIFFUSION
+#define PB_FAST_DEFAULT_DIFFUSION 1  // (the kernel of DiffusionUniformKh lists until afast2's out-of-line increment is measured)
+#endif
 static bool fast_kernel_enabled() {
     const char* v = getenv("PB_DISABLE_FAST_KERNEL");  // A/B switch of the parity tests and variant sweeps
     return !(v && v[0] == '1');
 }
-// which specialised RK4 kernel: 1 (default) = afast.cu (one evaluation site in a stage loop); 2 = afast2.cu (stages written out,
-// side path out of line) -- an experiment kept selectable: 19 % fewer instructions, but its hot loop no longer fits the 32 KB
-// L1.5 instruction cache and it measured 4 % (config 2) to 27 % (1/12 deg) SLOWER (profiles/README.md r02g)
-static int fast_kernel_version() {
+// which specialised RK4 kernel: 2 = afast2.cu (a two-stage loop body with compile-time renew / reuse, both side-path copies
+// inline), 1 = afast.cu (one evaluation site in a four-trip loop).  Measured (profiles/README.md r02m): advection only 14.2 vs
+// 15.8 ms on config 2 and 180 vs 198 ms on the 1/12 deg workload for afast2; with the fused diffusion block inline the two-stage body
+// overflows the instruction cache (318 vs 212 ms), so afast2 calls the diffusion increment out of line.  PB_FAST_KERNEL=1|2 forces one.
+static int fast_kernel_version(bool diffusion) {
     const char* v = getenv("PB_FAST_KERNEL");
-    return (v && v[0] == '2') ? 2 : 1;
+    if (v && v[0] == '1') return 1;
+    if (v && v[0] == '2') return 2;
+    return diffusion ? PB_FAST_DEFAULT_DIFFUSION : 2;
 }
 static int32_t ensure_interleaved(pb_engine* e, int scheme) {
     if (e->il_valid) return PB_OK;
@@ -1013,7 +1019,7 @@ static cudaError_t launch_advect_kernel(pb_engine* e, const AdvectParams& p, int
     const int alt = agrid_alt_mode(e->interp);
     if (e->interp == PB_INTERP_XLINEAR_VELOCITY && fast_kernel_enabled() &&
         agrid_fast_applies(p, e->coord_f64 != 0, e->f_f64[0] != 0, e->g.nt > 0, nc)) {
-        e->last_variant = fast_kernel_version();
+        e->last_variant = fast_kernel_version(p.diffusion != 0);
         return e->last_variant == 2 ? launch_agrid_fast2(p, nc, stream) : launch_agrid_fast(p, nc, stream);
     }
     e->last_variant = 0;

@@ -79,7 +79,8 @@ def _case(seed):
 
 
 def _run(c, fast: int):
-    """fast: 0 = the generic kernel, 1 = afast.cu (stage loop; the library default), 2 = afast2.cu (stages written out)"""
+    """fast: 0 = the generic kernel, 1 = afast.cu (four-trip stage loop), 2 = afast2.cu (two-stage loop body; the library default
+    for advection-only lists)"""
     os.environ["PB_DISABLE_FAST_KERNEL"] = "0" if fast else "1"
     os.environ["PB_FAST_KERNEL"] = str(fast or 1)
     try:
@@ -137,7 +138,7 @@ def test_fast_kernel_is_the_one_that_runs_and_refills_less_often_than_it_samples
     ps = pb.ParticleSet(fs, x=rng.uniform(5e3, 3.5e4, n), y=rng.uniform(-5e3, 2e4, n), z=rng.uniform(10, 700, n), t=np.zeros(n))
     ps.execute([pb.AdvectionRK4_3D, pb.DeleteParticle], dt=60.0, runtime=3600.0)
     rep = ps.last_report
-    assert rep["kernel_variant"] == 1
+    assert rep["kernel_variant"] == 2
     assert rep["particle_steps"] == n * 60
     assert 0 < rep["cache_refills"] < rep["particle_steps"] // 4
 
