@@ -9,8 +9,8 @@
 //   2. a TWO-stage body (a reusing + a renewing stage, run twice per step), side path out of line: 15.3 / 208 ms -- the cache is
 //      fine, but every call of the side path spills and reloads the hit path's live registers (1.5 trips per warp-step at 1/12 deg);
 //   3. the two-stage body with the side path INLINE at both sites: **14.2 / 180 ms** (+11 %, +10 %).  With the fused diffusion block
-//      also inline the body overflows the cache again (318 vs 212 ms), so the diffusion increment is one out-of-line call per step
-//      (common.cuh diffusion_increment: few values are live there).
+//      in the body it overflows the cache again (318 ms inline, 342 ms with the increment out of line, afast.cu 212 ms): lists
+//      with DiffusionUniformKh stay on afast.cu.  128 threads x 3 blocks per SM (r02n: 13.9 / 176.8 ms; 384 x 1: 14.2 / 179.8).
 // What the two-stage body buys: "renew or reuse the T-lerped block" is decided at compile time, half the loop-carried copies of
 // afast.cu's four-trip loop, 2217 instead of 2563 instructions per warp and dt-step at 1/12 deg.  Everything the side path reads
 // or writes that outlives an evaluation lives in the lane's shared-memory columns (raw block, T-lerped block, cells, reciprocals,

@@ -320,30 +320,6 @@ __device__ __forceinline__ double half_of(const Val& a) { return a.f32 ? (double
 #endif
 // DIFF = false compiles the kernel without the DiffusionUniformKh block (the specialised RK4 kernel is instantiated both ways:
 // the advection-only hot path carries neither the Philox / Box-Muller code nor its loop-invariant registers)
-// DiffusionUniformKh's displacement of one step (kernels/_advectiondiffusion.py:120-153), the same operations as the inline block
-// of advect_kernel, out of line for the kernels whose time loop has no instruction-cache room for it: bx * dWx, by * dWy
-struct DiffusionIncrement {
-    double x, y;
-};
-static __device__ __noinline__ DiffusionIncrement diffusion_increment(const AdvectParams* pp, long long it, long long i, float y, double dtp,
-                                                                      double diff_sq, double diff_by) {
-    const AdvectParams& p = *pp;
-    double zx, zy;
-    wiener_normals(p.seed, p.rng_call, it, p.P.pid[i], zx, zy);
-    const double sq = dtp == p.dt ? diff_sq : sqrt(fabs(dtp));
-    const double dWx = zx * sq, dWy = zy * sq;
-    double khz = p.kh_zonal;
-    if (p.kh_spherical) {
-        const float ang = (y * (float)3.14159265358979323846) / 180.0f;  // lat * np.pi / 180 in f32
-        const float m = (float)p.kh_deg2m * cosf(ang);
-        khz = khz / (double)(m * m);
-    }
-    DiffusionIncrement r;
-    r.x = sqrt(2 * khz) * dWx;
-    r.y = diff_by * dWy;
-    return r;
-}
-
 // whether a policy is a FAST_RK4 one whose four stages are written out (afast2.cu)
 template <class P, class = void>
 struct FastUnrolled : std::false_type {};
@@ -565,13 +541,6 @@ __global__ void PB_KERNEL_BOUNDS advect_kernel(const __grid_constant__ AdvectPar
 
             // ---- DiffusionUniformKh (kernels/_advectiondiffusion.py:120-153) ----
             if (DIFF && p.diffusion) {
-                if constexpr (fast_unrolled_v<Policy>) {
-                    // the two-stage loop body has no room for the Philox / Box-Muller block in the instruction cache (r02m: 318 vs
-                    // 212 ms with it inline): one out-of-line call per step -- few values are live here, the call is cheap
-                    const DiffusionIncrement inc = diffusion_increment(&p, it, i, y, dtp, diff_sq, diff_by);
-                    dx = (float)((double)dx + inc.x);
-                    dy = (float)((double)dy + inc.y);
-                } else {
                 double zx, zy;
                 wiener_normals(p.seed, p.rng_call, it, p.P.pid[i], zx, zy);  // (the id is read when needed: one register pair less in the loop)
                 const double sq = dtp == p.dt ? diff_sq : sqrt(fabs(dtp));
@@ -585,7 +554,6 @@ __global__ void PB_KERNEL_BOUNDS advect_kernel(const __grid_constant__ AdvectPar
                 const double bx = sqrt(2 * khz), by = diff_by;
                 dx = (float)((double)dx + bx * dWx);
                 dy = (float)((double)dy + by * dWy);
-                }
                 ei_zeroed = true;  // the constant-field evals overwrite ei[:, -1] with cell 0 (model.py:292-318)
             }
             if (p.kernels_only) { ++it; break; }  // dx/dy/dz, state, ei are written back below; the host finishes the iteration

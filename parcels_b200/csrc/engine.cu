@@ -941,7 +941,7 @@ int32_t pb_sample_scalar(pb_engine* e, int32_t slot, int32_t method, int64_t n, 
 // The specialised RK4 kernel (afast.cu) gathers from a node-interleaved {u, v, w, 0} copy of the float32 fields: built here, on
 // the device, the first time an RK4 launch can use it (float64 rectilinear grid, XLinear_Velocity, every level resident).
 #ifndef PB_FAST_DEFAULT_DIFFUSION
-#define PB_FAST_DEFAULT_DIFFUSION 1  // (the kernel of DiffusionUniformKh lists until afast2's out-of-line increment is measured)
+#define PB_FAST_DEFAULT_DIFFUSION 1  // (measured, profiles/README.md r02m / r02n)
 #endif
 static bool fast_kernel_enabled() {
     const char* v = getenv("PB_DISABLE_FAST_KERNEL");  // A/B switch of the parity tests and variant sweeps
@@ -949,8 +949,9 @@ static bool fast_kernel_enabled() {
 }
 // which specialised RK4 kernel: 2 = afast2.cu (a two-stage loop body with compile-time renew / reuse, both side-path copies
 // inline), 1 = afast.cu (one evaluation site in a four-trip loop).  Measured (profiles/README.md r02m): advection only 14.2 vs
-// 15.8 ms on config 2 and 180 vs 198 ms on the 1/12 deg workload for afast2; with the fused diffusion block inline the two-stage body
-// overflows the instruction cache (318 vs 212 ms), so afast2 calls the diffusion increment out of line.  PB_FAST_KERNEL=1|2 forces one.
+// 15.8 ms on config 2 and 180 vs 198 ms on the 1/12 deg workload for afast2; with the fused diffusion block the two-stage body
+// overflows the instruction cache (318 ms inline, 342 ms with the increment out of line, against 212 ms): lists with
+// DiffusionUniformKh run afast.cu.  PB_FAST_KERNEL=1|2 forces one.
 static int fast_kernel_version(bool diffusion) {
     const char* v = getenv("PB_FAST_KERNEL");
     if (v && v[0] == '1') return 1;
