@@ -25,8 +25,8 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "parcels_b200", "csrc")
 OUTDIR = os.path.join(ROOT, "oracle", "_build", "hostsim")
 OUT = os.path.join(OUTDIR, "libparcels_b200_hostsim.so")
-SOURCES = ["engine.cu", "afast.cu", "afast2.cu", "agrid.cu", "aslip.cu", "rk45.cu", "advdiff.cu", "hashbuild.cu", "cgrid.cu", "curva.cu"]
-HEADERS = ["common.cuh", "agrid.cuh", "rk45.cuh", "cgrid.cuh", "afast.cuh"]
+SOURCES = ["engine.cu", "afast.cu", "agrid.cu", "aslip.cu", "rk45.cu", "advdiff.cu", "hashbuild.cu", "cgrid.cu", "curva.cu"]
+HEADERS = ["common.cuh", "agrid.cuh", "rk45.cuh", "cgrid.cuh"]
 DEFINES = ["-DPB_SMEM_CACHE", "-DPB_MINBLOCKS=4"]
 BLOCK_KERNELS = {"sel_count": "hs_sel_count", "sel_scan": "hs_sel_scan", "sel_scatter": "hs_sel_scatter"}
 

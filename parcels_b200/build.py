@@ -7,13 +7,13 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["engine.cu", "afast.cu", "afast2.cu", "agrid.cu", "aslip.cu", "rk45.cu", "advdiff.cu", "hashbuild.cu", "cgrid.cu", "curva.cu"]  # one translation unit per kernel family: compiled in parallel
+SOURCES = ["engine.cu", "afast.cu", "agrid.cu", "aslip.cu", "rk45.cu", "advdiff.cu", "hashbuild.cu", "cgrid.cu", "curva.cu"]  # one translation unit per kernel family: compiled in parallel
 # Per-source tuning (measured on B200, profiles/README.md): the A-grid kernel runs best with its corner
 # cache in shared memory (float64 copies on float64 grids) and <= 128 registers (4 blocks of 128 threads per SM).
-EXTRA_FLAGS = {"afast.cu": ["-DPB_BLOCK=384", "-DPB_MINBLOCKS=1", "-DPB_SMEM_CACHE"], "afast2.cu": ["-DPB_BLOCK=128", "-DPB_MINBLOCKS=3", "-DPB_SMEM_CACHE"], "agrid.cu": ["-DPB_MINBLOCKS=4", "-DPB_SMEM_CACHE"], "aslip.cu": ["-DPB_MINBLOCKS=4", "-DPB_SMEM_CACHE"],
+EXTRA_FLAGS = {"afast.cu": ["-DPB_BLOCK=128", "-DPB_MINBLOCKS=3", "-DPB_SMEM_CACHE"], "agrid.cu": ["-DPB_MINBLOCKS=4", "-DPB_SMEM_CACHE"], "aslip.cu": ["-DPB_MINBLOCKS=4", "-DPB_SMEM_CACHE"],
                "rk45.cu": ["-DPB_MINBLOCKS=3", "-DPB_SMEM_CACHE"], "advdiff.cu": ["-DPB_SMEM_CACHE"],
                "cgrid.cu": ["-DPB_MINBLOCKS=3"], "curva.cu": ["-DPB_MINBLOCKS=3"]}  # fmt: skip
-DEPS = [os.path.join(CSRC, f) for f in (*SOURCES, "common.cuh", "agrid.cuh", "rk45.cuh", "cgrid.cuh", "afast.cuh")]
+DEPS = [os.path.join(CSRC, f) for f in (*SOURCES, "common.cuh", "agrid.cuh", "rk45.cuh", "cgrid.cuh")]
 OUT = os.path.join(HERE, "lib", "libparcels_b200.so")
 HEADER = os.path.join(os.path.dirname(HERE), "include", "parcels_b200.h")
 

@@ -2,20 +2,36 @@
 // interpolators/_xinterpolators.py:78-190, _core/field.py:250-405) on a rectilinear A-grid with FLOAT64 coordinates, FLOAT32
 // data and a time axis, every level resident (BASELINE configs 2, 4, 5 and the north-star workload).  Same arithmetic, operation
 // by operation, as the generic AGridPolicy<double, float, true, NC, 0> of agrid.cuh (which stays the kernel of every other
-// dtype / scheme / interpolator combination and is the cross-check of this one in the parity tests); what differs is the schedule:
+// dtype / scheme / interpolator combination and is the cross-check of this one: tests/test_gpu_fast_kernel.py, bit for bit);
+// what differs is the schedule:
 //
-//  * ONE evaluation site in a 4-trip stage loop.  The common case -- the sample is still inside the cached cell of every axis --
-//    is straight-line code: three bcoord divisions, the cos of the latitude, Z-lerp, bilinear, unit conversion.  Everything else
-//    (a cell change, a sentinel index, a sample on the first node of an axis, outside the time axis) is a rare side path.
-//  * The T-lerped block (8 values per component, float64) is kept per lane next to the raw 2x2x2x2 block (float32): the
-//    sample time of stage 3 equals stage 2's and stage 1's equals the previous step's stage 4, so the 24 time lerps are
-//    done twice per step instead of four times (odd stages renew, even stages reuse -- a warp-uniform decision).
-//  * Per-lane cache in shared memory as 16-byte columns ([chunk][lane]: LDS.128 / STS.128, conflict-free): 12 x float4 raw +
-//    12 x double2 lerped = 384 B per lane, 48 KB per 128-thread block, 4 blocks per SM.
+//  * The common case -- the sample is still inside the cached cell of every axis -- is straight-line code: three bcoord divisions
+//    through cached reciprocals, the cos of the latitude (one polynomial), Z-lerp, bilinear, unit conversion.  Everything else (a
+//    cell change, a sentinel index, a sample on the first node of an axis, outside the time axis) is a rare side path.
+//  * Everything a lane caches lives in SHARED MEMORY as 16-byte columns ([chunk][lane]: LDS.128 / STS.128, conflict-free): the raw
+//    2x2x2x2 block (float32), the T-LERPED block (float64: the sample time of stage 3 equals stage 2's and stage 1's equals the
+//    previous step's stage 4, so the 24 time lerps are done twice per step instead of four times), the cells {lo, hi} of z, y,
+//    x, t, the reciprocals of their widths and the cell indices = 496 B per lane, 384 lanes per SM.  The cells are re-read at
+//    every evaluation (volatile loads): they only change in the side path, and keeping them in registers costs moves and spills.
 //  * A refill reads the NODE-INTERLEAVED copy of U, V, W ({u, v, w, 0} per node, built on the device at upload,
-//    interleave_kernel below): 16 x 16-byte loads instead of 48 scattered 4-byte ones, a third of the DRAM sectors.
+//    interleave_kernel below): 16 x 16-byte loads instead of 48 scattered 4-byte ones, a fifth of the DRAM traffic.
 //  * On a cell miss the two neighbouring cells are tried before the full binary search (a particle crosses one face at a time).
-#include "afast.cuh"
+//
+// TWO SCHEDULES of the same evaluation (template parameter SCHED; the 32 KB L1.5 instruction cache decides -- profiles/README.md
+// r02g-r02n, config 2 / 1/12 deg workload / fused diffusion in ms):
+//   SCHED 2 (advection-only lists): a TWO-stage loop body -- a stage that reuses the T-lerped block and one that renews it, the
+//     choice a compile-time constant, run twice per step, both side-path copies inline: 13.9 / 177 / (318).
+//   SCHED 1 (lists with DiffusionUniformKh): ONE evaluation site in a four-trip stage loop, "renew" a run-time flag: 15.8 / 198 / 212
+//     -- next to the Philox / Box-Muller block only one copy of the hit and side paths fits the cache.
+//   Tried and measured slower: all four stages written out (17.0 / 259 / 396: 5000 SASS instructions, `stall_no_inst` on top), the
+//   side path or the diffusion increment out of line (208 / 342: every call spills the hit path's live registers).
+#include <cmath>
+
+#include "agrid.cuh"
+
+#ifndef PB_FAST_BLOCK
+#define PB_FAST_BLOCK PB_BLOCK
+#endif
 
 // ------------------------------------------------------------------------------------------------
 // node-interleaved field copy
@@ -39,72 +55,137 @@ cudaError_t launch_interleave(const float* u, const float* v, const float* w, lo
 }
 
 // ------------------------------------------------------------------------------------------------
-// per-lane state
+// axis search of the side path: the cell only (no bcoord division), neighbours of the cached cell first.
+// Same cell / sentinel as axis_search (common.cuh; reference _core/index_search.py:20-62).
 // ------------------------------------------------------------------------------------------------
-// Everything a lane caches lives in SHARED MEMORY as 16-byte columns [chunk][lane] (LDS.128 / STS.128, conflict-free):
-//   raw block (float32)            NC * NV / 4 chunks
-//   T-lerped block (float64)       NC * NL / 2 chunks
-//   cells: {lo, hi} of z, y, x, t  4 chunks      -- read by the hit test of every evaluation, written by the side path only
-//   reciprocals of the cell widths 2 chunks      -- {1 / dz, 1 / dy}, {1 / dx, 1 / dt}, for div_by_cached
-// = 480 B per lane for UVW.  Keeping the cells out of the registers matters twice: the side path (which rewrites them) no longer
-// forces register-to-register copies onto the hit path (measured: 80 moves per evaluation, profiles/README.md r02d), and the
-// kernel's loop-carried state fits the register file without spills.  One 480-thread block per SM (15 warps).
-// A cell that the straight-line path may use has lo < hi finite and idx >= 0; after a search that ended on a sentinel
-// (or on the first node of the axis, bcoord == 0) lo = hi = NaN so that `x > lo && x <= hi` fails and the lane takes the
-// side path again at its next evaluation.
+__device__ __forceinline__ void axis_locate(const double* __restrict__ arr, int n, double x, AxisCell<double>& c) {
+    if (n < 2) {  // index_search.py:45-46
+        c.idx = 0;
+        return;
+    }
+    if (c.idx >= 0) {
+        // lo < x <= hi of a cell inside the axis is exactly searchsorted(side="left") - 1 == that cell
+        if (x > c.lo && x <= c.hi) return;
+        if (x > c.hi && c.idx + 2 <= n - 1) {
+            const double nh = ldg(arr + c.idx + 2);
+            if (x <= nh) { c.lo = c.hi; c.hi = nh; c.idx += 1; return; }
+        } else if (x <= c.lo && c.idx >= 1) {
+            const double nl = ldg(arr + c.idx - 1);
+            if (x > nl) { c.hi = c.lo; c.lo = nl; c.idx -= 1; return; }
+        }
+    }
+    int l = 0, h = n;  // first i with arr[i] >= x   (side="left")
+    while (l < h) {
+        const int m = (l + h) >> 1;
+        if (ldg(arr + m) < x) l = m + 1; else h = m;
+    }
+    if (x != x) l = n;  // NaN sorts last
+    const int i = min(max(l - 1, 0), n - 2);
+    c.lo = ldg(arr + i);
+    c.hi = ldg(arr + i + 1);
+    c.idx = i;
+    if (x < ldg(arr)) c.idx = -2;          // LEFT_OUT_OF_BOUNDS
+    if (x > ldg(arr + n - 1)) c.idx = -1;  // RIGHT_OUT_OF_BOUNDS
+}
+// bcoord of x in the located cell (also of a clipped one: sentinels keep the cell of the nearest edge)
+__device__ __forceinline__ double axis_bcoord(int n, double x, const AxisCell<double>& c) {
+    return n < 2 ? 0.0 : (x - c.lo) / (c.hi - c.lo);
+}
+
+// The general evaluation of ONE component from a lane's raw block (special samples only: a sentinel index, a sample on the first
+// node of the time / depth axis -- lenT or lenZ == 1 for this particle): agrid.cuh's xlinear, the all-float64 path.  Out of line:
+// it is rare, and keeping its 16-value block out of the hot kernel's register allocation matters more than a call.
+template <int NV>
+__device__ __noinline__ double special_component(const float4* col, double tau, double zeta, double eta, double xsi, int two_t, int two_z) {
+    float blk[16];
+#pragma unroll
+    for (int j = 0; j < NV / 4; ++j) {
+        const float4 r = col[j * PB_FAST_BLOCK];
+        blk[4 * j] = r.x; blk[4 * j + 1] = r.y; blk[4 * j + 2] = r.z; blk[4 * j + 3] = r.w;
+    }
+    if (NV == 8) {  // (t, y, x) -> the generic (t, z, y, x) order with the one depth level twice
+#pragma unroll
+        for (int j = 3; j >= 0; --j) { blk[8 + j] = blk[4 + j]; blk[12 + j] = blk[4 + j]; }
+#pragma unroll
+        for (int j = 3; j >= 0; --j) blk[4 + j] = blk[j];
+    }
+    return xlinear<float, double, double, double, double>(blk, tau, zeta, eta, xsi, two_t != 0, two_z != 0).v;
+}
+
+// a 16-byte shared-memory load the compiler must issue where it is written (no hoisting, no store-to-load forwarding)
+__device__ __forceinline__ double2 lds_volatile(const double2* p) {
+#ifdef PB_HOSTSIM
+    return *p;
+#else
+    double2 r;
+    const unsigned a = (unsigned)__cvta_generic_to_shared(p);
+    asm volatile("ld.volatile.shared.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "r"(a));
+    return r;
+#endif
+}
+
+
+struct SideResult {
+    double u, v, w;
+    int state;
+    int flags;  // SIDE_*
+};
+enum { SIDE_FINAL = 1, SIDE_OUT_OF_TIME = 2, SIDE_REFILLED = 4, SIDE_SEARCHED = 8 };
+
 struct FastCtx {
-    int ti, zi, yi, xi;       // cell indices of the last search (-100: none): key of the raw block, and what `ei` is raveled from
-    double lerp_t;            // sample time the T-lerped block in shared memory belongs to (-1: none)
-    float4* raw;              // this lane's column of 16-byte chunks (raw block first, see the layout above)
-    bool searched;
+    double lerp_t;  // sample time the T-lerped block in shared memory belongs to (-1: none)
+    float4* raw;    // this lane's column of 16-byte chunks
     int state;
     int ei;
     unsigned int refills;
+    bool searched;
     bool out_of_time;
     signed char len_t, len_z;  // (interface of the generic kernel skeleton; unused here)
 };
 
-// NC: components sampled (2: fieldset.UV, 3: fieldset.UVW).  HZ: the grid has a depth axis with >= 2 levels (else zi = 0,
-// zeta = 0 and there is no Z-lerp: `lenZ == 1`, _xinterpolators.py:131).
-template <int NC_, bool HZ>
+// NC: components sampled (2: fieldset.UV, 3: fieldset.UVW).  HZ: the grid has a depth axis with >= 2 levels.  SCHED: see the head
+// of this file (2: two-stage loop body, 1: one evaluation site in a four-trip loop).
+template <int NC_, bool HZ, int SCHED>
 struct AFastPolicy {
     static constexpr int NC = NC_;
-    static constexpr int NV = HZ ? 16 : 8;        // raw values per component: (t, [z,] y, x) corners
-    static constexpr int NL = NV / 2;             // T-lerped values per component
+    static constexpr int NV = HZ ? 16 : 8;          // raw values per component: (t, [z,] y, x) corners
+    static constexpr int NL = NV / 2;               // T-lerped values per component
     static constexpr int RAW_CHUNKS = NC * NV / 4;  // float4 columns
     static constexpr int LRP_CHUNKS = NC * NL / 2;  // double2 columns
     static constexpr int CELL_CHUNKS = 4;           // double2 columns {lo, hi}: z, y, x, t
-    static constexpr int RCP_CHUNKS = 2;            // double2 columns: {1 / dz, 1 / dy}, {1 / dx, 1 / dt} of the current cells
-    static constexpr size_t SMEM = (size_t)(RAW_CHUNKS + LRP_CHUNKS + CELL_CHUNKS + RCP_CHUNKS) * 16 * PB_FAST_BLOCK;
+    static constexpr int RCP_CHUNKS = 2;            // {1 / dz, 1 / dy}, {1 / dx, 1 / dt} of the current cells
+    static constexpr int IDX_CHUNKS = 1;            // int4 {ti, zi, yi, xi} of the last search (-100: none)
+    static constexpr size_t SMEM = (size_t)(RAW_CHUNKS + LRP_CHUNKS + CELL_CHUNKS + RCP_CHUNKS + IDX_CHUNKS) * 16 * PB_FAST_BLOCK;
     static constexpr bool RUNTIME_DTYPE = false;
     static constexpr bool FAST_RK4 = true;
-    static constexpr bool FAST_UNROLLED = false;
+    static constexpr bool FAST_UNROLLED = SCHED == 2;
     static constexpr bool F32_STAGES = false;
-    static constexpr bool BATCH_LEN_T = false;  // float64 grid: every barycentric coordinate is float64, lenT changes no dtype
+    static constexpr bool BATCH_LEN_T = false;
     static constexpr bool BATCH_LEN_Z = false;
     using Ctx = FastCtx;
 
-    __device__ static __forceinline__ double2* lrp(const Ctx& e) {
-        return reinterpret_cast<double2*>(e.raw + (size_t)RAW_CHUNKS * PB_FAST_BLOCK);
+    __device__ static __forceinline__ double2* lrp(float4* raw) { return reinterpret_cast<double2*>(raw + (size_t)RAW_CHUNKS * PB_FAST_BLOCK); }
+    __device__ static __forceinline__ double2* cell(float4* raw, int k) {  // 0: z, 1: y, 2: x, 3: t
+        return reinterpret_cast<double2*>(raw + (size_t)(RAW_CHUNKS + LRP_CHUNKS + k) * PB_FAST_BLOCK);
     }
-    // cell k (0: z, 1: y, 2: x, 3: t) as {lo, hi}
-    __device__ static __forceinline__ double2* cell(const Ctx& e, int k) {
-        return reinterpret_cast<double2*>(e.raw + (size_t)(RAW_CHUNKS + LRP_CHUNKS + k) * PB_FAST_BLOCK);
+    __device__ static __forceinline__ double2* rcp(float4* raw) {
+        return reinterpret_cast<double2*>(raw + (size_t)(RAW_CHUNKS + LRP_CHUNKS + CELL_CHUNKS) * PB_FAST_BLOCK);
     }
-    // reciprocals of the cell widths (correctly rounded: computed by a division when the cell changes), for div_by_cached
-    __device__ static __forceinline__ double2* rcp(const Ctx& e) {
-        return reinterpret_cast<double2*>(e.raw + (size_t)(RAW_CHUNKS + LRP_CHUNKS + CELL_CHUNKS) * PB_FAST_BLOCK);
+    __device__ static __forceinline__ int4* idx(float4* raw) {
+        return reinterpret_cast<int4*>(raw + (size_t)(RAW_CHUNKS + LRP_CHUNKS + CELL_CHUNKS + RCP_CHUNKS) * PB_FAST_BLOCK);
     }
 
     __device__ static __forceinline__ void init(Ctx& e, const AdvectParams&, int ei) {
         const double nan = __longlong_as_double(0x7ff8000000000000LL);
-        e.ti = e.zi = e.yi = e.xi = -100;
         extern __shared__ __align__(16) unsigned char pb_smem[];
         e.raw = reinterpret_cast<float4*>(pb_smem) + threadIdx.x;
         double2 d;
         d.x = nan; d.y = nan;
 #pragma unroll
-        for (int k = 0; k < CELL_CHUNKS; ++k) *cell(e, k) = d;
+        for (int k = 0; k < CELL_CHUNKS; ++k) *cell(e.raw, k) = d;
+        int4 none;
+        none.x = none.y = none.z = none.w = -100;
+        *idx(e.raw) = none;
         e.lerp_t = -1.0;  // valid sample times are >= 0
         e.ei = ei;
         e.searched = false;
@@ -113,16 +194,16 @@ struct AFastPolicy {
     // ravel_index (basegrid.py:259-278) over the axes present of the last completed search; int64 arithmetic stored to int32
     __device__ static __forceinline__ void finish(Ctx& e, const AdvectParams& p) {
         if (!e.searched) return;
-        int gxi = e.xi;
+        const int4 ix = *idx(e.raw);
+        int gxi = ix.w;
         if (p.g.decomposed && gxi >= 0) gxi += p.g.xi_offset;  // mode D: local column -> global column
-        long long r = (long long)e.yi * p.g.xdim + (long long)gxi;
-        if (p.g.nz > 0) r += (long long)(HZ ? e.zi : 0) * (p.g.ydim * p.g.xdim);
+        long long r = (long long)ix.z * p.g.xdim + (long long)gxi;
+        if (p.g.nz > 0) r += (long long)(HZ ? ix.y : 0) * (p.g.ydim * p.g.xdim);
         e.ei = (int)r;
     }
 
-    // gather the (t, z, y, x) corner block of every component from the node-interleaved copy into this lane's raw columns:
-    // per (t, z) plane four 16-byte node loads -> one float4 chunk per component
-    __device__ static __forceinline__ void refill(const FieldDev& f, Ctx& e, int ti, int zi, int yi, int xi) {
+    // gather the (t, z, y, x) corner block of every component from the node-interleaved copy into this lane's raw columns
+    __device__ static __forceinline__ void refill(const FieldDev& f, float4* raw, int ti, int zi, int yi, int xi) {
         const long long ot[2] = {wrap_idx(ti, f.T) * f.sT, up_idx(ti, f.T) * f.sT};
         const long long oz[2] = {wrap_idx(zi, f.Z) * f.sZ, up_idx(zi, f.Z) * f.sZ};
         const long long oy[2] = {wrap_idx(yi, f.Y) * f.sY, up_idx(yi, f.Y) * f.sY};
@@ -136,15 +217,108 @@ struct AFastPolicy {
             const float4 n10 = ldg(base + o + oy[1] + ox[0]), n11 = ldg(base + o + oy[1] + ox[1]);
             float4 q;
             q.x = n00.x; q.y = n01.x; q.z = n10.x; q.w = n11.x;
-            e.raw[(0 * (NV / 4) + pl) * PB_FAST_BLOCK] = q;
+            raw[(0 * (NV / 4) + pl) * PB_FAST_BLOCK] = q;
             q.x = n00.y; q.y = n01.y; q.z = n10.y; q.w = n11.y;
-            e.raw[(1 * (NV / 4) + pl) * PB_FAST_BLOCK] = q;
+            raw[(1 * (NV / 4) + pl) * PB_FAST_BLOCK] = q;
             if (NC == 3) {
                 q.x = n00.z; q.y = n01.z; q.z = n10.z; q.w = n11.z;
-                e.raw[(2 * (NV / 4) + pl) * PB_FAST_BLOCK] = q;
+                raw[(2 * (NV / 4) + pl) * PB_FAST_BLOCK] = q;
             }
         }
-        e.refills++;
+    }
+
+    // ---------------- side path: searches, states, refill; special samples are finished here ----------------
+    // Inline at every evaluation site (out of line it costs the spill / reload of the hit path's live registers at every trip:
+    // measured, r02l).  Reads and rewrites the lane's cells / reciprocals / indices / raw block in shared memory; what the caller
+    // has in registers comes in as arguments and goes back through `out`.
+    __device__ static __forceinline__
+    void side_path(const AdvectParams* pp, float4* raw, int k, double ts, double zs, double ys, double xs, int state, SideResult* out) {
+        const GridDev& g = pp->g;
+        const FieldDev& f = pp->f;
+        int flags = 0;
+        if (!(0 <= ts && ts <= g.time_len)) {  // OutsideTimeInterval (index_search.py:85-86): state 70, sample (0, 0, 0)
+            out->u = out->v = out->w = 0.0;
+            out->state = PB_ERROR_OUTSIDE_TIME_INTERVAL;
+            out->flags = SIDE_FINAL | SIDE_OUT_OF_TIME;
+            return;
+        }
+        const double2 bz = HZ ? *cell(raw, 0) : double2{0.0, 0.0}, by = *cell(raw, 1), bx = *cell(raw, 2), bt = *cell(raw, 3);
+        const int4 old = *idx(raw);  // key of the raw block: {ti, zi, yi, xi}
+        AxisCell<double> ct{old.x, bt.x, bt.y}, cz{old.y, bz.x, bz.y}, cy{old.z, by.x, by.y}, cx{old.w, bx.x, bx.y};
+        const double wt = ct.hi - ct.lo, wz = cz.hi - cz.lo, wy = cy.hi - cy.lo, wx = cx.hi - cx.lo;  // (NaN for a poisoned cell)
+        if (old.x >= 0 && !(ct.lo == ct.lo)) ct.idx = -100;  // (a poisoned cell is not a neighbour-search seed)
+        if (old.y >= 0 && !(cz.lo == cz.lo)) cz.idx = -100;
+        if (old.z >= 0 && !(cy.lo == cy.lo)) cy.idx = -100;
+        if (old.w >= 0 && !(cx.lo == cx.lo)) cx.idx = -100;
+        axis_locate(g.time, g.nt, ts, ct);
+        const int ti = ct.idx;
+        int zi = 0;
+        if (HZ) {
+            axis_locate((const double*)g.depth, g.nz, zs, cz);
+            zi = cz.idx;
+        }
+        axis_locate((const double*)g.lat, g.ny, ys, cy);
+        axis_locate((const double*)g.lon, g.nx, xs, cx);
+        const int yi = cy.idx, xi = cx.idx;
+        {   // cell widths changed: new reciprocals (the division itself: correctly rounded)
+            double2* const rp = rcp(raw);
+            const double nwt = ct.hi - ct.lo, nwz = cz.hi - cz.lo, nwy = cy.hi - cy.lo, nwx = cx.hi - cx.lo;
+            if ((HZ && !(nwz == wz)) || !(nwy == wy)) {
+                double2 d;
+                d.x = 1.0 / nwz; d.y = 1.0 / nwy;
+                rp[0] = d;
+            }
+            if (!(nwx == wx) || !(nwt == wt)) {
+                double2 d;
+                d.x = 1.0 / nwx; d.y = 1.0 / nwt;
+                rp[PB_FAST_BLOCK] = d;
+            }
+        }
+        int4 now;
+        now.x = ti; now.y = zi; now.z = yi; now.w = xi;
+        *idx(raw) = now;
+        flags |= SIDE_SEARCHED;
+        if (g.decomposed) {  // mode D: a sentinel at a slab edge that is not the edge of the global domain = halo too small
+            if ((xi == -2 && !g.left_global) || (xi == -1 && !g.right_global)) state = max(state, 99);
+        }
+        int s = state;
+        if (xi == -1 || yi == -1 || zi == -1) s = max(s, (int)PB_ERROR_OUT_OF_BOUNDS);  // field.py:327-356
+        if (zi == -2) s = max(s, (int)PB_ERROR_THROUGH_SURFACE);
+        if (old.x != ti || (HZ && old.y != zi) || old.z != yi || old.w != xi) {
+            refill(f, raw, ti, zi, yi, xi);
+            flags |= SIDE_REFILLED;
+        }
+        // special: a sentinel index, or a sample not strictly inside (lo, hi] of the time / depth cell (tau or zeta == 0 on the
+        // first node: lenT / lenZ == 1 for this particle, _xinterpolators.py:130-131; NaN; a degenerate cell)
+        const bool t_in = ts > ct.lo && ts <= ct.hi, z_in = !HZ || (zs > cz.lo && zs <= cz.hi);
+        const bool special = xi < 0 || yi < 0 || zi < 0 || !t_in || !z_in;
+        {   // write the cells back; the ones a special sample involved are poisoned so that the lane comes back here next time
+            const double nan = __longlong_as_double(0x7ff8000000000000LL);
+            double2 d;
+            d.x = ct.lo; d.y = ct.hi; if (!t_in) { d.x = nan; d.y = nan; }
+            *cell(raw, 3) = d;
+            if (HZ) { d.x = cz.lo; d.y = cz.hi; if (zi < 0 || !z_in) { d.x = nan; d.y = nan; } *cell(raw, 0) = d; }
+            d.x = cy.lo; d.y = cy.hi; if (yi < 0) { d.x = nan; d.y = nan; }
+            *cell(raw, 1) = d;
+            d.x = cx.lo; d.y = cx.hi; if (xi < 0) { d.x = nan; d.y = nan; }
+            *cell(raw, 2) = d;
+        }
+        if (special) {
+            const double tau = axis_bcoord(g.nt, ts, ct), zeta = HZ ? axis_bcoord(g.nz, zs, cz) : 0.0;
+            const double eta = axis_bcoord(g.ny, ys, cy), xsi = axis_bcoord(g.nx, xs, cx);
+            const bool two_t = tau > 0;             // lenT, per particle (float64 grid: no dtype depends on the batch)
+            const bool two_z = HZ && !(zeta <= 0);  // lenZ, per particle (a NaN depth must poison the value)
+            double u = special_component<NV>(raw, tau, zeta, eta, xsi, two_t, two_z);
+            double v = special_component<NV>(raw + (NV / 4) * PB_FAST_BLOCK, tau, zeta, eta, xsi, two_t, two_z);
+            double w = NC == 3 ? special_component<NV>(raw + 2 * (NV / 4) * PB_FAST_BLOCK, tau, zeta, eta, xsi, two_t, two_z) : 0.0;
+            if (g.spherical) spherical(g, k == 0, ys, u, v);
+            if (u != u || v != v || w != w) s = max(s, (int)PB_ERROR_INTERPOLATION);
+            if (xi < 0 || yi < 0 || zi < 0) { u = 0.0; v = 0.0; w = 0.0; }
+            out->u = u; out->v = v; out->w = w;
+            flags |= SIDE_FINAL;
+        }
+        out->state = s;
+        out->flags = flags;
     }
 
     // Z-lerp (:141-145) and bilinear (:147-152, left to right) of one component's T-lerped values
@@ -160,118 +334,50 @@ struct AFastPolicy {
         return w00 * r[0] + w01 * r[1] + w10 * r[2] + w11 * r[3];
     }
 
-    // One VectorField.eval (field.py:250-304) at an RK4 stage position; k = stage 0..3 (warp-uniform).
-    __device__ static __forceinline__ void eval_fast(const AdvectParams& p, Ctx& e, const int k, const double ts, const double zs,
-                                                     const double ys, const double xs, double& u, double& v, double& w) {
+    // One VectorField.eval (field.py:250-304) at an RK4 stage position.  Odd stages sample a new time: the T-lerped block is
+    // renewed; even stages reuse it.  RENEW = 0 / 1: decided at compile time (SCHED 2: the loop body holds a reusing and a renewing
+    // copy of this function and runs twice per step); RENEW = -1: `renew_rt` decides (SCHED 1: one copy, four trips).
+    template <int RENEW>
+    __device__ static __forceinline__ void eval_fast(const AdvectParams& p, Ctx& e, const bool renew_rt, const bool first, const double ts,
+                                                     const double zs, const double ys, const double xs, double& u, double& v, double& w) {
         const GridDev& g = p.g;
-        const FieldDev& f = p.f;
-        const bool renew = (k & 1) != 0;  // odd stages sample a new time: the T-lerped block is renewed; even stages reuse it
-        // The cells are READ FROM SHARED MEMORY at every evaluation, on purpose: without this barrier the compiler keeps them in
-        // registers across evaluations (they only change in the side path) and pays for it with ~80 register moves per evaluation
-        // on the hit path plus spills of the particle state (volatile loads: neither NVVM nor ptxas may forward them).
-        bool lerp_now = renew, retried = false;
+        const bool renew = RENEW < 0 ? renew_rt : (RENEW != 0);
+        float4* const raw = e.raw;
+        bool lerp_now = renew;
         double2 bz, by, bx, bt;  // {lo, hi} of the current cells
-        // At most two trips: the hit test; on a miss the side path (which rewrites the cells IN SHARED MEMORY) and the test again.
-        // The cell values used below have ONE definition -- these loads -- so no register copies are needed where the paths join.
-        for (;;) {
-            bz = HZ ? lds_volatile(cell(e, 0)) : double2{0.0, 0.0};
-            by = lds_volatile(cell(e, 1));
-            bx = lds_volatile(cell(e, 2));
-            bt = (renew || retried) ? lds_volatile(cell(e, 3)) : double2{0.0, 0.0};  // (even stages test the cached lerp's time)
+        // The cells are READ FROM SHARED MEMORY at every evaluation, on purpose (volatile loads: neither NVVM nor ptxas may forward
+        // them): they only change in the side path, and keeping them in registers across evaluations costs moves and spills.
+#pragma unroll 1
+        for (int trip = 0;; ++trip) {
+            bz = HZ ? lds_volatile(cell(raw, 0)) : double2{0.0, 0.0};
+            by = lds_volatile(cell(raw, 1));
+            bx = lds_volatile(cell(raw, 2));
+            bt = (renew || trip) ? lds_volatile(cell(raw, 3)) : double2{0.0, 0.0};  // (even stages test the cached lerp's time)
             bool hit = xs > bx.x && xs <= bx.y && ys > by.x && ys <= by.y;
             if (HZ) hit = hit && zs > bz.x && zs <= bz.y;
             hit = hit && (renew ? (ts > bt.x && ts <= bt.y) : (ts == e.lerp_t));
-            if (hit || retried) break;
-            // ---------------- side path: searches, states, refill; special samples are finished here ----------------
-            if (!(0 <= ts && ts <= g.time_len)) {  // OutsideTimeInterval (index_search.py:85-86): state 70, sample (0, 0, 0)
-                e.state = PB_ERROR_OUTSIDE_TIME_INTERVAL;
-                e.out_of_time = true;
-                u = v = w = 0.0;
+            if (hit || trip) break;
+            SideResult r;
+            side_path(&p, raw, first ? 0 : 1, ts, zs, ys, xs, e.state, &r);
+            e.state = r.state;
+            if (r.flags & SIDE_OUT_OF_TIME) e.out_of_time = true;
+            if (r.flags & SIDE_SEARCHED) e.searched = true;
+            if (r.flags & SIDE_REFILLED) { e.refills++; e.lerp_t = -1.0; }
+            if (r.flags & SIDE_FINAL) {
+                u = r.u; v = r.v; w = r.w;
                 return;
             }
-            if (!renew) bt = lds_volatile(cell(e, 3));
-            AxisCell<double> ct{e.ti, bt.x, bt.y}, cz{e.zi, bz.x, bz.y}, cy{e.yi, by.x, by.y}, cx{e.xi, bx.x, bx.y};
-            const int oti = ct.idx, ozi = cz.idx, oyi = cy.idx, oxi = cx.idx;  // key of the raw block
-            const double wt = ct.hi - ct.lo, wz = cz.hi - cz.lo, wy = cy.hi - cy.lo, wx = cx.hi - cx.lo;  // (NaN for a poisoned cell)
-            if (oti >= 0 && !(ct.lo == ct.lo)) ct.idx = -100;  // (a poisoned cell is not a neighbour-search seed)
-            if (ozi >= 0 && !(cz.lo == cz.lo)) cz.idx = -100;
-            if (oyi >= 0 && !(cy.lo == cy.lo)) cy.idx = -100;
-            if (oxi >= 0 && !(cx.lo == cx.lo)) cx.idx = -100;
-            axis_locate(g.time, g.nt, ts, ct);
-            const int ti = ct.idx;
-            int zi = 0;
-            if (HZ) {
-                axis_locate((const double*)g.depth, g.nz, zs, cz);
-                zi = cz.idx;
-            }
-            axis_locate((const double*)g.lat, g.ny, ys, cy);
-            axis_locate((const double*)g.lon, g.nx, xs, cx);
-            const int yi = cy.idx, xi = cx.idx;
-            {   // cell widths changed: new reciprocals (the division itself: correctly rounded)
-                double2* const rp = rcp(e);
-                const double nwt = ct.hi - ct.lo, nwz = cz.hi - cz.lo, nwy = cy.hi - cy.lo, nwx = cx.hi - cx.lo;
-                // (one division per axis whose cell width changed -- a particle crosses one face at a time: usually one of the four)
-                double* const r0 = reinterpret_cast<double*>(rp);
-                double* const r1 = reinterpret_cast<double*>(rp + PB_FAST_BLOCK);
-                if (HZ && !(nwz == wz)) r0[0] = 1.0 / nwz;
-                if (!(nwy == wy)) r0[1] = 1.0 / nwy;
-                if (!(nwx == wx)) r1[0] = 1.0 / nwx;
-                if (!(nwt == wt)) r1[1] = 1.0 / nwt;
-            }
-            e.ti = ti; e.zi = zi; e.yi = yi; e.xi = xi;
-            if (g.decomposed) {  // mode D: a sentinel at a slab edge that is not the edge of the global domain = halo too small
-                if ((xi == -2 && !g.left_global) || (xi == -1 && !g.right_global)) e.state = max(e.state, 99);
-            }
-            e.searched = true;
-            int s = e.state;
-            if (xi == -1 || yi == -1 || zi == -1) s = max(s, (int)PB_ERROR_OUT_OF_BOUNDS);  // field.py:327-356
-            if (zi == -2) s = max(s, (int)PB_ERROR_THROUGH_SURFACE);
-            if (oti != ti || (HZ && ozi != zi) || oyi != yi || oxi != xi) {
-                refill(f, e, ti, zi, yi, xi);
-                e.lerp_t = -1.0;
-            }
-            // special: a sentinel index, or a sample not strictly inside (lo, hi] of the time / depth cell (tau or zeta == 0 on the
-            // first node: lenT / lenZ == 1 for this particle, _xinterpolators.py:130-131; NaN; a degenerate cell)
-            const bool t_in = ts > ct.lo && ts <= ct.hi, z_in = !HZ || (zs > cz.lo && zs <= cz.hi);
-            const bool special = xi < 0 || yi < 0 || zi < 0 || !t_in || !z_in;
-            {   // write the cells back; the ones a special sample involved are poisoned so that the lane comes back here next time
-                const double nan = __longlong_as_double(0x7ff8000000000000LL);
-                double2 d;
-                d.x = ct.lo; d.y = ct.hi; if (!t_in) { d.x = nan; d.y = nan; }
-                *cell(e, 3) = d;
-                if (HZ) { d.x = cz.lo; d.y = cz.hi; if (zi < 0 || !z_in) { d.x = nan; d.y = nan; } *cell(e, 0) = d; }
-                d.x = cy.lo; d.y = cy.hi; if (yi < 0) { d.x = nan; d.y = nan; }
-                *cell(e, 1) = d;
-                d.x = cx.lo; d.y = cx.hi; if (xi < 0) { d.x = nan; d.y = nan; }
-                *cell(e, 2) = d;
-            }
-            if (special) {
-                const double tau = axis_bcoord(g.nt, ts, ct), zeta = HZ ? axis_bcoord(g.nz, zs, cz) : 0.0;
-                const double eta = axis_bcoord(g.ny, ys, cy), xsi = axis_bcoord(g.nx, xs, cx);
-                const bool two_t = tau > 0;             // lenT, per particle (float64 grid: no dtype depends on the batch)
-                const bool two_z = HZ && !(zeta <= 0);  // lenZ, per particle (a NaN depth must poison the value)
-                u = special_component<NV>(e.raw, tau, zeta, eta, xsi, two_t, two_z);
-                v = special_component<NV>(e.raw + (NV / 4) * PB_FAST_BLOCK, tau, zeta, eta, xsi, two_t, two_z);
-                w = NC == 3 ? special_component<NV>(e.raw + 2 * (NV / 4) * PB_FAST_BLOCK, tau, zeta, eta, xsi, two_t, two_z) : 0.0;
-                if (g.spherical) spherical(g, k, ys, u, v);
-                if (u != u || v != v || w != w) s = max(s, (int)PB_ERROR_INTERPOLATION);
-                if (xi < 0 || yi < 0 || zi < 0) { u = 0.0; v = 0.0; w = 0.0; }
-                e.state = s;
-                return;
-            }
-            e.state = s;
             lerp_now = true;  // (an even stage after a cell change: its block has to be lerped for this sample time first)
-            retried = true;
         }
         // ---------------- straight-line path: every cell is current, 0 < bcoord <= 1 on every axis ----------------
         // bcoord = (x - lo) / (hi - lo), index_search.py:57 (denominator in the axis dtype), with the cell width's cached reciprocal
-        const double2 r_zy = rcp(e)[0], r_xt = rcp(e)[PB_FAST_BLOCK];
+        const double2 r_zy = rcp(raw)[0], r_xt = rcp(raw)[PB_FAST_BLOCK];
         const double zeta = HZ ? div_by_cached(zs - bz.x, bz.y - bz.x, r_zy.x) : 0.0;
         const double eta = div_by_cached(ys - by.x, by.y - by.x, r_zy.y);
         const double xsi = div_by_cached(xs - bx.x, bx.y - bx.x, r_xt.x);
         const double omz = 1 - zeta;
         const double w00 = (1 - xsi) * (1 - eta), w01 = xsi * (1 - eta), w10 = (1 - xsi) * eta, w11 = xsi * eta;
-        double2* const lp = lrp(e);
+        double2* const lp = lrp(raw);
         double q[3] = {0.0, 0.0, 0.0};
         if (lerp_now) {
             const double tau = div_by_cached(ts - bt.x, bt.y - bt.x, r_xt.y);
@@ -281,8 +387,8 @@ struct AFastPolicy {
                 float lo_t[NL], hi_t[NL];
 #pragma unroll
                 for (int j = 0; j < NL / 4; ++j) {
-                    const float4 a = e.raw[(c * (NV / 4) + j) * PB_FAST_BLOCK];
-                    const float4 b = e.raw[(c * (NV / 4) + NL / 4 + j) * PB_FAST_BLOCK];
+                    const float4 a = raw[(c * (NV / 4) + j) * PB_FAST_BLOCK];
+                    const float4 b = raw[(c * (NV / 4) + NL / 4 + j) * PB_FAST_BLOCK];
                     lo_t[4 * j] = a.x; lo_t[4 * j + 1] = a.y; lo_t[4 * j + 2] = a.z; lo_t[4 * j + 3] = a.w;
                     hi_t[4 * j] = b.x; hi_t[4 * j + 1] = b.y; hi_t[4 * j + 2] = b.z; hi_t[4 * j + 3] = b.w;
                 }
@@ -311,15 +417,15 @@ struct AFastPolicy {
             }
         }
         u = q[0]; v = q[1]; w = NC == 3 ? q[2] : 0.0;
-        if (g.spherical) spherical(g, k, ys, u, v);
+        if (g.spherical) spherical(g, first, ys, u, v);
         if (u != u || v != v || w != w) e.state = max(e.state, (int)PB_ERROR_INTERPOLATION);  // field.py:288-290
     }
 
     // u /= deg2m * cos(deg2rad(y)); v /= deg2m (_xinterpolators.py:182-184).  Stage 1 samples at the particle's own float32
     // latitude: the factor is float32 arithmetic there (and the float64 value is divided by its float64 promotion).
-    __device__ static __forceinline__ void spherical(const GridDev& g, int k, double ys, double& u, double& v) {
+    __device__ static __forceinline__ void spherical(const GridDev& g, bool first, double ys, double& u, double& v) {
         double conv;
-        if (k == 0) conv = (double)((float)g.deg2m * cos_np(deg2rad_np((float)ys)));
+        if (first) conv = (double)((float)g.deg2m * cos_np(deg2rad_np((float)ys)));
         else conv = g.deg2m * cos_np(deg2rad_np(ys));
         u = u / conv;
         v = div_by_cached_guarded(v, g.deg2m, g.inv_deg2m);
@@ -340,9 +446,9 @@ bool agrid_fast_applies(const AdvectParams& p, bool coord_f64, bool data_f64, bo
     return p.g.nt >= 2 && p.g.nx >= 2 && p.g.ny >= 2;
 }
 
-template <int NC, bool HZ, bool DIFF>
+template <int NC, bool HZ, int SCHED, bool DIFF>
 static cudaError_t launch_fast2(const AdvectParams& p, cudaStream_t s) {
-    using Pol = AFastPolicy<NC, HZ>;
+    using Pol = AFastPolicy<NC, HZ, SCHED>;
     const long long grid = (p.P.n + PB_FAST_BLOCK - 1) / PB_FAST_BLOCK;
     if (Pol::SMEM > 48 * 1024) {
         cudaError_t ce = cudaFuncSetAttribute(advect_kernel<Pol, DIFF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Pol::SMEM);
@@ -351,13 +457,15 @@ static cudaError_t launch_fast2(const AdvectParams& p, cudaStream_t s) {
     advect_kernel<Pol, DIFF><<<(unsigned)grid, PB_FAST_BLOCK, Pol::SMEM, s>>>(p);
     return cudaGetLastError();
 }
+// (each schedule is instantiated for the lists it is the kernel of, plus the advection-only form of SCHED 1 for A/B runs)
 template <int NC, bool HZ>
-static cudaError_t launch_fast1(const AdvectParams& p, cudaStream_t s) {
-    return p.diffusion ? launch_fast2<NC, HZ, true>(p, s) : launch_fast2<NC, HZ, false>(p, s);
+static cudaError_t launch_fast1(const AdvectParams& p, int sched, cudaStream_t s) {
+    if (p.diffusion) return sched == 2 ? launch_fast2<NC, HZ, 2, true>(p, s) : launch_fast2<NC, HZ, 1, true>(p, s);
+    return sched == 2 ? launch_fast2<NC, HZ, 2, false>(p, s) : launch_fast2<NC, HZ, 1, false>(p, s);
 }
 
-cudaError_t launch_agrid_fast(const AdvectParams& p, int nc, cudaStream_t s) {
+cudaError_t launch_agrid_fast(const AdvectParams& p, int nc, int sched, cudaStream_t s) {
     const bool hz = p.g.nz >= 2;
-    if (nc == 3) return launch_fast1<3, true>(p, s);
-    return hz ? launch_fast1<2, true>(p, s) : launch_fast1<2, false>(p, s);
+    if (nc == 3) return launch_fast1<3, true>(p, sched, s);
+    return hz ? launch_fast1<2, true>(p, sched, s) : launch_fast1<2, false>(p, sched, s);
 }

@@ -320,7 +320,7 @@ __device__ __forceinline__ double half_of(const Val& a) { return a.f32 ? (double
 #endif
 // DIFF = false compiles the kernel without the DiffusionUniformKh block (the specialised RK4 kernel is instantiated both ways:
 // the advection-only hot path carries neither the Philox / Box-Muller code nor its loop-invariant registers)
-// whether a policy is a FAST_RK4 one whose four stages are written out (afast2.cu)
+// whether a policy is a FAST_RK4 one with the two-stage loop body (afast.cu, SCHED 2)
 template <class P, class = void>
 struct FastUnrolled : std::false_type {};
 template <class P>
@@ -402,7 +402,7 @@ __global__ void PB_KERNEL_BOUNDS advect_kernel(const __grid_constant__ AdvectPar
             // constant-field evals of the previous step: curvilinear hints are all zero again
             const bool nohint1 = (it == 0 && p.hint_all_zero) || (it > 0 && DIFF && p.diffusion);
             if constexpr (fast_unrolled_v<Policy>) {
-                // afast2.cu: a two-stage loop body (an even stage that reuses the T-lerped block, an odd one that renews it), run
+                // afast.cu SCHED 2: a two-stage loop body (an even stage that reuses the T-lerped block, an odd one that renews it), run
                 // twice per step; operation for operation the arithmetic of the four-trip loop below
                 su = sv = sw = 0.0;
                 uk = Val{0.0, false}; vk = uk; wk = uk;
@@ -414,18 +414,18 @@ __global__ void PB_KERNEL_BOUNDS advect_kernel(const __grid_constant__ AdvectPar
                     // stage 1 (the particle's own position and time) or stage 3 (half a step with stage 2's velocities)
                     double xs = first ? xd : xd + (uk.v * 0.5) * dtp, ys = first ? yd : yd + (vk.v * 0.5) * dtp;
                     double zs = (first || !three_d) ? zd : zd + (wk.v * 0.5) * dtp;
-                    Policy::template eval_fast<false>(p, e, first, first ? t : th, zs, ys, xs, uk.v, vk.v, wk.v);
+                    Policy::template eval_fast<0>(p, e, false, first, first ? t : th, zs, ys, xs, uk.v, vk.v, wk.v);
                     if (first) { su = uk.v; sv = vk.v; sw = wk.v; }
                     else { su = su + 2.0 * uk.v; sv = sv + 2.0 * vk.v; sw = sw + 2.0 * wk.v; }
                     // stage 2 (half a step with stage 1's velocities) or stage 4 (a full step with stage 3's)
                     xs = xd + (first ? uk.v * 0.5 : uk.v) * dtp; ys = yd + (first ? vk.v * 0.5 : vk.v) * dtp;
                     zs = three_d ? zd + (first ? wk.v * 0.5 : wk.v) * dtp : zd;
-                    Policy::template eval_fast<true>(p, e, false, first ? th : t + dtp, zs, ys, xs, uk.v, vk.v, wk.v);
+                    Policy::template eval_fast<1>(p, e, true, false, first ? th : t + dtp, zs, ys, xs, uk.v, vk.v, wk.v);
                     const double m = first ? 2.0 : 1.0;  // u1 + 2*u2 + 2*u3 + u4
                     su = su + m * uk.v; sv = sv + m * vk.v; sw = sw + m * wk.v;
                 }
             } else if constexpr (Policy::FAST_RK4) {
-                // afast.cu: float64 grid, float32 data -- every stage value is float64 (Val::f32 never set), one eval site,
+                // afast.cu SCHED 1: float64 grid, float32 data -- every stage value is float64 (Val::f32 never set), one eval site,
                 // odd stages renew the T-lerped block, even stages reuse it (stages 2/3 and 4/next-1 share their sample time)
                 su = sv = sw = 0.0;
                 uk = Val{0.0, false}; vk = uk; wk = uk;
@@ -437,7 +437,7 @@ __global__ void PB_KERNEL_BOUNDS advect_kernel(const __grid_constant__ AdvectPar
                     const double ys = first ? (double)y : (double)y + (full ? vk.v : vk.v * 0.5) * dtp;
                     const double zs = (first || !three_d) ? (double)z : (double)z + (full ? wk.v : wk.v * 0.5) * dtp;
                     const double ts = first ? t : t + (full ? dtp : 0.5 * dtp);
-                    Policy::eval_fast(p, e, k, ts, zs, ys, xs, uk.v, vk.v, wk.v);
+                    Policy::template eval_fast<-1>(p, e, (k & 1) != 0, first, ts, zs, ys, xs, uk.v, vk.v, wk.v);
                     if (first) { su = uk.v; sv = vk.v; sw = wk.v; }
                     else {
                         const double m = (k == 3) ? 1.0 : 2.0;  // u1 + 2*u2 + 2*u3 + u4
@@ -736,8 +736,7 @@ __global__ void sample_kernel(const SampleParams s) {
 cudaError_t launch_agrid(const AdvectParams& p, bool coord_f64, bool data_f64, bool has_time, int nc, cudaStream_t s);
 // afast.cu: the specialised RK4 kernel (float64 grid, float32 node-interleaved data, time axis); `ok` tells whether it applies
 bool agrid_fast_applies(const AdvectParams& p, bool coord_f64, bool data_f64, bool has_time, int nc);
-cudaError_t launch_agrid_fast(const AdvectParams& p, int nc, cudaStream_t s);
-cudaError_t launch_agrid_fast2(const AdvectParams& p, int nc, cudaStream_t s);  // afast2.cu: stages written out, side path out of line
+cudaError_t launch_agrid_fast(const AdvectParams& p, int nc, int sched, cudaStream_t s);  // sched: 2 two-stage loop body, 1 four-trip loop
 cudaError_t launch_interleave(const float* u, const float* v, const float* w, long long nodes, void* out, cudaStream_t s);
 cudaError_t launch_cgrid(const AdvectParams& p, bool coord_f64, bool data_f64, int nc, cudaStream_t s);
 // mode: 1 = _Spatialslip (g.slip_a/b), 2 = XNearest per component  (aslip.cu)

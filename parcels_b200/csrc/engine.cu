@@ -947,11 +947,11 @@ static bool fast_kernel_enabled() {
     const char* v = getenv("PB_DISABLE_FAST_KERNEL");  // A/B switch of the parity tests and variant sweeps
     return !(v && v[0] == '1');
 }
-// which specialised RK4 kernel: 2 = afast2.cu (a two-stage loop body with compile-time renew / reuse, both side-path copies
-// inline), 1 = afast.cu (one evaluation site in a four-trip loop).  Measured (profiles/README.md r02m): advection only 14.2 vs
+// which schedule of the specialised RK4 kernel (afast.cu): 2 = a two-stage loop body with compile-time renew / reuse, 1 = one
+// evaluation site in a four-trip loop.  Measured (profiles/README.md r02m): advection only 14.2 vs
 // 15.8 ms on config 2 and 180 vs 198 ms on the 1/12 deg workload for afast2; with the fused diffusion block the two-stage body
 // overflows the instruction cache (318 ms inline, 342 ms with the increment out of line, against 212 ms): lists with
-// DiffusionUniformKh run afast.cu.  PB_FAST_KERNEL=1|2 forces one.
+// DiffusionUniformKh run schedule 1.  PB_FAST_KERNEL=1|2 forces one.
 static int fast_kernel_version(bool diffusion) {
     const char* v = getenv("PB_FAST_KERNEL");
     if (v && v[0] == '1') return 1;
@@ -1021,7 +1021,7 @@ static cudaError_t launch_advect_kernel(pb_engine* e, const AdvectParams& p, int
     if (e->interp == PB_INTERP_XLINEAR_VELOCITY && fast_kernel_enabled() &&
         agrid_fast_applies(p, e->coord_f64 != 0, e->f_f64[0] != 0, e->g.nt > 0, nc)) {
         e->last_variant = fast_kernel_version(p.diffusion != 0);
-        return e->last_variant == 2 ? launch_agrid_fast2(p, nc, stream) : launch_agrid_fast(p, nc, stream);
+        return launch_agrid_fast(p, nc, e->last_variant, stream);
     }
     e->last_variant = 0;
     return e->interp == PB_INTERP_CGRID_VELOCITY ? launch_cgrid(p, e->coord_f64 != 0, e->f_f64[0] != 0, nc, stream)

@@ -1,4 +1,4 @@
-"""The specialised RK4 kernel (csrc/afast.cu: float64 grid, float32 node-interleaved data, cached T-lerp) against the generic
+"""The specialised RK4 kernel (csrc/afast.cu: float64 grid, float32 node-interleaved data, cached T-lerp; two schedules) against the generic
 A-grid kernel (csrc/agrid.cuh) -- the SAME arithmetic in another schedule, so every array must agree BIT FOR BIT -- and against
 the oracle.  `PB_DISABLE_FAST_KERNEL=1` (read by the library at every launch) selects the generic kernel."""
 
@@ -79,8 +79,8 @@ def _case(seed):
 
 
 def _run(c, fast: int):
-    """fast: 0 = the generic kernel, 1 = afast.cu (four-trip stage loop), 2 = afast2.cu (two-stage loop body; the library default
-    for advection-only lists)"""
+    """fast: 0 = the generic kernel, 1 / 2 = afast.cu's schedule 1 (four-trip stage loop; the default of lists with diffusion) /
+    2 (two-stage loop body; the default of advection-only lists)"""
     os.environ["PB_DISABLE_FAST_KERNEL"] = "0" if fast else "1"
     os.environ["PB_FAST_KERNEL"] = str(fast or 1)
     try:
