@@ -949,7 +949,7 @@ static bool fast_kernel_enabled() {
 }
 // which schedule of the specialised RK4 kernel (afast.cu): 2 = a two-stage loop body with compile-time renew / reuse, 1 = one
 // evaluation site in a four-trip loop.  Measured (profiles/README.md r02m): advection only 14.2 vs
-// 15.8 ms on config 2 and 180 vs 198 ms on the 1/12 deg workload for afast2; with the fused diffusion block the two-stage body
+// 15.8 ms on config 2 and 180 vs 198 ms on the 1/12 deg workload for schedule 2; with the fused diffusion block the two-stage body
 // overflows the instruction cache (318 ms inline, 342 ms with the increment out of line, against 212 ms): lists with
 // DiffusionUniformKh run schedule 1.  PB_FAST_KERNEL=1|2 forces one.
 static int fast_kernel_version(bool diffusion) {

@@ -1,5 +1,5 @@
 """One tuning variant of the library: recompile some translation units with other flags, link with the default objects.
-   python scripts/build_variant.py cg3 cgrid.cu:-DPB_MINBLOCKS=3 [afast2.cu:"-DPB_BLOCK=448 -DPB_MAXNREG=144" ...]
+   python scripts/build_variant.py cg3 cgrid.cu:-DPB_MINBLOCKS=3 [afast.cu:"-DPB_BLOCK=384 -DPB_MINBLOCKS=1" ...]
    -> parcels_b200/lib/libparcels_b200_<tag>.so   (use with PB_LIB=...)"""
 import os
 import subprocess
