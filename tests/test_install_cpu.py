@@ -46,7 +46,7 @@ def test_errors_are_raised_as_the_references_own_classes(result):
 
 def test_config2_dtypes_take_the_specialised_kernel(result):
     r = result["c2_small"]
-    assert r["variant"] == 1 and r["err"] == ["", ""] and all(r["same"].values()), r
+    assert r["variant"] == 2 and r["err"] == ["", ""] and all(r["same"].values()), r  # (afast.cu, schedule 2: advection only)
 
 
 def test_output_intervals_of_the_references_outer_loop(result):
