@@ -314,25 +314,6 @@ __device__ __forceinline__ void hash_query(const GridDev& g, CGridCtx<A, D>& e, 
     }
 }
 
-// The same query OUT OF LINE (tuning build -DPB_HASH_COLD; an experiment that lost: a hash query happens 0.03 times per warp and
-// dt-step on config 3 and its ~350 instructions sit in the middle of the time loop, but calling it costs spills of the caller's
-// live registers -- 188.7 vs 160.8 ms).  It works on a private cell cache (by-value interface) and returns in registers.
-struct HashHit {
-    double xsi, eta;
-    int yi, xi;
-};
-template <class A, class D>
-static __device__ __noinline__ HashHit hash_query_cold(const GridDev* gp, double qx_, double qy_, double ux, double uy, double uz, int finite,
-                                                       unsigned int qx, unsigned int qy, unsigned int qz) {
-    CGridCtx<A, D> e;
-    e.kyi = e.kxi = INT_MIN;
-    Query q;
-    q.x = qx_; q.y = qy_; q.qu_x = ux; q.qu_y = uy; q.qu_z = uz;
-    HashHit r;
-    hash_query(*gp, e, q, finite != 0, qx, qy, qz, r.yi, r.xi, r.xsi, r.eta);
-    return r;
-}
-
 // ------------------------------------------------------------------------------------------------
 // CGrid_Velocity arithmetic (typed like NumPy: A corner coords, C face values, TY/TX bcoords)
 // ------------------------------------------------------------------------------------------------
@@ -733,14 +714,9 @@ struct CurvPolicy {
                 }
             }
             if (!nb) {
-#ifndef PB_HASH_COLD  // measured (profiles/README.md r02l): the query inlined in the time loop 160.8 ms on config 3, out of line
-                      // (hash_query_cold: registers spilled around the call) 188.7 ms -- inline is the build
+                // (inline on purpose: out of line -- 0.03 queries per warp-step, ~350 instructions -- the call spills the caller's live
+                //  registers: 188.7 vs 160.8 ms on config 3, profiles/README.md r02l)
                 hash_query(g, e, q, xy_f32 ? isfinite((float)x) && isfinite((float)y) : isfinite(x) && isfinite(y), qx, qy, qz, yi, xi, xsi, eta);
-#else
-                const HashHit hh = hash_query_cold<A, D>(&p.g, q.x, q.y, q.qu_x, q.qu_y, q.qu_z,
-                                                         xy_f32 ? isfinite((float)x) && isfinite((float)y) : isfinite(x) && isfinite(y), qx, qy, qz);
-                yi = hh.yi; xi = hh.xi; xsi = hh.xsi; eta = hh.eta;
-#endif
             }
         }
         e.yi = yi; e.xi = xi;

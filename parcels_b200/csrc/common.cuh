@@ -328,14 +328,8 @@ struct FastUnrolled<P, std::void_t<decltype(P::FAST_UNROLLED)>> : std::integral_
 template <class P>
 constexpr bool fast_unrolled_v = FastUnrolled<P>::value;
 
-// (PB_MAXNREG: a tuning build caps the registers directly -- __launch_bounds__ only offers the caps 65536 / threads rounds to)
-#ifdef PB_MAXNREG
-#define PB_KERNEL_BOUNDS __maxnreg__(PB_MAXNREG)
-#else
-#define PB_KERNEL_BOUNDS __launch_bounds__(PB_BLOCK_THREADS, PB_MINBLOCKS)
-#endif
 template <class Policy, bool DIFF = true>
-__global__ void PB_KERNEL_BOUNDS advect_kernel(const __grid_constant__ AdvectParams p) {
+__global__ void __launch_bounds__(PB_BLOCK_THREADS, PB_MINBLOCKS) advect_kernel(const __grid_constant__ AdvectParams p) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long my_steps = 0, my_refills = 0;  // (my_steps = the lane's iteration count, set on exit)
     int final_state = 0;
