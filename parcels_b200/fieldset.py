@@ -196,10 +196,11 @@ class Field:
 
 
 class VectorField:
-    def __init__(self, name, U, V, W=None):
+    def __init__(self, name, U, V, W=None, host=None):
         self.name, self.U, self.V, self.W = name, U, V, W
         self.grid = U.grid
         self.vector_type = "3D" if W is not None else "2D"
+        self._host = host  # who keeps the components in HBM: the FieldSet (None) or an _ExtraGrid (a vector field on another grid)
 
     def eval(self, t, z, y, x, particles=None, *, device=None, positions_are_f32=None):
         """``fieldset.UV.eval(t, z, y, x[, particles])`` (reference _core/field.py:250-295), evaluated ON THE DEVICE
@@ -207,6 +208,7 @@ class VectorField:
         ``particles`` (a ParticleSet or the ParticleSetView a user kernel received) the search is hinted by, and
         writes back, ``particles.ei[:, -1]`` and raises ``particles.state`` exactly like the reference does."""
         fs = self.U._fieldset
+        host = self._host or fs
         if device is None:
             device = next(iter(fs._engines), 0)
         z, y, x = (np.atleast_1d(a.__array__() if hasattr(a, "__array__") else a) for a in (z, y, x))
@@ -218,8 +220,8 @@ class VectorField:
         hint = None
         if particles is not None:
             hint = np.ascontiguousarray(np.asarray(particles.ei)[:, -1])
-        u, v, w, ei, st = fs.engine(device).sample_velocity(t, z, y, x, three_d=self.W is not None, positions_are_f32=positions_are_f32,
-                                                            ei_hint=hint, no_hint=_batch_skips_hint(fs.grid, hint))  # fmt: skip
+        u, v, w, ei, st = host.engine(device).sample_velocity(t, z, y, x, three_d=self.W is not None, positions_are_f32=positions_are_f32,
+                                                              ei_hint=hint, no_hint=_batch_skips_hint(self.grid, hint))  # fmt: skip
         if particles is not None:
             from .statuscodes import StatusCode
 
@@ -249,6 +251,8 @@ class _ExtraGrid:
     def __init__(self, grid, time_s):
         self.grid, self.time_s = grid, time_s
         self.fields = []
+        self.vector = None  # (U, V, W or None) Field objects of a vector field on this grid: device slots 0..2
+        self.vector_interp, self.offsets = None, (1, 1, 0)
         self._engines = {}
 
     def engine(self, device: int = 0) -> Engine:
@@ -261,7 +265,10 @@ class _ExtraGrid:
                                             g.get_spatial_hash())  # fmt: skip
             else:
                 eng.upload_rectilinear_grid(g.lon, g.lat, g.depth, self.time_s, g.is_spherical(), g.deg2m, g.xdim, g.ydim, g.zdim)
-            eng.set_interpolation(INTERP_METHODS["cgrid_velocity" if g.curvilinear else "linear"], 1, 1, 0)
+            eng.set_interpolation(INTERP_METHODS[self.vector_interp or ("cgrid_velocity" if g.curvilinear else "linear")], *self.offsets)
+            for slot, f in enumerate(self.vector or ()):
+                if f is not None:
+                    eng.upload_field(slot, f.data)
             for f in self.fields:
                 eng.upload_field(f._slot, f.data)
             self._engines[device] = eng
@@ -435,6 +442,42 @@ class FieldSet:
         for eng in host._engines.values():
             eng.upload_field(f._slot, data)
         return f
+
+    def add_vector_field(self, name, U, V, W=None, *, grid, interp_method="linear", padding=("low", "low", "high"), time=None):
+        """A further VectorField on ANOTHER XGrid of the FieldSet (reference: any ``VectorField(name, U, V[, W])`` of the fieldset,
+        e.g. a wind field on the atmospheric model's grid, _core/field.py:205-248), for sampling in user kernels --
+        ``fieldset.<name>[particles]`` / ``.eval(t, z, y, x)`` -> (u, v[, w]) in the units ``fieldset.UV`` gives (degrees per second on
+        a spherical mesh).  The advection kernels keep using ``fieldset.UV`` / ``UVW`` on the velocity grid."""
+        if not isinstance(grid, XGrid) or grid is self.grid:
+            raise ValueError("add_vector_field needs an XGrid other than the velocity grid (fieldset.UV is the vector field of that one)")
+        if name in self.fields:
+            raise ValueError(f"FieldSet already has a Field with name '{name}'")
+        if interp_method not in INTERP_METHODS or (grid.curvilinear and interp_method not in ("cgrid_velocity", "linear")):
+            raise NotImplementedError(f"interp_method {interp_method!r} on this grid")
+        time_s = self._time_s if time is None else _to_seconds(time)[0]
+        host = next((x for x in self._extra_grids if x.grid is grid), None)
+        if host is None:
+            host = _ExtraGrid(grid, time_s)
+            self._extra_grids.append(host)
+        elif host.vector is not None:
+            raise NotImplementedError("one vector field per grid")
+        elif host._engines:
+            raise NotImplementedError("add the vector field of a grid before its fields are first sampled")
+        comps = []
+        for cname, arr in (("U", U), ("V", V), ("W", W)):
+            if arr is None:
+                comps.append(None)
+                continue
+            arr = np.ascontiguousarray(arr)
+            if arr.ndim != 4 or arr.dtype not in (np.float32, np.float64):
+                raise ValueError(f"{name}.{cname} must be a float32 / float64 array laid out (T, Z, Y, X)")
+            comps.append(Field(f"{name}_{cname}", arr, grid, self, interp_method="linear", slot=len(comps), host=host))
+        host.vector, host.vector_interp = tuple(comps), interp_method
+        host.offsets = tuple(int(p == "low") for p in padding)
+        vf = VectorField(name, comps[0], comps[1], comps[2], host=host)
+        self.fields[name] = vf
+        setattr(self, name, vf)
+        return vf
 
     def add_context(self, name, value):
         """reference _core/fieldset.py:207-222; the value is then also an attribute (``fieldset.<name>``, :101-108)."""

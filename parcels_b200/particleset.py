@@ -612,9 +612,13 @@ class ParticleSet:
         if d["ei"].shape[1] > 1:
             d["ei"][:, 1:] = 0
         for k, host in enumerate(self.fieldset._extra_grids, start=1):  # further XGrids: the search of one of their fields
-            f = host.fields[0]
-            _, ei_k, _ = host.engine(self.device).sample_scalar(f._slot, f.interp_method, np.zeros(len(self)), d["z"], d["y"], d["x"],
-                                                                 positions_are_f32=True, ei_hint=None)  # fmt: skip
+            if host.vector is not None:
+                *_, ei_k, _ = host.engine(self.device).sample_velocity(np.zeros(len(self)), d["z"], d["y"], d["x"], three_d=False,
+                                                                        positions_are_f32=True, ei_hint=None, no_hint=True)  # fmt: skip
+            else:
+                f = host.fields[0]
+                _, ei_k, _ = host.engine(self.device).sample_scalar(f._slot, f.interp_method, np.zeros(len(self)), d["z"], d["y"], d["x"],
+                                                                     positions_are_f32=True, ei_hint=None)  # fmt: skip
             d["ei"][:, k] = ei_k
         self._device_synced = False
 

@@ -91,3 +91,29 @@ def test_mixed_kernel_list_with_a_field_on_a_second_grid():
     for k in "xyz":
         assert ulp_diff_f32(ps._data[k], pd[k]).max() <= 2, k
     assert np.abs(ps._data["w10"]).max() > 0
+
+
+def test_vector_field_on_a_second_grid_samples_like_the_oracle():
+    """A wind-like VectorField on its own (coarser, 2-D) grid next to the ocean velocities: `fieldset.wind[particles]` in a user
+    kernel, values / cells / states against the oracle's eval_uvw on that grid."""
+    fs, ofs1, _, _, (x, y, z), times = _setup(False)
+    rng = np.random.default_rng(9)
+    g3 = XGrid(np.linspace(-2, 12, 8), np.linspace(38, 52, 6), None, mesh="spherical")
+    U10 = rng.uniform(-8, 8, (3, 1, 6, 8)).astype(np.float32)
+    V10 = rng.uniform(-8, 8, (3, 1, 6, 8)).astype(np.float32)
+    fs.add_vector_field("wind10", U10, V10, grid=g3)
+    assert len(fs.gridset) == 3
+    ps = pb.ParticleSet(fs, x=x, y=y, z=z, t=np.zeros(len(x)))
+    tq = np.full(len(x), 2000.0)
+    u, v = fs.wind10.eval(tq, ps._data["z"], ps._data["y"], ps._data["x"], ps)
+    og = po.OGrid(g3.lon, g3.lat, None, mesh="spherical")
+    ofs = po.OFieldSet(og, U10, V10, None, time=times, interp="linear")
+    pd = po.create_particle_data(x, y, z, np.zeros(len(x)), ngrids=3)
+    view = po.View(pd, np.ones(len(x), dtype=bool))
+    ou, ov = po.eval_uvw(ofs, tq, pd["z"], pd["y"], pd["x"], view, False)
+    np.testing.assert_array_equal(ps._data["ei"][:, -1], pd["ei"][:, -1])
+    np.testing.assert_array_equal(ps._data["state"], pd["state"])
+    scale = float(np.abs(ou).max())
+    assert np.abs(u - ou).max() <= 4 * np.finfo(np.float32).eps * scale and np.abs(v - ov).max() <= 4 * np.finfo(np.float32).eps * scale
+    ps.populate_indices()
+    assert ps._data["ei"].shape[1] == 3 and np.array_equal(ps._data["ei"][:, 2], pd["ei"][:, -1])
