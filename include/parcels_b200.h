@@ -411,6 +411,7 @@ int32_t pb_debug_normals(pb_engine* e, uint64_t seed, uint64_t rng_call, int64_t
  * helpers split the column over a few host threads (memory-bandwidth bound).  No engine, no device. */
 int32_t pb_host_fill_f64(double* p, int64_t n, double value);
 int32_t pb_host_fill_i32(int32_t* p, int64_t n, int32_t value);
+int32_t pb_host_copy_strided_i32(int32_t* dst, int64_t dst_stride, const int32_t* src, int64_t src_stride, int64_t n); /* strides in elements */
 /* min and max of p[0..n) ignoring NaNs; *has_nan = 1 when any element is NaN (NumPy's min / max then return NaN);
  * n == 0: *mn = +inf, *mx = -inf */
 int32_t pb_host_min_max_f64(const double* p, int64_t n, double* mn, double* mx, int32_t* has_nan);

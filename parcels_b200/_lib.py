@@ -163,6 +163,7 @@ SYMBOLS = {
     "pb_host_fill_f64": (C.c_int32, [_P, C.c_int64, C.c_double]),
     "pb_host_fill_i32": (C.c_int32, [_P, C.c_int64, C.c_int32]),
     "pb_host_min_max_f64": (C.c_int32, [_P, C.c_int64, _P, _P, _P]),
+    "pb_host_copy_strided_i32": (C.c_int32, [_P, C.c_int64, _P, C.c_int64, C.c_int64]),
     "pb_host_count_keep": (C.c_int64, [_P, C.c_int64, C.c_int32]),
     "pb_host_compact": (C.c_int32, [_P, C.c_int64, C.c_int32, C.c_int32, _P, _P, _P]),
 }

@@ -1740,6 +1740,14 @@ int32_t pb_host_fill_i32(int32_t* p, int64_t n, int32_t value) {
     return PB_OK;
 }
 
+// dst[i * dst_stride] = src[i * src_stride] (strides in elements): the last column of a FieldSet with several grids' `ei` (N, ngrids)
+// to / from the contiguous column the device transfers use
+int32_t pb_host_copy_strided_i32(int32_t* dst, int64_t dst_stride, const int32_t* src, int64_t src_stride, int64_t n) {
+    if (n < 0 || (n && (!dst || !src)) || dst_stride < 1 || src_stride < 1) return fail(PB_ERR_INVALID, "bad argument");
+    host_parallel(n, [=](int, int64_t lo, int64_t hi) { for (int64_t i = lo; i < hi; ++i) dst[i * dst_stride] = src[i * src_stride]; });
+    return PB_OK;
+}
+
 int32_t pb_host_min_max_f64(const double* p, int64_t n, double* mn, double* mx, int32_t* has_nan) {
     if (n < 0 || (n && !p) || !mn || !mx || !has_nan) return fail(PB_ERR_INVALID, "bad argument");
     double lo_[8], hi_[8];
