@@ -11,7 +11,9 @@
 //  * Everything a lane caches lives in SHARED MEMORY as 16-byte columns ([chunk][lane]: LDS.128 / STS.128, conflict-free): the raw
 //    2x2x2x2 block (float32), the T-LERPED block (float64: the sample time of stage 3 equals stage 2's and stage 1's equals the
 //    previous step's stage 4, so the 24 time lerps are done twice per step instead of four times), the cells {lo, hi} of z, y,
-//    x, t, the reciprocals of their widths and the cell indices = 496 B per lane, 384 lanes per SM.  The cells are re-read at
+//    x, t, the reciprocals of their widths and the cell indices = 560 B per lane, 384 lanes per SM.  The raw block holds the corner
+//    NODE RECORDS {u, v, w, 0} as the refill loads them (transposing them into per-component chunks was 48 register moves per cell
+//    change); the T-lerp reads two corners' records at a time and feeds the Z-lerp / bilinear sum directly.  The cells are re-read at
 //    every evaluation (volatile loads): they only change in the side path, and keeping them in registers costs moves and spills.
 //  * A refill reads the NODE-INTERLEAVED copy of U, V, W ({u, v, w, 0} per node, built on the device at upload,
 //    interleave_kernel below): 16 x 16-byte loads instead of 48 scattered 4-byte ones, a fifth of the DRAM traffic.
@@ -96,12 +98,13 @@ __device__ __forceinline__ double axis_bcoord(int n, double x, const AxisCell<do
 // node of the time / depth axis -- lenT or lenZ == 1 for this particle): agrid.cuh's xlinear, the all-float64 path.  Out of line:
 // it is rare, and keeping its 16-value block out of the hot kernel's register allocation matters more than a call.
 template <int NV>
-__device__ __noinline__ double special_component(const float4* col, double tau, double zeta, double eta, double xsi, int two_t, int two_z) {
+__device__ __noinline__ double special_component(const float4* raw, int comp, double tau, double zeta, double eta, double xsi, int two_t,
+                                                 int two_z) {
     float blk[16];
 #pragma unroll
-    for (int j = 0; j < NV / 4; ++j) {
-        const float4 r = col[j * PB_FAST_BLOCK];
-        blk[4 * j] = r.x; blk[4 * j + 1] = r.y; blk[4 * j + 2] = r.z; blk[4 * j + 3] = r.w;
+    for (int k = 0; k < NV; ++k) {  // record k = (t * 2 + z) * 4 + y * 2 + x (NV 16) | t * 4 + y * 2 + x (NV 8)
+        const float4 r = raw[k * PB_FAST_BLOCK];
+        blk[k] = comp == 0 ? r.x : (comp == 1 ? r.y : r.z);
     }
     if (NV == 8) {  // (t, y, x) -> the generic (t, z, y, x) order with the one depth level twice
 #pragma unroll
@@ -150,7 +153,7 @@ struct AFastPolicy {
     static constexpr int NC = NC_;
     static constexpr int NV = HZ ? 16 : 8;          // raw values per component: (t, [z,] y, x) corners
     static constexpr int NL = NV / 2;               // T-lerped values per component
-    static constexpr int RAW_CHUNKS = NC * NV / 4;  // float4 columns
+    static constexpr int RAW_CHUNKS = NV;           // float4 columns: the corner NODE RECORDS {u, v, w, 0} as loaded (no transposition)
     static constexpr int LRP_CHUNKS = NC * NL / 2;  // double2 columns
     static constexpr int CELL_CHUNKS = 4;           // double2 columns {lo, hi}: z, y, x, t
     static constexpr int RCP_CHUNKS = 2;            // {1 / dz, 1 / dy}, {1 / dx, 1 / dt} of the current cells
@@ -211,19 +214,12 @@ struct AFastPolicy {
         const float4* __restrict__ base = (const float4*)f.il;
 #pragma unroll
         for (int pl = 0; pl < NV / 4; ++pl) {
-            // chunk pl of a component holds k = 4 pl .. 4 pl + 3,  k = (t * 2 + z) * 4 + y * 2 + x (HZ) | t * 4 + y * 2 + x
+            // records k = 4 pl .. 4 pl + 3,  k = (t * 2 + z) * 4 + y * 2 + x (HZ) | t * 4 + y * 2 + x: stored as they are loaded
             const long long o = ot[HZ ? (pl >> 1) : pl] + (HZ ? oz[pl & 1] : 0);
-            const float4 n00 = ldg(base + o + oy[0] + ox[0]), n01 = ldg(base + o + oy[0] + ox[1]);
-            const float4 n10 = ldg(base + o + oy[1] + ox[0]), n11 = ldg(base + o + oy[1] + ox[1]);
-            float4 q;
-            q.x = n00.x; q.y = n01.x; q.z = n10.x; q.w = n11.x;
-            raw[(0 * (NV / 4) + pl) * PB_FAST_BLOCK] = q;
-            q.x = n00.y; q.y = n01.y; q.z = n10.y; q.w = n11.y;
-            raw[(1 * (NV / 4) + pl) * PB_FAST_BLOCK] = q;
-            if (NC == 3) {
-                q.x = n00.z; q.y = n01.z; q.z = n10.z; q.w = n11.z;
-                raw[(2 * (NV / 4) + pl) * PB_FAST_BLOCK] = q;
-            }
+            raw[(4 * pl + 0) * PB_FAST_BLOCK] = ldg(base + o + oy[0] + ox[0]);
+            raw[(4 * pl + 1) * PB_FAST_BLOCK] = ldg(base + o + oy[0] + ox[1]);
+            raw[(4 * pl + 2) * PB_FAST_BLOCK] = ldg(base + o + oy[1] + ox[0]);
+            raw[(4 * pl + 3) * PB_FAST_BLOCK] = ldg(base + o + oy[1] + ox[1]);
         }
     }
 
@@ -308,9 +304,9 @@ struct AFastPolicy {
             const double eta = axis_bcoord(g.ny, ys, cy), xsi = axis_bcoord(g.nx, xs, cx);
             const bool two_t = tau > 0;             // lenT, per particle (float64 grid: no dtype depends on the batch)
             const bool two_z = HZ && !(zeta <= 0);  // lenZ, per particle (a NaN depth must poison the value)
-            double u = special_component<NV>(raw, tau, zeta, eta, xsi, two_t, two_z);
-            double v = special_component<NV>(raw + (NV / 4) * PB_FAST_BLOCK, tau, zeta, eta, xsi, two_t, two_z);
-            double w = NC == 3 ? special_component<NV>(raw + 2 * (NV / 4) * PB_FAST_BLOCK, tau, zeta, eta, xsi, two_t, two_z) : 0.0;
+            double u = special_component<NV>(raw, 0, tau, zeta, eta, xsi, two_t, two_z);
+            double v = special_component<NV>(raw, 1, tau, zeta, eta, xsi, two_t, two_z);
+            double w = NC == 3 ? special_component<NV>(raw, 2, tau, zeta, eta, xsi, two_t, two_z) : 0.0;
             if (g.spherical) spherical(g, k == 0, ys, u, v);
             if (u != u || v != v || w != w) s = max(s, (int)PB_ERROR_INTERPOLATION);
             if (xi < 0 || yi < 0 || zi < 0) { u = 0.0; v = 0.0; w = 0.0; }
@@ -382,26 +378,39 @@ struct AFastPolicy {
         if (lerp_now) {
             const double tau = div_by_cached(ts - bt.x, bt.y - bt.x, r_xt.y);
             const double omt = 1 - tau;
+            // two corners (y, x) at a time: their node records at both depth and both time levels -> the T-lerp of every component
+            // (_xinterpolators.py:135-139), stored pairwise into the T-lerped block, then straight on: Z-lerp (:141-145) and the
+            // bilinear sum (:147-152) accumulated corner by corner in the reference's left-to-right order
+            constexpr int NZ = HZ ? 2 : 1;
+            const double wgt[4] = {w00, w01, w10, w11};
 #pragma unroll
-            for (int c = 0; c < NC; ++c) {
-                float lo_t[NL], hi_t[NL];
+            for (int pr = 0; pr < 2; ++pr) {
+                double L[3][NZ][2];
 #pragma unroll
-                for (int j = 0; j < NL / 4; ++j) {
-                    const float4 a = raw[(c * (NV / 4) + j) * PB_FAST_BLOCK];
-                    const float4 b = raw[(c * (NV / 4) + NL / 4 + j) * PB_FAST_BLOCK];
-                    lo_t[4 * j] = a.x; lo_t[4 * j + 1] = a.y; lo_t[4 * j + 2] = a.z; lo_t[4 * j + 3] = a.w;
-                    hi_t[4 * j] = b.x; hi_t[4 * j + 1] = b.y; hi_t[4 * j + 2] = b.z; hi_t[4 * j + 3] = b.w;
+                for (int zz = 0; zz < NZ; ++zz) {
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int k = zz * 4 + 2 * pr + h;  // corner (z, y, x) within a time level
+                        const float4 a = raw[k * PB_FAST_BLOCK], b = raw[(NL + k) * PB_FAST_BLOCK];
+                        L[0][zz][h] = (double)a.x * omt + (double)b.x * tau;
+                        L[1][zz][h] = (double)a.y * omt + (double)b.y * tau;
+                        if (NC == 3) L[2][zz][h] = (double)a.z * omt + (double)b.z * tau;
+                    }
+#pragma unroll
+                    for (int c = 0; c < NC; ++c) {
+                        double2 d;
+                        d.x = L[c][zz][0]; d.y = L[c][zz][1];
+                        lp[(c * (NL / 2) + (zz * 4 + 2 * pr) / 2) * PB_FAST_BLOCK] = d;
+                    }
                 }
-                double L[NL];
 #pragma unroll
-                for (int j = 0; j < NL; ++j) L[j] = (double)lo_t[j] * omt + (double)hi_t[j] * tau;  // _xinterpolators.py:135-139
+                for (int c = 0; c < NC; ++c) {
 #pragma unroll
-                for (int j = 0; j < NL / 2; ++j) {
-                    double2 d;
-                    d.x = L[2 * j]; d.y = L[2 * j + 1];
-                    lp[(c * (NL / 2) + j) * PB_FAST_BLOCK] = d;
+                    for (int h = 0; h < 2; ++h) {
+                        const double r = HZ ? L[c][0][h] * omz + L[c][NZ - 1][h] * zeta : L[c][0][h];
+                        q[c] = (pr == 0 && h == 0) ? wgt[0] * r : q[c] + wgt[2 * pr + h] * r;
+                    }
                 }
-                q[c] = zxy(L, zeta, omz, w00, w01, w10, w11);
             }
             e.lerp_t = ts;
         } else {
