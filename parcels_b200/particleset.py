@@ -719,6 +719,11 @@ class ParticleSet:
                                  batch_levels=two_levels)  # fmt: skip
 
         needs_upload = not on_device and not (resident and self._device_synced and eng.particle_count() == n)
+        if not on_device and self.__dict__.get("_dt_pending") is not None and not (
+                needs_upload and self.pipeline_chunks > 1 and n >= self.PIPELINE_MIN_PARTICLES and plan.advdiff is None
+                and self.fieldset.time_window is None):  # fmt: skip
+            _fill(d["dt"], self.__dict__.pop("_dt_pending"))  # (not the pipelined path: the deferred fill is done here)
+            self.__dict__["_dt_filled"] = (d["dt"], dt)
         # host arrays in (and out): cut into chunks whose copies run under the kernels of the other chunks (pb_advect_host)
         pipelined = (needs_upload and self.pipeline_chunks > 1 and n >= self.PIPELINE_MIN_PARTICLES and plan.advdiff is None
                      and self.fieldset.time_window is None)  # fmt: skip
@@ -737,7 +742,18 @@ class ParticleSet:
         elif pipelined:
             # the result comes back with the same call when somebody is going to read it on the host anyway
             downloaded = not lazy or self.eager_host
-            rep = eng.advect_host(args(), d, ei_last, download=downloaded, n_chunks=self.pipeline_chunks)
+            filler = None
+            if self.__dict__.pop("_dt_pending", None) is not None:  # the deferred `particles.dt = dt` under the GPU work
+                import threading
+
+                filler = threading.Thread(target=_fill, args=(d["dt"], dt))
+                filler.start()
+                self.__dict__["_dt_filled"] = (d["dt"], dt)
+            try:
+                rep = eng.advect_host(args(), d, ei_last, download=downloaded, n_chunks=self.pipeline_chunks)
+            finally:
+                if filler is not None:
+                    filler.join()
         else:
             rep = eng.advect(args())
         if rep["n_error"] > 0 and self.fieldset.time_window is None:
@@ -902,10 +918,16 @@ class ParticleSet:
             assert sign_dt in (-1, 1)
         except (ValueError, TypeError, AssertionError) as e:
             raise ValueError(f"dt must be a non-zero datetime.timedelta or np.timedelta64 object, got {dt=!r}") from e
-        _fill(self._data["dt"], dt)
-        # (the fused device kernels leave this column alone: `_fill_dt` need not write it again at the end of Kernel.execute;
-        #  a plan with user kernels or RK45 may write per-particle steps into it -- no mark then)
-        self.__dict__["_dt_filled"] = (self._data["dt"], dt) if not plan.stepwise and plan.rk45 is None else None
+        # `particles.dt = dt` (particleset.py:414).  The fused device kernels never read or write this host column, so for them the
+        # 80 MB pass per 1e7 particles is taken off the critical path: a large set's column is filled by a helper thread WHILE the first
+        # pipelined Kernel.execute runs on the GPU (`_dt_pending` -> `_kernel_execute`); `_fill_dt` need not write it again at the end
+        # (`_dt_filled`).  Plans with user kernels or RK45 read / write per-particle steps: filled here, no mark.
+        fused = not plan.stepwise and plan.rk45 is None
+        if fused and len(self) >= self.PIPELINE_MIN_PARTICLES and not self._host_stale:
+            self.__dict__["_dt_pending"] = dt
+        else:
+            _fill(self._data["dt"], dt)
+            self.__dict__["_dt_filled"] = (self._data["dt"], dt) if fused else None
         if runtime is not None:
             try:
                 runtime = _to_float_seconds(runtime)
@@ -984,6 +1006,8 @@ class ParticleSet:
         finally:
             self.__dict__.pop("_t_nan_free", None)
             self.__dict__.pop("_dt_filled", None)
+            if self.__dict__.pop("_dt_pending", None) is not None and not self._host_stale:  # (no Kernel.execute ran: runtime 0)
+                _fill(self._data["dt"], dt)
             if output_file is not None and hasattr(output_file, "close"):  # `with output_file:` (particleset.py:444)
                 output_file.close()
         if self.eager_host and self._host_stale:

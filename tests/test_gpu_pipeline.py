@@ -86,3 +86,34 @@ def test_chunking_edge_sizes(monkeypatch):
             assert len(got) == len(ref)
             for k in KEYS:
                 np.testing.assert_array_equal(got._data[k], ref._data[k], err_msg=f"{k} n={n} chunks={chunks}")
+
+
+def test_dt_column_after_execute_with_the_deferred_fill():
+    """`particles.dt = dt` (reference _core/particleset.py:414, kernel.py:225-226): for fused plans on large sets the host column is
+    filled by a helper thread under the first pipelined launch -- whatever path execute() takes, the column must hold dt afterwards
+    (pipelined eager / lazy, a zero-length run, a backward run) and a user kernel must see it filled up front."""
+    import bench
+
+    f = bench.c2_field(nx=60, ny=40, nz=6, nt=3)
+    fs = pb.FieldSet.from_arrays(lon=f["lon"], lat=f["lat"], depth=f["depth"], time=f["times"], U=f["U"], V=f["V"], W=f["W"], mesh="spherical")
+    n = 300_000
+    p = bench.c2_particles(f, n, 1)
+    for eager in (True, False):
+        ps = pb.ParticleSet(fs, x=p["x"], y=p["y"], z=p["z"], t=p["t"], seed=1)
+        ps.eager_host = eager
+        ps._data["dt"][:] = 123.0
+        ps.execute([pb.AdvectionRK4_3D, pb.DeleteParticle], dt=600.0, runtime=600.0)
+        assert np.all(ps._data["dt"] == 600.0) and "_dt_pending" not in ps.__dict__
+        ps._data["dt"][:] = 5.0
+        ps.execute([pb.AdvectionRK4_3D, pb.DeleteParticle], dt=300.0, runtime=0.0)
+        assert np.all(ps._data["dt"] == 300.0)
+        ps.execute([pb.AdvectionRK4_3D, pb.DeleteParticle], dt=-300.0, runtime=300.0)
+        assert np.all(ps._data["dt"] == -300.0)
+    ps = pb.ParticleSet(fs, x=p["x"][:1000], y=p["y"][:1000], z=p["z"][:1000], t=p["t"][:1000])
+    seen = []
+
+    def K(particles, fieldset):
+        seen.append(np.unique(np.asarray(particles.dt)).tolist())
+
+    ps.execute([pb.AdvectionRK4_3D, K], dt=600.0, runtime=600.0)
+    assert seen and seen[0] == [600.0]
