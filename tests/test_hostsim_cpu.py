@@ -99,3 +99,29 @@ def test_domain_decomposed_diffusion_statistics_on_the_host_compiled_kernels():
            "--master-port", "29642", os.path.join(ROOT, "scripts", "decomposed_check.py"), "--same-gpu", "--particles", "3000", "--diffusion"]  # fmt: skip
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT, env=_env(lib))
     assert r.returncode == 0 and "PASS statistics" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_in_kernel_migration_logic_on_the_host_compiled_kernels():
+    """Mode D over peer memory: the advection kernel delivers leavers into the new owner's inbox itself.  CUDA IPC needs real devices,
+    so the kernel / inbox / finish LOGIC runs here with three slab engines of one process linked by address (incl. a 50-record inbox
+    that overflows); the cross-process mapping is covered on the GPU box (tests/test_gpu_decomposed.py, bench.py's bitexact_check)."""
+    from oracle.hostsim import build as hb
+
+    lib = hb.build()
+    cmd = [sys.executable, "-m", "pytest", "tests/test_gpu_decomposed.py", "-m", "gpu", "-q", "-x", "-p", "no:cacheprovider", "-k",
+           "three_slabs_one_process"]  # fmt: skip
+    res = subprocess.run(cmd, cwd=ROOT, env=_env(lib), capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0 and "2 passed" in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]
+
+
+def test_peer_memory_transport_falls_back_to_the_collectives_on_every_rank():
+    """A rank that cannot map a peer's inbox (here: no CUDA IPC in the host simulation) must not leave the others waiting: all ranks
+    agree -- one all-gather -- to stay on the collective transport, and the run is still bit-exact (distributed.connect_p2p)."""
+    from oracle.hostsim import build as hb
+
+    lib = hb.build()
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29643", os.path.join(ROOT, "scripts", "decomposed_check.py"), "--same-gpu", "--particles", "3000",
+           "--transport", "p2p"]  # fmt: skip
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT, env=_env(lib))
+    assert r.returncode == 0 and "PASS bit-exact" in r.stdout and "transport=collectives" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
