@@ -76,6 +76,19 @@ def test_differential_fuzz_of_sampling_rk45_and_advection_diffusion():
     assert res.stdout.strip().endswith("70 cases, 0 with differences"), res.stdout[-3000:]
 
 
+def test_differential_fuzz_of_the_round_two_paths():
+    """80 random cases of what round 2 added (scripts/fuzz_hostsim_r2.py): RK4 / Euler behind the curvilinear search (A-grid bilinear
+    and C-grid), scalar Field.eval on curvilinear meshes (XLinear and the C-grid tracer rules), AdvectionDiffusionM1 / EM on a C-grid
+    velocity, fields on a second grid inside one kernel list, and the in-kernel migration records of the peer-memory transport."""
+    from oracle.hostsim import build as hb
+
+    lib = hb.build()
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "fuzz_hostsim_r2.py"), "80", "2026"], cwd=ROOT, env=_env(lib),
+                         capture_output=True, text=True, timeout=900)  # fmt: skip
+    assert res.returncode == 0, res.stderr[-2000:]
+    assert res.stdout.strip().endswith("80 cases, 0 with differences"), res.stdout[-3000:]
+
+
 def test_domain_decomposed_migration_on_the_host_compiled_kernels():
     """Mode D (X-slab decomposition, classify / pack / compact / unpack kernels, gloo all-to-all of the 48-byte records): 2 ranks,
     each with its own simulated engine, reproduce the single-engine trajectories bit for bit (scripts/decomposed_check.py)."""
