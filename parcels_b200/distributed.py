@@ -18,6 +18,11 @@ Two transports:
 
 Trajectories are bit-identical to a single-GPU run either way because every particle-step sees the same grid
 values (the slab is a slice of the global axis; ``ei`` stays global).
+
+Time-slab streaming composes with mode D (``DecomposedFieldSet(..., time_window=W)``): every rank keeps W time levels of ITS slab
+in HBM and all ranks slide their windows in lock-step -- to the earliest time any particle anywhere waits at, and only once a
+round moved nobody (an arrival then always finds the levels it left with) -- so the host side of a rank reads only its own
+columns of each level (``_SlabLevels``), and the next level is copied while the kernel runs, as on one GPU.
 """
 
 from __future__ import annotations
@@ -104,20 +109,40 @@ def route_counts(x, bounds) -> np.ndarray:
     return np.clip(np.searchsorted(b[1:-1], x, side="right"), 0, len(b) - 2)
 
 
+class _SlabLevels:
+    """The X-slab of a (T, Z, Y, X) array-like, cut ONE TIME LEVEL AT A TIME: what a time-windowed FieldSet indexes
+    (``data[level]``).  The parent may be an ``np.memmap`` or any lazy loader -- a rank never reads another rank's columns."""
+
+    def __init__(self, parent, sl: slice):
+        self._parent, self._sl = parent, sl
+        T, Z, Y, X = parent.shape
+        self.shape = (T, Z, Y, len(range(*sl.indices(X))))
+        self.dtype = np.dtype(parent.dtype)
+
+    def __len__(self):
+        return self.shape[0]
+
+    def __getitem__(self, level):
+        return np.ascontiguousarray(np.asarray(self._parent[level])[..., self._sl])
+
+
 class DecomposedFieldSet:
-    """This rank's X-slab of a rectilinear A-grid FieldSet, resident on ``device``."""
+    """This rank's X-slab of a rectilinear A-grid FieldSet, resident on ``device`` (``time_window=W``: only W time levels of it)."""
 
     def __init__(self, *, lon, lat, U, V, W=None, depth=None, time=None, mesh="spherical", rank, world, halo_cells=4,
-                 device=0):  # fmt: skip
+                 device=0, time_window=None):  # fmt: skip
         from .fieldset import FieldSet
 
         self.rank, self.world, self.device = rank, world, device
         self.plan = slab_plan(lon, world, halo_cells)[rank]
         lo, hi = self.plan["lo"], self.plan["hi"]
         sl = slice(lo, hi + 1)
+        if time_window is None:
+            cut = lambda a: np.ascontiguousarray(np.asarray(a)[..., sl])  # noqa: E731
+        else:
+            cut = lambda a: _SlabLevels(a, sl)  # noqa: E731
         self.fs = FieldSet.from_arrays(lon=np.ascontiguousarray(np.asarray(lon)[sl]), lat=lat, depth=depth, time=time,
-                                       U=np.ascontiguousarray(np.asarray(U)[..., sl]), V=np.ascontiguousarray(np.asarray(V)[..., sl]),
-                                       W=None if W is None else np.ascontiguousarray(np.asarray(W)[..., sl]), mesh=mesh,
+                                       U=cut(U), V=cut(V), W=None if W is None else cut(W), mesh=mesh, time_window=time_window,
                                        xdim=np.asarray(lon).size - 1)  # fmt: skip  (GLOBAL cell count: ei stays global)
         self._attach()
 
@@ -238,6 +263,38 @@ def _advect_args(eng, plan, dt, endtime, first, seed, rng_call, rounds):
                          kh_spherical=plan.kh_spherical, kh_deg2m=plan.kh_deg2m, seed=seed, rng_call=(int(rng_call) << 20) + rounds)  # fmt: skip
 
 
+def _advect_round(dfs, args, sign):
+    """One launch on the resident particles; with a time-windowed field the next level's H2D copy is started under the kernel."""
+    eng = dfs.engine
+    if dfs.fs.time_window is None:
+        return eng.advect(args)
+    eng.advect_async(args)
+    dfs.fs.prefetch_next(dfs.device, sign)
+    return eng.last_report()
+
+
+def _slide_in_lockstep(dfs, rep, sign, dist, device) -> bool:
+    """Time-windowed field, called after a round in which NO particle moved between ranks: every unfinished particle anywhere now
+    waits for a time level that is not resident.  All ranks slide to the same window -- the one the earliest (latest, backward in
+    time) waiting particle needs -- so that a particle that migrates later finds, on its new owner, the levels it left with.
+    Returns False when nobody waits (the call is complete)."""
+    import torch
+
+    waits = rep["n_wait_window"] > 0
+    t = (rep["wait_t_min"] if sign > 0 else -rep["wait_t_max"]) if waits else np.inf
+    v = torch.tensor([t], dtype=torch.float64, device=device if dist.get_backend() == "nccl" else "cpu")
+    dist.all_reduce(v, op=dist.ReduceOp.MIN)
+    t = float(v.item())
+    if not np.isfinite(t):
+        return False
+    w = dfs.fs._win[dfs.device]
+    before = (w["first"], w["n"])
+    dfs.fs.slide_window(dfs.device, sign * t, sign)
+    if (w["first"], w["n"]) == before:
+        raise RuntimeError(f"time window of {dfs.fs.time_window} levels cannot cover one step: widen time_window")
+    return True
+
+
 def run_decomposed_p2p(dfs: DecomposedFieldSet, plan, dt: float, endtime: float, dist, max_rounds=100000, seed=0, rng_call=1):
     """The rounds of one ``Kernel.execute`` with in-kernel migration: advect (leavers are delivered to their new owners by the
     kernel itself) -> all-reduce of (#movers, halo flag) = the barrier that orders every rank's kernel before anybody reads an
@@ -248,9 +305,10 @@ def run_decomposed_p2p(dfs: DecomposedFieldSet, plan, dt: float, endtime: float,
 
     eng = dfs.engine
     device = _engine_memory_device(dfs.device)
+    sign = 1 if dt > 0 else -1
     stats = dict(rounds=0, migrated=0, particle_steps=0, kernel_ms=0.0, exchange_ms=0.0, transport="peer memory (in-kernel)")
     for _ in range(max_rounds):
-        rep = eng.advect(_advect_args(eng, plan, dt, endtime, stats["rounds"] == 0, seed, rng_call, stats["rounds"]))
+        rep = _advect_round(dfs, _advect_args(eng, plan, dt, endtime, stats["rounds"] == 0, seed, rng_call, stats["rounds"]), sign)
         t0 = time.perf_counter()
         flags = torch.tensor([float(rep["n_migrate"]), float(rep["max_state"] == 99)], dtype=torch.float64,
                              device=device if dist.get_backend() == "nccl" else "cpu")
@@ -265,7 +323,7 @@ def run_decomposed_p2p(dfs: DecomposedFieldSet, plan, dt: float, endtime: float,
         if halo:
             stats["halo_violation"] = True
             raise RuntimeError("halo violation: a stage position left the owned+halo columns; increase halo_cells or reduce dt")
-        if moved == 0:
+        if moved == 0 and not (dfs.fs.time_window is not None and _slide_in_lockstep(dfs, rep, sign, dist, device)):
             break
     return stats
 
@@ -280,17 +338,19 @@ def run_decomposed_resident(dfs: DecomposedFieldSet, plan, dt: float, endtime: f
         return run_decomposed_p2p(dfs, plan, dt, endtime, dist, max_rounds=max_rounds, seed=seed, rng_call=rng_call)
     eng = dfs.engine
     device = _engine_memory_device(dfs.device)
+    sign = 1 if dt > 0 else -1
     stats = dict(rounds=0, migrated=0, particle_steps=0, kernel_ms=0.0, exchange_ms=0.0, transport="collectives (all_to_all_single)")
     first = True
+    rep = None
     for _ in range(max_rounds):
         t0 = time.perf_counter()
         counts = eng.migrate_count()
         total, _ = _exchange(eng, counts, dist, device)
         stats["exchange_ms"] += 1e3 * (time.perf_counter() - t0)
         stats["migrated"] += int(counts.sum())
-        if total == 0 and not first:
+        if total == 0 and not first and not (dfs.fs.time_window is not None and _slide_in_lockstep(dfs, rep, sign, dist, device)):
             break
-        rep = eng.advect(_advect_args(eng, plan, dt, endtime, first, seed, rng_call, stats["rounds"]))
+        rep = _advect_round(dfs, _advect_args(eng, plan, dt, endtime, first, seed, rng_call, stats["rounds"]), sign)
         first = False
         stats["rounds"] += 1
         stats["particle_steps"] += rep["particle_steps"]
@@ -335,5 +395,17 @@ def execute_decomposed(dfs: DecomposedFieldSet, pdata: dict, kernels, dt: float,
     routed to the owners first).  Returns (local particle dict after the call, stats)."""
     plan = decomposed_plan(dfs, kernels)
     upload_decomposed(dfs, pdata, dt)
+    if dfs.fs.time_window is not None:
+        # first window: where the earliest (latest, backward in time) particle of ANY rank starts -- the same on every rank
+        import torch
+
+        sign = 1 if dt > 0 else -1
+        todo = sign * (endtime - pdata["t"]) >= 0
+        t0 = float((sign * pdata["t"][todo]).min()) if todo.any() else np.inf
+        device = _engine_memory_device(dfs.device)
+        v = torch.tensor([t0], dtype=torch.float64, device=device if dist.get_backend() == "nccl" else "cpu")
+        dist.all_reduce(v, op=dist.ReduceOp.MIN)
+        if np.isfinite(float(v.item())):
+            dfs.fs.slide_window(dfs.device, sign * float(v.item()), sign)
     stats = run_decomposed_resident(dfs, plan, dt, endtime, dist, max_rounds=max_rounds, seed=seed, rng_call=rng_call)
     return download_decomposed(dfs, dt, ngrids=pdata["ei"].shape[1]), stats

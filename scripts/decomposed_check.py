@@ -25,6 +25,10 @@ ap.add_argument("--umax", type=float, default=40.0, help="velocity scale: large 
 ap.add_argument("--transport", default="auto", choices=["auto", "p2p", "collective"],
                 help="p2p: in-kernel migration over peer memory (CUDA IPC; default over NCCL); collective: classify / pack / all-to-all")
 ap.add_argument("--inbox", type=int, default=0, help="p2p: records per inbox slot (default: the particle count; small values exercise the overflow path)")
+ap.add_argument("--time-window", type=int, default=0, help="time-slab streaming under mode D: W levels of each slab resident, windows slid in "
+                "lock-step (the undecomposed comparison run keeps every level resident)")
+ap.add_argument("--nt", type=int, default=3, help="time levels of the synthetic field (one day apart)")
+ap.add_argument("--runtime", type=float, default=86400.0)
 ap.add_argument("--diffusion", action="store_true", help="fused DiffusionUniformKh on a field at rest: statistical check (Var = 2 K t)")
 a = ap.parse_args()
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
@@ -34,13 +38,13 @@ if torch.cuda.is_available():  # (not under the host simulation of the test suit
 dist.init_process_group("gloo" if a.same_gpu else "nccl")
 p2p = a.transport == "p2p" or (a.transport == "auto" and not a.same_gpu)
 
-f = bench.c2_field(nx=120, ny=60, nz=12, nt=3)
+f = bench.c2_field(nx=120, ny=60, nz=12, nt=a.nt)
 f["U"] *= np.float32(a.umax)
 f["V"] *= np.float32(a.umax)
 n = a.particles
 rng = np.random.default_rng(7)
 x, y, z = rng.uniform(-175, 175, n), rng.uniform(-70, 70, n), rng.uniform(5, 5000, n)
-dt, runtime = 600.0, 86400.0
+dt, runtime = 600.0, a.runtime
 if a.diffusion:
     # a field at rest and a large constant diffusivity: particles released on the slab boundary (lon 0, equator) diffuse across it
     K, runtime = 1.0e5, 28800.0
@@ -71,7 +75,7 @@ if a.diffusion:
     sys.exit(0 if ok else 1)
 full = create_particle_data(nparticles=n, ngrids=1, initial=dict(x=x, y=y, z=z, t=np.zeros(n), particle_id=np.arange(n)))
 dfs = D.DecomposedFieldSet(lon=f["lon"], lat=f["lat"], depth=f["depth"], time=f["times"], U=f["U"], V=f["V"], W=f["W"],
-                           mesh="spherical", rank=rank, world=world, halo_cells=a.halo, device=dev)
+                           mesh="spherical", rank=rank, world=world, halo_cells=a.halo, device=dev, time_window=a.time_window or None)
 if p2p:
     D.connect_p2p(dfs, dist, a.inbox or n)
 mine = D.shard_particles(full, rank, world)  # arbitrary shard: routed to the owners by the first migration round
@@ -97,7 +101,8 @@ if rank == 0:
                 print("   count", len(bad), "first:", [(int(merged["particle_id"][b]), merged[k][b].tolist(), ref[k][b].tolist(),
                                                         float(merged["x"][b]), float(ref["x"][b])) for b in bad[:6]])
     print(f"decomposed({world} ranks, backend={dist.get_backend()}): {len(ref['x'])} survivors, {int(tot)} migrations, "
-          f"rounds={stats['rounds']}, transport={stats['transport']} -> {'PASS bit-exact' if ok else 'FAIL'}")
+          f"rounds={stats['rounds']}, transport={stats['transport']}"
+          + (f", time window {a.time_window} of {a.nt} levels" if a.time_window else "") + f" -> {'PASS bit-exact' if ok else 'FAIL'}")
 dist.barrier()
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)

@@ -1,0 +1,148 @@
+"""Mode D with IN-KERNEL migration driven by the product's own round loop (distributed.run_decomposed_p2p /
+execute_decomposed) on the host simulation: CUDA IPC needs real devices, so the ranks are THREADS of one process -- each with its
+own engine, inboxes linked by address (pb_migrate_p2p_connect's local bases) -- and ``torch.distributed`` is replaced by a
+thread-barrier stand-in with the same calls.  Engine calls of different ranks are serialised by a lock (the simulated device
+runs a kernel as a loop over global thread / block indices and its atomics are plain host operations).  Checks the merged result
+bit for bit against the undecomposed run; with --time-window the slabs stream their time levels and slide in lock-step while the
+comparison run keeps every level resident.
+Run:  PB_LIB=oracle/_build/hostsim/libparcels_b200_hostsim.so PB_HOSTSIM_TEST=1 python scripts/decomposed_threads_check.py"""
+import argparse
+import os
+import sys
+import threading
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
+import numpy as np
+import torch
+
+import bench
+import parcels_b200 as pb
+from parcels_b200 import distributed as D
+from parcels_b200.particle import create_particle_data
+
+
+class ThreadGroup:
+    """all_reduce over the threads of one process (what run_decomposed_p2p / execute_decomposed ask of torch.distributed)."""
+
+    class ReduceOp:
+        SUM, MIN, MAX = "sum", "min", "max"
+
+    def __init__(self, world):
+        self.world = world
+        self.barrier = threading.Barrier(world)
+        self.slots = [None] * world
+
+    def member(self, rank):
+        group = self
+
+        class Member:
+            ReduceOp = ThreadGroup.ReduceOp
+
+            @staticmethod
+            def get_rank():
+                return rank
+
+            @staticmethod
+            def get_world_size():
+                return group.world
+
+            @staticmethod
+            def get_backend():
+                return "threads"
+
+            @staticmethod
+            def all_reduce(t, op="sum"):
+                group.slots[rank] = t.clone()
+                group.barrier.wait()
+                stack = torch.stack(group.slots)
+                res = stack.sum(0) if op == "sum" else (stack.min(0).values if op == "min" else stack.max(0).values)
+                group.barrier.wait()  # everybody has read the slots before the next collective overwrites them
+                t.copy_(res)
+
+        return Member
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--world", type=int, default=3)
+    ap.add_argument("--particles", type=int, default=3000)
+    ap.add_argument("--inbox", type=int, default=0)
+    ap.add_argument("--time-window", type=int, default=0)
+    ap.add_argument("--nt", type=int, default=3)
+    ap.add_argument("--runtime", type=float, default=86400.0)
+    ap.add_argument("--backward", action="store_true")
+    a = ap.parse_args()
+    world, n = a.world, a.particles
+    f = bench.c2_field(nx=120, ny=60, nz=12, nt=a.nt)
+    f["U"] *= np.float32(40.0)
+    f["V"] *= np.float32(40.0)
+    rng = np.random.default_rng(7)
+    x, y, z = rng.uniform(-175, 175, n), rng.uniform(-70, 70, n), rng.uniform(5, 5000, n)
+    dt = -600.0 if a.backward else 600.0
+    t_start = float(f["times"][-1]) if a.backward else 0.0
+    # staggered releases: particles wait at different times, the lock-step slide has to serve the earliest first
+    t = t_start + np.sign(dt) * rng.choice([0.0, 7200.0, 100800.0], n) if a.time_window else np.full(n, t_start)
+    endtime = t_start + np.sign(dt) * a.runtime
+    kernels = [pb.AdvectionRK4_3D, pb.DeleteParticle]
+    full = create_particle_data(nparticles=n, ngrids=1, initial=dict(x=x, y=y, z=z, t=t, particle_id=np.arange(n)))
+    slabs = [D.DecomposedFieldSet(lon=f["lon"], lat=f["lat"], depth=f["depth"], time=f["times"], U=f["U"], V=f["V"], W=f["W"],
+                                  mesh="spherical", rank=r, world=world, halo_cells=3, device=0, time_window=a.time_window or None)
+             for r in range(world)]  # fmt: skip
+    bases = [s.engine.migrate_p2p_init(a.inbox or n)[1] for s in slabs]
+    for s in slabs:
+        s.engine.migrate_p2p_connect(local_bases=bases)
+        s.p2p = True
+    device_lock = threading.RLock()
+
+    def serialised(method):
+        def call(*args, **kw):
+            with device_lock:
+                return method(*args, **kw)
+
+        return call
+
+    from parcels_b200.engine import Engine
+
+    for name, method in list(vars(Engine).items()):
+        if callable(method) and not name.startswith("__") and not isinstance(method, (staticmethod, classmethod)):
+            setattr(Engine, name, serialised(method))
+    group = ThreadGroup(world)
+    outs, stats, errors = [None] * world, [None] * world, []
+
+    def rank_main(r):
+        try:
+            outs[r], stats[r] = D.execute_decomposed(slabs[r], D.shard_particles(full, r, world), kernels, dt, endtime, group.member(r))
+        except BaseException as e:  # a dead rank would leave the others in the barrier
+            errors.append(e)
+            group.barrier.abort()
+
+    threads = [threading.Thread(target=rank_main, args=(r,)) for r in range(world)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    if errors:
+        raise errors[0]
+    merged = {k: np.concatenate([o[k] for o in outs], axis=0) for k in outs[0]}
+    order = np.argsort(merged["particle_id"], kind="stable")
+    merged = {k: v[order] for k, v in merged.items()}
+    fs = pb.FieldSet.from_arrays(lon=f["lon"], lat=f["lat"], depth=f["depth"], time=f["times"], U=f["U"], V=f["V"], W=f["W"], mesh="spherical")
+    ps = pb.ParticleSet(fs, x=x, y=y, z=z, t=t, device=0)
+    ps.execute(kernels, dt=dt, endtime=endtime)
+    ref = ps._data
+    ok = True
+    for k in ("particle_id", "state", "t", "ei", "x", "y", "z"):
+        same = merged[k].shape == ref[k].shape and np.array_equal(merged[k], ref[k])
+        ok &= same
+        if not same:
+            print(f"MISMATCH {k}: {merged[k].shape} vs {ref[k].shape}")
+    migrated = sum(s["migrated"] for s in stats)
+    print(f"decomposed({world} thread ranks): {len(ref['x'])} survivors, {migrated} migrations, rounds={stats[0]['rounds']}, "
+          f"transport={stats[0]['transport']}" + (f", time window {a.time_window} of {a.nt} levels" if a.time_window else "")
+          + f" -> {'PASS bit-exact' if ok else 'FAIL'}")  # fmt: skip
+    return 0 if ok else 1
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -138,3 +138,33 @@ def test_peer_memory_transport_falls_back_to_the_collectives_on_every_rank():
            "--transport", "p2p"]  # fmt: skip
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT, env=_env(lib))
     assert r.returncode == 0 and "PASS bit-exact" in r.stdout and "transport=collectives" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_time_slab_streaming_under_domain_decomposition():
+    """Mode D on time-windowed slabs (2 of 6 levels resident per rank, windows slid in lock-step, distributed._slide_in_lockstep):
+    bit-exact against the undecomposed run that keeps every level resident.  (a) 2 gloo ranks on the collective transport;
+    (b) the product's own peer-memory round loop (execute_decomposed -> run_decomposed_p2p) with 3 thread ranks whose inboxes are
+    linked by address, staggered releases and a 50-record inbox that overflows; (c) backward in time, 4 ranks, 3 levels."""
+    from oracle.hostsim import build as hb
+
+    lib = hb.build()
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29644", os.path.join(ROOT, "scripts", "decomposed_check.py"), "--same-gpu", "--particles", "2000",
+           "--nt", "6", "--runtime", "345600", "--time-window", "2", "--transport", "collective"]  # fmt: skip
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT, env=_env(lib))
+    assert r.returncode == 0 and "PASS bit-exact" in r.stdout and "time window 2 of 6" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+    threads = [sys.executable, os.path.join(ROOT, "scripts", "decomposed_threads_check.py"), "--nt", "6", "--runtime", "345600"]
+    for extra in (["--inbox", "50", "--time-window", "2"], ["--backward", "--time-window", "3", "--world", "4"]):
+        r = subprocess.run(threads + extra, capture_output=True, text=True, timeout=900, cwd=ROOT, env=_env(lib))
+        assert r.returncode == 0 and "PASS bit-exact" in r.stdout and "peer memory" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+        assert " 0 migrations" not in r.stdout
+
+
+def test_peer_memory_round_loop_on_thread_ranks():
+    """distributed.run_decomposed_p2p itself (not a hand-driven copy of its rounds): 3 thread ranks, resident fields."""
+    from oracle.hostsim import build as hb
+
+    lib = hb.build()
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "decomposed_threads_check.py")], capture_output=True, text=True,
+                       timeout=900, cwd=ROOT, env=_env(lib))  # fmt: skip
+    assert r.returncode == 0 and "PASS bit-exact" in r.stdout and "peer memory" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
