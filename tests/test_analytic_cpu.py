@@ -62,6 +62,36 @@ def test_spatial_hash_known_answers(mesh):
 
 
 @pytest.mark.parametrize("mesh", ["flat", "spherical"])
+def test_nan_node_invalidates_touching_faces(mesh):
+    """reference tests/test_spatialhash.py:125-181: the four faces around a NaN node are not in the table, queries at their centres
+    give -3, every other cell centre still resolves to its own cell.  Oracle table, and the table of the product's host-side
+    build (parcels_b200/spatialhash.py, the one the device table is compared with) -- entry for entry the same."""
+    from parcels_b200.spatialhash import build_spatial_hash
+
+    lon, lat = A.rotated_grid()
+    clat, clon, jj, ii = A.cell_centers(lon, lat)
+    lon, lat = lon.copy(), lat.copy()
+    nj, ni = 10, 10
+    lon[nj, ni] = lat[nj, ni] = np.nan
+    nfx = lon.shape[1] - 1
+    touching = [(nj - 1, ni - 1), (nj - 1, ni), (nj, ni - 1), (nj, ni)]
+    invalid = {j * nfx + i for j, i in touching}
+    h = co.get_hash(po.OGrid(lon, lat, None, mesh=mesh))
+    in_table = set(np.unique(h.faces).tolist())
+    assert invalid.isdisjoint(in_table) and len(in_table) == jj.size - 4
+    j, i, _ = h.query(clat, clon)
+    bad = np.isin(jj * nfx + ii, list(invalid))
+    assert np.all(j[bad] == -3) and np.all(i[bad] == -3)
+    np.testing.assert_array_equal(j[~bad], jj[~bad])
+    np.testing.assert_array_equal(i[~bad], ii[~bad])
+    t = build_spatial_hash(lon, lat, mesh == "spherical", table=True)
+    assert t["bitwidth"] == h.bitwidth and t["n_entries"] == h.faces.size
+    np.testing.assert_array_equal(t["faces"], h.faces)
+    np.testing.assert_array_equal(t["keys"], h.keys)
+    np.testing.assert_array_equal(t["counts"], h.counts)
+
+
+@pytest.mark.parametrize("mesh", ["flat", "spherical"])
 def test_brownian_std(mesh):
     """reference tests/test_diffusion.py:19-46 (DiffusionUniformKh alone, Kh 100/50, 2 h, dt 1 h, N=100, tol 500 m)."""
     conv = 1 / 1852.0 / 60 if mesh == "spherical" else 1

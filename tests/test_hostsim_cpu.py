@@ -168,3 +168,14 @@ def test_peer_memory_round_loop_on_thread_ranks():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "decomposed_threads_check.py")], capture_output=True, text=True,
                        timeout=900, cwd=ROOT, env=_env(lib))  # fmt: skip
     assert r.returncode == 0 and "PASS bit-exact" in r.stdout and "peer memory" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_nan_node_on_the_device_side_hash_build_and_query():
+    """reference tests/test_spatialhash.py:125-181 through the device code (hash build from the per-face boxes + hintless query),
+    flat and spherical: scripts/hash_nan_check.py."""
+    from oracle.hostsim import build as hb
+
+    lib = hb.build()
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "hash_nan_check.py")], capture_output=True, text=True,
+                       timeout=600, cwd=ROOT, env=_env(lib))  # fmt: skip
+    assert r.returncode == 0 and "PASS nan node" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
