@@ -843,6 +843,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip parity_sample / cpu_baseline (the oracle legs)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-mode-d", action="store_true", help="N > 1: skip the domain-decomposed block")
+    ap.add_argument("--mode-d-timeout", type=float, default=0.0, help="N > 1: seconds the domain-decomposed block may take before the "
+                    "mode R line is printed without it (default: max(300, 2 x the time the mode R part took))")
     ap.add_argument("--mode-d-transport", default="p2p", choices=["p2p", "collective"],
                     help="mode D: p2p = in-kernel migration over peer memory (CUDA IPC + NVLink), collective = NCCL all-to-all-v")
     ap.add_argument("--pipeline", type=int, default=-1,
@@ -901,6 +903,7 @@ def main():
     extras = a.extras.split(",") if a.extras else (["c2", "c3", "c4"] if (name == "ns" and world == 1 and a.extras is None) else [])
     extras = [e for e in extras if e and e != name]
     cache = {}
+    t_main = time.perf_counter()
     main_out = run_gpu_workload(a, name, rank=rank, local_rank=local_rank, world=world, dist=dist, steps=a.steps, warmup=a.warmup,
                                 with_e2e=not a.no_e2e, with_cpu=not a.no_cpu_baseline, field_cache=cache)  # fmt: skip
     extra_out = {}
@@ -911,10 +914,33 @@ def main():
             r["config"] = config_block(e, WORKLOADS[e], a.particles or WORKLOADS[e]["n"])
             extra_out[e] = r
     cache.clear()
-    mode_d = None
+    line = None
+    if rank == 0:
+        n_per_gpu = a.particles or w["n"]
+        line = {
+            "metric": METRIC, "value": main_out["value"], "unit": "particle-steps/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": main_out["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": config_block(name, w, n_per_gpu),
+        }  # fmt: skip
+        for k in ("e2e", "gpu_launches", "roofline", "measured", "parity_sample", "cpu_baseline", "cpu_baseline_strong", "clocks"):
+            if k in main_out:
+                line[k] = main_out[k]
+        if a.sorted:
+            line["measured"]["sorted_release"] = True
+        if extra_out:
+            line["extra"] = extra_out
+    mode_d, watchdog = None, None
     if world > 1 and not a.no_mode_d:
         torch.cuda.empty_cache()
-        try:  # (the mode R line above is printed whatever happens in here)
+        # The mode R line is printed whatever happens in this block.  An exception is reported in the line; a rank that dies or
+        # hangs would leave the others inside a collective for good, so a watchdog bounds the block: past the limit rank 0 prints
+        # the mode R line with the reason and every rank leaves (the limit is generous: the block normally takes well under a
+        # minute, and scales with what the mode R part -- full-field generation included -- took on this box).
+        limit = a.mode_d_timeout or max(300.0, 2.0 * (time.perf_counter() - t_main))
+        watchdog = threading.Timer(limit, _leave_mode_d, args=(line, limit))
+        watchdog.daemon = True
+        watchdog.start()
+        try:
             mode_d = run_decomposed_bench(a, rank, local_rank, world, dist, "c5" if name == "ns" else "c5_small")
             chk = decomposed_bitexact_check(rank, local_rank, world, dist, transport=a.mode_d_transport)
             if mode_d is not None:
@@ -923,25 +949,23 @@ def main():
             mode_d = {"error": f"{type(ex).__name__}: {ex}"[:400]} if rank == 0 else None
     if dist is not None:
         dist.barrier()
+        if watchdog is not None:
+            watchdog.cancel()
         dist.destroy_process_group()
     if rank != 0:
         return
-    n_per_gpu = a.particles or w["n"]
-    line = {
-        "metric": METRIC, "value": main_out["value"], "unit": "particle-steps/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-        "ms_per_step": main_out["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic", "config": config_block(name, w, n_per_gpu),
-    }  # fmt: skip
-    for k in ("e2e", "gpu_launches", "roofline", "measured", "parity_sample", "cpu_baseline", "cpu_baseline_strong", "clocks"):
-        if k in main_out:
-            line[k] = main_out[k]
-    if a.sorted:
-        line["measured"]["sorted_release"] = True
-    if extra_out:
-        line["extra"] = extra_out
     if mode_d is not None:
         line["mode_d"] = mode_d
     print(json.dumps(line))
+
+
+def _leave_mode_d(line, limit):
+    """Watchdog of the mode D block of a multi-GPU run (see main): the block did not finish within ``limit`` seconds."""
+    if line is not None:
+        line["mode_d"] = {"error": f"the domain-decomposed block did not finish within {limit:.0f} s (a rank failed or hangs in a collective); "
+                                   "the mode R numbers of this line are complete"}  # fmt: skip
+        print(json.dumps(line), flush=True)
+    os._exit(0)
 
 
 if __name__ == "__main__":
