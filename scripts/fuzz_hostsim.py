@@ -115,6 +115,12 @@ def main():
             ps, err = run_engine(c)
             pd, oerr = run_oracle(c)
         except Exception as e:  # noqa: BLE001
+            if isinstance(e, IndexError) and spec.get("interp") in ("freeslip", "partialslip") and spec["kernels"][0].endswith("_3D"):
+                # the reference's own failure (DESIGN.md waiver 1, last paragraph): a 3-D slip evaluation of a batch with no particle
+                # below the first depth level indexes a depth level that was not gathered (_xinterpolators.py:460-470) -- the oracle
+                # restates it, the engine returns the value
+                print(f"[{k}] known: the reference raises IndexError here (3-D slip, lenZ == 1)")
+                continue
             print(f"[{k}] EXC {type(e).__name__}: {e}\n    spec={spec}")
             bad += 1
             continue
