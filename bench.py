@@ -341,6 +341,16 @@ def dram_traffic_per_launch(workload):
         return None
 
 
+def ncu_limiter(workload):
+    """Issue-slot / FP64-pipe utilisation of the workload's kernel from the committed ncu capture (same file), or None: the
+    byte model of `roofline` assumes no reuse, these say what the kernel is actually bound by."""
+    try:
+        j = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
+        return (j.get("limiter") or {}).get(workload)
+    except Exception:
+        return None
+
+
 # ------------------------------------------------------------------------------------------------
 # CPU legs (oracle port of the reference path): cpu_baseline / parity_sample and the reference arm
 # ------------------------------------------------------------------------------------------------
@@ -643,7 +653,8 @@ def run_gpu_workload(a, name, *, rank, local_rank, world, dist, steps, warmup, w
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": dram_traffic_per_launch(name), "peak_source": peak_src,
                          "algorithmic_bytes_per_particle_step": w["bytes"], "particle_steps_per_launch": steps_per_launch,
-                         **({"note": w["roofline_note"]} if "roofline_note" in w else {})},
+                         **({"note": w["roofline_note"]} if "roofline_note" in w else {}),
+                         **({"limiter_from_ncu": ncu_limiter(name)} if ncu_limiter(name) else {})},
             "clocks": clk.summary(),
         }  # fmt: skip
         if with_cpu and world == 1:
