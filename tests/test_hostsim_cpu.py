@@ -179,3 +179,56 @@ def test_nan_node_on_the_device_side_hash_build_and_query():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "hash_nan_check.py")], capture_output=True, text=True,
                        timeout=600, cwd=ROOT, env=_env(lib))  # fmt: skip
     assert r.returncode == 0 and "PASS nan node" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def _bench_line(stdout):
+    import json
+
+    lines = [ln for ln in stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1, stdout[-2000:]  # ONE JSON line
+    return json.loads(lines[0])
+
+
+def test_bench_control_flow_single_rank():
+    """bench.py's N = 1 flow on the simulated device (scripts/bench_hostsim.py: torch.cuda entry points stubbed, numbers
+    meaningless): the arms run, the line carries every key of the contract, the parity sample agrees with the oracle."""
+    from oracle.hostsim import build as hb
+
+    lib = hb.build()
+    cmd = [sys.executable, os.path.join(ROOT, "scripts", "bench_hostsim.py"), "--workload", "c2_small", "--particles", "1500", "--steps", "3",
+           "--warmup", "3", "--extras", "c3_small"]  # fmt: skip
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT, env=_env(lib))
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-2500:]
+    d = _bench_line(r.stdout)
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype",
+              "data", "config", "e2e", "gpu_launches", "roofline", "cpu_baseline", "parity_sample", "clocks", "extra"):  # fmt: skip
+        assert k in d, k
+    assert d["n_gpus"] == 1 and d["steps"] == 3 and d["gpu_launches"] > 0 and d["value"] > 0 and d["e2e"]["value"] > 0
+    assert d["e2e"]["h2d_bytes_per_step"] == 1500 * 48 and d["e2e"]["d2h_bytes_per_step"] == 1500 * 40
+    assert set(d["roofline"]) >= {"bound", "achieved", "peak", "unit", "frac", "traffic"}
+    assert d["parity_sample"]["ok"] and d["extra"]["c3_small"]["parity_sample"]["ok"]
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] == 1
+
+
+def test_bench_control_flow_two_ranks_and_the_mode_d_watchdog():
+    """bench.py under torchrun (2 ranks, gloo instead of NCCL, both on the simulated device): mode R line + `mode_d` block -- the
+    peer-memory transport is refused by the simulation, every rank agrees on the collectives, the bit-exactness check passes -- and
+    with a 1-second limit the watchdog prints the mode R line with the reason and every rank exits 0."""
+    from oracle.hostsim import build as hb
+
+    lib = hb.build()
+    base = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1"]
+    args = [os.path.join(ROOT, "scripts", "bench_hostsim.py"), "--gpus", "2", "--workload", "c2_small", "--particles", "1500",
+            "--particles-d", "3000", "--steps", "3", "--warmup", "3", "--extras", "", "--no-cpu-baseline"]  # fmt: skip
+    r = subprocess.run(base + ["--master-port", "29646"] + args, capture_output=True, text=True, timeout=900, cwd=ROOT, env=_env(lib))
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-2500:]
+    d = _bench_line(r.stdout)
+    md = d["mode_d"]
+    assert d["n_gpus"] == 2 and "error" not in md, md
+    assert md["transport"].startswith("collectives") and "p2p_unavailable" in md  # the agreed fallback
+    assert md["bitexact_check"]["bit_exact_vs_one_gpu"] is True and md["bitexact_check"]["migrations"] > 0
+    r = subprocess.run(base + ["--master-port", "29647"] + args + ["--mode-d-timeout", "1"], capture_output=True, text=True, timeout=900,
+                       cwd=ROOT, env=_env(lib))  # fmt: skip
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-2500:]
+    d = _bench_line(r.stdout)
+    assert d["value"] > 0 and "did not finish within 1 s" in d["mode_d"]["error"]
