@@ -370,3 +370,22 @@ def test_host_column_passes_match_numpy():
     for k in want:
         assert d[k].shape == want[k].shape and np.array_equal(d[k], want[k]), k
     assert P._remove_deleted_host(d) == 0
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the driver's second arm: the oracle port of the reference path on the host cores, no GPU, no
+    CUDA library): one JSON line with `impl`, the arm's own `cpu_baseline` and an `e2e` that repeats the value with zero copies."""
+    import json
+    import subprocess
+    import sys
+
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "c2_small", "--steps", "2",
+                        "--warmup", "1"], capture_output=True, text=True, timeout=600, cwd=ROOT)  # fmt: skip
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "particle-RK4-steps/sec" and d["value"] > 0 and d["higher_is_better"] is True
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] == d["value"] and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["config"]["kernels"] == ["AdvectionRK4_3D", "DeleteParticle"]
