@@ -232,3 +232,13 @@ def test_bench_control_flow_two_ranks_and_the_mode_d_watchdog():
     assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-2500:]
     d = _bench_line(r.stdout)
     assert d["value"] > 0 and "did not finish within 1 s" in d["mode_d"]["error"]
+
+
+def test_graft_entry_smoke_on_the_simulated_device():
+    """__graft_entry__.smoke() (what the driver runs on cuda:0 before the bench) end to end on the simulated device."""
+    from oracle.hostsim import build as hb
+
+    lib = hb.build()
+    r = subprocess.run([sys.executable, "-c", "import __graft_entry__ as g; g.smoke()"], capture_output=True, text=True, timeout=900,
+                       cwd=ROOT, env=_env(lib))  # fmt: skip
+    assert r.returncode == 0 and "smoke ok" in r.stdout, r.stdout[-1500:] + r.stderr[-2000:]
