@@ -9,58 +9,16 @@ Run:  PB_LIB=oracle/_build/hostsim/libparcels_b200_hostsim.so PB_HOSTSIM_TEST=1 
 import argparse
 import os
 import sys
-import threading
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
+sys.path[:0] = [ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "scripts")]
 import numpy as np
-import torch
 
 import bench
 import parcels_b200 as pb
+import thread_ranks
 from parcels_b200 import distributed as D
 from parcels_b200.particle import create_particle_data
-
-
-class ThreadGroup:
-    """all_reduce over the threads of one process (what run_decomposed_p2p / execute_decomposed ask of torch.distributed)."""
-
-    class ReduceOp:
-        SUM, MIN, MAX = "sum", "min", "max"
-
-    def __init__(self, world):
-        self.world = world
-        self.barrier = threading.Barrier(world)
-        self.slots = [None] * world
-
-    def member(self, rank):
-        group = self
-
-        class Member:
-            ReduceOp = ThreadGroup.ReduceOp
-
-            @staticmethod
-            def get_rank():
-                return rank
-
-            @staticmethod
-            def get_world_size():
-                return group.world
-
-            @staticmethod
-            def get_backend():
-                return "threads"
-
-            @staticmethod
-            def all_reduce(t, op="sum"):
-                group.slots[rank] = t.clone()
-                group.barrier.wait()
-                stack = torch.stack(group.slots)
-                res = stack.sum(0) if op == "sum" else (stack.min(0).values if op == "min" else stack.max(0).values)
-                group.barrier.wait()  # everybody has read the slots before the next collective overwrites them
-                t.copy_(res)
-
-        return Member
 
 
 def main():
@@ -93,37 +51,10 @@ def main():
     for s in slabs:
         s.engine.migrate_p2p_connect(local_bases=bases)
         s.p2p = True
-    device_lock = threading.RLock()
-
-    def serialised(method):
-        def call(*args, **kw):
-            with device_lock:
-                return method(*args, **kw)
-
-        return call
-
-    from parcels_b200.engine import Engine
-
-    for name, method in list(vars(Engine).items()):
-        if callable(method) and not name.startswith("__") and not isinstance(method, (staticmethod, classmethod)):
-            setattr(Engine, name, serialised(method))
-    group = ThreadGroup(world)
-    outs, stats, errors = [None] * world, [None] * world, []
-
-    def rank_main(r):
-        try:
-            outs[r], stats[r] = D.execute_decomposed(slabs[r], D.shard_particles(full, r, world), kernels, dt, endtime, group.member(r))
-        except BaseException as e:  # a dead rank would leave the others in the barrier
-            errors.append(e)
-            group.barrier.abort()
-
-    threads = [threading.Thread(target=rank_main, args=(r,)) for r in range(world)]
-    for th in threads:
-        th.start()
-    for th in threads:
-        th.join()
-    if errors:
-        raise errors[0]
+    thread_ranks.serialise_engine_calls()
+    res = thread_ranks.run_ranks(world, lambda r, dist: D.execute_decomposed(slabs[r], D.shard_particles(full, r, world), kernels, dt,
+                                                                             endtime, dist))  # fmt: skip
+    outs, stats = [o for o, _ in res], [s for _, s in res]
     merged = {k: np.concatenate([o[k] for o in outs], axis=0) for k in outs[0]}
     order = np.argsort(merged["particle_id"], kind="stable")
     merged = {k: v[order] for k, v in merged.items()}

@@ -5,11 +5,13 @@
   advdiff_c AdvectionDiffusionM1 / EM with CGrid_Velocity on rectilinear C-grids (the oracle fed the device's own increments);
   mig       in-kernel migration: 2-5 slab engines of one process linked by address, random inbox capacity (overflow), against the
             undecomposed run, bit for bit;
+  mig_w     the same under time-slab streaming, through distributed.execute_decomposed itself on THREAD ranks (scripts/thread_ranks.py):
+            random window / level count / direction / staggered releases, against the undecomposed resident run;
   multigrid a scalar and a vector field on further XGrids sampled through their own engines.
 Run:  PB_LIB=oracle/_build/hostsim/libparcels_b200_hostsim.so PB_HOSTSIM_TEST=1 python scripts/fuzz_hostsim_r2.py [n] [seed]"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests")); sys.path.insert(0, os.path.join(ROOT, "scripts"))
 import warnings
 import numpy as np
 import cases
@@ -233,6 +235,69 @@ def fuzz_migration(rng):
     return f"migration world={world} n={n} inbox={cap} rounds={rounds}", dict(world=world, n=n, cap=cap), msg
 
 
+def fuzz_migration_windowed(rng):
+    """Time-slab streaming under mode D through the product's own loop (execute_decomposed -> run_decomposed_p2p) on thread ranks:
+    random slab count, window, level count, time direction, inbox capacity and staggered releases, against the undecomposed run
+    with every level resident."""
+    import thread_ranks
+
+    thread_ranks.serialise_engine_calls()
+    world = int(rng.integers(2, 5))
+    n = int(rng.integers(50, 900))
+    nt = int(rng.integers(3, 8))
+    window = int(rng.integers(2, min(nt - 1, 4) + 1))  # (window + 1 prefetch slot <= levels of the field)
+    tstep = 3600.0
+    times = np.arange(nt) * tstep
+    nx = int(rng.integers(30, 60))
+    lon, lat, depth = np.linspace(-40.0, 40.0, nx), np.linspace(-30.0, 30.0, 20), 800.0 * np.linspace(0, 1, 5) ** 1.5
+    shape = (nt, 5, 20, nx)
+    U = (40.0 * rng.uniform(-1, 1, shape)).astype(np.float32)
+    V = (20.0 * rng.uniform(-1, 1, shape)).astype(np.float32)
+    W = (1e-3 * rng.uniform(-1, 1, shape)).astype(np.float32)
+    x, y, z = rng.uniform(-38, 38, n), rng.uniform(-28, 28, n), rng.uniform(5, 700, n)
+    sign = 1 if rng.random() < 0.65 else -1
+    # level-aligned steps when the window is 2 (DESIGN.md 7b: a step that straddles a level samples 3 levels)
+    dt = sign * (float(rng.choice([600.0, 900.0, 1200.0])) if window == 2 else float(rng.choice([600.0, 700.0, 1100.0])))
+    t_start = 0.0 if sign > 0 else float(times[-1])
+    span = float(times[-1])
+    t = t_start + sign * rng.choice([0.0, 0.0, abs(dt) * 3, tstep, 2 * tstep + abs(dt)], n)
+    t = np.clip(t, 0.0, span)
+    endtime = t_start + sign * float(rng.uniform(0.3, 1.0)) * span
+    endtime = t_start + sign * abs(dt) * max(1, round(abs(endtime - t_start) / abs(dt))) if window == 2 else endtime
+    endtime = float(np.clip(endtime, 0.0, span))
+    kernels = [pb.AdvectionRK4_3D, pb.DeleteParticle]
+    full = create_particle_data(nparticles=n, ngrids=1, initial=dict(x=x, y=y, z=z, t=t, particle_id=np.arange(n)))
+    slabs = [D.DecomposedFieldSet(lon=lon, lat=lat, depth=depth, time=times, U=U, V=V, W=W, mesh="spherical", rank=r, world=world,
+                                  halo_cells=3, device=0, time_window=window) for r in range(world)]  # fmt: skip
+    cap = int(rng.choice([4, 50, n + 8]))
+    bases = [s.engine.migrate_p2p_init(cap)[1] for s in slabs]
+    for s in slabs:
+        s.engine.migrate_p2p_connect(local_bases=bases)
+        s.p2p = True
+    what = f"windowed migration world={world} n={n} nt={nt} window={window} dt={dt} inbox={cap}"
+    try:
+        res = thread_ranks.run_ranks(world, lambda r, dist: D.execute_decomposed(slabs[r], D.shard_particles(full, r, world), kernels, dt,
+                                                                                 endtime, dist))  # fmt: skip
+    except RuntimeError as e:
+        if "halo violation" in str(e):
+            return what + " (halo violation: skipped)", None, []
+        raise
+    finally:
+        for s in slabs:
+            s.fs.release()
+    outs = [o for o, _ in res]
+    merged = {k: np.concatenate([o[k] for o in outs], axis=0) for k in outs[0]}
+    order = np.argsort(merged["particle_id"], kind="stable")
+    merged = {k: v[order] for k, v in merged.items()}
+    fs = pb.FieldSet.from_arrays(lon=lon, lat=lat, depth=depth, time=times, U=U, V=V, W=W, mesh="spherical")
+    ps = pb.ParticleSet(fs, x=x, y=y, z=z, t=t)
+    ps.execute(kernels, dt=dt, endtime=endtime)
+    ref = ps._data
+    fs.release()
+    msg = [k for k in ("particle_id", "state", "t", "ei", "x", "y", "z") if not (merged[k].shape == ref[k].shape and np.array_equal(merged[k], ref[k]))]
+    return what + f" rounds={res[0][1]['rounds']}", dict(world=world, n=n, nt=nt, window=window, dt=dt, cap=cap), msg
+
+
 def fuzz_multigrid(rng):
     spec = dict(seed=int(rng.integers(1, 10**6)), kind="smooth", cdtype="f8", ddtype="f4", mesh="spherical", nx=int(rng.integers(8, 20)),
                 ny=int(rng.integers(8, 18)), nz=4, nt=3, tstep=3600.0, n=int(rng.integers(1, 80)), kernels=["AdvectionRK4_3D"], dt=600.0,
@@ -281,7 +346,7 @@ def fuzz_multigrid(rng):
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 50
     rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
-    kinds = (fuzz_curv, fuzz_curv, fuzz_curv_scalar, fuzz_advdiff_cgrid, fuzz_migration, fuzz_multigrid)
+    kinds = (fuzz_curv, fuzz_curv, fuzz_curv_scalar, fuzz_advdiff_cgrid, fuzz_migration, fuzz_multigrid, fuzz_migration_windowed)
     bad = 0
     for k in range(n):
         f = kinds[k % len(kinds)]

@@ -79,7 +79,8 @@ def test_differential_fuzz_of_sampling_rk45_and_advection_diffusion():
 def test_differential_fuzz_of_the_round_two_paths():
     """80 random cases of what round 2 added (scripts/fuzz_hostsim_r2.py): RK4 / Euler behind the curvilinear search (A-grid bilinear
     and C-grid), scalar Field.eval on curvilinear meshes (XLinear and the C-grid tracer rules), AdvectionDiffusionM1 / EM on a C-grid
-    velocity, fields on a second grid inside one kernel list, and the in-kernel migration records of the peer-memory transport."""
+    velocity, fields on a second grid inside one kernel list, the in-kernel migration records of the peer-memory transport, and
+    time-slab streaming under mode D through distributed.execute_decomposed on thread ranks."""
     from oracle.hostsim import build as hb
 
     lib = hb.build()
