@@ -90,6 +90,20 @@ def test_differential_fuzz_of_the_round_two_paths():
     assert res.stdout.strip().endswith("80 cases, 0 with differences"), res.stdout[-3000:]
 
 
+def test_differential_fuzz_of_the_host_layers_bookkeeping():
+    """400 random SEQUENCES of public-API operations on one ParticleSet (execute with random kernel lists and output files, in-place
+    edits, views, removals, additions, a second set on the same FieldSet, the chunked host-array pipeline forced on small sets),
+    mirrored on the oracle and compared after every execute (scripts/fuzz_hostsim_api.py): which copy of the set is current --
+    host arrays, device arrays, a lazily resident set -- never goes wrong."""
+    from oracle.hostsim import build as hb
+
+    lib = hb.build()
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "fuzz_hostsim_api.py"), "400", "2026"], cwd=ROOT, env=_env(lib),
+                         capture_output=True, text=True, timeout=900)  # fmt: skip
+    assert res.returncode == 0, res.stderr[-2000:]
+    assert res.stdout.strip().endswith("400 cases, 0 with differences"), res.stdout[-3000:]
+
+
 def test_domain_decomposed_migration_on_the_host_compiled_kernels():
     """Mode D (X-slab decomposition, classify / pack / compact / unpack kernels, gloo all-to-all of the 48-byte records): 2 ranks,
     each with its own simulated engine, reproduce the single-engine trajectories bit for bit (scripts/decomposed_check.py)."""
