@@ -2,7 +2,8 @@
 a lazily resident set -- across execute() calls, edits, removals and additions): random SEQUENCES of public-API operations on one
 ParticleSet, mirrored on the oracle's particle dict, compared after every execute().  Rectilinear flat A-grids, where the kernels are
 bit-exact, so any difference is the bookkeeping's.
-  ops: execute (random kernel list, runtime, with or without an output file between the intervals), in-place edits through the
+  ops: execute (random kernel list, runtime, with or without an output file between the intervals; also WITHOUT the DeleteParticle
+       handler: same exception, same states, the set usable afterwards), in-place edits through the
        arrays the attributes return, `pset[i].x = ...` / `pset[mask].y = ...` views, `pset.z = ...`, remove_indices, add(),
        plain reads (len, attribute access), a second ParticleSet on the same FieldSet executing in between.
 Run:  PB_LIB=oracle/_build/hostsim/libparcels_b200_hostsim.so PB_HOSTSIM_TEST=1 python scripts/fuzz_hostsim_api.py [n] [seed]"""
@@ -18,6 +19,8 @@ from oracle import parcels_oracle as po
 from oracle_run import oracle_fieldset
 
 warnings.simplefilter("ignore")
+ERR_NAME = {60: "FieldOutOfBoundError", 61: "FieldOutOfBoundSurfaceError", 70: "OutsideTimeInterval", 51: "FieldInterpolationError",
+            52: "GridSearchingError", 50: "GeneralError"}
 VERBOSE = os.environ.get("FUZZ_VERBOSE") == "1"
 KEYS = ("particle_id", "state", "t", "ei", "x", "y", "z", "dx", "dy", "dz", "dt")
 
@@ -84,7 +87,7 @@ def one_case(rng):
     names3 = ["AdvectionRK4_3D", "AdvectionRK2_3D"] + names2
     log, msg = [], []
     for step in range(int(rng.integers(3, 9))):
-        op = str(rng.choice(["exec", "exec", "exec", "edit", "view", "setattr", "remove", "add", "read", "other"]))
+        op = str(rng.choice(["exec", "exec", "exec", "exec_raise", "edit", "view", "setattr", "remove", "add", "read", "other"]))
         n = len(pd["x"])
         if n == 0:
             break
@@ -108,6 +111,37 @@ def one_case(rng):
                 msg.append(f"step {step}: output rows differ ({[(t, len(c_['x'])) for t, c_ in rec.rows]} vs {[(t, len(c_['x'])) for t, c_ in orows]})")
             if rng.random() < 0.5:  # sometimes look right away, sometimes leave the set where it is (lazy residency)
                 msg += compare(ps, pd, f"step {step} ({log[-1]})")
+        elif op == "exec_raise":
+            # no DeleteParticle handler: a particle that leaves the domain stops the whole set at the end of that iteration with the
+            # reference's exception (kernel.py:239-245) -- the engine replays up to that iteration; the set must be usable afterwards
+            name = str(rng.choice(names3 if three else names2))
+            nsteps = int(rng.integers(1, 6))
+            if float(np.nanmax(pd["t"])) + nsteps * dt > t_end:
+                continue
+            err, oerr = "", None
+            try:
+                ps.execute([getattr(pb, name)], dt=dt, runtime=nsteps * dt)
+            except RuntimeError as e:
+                if type(e).__module__.startswith("parcels_b200._lib"):
+                    raise
+                err = type(e).__name__
+            try:
+                po.pset_execute(pd, ofs, [getattr(po, name)], dt, runtime=nsteps * dt)
+            except po.OracleParticleError as e:
+                oerr = e.code
+            log.append(f"exec {name} x{nsteps} without handler -> {err or 'no error'}")
+            if err != (ERR_NAME.get(oerr, str(oerr)) if oerr else ""):
+                msg.append(f"step {step}: raised {err!r} vs oracle {oerr}")
+            msg += compare(ps, pd, f"step {step} ({log[-1]})")
+            if err:  # what a user does next: drop the particles in an error state, carry on
+                bad_rows = np.where(pd["state"] >= 50)[0]
+                if len(bad_rows) == 0 or len(bad_rows) >= len(pd["x"]):
+                    break
+                if not np.array_equal(np.where(ps.state >= 50)[0], bad_rows):
+                    msg.append(f"step {step}: error rows")
+                ps.remove_indices(bad_rows)
+                for k in pd:
+                    pd[k] = np.delete(pd[k], bad_rows, axis=0)
         elif op == "edit":
             idx = rng.integers(0, n, int(rng.integers(1, 4)))
             key = str(rng.choice(["x", "y", "z"] if three else ["x", "y"]))
