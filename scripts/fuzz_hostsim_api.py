@@ -3,7 +3,8 @@ a lazily resident set -- across execute() calls, edits, removals and additions):
 ParticleSet, mirrored on the oracle's particle dict, compared after every execute().  Rectilinear flat A-grids, where the kernels are
 bit-exact, so any difference is the bookkeeping's.
   ops: execute (random kernel list, runtime, with or without an output file between the intervals; also WITHOUT the DeleteParticle
-       handler: same exception, same states, the set usable afterwards), in-place edits through the
+       handler: same exception, same states, the set usable afterwards; and with a user Python kernel + error handler in the list:
+       loop control on the host), in-place edits through the
        arrays the attributes return, `pset[i].x = ...` / `pset[mask].y = ...` views, `pset.z = ...`, remove_indices, add(),
        plain reads (len, attribute access), a second ParticleSet on the same FieldSet executing in between.
 Run:  PB_LIB=oracle/_build/hostsim/libparcels_b200_hostsim.so PB_HOSTSIM_TEST=1 python scripts/fuzz_hostsim_api.py [n] [seed]"""
@@ -87,7 +88,7 @@ def one_case(rng):
     names3 = ["AdvectionRK4_3D", "AdvectionRK2_3D"] + names2
     log, msg = [], []
     for step in range(int(rng.integers(3, 9))):
-        op = str(rng.choice(["exec", "exec", "exec", "exec_raise", "edit", "view", "setattr", "remove", "add", "read", "other"]))
+        op = str(rng.choice(["exec", "exec", "exec", "exec_raise", "exec_mixed", "edit", "view", "setattr", "remove", "add", "read", "other"]))
         n = len(pd["x"])
         if n == 0:
             break
@@ -110,6 +111,28 @@ def one_case(rng):
             if kw and not same_rows(rec.rows, orows):
                 msg.append(f"step {step}: output rows differ ({[(t, len(c_['x'])) for t, c_ in rec.rows]} vs {[(t, len(c_['x'])) for t, c_ in orows]})")
             if rng.random() < 0.5:  # sometimes look right away, sometimes leave the set where it is (lazy residency)
+                msg += compare(ps, pd, f"step {step} ({log[-1]})")
+        elif op == "exec_mixed":
+            # a user Python kernel and a user error handler in the list: loop control on the host, the built-in on the device
+            name = str(rng.choice(names3 if three else names2))
+            nsteps = int(rng.integers(1, 5))
+            if float(np.nanmax(pd["t"])) + nsteps * dt > t_end:
+                continue
+            drift = float(rng.choice([0.0, 0.01, 0.25])) * float(spec["umax"])
+
+            def Drift(particles, fieldset):
+                particles.dy += drift * particles.dt
+
+            def DeleteErr(particles, fieldset):
+                particles[particles.state >= 50].state = 30
+
+            def ODrift(p, fs_):
+                p.dy = p.dy + drift * p.dt
+
+            log.append(f"exec [{name}, Drift({drift}), DeleteErr] x{nsteps}")
+            ps.execute([getattr(pb, name), Drift, DeleteErr], dt=dt, runtime=nsteps * dt)
+            po.pset_execute(pd, ofs, [getattr(po, name), ODrift, po.DeleteOnError], dt, runtime=nsteps * dt)
+            if rng.random() < 0.5:
                 msg += compare(ps, pd, f"step {step} ({log[-1]})")
         elif op == "exec_raise":
             # no DeleteParticle handler: a particle that leaves the domain stops the whole set at the end of that iteration with the
