@@ -68,12 +68,19 @@ def one_case(rng):
     if nt > 1:
         spec["release"] = ("const", 0.0)
     c = cases.build(spec)
-    fs = make_fieldset(c)
+    # time-slab streaming in a quarter of the cases with a time axis: 2 or 3 of the levels resident, slid as the set's clock advances
+    # across the calls of the sequence (lists need the DeleteParticle handler there: the other executes are skipped)
+    window = int(rng.choice([2, 3])) if (nt == 4 and rng.random() < 0.4) else None
+    if window:
+        fs = pb.FieldSet.from_arrays(lon=c["lon"], lat=c["lat"], depth=c["depth"], time=c["times"], U=c["U"], V=c["V"], W=c["W"],
+                                     mesh=c["mesh"], time_window=window)  # fmt: skip
+    else:
+        fs = make_fieldset(c)
     ofs = oracle_fieldset(c)
     ps = pb.ParticleSet(fs, x=c["x"], y=c["y"], z=c["z"], t=c["t"])
     # the paths large sets take -- chunked host-array pipeline (pb_advect_host), deferred `particles.dt` fill, compacted download
     # after deletions -- at these sizes: lower the set's threshold in half of the cases
-    knobs = ""
+    knobs = f"[time_window {window}] " if window else ""
     if rng.random() < 0.5:
         ps.PIPELINE_MIN_PARTICLES = int(rng.choice([1, 4, 16]))
         ps.pipeline_chunks = int(rng.choice([2, 3, 8]))
@@ -92,6 +99,8 @@ def one_case(rng):
         n = len(pd["x"])
         if n == 0:
             break
+        if window and op in ("exec_raise", "exec_mixed"):
+            continue
         if op == "exec":
             name = str(rng.choice(names3 if three else names2))
             nsteps = int(rng.integers(1, 6))
