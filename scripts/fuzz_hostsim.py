@@ -78,6 +78,36 @@ def random_spec(rng):
     return spec
 
 
+def inject_boundary_cases(rng, spec, c):
+    """Releases on nodes / domain edges / depth levels, non-finite coordinates, releases just outside the time interval, repeated
+    releases on the first time level (in place, on the case dict ``c``)."""
+    n = len(c["x"])
+    if spec["kind"] == "smooth" and rng.random() < 0.4 and n >= 4:
+        # boundary cases: releases exactly on nodes, on the domain edges, on depth levels; a few non-finite coordinates
+        lon, lat = np.asarray(c["lon"], dtype=np.float64), np.asarray(c["lat"], dtype=np.float64)
+        pick = rng.integers(0, n, 4)
+        c["x"][pick[0]], c["y"][pick[0]] = lon[rng.integers(0, len(lon))], lat[rng.integers(0, len(lat))]
+        c["x"][pick[1]] = lon[[0, -1][rng.integers(0, 2)]]
+        c["y"][pick[2]] = lat[[0, -1][rng.integers(0, 2)]]
+        if c["depth"] is not None:
+            c["z"][pick[3]] = np.asarray(c["depth"], dtype=np.float64)[rng.integers(0, len(c["depth"]))]
+        if rng.random() < 0.3:
+            c[str(rng.choice(list("xyz")))][rng.integers(0, n)] = rng.choice([np.nan, np.inf, -np.inf])
+    if spec["kind"] == "smooth" and spec["nt"] > 1 and rng.random() < 0.3:
+        # a few releases just outside the fields' time interval: their first sample raises OutsideTimeInterval, which flags
+        # (with DeleteParticle: deletes) the reference's WHOLE evaluated view of that iteration (field.py:31-44)
+        runtime0 = spec["segments"][0]["runtime"]
+        delta = float(rng.uniform(0.05, 0.95)) * min(runtime0, 2 * abs(spec["dt"]))
+        pick = rng.integers(0, n, int(rng.integers(1, 3)))
+        c["t"] = np.asarray(c["t"], dtype=np.float64).copy()
+        c["t"][pick] = -delta if spec["dt"] > 0 else spec["tstep"] * (spec["nt"] - 1) + delta
+    elif spec["kind"] == "smooth" and spec["nt"] > 1 and spec["dt"] > 0 and rng.random() < 0.3:
+        # repeated release: some particles exactly on the first time level (tau == 0), the others later -- the reference's
+        # batch-level lenT then promotes the first-level particles' first sample (float32 grids)
+        later = float(rng.choice([0.5, 1.0, 2.0])) * spec["dt"]
+        c["t"] = np.where(rng.random(n) < 0.5, 0.0, later)
+
+
 def main():
     argv = [a for a in sys.argv[1:] if not a.startswith("--")]
     n_cases = int(argv[0]) if argv else 100
@@ -87,31 +117,7 @@ def main():
         spec = random_spec(rng)
         try:
             c = cases.build(spec)
-            n = len(c["x"])
-            if spec["kind"] == "smooth" and rng.random() < 0.4 and n >= 4:
-                # boundary cases: releases exactly on nodes, on the domain edges, on depth levels; a few non-finite coordinates
-                lon, lat = np.asarray(c["lon"], dtype=np.float64), np.asarray(c["lat"], dtype=np.float64)
-                pick = rng.integers(0, n, 4)
-                c["x"][pick[0]], c["y"][pick[0]] = lon[rng.integers(0, len(lon))], lat[rng.integers(0, len(lat))]
-                c["x"][pick[1]] = lon[[0, -1][rng.integers(0, 2)]]
-                c["y"][pick[2]] = lat[[0, -1][rng.integers(0, 2)]]
-                if c["depth"] is not None:
-                    c["z"][pick[3]] = np.asarray(c["depth"], dtype=np.float64)[rng.integers(0, len(c["depth"]))]
-                if rng.random() < 0.3:
-                    c[str(rng.choice(list("xyz")))][rng.integers(0, n)] = rng.choice([np.nan, np.inf, -np.inf])
-            if spec["kind"] == "smooth" and spec["nt"] > 1 and rng.random() < 0.3:
-                # a few releases just outside the fields' time interval: their first sample raises OutsideTimeInterval, which flags
-                # (with DeleteParticle: deletes) the reference's WHOLE evaluated view of that iteration (field.py:31-44)
-                runtime0 = spec["segments"][0]["runtime"]
-                delta = float(rng.uniform(0.05, 0.95)) * min(runtime0, 2 * abs(spec["dt"]))
-                pick = rng.integers(0, n, int(rng.integers(1, 3)))
-                c["t"] = np.asarray(c["t"], dtype=np.float64).copy()
-                c["t"][pick] = -delta if spec["dt"] > 0 else spec["tstep"] * (spec["nt"] - 1) + delta
-            elif spec["kind"] == "smooth" and spec["nt"] > 1 and spec["dt"] > 0 and rng.random() < 0.3:
-                # repeated release: some particles exactly on the first time level (tau == 0), the others later -- the reference's
-                # batch-level lenT then promotes the first-level particles' first sample (float32 grids)
-                later = float(rng.choice([0.5, 1.0, 2.0])) * spec["dt"]
-                c["t"] = np.where(rng.random(n) < 0.5, 0.0, later)
+            inject_boundary_cases(rng, spec, c)
             ps, err = run_engine(c)
             pd, oerr = run_oracle(c)
         except Exception as e:  # noqa: BLE001
