@@ -3,7 +3,8 @@
 ``Kernel.execute`` so that the inner loop runs on the engine (here: the host simulation of the kernel sources) -- and the two
 ``pset._data`` compared: ids / states / times / cells / dt identical, positions bit-exact on flat meshes and within 4 float32 ulp on
 spherical ones (the tolerances of scripts/fuzz_hostsim.py), the same exception class when there is no error handler.  Every fifth
-case is AdvectionRK45 (per-particle dt / next_dt and the Repeat loop; alone or followed by a user kernel).
+case is AdvectionRK45 (per-particle dt / next_dt and the Repeat loop; alone or followed by a user kernel), every fifth a batch of
+single evaluations: the reference's `Field.eval` (four scalar interpolators) and `VectorField.eval` against the device sampling.
 Needs /root/reference (the build container).
 Run:  PB_LIB=oracle/_build/hostsim/libparcels_b200_hostsim.so PB_HOSTSIM_TEST=1 python scripts/fuzz_install_vs_reference.py [n] [seed]"""
 import os, sys
@@ -107,6 +108,71 @@ def rk45_case(rng):
     return spec, msg, b
 
 
+def eval_case(rng):
+    """Single evaluations: `fieldset.P.eval(t, z, y, x, particles)` (XLinear / XNearest / CGrid_Tracer / XLinearInvdistLandTracer) and
+    `fieldset.UVW.eval(...)` of the reference against the engine's device sampling: values, dtypes, `ei`, states."""
+    from engine_run import make_fieldset
+    from fuzz_hostsim_more import base_case
+
+    spec, c = base_case(rng, two_d=False, interps=("linear", "cgrid_velocity", "freeslip", "partialslip"))
+    T = c["U"].shape[0] if rng.random() < 0.6 else 1
+    P = (1.0 + rng.uniform(0, 1, (T,) + c["U"].shape[1:])).astype(rng.choice([np.float32, np.float64]))
+    P[rng.uniform(size=P.shape) < 0.15] = 0  # land
+    how = str(rng.choice(["linear", "nearest", "cgrid_tracer", "linear_invdist_land"]))
+    n = len(c["x"])
+    if n == 1 and how == "linear_invdist_land":
+        how = "linear"  # (a batch of ONE sample: DESIGN.md waiver 1)
+    tmax = 0.0 if c["times"] is None else float(c["times"][-1])
+    tq = rng.uniform(0, tmax, n) if tmax else np.zeros(n)
+    f32 = bool(rng.random() < 0.5)
+    dt_ = np.float32 if f32 else np.float64
+    x, y, z = (np.asarray(c[k]).astype(dt_) for k in "xyz")
+    # reference
+    rfs = rh.build_fieldset(lon=c["lon"], lat=c["lat"], depth=c["depth"], times=c["times"], U=c["U"], V=c["V"], W=c["W"], mesh=c["mesh"],
+                            interp=c.get("interp", "linear"), padding=c.get("padding", ("low", "low", "high")), scalars={"P": (P, how)})  # fmt: skip
+    rps = rh.make_pset(rfs, x=c["x"], y=c["y"], z=c["z"], t=c["t"])
+    rval = np.asarray(rfs.P.eval(tq, z, y, x, rps))
+    r_ei, r_state = rps._data["ei"].copy(), rps._data["state"].copy()
+    rps2 = rh.make_pset(rfs, x=c["x"], y=c["y"], z=c["z"], t=c["t"])
+    ruvw = [np.asarray(a) for a in rfs.UVW.eval(tq, z, y, x, rps2)]
+    # engine
+    fs = make_fieldset(c)
+    fs.add_field("P", P, interp_method=how)
+    ps = pb.ParticleSet(fs, x=c["x"], y=c["y"], z=c["z"], t=c["t"])
+    val = np.asarray(fs.P.eval(tq, z, y, x, ps))
+    ps2 = pb.ParticleSet(fs, x=c["x"], y=c["y"], z=c["z"], t=c["t"])
+    uvw = [np.asarray(a) for a in fs.UVW.eval(tq, z, y, x, ps2)]
+    msg = []
+    if val.dtype != rval.dtype and not (T > 1):
+        msg.append(f"P dtype {val.dtype} vs {rval.dtype}")
+    if not np.array_equal(ps._data["ei"], r_ei):
+        msg.append("P ei")
+    if not np.array_equal(ps._data["state"], r_state):
+        msg.append("P state")
+    same = (val.astype(np.float64) == rval.astype(np.float64)) | (np.isnan(val) & np.isnan(rval))
+    if not same.all():
+        bad = np.flatnonzero(~same)
+        msg.append(f"P at {bad[:4]}: {val[bad[:4]]} vs {rval[bad[:4]]}")
+    if not np.array_equal(ps2._data["ei"], rps2._data["ei"]) or not np.array_equal(ps2._data["state"], rps2._data["state"]):
+        msg.append("UVW ei / state")
+    for name, g, w in zip("uvw", uvw, ruvw):
+        scale = float(np.abs(w[np.isfinite(w)]).max()) if np.isfinite(w).any() else 0.0
+        if c["mesh"] == "spherical":  # (the tolerances of tests/test_gpu_eval.py)
+            tol = 4 * np.finfo(np.float32).eps if (f32 or w.dtype == np.float32) else 64 * np.finfo(np.float64).eps
+            if c.get("interp") == "cgrid_velocity" and spec["cdtype"] == "f4":
+                tol = 64 * np.finfo(np.float32).eps  # float32 edge lengths with a float32 cos (the trajectory rule above)
+        elif c.get("interp") == "cgrid_velocity":
+            tol = 32 * np.finfo(np.float64).eps if w.dtype == np.float64 and not f32 else 4 * np.finfo(np.float32).eps
+        else:
+            tol = 0.0
+        err = np.abs(g.astype(np.float64) - w.astype(np.float64))
+        err = np.where(np.isnan(w) & np.isnan(g), 0.0, err)
+        if err.size and float(np.nanmax(err)) > tol * scale:
+            msg.append(f"{name}: {float(np.nanmax(err)) / max(scale, 1e-300):.2e} x scale (tol {tol:.1e})")
+    spec = dict(spec, eval=dict(how=how, T=T, f32=f32, P=str(P.dtype)))
+    return spec, msg
+
+
 def main():
     n_cases = int(sys.argv[1]) if len(sys.argv) > 1 else 40
     rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
@@ -126,6 +192,21 @@ def main():
             if msg:
                 bad += 1
                 print(f"[{k}] MISMATCH (AdvectionRK45) {'; '.join(msg)}\n    spec={spec}")
+            continue
+        if k % 5 == 2:
+            try:
+                spec, msg = eval_case(rng)
+            except Exception as e:  # noqa: BLE001
+                import traceback
+
+                print(f"[{k}] EXC {type(e).__name__}: {e}")
+                traceback.print_exc()
+                bad += 1
+                continue
+            on_engine += 1
+            if msg:
+                bad += 1
+                print(f"[{k}] MISMATCH (eval) {'; '.join(msg)}\n    spec={spec}")
             continue
         spec = random_spec(rng)
         token = bool(rng.random() < 0.6)
