@@ -210,6 +210,8 @@ def main():
                 print(f"[{k}] MISMATCH (eval) {'; '.join(msg)}\n    spec={spec}")
             continue
         spec = random_curv_spec(rng) if k % 7 == 3 else random_spec(rng)
+        if spec["kind"] == "curv" and rng.random() < 0.4:
+            spec["interp"] = "linear"  # XLinear_Velocity behind the curvilinear search (A-grid data on a curvilinear mesh)
         token = bool(rng.random() < 0.6)
         try:
             c = cases.build(spec)
