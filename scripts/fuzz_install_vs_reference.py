@@ -5,7 +5,8 @@
 spherical ones (the tolerances of scripts/fuzz_hostsim.py), the same exception class when there is no error handler.  Every fifth
 case is AdvectionRK45 (per-particle dt / next_dt and the Repeat loop; alone or followed by a user kernel), every fifth a batch of
 single evaluations: the reference's `Field.eval` (four scalar interpolators) and `VectorField.eval` against the device sampling; every
-seventh a random CURVILINEAR C-grid mesh (cells / states / times identical, positions asserted on spherical meshes).
+seventh a random CURVILINEAR C-grid mesh (cells / states / times identical, positions asserted on spherical meshes), every fifth a
+random SEQUENCE of operations on the reference's own ParticleSet (executes, edits, views, remove_indices, add) with and without the patch.
 Needs /root/reference (the build container).
 Run:  PB_LIB=oracle/_build/hostsim/libparcels_b200_hostsim.so PB_HOSTSIM_TEST=1 python scripts/fuzz_install_vs_reference.py [n] [seed]"""
 import os, sys
@@ -174,6 +175,94 @@ def eval_case(rng):
     return spec, msg
 
 
+def sequence_case(rng):
+    """A random SEQUENCE of operations on the reference's own ParticleSet -- executes (built-ins with the user error handler or the
+    engine's token, several kernels), in-place edits of `pset._data`, `pset[i]` / `pset[mask]` view assignments, `remove_indices`,
+    `add` -- applied to an untouched set and to one whose Kernel.execute is patched: the adapter shares the reference's arrays, so
+    every mutation between the calls (np.delete and np.concatenate REPLACE the columns) has to be picked up."""
+    from fuzz_hostsim_more import base_case
+
+    three = bool(rng.random() < 0.5)
+    spec, c = base_case(rng, two_d=not three, interps=("linear", "freeslip", "cgrid_velocity"))
+    if spec["mesh"] != "flat":  # bit-exact comparison: flat meshes
+        spec["mesh"] = "flat"
+        c = cases.build(spec)
+        if not three:
+            c["W"] = None
+            c["z"] = np.abs(np.asarray(c["z"]))
+    dt = float(rng.choice([50.0, 100.0]))
+    tmax = np.inf if c["times"] is None else float(c["times"][-1])
+    names = ["AdvectionRK4_3D", "AdvectionRK2_3D"] if three else ["AdvectionRK4", "AdvectionRK2", "AdvectionEE"]
+    sets = []
+    for patched in (False, True):
+        fs = rh.build_fieldset(lon=c["lon"], lat=c["lat"], depth=c["depth"], times=c["times"], U=c["U"], V=c["V"], W=c["W"], mesh=c["mesh"],
+                               interp=c.get("interp", "linear"), padding=c.get("padding", ("low", "low", "high")))  # fmt: skip
+        sets.append((fs, rh.make_pset(fs, x=c["x"], y=c["y"], z=c["z"], t=np.zeros(len(c["x"])))))
+    log, msg = [], []
+    t_now = 0.0
+    for step in range(int(rng.integers(3, 8))):
+        n = len(sets[0][1]._data["x"])
+        if n == 0:
+            break
+        op = str(rng.choice(["exec", "exec", "exec", "edit", "view", "remove", "add"]))
+        if op == "exec":
+            name = str(rng.choice(names))
+            nsteps = int(rng.integers(1, 5))
+            if t_now + nsteps * dt > tmax:
+                continue
+            token = bool(rng.random() < 0.5)
+            errs = []
+            for patched, (fs, ps) in zip((False, True), sets):
+                (pb.install if patched else pb.uninstall)()
+                try:
+                    ps.execute([getattr(K, name), pb.DeleteParticle if (patched and token) else user_delete], dt=np.timedelta64(int(dt), "s"),
+                               runtime=np.timedelta64(int(nsteps * dt), "s"), verbose_progress=False)  # fmt: skip
+                    errs.append("")
+                except Exception as e:  # noqa: BLE001
+                    errs.append(type(e).__name__)
+                finally:
+                    pb.uninstall()
+            t_now += nsteps * dt
+            log.append(f"exec {name} x{nsteps} token={token}")
+            if errs[0] != errs[1]:
+                msg.append(f"step {step}: raised {errs}")
+            da, db = sets[0][1]._data, sets[1][1]._data
+            if set(da) != set(db) or len(da["x"]) != len(db["x"]):
+                msg.append(f"step {step}: {len(db['x'])} particles vs {len(da['x'])}")
+            else:
+                msg += [f"step {step} ({log[-1]}): {k}" for k in da if not np.array_equal(da[k], db[k], equal_nan=True)]
+        elif op == "edit":
+            idx = rng.integers(0, n, int(rng.integers(1, 4)))
+            delta = np.float32(rng.uniform(-0.01, 0.01) * float(np.abs(np.asarray(c["lon"])).max()))
+            log.append(f"edit x[{idx.tolist()}]")
+            for _, ps in sets:
+                ps._data["x"][idx] += delta
+        elif op == "view":
+            i = int(rng.integers(0, n))
+            mask = rng.random(n) < 0.3
+            log.append(f"views [{i}], mask {int(mask.sum())}")
+            for _, ps in sets:
+                ps[i].y = ps[i].y * np.float32(0.999)
+                v = ps[mask]
+                v.x = v.x * np.float32(0.9995)
+        elif op == "remove":
+            idx = np.unique(rng.integers(0, n, int(rng.integers(1, 3))))
+            if len(idx) >= n:
+                continue
+            log.append(f"remove {idx.tolist()}")
+            for _, ps in sets:
+                ps.remove_indices(idx)
+        elif op == "add":
+            m = int(rng.integers(1, 4))
+            j = rng.integers(0, len(c["x"]), m)
+            log.append(f"add {m}")
+            for fs, ps in sets:
+                ps.add(rh.make_pset(fs, x=np.asarray(c["x"])[j], y=np.asarray(c["y"])[j], z=np.asarray(c["z"])[j], t=np.full(m, t_now)))
+        if msg:
+            break
+    return dict(spec, sequence=" | ".join(log)), msg
+
+
 def main():
     n_cases = int(sys.argv[1]) if len(sys.argv) > 1 else 40
     rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
@@ -194,9 +283,9 @@ def main():
                 bad += 1
                 print(f"[{k}] MISMATCH (AdvectionRK45) {'; '.join(msg)}\n    spec={spec}")
             continue
-        if k % 5 == 2:
+        if k % 5 in (0, 2):
             try:
-                spec, msg = eval_case(rng)
+                spec, msg = eval_case(rng) if k % 5 == 2 else sequence_case(rng)
             except Exception as e:  # noqa: BLE001
                 import traceback
 
@@ -207,7 +296,7 @@ def main():
             on_engine += 1
             if msg:
                 bad += 1
-                print(f"[{k}] MISMATCH (eval) {'; '.join(msg)}\n    spec={spec}")
+                print(f"[{k}] MISMATCH ({'eval' if k % 5 == 2 else 'sequence'}) {'; '.join(msg)}\n    spec={spec}")
             continue
         spec = random_curv_spec(rng) if k % 7 == 3 else random_spec(rng)
         if spec["kind"] == "curv" and rng.random() < 0.4:
