@@ -163,6 +163,8 @@ def eval_case(rng):
             tol = 4 * np.finfo(np.float32).eps if (f32 or w.dtype == np.float32) else 64 * np.finfo(np.float64).eps
             if c.get("interp") == "cgrid_velocity" and spec["cdtype"] == "f4":
                 tol = 64 * np.finfo(np.float32).eps  # float32 edge lengths with a float32 cos (the trajectory rule above)
+            elif c.get("interp") == "cgrid_velocity" and tol < 1e-10:
+                tol = 1024 * np.finfo(np.float64).eps  # Jacobian cancellation on top of the einsum / cos last bits (waivers 8, 9)
         elif c.get("interp") == "cgrid_velocity":
             tol = 32 * np.finfo(np.float64).eps if w.dtype == np.float64 and not f32 else 4 * np.finfo(np.float32).eps
         else:
