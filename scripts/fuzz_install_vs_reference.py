@@ -173,6 +173,28 @@ def eval_case(rng):
         err = np.where(np.isnan(w) & np.isnan(g), 0.0, err)
         if err.size and float(np.nanmax(err)) > tol * scale:
             msg.append(f"{name}: {float(np.nanmax(err)) / max(scale, 1e-300):.2e} x scale (tol {tol:.1e})")
+    # ParticleSet.populate_indices (reference _core/particleset.py:252-262): the hintless search of every particle, also on a random
+    # curvilinear mesh (spatial hash)
+    rps3 = rh.make_pset(rfs, x=c["x"], y=c["y"], z=c["z"], t=c["t"])
+    rps3.populate_indices()
+    ps3 = pb.ParticleSet(fs, x=c["x"], y=c["y"], z=c["z"], t=c["t"])
+    ps3.populate_indices()
+    if not np.array_equal(ps3._data["ei"], rps3._data["ei"]):
+        msg.append("populate_indices")
+    cspec = random_curv_spec(rng)
+    cc = cases.build(cspec)
+    cfs = rh.build_fieldset(lon=cc["lon"], lat=cc["lat"], depth=cc["depth"], times=cc["times"], U=cc["U"], V=cc["V"], W=cc["W"],
+                            mesh=cc["mesh"], interp="cgrid_velocity", padding=cc.get("padding", ("low", "low", "high")))  # fmt: skip
+    rps4 = rh.make_pset(cfs, x=cc["x"], y=cc["y"], z=cc["z"], t=cc["t"])
+    rps4.populate_indices()
+    efs = make_fieldset(cc)
+    ps4 = pb.ParticleSet(efs, x=cc["x"], y=cc["y"], z=cc["z"], t=cc["t"])
+    ps4.populate_indices()
+    if not np.array_equal(ps4._data["ei"], rps4._data["ei"]):
+        bad_ = np.flatnonzero((ps4._data["ei"] != rps4._data["ei"]).any(axis=1))
+        msg.append(f"populate_indices (curvilinear {cspec['mesh']} {cspec['cdtype']}): {len(bad_)} of {len(cc['x'])} cells differ")
+    efs.release()
+    fs.release()
     spec = dict(spec, eval=dict(how=how, T=T, f32=f32, P=str(P.dtype)))
     return spec, msg
 
