@@ -855,7 +855,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-mode-d", action="store_true", help="N > 1: skip the domain-decomposed block")
     ap.add_argument("--mode-d-timeout", type=float, default=0.0, help="N > 1: seconds the domain-decomposed block may take before the "
-                    "mode R line is printed without it (default: max(600, 3 x the time the mode R part took))")
+                    "mode R line is printed without it (default: max(900, 3 x the time the mode R part took))")
     ap.add_argument("--mode-d-transport", default="p2p", choices=["p2p", "collective"],
                     help="mode D: p2p = in-kernel migration over peer memory (CUDA IPC + NVLink), collective = NCCL all-to-all-v")
     ap.add_argument("--pipeline", type=int, default=-1,
@@ -947,7 +947,7 @@ def main():
         # hangs would leave the others inside a collective for good, so a watchdog bounds the block: past the limit rank 0 prints
         # the mode R line with the reason and every rank leaves (the limit is generous: the block normally takes well under a
         # minute, and scales with what the mode R part -- full-field generation included -- took on this box).
-        limit = a.mode_d_timeout or max(600.0, 3.0 * (time.perf_counter() - t_main))
+        limit = a.mode_d_timeout or max(900.0, 3.0 * (time.perf_counter() - t_main))
         watchdog = threading.Timer(limit, _leave_mode_d, args=(line, limit))
         watchdog.daemon = True
         watchdog.start()
