@@ -104,6 +104,27 @@ def fuzz_curv(rng):
         ps.execute([getattr(pb, kern), pb.DeleteParticle], dt=dt, runtime=s)
         po.pset_execute(pd, ofs, [getattr(po, kern), po.DeleteOnError], dt, runtime=s)
     what = f"curv {spec['interp']} {kern} {spec['mesh']} {spec['cdtype']} dt={dt} segs={segs} fresh={fresh}"
+    if rng.random() < 0.3 and c["U"].shape[0] >= 3:
+        # the same run with only 2 of the time levels resident (time-slab streaming behind the curvilinear search): bit-identical to
+        # the resident engine run.  Steps that straddle a level sample three levels: such windows are refused, not wrong.
+        wfs = pb.FieldSet.from_arrays(lon=c["lon"], lat=c["lat"], depth=c["depth"], time=c["times"], U=c["U"], V=c["V"], W=c["W"],
+                                      mesh=c["mesh"], interp_method=c.get("interp", "cgrid_velocity"),
+                                      padding=c.get("padding", ("low", "low", "high")), time_window=2)  # fmt: skip
+        wps = pb.ParticleSet(wfs, x=c["x"], y=c["y"], z=c["z"], t=c["t"])
+        if not fresh:
+            wps.populate_indices()
+        try:
+            for s in segs:
+                wps.execute([getattr(pb, kern), pb.DeleteParticle], dt=dt, runtime=s)
+        except RuntimeError as e:
+            if "cannot cover one step" not in str(e):
+                raise
+        else:
+            what += " +window"
+            diff = [k for k in ("particle_id", "state", "t", "ei", "x", "y", "z") if not np.array_equal(wps._data[k], ps._data[k])]
+            if diff:
+                return what, spec, [f"time-windowed run differs from the resident one: {diff}"]
+        wfs.release()
     if fresh:  # ids / states / times exact; positions within 1e-4 of a cell (the float32-typed first evaluation, grown over the run)
         d = ps._data
         if len(d["x"]) != len(pd["x"]):
