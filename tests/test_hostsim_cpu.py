@@ -176,13 +176,17 @@ def test_time_slab_streaming_under_domain_decomposition():
 
 
 def test_peer_memory_round_loop_on_thread_ranks():
-    """distributed.run_decomposed_p2p itself (not a hand-driven copy of its rounds): 3 thread ranks, resident fields."""
+    """distributed.run_decomposed_p2p itself (not a hand-driven copy of its rounds): 3 and 8 thread ranks, resident fields."""
     from oracle.hostsim import build as hb
 
     lib = hb.build()
     r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "decomposed_threads_check.py")], capture_output=True, text=True,
                        timeout=900, cwd=ROOT, env=_env(lib))  # fmt: skip
     assert r.returncode == 0 and "PASS bit-exact" in r.stdout and "peer memory" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+    # the slab count of the driver's largest run (8), with an inbox that overflows: leavers wait for later rounds, some cross several slabs
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "decomposed_threads_check.py"), "--world", "8", "--particles", "6000",
+                        "--inbox", "64"], capture_output=True, text=True, timeout=900, cwd=ROOT, env=_env(lib))  # fmt: skip
+    assert r.returncode == 0 and "PASS bit-exact" in r.stdout and "8 thread ranks" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
 
 def test_nan_node_on_the_device_side_hash_build_and_query():
